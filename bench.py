@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- views/sec forward+backward of the rasterizer hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE config 3 -- synthetic 1M Gaussians, 1920x1080, SH degree 3,
+seed-0 generator of SURVEY.md section 8d.  A *step* is one forward + backward of one view per GPU
+(weak scaling: rank k renders the k-th yawed camera of the batch) followed, when N > 1, by the
+path's single collective: one NCCL all-reduce over the flat gradient buffer.
+
+Printed JSON line (rank 0):
+  value        views/s over all ranks, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e          the same metric through the public operator (GaussianRasterizer + autograd), with the
+               per-step host inputs of a training step (camera matrices + ground-truth image, pinned
+               host memory -> device) and the loss read back (device -> host) inside the timed region
+  roofline     dominant kernel: algorithmic bytes / its CUDA-event duration
+  kernels      per-kernel average milliseconds of one step (profiled in a separate short loop)
+  cpu_baseline the CPU oracle (scalar C port, OpenMP) timed on this host on one full view
+  --impl reference: the reference has no CPU path and its CUDA rasterizer is not obtainable offline
+  (SURVEY.md section 0); this arm times the oracle port of its algorithm on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+P_GAUSS, WIDTH, HEIGHT, SH_DEG, SCALE_MED = 1_000_000, 1920, 1080, 3, 0.01
+METRIC = "views/sec fwd+bwd @ 1M Gaussians, 1080p, SH3"
+UNIT = "views/s"
+WORKLOAD = "config3: synthetic 1M Gaussians, 1920x1080, SH deg 3, seed 0 (SURVEY 8d)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_inputs(rank: int, device):
+    from oracle import torch_oracle as O   # the seed-0 generator is shared with the tests
+    cam = O.make_camera(WIDTH, HEIGHT, w2c=O.yaw_w2c((rank - 3.5) * 2.0 if int(os.environ.get("WORLD_SIZE", "1")) > 1 else 0.0))
+    sc = O.synth_scene(P_GAUSS, WIDTH, HEIGHT, sh_degree=SH_DEG, scale_median=SCALE_MED, seed=0)
+    grads = O.synth_upstream_grads(WIDTH, HEIGHT, seed=1)
+    return cam, sc, grads
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_views_per_s(reps: int):
+    """Times the scalar C oracle (all host cores, OpenMP) on full views of the workload."""
+    from oracle import torch_oracle as O
+    from oracle.c_oracle import COracle
+    cam = O.make_camera(WIDTH, HEIGHT)
+    sc = O.synth_scene(P_GAUSS, WIDTH, HEIGHT, sh_degree=SH_DEG, scale_median=SCALE_MED, seed=0)
+    gC, gD, gA = [g.numpy() for g in O.synth_upstream_grads(WIDTH, HEIGHT, seed=1)]
+    co = COracle("f32")
+    kw = dict(means3D=sc["means3D"].numpy(), opacities=sc["opacities"].numpy(), W=WIDTH, H=HEIGHT,
+              tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=[0.0, 0.0, 0.0],
+              viewmatrix=cam["viewmatrix"].numpy(), projmatrix=cam["projmatrix"].numpy(),
+              campos=cam["campos"].numpy(), sh_degree=SH_DEG, shs=sc["shs"].numpy(),
+              scales=sc["scales"].numpy(), rotations=sc["rotations"].numpy())
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        co.forward(**kw)
+        co.backward(gC, gD, gA)
+        times.append(time.perf_counter() - t0)
+    return times, os.cpu_count() or 1
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: CPU oracle port of the reference's algorithm (the reference itself has no
+    CPU path and its CUDA package is not in /root/reference nor installable offline)."""
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    c_oracle.build()
+    steps = max(1, args.steps)
+    warm = max(0, min(args.warmup, 1))       # each step is ~seconds of CPU work: one warm-up is plenty
+    times, cores = cpu_oracle_views_per_s(warm + steps)
+    times = times[warm:]
+    ms = 1000.0 * sum(times) / len(times)
+    v = 1000.0 / ms
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference CUDA rasterizer unavailable offline; this is the CPU oracle port of its algorithm"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} full view(s) fwd+bwd (1M Gaussians, 1080p), OpenMP over all cores"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch.distributed as dist
+    from scgaussian_b200 import GaussianRasterizationSettings, GaussianRasterizer, _lib
+    from scgaussian_b200 import rasterizer as R
+    from scgaussian_b200.parallel import FlatGradBuffer
+
+    lib = _lib.load()                      # raises if libscgr.so is missing: no fallback
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W_ = max(3, args.warmup)
+    K = max(1, args.steps)
+
+    cam, sc, grads = make_inputs(rank, dev)
+    t = {k: v.to(dev).contiguous() for k, v in sc.items()}
+    gC, gD, gA = [g.to(dev).contiguous() for g in grads]
+    bg = torch.zeros(3, device=dev)
+    s = GaussianRasterizationSettings(
+        image_height=HEIGHT, image_width=WIDTH, tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=bg,
+        scale_modifier=1.0, viewmatrix=cam["viewmatrix"].to(dev), projmatrix=cam["projmatrix"].to(dev),
+        sh_degree=SH_DEG, campos=cam["campos"].to(dev), prefiltered=False, debug=False)
+    args_in = (t["means3D"], t["opacities"], t["shs"], None, t["scales"], t["rotations"], None)
+    flat = FlatGradBuffer(P_GAUSS, sh_coeffs=(SH_DEG + 1) ** 2, device=dev)
+    out_views = flat.out_dict()
+
+    def step():
+        color, radii, depth, alpha, state = R.rasterize_forward_raw(*args_in, s)
+        R.rasterize_backward_raw(state, *args_in, s, gC, gD, gA, out=out_views)
+        if world > 1:
+            flat.fill_stats(radii)
+            flat.all_reduce()               # THE collective of the path
+        return state
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (value) ----------------
+    for _ in range(W_):
+        state = step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.scgr_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        state = step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.scgr_kernel_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    tms = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_step = float(tms.item()) / K
+    value = world * 1000.0 / ms_step
+    R_inst = state.num_rendered
+
+    # ---------------- per-kernel profile (separate short loop; not the reported value) ----------------
+    kernels = {}
+    if rank == 0:
+        lib.scgr_profile_enable(1)
+        nprof = min(K, 5)
+        for _ in range(nprof):
+            step()
+        torch.cuda.synchronize()
+        import ctypes as C
+        names = (C.c_char_p * 4096)()
+        msarr = (C.c_float * 4096)()
+        n = lib.scgr_profile_fetch(names, msarr, 4096)
+        lib.scgr_profile_enable(0)
+        for i in range(max(n, 0)):
+            kernels.setdefault(names[i].decode(), []).append(float(msarr[i]))
+        kernels = {k: {"ms_per_step": sum(v) / nprof, "launches_per_step": len(v) / nprof,
+                       "ms_per_launch": sum(v) / len(v)} for k, v in kernels.items()}
+
+    # ---------------- end-to-end through the public operator (e2e) ----------------
+    e2e = None
+    if not args.no_e2e:
+        gt_host = torch.rand(3, HEIGHT, WIDTH).pin_memory()
+        vm_host, pm_host = cam["viewmatrix"].clone().pin_memory(), cam["projmatrix"].clone().pin_memory()
+        cp_host, bg_host = cam["campos"].clone().pin_memory(), torch.zeros(3).pin_memory()
+        leaves = {k: t[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+        h2d = sum(x.numel() * 4 for x in (gt_host, vm_host, pm_host, cp_host, bg_host))
+        loss_host = torch.zeros(1).pin_memory()
+
+        def e2e_step():
+            # per-step host inputs of a training step (reference train.py:135-147): camera + GT image
+            gt = gt_host.to(dev, non_blocking=True)
+            s2 = s._replace(viewmatrix=vm_host.to(dev, non_blocking=True), projmatrix=pm_host.to(dev, non_blocking=True),
+                            campos=cp_host.to(dev, non_blocking=True), bg=bg_host.to(dev, non_blocking=True))
+            m2d = torch.zeros(P_GAUSS, 3, device=dev, requires_grad=True)
+            color, radii, depth, alpha = GaussianRasterizer(s2)(
+                means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"], shs=leaves["shs"],
+                scales=leaves["scales"], rotations=leaves["rotations"])
+            loss = (color - gt).abs().mean() + 0.01 * depth.mean() + 0.01 * alpha.mean()
+            loss.backward()
+            if world > 1:
+                for v in leaves.values():
+                    dist.all_reduce(v.grad)
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=False)   # D2H read of the step's result
+            for v in leaves.values():
+                v.grad = None
+            return float(loss_host[0])
+
+        for _ in range(W_):
+            e2e_step()
+        barrier()
+        ke = max(3, K // 2)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(ke):
+            e2e_step()
+        e1.record()
+        barrier()
+        ms_e = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * 1000.0 * ke / float(ms_e.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4, "steps": ke,
+               "what": "GaussianRasterizer + L1/depth/alpha loss + autograd backward; camera matrices + GT image H2D from pinned memory and loss D2H every step; Gaussian parameters stay resident (they are model state, reference train.py)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peak, peak_src = peaks()
+    N = WIDTH * HEIGHT
+    Tn = ((WIDTH + 15) // 16) * ((HEIGHT + 15) // 16)
+    algo_bytes = {   # SURVEY.md section 8d, per launch (one view)
+        "preprocess_forward": 311 * P_GAUSS,
+        "render_forward": 44 * R_inst + 8 * Tn + 24 * N,
+        "render_backward": 84 * R_inst + 8 * Tn + 28 * N,
+        "preprocess_backward": 579 * P_GAUSS,
+    }
+    roof = None
+    if kernels:
+        dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+        share = kernels[dom]["ms_per_step"] / max(sum(v["ms_per_step"] for v in kernels.values()), 1e-9)
+        if dom in algo_bytes:
+            ach = algo_bytes[dom] / (kernels[dom]["ms_per_launch"] * 1e-3) / 1e9
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tp):
+                try:
+                    traffic = json.load(open(tp)).get(dom)
+                except Exception:
+                    traffic = None
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": algo_bytes[dom],
+                    "share_of_step": share,
+                    "note": "render kernels are SM-issue/MUFU/atomic bound, not HBM bound (SURVEY 8d); HBM fraction reported as BASELINE.json requires"}
+        for k, v in kernels.items():
+            if k in algo_bytes:
+                v["hbm_gbs_algorithmic"] = algo_bytes[k] / (v["ms_per_launch"] * 1e-3) / 1e9
+                v["hbm_frac"] = v["hbm_gbs_algorithmic"] / peak
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import c_oracle
+        c_oracle.build()
+        times, cores = cpu_oracle_views_per_s(3)
+        cpu = {"value": 1.0 / (sum(times[1:]) / len(times[1:])), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "2 full views fwd+bwd (1M Gaussians, 1080p) after 1 warm-up, scalar C oracle, OpenMP over all cores"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "P": P_GAUSS, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEG,
+                   "num_rendered_R": R_inst, "views_per_step": world, "parallelism": f"view-sharded dp{world}",
+                   "collective": "1 NCCL all-reduce of the flat gradient buffer per step" if world > 1 else "none (1 GPU)",
+                   "grad_allreduce_bytes": flat.nbytes() if world > 1 else 0,
+                   "l2": "no explicit flush: one step streams >1 GB (inputs 236 MB + gradients 232 MB + scratch) through the 126 MB L2"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,161 @@
+/* scgr.h -- C ABI of the B200-native differentiable Gaussian rasterizer (libscgr.so).
+ *
+ * Drop-in boundary for the operator SCGaussian calls from
+ *   reference gaussian_renderer/__init__.py:15      (import of the external rasterizer package)
+ *   reference gaussian_renderer/__init__.py:38-51   (GaussianRasterizationSettings -> ScgrView)
+ *   reference gaussian_renderer/__init__.py:100-108 (GaussianRasterizer.forward -> scgr_forward_*)
+ * The reference's own native layer is an external torch extension (`_C.rasterize_gaussians`,
+ * `_C.rasterize_gaussians_backward`, `_C.mark_visible`) with torch::Tensor
+ * signatures; this header is the torch-free equivalent: plain device pointers, sizes and a
+ * stream.  The Python host side (scgaussian_b200/rasterizer.py, re-exported as the package
+ * `diff_gaussian_rasterization`) binds it with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Ownership: the library never allocates device memory.  The caller owns inputs, outputs,
+ * gradients and the three scratch buffers (geometry / binning / image -- the counterparts of the
+ * reference extension's geomBuffer / binningBuffer / imgBuffer), whose sizes it queries with
+ * scgr_*_bytes().  The library keeps no global mutable state besides a thread-local error string,
+ * a launch counter and the (off by default) profiling log.
+ *
+ * Streams: every entry point only enqueues work on `stream` and returns; nothing blocks the host
+ * (the reference extension blocks once per forward on a D2H copy of num_rendered).  The number of
+ * (Gaussian, tile) instances R is produced on the device; scgr_forward_geometry() also copies it
+ * asynchronously to `num_rendered_host` (pinned host memory) so that the caller can size the
+ * binning buffer.  scgr_forward_render() takes the *capacity* of the binning buffer; when R >
+ * capacity it renders nothing and raises the overflow flag readable at status_host[1] after the
+ * stream has been synchronised -- the caller then grows the buffer and calls it again.
+ *
+ * Errors: every function returns 0 on success, non-zero otherwise; scgr_last_error() gives the
+ * message (thread-local).  Nothing is thrown across the boundary.
+ *
+ * All device pointers are fp32 / int32 unless stated, row-major, contiguous; 16-byte alignment
+ * of `shs` enables the vectorised load path (torch allocations always satisfy it).
+ */
+#ifndef SCGR_H_
+#define SCGR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCGR_VERSION 100   /* major*10000 + minor*100 + patch */
+#define SCGR_TILE 16        /* BLOCK_X = BLOCK_Y of the external rasterizer's config.h */
+
+typedef void* scgr_stream_t;   /* cudaStream_t */
+
+/* Counterpart of GaussianRasterizationSettings (12 fields; reference
+ * gaussian_renderer/__init__.py:38-51).  Matrices are the torch tensors' storage as-is:
+ * viewmatrix = W2C^T, projmatrix = (P*W2C)^T row-major (reference scene/cameras.py:60-62). */
+typedef struct ScgrView {
+    int32_t image_height;
+    int32_t image_width;
+    float tanfovx;
+    float tanfovy;
+    const float* bg;          /* device [3] */
+    float scale_modifier;
+    const float* viewmatrix;  /* device [16] */
+    const float* projmatrix;  /* device [16] */
+    int32_t sh_degree;        /* active degree, 0..3 */
+    const float* campos;      /* device [3] */
+    int32_t prefiltered;
+    int32_t debug;            /* non-zero: synchronise + check after every kernel */
+} ScgrView;
+
+/* The per-Gaussian inputs of GaussianRasterizer.forward (reference
+ * gaussian_renderer/__init__.py:100-108).  Exactly one of shs / colors_precomp and exactly one
+ * of (scales, rotations) / cov3D_precomp is non-NULL.  means2D is never read (it only exists on
+ * the Python side as the gradient hook) and is therefore absent here. */
+typedef struct ScgrGaussians {
+    int32_t P;
+    int32_t sh_coeffs;             /* M: coefficients stored per Gaussian in shs ((max_deg+1)^2) */
+    const float* means3D;          /* [P,3] */
+    const float* opacities;        /* [P] (the [P,1] tensor) */
+    const float* shs;              /* [P,M,3] or NULL */
+    const float* colors_precomp;   /* [P,3] or NULL */
+    const float* scales;           /* [P,3] or NULL */
+    const float* rotations;        /* [P,4] (r,x,y,z), used as given, or NULL */
+    const float* cov3D_precomp;    /* [P,6] xx,xy,xz,yy,yz,zz or NULL */
+} ScgrGaussians;
+
+/* Gradients returned by _RasterizeGaussians.backward.  Every
+ * non-NULL array is written in full (zeros for culled Gaussians): no caller-side memset needed. */
+typedef struct ScgrGrads {
+    float* dL_dmeans3D;        /* [P,3] */
+    float* dL_dmeans2D;        /* [P,3]  NDC-scaled screen-space gradient, z = 0 */
+    float* dL_dshs;            /* [P,M,3] or NULL */
+    float* dL_dcolors_precomp; /* [P,3] or NULL */
+    float* dL_dopacities;      /* [P] */
+    float* dL_dscales;         /* [P,3] or NULL */
+    float* dL_drotations;      /* [P,4] or NULL */
+    float* dL_dcov3D_precomp;  /* [P,6] or NULL */
+} ScgrGrads;
+
+int scgr_version(void);
+const char* scgr_last_error(void);
+
+/* Scratch sizes in bytes (each buffer must be 256-byte aligned). */
+size_t scgr_geometry_bytes(int32_t P);
+size_t scgr_binning_bytes(int32_t P, int32_t image_width, int32_t image_height, int64_t capacity);
+size_t scgr_image_bytes(int32_t image_width, int32_t image_height);
+
+/* Stage 1 of GaussianRasterizer.forward: preprocess (cull, project, EWA cov2D, SH->RGB), depth
+ * ordering of the Gaussians, prefix sum of tiles touched.  Writes radii[P] (int32) and the
+ * geometry scratch; enqueues an async copy of {R, 0} to status_host[0..1] (int64, pinned host
+ * memory; may be NULL). */
+int scgr_forward_geometry(const ScgrView* view, const ScgrGaussians* g, void* geometry_scratch,
+                          int32_t* radii, int64_t* status_host, scgr_stream_t stream);
+
+/* Stage 2: instance emission, stable tile partition, per-tile ranges, alpha compositing.
+ * out_color[3,H,W], out_depth[1,H,W] (un-normalised sum d*alpha*T), out_alpha[1,H,W] are written in
+ * full.  `capacity` = number of instances the binning scratch was sized for.  Enqueues an async
+ * copy of {R, overflow} to status_host[0..1] (may be NULL). */
+int scgr_forward_render(const ScgrView* view, const ScgrGaussians* g, void* geometry_scratch,
+                        void* binning_scratch, int64_t capacity, void* image_scratch,
+                        float* out_color, float* out_depth, float* out_alpha,
+                        int64_t* status_host, scgr_stream_t stream);
+
+/* _RasterizeGaussians.backward: needs the inputs and the three scratch buffers of the matching
+ * forward, untouched. */
+int scgr_backward(const ScgrView* view, const ScgrGaussians* g, const void* geometry_scratch,
+                  const void* binning_scratch, int64_t capacity, const void* image_scratch,
+                  const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                  const ScgrGrads* grads, scgr_stream_t stream);
+
+/* GaussianRasterizer.markVisible: present[i] = view-space z of means3D[i] > 0.2. */
+int scgr_mark_visible(const float* means3D, int32_t P, const float* viewmatrix, uint8_t* present,
+                      scgr_stream_t stream);
+
+/* Launch accounting and per-kernel timing (the reference has no tracing at all, SURVEY.md section 5;
+ * bench.py uses this for the live roofline numbers).  scgr_kernel_launch_count(): kernels this
+ * library has launched since load.  scgr_profile_enable(1): from now on every kernel is bracketed
+ * by CUDA events on its stream; scgr_profile_fetch() synchronises them, returns up to max_entries
+ * (name, milliseconds) pairs in launch order (names are static strings) and clears the log;
+ * returns the number of entries, or -1 on error. */
+long long scgr_kernel_launch_count(void);
+int scgr_profile_enable(int on);
+int scgr_profile_fetch(const char** names, float* ms, int max_entries);
+
+/* Introspection for stage-level parity tests (device pointers into the scratch buffers).
+ * record  : [P] x 12 floats {x, y, conicA, conicB | conicC, opacity, depth, flags(u32) | r, g, b, radius}
+ * point_list : [R] uint32 Gaussian ids, tile-major, depth-ordered;  ranges : [tiles] x {start,end} uint32
+ * n_contrib : [H*W] uint32;  final_T : [H*W] float;  tiles_touched : [P] uint32 */
+typedef struct ScgrDebugViews {
+    const float* record;
+    const uint32_t* tiles_touched;
+    const uint32_t* depth_order;      /* [P] Gaussian ids in ascending (depth, id) */
+    const uint32_t* point_list;
+    const uint32_t* ranges;
+    const uint32_t* n_contrib;
+    const float* final_T;
+    const int64_t* num_rendered;      /* device int64[2] = {R, overflow} */
+} ScgrDebugViews;
+int scgr_debug_views(int32_t P, int32_t image_width, int32_t image_height, int64_t capacity,
+                     const void* geometry_scratch, const void* binning_scratch,
+                     const void* image_scratch, ScgrDebugViews* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCGR_H_ */

@@ -1,0 +1,92 @@
+"""ctypes binding of libscgr.so (include/scgr.h).  This is the ONLY route from Python to the
+rasterizer: there is no eager / CPU fallback -- if the library is missing or fails to load, every
+operator call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libscgr.so")
+
+
+class ScgrView(C.Structure):
+    _fields_ = [("image_height", C.c_int32), ("image_width", C.c_int32),
+                ("tanfovx", C.c_float), ("tanfovy", C.c_float),
+                ("bg", C.c_void_p), ("scale_modifier", C.c_float),
+                ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
+                ("sh_degree", C.c_int32), ("campos", C.c_void_p),
+                ("prefiltered", C.c_int32), ("debug", C.c_int32)]
+
+
+class ScgrGaussians(C.Structure):
+    _fields_ = [("P", C.c_int32), ("sh_coeffs", C.c_int32),
+                ("means3D", C.c_void_p), ("opacities", C.c_void_p), ("shs", C.c_void_p),
+                ("colors_precomp", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
+                ("cov3D_precomp", C.c_void_p)]
+
+
+class ScgrGrads(C.Structure):
+    _fields_ = [("dL_dmeans3D", C.c_void_p), ("dL_dmeans2D", C.c_void_p), ("dL_dshs", C.c_void_p),
+                ("dL_dcolors_precomp", C.c_void_p), ("dL_dopacities", C.c_void_p),
+                ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p),
+                ("dL_dcov3D_precomp", C.c_void_p)]
+
+
+class ScgrDebugViews(C.Structure):
+    _fields_ = [("record", C.c_void_p), ("tiles_touched", C.c_void_p), ("depth_order", C.c_void_p),
+                ("point_list", C.c_void_p), ("ranges", C.c_void_p), ("n_contrib", C.c_void_p),
+                ("final_T", C.c_void_p), ("num_rendered", C.c_void_p)]
+
+
+# every symbol include/scgr.h declares: (restype, argtypes)
+SYMBOLS = {
+    "scgr_version": (C.c_int, []),
+    "scgr_last_error": (C.c_char_p, []),
+    "scgr_geometry_bytes": (C.c_size_t, [C.c_int32]),
+    "scgr_binning_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
+    "scgr_image_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "scgr_forward_geometry": (C.c_int, [C.POINTER(ScgrView), C.POINTER(ScgrGaussians), C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scgr_forward_render": (C.c_int, [C.POINTER(ScgrView), C.POINTER(ScgrGaussians), C.c_void_p,
+                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scgr_backward": (C.c_int, [C.POINTER(ScgrView), C.POINTER(ScgrGaussians), C.c_void_p, C.c_void_p,
+                                C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.POINTER(ScgrGrads), C.c_void_p]),
+    "scgr_mark_visible": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scgr_kernel_launch_count": (C.c_longlong, []),
+    "scgr_profile_enable": (C.c_int, [C.c_int]),
+    "scgr_profile_fetch": (C.c_int, [C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]),
+    "scgr_debug_views": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.POINTER(ScgrDebugViews)]),
+}
+
+_lib = None
+
+
+class ScgrError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads libscgr.so (once).  Raises ScgrError -- never falls back -- when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ScgrError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `python -m scgaussian_b200.build`). There is no CPU / eager fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)   # AttributeError if the export is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise ScgrError(load().scgr_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,265 @@
+// capi.cu -- the C ABI of libscgr.so (include/scgr.h): argument checking, scratch carving,
+// stage orchestration, error translation.  Replaces the external extension's
+// RasterizeGaussiansCUDA / RasterizeGaussiansBackwardCUDA / markVisible + Rasterizer::forward /
+// backward without torch types, allocations or host syncs.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace scgr {
+
+static thread_local std::string g_last_error;
+
+// ---- launch accounting + optional per-kernel event timing (scgr_profile_*) ----
+struct ProfEntry {
+    const char* name;
+    cudaEvent_t start, stop;
+    bool stop_pending;
+};
+static std::mutex g_prof_mutex;
+static std::vector<ProfEntry> g_prof;
+static std::atomic<bool> g_prof_on{false};
+static std::atomic<long long> g_kernel_launches{0};
+
+void begin_kernel(const char* what, const Launch& L) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfEntry e{what, nullptr, nullptr, true};
+    cudaEventCreate(&e.start);
+    cudaEventCreate(&e.stop);
+    cudaEventRecord(e.start, L.stream);
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_prof.push_back(e);
+}
+
+void check_stage(const char* what, const Launch& L) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && L.debug) e = cudaStreamSynchronize(L.stream);   // reference `debug` semantics
+    if (e != cudaSuccess)
+        throw std::runtime_error(std::string("scgr: ") + what + ": " + cudaGetErrorString(e));
+}
+
+void check_launch(const char* what, const Launch& L) {
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    if (g_prof_on.load(std::memory_order_relaxed)) {
+        std::lock_guard<std::mutex> lock(g_prof_mutex);
+        // the matching begin_kernel pushed the last entry with this name
+        for (size_t i = g_prof.size(); i-- > 0;)
+            if (std::strcmp(g_prof[i].name, what) == 0 && g_prof[i].stop_pending) { g_prof[i].stop_pending = false; cudaEventRecord(g_prof[i].stop, L.stream); break; }
+    }
+    check_stage(what, L);
+}
+
+static void require(bool cond, const char* msg) {
+    if (!cond) throw std::invalid_argument(std::string("scgr: ") + msg);
+}
+
+static void validate(const ScgrView* v, const ScgrGaussians* g) {
+    require(v && g, "null view / gaussians");
+    require(v->image_width >= 0 && v->image_height >= 0, "negative image size");
+    require((v->image_width + TILE - 1) / TILE < 65536 && (v->image_height + TILE - 1) / TILE < 65536,
+            "image too large for 16-bit tile coordinates");
+    require(g->P >= 0, "negative P");
+    if (g->P == 0) return;
+    require(v->bg && v->viewmatrix && v->projmatrix && v->campos, "null camera tensors");
+    require(g->means3D && g->opacities, "null means3D / opacities");
+    require((g->shs != nullptr) != (g->colors_precomp != nullptr),
+            "provide exactly one of shs / colors_precomp");
+    const bool sr = g->scales != nullptr && g->rotations != nullptr;
+    require(sr != (g->cov3D_precomp != nullptr) && (sr || (!g->scales && !g->rotations)),
+            "provide exactly one of (scales, rotations) / cov3D_precomp");
+    if (g->shs) {
+        require(v->sh_degree >= 0 && v->sh_degree <= 3, "sh_degree must be 0..3");
+        require(g->sh_coeffs >= (v->sh_degree + 1) * (v->sh_degree + 1), "shs has too few coefficients for sh_degree");
+    }
+    if (g->rotations) require((reinterpret_cast<uintptr_t>(g->rotations) & 15) == 0, "rotations must be 16-byte aligned");
+}
+
+template <typename F>
+static int guarded(F&& f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return 1;
+    } catch (...) {
+        g_last_error = "scgr: unknown error";
+        return 2;
+    }
+}
+
+static void copy_status(const GeometryLayout& G, int64_t* status_host, cudaStream_t s) {
+    if (status_host) cudaMemcpyAsync(status_host, G.status, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+}
+
+}  // namespace scgr
+
+using namespace scgr;
+
+extern "C" {
+
+int scgr_version(void) { return SCGR_VERSION; }
+const char* scgr_last_error(void) { return g_last_error.c_str(); }
+
+size_t scgr_geometry_bytes(int32_t P) { return carve_geometry(nullptr, P).bytes; }
+size_t scgr_binning_bytes(int32_t P, int32_t W, int32_t H, int64_t capacity) {
+    (void)P;
+    return carve_binning(nullptr, W, H, capacity).bytes;
+}
+size_t scgr_image_bytes(int32_t W, int32_t H) { return carve_image(nullptr, W, H).bytes; }
+
+int scgr_forward_geometry(const ScgrView* view, const ScgrGaussians* g, void* geometry_scratch,
+                          int32_t* radii, int64_t* status_host, scgr_stream_t stream) {
+    return guarded([&] {
+        validate(view, g);
+        require(geometry_scratch != nullptr, "null geometry scratch");
+        require((reinterpret_cast<uintptr_t>(geometry_scratch) & 255) == 0, "geometry scratch must be 256-byte aligned");
+        const Launch L{(cudaStream_t)stream, view->debug != 0};
+        const GeometryLayout G = carve_geometry(geometry_scratch, g->P);
+        if (g->P == 0) {
+            cudaMemsetAsync(G.status, 0, 2 * sizeof(int64_t), L.stream);
+        } else {
+            require(radii != nullptr, "null radii");
+            launch_preprocess_forward(*view, *g, G, radii, L);
+            launch_depth_order(G, g->P, L);
+        }
+        copy_status(G, status_host, L.stream);
+        check_stage("forward_geometry", L);
+    });
+}
+
+int scgr_forward_render(const ScgrView* view, const ScgrGaussians* g, void* geometry_scratch,
+                        void* binning_scratch, int64_t capacity, void* image_scratch,
+                        float* out_color, float* out_depth, float* out_alpha, int64_t* status_host,
+                        scgr_stream_t stream) {
+    return guarded([&] {
+        validate(view, g);
+        require(geometry_scratch && binning_scratch && image_scratch, "null scratch");
+        require(out_color && out_depth && out_alpha, "null outputs");
+        require(capacity >= 0 && capacity < (int64_t)0xFFFFFFFFll, "capacity out of range");
+        const Launch L{(cudaStream_t)stream, view->debug != 0};
+        const int W = view->image_width, H = view->image_height;
+        const GeometryLayout G = carve_geometry(geometry_scratch, g->P);
+        const BinningLayout B = carve_binning(binning_scratch, W, H, capacity);
+        const ImageLayout I = carve_image(image_scratch, W, H);
+        if (g->P == 0) {
+            // section 8b: P = 0 returns all-zero images (not background-filled)
+            const size_t N = (size_t)W * H;
+            cudaMemsetAsync(out_color, 0, 3 * N * sizeof(float), L.stream);
+            cudaMemsetAsync(out_depth, 0, N * sizeof(float), L.stream);
+            cudaMemsetAsync(out_alpha, 0, N * sizeof(float), L.stream);
+            cudaMemsetAsync(I.n_contrib, 0, N * sizeof(uint32_t), L.stream);
+            cudaMemsetAsync(I.final_T, 0, N * sizeof(float), L.stream);
+        } else {
+            int fin = 0;
+            launch_emit_and_partition(*view, G, B, g->P, capacity, &fin, L);
+            launch_render_forward(*view, G, B, B.vals[fin], capacity, I, out_color, out_depth, out_alpha, L);
+        }
+        copy_status(G, status_host, L.stream);
+        check_stage("forward_render", L);
+    });
+}
+
+int scgr_backward(const ScgrView* view, const ScgrGaussians* g, const void* geometry_scratch,
+                  const void* binning_scratch, int64_t capacity, const void* image_scratch,
+                  const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                  const ScgrGrads* grads, scgr_stream_t stream) {
+    return guarded([&] {
+        validate(view, g);
+        require(grads != nullptr, "null grads");
+        if (g->P == 0) return;
+        require(geometry_scratch && binning_scratch && image_scratch, "null scratch");
+        require(dL_dcolor && dL_ddepth && dL_dalpha, "null upstream gradients");
+        require(grads->dL_dmeans3D && grads->dL_dmeans2D && grads->dL_dopacities, "null gradient outputs");
+        require((g->shs != nullptr) == (grads->dL_dshs != nullptr), "dL_dshs must match shs");
+        require((g->colors_precomp != nullptr) == (grads->dL_dcolors_precomp != nullptr), "dL_dcolors_precomp must match colors_precomp");
+        require((g->scales != nullptr) == (grads->dL_dscales != nullptr) &&
+                (g->rotations != nullptr) == (grads->dL_drotations != nullptr), "dL_dscales / dL_drotations must match inputs");
+        require((g->cov3D_precomp != nullptr) == (grads->dL_dcov3D_precomp != nullptr), "dL_dcov3D_precomp must match cov3D_precomp");
+        if (grads->dL_drotations) require((reinterpret_cast<uintptr_t>(grads->dL_drotations) & 15) == 0, "dL_drotations must be 16-byte aligned");
+        const Launch L{(cudaStream_t)stream, view->debug != 0};
+        const int W = view->image_width, H = view->image_height;
+        const GeometryLayout G = carve_geometry(const_cast<void*>(geometry_scratch), g->P);
+        const BinningLayout B = carve_binning(const_cast<void*>(binning_scratch), W, H, capacity);
+        const ImageLayout I = carve_image(const_cast<void*>(image_scratch), W, H);
+        const uint32_t n_tiles = (uint32_t)((W + TILE - 1) / TILE) * (uint32_t)((H + TILE - 1) / TILE);
+        const int fin = tile_partition_final_buffer(n_tiles);
+        launch_render_backward(*view, G, B, B.vals[fin], capacity, I, dL_dcolor, dL_ddepth, dL_dalpha, g->P, L);
+        launch_preprocess_backward(*view, *g, G, *grads, L);
+        check_stage("backward", L);
+    });
+}
+
+int scgr_mark_visible(const float* means3D, int32_t P, const float* viewmatrix, uint8_t* present,
+                      scgr_stream_t stream) {
+    return guarded([&] {
+        require(P >= 0, "negative P");
+        if (P == 0) return;
+        require(means3D && viewmatrix && present, "null argument");
+        const Launch L{(cudaStream_t)stream, false};
+        launch_mark_visible(means3D, P, viewmatrix, present, L);
+    });
+}
+
+long long scgr_kernel_launch_count(void) { return g_kernel_launches.load(); }
+
+int scgr_profile_enable(int on) {
+    return guarded([&] {
+        std::lock_guard<std::mutex> lock(g_prof_mutex);
+        for (auto& e : g_prof) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
+        g_prof.clear();
+        g_prof_on.store(on != 0);
+    });
+}
+
+int scgr_profile_fetch(const char** names, float* ms, int max_entries) {
+    int n = 0;
+    int rc = guarded([&] {
+        std::lock_guard<std::mutex> lock(g_prof_mutex);
+        for (auto& e : g_prof) {
+            float t = 0.f;
+            cudaError_t err = cudaEventSynchronize(e.stop);
+            if (err == cudaSuccess) err = cudaEventElapsedTime(&t, e.start, e.stop);
+            if (err != cudaSuccess) { (void)cudaGetLastError(); t = -1.f; }
+            if (n < max_entries) { names[n] = e.name; ms[n] = t; n++; }
+            cudaEventDestroy(e.start);
+            cudaEventDestroy(e.stop);
+        }
+        g_prof.clear();
+    });
+    return rc == 0 ? n : -1;
+}
+
+int scgr_debug_views(int32_t P, int32_t W, int32_t H, int64_t capacity, const void* geometry_scratch,
+                     const void* binning_scratch, const void* image_scratch, ScgrDebugViews* out) {
+    return guarded([&] {
+        require(out != nullptr, "null out");
+        std::memset(out, 0, sizeof(*out));
+        if (geometry_scratch) {
+            const GeometryLayout G = carve_geometry(const_cast<void*>(geometry_scratch), P);
+            out->record = reinterpret_cast<const float*>(G.rec);
+            out->tiles_touched = G.tiles_touched;
+            out->depth_order = G.sort_vals[0];
+            out->num_rendered = G.status;
+        }
+        if (binning_scratch) {
+            const BinningLayout B = carve_binning(const_cast<void*>(binning_scratch), W, H, capacity);
+            const uint32_t n_tiles = (uint32_t)((W + TILE - 1) / TILE) * (uint32_t)((H + TILE - 1) / TILE);
+            out->point_list = B.vals[tile_partition_final_buffer(n_tiles)];
+            out->ranges = reinterpret_cast<const uint32_t*>(B.ranges);
+        }
+        if (image_scratch) {
+            const ImageLayout I = carve_image(const_cast<void*>(image_scratch), W, H);
+            out->n_contrib = I.n_contrib;
+            out->final_T = I.final_T;
+        }
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+// common.cuh -- shared definitions of the sm_100a rasterizer kernels (internal; the public
+// surface is include/scgr.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/scgr.h"
+
+namespace scgr {
+
+constexpr int TILE = SCGR_TILE;             // 16x16 pixel tiles
+constexpr int TILE_PIX = TILE * TILE;
+constexpr float NEAR_Z = 0.2f;              // A.1
+constexpr float ALPHA_MIN = 1.0f / 255.0f;  // A.8
+constexpr float ALPHA_MAX = 0.99f;          // A.8
+constexpr float T_EPS = 1e-4f;              // A.8
+constexpr float DILATION = 0.3f;            // A.4
+constexpr uint32_t CULLED_KEY = 0xFFFFFFFFu;
+
+// ---- per-Gaussian record written by preprocess, gathered by render (48 B, 3 x 16-B loads) ----
+//   q0 = {mean_x, mean_y, conic_A, conic_B}
+//   q1 = {conic_C, opacity, depth, flags}      flags: bit0..2 = SH colour clamped (r,g,b)
+//   q2 = {r, g, b, radius (as float)}
+struct __align__(16) Record {
+    float4 q0, q1, q2;
+};
+static_assert(sizeof(Record) == 48, "Record must be 48 bytes");
+
+// ---- per-Gaussian screen-space gradient accumulator written by render-backward (48 B) ----
+//   a0 = {dL/dmean_x (pixel units), dL/dmean_y, dL/dconic_A, dL/dconic_B (true derivative)}
+//   a1 = {dL/dconic_C, dL/dopacity, dL/ddepth, 0}
+//   a2 = {dL/dr, dL/dg, dL/db, 0}
+struct __align__(16) ScreenGrad {
+    float4 a0, a1, a2;
+};
+static_assert(sizeof(ScreenGrad) == 48, "ScreenGrad must be 48 bytes");
+
+// ---- scratch carving (256-B aligned sub-allocations) ----
+__host__ __device__ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+constexpr int RADIX_THREADS = 256;
+constexpr int RADIX_ITEMS = 16;                                // items per thread
+constexpr int RADIX_TILE = RADIX_THREADS * RADIX_ITEMS;        // 4096 items per block
+constexpr int RADIX_BINS = 256;
+constexpr int SCAN_BLOCK = 1024;
+
+inline uint32_t radix_blocks(int64_t n) { return (uint32_t)((n + RADIX_TILE - 1) / RADIX_TILE); }
+
+struct GeometryLayout {
+    Record* rec;              // [P]
+    uint32_t* depth_key;      // == sort_keys[0]: float bits of view depth, CULLED_KEY if culled
+    uint32_t* tiles_touched;  // [P]
+    uint2* rect;              // [P] {minx | miny << 16, maxx | maxy << 16}
+    uint32_t* sort_keys[2];   // [P] ping-pong
+    uint32_t* sort_vals[2];   // [P] ping-pong (Gaussian ids); final depth order in sort_vals[0]
+    uint32_t* offsets;        // [P] inclusive scan of tiles_touched in depth order
+    uint32_t* scan_partials;  // [ceil(P / SCAN_BLOCK) + 1]
+    uint32_t* radix_hist;     // [RADIX_BINS * radix_blocks(P)]
+    uint32_t* radix_totals;   // [RADIX_BINS]
+    ScreenGrad* screen_grad;  // [P] (used by backward only; lives here so backward allocates nothing)
+    int64_t* status;          // [2] {R, overflow}
+    size_t bytes;
+};
+
+inline GeometryLayout carve_geometry(void* base, int32_t P) {
+    GeometryLayout L;
+    size_t o = 0;
+    char* b = (char*)base;
+    size_t Pa = P > 0 ? (size_t)P : 1;
+    auto take = [&](size_t n) { char* p = b + o; o += align_up(n); return (void*)p; };
+    L.status = (int64_t*)take(2 * sizeof(int64_t));
+    L.rec = (Record*)take(Pa * sizeof(Record));
+    L.tiles_touched = (uint32_t*)take(Pa * 4);
+    L.rect = (uint2*)take(Pa * 8);
+    for (int i = 0; i < 2; i++) L.sort_keys[i] = (uint32_t*)take(Pa * 4);
+    for (int i = 0; i < 2; i++) L.sort_vals[i] = (uint32_t*)take(Pa * 4);
+    L.depth_key = L.sort_keys[0];   // preprocess writes the sort input in place
+    L.offsets = (uint32_t*)take(Pa * 4);
+    L.scan_partials = (uint32_t*)take(((Pa + SCAN_BLOCK - 1) / SCAN_BLOCK + 1) * 4);
+    L.radix_hist = (uint32_t*)take((size_t)RADIX_BINS * radix_blocks(Pa) * 4);
+    L.radix_totals = (uint32_t*)take(RADIX_BINS * 4);
+    L.screen_grad = (ScreenGrad*)take(Pa * sizeof(ScreenGrad));
+    L.bytes = o;
+    return L;
+}
+
+struct BinningLayout {
+    uint32_t* keys[2];        // [capacity] tile ids, ping-pong
+    uint32_t* vals[2];        // [capacity] Gaussian ids, ping-pong
+    uint32_t* radix_hist;     // [RADIX_BINS * radix_blocks(capacity)]
+    uint32_t* radix_totals;   // [RADIX_BINS]
+    uint2* ranges;            // [tiles]
+    size_t bytes;
+};
+
+inline BinningLayout carve_binning(void* base, int32_t W, int32_t H, int64_t capacity) {
+    BinningLayout L;
+    size_t o = 0;
+    char* b = (char*)base;
+    size_t C = capacity > 0 ? (size_t)capacity : 1;
+    size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    if (tiles == 0) tiles = 1;
+    auto take = [&](size_t n) { char* p = b + o; o += align_up(n); return (void*)p; };
+    L.ranges = (uint2*)take(tiles * sizeof(uint2));
+    for (int i = 0; i < 2; i++) L.keys[i] = (uint32_t*)take(C * 4);
+    for (int i = 0; i < 2; i++) L.vals[i] = (uint32_t*)take(C * 4);
+    L.radix_hist = (uint32_t*)take((size_t)RADIX_BINS * radix_blocks(C) * 4);
+    L.radix_totals = (uint32_t*)take(RADIX_BINS * 4);
+    L.bytes = o;
+    return L;
+}
+
+struct ImageLayout {
+    uint32_t* n_contrib;      // [H*W]
+    float* final_T;           // [H*W]
+    size_t bytes;
+};
+
+inline ImageLayout carve_image(void* base, int32_t W, int32_t H) {
+    ImageLayout L;
+    size_t o = 0;
+    char* b = (char*)base;
+    size_t N = (size_t)W * H;
+    if (N == 0) N = 1;
+    auto take = [&](size_t n) { char* p = b + o; o += align_up(n); return (void*)p; };
+    L.n_contrib = (uint32_t*)take(N * 4);
+    L.final_T = (float*)take(N * 4);
+    L.bytes = o;
+    return L;
+}
+
+// ---- kernel launchers (defined in the .cu files) ----
+struct Launch {
+    cudaStream_t stream;
+    bool debug;
+};
+
+void launch_preprocess_forward(const ScgrView& v, const ScgrGaussians& g, const GeometryLayout& G,
+                               int32_t* radii, const Launch& L);
+void launch_preprocess_backward(const ScgrView& v, const ScgrGaussians& g, const GeometryLayout& G,
+                                const ScgrGrads& out, const Launch& L);
+void launch_mark_visible(const float* means3D, int32_t P, const float* viewmatrix, uint8_t* present,
+                         const Launch& L);
+
+// Stable LSD radix pass machinery.  `n_dev` (device uint32/int64 low word) overrides `n_host` when
+// non-NULL; `cap` bounds the grid.
+void radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], const int64_t* n_dev, int64_t n_host,
+                      int64_t cap, int begin_bit, int end_bit, uint32_t* hist, uint32_t* totals,
+                      int* final_buffer, const Launch& L);
+void launch_depth_order(const GeometryLayout& G, int32_t P, const Launch& L);
+void launch_emit_and_partition(const ScgrView& v, const GeometryLayout& G, const BinningLayout& B,
+                               int32_t P, int64_t capacity, int* final_buffer, const Launch& L);
+
+void launch_render_forward(const ScgrView& v, const GeometryLayout& G, const BinningLayout& B,
+                           const uint32_t* point_list, int64_t capacity, const ImageLayout& I,
+                           float* out_color, float* out_depth, float* out_alpha, const Launch& L);
+void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const BinningLayout& B,
+                            const uint32_t* point_list, int64_t capacity, const ImageLayout& I,
+                            const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                            int32_t P, const Launch& L);
+int tile_partition_final_buffer(uint32_t n_tiles);
+
+// Every kernel launch is bracketed:  begin_kernel(name, L); kernel<<<...>>>(...); check_launch(name, L);
+// begin_kernel records a start event when profiling is on (scgr_profile_enable); check_launch
+// counts the launch, records the stop event, and turns CUDA errors into std::runtime_error
+// (synchronising first when the view's `debug` flag is set, like the reference's CHECK_CUDA).
+void begin_kernel(const char* what, const Launch& L);
+void check_launch(const char* what, const Launch& L);
+void check_stage(const char* what, const Launch& L);
+
+}  // namespace scgr

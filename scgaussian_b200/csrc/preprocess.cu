@@ -1,0 +1,580 @@
+// preprocess.cu -- per-Gaussian stages of the rasterizer, forward and backward (sm_100a).
+//
+// Replaces the external rasterizer's FORWARD::preprocessCUDA, BACKWARD::computeCov2DCUDA,
+// BACKWARD::preprocessCUDA and checkFrustum, i.e. the
+// per-Gaussian half of what reference gaussian_renderer/__init__.py:100-108 invokes.  Semantics:
+// SURVEY.md Appendix A.1-A.5 (forward), A.10 (backward).  The SH polynomial is the one of
+// reference utils/sh_utils.py:74-100; R(q) that of reference utils/general_utils.py:96-104.
+//
+// B200 design: both kernels are HBM-bound streaming passes (311 B / 579 B of compulsory traffic
+// per Gaussian).  One thread per Gaussian, 128-thread CTAs; the 192-byte SH row of each Gaussian
+// (and its gradient) is moved between HBM and shared memory by the whole CTA with 128-bit,
+// fully-coalesced accesses into a padded (13 x float4 per row) layout that is bank-conflict-free
+// for the per-thread 128-bit reads/writes; the backward fuses cov2D-, projection-, depth-, SH-
+// and cov3D-backward in one pass and writes every gradient tensor in full (zeros for culled
+// Gaussians), so the host never memsets them.
+#include <stdexcept>
+#include <string>
+
+#include "common.cuh"
+
+namespace scgr {
+
+namespace {
+
+constexpr int PRE_THREADS = 128;
+constexpr int SH_ROW_F4 = 12;       // 48 floats = 12 float4 per Gaussian at M = 16
+constexpr int SH_ROW_F4_PAD = 13;   // padded row stride (float4 units): conflict-free LDS.128/STS.128
+
+__constant__ const float kC0 = 0.28209479177387814f;
+__constant__ const float kC1 = 0.4886025119029199f;
+__device__ const float kC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                 -1.0925484305920792f, 0.5462742152960396f};
+__device__ const float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                 0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                 -0.5900435899266435f};
+
+struct Camera {
+    float V[16];   // viewmatrix tensor, row-major: p_view_j = sum_k hom_k V[k*4+j]
+    float PM[16];  // projmatrix tensor, same convention
+    float cam[3];
+};
+
+__device__ __forceinline__ void load_camera(const ScgrView& v, Camera& c) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        c.V[i] = __ldg(v.viewmatrix + i);
+        c.PM[i] = __ldg(v.projmatrix + i);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) c.cam[i] = __ldg(v.campos + i);
+}
+
+// Everything the EWA projection of one Gaussian produces; shared by forward and backward.
+struct Proj {
+    float3 t;        // view-space point
+    float tx, ty;    // after the 1.3*tanfov clamp
+    bool xin, yin;   // clamp inactive
+    float3 M0, M1;   // rows of J * W3
+    float a, b, c;   // dilated 2D covariance
+    float fx, fy;
+};
+
+__device__ __forceinline__ void quat_to_R(const float4 q, float R[9]) {
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - r * z); R[2] = 2.f * (x * z + r * y);
+    R[3] = 2.f * (x * y + r * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - r * x);
+    R[6] = 2.f * (x * z - r * y); R[7] = 2.f * (y * z + r * x); R[8] = 1.f - 2.f * (x * x + y * y);
+}
+
+// Sigma = (R S)(R S)^T as 6 floats xx,xy,xz,yy,yz,zz  (A.3)
+__device__ __forceinline__ void cov3d_from_scale_rot(const float3 s, const float mod, const float4 q,
+                                                     float c6[6]) {
+    float R[9];
+    quat_to_R(q, R);
+    const float sx = mod * s.x, sy = mod * s.y, sz = mod * s.z;
+    float L[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { L[i * 3] = R[i * 3] * sx; L[i * 3 + 1] = R[i * 3 + 1] * sy; L[i * 3 + 2] = R[i * 3 + 2] * sz; }
+    c6[0] = L[0] * L[0] + L[1] * L[1] + L[2] * L[2];
+    c6[1] = L[0] * L[3] + L[1] * L[4] + L[2] * L[5];
+    c6[2] = L[0] * L[6] + L[1] * L[7] + L[2] * L[8];
+    c6[3] = L[3] * L[3] + L[4] * L[4] + L[5] * L[5];
+    c6[4] = L[3] * L[6] + L[4] * L[7] + L[5] * L[8];
+    c6[5] = L[6] * L[6] + L[7] * L[7] + L[8] * L[8];
+}
+
+__device__ __forceinline__ void project_cov(const Camera& cam, const ScgrView& v, const float3 p,
+                                            const float c6[6], Proj& o) {
+    const float* V = cam.V;
+    o.t.x = p.x * V[0] + p.y * V[4] + p.z * V[8] + V[12];
+    o.t.y = p.x * V[1] + p.y * V[5] + p.z * V[9] + V[13];
+    o.t.z = p.x * V[2] + p.y * V[6] + p.z * V[10] + V[14];
+    o.fx = v.image_width / (2.f * v.tanfovx);
+    o.fy = v.image_height / (2.f * v.tanfovy);
+    const float limx = 1.3f * v.tanfovx, limy = 1.3f * v.tanfovy;
+    const float tz = o.t.z;
+    const float txtz = o.t.x / tz, tytz = o.t.y / tz;
+    o.xin = (txtz >= -limx) && (txtz <= limx);
+    o.yin = (tytz >= -limy) && (tytz <= limy);
+    o.tx = fminf(limx, fmaxf(-limx, txtz)) * tz;
+    o.ty = fminf(limy, fmaxf(-limy, tytz)) * tz;
+    const float j00 = o.fx / tz, j02 = -o.fx * o.tx / (tz * tz);
+    const float j11 = o.fy / tz, j12 = -o.fy * o.ty / (tz * tz);
+    // W3[r][k] = V[k*4+r];  M = J W3
+    o.M0 = make_float3(j00 * V[0] + j02 * V[2], j00 * V[4] + j02 * V[6], j00 * V[8] + j02 * V[10]);
+    o.M1 = make_float3(j11 * V[1] + j12 * V[2], j11 * V[5] + j12 * V[6], j11 * V[9] + j12 * V[10]);
+    const float s0x = c6[0] * o.M0.x + c6[1] * o.M0.y + c6[2] * o.M0.z;
+    const float s0y = c6[1] * o.M0.x + c6[3] * o.M0.y + c6[4] * o.M0.z;
+    const float s0z = c6[2] * o.M0.x + c6[4] * o.M0.y + c6[5] * o.M0.z;
+    const float s1x = c6[0] * o.M1.x + c6[1] * o.M1.y + c6[2] * o.M1.z;
+    const float s1y = c6[1] * o.M1.x + c6[3] * o.M1.y + c6[4] * o.M1.z;
+    const float s1z = c6[2] * o.M1.x + c6[4] * o.M1.y + c6[5] * o.M1.z;
+    o.a = o.M0.x * s0x + o.M0.y * s0y + o.M0.z * s0z + DILATION;
+    o.b = o.M0.x * s1x + o.M0.y * s1y + o.M0.z * s1z;
+    o.c = o.M1.x * s1x + o.M1.y * s1y + o.M1.z * s1z + DILATION;
+}
+
+// SH basis b[k] at unit direction d, for k < (D+1)^2  (reference utils/sh_utils.py:74-100)
+__device__ __forceinline__ void sh_basis(const int D, const float3 d, float b[16]) {
+    b[0] = kC0;
+    if (D < 1) return;
+    const float x = d.x, y = d.y, z = d.z;
+    b[1] = -kC1 * y; b[2] = kC1 * z; b[3] = -kC1 * x;
+    if (D < 2) return;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    b[4] = kC2[0] * xy; b[5] = kC2[1] * yz; b[6] = kC2[2] * (2.f * zz - xx - yy);
+    b[7] = kC2[3] * xz; b[8] = kC2[4] * (xx - yy);
+    if (D < 3) return;
+    b[9] = kC3[0] * y * (3.f * xx - yy); b[10] = kC3[1] * xy * z;
+    b[11] = kC3[2] * y * (4.f * zz - xx - yy); b[12] = kC3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+    b[13] = kC3[4] * x * (4.f * zz - xx - yy); b[14] = kC3[5] * z * (xx - yy);
+    b[15] = kC3[6] * x * (xx - 3.f * yy);
+}
+
+// d(basis)/d(direction): gx[k], gy[k], gz[k]
+__device__ __forceinline__ void sh_basis_grad(const int D, const float3 d, float gx[16], float gy[16],
+                                              float gz[16]) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) { gx[k] = 0.f; gy[k] = 0.f; gz[k] = 0.f; }
+    if (D < 1) return;
+    const float x = d.x, y = d.y, z = d.z;
+    gy[1] = -kC1; gz[2] = kC1; gx[3] = -kC1;
+    if (D < 2) return;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    gx[4] = kC2[0] * y; gy[4] = kC2[0] * x;
+    gy[5] = kC2[1] * z; gz[5] = kC2[1] * y;
+    gx[6] = kC2[2] * -2.f * x; gy[6] = kC2[2] * -2.f * y; gz[6] = kC2[2] * 4.f * z;
+    gx[7] = kC2[3] * z; gz[7] = kC2[3] * x;
+    gx[8] = kC2[4] * 2.f * x; gy[8] = kC2[4] * -2.f * y;
+    if (D < 3) return;
+    gx[9] = kC3[0] * 6.f * xy; gy[9] = kC3[0] * (3.f * xx - 3.f * yy);
+    gx[10] = kC3[1] * yz; gy[10] = kC3[1] * xz; gz[10] = kC3[1] * xy;
+    gx[11] = kC3[2] * -2.f * xy; gy[11] = kC3[2] * (4.f * zz - xx - 3.f * yy); gz[11] = kC3[2] * 8.f * yz;
+    gx[12] = kC3[3] * -6.f * xz; gy[12] = kC3[3] * -6.f * yz; gz[12] = kC3[3] * (6.f * zz - 3.f * xx - 3.f * yy);
+    gx[13] = kC3[4] * (4.f * zz - 3.f * xx - yy); gy[13] = kC3[4] * -2.f * xy; gz[13] = kC3[4] * 8.f * xz;
+    gx[14] = kC3[5] * 2.f * xz; gy[14] = kC3[5] * -2.f * yz; gz[14] = kC3[5] * (xx - yy);
+    gx[15] = kC3[6] * (3.f * xx - 3.f * yy); gy[15] = kC3[6] * -6.f * xy;
+}
+
+__device__ __forceinline__ float3 load3(const float* p, int i) {
+    return make_float3(__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2));
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+// SH_FAST: M == 16 and shs 16-byte aligned -> CTA-cooperative 128-bit staging through smem.
+template <bool SH_FAST>
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __restrict__ rec,
+                          uint32_t* __restrict__ depth_key, uint32_t* __restrict__ tiles_touched,
+                          uint2* __restrict__ rect, uint32_t* __restrict__ order_init,
+                          int32_t* __restrict__ radii) {
+    __shared__ float4 s_sh[SH_FAST ? PRE_THREADS * SH_ROW_F4_PAD : 1];
+    const int P = g.P;
+    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
+    const bool use_sh = g.shs != nullptr;
+
+    if (SH_FAST && use_sh) {
+        // rows [block0, block0 + 128) are one contiguous run of 128*12 float4 in HBM
+        const int row0 = blockIdx.x * PRE_THREADS;
+        const int nrows = min(PRE_THREADS, P - row0);
+        const float4* src = reinterpret_cast<const float4*>(g.shs) + (size_t)row0 * SH_ROW_F4;
+        const int nf4 = nrows * SH_ROW_F4;
+        for (int f = threadIdx.x; f < nf4; f += PRE_THREADS) {
+            const int r = f / SH_ROW_F4, c = f - r * SH_ROW_F4;
+            s_sh[r * SH_ROW_F4_PAD + c] = __ldg(src + f);
+        }
+        __syncthreads();
+    }
+    if (i >= P) return;
+    order_init[i] = (uint32_t)i;   // value array of the depth sort
+
+    Camera cam;
+    load_camera(v, cam);
+    const float3 p = load3(g.means3D, i);
+    const float zv = p.x * cam.V[2] + p.y * cam.V[6] + p.z * cam.V[10] + cam.V[14];
+
+    bool alive = zv > NEAR_Z;   // A.1
+    if (!alive && v.prefiltered) {
+        printf("scgr: point %d is filtered although prefiltered is set\n", i);
+        __trap();
+    }
+    Proj pr;
+    float det = 0.f, px = 0.f, py = 0.f;
+    int rad = 0, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
+    if (alive) {
+        const float* PM = cam.PM;
+        const float h0 = p.x * PM[0] + p.y * PM[4] + p.z * PM[8] + PM[12];
+        const float h1 = p.x * PM[1] + p.y * PM[5] + p.z * PM[9] + PM[13];
+        const float h3 = p.x * PM[3] + p.y * PM[7] + p.z * PM[11] + PM[15];
+        const float pw = 1.f / (h3 + 1e-7f);                          // A.2
+        float c6[6];
+        if (g.cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) c6[k] = __ldg(g.cov3D_precomp + 6 * (size_t)i + k);
+        } else {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(g.rotations) + i);
+            cov3d_from_scale_rot(load3(g.scales, i), v.scale_modifier, q, c6);   // A.3
+        }
+        project_cov(cam, v, p, c6, pr);                               // A.4
+        det = pr.a * pr.c - pr.b * pr.b;
+        alive = det != 0.f;
+        if (alive) {
+            const float mid = 0.5f * (pr.a + pr.c);
+            const float disc = sqrtf(fmaxf(0.1f, mid * mid - det));
+            const float lam = fmaxf(mid + disc, mid - disc);
+            rad = (int)ceilf(3.f * sqrtf(lam));
+            px = ((h0 * pw + 1.f) * v.image_width - 1.f) * 0.5f;
+            py = ((h1 * pw + 1.f) * v.image_height - 1.f) * 0.5f;
+            x0 = min(gx, max(0, (int)((px - rad) / TILE)));
+            y0 = min(gy, max(0, (int)((py - rad) / TILE)));
+            x1 = min(gx, max(0, (int)((px + rad + TILE - 1) / TILE)));
+            y1 = min(gy, max(0, (int)((py + rad + TILE - 1) / TILE)));
+            alive = (x1 - x0) * (y1 - y0) != 0;
+        }
+    }
+    if (!alive) {
+        radii[i] = 0;
+        tiles_touched[i] = 0;
+        depth_key[i] = CULLED_KEY;
+        rect[i] = make_uint2(0u, 0u);
+        rec[i].q2 = make_float4(0.f, 0.f, 0.f, 0.f);   // radius 0 marks "culled" for the backward
+        return;
+    }
+
+    // A.5 colour
+    float3 rgb;
+    uint32_t flags = 0;
+    if (use_sh) {
+        float3 d = make_float3(p.x - cam.cam[0], p.y - cam.cam[1], p.z - cam.cam[2]);
+        const float inv = 1.f / sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+        d.x *= inv; d.y *= inv; d.z *= inv;
+        float b[16];
+        sh_basis(v.sh_degree, d, b);
+        const int nk = (v.sh_degree + 1) * (v.sh_degree + 1);
+        float acc[3] = {0.f, 0.f, 0.f};
+        if (SH_FAST) {
+            const float4* row = s_sh + threadIdx.x * SH_ROW_F4_PAD;
+#pragma unroll
+            for (int cc = 0; cc < SH_ROW_F4; cc++) {
+                const float4 q = row[cc];
+                const float in[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int k = (4 * cc + e) / 3, c = (4 * cc + e) - 3 * k;   // compile-time
+                    if (k < nk) acc[c] += b[k] * in[e];
+                }
+            }
+        } else {
+            const float* row = g.shs + (size_t)i * g.sh_coeffs * 3;
+            for (int k = 0; k < nk; k++) {
+                acc[0] += b[k] * __ldg(row + 3 * k); acc[1] += b[k] * __ldg(row + 3 * k + 1); acc[2] += b[k] * __ldg(row + 3 * k + 2);
+            }
+        }
+        rgb = make_float3(acc[0] + 0.5f, acc[1] + 0.5f, acc[2] + 0.5f);
+        if (rgb.x < 0.f) flags |= 1u;
+        if (rgb.y < 0.f) flags |= 2u;
+        if (rgb.z < 0.f) flags |= 4u;
+        rgb.x = fmaxf(rgb.x, 0.f); rgb.y = fmaxf(rgb.y, 0.f); rgb.z = fmaxf(rgb.z, 0.f);
+    } else {
+        rgb = load3(g.colors_precomp, i);
+    }
+
+    const float dinv = 1.f / det;
+    Record r;
+    r.q0 = make_float4(px, py, pr.c * dinv, -pr.b * dinv);
+    r.q1 = make_float4(pr.a * dinv, __ldg(g.opacities + i), zv, __uint_as_float(flags));
+    r.q2 = make_float4(rgb.x, rgb.y, rgb.z, (float)rad);
+    rec[i] = r;
+    radii[i] = rad;
+    tiles_touched[i] = (uint32_t)((x1 - x0) * (y1 - y0));
+    depth_key[i] = __float_as_uint(zv);   // zv > 0.2 => bit order == numeric order (A.6)
+    rect[i] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
+}
+
+// ------------------------------------------------------------------------------------------
+// backward (A.10), fused: conic->cov2D->{Sigma, t}, NDC mean, depth, SH, Sigma->{scale, rot}
+// ------------------------------------------------------------------------------------------
+template <bool SH_FAST>
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record* __restrict__ rec,
+                           const ScreenGrad* __restrict__ sg, const ScgrGrads out) {
+    __shared__ float4 s_sh[SH_FAST ? PRE_THREADS * SH_ROW_F4_PAD : 1];
+    const int P = g.P;
+    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
+    const bool use_sh = g.shs != nullptr;
+    const int row0 = blockIdx.x * PRE_THREADS;
+    const int nrows = min(PRE_THREADS, P - row0);
+
+    if (SH_FAST && use_sh) {
+        const float4* src = reinterpret_cast<const float4*>(g.shs) + (size_t)row0 * SH_ROW_F4;
+        const int nf4 = nrows * SH_ROW_F4;
+        for (int f = threadIdx.x; f < nf4; f += PRE_THREADS) {
+            const int r = f / SH_ROW_F4, c = f - r * SH_ROW_F4;
+            s_sh[r * SH_ROW_F4_PAD + c] = __ldg(src + f);
+        }
+        __syncthreads();
+    }
+
+    float dmean[3] = {0.f, 0.f, 0.f};
+    float dm2x = 0.f, dm2y = 0.f, dop = 0.f;
+    float d6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float dscale[3] = {0.f, 0.f, 0.f};
+    float drot[4] = {0.f, 0.f, 0.f, 0.f};
+    float dcol[3] = {0.f, 0.f, 0.f};
+    bool live = false;
+    if (i < P) {
+        const float4 q2 = rec[i].q2;
+        live = q2.w > 0.f;
+    }
+    if (live) {
+        Camera cam;
+        load_camera(v, cam);
+        const float4 q1 = rec[i].q1;
+        const uint32_t flags = __float_as_uint(q1.w);
+        const ScreenGrad A = sg[i];
+        const float3 p = load3(g.means3D, i);
+        const float* V = cam.V;
+        const float* PM = cam.PM;
+        dm2x = A.a0.x * (0.5f * v.image_width);    // NDC units (A.9)
+        dm2y = A.a0.y * (0.5f * v.image_height);
+        dop = A.a1.y;
+        // (1) conic -> cov2D
+        float c6[6];
+        float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+        float3 sc = make_float3(0.f, 0.f, 0.f);
+        if (g.cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) c6[k] = __ldg(g.cov3D_precomp + 6 * (size_t)i + k);
+        } else {
+            q = __ldg(reinterpret_cast<const float4*>(g.rotations) + i);
+            sc = load3(g.scales, i);
+            cov3d_from_scale_rot(sc, v.scale_modifier, q, c6);
+        }
+        Proj pr;
+        project_cov(cam, v, p, c6, pr);
+        const float a = pr.a, b = pr.b, c = pr.c;
+        const float den = a * c - b * b;
+        const float k2 = 1.f / (den * den + 1e-7f);
+        const float dA = A.a0.z, dB = A.a0.w, dC = A.a1.x;
+        const float dLa = k2 * (-c * c * dA + b * c * dB - b * b * dC);
+        const float dLb = k2 * (2.f * b * c * dA - (den + 2.f * b * b) * dB + 2.f * a * b * dC);
+        const float dLc = k2 * (-b * b * dA + a * b * dB - a * a * dC);
+        const float3 M0 = pr.M0, M1 = pr.M1;
+        d6[0] = dLa * M0.x * M0.x + dLb * M0.x * M1.x + dLc * M1.x * M1.x;
+        d6[3] = dLa * M0.y * M0.y + dLb * M0.y * M1.y + dLc * M1.y * M1.y;
+        d6[5] = dLa * M0.z * M0.z + dLb * M0.z * M1.z + dLc * M1.z * M1.z;
+        d6[1] = 2.f * dLa * M0.x * M0.y + dLb * (M0.x * M1.y + M0.y * M1.x) + 2.f * dLc * M1.x * M1.y;
+        d6[2] = 2.f * dLa * M0.x * M0.z + dLb * (M0.x * M1.z + M0.z * M1.x) + 2.f * dLc * M1.x * M1.z;
+        d6[4] = 2.f * dLa * M0.y * M0.z + dLb * (M0.y * M1.z + M0.z * M1.y) + 2.f * dLc * M1.y * M1.z;
+        // cov2D -> M -> J -> t -> mean
+        const float s0x = c6[0] * M0.x + c6[1] * M0.y + c6[2] * M0.z;
+        const float s0y = c6[1] * M0.x + c6[3] * M0.y + c6[4] * M0.z;
+        const float s0z = c6[2] * M0.x + c6[4] * M0.y + c6[5] * M0.z;
+        const float s1x = c6[0] * M1.x + c6[1] * M1.y + c6[2] * M1.z;
+        const float s1y = c6[1] * M1.x + c6[3] * M1.y + c6[4] * M1.z;
+        const float s1z = c6[2] * M1.x + c6[4] * M1.y + c6[5] * M1.z;
+        const float dM0x = 2.f * dLa * s0x + dLb * s1x, dM0y = 2.f * dLa * s0y + dLb * s1y, dM0z = 2.f * dLa * s0z + dLb * s1z;
+        const float dM1x = dLb * s0x + 2.f * dLc * s1x, dM1y = dLb * s0y + 2.f * dLc * s1y, dM1z = dLb * s0z + 2.f * dLc * s1z;
+        const float dJ00 = dM0x * V[0] + dM0y * V[4] + dM0z * V[8];
+        const float dJ02 = dM0x * V[2] + dM0y * V[6] + dM0z * V[10];
+        const float dJ11 = dM1x * V[1] + dM1y * V[5] + dM1z * V[9];
+        const float dJ12 = dM1x * V[2] + dM1y * V[6] + dM1z * V[10];
+        const float tzi = 1.f / pr.t.z, tz2 = tzi * tzi, tz3 = tz2 * tzi;
+        const float dtx = pr.xin ? -pr.fx * tz2 * dJ02 : 0.f;
+        const float dty = pr.yin ? -pr.fy * tz2 * dJ12 : 0.f;
+        const float dtz = -pr.fx * tz2 * dJ00 - pr.fy * tz2 * dJ11 + 2.f * pr.fx * pr.tx * tz3 * dJ02 +
+                          2.f * pr.fy * pr.ty * tz3 * dJ12;
+#pragma unroll
+        for (int k = 0; k < 3; k++) dmean[k] = V[k * 4] * dtx + V[k * 4 + 1] * dty + V[k * 4 + 2] * dtz;
+        // (2) NDC mean -> mean3D
+        const float h0 = p.x * PM[0] + p.y * PM[4] + p.z * PM[8] + PM[12];
+        const float h1 = p.x * PM[1] + p.y * PM[5] + p.z * PM[9] + PM[13];
+        const float h3 = p.x * PM[3] + p.y * PM[7] + p.z * PM[11] + PM[15];
+        const float pw = 1.f / (h3 + 1e-7f);
+        const float mx = h0 * pw * pw, my = h1 * pw * pw;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            dmean[k] += dm2x * (PM[k * 4] * pw - mx * PM[k * 4 + 3]) + dm2y * (PM[k * 4 + 1] * pw - my * PM[k * 4 + 3]);
+        // (3) depth -> mean3D
+        const float dd = A.a1.z;
+#pragma unroll
+        for (int k = 0; k < 3; k++) dmean[k] += V[k * 4 + 2] * dd;
+        // (4) colour
+        const float gr = (flags & 1u) ? 0.f : A.a2.x;
+        const float gg = (flags & 2u) ? 0.f : A.a2.y;
+        const float gb = (flags & 4u) ? 0.f : A.a2.z;
+        if (use_sh) {
+            float3 d = make_float3(p.x - cam.cam[0], p.y - cam.cam[1], p.z - cam.cam[2]);
+            const float inv = 1.f / sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+            d.x *= inv; d.y *= inv; d.z *= inv;
+            const int D = v.sh_degree;
+            const int nk = (D + 1) * (D + 1);
+            float bb[16], bx[16], by[16], bz[16];
+            sh_basis(D, d, bb);
+            sh_basis_grad(D, d, bx, by, bz);
+            float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+            if (SH_FAST) {
+                // in place: this thread's staged input row becomes its gradient row
+                float4* row = s_sh + threadIdx.x * SH_ROW_F4_PAD;
+                const float gch[3] = {gr, gg, gb};
+#pragma unroll
+                for (int cc = 0; cc < SH_ROW_F4; cc++) {
+                    const float4 qq = row[cc];
+                    const float in[4] = {qq.x, qq.y, qq.z, qq.w};
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int k = (4 * cc + e) / 3, c = (4 * cc + e) - 3 * k;   // compile-time
+                        if (k < nk) {
+                            o[e] = bb[k] * gch[c];
+                            const float w = gch[c] * in[e];
+                            ddx += bx[k] * w; ddy += by[k] * w; ddz += bz[k] * w;
+                        } else {
+                            o[e] = 0.f;
+                        }
+                    }
+                    row[cc] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            } else {
+                const float* row = g.shs + (size_t)i * g.sh_coeffs * 3;
+                float* orow = out.dL_dshs + (size_t)i * g.sh_coeffs * 3;
+                for (int k = 0; k < g.sh_coeffs; k++) {
+                    if (k < nk) {
+                        orow[3 * k] = bb[k] * gr; orow[3 * k + 1] = bb[k] * gg; orow[3 * k + 2] = bb[k] * gb;
+                        const float w = gr * __ldg(row + 3 * k) + gg * __ldg(row + 3 * k + 1) + gb * __ldg(row + 3 * k + 2);
+                        ddx += bx[k] * w; ddy += by[k] * w; ddz += bz[k] * w;
+                    } else {
+                        orow[3 * k] = 0.f; orow[3 * k + 1] = 0.f; orow[3 * k + 2] = 0.f;
+                    }
+                }
+            }
+            const float dot = d.x * ddx + d.y * ddy + d.z * ddz;   // through dir = v / |v|
+            dmean[0] += (ddx - d.x * dot) * inv;
+            dmean[1] += (ddy - d.y * dot) * inv;
+            dmean[2] += (ddz - d.z * dot) * inv;
+        } else {
+            dcol[0] = A.a2.x; dcol[1] = A.a2.y; dcol[2] = A.a2.z;
+        }
+        // (5) Sigma -> scale, rotation
+        if (!g.cov3D_precomp) {
+            float R[9];
+            quat_to_R(q, R);
+            const float mod = v.scale_modifier;
+            const float sp[3] = {mod * sc.x, mod * sc.y, mod * sc.z};
+            const float Sg[9] = {2.f * d6[0], d6[1], d6[2], d6[1], 2.f * d6[3], d6[4], d6[2], d6[4], 2.f * d6[5]};
+            float Lm[9], dLm[9], Dm[9];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) Lm[r * 3 + j] = R[r * 3 + j] * sp[j];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+                    dLm[r * 3 + j] = Sg[r * 3] * Lm[j] + Sg[r * 3 + 1] * Lm[3 + j] + Sg[r * 3 + 2] * Lm[6 + j];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                dscale[j] = mod * (dLm[j] * R[j] + dLm[3 + j] * R[3 + j] + dLm[6 + j] * R[6 + j]);
+#pragma unroll
+                for (int r = 0; r < 3; r++) Dm[r * 3 + j] = dLm[r * 3 + j] * sp[j];
+            }
+            const float r = q.x, x = q.y, y = q.z, z = q.w;
+            drot[0] = 2.f * (-z * Dm[1] + y * Dm[2] + z * Dm[3] - x * Dm[5] - y * Dm[6] + x * Dm[7]);
+            drot[1] = 2.f * (y * Dm[1] + z * Dm[2] + y * Dm[3] - 2.f * x * Dm[4] - r * Dm[5] + z * Dm[6] + r * Dm[7] - 2.f * x * Dm[8]);
+            drot[2] = 2.f * (-2.f * y * Dm[0] + x * Dm[1] + r * Dm[2] + x * Dm[3] + z * Dm[5] - r * Dm[6] + z * Dm[7] - 2.f * y * Dm[8]);
+            drot[3] = 2.f * (-2.f * z * Dm[0] - r * Dm[1] + x * Dm[2] + r * Dm[3] - 2.f * z * Dm[4] + y * Dm[5] + x * Dm[6] + y * Dm[7]);
+        }
+    } else if (i < P && use_sh) {
+        if (SH_FAST) {
+            float4* row = s_sh + threadIdx.x * SH_ROW_F4_PAD;
+#pragma unroll
+            for (int cc = 0; cc < SH_ROW_F4; cc++) row[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            float* orow = out.dL_dshs + (size_t)i * g.sh_coeffs * 3;
+            for (int k = 0; k < 3 * g.sh_coeffs; k++) orow[k] = 0.f;
+        }
+    }
+
+    if (i < P) {
+        out.dL_dmeans3D[3 * (size_t)i] = dmean[0]; out.dL_dmeans3D[3 * (size_t)i + 1] = dmean[1]; out.dL_dmeans3D[3 * (size_t)i + 2] = dmean[2];
+        out.dL_dmeans2D[3 * (size_t)i] = dm2x; out.dL_dmeans2D[3 * (size_t)i + 1] = dm2y; out.dL_dmeans2D[3 * (size_t)i + 2] = 0.f;
+        out.dL_dopacities[i] = dop;
+        if (out.dL_dcolors_precomp) {
+            out.dL_dcolors_precomp[3 * (size_t)i] = dcol[0]; out.dL_dcolors_precomp[3 * (size_t)i + 1] = dcol[1]; out.dL_dcolors_precomp[3 * (size_t)i + 2] = dcol[2];
+        }
+        if (out.dL_dscales) {
+            out.dL_dscales[3 * (size_t)i] = dscale[0]; out.dL_dscales[3 * (size_t)i + 1] = dscale[1]; out.dL_dscales[3 * (size_t)i + 2] = dscale[2];
+        }
+        if (out.dL_drotations)
+            reinterpret_cast<float4*>(out.dL_drotations)[i] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+        if (out.dL_dcov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) out.dL_dcov3D_precomp[6 * (size_t)i + k] = d6[k];
+        }
+    }
+    if (SH_FAST && use_sh) {
+        // the 192-byte gradient rows sit in smem (written in place above): stream them out
+        // fully coalesced
+        __syncthreads();
+        float4* dst = reinterpret_cast<float4*>(out.dL_dshs) + (size_t)row0 * SH_ROW_F4;
+        const int nf4 = nrows * SH_ROW_F4;
+        for (int f = threadIdx.x; f < nf4; f += PRE_THREADS) {
+            const int r = f / SH_ROW_F4, c = f - r * SH_ROW_F4;
+            dst[f] = s_sh[r * SH_ROW_F4_PAD + c];
+        }
+    }
+}
+
+__global__ void mark_visible_kernel(const float* __restrict__ means3D, int P, const float* __restrict__ V,
+                                    uint8_t* __restrict__ present) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float3 p = load3(means3D, i);
+    const float zv = p.x * __ldg(V + 2) + p.y * __ldg(V + 6) + p.z * __ldg(V + 10) + __ldg(V + 14);
+    present[i] = zv > NEAR_Z ? 1 : 0;
+}
+
+inline bool sh_fast_ok(const ScgrGaussians& g, const void* dsh) {
+    return g.shs != nullptr && g.sh_coeffs == 16 && (reinterpret_cast<uintptr_t>(g.shs) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(dsh) & 15) == 0;
+}
+
+}  // namespace
+
+void launch_preprocess_forward(const ScgrView& v, const ScgrGaussians& g, const GeometryLayout& G,
+                               int32_t* radii, const Launch& L) {
+    if (g.P <= 0) return;
+    const int blocks = (g.P + PRE_THREADS - 1) / PRE_THREADS;
+    begin_kernel("preprocess_forward", L);
+    if (sh_fast_ok(g, nullptr))
+        preprocess_forward_kernel<true><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.depth_key, G.tiles_touched, G.rect, G.sort_vals[0], radii);
+    else
+        preprocess_forward_kernel<false><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.depth_key, G.tiles_touched, G.rect, G.sort_vals[0], radii);
+    check_launch("preprocess_forward", L);
+}
+
+void launch_preprocess_backward(const ScgrView& v, const ScgrGaussians& g, const GeometryLayout& G,
+                                const ScgrGrads& out, const Launch& L) {
+    if (g.P <= 0) return;
+    const int blocks = (g.P + PRE_THREADS - 1) / PRE_THREADS;
+    begin_kernel("preprocess_backward", L);
+    if (sh_fast_ok(g, out.dL_dshs))
+        preprocess_backward_kernel<true><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+    else
+        preprocess_backward_kernel<false><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+    check_launch("preprocess_backward", L);
+}
+
+void launch_mark_visible(const float* means3D, int32_t P, const float* viewmatrix, uint8_t* present,
+                         const Launch& L) {
+    if (P <= 0) return;
+    begin_kernel("mark_visible", L);
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, L.stream>>>(means3D, P, viewmatrix, present);
+    check_launch("mark_visible", L);
+}
+
+}  // namespace scgr

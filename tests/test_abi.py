@@ -1,0 +1,120 @@
+"""CPU tests of the drop-in boundary: libscgr.so loads without a GPU, exports every symbol that
+include/scgr.h declares, sizes its scratch sanely and reports argument errors through the C ABI
+(status + scgr_last_error) -- no compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from scgaussian_b200 import _lib
+from scgaussian_b200._lib import ScgrGaussians, ScgrGrads, ScgrView
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "scgr.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(scgr_[a-z_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    lib = _lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 10
+    for s in syms:
+        assert hasattr(lib, s), f"libscgr.so does not export {s}"
+        assert s in _lib.SYMBOLS, f"python binding misses {s}"
+    assert sorted(_lib.SYMBOLS) == syms
+
+
+def test_version_and_scratch_sizes():
+    lib = _lib.load()
+    assert lib.scgr_version() == 100
+    g1, g2 = lib.scgr_geometry_bytes(1000), lib.scgr_geometry_bytes(1_000_000)
+    assert 0 < g1 < g2 and g2 % 256 == 0
+    # per-Gaussian footprint stays well under the reference's own geomBuffer + our gradient staging
+    assert g2 / 1e6 < 160
+    b = lib.scgr_binning_bytes(1_000_000, 1920, 1080, 10_000_000)
+    assert 16 * 10_000_000 <= b < 20 * 10_000_000          # two ping-pong (key, value) arrays
+    assert lib.scgr_image_bytes(1920, 1080) >= 8 * 1920 * 1080
+    assert lib.scgr_geometry_bytes(0) > 0 and lib.scgr_binning_bytes(0, 0, 0, 0) > 0
+
+
+def _view(**kw):
+    d = dict(image_height=32, image_width=32, tanfovx=0.5, tanfovy=0.5, bg=1, scale_modifier=1.0,
+             viewmatrix=1, projmatrix=1, sh_degree=0, campos=1, prefiltered=0, debug=0)
+    d.update(kw)
+    return ScgrView(**d)
+
+
+def test_argument_errors_come_back_through_the_c_abi():
+    lib = _lib.load()
+    v = _view()
+    # both colour sources given
+    g = ScgrGaussians(P=4, sh_coeffs=1, means3D=256, opacities=256, shs=256, colors_precomp=256,
+                      scales=256, rotations=256, cov3D_precomp=None)
+    rc = lib.scgr_forward_geometry(C.byref(v), C.byref(g), 256, 256, None, None)
+    assert rc != 0 and b"exactly one of shs / colors_precomp" in lib.scgr_last_error()
+    # neither covariance source
+    g = ScgrGaussians(P=4, sh_coeffs=1, means3D=256, opacities=256, shs=256, colors_precomp=None,
+                      scales=None, rotations=None, cov3D_precomp=None)
+    rc = lib.scgr_forward_geometry(C.byref(v), C.byref(g), 256, 256, None, None)
+    assert rc != 0 and b"cov3D_precomp" in lib.scgr_last_error()
+    # sh degree out of range / too few coefficients
+    g = ScgrGaussians(P=4, sh_coeffs=4, means3D=256, opacities=256, shs=256, colors_precomp=None,
+                      scales=256, rotations=256, cov3D_precomp=None)
+    rc = lib.scgr_forward_geometry(C.byref(_view(sh_degree=3)), C.byref(g), 256, 256, None, None)
+    assert rc != 0 and b"too few coefficients" in lib.scgr_last_error()
+    # unaligned scratch
+    g = ScgrGaussians(P=4, sh_coeffs=1, means3D=256, opacities=256, shs=256, colors_precomp=None,
+                      scales=256, rotations=256, cov3D_precomp=None)
+    rc = lib.scgr_forward_geometry(C.byref(v), C.byref(g), 260, 256, None, None)
+    assert rc != 0 and b"256-byte aligned" in lib.scgr_last_error()
+    # backward: gradient set must mirror the inputs
+    gr = ScgrGrads(256, 256, None, None, 256, 256, 256, None)
+    rc = lib.scgr_backward(C.byref(v), C.byref(g), 256, 256, 0, 256, 256, 256, 256, C.byref(gr), None)
+    assert rc != 0 and b"dL_dshs must match shs" in lib.scgr_last_error()
+    # null pointers
+    assert lib.scgr_mark_visible(None, 3, None, None, None) != 0
+
+
+def test_host_api_mirrors_reference_operator_surface():
+    import diff_gaussian_rasterization as D
+    from scgaussian_b200 import GaussianRasterizationSettings, GaussianRasterizer, ScgrError
+    assert D.GaussianRasterizer is GaussianRasterizer
+    # the 12 keyword fields of reference gaussian_renderer/__init__.py:38-51
+    s = GaussianRasterizationSettings(image_height=8, image_width=8, tanfovx=0.5, tanfovy=0.5,
+                                      bg=torch.zeros(3), scale_modifier=1.0, viewmatrix=torch.eye(4),
+                                      projmatrix=torch.eye(4), sh_degree=0, campos=torch.zeros(3),
+                                      prefiltered=False, debug=False)
+    r = GaussianRasterizer(raster_settings=s)
+    m3, m2, op = torch.zeros(5, 3), torch.zeros(5, 3), torch.ones(5, 1)
+    sh, col = torch.zeros(5, 1, 3), torch.zeros(5, 3)
+    sc, rot, cov = torch.ones(5, 3), torch.zeros(5, 4), torch.zeros(5, 6)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(means3D=m3, means2D=m2, opacities=op, scales=sc, rotations=rot)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(means3D=m3, means2D=m2, opacities=op, shs=sh, colors_precomp=col, scales=sc, rotations=rot)
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=m3, means2D=m2, opacities=op, shs=sh)
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=m3, means2D=m2, opacities=op, shs=sh, scales=sc, rotations=rot, cov3D_precomp=cov)
+    # no CPU path, ever: CPU tensors fail loudly instead of falling back
+    with pytest.raises(ScgrError, match="CUDA"):
+        r(means3D=m3, means2D=m2, opacities=op, shs=sh, scales=sc, rotations=rot)
+    with pytest.raises(ScgrError, match="CUDA"):
+        r.markVisible(m3)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "scgaussian_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower().replace("# no oracle", ""), f"{f} mentions the oracle"
+    txt = open(os.path.join(ROOT, "diff_gaussian_rasterization", "__init__.py")).read()
+    assert "oracle" not in txt
