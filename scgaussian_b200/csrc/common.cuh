@@ -18,17 +18,18 @@ constexpr float DILATION = 0.3f;            // A.4
 constexpr uint32_t CULLED_KEY = 0xFFFFFFFFu;
 
 // ---- per-Gaussian record written by preprocess, gathered by render (48 B, 3 x 16-B loads) ----
-//   q0 = {mean_x, mean_y, conic_A, conic_B}
-//   q1 = {conic_C, opacity, depth, flags}      flags: bit0..2 = SH colour clamped (r,g,b)
-//   q2 = {r, g, b, radius (as float)}
+//   q0 = {mean_x, mean_y, cA, cB}      cA = -0.5 log2e A, cB = -log2e B, cC = -0.5 log2e C  (A,B,C = conic)
+//   q1 = {cC, opacity, depth, pmin2}   so that G = exp2(cA dx^2 + cB dx dy + cC dy^2); pmin2 = -log2(255 opacity)
+//   q2 = {r, g, b, bits}               bits (uint32) = radius | flags << 28; flags bit0..2 = SH colour clamped
 struct __align__(16) Record {
     float4 q0, q1, q2;
 };
 static_assert(sizeof(Record) == 48, "Record must be 48 bytes");
 
 // ---- per-Gaussian screen-space gradient accumulator written by render-backward (48 B) ----
-//   a0 = {dL/dmean_x (pixel units), dL/dmean_y, dL/dconic_A, dL/dconic_B (true derivative)}
-//   a1 = {dL/dconic_C, dL/dopacity, dL/ddepth, 0}
+// raw sums over (pixel, Gaussian) pairs; preprocess-backward applies the constant factors:
+//   a0 = {Sx, Sy, SA, SB}     dL/dmean_xy (pixels) = ln2 * S{x,y};  dL/dconic_{A,B} = {-0.5 SA, -SB}
+//   a1 = {SC, dL/dopacity, dL/ddepth, 0}     dL/dconic_C = -0.5 SC   (dL/dconic_B is the true derivative)
 //   a2 = {dL/dr, dL/dg, dL/db, 0}
 struct __align__(16) ScreenGrad {
     float4 a0, a1, a2;

@@ -241,7 +241,7 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
         tiles_touched[i] = 0;
         depth_key[i] = CULLED_KEY;
         rect[i] = make_uint2(0u, 0u);
-        rec[i].q2 = make_float4(0.f, 0.f, 0.f, 0.f);   // radius 0 marks "culled" for the backward
+        rec[i].q2 = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));   // radius 0 marks "culled" for the backward
         return;
     }
 
@@ -284,10 +284,14 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
     }
 
     const float dinv = 1.f / det;
+    const float opac = __ldg(g.opacities + i);
+    // render-ready conic: power2 = cA dx^2 + cB dx dy + cC dy^2 = log2(e) * (-0.5 (A dx^2 + C dy^2) - B dx dy)
+    constexpr float LOG2E = 1.4426950408889634f;
     Record r;
-    r.q0 = make_float4(px, py, pr.c * dinv, -pr.b * dinv);
-    r.q1 = make_float4(pr.a * dinv, __ldg(g.opacities + i), zv, __uint_as_float(flags));
-    r.q2 = make_float4(rgb.x, rgb.y, rgb.z, (float)rad);
+    r.q0 = make_float4(px, py, -0.5f * LOG2E * (pr.c * dinv), LOG2E * (pr.b * dinv));
+    // q1.w: alpha >= 1/255  <=>  power2 >= -log2(255 * opacity)
+    r.q1 = make_float4(-0.5f * LOG2E * (pr.a * dinv), opac, zv, -log2f(255.f * opac));
+    r.q2 = make_float4(rgb.x, rgb.y, rgb.z, __uint_as_float((uint32_t)rad | (flags << 28)));
     rec[i] = r;
     radii[i] = rad;
     tiles_touched[i] = (uint32_t)((x1 - x0) * (y1 - y0));
@@ -327,20 +331,20 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     float dcol[3] = {0.f, 0.f, 0.f};
     bool live = false;
     if (i < P) {
-        const float4 q2 = rec[i].q2;
-        live = q2.w > 0.f;
+        live = (__float_as_uint(rec[i].q2.w) & 0x0FFFFFFFu) != 0u;
     }
     if (live) {
         Camera cam;
         load_camera(v, cam);
-        const float4 q1 = rec[i].q1;
-        const uint32_t flags = __float_as_uint(q1.w);
+        const uint32_t flags = __float_as_uint(rec[i].q2.w) >> 28;
         const ScreenGrad A = sg[i];
         const float3 p = load3(g.means3D, i);
         const float* V = cam.V;
         const float* PM = cam.PM;
-        dm2x = A.a0.x * (0.5f * v.image_width);    // NDC units (A.9)
-        dm2y = A.a0.y * (0.5f * v.image_height);
+        // render-backward stores raw sums (render.cu): scale them into true derivatives here
+        constexpr float LN2 = 0.6931471805599453f;
+        dm2x = LN2 * A.a0.x * (0.5f * v.image_width);    // NDC units (A.9)
+        dm2y = LN2 * A.a0.y * (0.5f * v.image_height);
         dop = A.a1.y;
         // (1) conic -> cov2D
         float c6[6];
@@ -359,7 +363,7 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
         const float a = pr.a, b = pr.b, c = pr.c;
         const float den = a * c - b * b;
         const float k2 = 1.f / (den * den + 1e-7f);
-        const float dA = A.a0.z, dB = A.a0.w, dC = A.a1.x;
+        const float dA = -0.5f * A.a0.z, dB = -A.a0.w, dC = -0.5f * A.a1.x;
         const float dLa = k2 * (-c * c * dA + b * c * dB - b * b * dC);
         const float dLb = k2 * (2.f * b * c * dA - (den + 2.f * b * b) * dB + 2.f * a * b * dC);
         const float dLc = k2 * (-b * b * dA + a * b * dB - a * a * dC);

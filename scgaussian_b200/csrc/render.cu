@@ -4,225 +4,343 @@
 // section 2c, section 8a rows a14/a15; semantics Appendix A.8 / A.9) behind
 // reference gaussian_renderer/__init__.py:100-108.
 //
-// One CTA per 16x16 tile, one thread per pixel; a warp owns an 8x4 pixel block (compact
-// footprint -> more warp-uniform skips than the reference's 16x2 rows).  The tile's depth-ordered
-// Gaussian list is consumed in batches of 256: each thread gathers ONE packed 48-byte record
-// {xy, conic, opacity, depth, rgb} with three 128-bit loads (the reference gathers five separate
-// arrays and re-reads colour/depth from global memory per pixel per Gaussian) into shared
-// memory, from where all 256 pixels read it by broadcast.
-//
-// Backward: the per-(pixel, Gaussian) gradients are reduced hierarchically -- warp shuffle
-// butterfly over the 32 pixels of a warp, shared-memory float atomics across the 8 warps of the
-// tile, then ONE set of three 128-bit vector reductions (red.global.add.v4.f32) per (Gaussian,
-// tile) -- instead of the reference's 10 global atomics per contributing pair.
+// Design (differs from the reference's one-thread-per-pixel, 256-thread CTA):
+//   * ONE WARP per 16x16 tile.  The tile is cut into 8 "slots" of 8x4 pixels; lane l owns pixel
+//     (l % 8, l / 8) of every slot, i.e. 8 pixels per thread held in registers.
+//   * The tile's depth-ordered list is consumed 32 Gaussians at a time: lane l gathers the packed
+//     48-byte record of the l-th one (3 x 128-bit loads; the NEXT batch is prefetched into
+//     registers while the current one is processed) and computes, for its Gaussian, an exact
+//     closed-form bound of the maximum of the Gaussian's exponent over each slot rectangle.
+//     Slots whose bound says alpha < 1/255 everywhere are skipped without touching a pixel
+//     (conservative: the per-pixel test that follows is the reference's, so no output changes).
+//   * Backward: every lane accumulates its 10 per-Gaussian gradient terms over its 8 pixels in
+//     registers; one 12-shuffle transposing butterfly per (tile, Gaussian) leaves each term summed
+//     over all 256 pixels in one lane, and those 10 lanes issue one coalesced `red.global.add.f32`
+//     -- instead of the reference's 10 global atomics per contributing (pixel, Gaussian) pair.
+//   * exp() is one MUFU.EX2: the conic is stored pre-multiplied by -0.5*log2(e).
+// No block-level barriers at all (a warp never waits for another); no tensor cores (blend is not a
+// contraction).
 #include "common.cuh"
 
 namespace scgr {
 
 namespace {
 
-constexpr int BATCH = 256;
+constexpr int SLOTS = 8;
+constexpr float PREFILTER_MARGIN = 0.02f;   // log2 units; keeps the slot bound conservative under fp32 rounding
 
-__device__ __forceinline__ void pixel_of_thread(int& lx, int& ly) {
-    // warp w covers the 8x4 block at (w%2 * 8, w/2 * 4); lane -> (lane%8, lane/8)
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    lx = ((w & 1) << 3) + (lane & 7);
-    ly = ((w >> 1) << 2) + (lane >> 3);
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
-__global__ void __launch_bounds__(TILE_PIX)
+// Maximum over the pixel rectangle [x0, x1] x [y0, y1] of
+//   p2(d) = cA dx^2 + cB dx dy + cC dy^2,  d = mean - pixel   (negative definite, max 0 at d = 0).
+// The maximiser of a concave function whose global maximum lies outside the box is on one of the
+// two faces that look at the origin; each face is a 1-D concave parabola.
+__device__ __forceinline__ float max_power_over_rect(const float cA, const float cB, const float cC,
+                                                     const float kx, const float ky, const float mx,
+                                                     const float my, const float x0, const float x1,
+                                                     const float y0, const float y1) {
+    const float dxl = mx - x1, dxh = mx - x0, dyl = my - y1, dyh = my - y0;
+    const float cx = fminf(fmaxf(0.f, dxl), dxh);
+    const float cy = fminf(fmaxf(0.f, dyl), dyh);
+    const float dy1 = fminf(fmaxf(ky * cx, dyl), dyh);   // face dx = cx
+    const float f1 = cx * (cA * cx + cB * dy1) + cC * dy1 * dy1;
+    const float dx2 = fminf(fmaxf(kx * cy, dxl), dxh);   // face dy = cy
+    const float f2 = dx2 * (cA * dx2 + cB * cy) + cC * cy * cy;
+    return fmaxf(f1, f2);
+}
+
+struct Rec {
+    float4 q0, q1, q2;
+};
+
+__device__ __forceinline__ Rec load_rec(const Record* __restrict__ rec, uint32_t id) {
+    const float4* p = reinterpret_cast<const float4*>(rec + id);
+    Rec r;
+    r.q0 = __ldg(p);
+    r.q1 = __ldg(p + 1);
+    r.q2 = __ldg(p + 2);
+    return r;
+}
+
+// slot mask of one Gaussian: bit k set <=> slot k may receive a contribution
+__device__ __forceinline__ uint32_t slot_mask(const Rec& r, const float X0, const float Y0, const uint32_t live_slots) {
+    const float cA = r.q0.z, cB = r.q0.w, cC = r.q1.x;
+    const float kx = -cB / (2.f * cA), ky = -cB / (2.f * cC);
+    const float thr = r.q1.w - PREFILTER_MARGIN;
+    uint32_t m = 0u;
+#pragma unroll
+    for (int k = 0; k < SLOTS; k++) {
+        const float x0 = X0 + (float)((k & 1) << 3), y0 = Y0 + (float)((k >> 1) << 2);
+        const float mp = max_power_over_rect(cA, cB, cC, kx, ky, r.q0.x, r.q0.y, x0, x0 + 7.f, y0, y0 + 3.f);
+        if (mp >= thr) m |= 1u << k;
+    }
+    return m & live_slots;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward (A.8)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
 render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                       const Record* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                       const int64_t* __restrict__ status, int64_t capacity, float* __restrict__ out_color,
                       float* __restrict__ out_depth, float* __restrict__ out_alpha,
                       uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
-    __shared__ float4 s_q0[BATCH], s_q1[BATCH], s_q2[BATCH];
+    __shared__ float4 s_q0[32], s_q1[32], s_q2[32];
     if (status[0] > capacity) return;   // binning overflowed: caller re-runs with a larger buffer
-    int lx, ly;
-    pixel_of_thread(lx, ly);
-    const int px = blockIdx.x * TILE + lx, py = blockIdx.y * TILE + ly;
-    const bool inside = px < W && py < H;
-    const float pxf = (float)px, pyf = (float)py;
+    const int lane = threadIdx.x;
+    const int lx = lane & 7, ly = lane >> 3;
+    const int X0 = blockIdx.x * TILE, Y0 = blockIdx.y * TILE;
     const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
     const int total = (int)(range.y - range.x);
 
-    bool done = !inside;
-    float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Dsum = 0.f, Wsum = 0.f;
-    uint32_t last = 0u;
+    float T[SLOTS], Cr[SLOTS], Cg[SLOTS], Cb[SLOTS], Dd[SLOTS];
+    uint32_t last[SLOTS];
+    uint32_t done = 0u;    // bit k: this lane's pixel of slot k is finished
+#pragma unroll
+    for (int k = 0; k < SLOTS; k++) {
+        T[k] = 1.f; Cr[k] = 0.f; Cg[k] = 0.f; Cb[k] = 0.f; Dd[k] = 0.f; last[k] = 0u;
+        const int px = X0 + ((k & 1) << 3) + lx, py = Y0 + ((k >> 1) << 2) + ly;
+        if (px >= W || py >= H) done |= 1u << k;
+    }
+    const float pxf = (float)(X0 + lx), pyf = (float)(Y0 + ly);
 
-    for (int base = 0; base < total; base += BATCH) {
-        if (__syncthreads_count(done) == TILE_PIX) break;
-        const int cnt = min(BATCH, total - base);
-        if ((int)threadIdx.x < cnt) {
-            const uint32_t id = point_list[range.x + base + threadIdx.x];
-            const Record* r = rec + id;
-            s_q0[threadIdx.x] = r->q0;
-            s_q1[threadIdx.x] = r->q1;
-            s_q2[threadIdx.x] = r->q2;
-        }
-        __syncthreads();
+    Rec nxt;
+    nxt.q0 = nxt.q1 = nxt.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < total) nxt = load_rec(rec, point_list[range.x + lane]);
+
+    for (int base = 0; base < total; base += 32) {
+        // slots in which some pixel is still open
+        uint32_t live = 0u;
+#pragma unroll
+        for (int k = 0; k < SLOTS; k++)
+            if (!__all_sync(0xffffffffu, (done >> k) & 1u)) live |= 1u << k;
+        if (live == 0u) break;
+        const int cnt = min(32, total - base);
+        const Rec cur = nxt;
+        __syncwarp();
+        s_q0[lane] = cur.q0; s_q1[lane] = cur.q1; s_q2[lane] = cur.q2;
+        __syncwarp();
+        if (base + 32 + lane < total) nxt = load_rec(rec, point_list[range.x + base + 32 + lane]);
+        const uint32_t mymask = lane < cnt ? slot_mask(cur, (float)X0, (float)Y0, live) : 0u;
+
         for (int j = 0; j < cnt; j++) {
-            if (__all_sync(0xffffffffu, done)) break;
+            const uint32_t mj = __shfl_sync(0xffffffffu, mymask, j);
+            if (mj == 0u) continue;
             const float4 q0 = s_q0[j];
             const float4 q1 = s_q1[j];
-            const float dx = q0.x - pxf, dy = q0.y - pyf;
-            const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
-            const float alpha = fminf(ALPHA_MAX, q1.y * __expf(power));
-            if (done || power > 0.f || alpha < ALPHA_MIN) continue;
-            const float test_T = T * (1.f - alpha);
-            if (test_T < T_EPS) { done = true; continue; }
             const float4 q2 = s_q2[j];
-            const float w = alpha * T;
-            Cr += q2.x * w; Cg += q2.y * w; Cb += q2.z * w;
-            Dsum += q1.z * w;
-            Wsum += w;
-            T = test_T;
-            last = (uint32_t)(base + j + 1);
+            const float dx0 = q0.x - pxf, dy0 = q0.y - pyf;
+#pragma unroll
+            for (int k = 0; k < SLOTS; k++) {
+                if (!(mj & (1u << k))) continue;      // warp-uniform
+                const float dx = dx0 - (float)((k & 1) << 3), dy = dy0 - (float)((k >> 1) << 2);
+                const float power = dx * (q0.z * dx + q0.w * dy) + q1.x * dy * dy;
+                if (((done >> k) & 1u) || power > 0.f || power < q1.w - PREFILTER_MARGIN) continue;
+                const float alpha = fminf(ALPHA_MAX, q1.y * ex2(power));
+                if (alpha < ALPHA_MIN) continue;
+                const float test_T = T[k] * (1.f - alpha);
+                if (test_T < T_EPS) { done |= 1u << k; continue; }
+                const float w = alpha * T[k];
+                Cr[k] += q2.x * w; Cg[k] += q2.y * w; Cb[k] += q2.z * w;
+                Dd[k] += q1.z * w;
+                T[k] = test_T;
+                last[k] = (uint32_t)(base + j + 1);
+            }
         }
     }
-    if (inside) {
-        const size_t pid = (size_t)py * W + px, N = (size_t)W * H;
-        out_color[pid] = Cr + T * __ldg(bg);
-        out_color[N + pid] = Cg + T * __ldg(bg + 1);
-        out_color[2 * N + pid] = Cb + T * __ldg(bg + 2);
-        out_depth[pid] = Dsum;
-        out_alpha[pid] = Wsum;
-        n_contrib[pid] = last;
-        final_T[pid] = T;
+    const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
+    const size_t N = (size_t)W * H;
+#pragma unroll
+    for (int k = 0; k < SLOTS; k++) {
+        const int px = X0 + ((k & 1) << 3) + lx, py = Y0 + ((k >> 1) << 2) + ly;
+        if (px < W && py < H) {
+            const size_t pid = (size_t)py * W + px;
+            out_color[pid] = Cr[k] + T[k] * bg0;
+            out_color[N + pid] = Cg[k] + T[k] * bg1;
+            out_color[2 * N + pid] = Cb[k] + T[k] * bg2;
+            out_depth[pid] = Dd[k];
+            out_alpha[pid] = 1.f - T[k];      // == sum alpha_i T_i (telescoping), A.8
+            n_contrib[pid] = last[k];
+            final_T[pid] = T[k];
+        }
     }
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
+// ------------------------------------------------------------------------------------------
+// backward (A.9)
+// ------------------------------------------------------------------------------------------
+// 10 per-lane partial sums -> lane (h, b8, b4, b2, 0) ends up holding the full 32-lane sum of ONE
+// of them.  12 shuffles instead of 50.  Returns the value; `*slot` = float offset inside ScreenGrad
+// (or -1 if this lane holds nothing).
+__device__ __forceinline__ float transpose_reduce10(const float v[10], const int lane, int* slot) {
+    const bool h = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
+    float a[5];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    for (int i = 0; i < 5; i++) {
+        const float keep = h ? v[5 + i] : v[i];
+        const float send = h ? v[i] : v[5 + i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    float b[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float up = i < 2 ? a[3 + i] : 0.f;
+        const float keep = b8 ? up : a[i];
+        const float send = b8 ? a[i] : up;
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    float c[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const float up = i < 1 ? b[2] : 0.f;
+        const float keep = b4 ? up : b[i];
+        const float send = b4 ? b[i] : up;
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const float keep = b2 ? c[1] : c[0];
+    const float send = b2 ? c[0] : c[1];
+    float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    // which of the 10 values does this lane hold?
+    int idx = -1;
+    if (!(lane & 1)) {
+        if (!b8) idx = b4 ? (b2 ? -1 : 2) : (b2 ? 1 : 0);
+        else idx = b4 ? -1 : (b2 ? 4 : 3);
+        if (idx >= 0 && h) idx += 5;
+    }
+    // value order {mx, my, A, B, C, opacity, depth, r, g, b} -> ScreenGrad float offsets
+    *slot = idx < 0 ? -1 : (idx < 7 ? idx : idx + 1);
+    return d;
 }
 
-__global__ void __launch_bounds__(TILE_PIX)
+__global__ void __launch_bounds__(32)
 render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                        const Record* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                        const int64_t* __restrict__ status, int64_t capacity,
                        const uint32_t* __restrict__ n_contrib, const float* __restrict__ final_T,
                        const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
                        const float* __restrict__ dL_dalpha, ScreenGrad* __restrict__ screen_grad) {
-    __shared__ float4 s_q0[BATCH], s_q1[BATCH], s_q2[BATCH];
-    __shared__ uint32_t s_id[BATCH];
-    __shared__ float s_acc[10][BATCH];
-    __shared__ int s_max[TILE_PIX / 32];
+    __shared__ float4 s_q0[32], s_q1[32], s_q2[32];
+    __shared__ uint32_t s_id[32];
+    __shared__ float s_g[5][TILE_PIX];      // upstream gradients of the tile: r, g, b, depth, alpha
     if (status[0] > capacity) return;
-    int lx, ly;
-    pixel_of_thread(lx, ly);
-    const int px = blockIdx.x * TILE + lx, py = blockIdx.y * TILE + ly;
-    const bool inside = px < W && py < H;
-    const float pxf = (float)px, pyf = (float)py;
+    const int lane = threadIdx.x;
+    const int lx = lane & 7, ly = lane >> 3;
+    const int X0 = blockIdx.x * TILE, Y0 = blockIdx.y * TILE;
     const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
-    const int lane = threadIdx.x & 31;
+    const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
+    const size_t N = (size_t)W * H;
 
-    float T_final = 0.f, gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f;
-    int last_contributor = 0;
-    if (inside) {
-        const size_t pid = (size_t)py * W + px, N = (size_t)W * H;
-        T_final = final_T[pid];
-        last_contributor = (int)n_contrib[pid];
-        gr = dL_dcolor[pid]; gg = dL_dcolor[N + pid]; gb = dL_dcolor[2 * N + pid];
-        gd = dL_ddepth[pid];
-        ga = dL_dalpha[pid];
-    }
-    const float bgdot = __ldg(bg) * gr + __ldg(bg + 1) * gg + __ldg(bg + 2) * gb;
-
-    // nothing behind the deepest contributor of the whole tile matters
-    int m = last_contributor;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) s_max[threadIdx.x >> 5] = m;
-    __syncthreads();
+    float T[SLOTS], Ar[SLOTS], Ag[SLOTS], Ab[SLOTS], Ad[SLOTS], Aa[SLOTS], tfb[SLOTS];
+    int lc[SLOTS];
+    int slot_lc[SLOTS];
     int toDo = 0;
 #pragma unroll
-    for (int k = 0; k < TILE_PIX / 32; k++) toDo = max(toDo, s_max[k]);
-
-    float T = T_final;
-    float arec_r = 0.f, arec_g = 0.f, arec_b = 0.f, drec = 0.f, alrec = 0.f;
-    float last_alpha = 0.f, last_r = 0.f, last_g = 0.f, last_b = 0.f, last_d = 0.f;
-
-    for (int base = 0; base < toDo; base += BATCH) {
-        // batch entry j  <->  0-based list position  pos = toDo - 1 - (base + j)
-        const int cnt = min(BATCH, toDo - base);
-        if ((int)threadIdx.x < cnt) {
-            const uint32_t id = point_list[range.x + (toDo - 1 - (base + threadIdx.x))];
-            const Record* r = rec + id;
-            s_id[threadIdx.x] = id;
-            s_q0[threadIdx.x] = r->q0;
-            s_q1[threadIdx.x] = r->q1;
-            s_q2[threadIdx.x] = r->q2;
+    for (int k = 0; k < SLOTS; k++) {
+        const int px = X0 + ((k & 1) << 3) + lx, py = Y0 + ((k >> 1) << 2) + ly;
+        float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f, Tf = 0.f;
+        lc[k] = 0;
+        if (px < W && py < H) {
+            const size_t pid = (size_t)py * W + px;
+            Tf = final_T[pid];
+            lc[k] = (int)n_contrib[pid];
+            gr = dL_dcolor[pid]; gg = dL_dcolor[N + pid]; gb = dL_dcolor[2 * N + pid];
+            gd = dL_ddepth[pid];
+            ga = dL_dalpha[pid];
         }
+        s_g[0][k * 32 + lane] = gr; s_g[1][k * 32 + lane] = gg; s_g[2][k * 32 + lane] = gb;
+        s_g[3][k * 32 + lane] = gd; s_g[4][k * 32 + lane] = ga;
+        T[k] = Tf;
+        tfb[k] = -Tf * (bg0 * gr + bg1 * gg + bg2 * gb);
+        Ar[k] = 0.f; Ag[k] = 0.f; Ab[k] = 0.f; Ad[k] = 0.f; Aa[k] = 0.f;
+        slot_lc[k] = __reduce_max_sync(0xffffffffu, lc[k]);
+        toDo = max(toDo, slot_lc[k]);
+    }
+    const float pxf = (float)(X0 + lx), pyf = (float)(Y0 + ly);
+    // (each lane only ever reads back the s_g entries it wrote itself: no barrier needed)
+
+    // batch entry j  <->  0-based list position  pos = toDo - 1 - (base + j)   (back to front)
+    Rec nxt;
+    uint32_t nxt_id = 0u;
+    nxt.q0 = nxt.q1 = nxt.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < toDo) {
+        nxt_id = point_list[range.x + (toDo - 1 - lane)];
+        nxt = load_rec(rec, nxt_id);
+    }
+    for (int base = 0; base < toDo; base += 32) {
+        const int cnt = min(32, toDo - base);
+        const Rec cur = nxt;
+        __syncwarp();
+        s_q0[lane] = cur.q0; s_q1[lane] = cur.q1; s_q2[lane] = cur.q2; s_id[lane] = nxt_id;
+        __syncwarp();
+        if (base + 32 + lane < toDo) {
+            nxt_id = point_list[range.x + (toDo - 1 - (base + 32 + lane))];
+            nxt = load_rec(rec, nxt_id);
+        }
+        uint32_t mymask = 0u;
+        if (lane < cnt) {
+            const int mypos = toDo - 1 - (base + lane);
+            uint32_t live = 0u;
 #pragma unroll
-        for (int k = 0; k < 10; k++) s_acc[k][threadIdx.x] = 0.f;
-        __syncthreads();
+            for (int k = 0; k < SLOTS; k++)
+                if (mypos < slot_lc[k]) live |= 1u << k;
+            mymask = slot_mask(cur, (float)X0, (float)Y0, live);
+        }
         for (int j = 0; j < cnt; j++) {
+            const uint32_t mj = __shfl_sync(0xffffffffu, mymask, j);
+            if (mj == 0u) continue;
             const int pos = toDo - 1 - (base + j);
             const float4 q0 = s_q0[j];
             const float4 q1 = s_q1[j];
-            const float dx = q0.x - pxf, dy = q0.y - pyf;
-            const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
-            const float G = __expf(power);
-            const float alpha = fminf(ALPHA_MAX, q1.y * G);
-            const bool ok = (pos < last_contributor) && (power <= 0.f) && (alpha >= ALPHA_MIN);
-            if (!__any_sync(0xffffffffu, ok)) continue;
-            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f, v9 = 0.f;
-            if (ok) {
-                const float4 q2 = s_q2[j];
-                T = T / (1.f - alpha);
-                const float w = alpha * T;
-                float dL_dalpha_ = 0.f;
-                arec_r = last_alpha * last_r + (1.f - last_alpha) * arec_r; last_r = q2.x;
-                dL_dalpha_ += (q2.x - arec_r) * gr;
-                arec_g = last_alpha * last_g + (1.f - last_alpha) * arec_g; last_g = q2.y;
-                dL_dalpha_ += (q2.y - arec_g) * gg;
-                arec_b = last_alpha * last_b + (1.f - last_alpha) * arec_b; last_b = q2.z;
-                dL_dalpha_ += (q2.z - arec_b) * gb;
-                drec = last_alpha * last_d + (1.f - last_alpha) * drec; last_d = q1.z;
-                dL_dalpha_ += (q1.z - drec) * gd;
-                alrec = last_alpha + (1.f - last_alpha) * alrec;
-                dL_dalpha_ += (1.f - alrec) * ga;
-                dL_dalpha_ *= T;
-                last_alpha = alpha;
-                dL_dalpha_ += (-T_final / (1.f - alpha)) * bgdot;
-                const float dL_dG = q1.y * dL_dalpha_;   // propagated even when alpha was capped (A.9)
+            const float4 q2 = s_q2[j];
+            const float dx0 = q0.x - pxf, dy0 = q0.y - pyf;
+            float v[10];
+#pragma unroll
+            for (int i = 0; i < 10; i++) v[i] = 0.f;
+            bool touched = false;
+#pragma unroll
+            for (int k = 0; k < SLOTS; k++) {
+                if (!(mj & (1u << k))) continue;      // warp-uniform
+                const float dx = dx0 - (float)((k & 1) << 3), dy = dy0 - (float)((k >> 1) << 2);
+                const float power = dx * (q0.z * dx + q0.w * dy) + q1.x * dy * dy;
+                if (pos >= lc[k] || power > 0.f || power < q1.w - PREFILTER_MARGIN) continue;
+                const float G = ex2(power);
+                const float alpha = fminf(ALPHA_MAX, q1.y * G);
+                if (alpha < ALPHA_MIN) continue;
+                touched = true;
+                const float ra = 1.f / (1.f - alpha);
+                T[k] *= ra;                                  // transmittance in front of this Gaussian
+                const float gr = s_g[0][k * 32 + lane], gg = s_g[1][k * 32 + lane], gb = s_g[2][k * 32 + lane];
+                const float gd = s_g[3][k * 32 + lane], ga = s_g[4][k * 32 + lane];
+                // suffix-blended values behind this Gaussian: A* = alpha_{j+1} c_{j+1} + (1-alpha_{j+1}) A*
+                const float er = q2.x - Ar[k], eg = q2.y - Ag[k], eb = q2.z - Ab[k], ed = q1.z - Ad[k], ea = 1.f - Aa[k];
+                float dL_dalpha_ = er * gr + eg * gg + eb * gb + ed * gd + ea * ga;
+                Ar[k] += alpha * er; Ag[k] += alpha * eg; Ab[k] += alpha * eb; Ad[k] += alpha * ed; Aa[k] += alpha * ea;
+                dL_dalpha_ = dL_dalpha_ * T[k] + tfb[k] * ra;
+                const float w = alpha * T[k];
+                const float u = q1.y * dL_dalpha_;           // dL/dG, propagated even when alpha was capped (A.9)
                 const float gdx = G * dx, gdy = G * dy;
-                v0 = dL_dG * (-gdx * q0.z - gdy * q0.w);      // dL/dmean_x, pixel units
-                v1 = dL_dG * (-gdy * q1.x - gdx * q0.w);      // dL/dmean_y
-                v2 = -0.5f * gdx * dx * dL_dG;                // dL/dconic_A
-                v3 = -gdx * dy * dL_dG;                       // dL/dconic_B (true derivative)
-                v4 = -0.5f * gdy * dy * dL_dG;                // dL/dconic_C
-                v5 = G * dL_dalpha_;                          // dL/dopacity
-                v6 = w * gd;                                  // dL/ddepth
-                v7 = w * gr; v8 = w * gg; v9 = w * gb;        // dL/drgb
+                v[0] += u * (2.f * q0.z * gdx + q0.w * gdy);  // * ln2  = dL/dmean_x (pixel units)
+                v[1] += u * (2.f * q1.x * gdy + q0.w * gdx);  // * ln2  = dL/dmean_y
+                const float ux = u * gdx;
+                v[2] += ux * dx;                             // * -0.5 = dL/dconic_A
+                v[3] += ux * dy;                             // * -1   = dL/dconic_B
+                v[4] += u * gdy * dy;                        // * -0.5 = dL/dconic_C
+                v[5] += G * dL_dalpha_;                      // dL/dopacity
+                v[6] += w * gd;                              // dL/ddepth
+                v[7] += w * gr; v[8] += w * gg; v[9] += w * gb;
             }
-            v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3); v4 = warp_sum(v4);
-            v5 = warp_sum(v5); v6 = warp_sum(v6); v7 = warp_sum(v7); v8 = warp_sum(v8); v9 = warp_sum(v9);
-            if (lane == 0) {
-                atomicAdd(&s_acc[0][j], v0); atomicAdd(&s_acc[1][j], v1); atomicAdd(&s_acc[2][j], v2);
-                atomicAdd(&s_acc[3][j], v3); atomicAdd(&s_acc[4][j], v4); atomicAdd(&s_acc[5][j], v5);
-                atomicAdd(&s_acc[6][j], v6); atomicAdd(&s_acc[7][j], v7); atomicAdd(&s_acc[8][j], v8);
-                atomicAdd(&s_acc[9][j], v9);
-            }
+            if (!__any_sync(0xffffffffu, touched)) continue;
+            int slot;
+            const float sum = transpose_reduce10(v, lane, &slot);
+            if (slot >= 0 && sum != 0.f)
+                atomicAdd(reinterpret_cast<float*>(screen_grad + s_id[j]) + slot, sum);   // RED.E.ADD.F32
         }
-        __syncthreads();
-        if ((int)threadIdx.x < cnt) {
-            const int j = threadIdx.x;
-            const float4 a0 = make_float4(s_acc[0][j], s_acc[1][j], s_acc[2][j], s_acc[3][j]);
-            const float4 a1 = make_float4(s_acc[4][j], s_acc[5][j], s_acc[6][j], 0.f);
-            const float4 a2 = make_float4(s_acc[7][j], s_acc[8][j], s_acc[9][j], 0.f);
-            const bool any = a0.x != 0.f || a0.y != 0.f || a0.z != 0.f || a0.w != 0.f || a1.x != 0.f ||
-                             a1.y != 0.f || a1.z != 0.f || a2.x != 0.f || a2.y != 0.f || a2.z != 0.f;
-            if (any) {
-                ScreenGrad* dst = screen_grad + s_id[j];
-                atomicAdd(&dst->a0, a0);   // red.global.add.v4.f32 (sm_90+)
-                atomicAdd(&dst->a1, a1);
-                atomicAdd(&dst->a2, a2);
-            }
-        }
-        __syncthreads();
     }
 }
 
@@ -234,9 +352,9 @@ void launch_render_forward(const ScgrView& v, const GeometryLayout& G, const Bin
     const dim3 grid((v.image_width + TILE - 1) / TILE, (v.image_height + TILE - 1) / TILE);
     if (grid.x == 0 || grid.y == 0) return;
     begin_kernel("render_forward", L);
-    render_forward_kernel<<<grid, TILE_PIX, 0, L.stream>>>(B.ranges, point_list, G.rec, v.image_width,
-                                                           v.image_height, v.bg, G.status, capacity, out_color,
-                                                           out_depth, out_alpha, I.n_contrib, I.final_T);
+    render_forward_kernel<<<grid, 32, 0, L.stream>>>(B.ranges, point_list, G.rec, v.image_width,
+                                                     v.image_height, v.bg, G.status, capacity, out_color,
+                                                     out_depth, out_alpha, I.n_contrib, I.final_T);
     check_launch("render_forward", L);
 }
 
@@ -248,9 +366,9 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
     cudaMemsetAsync(G.screen_grad, 0, (size_t)(P > 0 ? P : 0) * sizeof(ScreenGrad), L.stream);
     if (grid.x == 0 || grid.y == 0) return;
     begin_kernel("render_backward", L);
-    render_backward_kernel<<<grid, TILE_PIX, 0, L.stream>>>(B.ranges, point_list, G.rec, v.image_width,
-                                                            v.image_height, v.bg, G.status, capacity, I.n_contrib,
-                                                            I.final_T, dL_dcolor, dL_ddepth, dL_dalpha, G.screen_grad);
+    render_backward_kernel<<<grid, 32, 0, L.stream>>>(B.ranges, point_list, G.rec, v.image_width,
+                                                      v.image_height, v.bg, G.status, capacity, I.n_contrib,
+                                                      I.final_T, dL_dcolor, dL_ddepth, dL_dalpha, G.screen_grad);
     check_launch("render_backward", L);
 }
 

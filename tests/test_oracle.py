@@ -187,3 +187,16 @@ def test_edge_cases_cpu():
     util.assert_image_close("ragged color", c2, ct.numpy())
     assert (np.abs(r2 - rt.numpy()) <= 1).all() and (r2 != rt.numpy()).mean() < 0.02
     assert math.isfinite(float(c2.sum()))
+
+
+def test_f32_f64_oracles_differ_only_by_isolated_flips():
+    """Documents why the GPU-vs-oracle gradient check allows a few outliers: the two builds of the
+    SAME C oracle differ by isolated discrete flips in fp32."""
+    case = util.make_case(5000, 378, 504, sh_degree=0, scale_median=0.03, w2c=O.yaw_w2c(5.0))
+    grads = O.synth_upstream_grads(378, 504)
+    _, _, g32 = util.run_c_oracle(case, "f32", grads=grads)
+    _, _, g64 = util.run_c_oracle(case, "f64", grads=grads)
+    for k in ("means3D", "means2D", "opacities", "shs", "scales", "rotations"):
+        util.assert_grad_close(k, g32[k], g64[k])
+        err = np.abs(g32[k] - g64[k]) / np.abs(g64[k]).max()
+        assert (err > 1e-4).mean() < 2e-3

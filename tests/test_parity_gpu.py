@@ -104,12 +104,15 @@ def test_forward_stages_match_oracle(dev):
     assert n_rad <= max(2, case["P"] // 2000) and np.abs(radii - r2).max() <= 1, n_rad
     both = vis & (radii > 0)
     e_xy = util.rel_err(rec[both][:, 0:2], st["means2D"][both])
-    e_conic = max(util.rel_err(rec[both][:, 2], st["conic"][both][:, 0]), util.rel_err(rec[both][:, 3], st["conic"][both][:, 1]),
-                  util.rel_err(rec[both][:, 4], st["conic"][both][:, 2]))
+    log2e = 1.4426950408889634       # record holds the render-ready conic (include/scgr.h)
+    e_conic = max(util.rel_err(rec[both][:, 2] / (-0.5 * log2e), st["conic"][both][:, 0]),
+                  util.rel_err(rec[both][:, 3] / -log2e, st["conic"][both][:, 1]),
+                  util.rel_err(rec[both][:, 4] / (-0.5 * log2e), st["conic"][both][:, 2]))
     e_rgb = util.rel_err(rec[both][:, 8:11], st["rgb"][both])
     e_depth = util.rel_err(rec[both][:, 6], st["depths"][both])
     assert np.array_equal(rec[both][:, 5], case["opacities"].numpy()[both, 0])
-    assert np.array_equal(rec[both][:, 11].astype(np.int32), radii[both])
+    bits = rec[:, 11].copy().view(np.uint32)
+    assert np.array_equal((bits & 0x0FFFFFFF).astype(np.int32)[both], radii[both])
     report("stages", radii_mismatch=n_rad, e_xy=e_xy, e_conic=e_conic, e_rgb=e_rgb, e_depth=e_depth,
            R_gpu=int(state.num_rendered), R_cpu=int(co.num_rendered))
     assert e_xy < 1e-5 and e_conic < 1e-4 and e_rgb < 1e-5 and e_depth < 1e-6
@@ -252,11 +255,12 @@ def test_alpha_cap_equal_depth_and_saturation(dev):
     (c, r, d, a), g = gpu_forward_backward(case, dev, grads)
     co, (c2, r2, d2, a2), g2 = util.run_c_oracle(case, "f64", grads=grads)
     st = co.state()
-    assert st["n_contrib"].max() < P                   # saturation really happened
+    nc = st["n_contrib"]
+    assert (a2 > 0.9998).any() and (nc[a2[0] > 0.9998] < P).any()   # saturation (early stop) really happened
     util.assert_image_close("color", c, c2)
     util.assert_image_close("alpha", a, a2)
     for k in ("means3D", "opacities", "shs", "scales", "rotations"):
-        util.assert_grad_close(k, g[k], g2[k].reshape(g[k].shape), rtol=2e-3)
+        util.assert_grad_close(k, g[k], g2[k].reshape(g[k].shape), flip_frac=5e-3)
 
 
 def test_mark_visible(dev):

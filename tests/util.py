@@ -1,6 +1,8 @@
 """Shared helpers of the parity tests: scene construction, oracle front-ends, tolerant compares."""
 from __future__ import annotations
 
+import math
+
 import numpy as np
 import torch
 
@@ -77,7 +79,20 @@ def assert_image_close(name, got, want, rtol=RTOL_IMAGE, flip_frac=2e-4, flip_at
     return float(err.max()), float(frac)
 
 
-def assert_grad_close(name, got, want, rtol=RTOL_GRAD):
-    e = rel_err(got, want)
-    assert e <= rtol, f"{name}: rel err {e:.3e} > {rtol}"
-    return e
+def assert_grad_close(name, got, want, rtol=RTOL_GRAD, flip_frac=1e-3, flip_atol=2e-2):
+    """Gradients agree within rtol (max|a-b| / max|b|).  Like the images they inherit isolated
+    discrete flips of the fp32 forward (alpha < 1/255, T < 1e-4): the float32 and float64 builds of
+    the CPU oracle differ from EACH OTHER by up to ~6e-3 on 1-4 of 15000 elements on such a case
+    (tests/test_oracle.py::test_f32_f64_oracles_differ_only_by_isolated_flips), so a fraction
+    `flip_frac` of elements may exceed rtol, none may exceed flip_atol."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (name, got.shape, want.shape)
+    if got.size == 0:
+        return 0.0
+    err = np.abs(got - want) / (np.abs(want).max() + 1e-30)
+    bad = int((err > rtol).sum())
+    allowed = max(1, int(math.ceil(flip_frac * err.size))) if flip_frac > 0 else 0
+    assert bad <= allowed, f"{name}: {bad} / {err.size} elements beyond rtol={rtol} (max {err.max():.3e})"
+    assert err.max() <= flip_atol, f"{name}: max rel err {err.max():.3e} > {flip_atol}"
+    return float(err.max())
