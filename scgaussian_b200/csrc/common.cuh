@@ -36,6 +36,50 @@ struct __align__(16) ScreenGrad {
 };
 static_assert(sizeof(ScreenGrad) == 48, "ScreenGrad must be 48 bytes");
 
+// ---- exact (Gaussian, pixel-rectangle) culling, shared by preprocess (count), emission (write) and
+// render (per-slot skip).  Maximum over the pixel rectangle [x0, x1] x [y0, y1] of
+//   p2(d) = cA dx^2 + cB dx dy + cC dy^2,  d = mean - pixel   (negative definite, max 0 at d = 0).
+// The maximiser of a concave function whose global maximum lies outside the box is on one of the
+// two faces that look at the origin; each face is a 1-D concave parabola (kx = -cB/(2cA),
+// ky = -cB/(2cC) give its vertex).  Written with explicit round-to-nearest intrinsics so that the
+// counting pass and the emission pass -- two different kernels -- take bit-identical decisions.
+#ifdef __CUDACC__
+__device__ __forceinline__ float max_power_over_rect(const float cA, const float cB, const float cC,
+                                                     const float kx, const float ky, const float mx,
+                                                     const float my, const float x0, const float x1,
+                                                     const float y0, const float y1) {
+    const float dxl = __fsub_rn(mx, x1), dxh = __fsub_rn(mx, x0);
+    const float dyl = __fsub_rn(my, y1), dyh = __fsub_rn(my, y0);
+    const float cx = fminf(fmaxf(0.f, dxl), dxh);
+    const float cy = fminf(fmaxf(0.f, dyl), dyh);
+    const float dy1 = fminf(fmaxf(__fmul_rn(ky, cx), dyl), dyh);   // face dx = cx
+    const float f1 = __fmaf_rn(cx, __fmaf_rn(cA, cx, __fmul_rn(cB, dy1)), __fmul_rn(__fmul_rn(cC, dy1), dy1));
+    const float dx2 = fminf(fmaxf(__fmul_rn(kx, cy), dxl), dxh);   // face dy = cy
+    const float f2 = __fmaf_rn(dx2, __fmaf_rn(cA, dx2, __fmul_rn(cB, cy)), __fmul_rn(__fmul_rn(cC, cy), cy));
+    return fmaxf(f1, f2);
+}
+// log2 units; keeps every rectangle bound conservative under fp32 rounding of the per-pixel test
+constexpr float CULL_MARGIN = 0.02f;
+
+struct CullParams {   // per-Gaussian constants of the test, derived from the stored record only
+    float cA, cB, cC, kx, ky, mx, my, thr;
+};
+__device__ __forceinline__ CullParams make_cull(const float4 q0, const float4 q1) {
+    CullParams c;
+    c.mx = q0.x; c.my = q0.y; c.cA = q0.z; c.cB = q0.w; c.cC = q1.x;
+    c.kx = __fdiv_rn(-c.cB, __fmul_rn(2.f, c.cA));
+    c.ky = __fdiv_rn(-c.cB, __fmul_rn(2.f, c.cC));
+    c.thr = __fsub_rn(q1.w, CULL_MARGIN);
+    return c;
+}
+// may any pixel of tile (tx, ty) see alpha >= 1/255 from this Gaussian?
+__device__ __forceinline__ bool tile_may_contribute(const CullParams& c, const int tx, const int ty) {
+    const float x0 = (float)(tx * TILE), y0 = (float)(ty * TILE);
+    return max_power_over_rect(c.cA, c.cB, c.cC, c.kx, c.ky, c.mx, c.my, x0, x0 + (float)(TILE - 1), y0,
+                               y0 + (float)(TILE - 1)) >= c.thr;
+}
+#endif
+
 // ---- scratch carving (256-B aligned sub-allocations) ----
 __host__ __device__ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -45,7 +89,16 @@ constexpr int RADIX_TILE = RADIX_THREADS * RADIX_ITEMS;        // 4096 items per
 constexpr int RADIX_BINS = 256;
 constexpr int SCAN_BLOCK = 1024;
 
+constexpr int MAX_TILE_PASSES = 4;   // tile ids are < 2^32
+
 inline uint32_t radix_blocks(int64_t n) { return (uint32_t)((n + RADIX_TILE - 1) / RADIX_TILE); }
+
+// Per-pass "onesweep" state, all zero before the pass starts:
+//   [0, 256)                       global digit histogram of the pass
+//   [256]                          dynamic tile ticket;  [257..259] padding
+//   [260, 260 + 256 * nblocks)     decoupled look-back words: flag (2 msb) | count (30 lsb), [block][digit]
+inline size_t sweep_pass_words(int64_t n) { return 260 + (size_t)RADIX_BINS * radix_blocks(n > 0 ? n : 1); }
+inline size_t sweep_words(int64_t n, int passes) { return sweep_pass_words(n) * (size_t)passes; }
 
 struct GeometryLayout {
     Record* rec;              // [P]
@@ -56,8 +109,7 @@ struct GeometryLayout {
     uint32_t* sort_vals[2];   // [P] ping-pong (Gaussian ids); final depth order in sort_vals[0]
     uint32_t* offsets;        // [P] inclusive scan of tiles_touched in depth order
     uint32_t* scan_partials;  // [ceil(P / SCAN_BLOCK) + 1]
-    uint32_t* radix_hist;     // [RADIX_BINS * radix_blocks(P)]
-    uint32_t* radix_totals;   // [RADIX_BINS]
+    uint32_t* sweep;          // onesweep state of the 4 depth passes, zeroed once per forward (sweep_words(P, 4))
     ScreenGrad* screen_grad;  // [P] (used by backward only; lives here so backward allocates nothing)
     int64_t* status;          // [2] {R, overflow}
     size_t bytes;
@@ -78,8 +130,7 @@ inline GeometryLayout carve_geometry(void* base, int32_t P) {
     L.depth_key = L.sort_keys[0];   // preprocess writes the sort input in place
     L.offsets = (uint32_t*)take(Pa * 4);
     L.scan_partials = (uint32_t*)take(((Pa + SCAN_BLOCK - 1) / SCAN_BLOCK + 1) * 4);
-    L.radix_hist = (uint32_t*)take((size_t)RADIX_BINS * radix_blocks(Pa) * 4);
-    L.radix_totals = (uint32_t*)take(RADIX_BINS * 4);
+    L.sweep = (uint32_t*)take(sweep_words(Pa, 4) * 4);
     L.screen_grad = (ScreenGrad*)take(Pa * sizeof(ScreenGrad));
     L.bytes = o;
     return L;
@@ -88,8 +139,7 @@ inline GeometryLayout carve_geometry(void* base, int32_t P) {
 struct BinningLayout {
     uint32_t* keys[2];        // [capacity] tile ids, ping-pong
     uint32_t* vals[2];        // [capacity] Gaussian ids, ping-pong
-    uint32_t* radix_hist;     // [RADIX_BINS * radix_blocks(capacity)]
-    uint32_t* radix_totals;   // [RADIX_BINS]
+    uint32_t* sweep;          // onesweep state of the (<= 2) tile passes (sweep_words(capacity, 2))
     uint2* ranges;            // [tiles]
     size_t bytes;
 };
@@ -105,8 +155,7 @@ inline BinningLayout carve_binning(void* base, int32_t W, int32_t H, int64_t cap
     L.ranges = (uint2*)take(tiles * sizeof(uint2));
     for (int i = 0; i < 2; i++) L.keys[i] = (uint32_t*)take(C * 4);
     for (int i = 0; i < 2; i++) L.vals[i] = (uint32_t*)take(C * 4);
-    L.radix_hist = (uint32_t*)take((size_t)RADIX_BINS * radix_blocks(C) * 4);
-    L.radix_totals = (uint32_t*)take(RADIX_BINS * 4);
+    L.sweep = (uint32_t*)take(sweep_words(C, MAX_TILE_PASSES) * 4);
     L.bytes = o;
     return L;
 }
@@ -143,11 +192,6 @@ void launch_preprocess_backward(const ScgrView& v, const ScgrGaussians& g, const
 void launch_mark_visible(const float* means3D, int32_t P, const float* viewmatrix, uint8_t* present,
                          const Launch& L);
 
-// Stable LSD radix pass machinery.  `n_dev` (device uint32/int64 low word) overrides `n_host` when
-// non-NULL; `cap` bounds the grid.
-void radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], const int64_t* n_dev, int64_t n_host,
-                      int64_t cap, int begin_bit, int end_bit, uint32_t* hist, uint32_t* totals,
-                      int* final_buffer, const Launch& L);
 void launch_depth_order(const GeometryLayout& G, int32_t P, const Launch& L);
 void launch_emit_and_partition(const ScgrView& v, const GeometryLayout& G, const BinningLayout& B,
                                int32_t P, int64_t capacity, int* final_buffer, const Launch& L);

@@ -294,7 +294,14 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
     r.q2 = make_float4(rgb.x, rgb.y, rgb.z, __uint_as_float((uint32_t)rad | (flags << 28)));
     rec[i] = r;
     radii[i] = rad;
-    tiles_touched[i] = (uint32_t)((x1 - x0) * (y1 - y0));
+    // Output-preserving culling: of the tiles in the reference's rect (A.4) keep only those in which
+    // some pixel can pass the reference's own alpha >= 1/255 test (exact closed-form bound).  The
+    // dropped (Gaussian, tile) pairs would be evaluated and skipped pixel by pixel in A.8.
+    const CullParams cp = make_cull(r.q0, r.q1);
+    uint32_t touched = 0u;
+    for (int ty = y0; ty < y1; ty++)
+        for (int tx = x0; tx < x1; tx++) touched += tile_may_contribute(cp, tx, ty) ? 1u : 0u;
+    tiles_touched[i] = touched;
     depth_key[i] = __float_as_uint(zv);   // zv > 0.2 => bit order == numeric order (A.6)
     rect[i] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
 }

@@ -27,30 +27,12 @@ namespace scgr {
 namespace {
 
 constexpr int SLOTS = 8;
-constexpr float PREFILTER_MARGIN = 0.02f;   // log2 units; keeps the slot bound conservative under fp32 rounding
+constexpr float PREFILTER_MARGIN = CULL_MARGIN;
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
-}
-
-// Maximum over the pixel rectangle [x0, x1] x [y0, y1] of
-//   p2(d) = cA dx^2 + cB dx dy + cC dy^2,  d = mean - pixel   (negative definite, max 0 at d = 0).
-// The maximiser of a concave function whose global maximum lies outside the box is on one of the
-// two faces that look at the origin; each face is a 1-D concave parabola.
-__device__ __forceinline__ float max_power_over_rect(const float cA, const float cB, const float cC,
-                                                     const float kx, const float ky, const float mx,
-                                                     const float my, const float x0, const float x1,
-                                                     const float y0, const float y1) {
-    const float dxl = mx - x1, dxh = mx - x0, dyl = my - y1, dyh = my - y0;
-    const float cx = fminf(fmaxf(0.f, dxl), dxh);
-    const float cy = fminf(fmaxf(0.f, dyl), dyh);
-    const float dy1 = fminf(fmaxf(ky * cx, dyl), dyh);   // face dx = cx
-    const float f1 = cx * (cA * cx + cB * dy1) + cC * dy1 * dy1;
-    const float dx2 = fminf(fmaxf(kx * cy, dxl), dxh);   // face dy = cy
-    const float f2 = dx2 * (cA * dx2 + cB * cy) + cC * cy * cy;
-    return fmaxf(f1, f2);
 }
 
 struct Rec {
@@ -68,15 +50,13 @@ __device__ __forceinline__ Rec load_rec(const Record* __restrict__ rec, uint32_t
 
 // slot mask of one Gaussian: bit k set <=> slot k may receive a contribution
 __device__ __forceinline__ uint32_t slot_mask(const Rec& r, const float X0, const float Y0, const uint32_t live_slots) {
-    const float cA = r.q0.z, cB = r.q0.w, cC = r.q1.x;
-    const float kx = -cB / (2.f * cA), ky = -cB / (2.f * cC);
-    const float thr = r.q1.w - PREFILTER_MARGIN;
+    const CullParams c = make_cull(r.q0, r.q1);
     uint32_t m = 0u;
 #pragma unroll
     for (int k = 0; k < SLOTS; k++) {
         const float x0 = X0 + (float)((k & 1) << 3), y0 = Y0 + (float)((k >> 1) << 2);
-        const float mp = max_power_over_rect(cA, cB, cC, kx, ky, r.q0.x, r.q0.y, x0, x0 + 7.f, y0, y0 + 3.f);
-        if (mp >= thr) m |= 1u << k;
+        const float mp = max_power_over_rect(c.cA, c.cB, c.cC, c.kx, c.ky, c.mx, c.my, x0, x0 + 7.f, y0, y0 + 3.f);
+        if (mp >= c.thr) m |= 1u << k;
     }
     return m & live_slots;
 }

@@ -116,22 +116,45 @@ def test_forward_stages_match_oracle(dev):
     report("stages", radii_mismatch=n_rad, e_xy=e_xy, e_conic=e_conic, e_rgb=e_rgb, e_depth=e_depth,
            R_gpu=int(state.num_rendered), R_cpu=int(co.num_rendered))
     assert e_xy < 1e-5 and e_conic < 1e-4 and e_rgb < 1e-5 and e_depth < 1e-6
-    n_tiles_mis = int((dv["tiles_touched"] != st["tiles_touched"]).sum())
-    assert n_tiles_mis <= max(2, case["P"] // 2000)
     # depth order: ascending (depth, id), culled last
     order = dv["depth_order"].astype(np.int64)
     assert np.array_equal(np.sort(order), np.arange(case["P"]))
     dkey = np.where(radii > 0, rec[:, 6], np.inf)[order]
     assert (np.diff(dkey[np.isfinite(dkey)]) >= 0).all()
     assert np.isfinite(dkey[: int((radii > 0).sum())]).all()
-    # tile lists
+    # tile lists.  Ours = the reference's per-tile lists (A.6/A.7, the oracle's) MINUS the (Gaussian,
+    # tile) pairs in which no pixel can pass the reference's alpha >= 1/255 test: a subsequence, in
+    # the same depth order, and every dropped pair is checked to be non-contributing.
     assert int(dv["status"][0]) == state.num_rendered and int(dv["status"][1]) == 0
-    if n_rad == 0 and n_tiles_mis == 0:
-        assert state.num_rendered == co.num_rendered
-        assert np.array_equal(dv["ranges"].astype(np.int64), st["ranges"])
-        assert np.array_equal(dv["point_list"].astype(np.int64), st["point_list"].astype(np.int64))
-        nc = dv["n_contrib"].astype(np.int64)
-        assert (nc != st["n_contrib"]).mean() < 1e-3
+    assert int(dv["tiles_touched"].sum()) == state.num_rendered
+    assert (dv["tiles_touched"] <= st["tiles_touched"]).all() or n_rad > 0
+    assert state.num_rendered <= co.num_rendered
+    gx = (case["W"] + 15) // 16
+    rg, pl = dv["ranges"].astype(np.int64), dv["point_list"].astype(np.int64)
+    ne = rg[:, 1] > rg[:, 0]
+    assert rg[ne, 0][0] == 0 and rg[ne, 1][-1] == state.num_rendered and np.array_equal(rg[ne, 0][1:], rg[ne, 1][:-1])
+    dropped = kept = 0
+    for t in range(len(rg)):
+        mine = pl[rg[t, 0]:rg[t, 1]]
+        ref = st["point_list"][st["ranges"][t, 0]:st["ranges"][t, 1]].astype(np.int64)
+        pos = {g: i for i, g in enumerate(ref)}
+        if n_rad == 0:
+            idx = np.array([pos[g] for g in mine], dtype=np.int64)      # KeyError = not a subset
+            assert (np.diff(idx) > 0).all(), f"tile {t}: order differs from the reference's"
+        gone = np.setdiff1d(ref, mine)
+        kept += len(mine)
+        dropped += len(gone)
+        if len(gone):
+            ty, tx = divmod(t, gx)
+            ys, xs = np.meshgrid(np.arange(ty * 16, ty * 16 + 16), np.arange(tx * 16, tx * 16 + 16), indexing="ij")
+            dx = st["means2D"][gone, 0][:, None, None] - xs[None]
+            dy = st["means2D"][gone, 1][:, None, None] - ys[None]
+            cn = st["conic"][gone].astype(np.float64)
+            power = -0.5 * (cn[:, 0, None, None] * dx * dx + cn[:, 2, None, None] * dy * dy) - cn[:, 1, None, None] * dx * dy
+            al = case["opacities"].numpy()[gone, 0][:, None, None] * np.exp(power)
+            assert ((al < 1.0 / 255.0) | (power > 0)).all(), f"tile {t}: a contributing pair was culled"
+    report("stages_lists", kept=kept, dropped=dropped)
+    assert kept == state.num_rendered and dropped > 0
     util.assert_image_close("color", color.cpu().numpy(), c2)
     util.assert_image_close("depth", depth.cpu().numpy(), d2)
     util.assert_image_close("alpha", alpha.cpu().numpy(), a2)
@@ -309,7 +332,7 @@ def test_config3_structural_properties(dev, config3):
     dv = R.debug_views(state, case["P"], s)
     Rn = state.num_rendered
     report("config3", R=Rn, visible=int((radii > 0).sum()))
-    assert 5_000_000 < Rn < 20_000_000
+    assert 3_000_000 < Rn < 20_000_000
     ranges = dv["ranges"].cpu().numpy().astype(np.int64)
     ne = ranges[:, 1] > ranges[:, 0]
     # ranges tile the sorted list exactly: consecutive, disjoint, covering [0, R)
