@@ -140,7 +140,8 @@ int scgr_profile_fetch(const char** names, float* ms, int max_entries);
 /* Introspection for stage-level parity tests (device pointers into the scratch buffers).
  * record  : [P] x 12 floats {x, y, cA, cB | cC, opacity, depth, pmin2 | r, g, b, bits(u32: radius | flags << 28)}
  *           with cA = -0.5 log2(e) conicA, cB = -log2(e) conicB, cC = -0.5 log2(e) conicC
- * point_list : [R] uint32 Gaussian ids, tile-major, depth-ordered;  ranges : [tiles] x {start,end} uint32
+ * point_list : [R] uint32 Gaussian ids, tile-major, depth-ordered;  ranges : [tiles] x {start,end} uint32,
+ *           an empty tile holds (0xffffffff, 0)
  * n_contrib : [H*W] uint32;  final_T : [H*W] float;  tiles_touched : [P] uint32 */
 typedef struct ScgrDebugViews {
     const float* record;

@@ -26,6 +26,8 @@
 // Nothing here needs R on the host: every kernel reads the instance count from device memory
 // and clamps its work to the binning capacity (overflow is flagged, never written past).
 // All passes are HBM/L2-bound integer work -- no tensor cores.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace scgr {
@@ -61,51 +63,82 @@ __device__ __forceinline__ uint32_t block_inclusive_scan(uint32_t v, uint32_t* s
     return inc + base;
 }
 
-// pass 1: per-block sums of tiles_touched[order[s]]
-__global__ void __launch_bounds__(SCAN_BLOCK)
-scan_reduce_kernel(const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ order, int P,
-                   uint32_t* __restrict__ partials) {
-    __shared__ uint32_t s_warp[32];
-    const int s = blockIdx.x * SCAN_BLOCK + threadIdx.x;
-    const uint32_t v = s < P ? tiles_touched[order[s]] : 0u;
-    uint32_t total;
-    block_inclusive_scan(v, s_warp, &total);
-    if (threadIdx.x == 0) partials[blockIdx.x] = total;
+// Single-pass chained scan (decoupled look-back): offsets[s] = inclusive prefix of
+// tiles_touched[order[s]] in depth order; the grand total R goes to status[0].
+// state[0] = ticket, state[1 + tile] = flag (2 msb) | value (62 lsb); all zero before the launch.
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+constexpr unsigned long long SFLAG_PARTIAL = 1ull << 62, SFLAG_INCLUSIVE = 2ull << 62, SFLAG_MASK = 3ull << 62;
+
+__device__ __forceinline__ unsigned long long ld_volatile64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// pass 2 (single block): exclusive scan of the partials in place; grand total -> status[0]
 __global__ void __launch_bounds__(SCAN_BLOCK)
-scan_partials_kernel(uint32_t* __restrict__ partials, int n, int64_t* __restrict__ status) {
+scan_offsets_kernel(const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ order, int P,
+                    uint32_t* __restrict__ offsets, int64_t* __restrict__ status, unsigned long long* __restrict__ state) {
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0u;
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_prefix;
+    if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd(state, 1ull);
     __syncthreads();
-    for (int base = 0; base < n; base += SCAN_BLOCK) {
-        const int i = base + threadIdx.x;
-        const uint32_t v = i < n ? partials[i] : 0u;
-        uint32_t total;
-        const uint32_t inc = block_inclusive_scan(v, s_warp, &total);
-        const uint32_t carry = s_carry;
-        if (i < n) partials[i] = carry + inc - v;
-        __syncthreads();
-        if (threadIdx.x == 0) s_carry = carry + total;
-        __syncthreads();
+    const uint32_t tile = s_tile;
+    const int ntiles = (P + SCAN_TILE - 1) / SCAN_TILE;
+    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t mine = 0u;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        v[i] = base + i < P ? tiles_touched[order[base + i]] : 0u;
+        mine += v[i];
     }
-    if (threadIdx.x == 0) {
-        status[0] = (int64_t)s_carry;   // R = num_rendered
-        status[1] = 0;                  // overflow flag, raised later by the emission kernel
+    uint32_t total;
+    const uint32_t inc = block_inclusive_scan(mine, s_warp, &total);
+    unsigned long long* words = state + 1;
+    if (threadIdx.x == 0)
+        st_volatile64(words + tile, (tile == 0 ? SFLAG_INCLUSIVE : SFLAG_PARTIAL) | (unsigned long long)total);
+    if (threadIdx.x < 32) {
+        // warp 0 looks back 32 predecessors at a time
+        unsigned long long excl = 0ull;
+        int p = (int)tile - 1;
+        while (p >= 0) {
+            const int q = p - (int)threadIdx.x;
+            unsigned long long w = SFLAG_INCLUSIVE;           // virtual tile -1: inclusive prefix 0
+            if (q >= 0) w = ld_volatile64(words + q);
+            const uint32_t unpublished = __ballot_sync(0xffffffffu, (w & SFLAG_MASK) == 0ull);
+            const uint32_t inclusive = __ballot_sync(0xffffffffu, (w & SFLAG_MASK) == SFLAG_INCLUSIVE);
+            // usable lanes: those before the first unpublished one, up to and including the first inclusive one
+            const int first_unpub = unpublished ? __ffs(unpublished) - 1 : 32;
+            const int first_incl = inclusive ? __ffs(inclusive) - 1 : 32;
+            const int take = min(first_unpub, first_incl + 1);      // number of lanes consumed
+            unsigned long long val = (int)threadIdx.x < take ? (w & ~SFLAG_MASK) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+            excl += val;
+            if (first_incl < first_unpub) break;              // reached an inclusive word
+            p -= take;                                         // retry from the first unpublished word
+        }
+        if (threadIdx.x == 0) {
+            if (tile > 0) st_volatile64(words + tile, SFLAG_INCLUSIVE | (excl + total));
+            s_prefix = excl;
+            if ((int)tile == ntiles - 1) {
+                status[0] = (int64_t)(excl + total);   // R = num_rendered
+                status[1] = 0;                         // overflow flag, raised later by the emission kernel
+            }
+        }
     }
-}
-
-// pass 3: offsets[s] = inclusive prefix of tiles_touched in depth order
-__global__ void __launch_bounds__(SCAN_BLOCK)
-scan_finish_kernel(const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ order, int P,
-                   const uint32_t* __restrict__ partials, uint32_t* __restrict__ offsets) {
-    __shared__ uint32_t s_warp[32];
-    const int s = blockIdx.x * SCAN_BLOCK + threadIdx.x;
-    const uint32_t v = s < P ? tiles_touched[order[s]] : 0u;
-    const uint32_t inc = block_inclusive_scan(v, s_warp, nullptr);
-    if (s < P) offsets[s] = partials[blockIdx.x] + inc;
+    __syncthreads();
+    uint32_t run = (uint32_t)s_prefix + inc - mine;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        run += v[i];
+        if (base + i < P) offsets[base + i] = run;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -132,7 +165,7 @@ __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
 }
 
 // global digit histograms of the 4 byte-digits of the depth keys -> sweep[pass][0..255]
-constexpr int HIST_ITEMS = 32;
+constexpr int HIST_ITEMS = 8;
 __global__ void __launch_bounds__(256)
 depth_hist_kernel(const uint32_t* __restrict__ keys, int n, uint32_t* __restrict__ sweep, size_t pass_words) {
     __shared__ uint32_t s_hist[4][RADIX_BINS];
@@ -140,11 +173,17 @@ depth_hist_kernel(const uint32_t* __restrict__ keys, int n, uint32_t* __restrict
     for (int p = 0; p < 4; p++) s_hist[p][threadIdx.x] = 0u;
     __syncthreads();
     const int base = blockIdx.x * 256 * HIST_ITEMS;
-#pragma unroll 4
+    uint32_t kk[HIST_ITEMS];
+#pragma unroll
+    for (int it = 0; it < HIST_ITEMS; it++) {
+        const int idx = base + it * 256 + threadIdx.x;
+        kk[it] = idx < n ? keys[idx] : 0u;
+    }
+#pragma unroll
     for (int it = 0; it < HIST_ITEMS; it++) {
         const int idx = base + it * 256 + threadIdx.x;
         if (idx < n) {
-            const uint32_t k = keys[idx];
+            const uint32_t k = kk[it];
             atomicAdd(&s_hist[0][k & 255u], 1u);
             atomicAdd(&s_hist[1][(k >> 8) & 255u], 1u);
             atomicAdd(&s_hist[2][(k >> 16) & 255u], 1u);
@@ -159,31 +198,49 @@ depth_hist_kernel(const uint32_t* __restrict__ keys, int n, uint32_t* __restrict
     }
 }
 
+// peers of this lane = lanes holding the same (<= 8-bit) digit.  8 independent ballots instead of
+// one MATCH.ANY: VOTE has a short fixed latency and the ballots of all items pipeline.
+__device__ __forceinline__ uint32_t peers_by_ballot(const uint32_t d, const bool valid) {
+    uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+}
+
 // One stable pass.  sweep = this pass's state (layout in common.cuh), zero before the launch except
-// for the histogram, which must be complete.
-template <bool WRITE_KEYS>
-__global__ void __launch_bounds__(RADIX_THREADS)
+// for the histogram, which must be complete.  THREADS * ITEMS == RADIX_TILE.
+// RANGES (last tile-partition pass): instead of writing the sorted keys, derive the per-tile
+// [start, end) ranges (A.7) on the fly -- inside a CTA the reordered items are sorted by full key,
+// so every CTA-local run boundary contributes an atomicMin(start) / atomicMax(end).
+template <int THREADS, int ITEMS, bool BALLOT, bool RANGES>
+__global__ void __launch_bounds__(THREADS)
 onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                      const int64_t* __restrict__ n_dev, int64_t n_host, int64_t cap, int shift,
-                     uint32_t mask, uint32_t* __restrict__ sweep) {
-    constexpr int WARPS = RADIX_THREADS / 32;
-    constexpr int PER_WARP = RADIX_TILE / WARPS;   // 512
-    __shared__ uint32_t s_cnt[WARPS][RADIX_BINS];  // per-warp digit counts -> offsets
-    __shared__ uint32_t s_start[RADIX_BINS];       // CTA-local sorted position of each digit's run
-    __shared__ uint32_t s_gbase[RADIX_BINS];       // global position of element 0 of each digit's run, minus s_start
-    __shared__ uint32_t s_keys[RADIX_TILE];
-    __shared__ uint32_t s_vals[RADIX_TILE];
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_tile;
+                     uint32_t mask, uint32_t* __restrict__ sweep, uint2* __restrict__ ranges) {
+    static_assert(THREADS * ITEMS == RADIX_TILE, "tile size is part of the scratch layout");
+    constexpr int WARPS = THREADS / 32;
+    constexpr int PER_WARP = RADIX_TILE / WARPS;
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    uint32_t* const s_keys = s_dyn;                          // [RADIX_TILE]
+    uint32_t* const s_vals = s_keys + RADIX_TILE;            // [RADIX_TILE]
+    uint32_t* const s_start = s_vals + RADIX_TILE;           // [256] CTA-local sorted position of each digit's run
+    uint32_t* const s_gbase = s_start + RADIX_BINS;          // [256] global position of the run's element 0, minus s_start
+    uint32_t* const s_warp = s_gbase + RADIX_BINS;           // [32]
+    uint32_t& s_tile = s_warp[32];                           // [1] (+3 pad)
+    uint16_t (*s_cnt)[RADIX_BINS] = reinterpret_cast<uint16_t (*)[RADIX_BINS]>(s_warp + 36);   // [WARPS][256] counts -> offsets
 
     const uint32_t* ghist = sweep;
     uint32_t* ticket = sweep + 256;
     uint32_t* lookback = sweep + 260;
 
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-#pragma unroll
-    for (int k = 0; k < WARPS; k++) s_cnt[k][threadIdx.x] = 0u;
+    for (int i = threadIdx.x; i < WARPS * RADIX_BINS; i += THREADS) (&s_cnt[0][0])[i] = 0;
+    if (threadIdx.x < RADIX_BINS) s_start[threadIdx.x] = 0u;
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t n = load_count(n_dev, n_host, cap);
@@ -193,82 +250,101 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     const uint32_t in_tile = min((uint32_t)RADIX_TILE, n - base);
 
     // ---- stable ranks: (warp, iteration, lane) order == input order ----
-    uint32_t key[RADIX_ITEMS], val[RADIX_ITEMS], rank[RADIX_ITEMS];
+    uint32_t key[ITEMS], val[ITEMS], rank[ITEMS], peers[ITEMS];
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
-    for (int it = 0; it < RADIX_ITEMS; it++) {
+    for (int it = 0; it < ITEMS; it++) {
         const uint32_t idx = base + w * PER_WARP + it * 32 + lane;
         const bool valid = idx < n;
         key[it] = valid ? keys_in[idx] : 0u;
         val[it] = valid ? vals_in[idx] : 0u;
     }
+    // Publish this tile's digit counts EARLY (a cheap unordered shared-memory histogram), long
+    // before they are needed: the ranking below gives the preceding tiles time to resolve their
+    // own prefixes, so the look-back further down usually finds an inclusive word one hop away.
 #pragma unroll
-    for (int it = 0; it < RADIX_ITEMS; it++) {
+    for (int it = 0; it < ITEMS; it++)
+        if (base + w * PER_WARP + it * 32 + lane < n) atomicAdd(&s_start[(key[it] >> shift) & mask], 1u);
+    __syncthreads();
+    if (threadIdx.x < RADIX_BINS)
+        st_volatile(lookback + (size_t)tile * RADIX_BINS + threadIdx.x,
+                    (tile == 0 ? FLAG_INCLUSIVE : FLAG_PARTIAL) | s_start[threadIdx.x]);
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
         const bool valid = base + w * PER_WARP + it * 32 + lane < n;
         const uint32_t d = (key[it] >> shift) & mask;
         // invalid lanes become singletons that match nobody
-        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : (0x10000u | (uint32_t)lane));
-        const int leader = __ffs(peers) - 1;
+        peers[it] = BALLOT ? peers_by_ballot(d, valid)
+                           : __match_any_sync(0xffffffffu, valid ? d : (0x10000u | (uint32_t)lane));
+    }
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+        const bool valid = base + w * PER_WARP + it * 32 + lane < n;
+        const uint32_t d = (key[it] >> shift) & mask;
+        const int leader = __ffs(peers[it]) - 1;
         uint32_t c = 0u;
         if (valid && lane == leader) {
             c = s_cnt[w][d];
-            s_cnt[w][d] = c + __popc(peers);
+            s_cnt[w][d] = (uint16_t)(c + __popc(peers[it]));
         }
         c = __shfl_sync(0xffffffffu, c, leader);
-        rank[it] = c + __popc(peers & lt_mask);
+        rank[it] = c + __popc(peers[it] & lt_mask);
         __syncwarp();
     }
     __syncthreads();
 
-    // ---- per digit (thread d): CTA total, publish, look back, global base ----
+    // ---- per digit (thread d < 256): CTA total, publish, look back, global base ----
     {
         const uint32_t d = threadIdx.x;
         uint32_t total = 0u;
+        if (d < RADIX_BINS) {
 #pragma unroll
-        for (int k = 0; k < WARPS; k++) {
-            const uint32_t c = s_cnt[k][d];
-            s_cnt[k][d] = total;      // offset of warp k inside the digit's run
-            total += c;
+            for (int k = 0; k < WARPS; k++) {
+                const uint32_t c = s_cnt[k][d];
+                s_cnt[k][d] = (uint16_t)total;      // offset of warp k inside the digit's run
+                total += c;
+            }
         }
-        st_volatile(lookback + (size_t)tile * RADIX_BINS + d, (tile == 0 ? FLAG_INCLUSIVE : FLAG_PARTIAL) | total);
         // CTA-local start of the digit's run, and global start of the digit (all tiles)
         const uint32_t inc_local = block_inclusive_scan(total, s_warp, nullptr);
         __syncthreads();
-        const uint32_t gh = ghist[d];
+        const uint32_t gh = d < RADIX_BINS ? ghist[d] : 0u;
         const uint32_t inc_global = block_inclusive_scan(gh, s_warp, nullptr);
-        uint32_t excl = 0u;          // items with this digit in preceding tiles
-        if (tile > 0) {
-            // Decoupled look-back, LOOK predecessors per round trip: the loads of a window are
-            // independent, so a chain of k unresolved predecessors costs k / LOOK L2 latencies.
-            constexpr int LOOK = 8;
-            int p = (int)tile - 1;
-            bool resolved = false;
-            while (!resolved) {
-                uint32_t v[LOOK];
+        if (d < RADIX_BINS) {
+            uint32_t excl = 0u;          // items with this digit in preceding tiles
+            if (tile > 0) {
+                // Decoupled look-back, LOOK predecessors per round trip: the loads of a window are
+                // independent, so a chain of k unresolved predecessors costs k / LOOK L2 latencies.
+                constexpr int LOOK = 8;
+                int p = (int)tile - 1;
+                bool resolved = false;
+                while (!resolved) {
+                    uint32_t v[LOOK];
 #pragma unroll
-                for (int i = 0; i < LOOK; i++)
-                    v[i] = p - i >= 0 ? ld_volatile(lookback + (size_t)(p - i) * RADIX_BINS + d) : FLAG_INCLUSIVE;
+                    for (int i = 0; i < LOOK; i++)
+                        v[i] = p - i >= 0 ? ld_volatile(lookback + (size_t)(p - i) * RADIX_BINS + d) : FLAG_INCLUSIVE;
 #pragma unroll
-                for (int i = 0; i < LOOK; i++) {
-                    if (resolved) break;
-                    const uint32_t f = v[i] & FLAG_MASK;
-                    if (f == 0u) break;                 // not published yet: re-read from here
-                    excl += v[i] & VALUE_MASK;
-                    p--;
-                    if (f == FLAG_INCLUSIVE) resolved = true;
+                    for (int i = 0; i < LOOK; i++) {
+                        if (resolved) break;
+                        const uint32_t f = v[i] & FLAG_MASK;
+                        if (f == 0u) break;                 // not published yet: re-read from here
+                        excl += v[i] & VALUE_MASK;
+                        p--;
+                        if (f == FLAG_INCLUSIVE) resolved = true;
+                    }
                 }
+                st_volatile(lookback + (size_t)tile * RADIX_BINS + d, FLAG_INCLUSIVE | (excl + total));
             }
-            st_volatile(lookback + (size_t)tile * RADIX_BINS + d, FLAG_INCLUSIVE | (excl + total));
+            const uint32_t start = inc_local - total;
+            s_start[d] = start;
+            s_gbase[d] = (inc_global - gh) + excl - start;
         }
-        const uint32_t start = inc_local - total;
-        s_start[d] = start;
-        s_gbase[d] = (inc_global - gh) + excl - start;
     }
     __syncthreads();
 
     // ---- reorder through shared memory, then coalesced runs to global ----
 #pragma unroll
-    for (int it = 0; it < RADIX_ITEMS; it++) {
+    for (int it = 0; it < ITEMS; it++) {
         if (base + w * PER_WARP + it * 32 + lane < n) {
             const uint32_t d = (key[it] >> shift) & mask;
             const uint32_t lp = s_start[d] + s_cnt[w][d] + rank[it];
@@ -277,23 +353,69 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
         }
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < in_tile; i += RADIX_THREADS) {
+    for (uint32_t i = threadIdx.x; i < in_tile; i += THREADS) {
         const uint32_t k = s_keys[i];
         const uint32_t pos = s_gbase[(k >> shift) & mask] + i;
-        if (WRITE_KEYS) keys_out[pos] = k;
         vals_out[pos] = s_vals[i];
+        if (RANGES) {
+            if (i == 0 || s_keys[i - 1] != k) atomicMin(&ranges[k].x, pos);
+            if (i == in_tile - 1 || s_keys[i + 1] != k) atomicMax(&ranges[k].y, pos + 1u);
+        } else {
+            keys_out[pos] = k;
+        }
     }
 }
 
+constexpr size_t onesweep_smem_bytes(int threads) {
+    return (size_t)(2 * RADIX_TILE + 2 * RADIX_BINS + 36) * 4 + (size_t)(threads / 32) * RADIX_BINS * 2;
+}
+
+__global__ void init_ranges_kernel(uint2* __restrict__ ranges, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ranges[i] = make_uint2(0xFFFFFFFFu, 0u);     // empty: start > end
+}
+
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+template <int THREADS, int ITEMS, bool BALLOT, bool RANGES>
+void launch_onesweep_variant(uint32_t nb, const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout,
+                             const int64_t* n_dev, int64_t n_host, int64_t cap, int shift, uint32_t mask,
+                             uint32_t* sweep, uint2* ranges, const Launch& L) {
+    auto kern = onesweep_pass_kernel<THREADS, ITEMS, BALLOT, RANGES>;
+    constexpr size_t smem = onesweep_smem_bytes(THREADS);
+    static bool configured = false;     // per-process, idempotent
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    kern<<<nb, THREADS, smem, L.stream>>>(kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges);
+}
+
+// variant 1: 256 threads x 16 items; 2: 512 x 8; 4: 1024 x 4 (all ballot ranking); 0: 256 x 16 with MATCH.ANY
+template <bool RANGES>
+void launch_onesweep(const char* name, const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout,
+                     const int64_t* n_dev, int64_t n_host, int64_t cap, int shift, uint32_t mask, uint32_t* sweep,
+                     uint2* ranges, const Launch& L) {
+    static const int variant = env_int("SCGR_SORT_VARIANT", 2);
+    const uint32_t nb = radix_blocks(cap > 0 ? cap : 1);
+    begin_kernel(name, L);
+    switch (variant) {
+        case 0: launch_onesweep_variant<256, 16, false, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
+        case 1: launch_onesweep_variant<256, 16, true, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
+        case 4: launch_onesweep_variant<1024, 4, true, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
+        default: launch_onesweep_variant<512, 8, true, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
+    }
+    check_launch(name, L);
+}
+
 // ------------------------------------------------------------------------------------------
-// instance emission in depth order (A.6 without the depth half of the key)
-// One warp per 32 consecutive depth-ordered Gaussians; for each of them the 32 lanes test the
-// tiles of its rect in parallel (exact culling), compact the survivors with a ballot and write
-// them out -> coalesced stores, no per-thread rect loops.  Also accumulates the global digit
-// histograms of the tile ids for the partition passes.
+// instance emission in depth order (A.6 without the depth half of the key).  Also accumulates the
+// global digit histograms of the tile ids for the partition passes.
 // ------------------------------------------------------------------------------------------
 constexpr int EMIT_THREADS = 256;
-constexpr int EMIT_GROUPS_PER_WARP = 4;   // 8 warps x 4 x 32 = 1024 Gaussians per CTA
 
 struct TilePasses {
     int passes;
@@ -301,12 +423,17 @@ struct TilePasses {
     uint32_t mask[MAX_TILE_PASSES];
 };
 
+// One thread per depth-ordered Gaussian expands the survivor bit mask written by preprocess into
+// (tile id, Gaussian id) pairs at its slice [offsets[s-1], offsets[s]) of the instance arrays --
+// consecutive threads own consecutive slices, so a warp's stores fall into a few cache lines.
+// Rects of more than 64 tiles (no mask) are handled afterwards by the whole warp: the 32 lanes
+// re-run the exact test on 32 tiles at a time and compact the survivors with a ballot.
 __global__ void __launch_bounds__(EMIT_THREADS)
 emit_instances_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
-                      const uint2* __restrict__ rect, const Record* __restrict__ rec, int P, int grid_x,
-                      int64_t capacity, int64_t* __restrict__ status, uint32_t* __restrict__ keys,
-                      uint32_t* __restrict__ vals, uint32_t* __restrict__ sweep, size_t pass_words,
-                      const TilePasses tp) {
+                      const uint2* __restrict__ rect, const unsigned long long* __restrict__ tile_mask,
+                      const Record* __restrict__ rec, int P, int grid_x, int64_t capacity,
+                      int64_t* __restrict__ status, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                      uint32_t* __restrict__ sweep, size_t pass_words, const TilePasses tp) {
     __shared__ uint32_t s_hist[MAX_TILE_PASSES][RADIX_BINS];
     const int64_t R = status[0];
     if (R > capacity) {
@@ -315,51 +442,87 @@ emit_instances_kernel(const uint32_t* __restrict__ order, const uint32_t* __rest
     }
     for (int p = 0; p < tp.passes; p++) s_hist[p][threadIdx.x] = 0u;
     __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    for (int gi = 0; gi < EMIT_GROUPS_PER_WARP; gi++) {
-        const int s = ((blockIdx.x * (EMIT_THREADS / 32) + w) * EMIT_GROUPS_PER_WARP + gi) * 32 + lane;
-        uint32_t gid = 0u, end = 0u, begin = 0u;
-        uint2 rc = make_uint2(0u, 0u);
-        float4 q0 = make_float4(0.f, 0.f, -1.f, 0.f), q1 = make_float4(-1.f, 0.f, 0.f, 0.f);
-        if (s < P) {
-            gid = order[s];
-            end = offsets[s];
-            begin = s > 0 ? offsets[s - 1] : 0u;
-            if (end != begin) {
-                rc = rect[gid];
-                const float4* r = reinterpret_cast<const float4*>(rec + gid);
-                q0 = __ldg(r);
-                q1 = __ldg(r + 1);
+    const int s = blockIdx.x * EMIT_THREADS + threadIdx.x;
+    uint32_t gid = 0u, end = 0u, begin = 0u, x0 = 0u, y0 = 0u, rw = 0u, rh = 0u;
+    if (s < P) {
+        gid = order[s];
+        end = offsets[s];
+        begin = s > 0 ? offsets[s - 1] : 0u;
+        if (end != begin) {
+            const uint2 rc = rect[gid];
+            x0 = rc.x & 0xffffu; y0 = rc.x >> 16;
+            rw = (rc.y & 0xffffu) - x0; rh = (rc.y >> 16) - y0;
+        }
+    }
+    const bool big = rw * rh > 64u;
+    if (end != begin && !big) {
+        unsigned long long m = tile_mask[gid];
+        uint32_t pos = begin;
+        const uint32_t row_bits = rw >= 32u ? 0xffffffffu : ((1u << rw) - 1u);
+        for (uint32_t ty = 0; ty < rh && m; ty++) {
+            uint32_t row = (uint32_t)m & row_bits;     // rw <= 64 / rh; rows wider than 32 only if rh == 1 or 2
+            if (rw > 32u) {                            // (rare) 33..64-tile wide single/double rows: take 64-bit path
+                unsigned long long row64 = rw >= 64u ? m : (m & ((1ull << rw) - 1ull));
+                while (row64) {
+                    const uint32_t tx = (uint32_t)__ffsll((long long)row64) - 1u;
+                    row64 &= row64 - 1ull;
+                    const uint32_t tile = (y0 + ty) * (uint32_t)grid_x + x0 + tx;
+                    if (pos < end) {
+                        keys[pos] = tile; vals[pos] = gid;
+                        for (int p = 0; p < tp.passes; p++) atomicAdd(&s_hist[p][(tile >> tp.shift[p]) & tp.mask[p]], 1u);
+                    }
+                    pos++;
+                }
+            } else {
+                while (row) {
+                    const uint32_t tx = (uint32_t)__ffs((int)row) - 1u;
+                    row &= row - 1u;
+                    const uint32_t tile = (y0 + ty) * (uint32_t)grid_x + x0 + tx;
+                    if (pos < end) {      // always true: the mask has exactly end - begin bits
+                        keys[pos] = tile; vals[pos] = gid;
+                        for (int p = 0; p < tp.passes; p++) atomicAdd(&s_hist[p][(tile >> tp.shift[p]) & tp.mask[p]], 1u);
+                    }
+                    pos++;
+                }
             }
+            m = rw >= 64u ? 0ull : (m >> rw);
+        }
+    }
+    // large rects, warp-cooperatively
+    uint32_t todo = __ballot_sync(0xffffffffu, end != begin && big);
+    if (todo) {
+        float4 q0 = make_float4(0.f, 0.f, -1.f, 0.f), q1 = make_float4(-1.f, 0.f, 0.f, 0.f);
+        if (end != begin && big) {
+            const float4* r = reinterpret_cast<const float4*>(rec + gid);
+            q0 = __ldg(r);
+            q1 = __ldg(r + 1);
         }
         const CullParams mine = make_cull(q0, q1);
-        uint32_t todo = __ballot_sync(0xffffffffu, end != begin);
         while (todo) {
             const int j = __ffs(todo) - 1;
             todo &= todo - 1;
             const uint32_t b = __shfl_sync(0xffffffffu, begin, j);
             const uint32_t e = __shfl_sync(0xffffffffu, end, j);
             const uint32_t g = __shfl_sync(0xffffffffu, gid, j);
-            const uint32_t rmin = __shfl_sync(0xffffffffu, rc.x, j);
-            const uint32_t rmax = __shfl_sync(0xffffffffu, rc.y, j);
+            const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, j), by0 = __shfl_sync(0xffffffffu, y0, j);
+            const uint32_t brw = __shfl_sync(0xffffffffu, rw, j), brh = __shfl_sync(0xffffffffu, rh, j);
             CullParams c;
             c.cA = __shfl_sync(0xffffffffu, mine.cA, j); c.cB = __shfl_sync(0xffffffffu, mine.cB, j);
             c.cC = __shfl_sync(0xffffffffu, mine.cC, j); c.kx = __shfl_sync(0xffffffffu, mine.kx, j);
             c.ky = __shfl_sync(0xffffffffu, mine.ky, j); c.mx = __shfl_sync(0xffffffffu, mine.mx, j);
             c.my = __shfl_sync(0xffffffffu, mine.my, j); c.thr = __shfl_sync(0xffffffffu, mine.thr, j);
-            const uint32_t x0 = rmin & 0xffffu, y0 = rmin >> 16;
-            const uint32_t rw = (rmax & 0xffffu) - x0, rh = (rmax >> 16) - y0;
-            const uint32_t ntiles = rw * rh;
+            const uint32_t ntiles = brw * brh;
             uint32_t out = b;
             for (uint32_t k0 = 0; k0 < ntiles; k0 += 32) {
                 const uint32_t k = k0 + lane;
                 bool pass = false;
                 uint32_t tile = 0u;
                 if (k < ntiles) {
-                    const uint32_t ty = k / rw, tx = k - ty * rw;
-                    pass = tile_may_contribute(c, (int)(x0 + tx), (int)(y0 + ty));
-                    tile = (y0 + ty) * (uint32_t)grid_x + x0 + tx;
+                    const uint32_t ty = k / brw, tx = k - ty * brw;
+                    pass = tile_may_contribute(c, (int)(bx0 + tx), (int)(by0 + ty));
+                    tile = (by0 + ty) * (uint32_t)grid_x + bx0 + tx;
                 }
                 const uint32_t bal = __ballot_sync(0xffffffffu, pass);
                 if (pass) {
@@ -379,18 +542,6 @@ emit_instances_kernel(const uint32_t* __restrict__ order, const uint32_t* __rest
         const uint32_t c = s_hist[p][threadIdx.x];
         if (c) atomicAdd(sweep + p * pass_words + threadIdx.x, c);
     }
-}
-
-// A.7
-__global__ void identify_ranges_kernel(const uint32_t* __restrict__ keys, const int64_t* __restrict__ status,
-                                       int64_t capacity, uint2* __restrict__ ranges) {
-    const int64_t R = status[0];
-    if (R > capacity) return;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R) return;
-    const uint32_t t = keys[i];
-    if (i == 0 || keys[i - 1] != t) ranges[t].x = (uint32_t)i;
-    if (i == R - 1 || keys[i + 1] != t) ranges[t].y = (uint32_t)(i + 1);
 }
 
 int bits_for(uint32_t n_values) {   // bits needed to represent 0 .. n_values-1
@@ -426,66 +577,52 @@ void launch_depth_order(const GeometryLayout& G, int32_t P, const Launch& L) {
     if (P <= 0) return;
     // preprocess already wrote sort_keys[0] (= depth_key) and sort_vals[0] (= 0..P-1)
     const size_t pw = sweep_pass_words(P);
-    cudaMemsetAsync(G.sweep, 0, sweep_words(P, 4) * 4, L.stream);
+    // one memset clears the onesweep state of the 4 passes and the scan state behind it
+    cudaMemsetAsync(G.sweep, 0, (size_t)((char*)G.scan_state - (char*)G.sweep) + scan_state_bytes(P), L.stream);
     begin_kernel("depth_hist", L);
     depth_hist_kernel<<<(P + 256 * HIST_ITEMS - 1) / (256 * HIST_ITEMS), 256, 0, L.stream>>>(G.sort_keys[0], P, G.sweep, pw);
     check_launch("depth_hist", L);
-    const uint32_t nb = radix_blocks(P);
     int cur = 0;
     for (int p = 0; p < 4; p++) {
-        begin_kernel("depth_sort_pass", L);
-        onesweep_pass_kernel<true><<<nb, RADIX_THREADS, 0, L.stream>>>(
-            G.sort_keys[cur], G.sort_vals[cur], G.sort_keys[cur ^ 1], G.sort_vals[cur ^ 1], nullptr, P, P, 8 * p, 255u,
-            G.sweep + p * pw);
-        check_launch("depth_sort_pass", L);
+        launch_onesweep<false>("depth_sort_pass", G.sort_keys[cur], G.sort_vals[cur], G.sort_keys[cur ^ 1],
+                               G.sort_vals[cur ^ 1], nullptr, P, P, 8 * p, 255u, G.sweep + p * pw, nullptr, L);
         cur ^= 1;
     }
     // 4 passes -> result is back in buffer 0
     const uint32_t* order = G.sort_vals[0];
-    const int nblk = (P + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    begin_kernel("scan_reduce", L);
-    scan_reduce_kernel<<<nblk, SCAN_BLOCK, 0, L.stream>>>(G.tiles_touched, order, P, G.scan_partials);
-    check_launch("scan_reduce", L);
-    begin_kernel("scan_partials", L);
-    scan_partials_kernel<<<1, SCAN_BLOCK, 0, L.stream>>>(G.scan_partials, nblk, G.status);
-    check_launch("scan_partials", L);
-    begin_kernel("scan_finish", L);
-    scan_finish_kernel<<<nblk, SCAN_BLOCK, 0, L.stream>>>(G.tiles_touched, order, P, G.scan_partials, G.offsets);
-    check_launch("scan_finish", L);
+    const int nblk = (P + SCAN_TILE - 1) / SCAN_TILE;
+    begin_kernel("scan_offsets", L);
+    scan_offsets_kernel<<<nblk, SCAN_BLOCK, 0, L.stream>>>(G.tiles_touched, order, P, G.offsets, G.status, G.scan_state);
+    check_launch("scan_offsets", L);
 }
 
 void launch_emit_and_partition(const ScgrView& v, const GeometryLayout& G, const BinningLayout& B,
                                int32_t P, int64_t capacity, int* final_buffer, const Launch& L) {
     const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
     const uint32_t n_tiles = (uint32_t)gx * gy;
-    cudaMemsetAsync(B.ranges, 0, (size_t)n_tiles * sizeof(uint2), L.stream);
+    begin_kernel("init_ranges", L);
+    init_ranges_kernel<<<(n_tiles + 255) / 256, 256, 0, L.stream>>>(B.ranges, n_tiles);
+    check_launch("init_ranges", L);
     if (P <= 0) { if (final_buffer) *final_buffer = 0; return; }
     const TilePasses tp = plan_tile_passes(n_tiles);
     const size_t pw = sweep_pass_words(capacity);
     cudaMemsetAsync(B.sweep, 0, pw * tp.passes * 4, L.stream);
     const uint32_t* order = G.sort_vals[0];   // 32-bit sort = 4 passes = even number of flips
-    const int per_cta = (EMIT_THREADS / 32) * EMIT_GROUPS_PER_WARP * 32;
     begin_kernel("emit_instances", L);
-    emit_instances_kernel<<<(P + per_cta - 1) / per_cta, EMIT_THREADS, 0, L.stream>>>(
-        order, G.offsets, G.rect, G.rec, P, gx, capacity, G.status, B.keys[0], B.vals[0], B.sweep, pw, tp);
+    emit_instances_kernel<<<(P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, L.stream>>>(
+        order, G.offsets, G.rect, G.tile_mask, G.rec, P, gx, capacity, G.status, B.keys[0], B.vals[0], B.sweep, pw, tp);
     check_launch("emit_instances", L);
-    const uint32_t nb = radix_blocks(capacity > 0 ? capacity : 1);
     int cur = 0;
     for (int p = 0; p < tp.passes; p++) {
-        begin_kernel("tile_partition_pass", L);
-        onesweep_pass_kernel<true><<<nb, RADIX_THREADS, 0, L.stream>>>(
-            B.keys[cur], B.vals[cur], B.keys[cur ^ 1], B.vals[cur ^ 1], G.status, 0, capacity, tp.shift[p], tp.mask[p],
-            B.sweep + p * pw);
-        check_launch("tile_partition_pass", L);
+        if (p == tp.passes - 1)
+            launch_onesweep<true>("tile_partition_pass", B.keys[cur], B.vals[cur], B.keys[cur ^ 1], B.vals[cur ^ 1], G.status,
+                                  0, capacity, tp.shift[p], tp.mask[p], B.sweep + p * pw, B.ranges, L);
+        else
+            launch_onesweep<false>("tile_partition_pass", B.keys[cur], B.vals[cur], B.keys[cur ^ 1], B.vals[cur ^ 1], G.status,
+                                   0, capacity, tp.shift[p], tp.mask[p], B.sweep + p * pw, nullptr, L);
         cur ^= 1;
     }
     if (final_buffer) *final_buffer = cur;
-    const int64_t blocks = (capacity + 255) / 256;
-    if (blocks > 0) {
-        begin_kernel("identify_ranges", L);
-        identify_ranges_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(B.keys[cur], G.status, capacity, B.ranges);
-        check_launch("identify_ranges", L);
-    }
 }
 
 }  // namespace scgr

@@ -99,17 +99,19 @@ inline uint32_t radix_blocks(int64_t n) { return (uint32_t)((n + RADIX_TILE - 1)
 //   [260, 260 + 256 * nblocks)     decoupled look-back words: flag (2 msb) | count (30 lsb), [block][digit]
 inline size_t sweep_pass_words(int64_t n) { return 260 + (size_t)RADIX_BINS * radix_blocks(n > 0 ? n : 1); }
 inline size_t sweep_words(int64_t n, int passes) { return sweep_pass_words(n) * (size_t)passes; }
+inline size_t scan_state_bytes(int64_t n) { return ((size_t)(n > 0 ? n : 1) / 4096 + 3) * 8; }
 
 struct GeometryLayout {
     Record* rec;              // [P]
     uint32_t* depth_key;      // == sort_keys[0]: float bits of view depth, CULLED_KEY if culled
     uint32_t* tiles_touched;  // [P]
     uint2* rect;              // [P] {minx | miny << 16, maxx | maxy << 16}
+    unsigned long long* tile_mask;  // [P] bit (ty * rect_w + tx) = tile of the rect survives culling (rects <= 64 tiles)
     uint32_t* sort_keys[2];   // [P] ping-pong
     uint32_t* sort_vals[2];   // [P] ping-pong (Gaussian ids); final depth order in sort_vals[0]
     uint32_t* offsets;        // [P] inclusive scan of tiles_touched in depth order
-    uint32_t* scan_partials;  // [ceil(P / SCAN_BLOCK) + 1]
     uint32_t* sweep;          // onesweep state of the 4 depth passes, zeroed once per forward (sweep_words(P, 4))
+    unsigned long long* scan_state;  // chained-scan ticket + look-back words; directly after `sweep`, zeroed with it
     ScreenGrad* screen_grad;  // [P] (used by backward only; lives here so backward allocates nothing)
     int64_t* status;          // [2] {R, overflow}
     size_t bytes;
@@ -125,12 +127,13 @@ inline GeometryLayout carve_geometry(void* base, int32_t P) {
     L.rec = (Record*)take(Pa * sizeof(Record));
     L.tiles_touched = (uint32_t*)take(Pa * 4);
     L.rect = (uint2*)take(Pa * 8);
+    L.tile_mask = (unsigned long long*)take(Pa * 8);
     for (int i = 0; i < 2; i++) L.sort_keys[i] = (uint32_t*)take(Pa * 4);
     for (int i = 0; i < 2; i++) L.sort_vals[i] = (uint32_t*)take(Pa * 4);
     L.depth_key = L.sort_keys[0];   // preprocess writes the sort input in place
     L.offsets = (uint32_t*)take(Pa * 4);
-    L.scan_partials = (uint32_t*)take(((Pa + SCAN_BLOCK - 1) / SCAN_BLOCK + 1) * 4);
-    L.sweep = (uint32_t*)take(sweep_words(Pa, 4) * 4);
+    L.sweep = (uint32_t*)take(align_up(sweep_words(Pa, 4) * 4));
+    L.scan_state = (unsigned long long*)take(scan_state_bytes(Pa));   // contiguous with sweep (both 256-B multiples)
     L.screen_grad = (ScreenGrad*)take(Pa * sizeof(ScreenGrad));
     L.bytes = o;
     return L;

@@ -169,7 +169,8 @@ template <bool SH_FAST>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __restrict__ rec,
                           uint32_t* __restrict__ depth_key, uint32_t* __restrict__ tiles_touched,
-                          uint2* __restrict__ rect, uint32_t* __restrict__ order_init,
+                          uint2* __restrict__ rect, unsigned long long* __restrict__ tile_mask,
+                          uint32_t* __restrict__ order_init,
                           int32_t* __restrict__ radii) {
     __shared__ float4 s_sh[SH_FAST ? PRE_THREADS * SH_ROW_F4_PAD : 1];
     const int P = g.P;
@@ -241,6 +242,7 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
         tiles_touched[i] = 0;
         depth_key[i] = CULLED_KEY;
         rect[i] = make_uint2(0u, 0u);
+        tile_mask[i] = 0ull;
         rec[i].q2 = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));   // radius 0 marks "culled" for the backward
         return;
     }
@@ -297,11 +299,21 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
     // Output-preserving culling: of the tiles in the reference's rect (A.4) keep only those in which
     // some pixel can pass the reference's own alpha >= 1/255 test (exact closed-form bound).  The
     // dropped (Gaussian, tile) pairs would be evaluated and skipped pixel by pixel in A.8.
+    // For rects of <= 64 tiles the survivors are also recorded as a bit mask, so that the emission
+    // kernel expands bits instead of repeating the test.
     const CullParams cp = make_cull(r.q0, r.q1);
     uint32_t touched = 0u;
+    unsigned long long mask = 0ull;
+    const int rw = x1 - x0;
+    const bool small_rect = rw * (y1 - y0) <= 64;
     for (int ty = y0; ty < y1; ty++)
-        for (int tx = x0; tx < x1; tx++) touched += tile_may_contribute(cp, tx, ty) ? 1u : 0u;
+        for (int tx = x0; tx < x1; tx++)
+            if (tile_may_contribute(cp, tx, ty)) {
+                touched++;
+                if (small_rect) mask |= 1ull << ((ty - y0) * rw + (tx - x0));
+            }
     tiles_touched[i] = touched;
+    tile_mask[i] = mask;
     depth_key[i] = __float_as_uint(zv);   // zv > 0.2 => bit order == numeric order (A.6)
     rect[i] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
 }
@@ -562,9 +574,9 @@ void launch_preprocess_forward(const ScgrView& v, const ScgrGaussians& g, const 
     const int blocks = (g.P + PRE_THREADS - 1) / PRE_THREADS;
     begin_kernel("preprocess_forward", L);
     if (sh_fast_ok(g, nullptr))
-        preprocess_forward_kernel<true><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.depth_key, G.tiles_touched, G.rect, G.sort_vals[0], radii);
+        preprocess_forward_kernel<true><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.depth_key, G.tiles_touched, G.rect, G.tile_mask, G.sort_vals[0], radii);
     else
-        preprocess_forward_kernel<false><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.depth_key, G.tiles_touched, G.rect, G.sort_vals[0], radii);
+        preprocess_forward_kernel<false><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.depth_key, G.tiles_touched, G.rect, G.tile_mask, G.sort_vals[0], radii);
     check_launch("preprocess_forward", L);
 }
 

@@ -20,6 +20,8 @@
 //   * exp() is one MUFU.EX2: the conic is stored pre-multiplied by -0.5*log2(e).
 // No block-level barriers at all (a warp never waits for another); no tensor cores (blend is not a
 // contraction).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace scgr {
@@ -32,6 +34,12 @@ constexpr float PREFILTER_MARGIN = CULL_MARGIN;
 __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 
@@ -64,26 +72,35 @@ __device__ __forceinline__ uint32_t slot_mask(const Rec& r, const float X0, cons
 // ------------------------------------------------------------------------------------------
 // forward (A.8)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
+// WPT warps share a tile: warp w owns slots [w * SLOTS / WPT, (w + 1) * SLOTS / WPT).  The warps of a
+// tile never synchronise with each other (disjoint pixels, private staging buffers).
+template <int WPT>
+__global__ void __launch_bounds__(32 * WPT)
 render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                       const Record* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                       const int64_t* __restrict__ status, int64_t capacity, float* __restrict__ out_color,
                       float* __restrict__ out_depth, float* __restrict__ out_alpha,
                       uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
-    __shared__ float4 s_q0[32], s_q1[32], s_q2[32];
+    constexpr int SPW = SLOTS / WPT;      // slots per warp
+    __shared__ float4 s_q0_[WPT][32], s_q1_[WPT][32], s_q2_[WPT][32];
     if (status[0] > capacity) return;   // binning overflowed: caller re-runs with a larger buffer
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int k0 = wid * SPW;             // first slot of this warp
+    float4* const s_q0 = s_q0_[wid];
+    float4* const s_q1 = s_q1_[wid];
+    float4* const s_q2 = s_q2_[wid];
     const int lx = lane & 7, ly = lane >> 3;
     const int X0 = blockIdx.x * TILE, Y0 = blockIdx.y * TILE;
     const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
-    const int total = (int)(range.y - range.x);
+    const int total = range.y > range.x ? (int)(range.y - range.x) : 0;   // empty tiles hold (0xffffffff, 0)
 
-    float T[SLOTS], Cr[SLOTS], Cg[SLOTS], Cb[SLOTS], Dd[SLOTS];
-    uint32_t last[SLOTS];
+    float T[SPW], Cr[SPW], Cg[SPW], Cb[SPW], Dd[SPW];
+    uint32_t last[SPW];
     uint32_t done = 0u;    // bit k: this lane's pixel of slot k is finished
 #pragma unroll
-    for (int k = 0; k < SLOTS; k++) {
-        T[k] = 1.f; Cr[k] = 0.f; Cg[k] = 0.f; Cb[k] = 0.f; Dd[k] = 0.f; last[k] = 0u;
+    for (int i = 0; i < SPW; i++) {
+        const int k = k0 + i;
+        T[i] = 1.f; Cr[i] = 0.f; Cg[i] = 0.f; Cb[i] = 0.f; Dd[i] = 0.f; last[i] = 0u;
         const int px = X0 + ((k & 1) << 3) + lx, py = Y0 + ((k >> 1) << 2) + ly;
         if (px >= W || py >= H) done |= 1u << k;
     }
@@ -97,8 +114,8 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         // slots in which some pixel is still open
         uint32_t live = 0u;
 #pragma unroll
-        for (int k = 0; k < SLOTS; k++)
-            if (!__all_sync(0xffffffffu, (done >> k) & 1u)) live |= 1u << k;
+        for (int i = 0; i < SPW; i++)
+            if (!__all_sync(0xffffffffu, (done >> (k0 + i)) & 1u)) live |= 1u << (k0 + i);
         if (live == 0u) break;
         const int cnt = min(32, total - base);
         const Rec cur = nxt;
@@ -115,38 +132,43 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
             const float4 q1 = s_q1[j];
             const float4 q2 = s_q2[j];
             const float dx0 = q0.x - pxf, dy0 = q0.y - pyf;
+            const float thr = q1.w - PREFILTER_MARGIN;
 #pragma unroll
-            for (int k = 0; k < SLOTS; k++) {
+            for (int i = 0; i < SPW; i++) {
+                const int k = k0 + i;
                 if (!(mj & (1u << k))) continue;      // warp-uniform
                 const float dx = dx0 - (float)((k & 1) << 3), dy = dy0 - (float)((k >> 1) << 2);
                 const float power = dx * (q0.z * dx + q0.w * dy) + q1.x * dy * dy;
-                if (((done >> k) & 1u) || power > 0.f || power < q1.w - PREFILTER_MARGIN) continue;
+                // straight-line, predicated: the reference's skip chain (A.8) without divergent branches
                 const float alpha = fminf(ALPHA_MAX, q1.y * ex2(power));
-                if (alpha < ALPHA_MIN) continue;
-                const float test_T = T[k] * (1.f - alpha);
-                if (test_T < T_EPS) { done |= 1u << k; continue; }
-                const float w = alpha * T[k];
-                Cr[k] += q2.x * w; Cg[k] += q2.y * w; Cb[k] += q2.z * w;
-                Dd[k] += q1.z * w;
-                T[k] = test_T;
-                last[k] = (uint32_t)(base + j + 1);
+                const float test_T = T[i] * (1.f - alpha);
+                const bool cand = !((done >> k) & 1u) && power <= 0.f && power >= thr && alpha >= ALPHA_MIN;
+                const bool stop = cand && test_T < T_EPS;      // pixel saturated: this Gaussian is NOT blended
+                const bool go = cand && !stop;
+                if (stop) done |= 1u << k;
+                const float w = go ? alpha * T[i] : 0.f;
+                Cr[i] += q2.x * w; Cg[i] += q2.y * w; Cb[i] += q2.z * w;
+                Dd[i] += q1.z * w;
+                T[i] = go ? test_T : T[i];
+                last[i] = go ? (uint32_t)(base + j + 1) : last[i];
             }
         }
     }
     const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
     const size_t N = (size_t)W * H;
 #pragma unroll
-    for (int k = 0; k < SLOTS; k++) {
+    for (int i = 0; i < SPW; i++) {
+        const int k = k0 + i;
         const int px = X0 + ((k & 1) << 3) + lx, py = Y0 + ((k >> 1) << 2) + ly;
         if (px < W && py < H) {
             const size_t pid = (size_t)py * W + px;
-            out_color[pid] = Cr[k] + T[k] * bg0;
-            out_color[N + pid] = Cg[k] + T[k] * bg1;
-            out_color[2 * N + pid] = Cb[k] + T[k] * bg2;
-            out_depth[pid] = Dd[k];
-            out_alpha[pid] = 1.f - T[k];      // == sum alpha_i T_i (telescoping), A.8
-            n_contrib[pid] = last[k];
-            final_T[pid] = T[k];
+            out_color[pid] = Cr[i] + T[i] * bg0;
+            out_color[N + pid] = Cg[i] + T[i] * bg1;
+            out_color[2 * N + pid] = Cb[i] + T[i] * bg2;
+            out_depth[pid] = Dd[i];
+            out_alpha[pid] = 1.f - T[i];      // == sum alpha_i T_i (telescoping), A.8
+            n_contrib[pid] = last[i];
+            final_T[pid] = T[i];
         }
     }
 }
@@ -198,51 +220,60 @@ __device__ __forceinline__ float transpose_reduce10(const float v[10], const int
     return d;
 }
 
-__global__ void __launch_bounds__(32)
+template <int WPT>
+__global__ void __launch_bounds__(32 * WPT)
 render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                        const Record* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                        const int64_t* __restrict__ status, int64_t capacity,
                        const uint32_t* __restrict__ n_contrib, const float* __restrict__ final_T,
                        const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
                        const float* __restrict__ dL_dalpha, ScreenGrad* __restrict__ screen_grad) {
-    __shared__ float4 s_q0[32], s_q1[32], s_q2[32];
-    __shared__ uint32_t s_id[32];
-    __shared__ float s_g[5][TILE_PIX];      // upstream gradients of the tile: r, g, b, depth, alpha
+    constexpr int SPW = SLOTS / WPT;      // slots per warp
+    __shared__ float4 s_q0_[WPT][32], s_q1_[WPT][32], s_q2_[WPT][32];
+    __shared__ uint32_t s_id_[WPT][32];
+    __shared__ float4 s_g4[TILE_PIX];       // upstream gradients of the tile: r, g, b, depth
+    __shared__ float s_ga[TILE_PIX];        //                                 alpha
     if (status[0] > capacity) return;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int k0 = wid * SPW;             // first slot of this warp
+    float4* const s_q0 = s_q0_[wid];
+    float4* const s_q1 = s_q1_[wid];
+    float4* const s_q2 = s_q2_[wid];
+    uint32_t* const s_id = s_id_[wid];
     const int lx = lane & 7, ly = lane >> 3;
     const int X0 = blockIdx.x * TILE, Y0 = blockIdx.y * TILE;
     const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
     const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
     const size_t N = (size_t)W * H;
 
-    float T[SLOTS], Ar[SLOTS], Ag[SLOTS], Ab[SLOTS], Ad[SLOTS], Aa[SLOTS], tfb[SLOTS];
-    int lc[SLOTS];
-    int slot_lc[SLOTS];
+    float T[SPW], Ar[SPW], Ag[SPW], Ab[SPW], Ad[SPW], Aa[SPW], tfb[SPW];
+    int lc[SPW];
+    int slot_lc[SPW];
     int toDo = 0;
 #pragma unroll
-    for (int k = 0; k < SLOTS; k++) {
+    for (int i = 0; i < SPW; i++) {
+        const int k = k0 + i;
         const int px = X0 + ((k & 1) << 3) + lx, py = Y0 + ((k >> 1) << 2) + ly;
         float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f, Tf = 0.f;
-        lc[k] = 0;
+        lc[i] = 0;
         if (px < W && py < H) {
             const size_t pid = (size_t)py * W + px;
             Tf = final_T[pid];
-            lc[k] = (int)n_contrib[pid];
+            lc[i] = (int)n_contrib[pid];
             gr = dL_dcolor[pid]; gg = dL_dcolor[N + pid]; gb = dL_dcolor[2 * N + pid];
             gd = dL_ddepth[pid];
             ga = dL_dalpha[pid];
         }
-        s_g[0][k * 32 + lane] = gr; s_g[1][k * 32 + lane] = gg; s_g[2][k * 32 + lane] = gb;
-        s_g[3][k * 32 + lane] = gd; s_g[4][k * 32 + lane] = ga;
-        T[k] = Tf;
-        tfb[k] = -Tf * (bg0 * gr + bg1 * gg + bg2 * gb);
-        Ar[k] = 0.f; Ag[k] = 0.f; Ab[k] = 0.f; Ad[k] = 0.f; Aa[k] = 0.f;
-        slot_lc[k] = __reduce_max_sync(0xffffffffu, lc[k]);
-        toDo = max(toDo, slot_lc[k]);
+        s_g4[k * 32 + lane] = make_float4(gr, gg, gb, gd);
+        s_ga[k * 32 + lane] = ga;
+        T[i] = Tf;
+        tfb[i] = -Tf * (bg0 * gr + bg1 * gg + bg2 * gb);
+        Ar[i] = 0.f; Ag[i] = 0.f; Ab[i] = 0.f; Ad[i] = 0.f; Aa[i] = 0.f;
+        slot_lc[i] = __reduce_max_sync(0xffffffffu, lc[i]);
+        toDo = max(toDo, slot_lc[i]);
     }
     const float pxf = (float)(X0 + lx), pyf = (float)(Y0 + ly);
-    // (each lane only ever reads back the s_g entries it wrote itself: no barrier needed)
+    // (each lane only ever reads back the s_g4 / s_ga entries it wrote itself: no barrier needed)
 
     // batch entry j  <->  0-based list position  pos = toDo - 1 - (base + j)   (back to front)
     Rec nxt;
@@ -267,8 +298,8 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
             const int mypos = toDo - 1 - (base + lane);
             uint32_t live = 0u;
 #pragma unroll
-            for (int k = 0; k < SLOTS; k++)
-                if (mypos < slot_lc[k]) live |= 1u << k;
+            for (int i = 0; i < SPW; i++)
+                if (mypos < slot_lc[i]) live |= 1u << (k0 + i);
             mymask = slot_mask(cur, (float)X0, (float)Y0, live);
         }
         for (int j = 0; j < cnt; j++) {
@@ -279,30 +310,32 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
             const float4 q1 = s_q1[j];
             const float4 q2 = s_q2[j];
             const float dx0 = q0.x - pxf, dy0 = q0.y - pyf;
+            const float thr = q1.w - PREFILTER_MARGIN;
             float v[10];
 #pragma unroll
             for (int i = 0; i < 10; i++) v[i] = 0.f;
             bool touched = false;
 #pragma unroll
-            for (int k = 0; k < SLOTS; k++) {
+            for (int i = 0; i < SPW; i++) {
+                const int k = k0 + i;
                 if (!(mj & (1u << k))) continue;      // warp-uniform
                 const float dx = dx0 - (float)((k & 1) << 3), dy = dy0 - (float)((k >> 1) << 2);
                 const float power = dx * (q0.z * dx + q0.w * dy) + q1.x * dy * dy;
-                if (pos >= lc[k] || power > 0.f || power < q1.w - PREFILTER_MARGIN) continue;
+                if (pos >= lc[i] || power > 0.f || power < thr) continue;
                 const float G = ex2(power);
                 const float alpha = fminf(ALPHA_MAX, q1.y * G);
                 if (alpha < ALPHA_MIN) continue;
                 touched = true;
-                const float ra = 1.f / (1.f - alpha);
-                T[k] *= ra;                                  // transmittance in front of this Gaussian
-                const float gr = s_g[0][k * 32 + lane], gg = s_g[1][k * 32 + lane], gb = s_g[2][k * 32 + lane];
-                const float gd = s_g[3][k * 32 + lane], ga = s_g[4][k * 32 + lane];
+                const float ra = rcp_approx(1.f - alpha);   // 1 - alpha >= 0.01
+                T[i] *= ra;                                  // transmittance in front of this Gaussian
+                const float4 g4 = s_g4[k * 32 + lane];
+                const float gr = g4.x, gg = g4.y, gb = g4.z, gd = g4.w, ga = s_ga[k * 32 + lane];
                 // suffix-blended values behind this Gaussian: A* = alpha_{j+1} c_{j+1} + (1-alpha_{j+1}) A*
-                const float er = q2.x - Ar[k], eg = q2.y - Ag[k], eb = q2.z - Ab[k], ed = q1.z - Ad[k], ea = 1.f - Aa[k];
+                const float er = q2.x - Ar[i], eg = q2.y - Ag[i], eb = q2.z - Ab[i], ed = q1.z - Ad[i], ea = 1.f - Aa[i];
                 float dL_dalpha_ = er * gr + eg * gg + eb * gb + ed * gd + ea * ga;
-                Ar[k] += alpha * er; Ag[k] += alpha * eg; Ab[k] += alpha * eb; Ad[k] += alpha * ed; Aa[k] += alpha * ea;
-                dL_dalpha_ = dL_dalpha_ * T[k] + tfb[k] * ra;
-                const float w = alpha * T[k];
+                Ar[i] += alpha * er; Ag[i] += alpha * eg; Ab[i] += alpha * eb; Ad[i] += alpha * ed; Aa[i] += alpha * ea;
+                dL_dalpha_ = dL_dalpha_ * T[i] + tfb[i] * ra;
+                const float w = alpha * T[i];
                 const float u = q1.y * dL_dalpha_;           // dL/dG, propagated even when alpha was capped (A.9)
                 const float gdx = G * dx, gdy = G * dy;
                 v[0] += u * (2.f * q0.z * gdx + q0.w * gdy);  // * ln2  = dL/dmean_x (pixel units)
@@ -324,6 +357,11 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     }
 }
 
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 }  // namespace
 
 void launch_render_forward(const ScgrView& v, const GeometryLayout& G, const BinningLayout& B,
@@ -331,10 +369,12 @@ void launch_render_forward(const ScgrView& v, const GeometryLayout& G, const Bin
                            float* out_color, float* out_depth, float* out_alpha, const Launch& L) {
     const dim3 grid((v.image_width + TILE - 1) / TILE, (v.image_height + TILE - 1) / TILE);
     if (grid.x == 0 || grid.y == 0) return;
+    static const int wpt = env_int("SCGR_FWD_WPT", 1);
     begin_kernel("render_forward", L);
-    render_forward_kernel<<<grid, 32, 0, L.stream>>>(B.ranges, point_list, G.rec, v.image_width,
-                                                     v.image_height, v.bg, G.status, capacity, out_color,
-                                                     out_depth, out_alpha, I.n_contrib, I.final_T);
+#define SCGR_FWD(W_) render_forward_kernel<W_><<<grid, 32 * W_, 0, L.stream>>>(B.ranges, point_list, G.rec, \
+        v.image_width, v.image_height, v.bg, G.status, capacity, out_color, out_depth, out_alpha, I.n_contrib, I.final_T)
+    if (wpt == 2) SCGR_FWD(2); else if (wpt == 4) SCGR_FWD(4); else SCGR_FWD(1);
+#undef SCGR_FWD
     check_launch("render_forward", L);
 }
 
@@ -345,10 +385,13 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
     const dim3 grid((v.image_width + TILE - 1) / TILE, (v.image_height + TILE - 1) / TILE);
     cudaMemsetAsync(G.screen_grad, 0, (size_t)(P > 0 ? P : 0) * sizeof(ScreenGrad), L.stream);
     if (grid.x == 0 || grid.y == 0) return;
+    static const int wpt = env_int("SCGR_BWD_WPT", 1);
     begin_kernel("render_backward", L);
-    render_backward_kernel<<<grid, 32, 0, L.stream>>>(B.ranges, point_list, G.rec, v.image_width,
-                                                      v.image_height, v.bg, G.status, capacity, I.n_contrib,
-                                                      I.final_T, dL_dcolor, dL_ddepth, dL_dalpha, G.screen_grad);
+#define SCGR_BWD(W_) render_backward_kernel<W_><<<grid, 32 * W_, 0, L.stream>>>(B.ranges, point_list, G.rec, \
+        v.image_width, v.image_height, v.bg, G.status, capacity, I.n_contrib, I.final_T, dL_dcolor, dL_ddepth, \
+        dL_dalpha, G.screen_grad)
+    if (wpt == 2) SCGR_BWD(2); else if (wpt == 4) SCGR_BWD(4); else SCGR_BWD(1);
+#undef SCGR_BWD
     check_launch("render_backward", L);
 }
 

@@ -357,4 +357,5 @@ def debug_views(state: ForwardState, P: int, s: GaussianRasterizationSettings) -
         "n_contrib": grab(state.image, dv.n_contrib, W * H * 4, torch.int32).view(H, W),
         "final_T": grab(state.image, dv.final_T, W * H * 4, torch.float32).view(H, W),
     }
+    out["ranges"][out["ranges"][:, 1] == 0] = 0      # empty tiles are stored as (0xffffffff, 0)
     return out
