@@ -74,8 +74,8 @@ __device__ __forceinline__ uint32_t slot_mask(const Rec& r, const float X0, cons
 // ------------------------------------------------------------------------------------------
 // WPT warps share a tile: warp w owns slots [w * SLOTS / WPT, (w + 1) * SLOTS / WPT).  The warps of a
 // tile never synchronise with each other (disjoint pixels, private staging buffers).
-template <int WPT>
-__global__ void __launch_bounds__(32 * WPT)
+template <int WPT, int MINB>
+__global__ void __launch_bounds__(32 * WPT, MINB)
 render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                       const Record* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                       const int64_t* __restrict__ status, int64_t capacity, float* __restrict__ out_color,
@@ -220,8 +220,8 @@ __device__ __forceinline__ float transpose_reduce10(const float v[10], const int
     return d;
 }
 
-template <int WPT>
-__global__ void __launch_bounds__(32 * WPT)
+template <int WPT, int MINB, bool PRED>
+__global__ void __launch_bounds__(32 * WPT, MINB)
 render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                        const Record* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                        const int64_t* __restrict__ status, int64_t capacity,
@@ -321,11 +321,23 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
                 if (!(mj & (1u << k))) continue;      // warp-uniform
                 const float dx = dx0 - (float)((k & 1) << 3), dy = dy0 - (float)((k >> 1) << 2);
                 const float power = dx * (q0.z * dx + q0.w * dy) + q1.x * dy * dy;
-                if (pos >= lc[i] || power > 0.f || power < thr) continue;
-                const float G = ex2(power);
-                const float alpha = fminf(ALPHA_MAX, q1.y * G);
-                if (alpha < ALPHA_MIN) continue;
-                touched = true;
+                float G, alpha;
+                if (PRED) {
+                    // straight-line: a pair that fails the reference's tests (A.9) runs with G = alpha = 0,
+                    // which makes every term below vanish and leaves the pixel state untouched
+                    const float Graw = ex2(power);
+                    const float araw = fminf(ALPHA_MAX, q1.y * Graw);
+                    const bool ok = pos < lc[i] && power <= 0.f && power >= thr && araw >= ALPHA_MIN;
+                    touched |= ok;
+                    G = ok ? Graw : 0.f;
+                    alpha = ok ? araw : 0.f;
+                } else {
+                    if (pos >= lc[i] || power > 0.f || power < thr) continue;
+                    G = ex2(power);
+                    alpha = fminf(ALPHA_MAX, q1.y * G);
+                    if (alpha < ALPHA_MIN) continue;
+                    touched = true;
+                }
                 const float ra = rcp_approx(1.f - alpha);   // 1 - alpha >= 0.01
                 T[i] *= ra;                                  // transmittance in front of this Gaussian
                 const float4 g4 = s_g4[k * 32 + lane];
@@ -371,9 +383,11 @@ void launch_render_forward(const ScgrView& v, const GeometryLayout& G, const Bin
     if (grid.x == 0 || grid.y == 0) return;
     static const int wpt = env_int("SCGR_FWD_WPT", 1);
     begin_kernel("render_forward", L);
-#define SCGR_FWD(W_) render_forward_kernel<W_><<<grid, 32 * W_, 0, L.stream>>>(B.ranges, point_list, G.rec, \
+    static const int minb = env_int("SCGR_FWD_MINB", 20);
+#define SCGR_FWD(W_, M_) render_forward_kernel<W_, M_><<<grid, 32 * W_, 0, L.stream>>>(B.ranges, point_list, G.rec, \
         v.image_width, v.image_height, v.bg, G.status, capacity, out_color, out_depth, out_alpha, I.n_contrib, I.final_T)
-    if (wpt == 2) SCGR_FWD(2); else if (wpt == 4) SCGR_FWD(4); else SCGR_FWD(1);
+    if (wpt == 2) SCGR_FWD(2, 1); else if (wpt == 4) SCGR_FWD(4, 1); else if (minb == 20) SCGR_FWD(1, 20);
+    else if (minb == 24) SCGR_FWD(1, 24); else SCGR_FWD(1, 1);
 #undef SCGR_FWD
     check_launch("render_forward", L);
 }
@@ -387,10 +401,15 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
     if (grid.x == 0 || grid.y == 0) return;
     static const int wpt = env_int("SCGR_BWD_WPT", 1);
     begin_kernel("render_backward", L);
-#define SCGR_BWD(W_) render_backward_kernel<W_><<<grid, 32 * W_, 0, L.stream>>>(B.ranges, point_list, G.rec, \
-        v.image_width, v.image_height, v.bg, G.status, capacity, I.n_contrib, I.final_T, dL_dcolor, dL_ddepth, \
+    static const int minb = env_int("SCGR_BWD_MINB", 0);
+    static const int pred = env_int("SCGR_BWD_PRED", 1);
+#define SCGR_BWD(W_, M_, P_) render_backward_kernel<W_, M_, P_><<<grid, 32 * W_, 0, L.stream>>>(B.ranges, point_list, \
+        G.rec, v.image_width, v.image_height, v.bg, G.status, capacity, I.n_contrib, I.final_T, dL_dcolor, dL_ddepth, \
         dL_dalpha, G.screen_grad)
-    if (wpt == 2) SCGR_BWD(2); else if (wpt == 4) SCGR_BWD(4); else SCGR_BWD(1);
+    if (wpt == 2) SCGR_BWD(2, 1, true); else if (wpt == 4) SCGR_BWD(4, 1, true);
+    else if (!pred) SCGR_BWD(1, 1, false);
+    else if (minb == 16) SCGR_BWD(1, 16, true); else if (minb == 14) SCGR_BWD(1, 14, true);
+    else SCGR_BWD(1, 1, true);
 #undef SCGR_BWD
     check_launch("render_backward", L);
 }
