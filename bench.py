@@ -176,7 +176,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     W_ = max(3, args.warmup)
     K = max(1, args.steps)
 
@@ -192,10 +193,10 @@ def main():
     flat = FlatGradBuffer(P_GAUSS, sh_coeffs=(SH_DEG + 1) ** 2, device=dev)
     out_views = flat.out_dict()
 
-    def step():
+    def step(collective=True):
         color, radii, depth, alpha, state = R.rasterize_forward_raw(*args_in, s)
         R.rasterize_backward_raw(state, *args_in, s, gC, gD, gA, out=out_views)
-        if world > 1:
+        if world > 1 and collective:
             flat.fill_stats(radii)
             flat.all_reduce()               # THE collective of the path
         return state
@@ -236,7 +237,7 @@ def main():
         lib.scgr_profile_enable(1)
         nprof = min(K, 5)
         for _ in range(nprof):
-            step()
+            step(collective=False)          # rank 0 only: must not enter a collective
         torch.cuda.synchronize()
         import ctypes as C
         names = (C.c_char_p * 4096)()
@@ -270,8 +271,11 @@ def main():
             loss = (color - gt).abs().mean() + 0.01 * depth.mean() + 0.01 * alpha.mean()
             loss.backward()
             if world > 1:
-                for v in leaves.values():
-                    dist.all_reduce(v.grad)
+                # one all-reduce for the public-API path too: pack the leaf gradients into the flat buffer
+                for name, v in leaves.items():
+                    flat.views[name].copy_(v.grad.reshape(flat.views[name].shape))
+                flat.fill_stats(radii)
+                flat.all_reduce()
             loss_host.copy_(loss.detach().reshape(1), non_blocking=False)   # D2H read of the step's result
             for v in leaves.values():
                 v.grad = None
