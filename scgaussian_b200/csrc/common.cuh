@@ -28,8 +28,9 @@ static_assert(sizeof(Record) == 48, "Record must be 48 bytes");
 
 // ---- per-Gaussian screen-space gradient accumulator written by render-backward (48 B) ----
 // raw sums over (pixel, Gaussian) pairs; preprocess-backward applies the constant factors:
-//   a0 = {Sx, Sy, SA, SB}     dL/dmean_xy (pixels) = ln2 * S{x,y};  dL/dconic_{A,B} = {-0.5 SA, -SB}
-//   a1 = {SC, dL/dopacity, dL/ddepth, 0}     dL/dconic_C = -0.5 SC   (dL/dconic_B is the true derivative)
+// with u = opacity * G * dL/dalpha per pair:
+//   a0 = {Sx, Sy, SA, SB} = sum {u dx, u dy, u dx^2, u dx dy}    dL/dmean (pixels) = ln2 * (2cA Sx + cB Sy, 2cC Sy + cB Sx)
+//   a1 = {SC, Su, dL/ddepth, 0} = sum {u dy^2, u, ...}           dL/dconic = (-0.5 SA, -SB, -0.5 SC), dL/dopacity = Su / opacity
 //   a2 = {dL/dr, dL/dg, dL/db, 0}
 struct __align__(16) ScreenGrad {
     float4 a0, a1, a2;

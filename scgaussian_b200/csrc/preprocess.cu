@@ -304,14 +304,19 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
     const CullParams cp = make_cull(r.q0, r.q1);
     uint32_t touched = 0u;
     unsigned long long mask = 0ull;
-    const int rw = x1 - x0;
-    const bool small_rect = rw * (y1 - y0) <= 64;
-    for (int ty = y0; ty < y1; ty++)
-        for (int tx = x0; tx < x1; tx++)
-            if (tile_may_contribute(cp, tx, ty)) {
-                touched++;
-                if (small_rect) mask |= 1ull << ((ty - y0) * rw + (tx - x0));
-            }
+    const int rw = x1 - x0, ntiles = rw * (y1 - y0);
+    const bool small_rect = ntiles <= 64;
+    // one flat loop over the rect (row-major, bit k = k-th tile): lanes of a warp diverge only by
+    // their total tile count, not per row
+    int tx = x0, ty = y0;
+#pragma unroll 1
+    for (int k = 0; k < ntiles; k++) {
+        if (tile_may_contribute(cp, tx, ty)) {
+            touched++;
+            if (small_rect) mask |= 1ull << k;
+        }
+        if (++tx == x1) { tx = x0; ty++; }
+    }
     tiles_touched[i] = touched;
     tile_mask[i] = mask;
     depth_key[i] = __float_as_uint(zv);   // zv > 0.2 => bit order == numeric order (A.6)
@@ -362,9 +367,11 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
         const float* PM = cam.PM;
         // render-backward stores raw sums (render.cu): scale them into true derivatives here
         constexpr float LN2 = 0.6931471805599453f;
-        dm2x = LN2 * A.a0.x * (0.5f * v.image_width);    // NDC units (A.9)
-        dm2y = LN2 * A.a0.y * (0.5f * v.image_height);
-        dop = A.a1.y;
+        const float4 rq0 = rec[i].q0, rq1 = rec[i].q1;
+        const float Sx = A.a0.x, Sy = A.a0.y;            // sum u G dx, sum u G dy
+        dm2x = LN2 * (2.f * rq0.z * Sx + rq0.w * Sy) * (0.5f * v.image_width);    // NDC units (A.9)
+        dm2y = LN2 * (2.f * rq1.x * Sy + rq0.w * Sx) * (0.5f * v.image_height);
+        dop = A.a1.y / rq1.y;                            // sum (opacity G) dL/dalpha  ->  sum G dL/dalpha
         // (1) conic -> cov2D
         float c6[6];
         float4 q = make_float4(1.f, 0.f, 0.f, 0.f);

@@ -232,7 +232,6 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     __shared__ float4 s_q0_[WPT][32], s_q1_[WPT][32], s_q2_[WPT][32];
     __shared__ uint32_t s_id_[WPT][32];
     __shared__ float4 s_g4[TILE_PIX];       // upstream gradients of the tile: r, g, b, depth
-    __shared__ float s_ga[TILE_PIX];        //                                 alpha
     if (status[0] > capacity) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int k0 = wid * SPW;             // first slot of this warp
@@ -246,7 +245,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
     const size_t N = (size_t)W * H;
 
-    float T[SPW], Ar[SPW], Ag[SPW], Ab[SPW], Ad[SPW], Aa[SPW], tfb[SPW];
+    float T[SPW], Ar[SPW], Ag[SPW], Ab[SPW], Ad[SPW], tfb[SPW];
     int lc[SPW];
     int slot_lc[SPW];
     int toDo = 0;
@@ -265,15 +264,14 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
             ga = dL_dalpha[pid];
         }
         s_g4[k * 32 + lane] = make_float4(gr, gg, gb, gd);
-        s_ga[k * 32 + lane] = ga;
         T[i] = Tf;
-        tfb[i] = -Tf * (bg0 * gr + bg1 * gg + bg2 * gb);
-        Ar[i] = 0.f; Ag[i] = 0.f; Ab[i] = 0.f; Ad[i] = 0.f; Aa[i] = 0.f;
+        tfb[i] = Tf * (ga - (bg0 * gr + bg1 * gg + bg2 * gb));
+        Ar[i] = 0.f; Ag[i] = 0.f; Ab[i] = 0.f; Ad[i] = 0.f;
         slot_lc[i] = __reduce_max_sync(0xffffffffu, lc[i]);
         toDo = max(toDo, slot_lc[i]);
     }
     const float pxf = (float)(X0 + lx), pyf = (float)(Y0 + ly);
-    // (each lane only ever reads back the s_g4 / s_ga entries it wrote itself: no barrier needed)
+    // (each lane only ever reads back the s_g4 entries it wrote itself: no barrier needed)
 
     // batch entry j  <->  0-based list position  pos = toDo - 1 - (base + j)   (back to front)
     Rec nxt;
@@ -321,44 +319,43 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
                 if (!(mj & (1u << k))) continue;      // warp-uniform
                 const float dx = dx0 - (float)((k & 1) << 3), dy = dy0 - (float)((k >> 1) << 2);
                 const float power = dx * (q0.z * dx + q0.w * dy) + q1.x * dy * dy;
-                float G, alpha;
+                float og, alpha;       // og = opacity * G (un-capped), alpha = min(0.99, og)
                 if (PRED) {
-                    // straight-line: a pair that fails the reference's tests (A.9) runs with G = alpha = 0,
+                    // straight-line: a pair that fails the reference's tests (A.9) runs with og = alpha = 0,
                     // which makes every term below vanish and leaves the pixel state untouched
-                    const float Graw = ex2(power);
-                    const float araw = fminf(ALPHA_MAX, q1.y * Graw);
+                    const float ograw = q1.y * ex2(power);
+                    const float araw = fminf(ALPHA_MAX, ograw);
                     const bool ok = pos < lc[i] && power <= 0.f && power >= thr && araw >= ALPHA_MIN;
                     touched |= ok;
-                    G = ok ? Graw : 0.f;
+                    og = ok ? ograw : 0.f;
                     alpha = ok ? araw : 0.f;
                 } else {
                     if (pos >= lc[i] || power > 0.f || power < thr) continue;
-                    G = ex2(power);
-                    alpha = fminf(ALPHA_MAX, q1.y * G);
+                    og = q1.y * ex2(power);
+                    alpha = fminf(ALPHA_MAX, og);
                     if (alpha < ALPHA_MIN) continue;
                     touched = true;
                 }
                 const float ra = rcp_approx(1.f - alpha);   // 1 - alpha >= 0.01
                 T[i] *= ra;                                  // transmittance in front of this Gaussian
-                const float4 g4 = s_g4[k * 32 + lane];
-                const float gr = g4.x, gg = g4.y, gb = g4.z, gd = g4.w, ga = s_ga[k * 32 + lane];
-                // suffix-blended values behind this Gaussian: A* = alpha_{j+1} c_{j+1} + (1-alpha_{j+1}) A*
-                const float er = q2.x - Ar[i], eg = q2.y - Ag[i], eb = q2.z - Ab[i], ed = q1.z - Ad[i], ea = 1.f - Aa[i];
-                float dL_dalpha_ = er * gr + eg * gg + eb * gb + ed * gd + ea * ga;
-                Ar[i] += alpha * er; Ag[i] += alpha * eg; Ab[i] += alpha * eb; Ad[i] += alpha * ed; Aa[i] += alpha * ea;
+                const float4 g4 = s_g4[k * 32 + lane];      // upstream dL/d{r, g, b, depth} of this pixel
+                // suffix-blended values behind this Gaussian: A* <- alpha c + (1 - alpha) A*   (after use)
+                const float er = q2.x - Ar[i], eg = q2.y - Ag[i], eb = q2.z - Ab[i], ed = q1.z - Ad[i];
+                float dL_dalpha_ = er * g4.x + eg * g4.y + eb * g4.z + ed * g4.w;
+                Ar[i] += alpha * er; Ag[i] += alpha * eg; Ab[i] += alpha * eb; Ad[i] += alpha * ed;
+                // the alpha output and the background enter as T_final / (1 - alpha) * (dL/dalpha_pix - bg . dL/dC)
                 dL_dalpha_ = dL_dalpha_ * T[i] + tfb[i] * ra;
                 const float w = alpha * T[i];
-                const float u = q1.y * dL_dalpha_;           // dL/dG, propagated even when alpha was capped (A.9)
-                const float gdx = G * dx, gdy = G * dy;
-                v[0] += u * (2.f * q0.z * gdx + q0.w * gdy);  // * ln2  = dL/dmean_x (pixel units)
-                v[1] += u * (2.f * q1.x * gdy + q0.w * gdx);  // * ln2  = dL/dmean_y
-                const float ux = u * gdx;
+                const float uG = og * dL_dalpha_;            // G * dL/dG; propagated even when alpha was capped (A.9)
+                const float ux = uG * dx, uy = uG * dy;
+                v[0] += ux;                                  // preprocess-backward rebuilds dL/dmean from these two
+                v[1] += uy;
                 v[2] += ux * dx;                             // * -0.5 = dL/dconic_A
                 v[3] += ux * dy;                             // * -1   = dL/dconic_B
-                v[4] += u * gdy * dy;                        // * -0.5 = dL/dconic_C
-                v[5] += G * dL_dalpha_;                      // dL/dopacity
-                v[6] += w * gd;                              // dL/ddepth
-                v[7] += w * gr; v[8] += w * gg; v[9] += w * gb;
+                v[4] += uy * dy;                             // * -0.5 = dL/dconic_C
+                v[5] += uG;                                  // / opacity = dL/dopacity
+                v[6] += w * g4.w;                            // dL/ddepth
+                v[7] += w * g4.x; v[8] += w * g4.y; v[9] += w * g4.z;
             }
             if (!__any_sync(0xffffffffu, touched)) continue;
             int slot;
@@ -401,7 +398,7 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
     if (grid.x == 0 || grid.y == 0) return;
     static const int wpt = env_int("SCGR_BWD_WPT", 1);
     begin_kernel("render_backward", L);
-    static const int minb = env_int("SCGR_BWD_MINB", 0);
+    static const int minb = env_int("SCGR_BWD_MINB", 14);
     static const int pred = env_int("SCGR_BWD_PRED", 1);
 #define SCGR_BWD(W_, M_, P_) render_backward_kernel<W_, M_, P_><<<grid, 32 * W_, 0, L.stream>>>(B.ranges, point_list, \
         G.rec, v.image_width, v.image_height, v.bg, G.status, capacity, I.n_contrib, I.final_T, dL_dcolor, dL_ddepth, \
