@@ -304,19 +304,14 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
     const CullParams cp = make_cull(r.q0, r.q1);
     uint32_t touched = 0u;
     unsigned long long mask = 0ull;
-    const int rw = x1 - x0, ntiles = rw * (y1 - y0);
-    const bool small_rect = ntiles <= 64;
-    // one flat loop over the rect (row-major, bit k = k-th tile): lanes of a warp diverge only by
-    // their total tile count, not per row
-    int tx = x0, ty = y0;
-#pragma unroll 1
-    for (int k = 0; k < ntiles; k++) {
-        if (tile_may_contribute(cp, tx, ty)) {
-            touched++;
-            if (small_rect) mask |= 1ull << k;
-        }
-        if (++tx == x1) { tx = x0; ty++; }
-    }
+    const int rw = x1 - x0;
+    const bool small_rect = rw * (y1 - y0) <= 64;
+    for (int ty = y0; ty < y1; ty++)
+        for (int tx = x0; tx < x1; tx++)
+            if (tile_may_contribute(cp, tx, ty)) {
+                touched++;
+                if (small_rect) mask |= 1ull << ((ty - y0) * rw + (tx - x0));
+            }
     tiles_touched[i] = touched;
     tile_mask[i] = mask;
     depth_key[i] = __float_as_uint(zv);   // zv > 0.2 => bit order == numeric order (A.6)

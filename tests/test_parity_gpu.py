@@ -167,6 +167,8 @@ CASES = [
     (2000, 63, 49, 1, 0.10, (0.2, 0.5, 0.7), 1.4, -20.0),      # big splats, scale_modifier
     (5000, 378, 504, 0, 0.03, (0.0, 0.0, 0.0), 1.0, 5.0),      # config-2 resolution (504x378 transposed)
     (40, 16, 16, 3, 0.30, (0.3, 0.3, 0.3), 1.0, 0.0),          # a single tile, huge overlapping splats
+    (600, 256, 192, 2, 0.60, (0.1, 0.0, 0.2), 1.0, 10.0),      # rects of > 64 tiles: warp-cooperative emission path
+    (3000, 4096, 4096, 1, 0.02, (0.0, 0.0, 0.0), 1.0, 0.0),    # 65536 tiles = 17-bit tile ids: 3 partition passes
 ]
 
 
@@ -187,6 +189,38 @@ def test_forward_backward_match_oracle(dev, P, W, H, deg, smed, bg, mod, yaw):
         errs[k] = util.assert_grad_close(k, g[k], g64[k].reshape(g[k].shape))
     assert np.all(g["means2D"][:, 2] == 0)
     report("fwd_bwd", P=P, W=W, H=H, deg=deg, color=ec, depth=ed, alpha=ea, grads=errs, R=int(co.num_rendered))
+
+
+@pytest.mark.parametrize("deg,max_deg", [(1, 1), (2, 2), (0, 2)])
+def test_sh_layouts_other_than_16_coefficients(dev, deg, max_deg):
+    """M = 4 / 9 coefficients per Gaussian take the generic (non-staged) SH load/store path."""
+    case = util.make_case(2500, 144, 112, sh_degree=deg, max_sh_degree=max_deg, scale_median=0.06, bg=(0.2, 0.1, 0.0))
+    grads = O.synth_upstream_grads(case["W"], case["H"])
+    (c, r, d, a), g = gpu_forward_backward(case, dev, grads)
+    co, (c2, r2, d2, a2), g2 = util.run_c_oracle(case, "f64", grads=grads)
+    util.assert_image_close("color", c, c2)
+    for k in ("means3D", "means2D", "opacities", "shs", "scales", "rotations"):
+        util.assert_grad_close(k, g[k], g2[k].reshape(g[k].shape))
+    assert g["shs"].shape == (2500, (max_deg + 1) ** 2, 3)
+
+
+def test_near_plane_and_lateral_clamp(dev):
+    """z in [0.1, 8.1]: some Gaussians behind the 0.2 near plane (culled), some so close that their
+    splats cover hundreds of tiles and the 1.3*tanfov clamp of A.4 is active (zeroed x/y gradient)."""
+    case = util.make_case(1500, 200, 152, sh_degree=2, scale_median=0.08, bg=(0.0, 0.3, 0.1), z_shift=-1.9)
+    case["means3D"][:, :2] *= 1.5              # push a share of the points outside the frustum laterally
+    grads = O.synth_upstream_grads(case["W"], case["H"])
+    (c, r, d, a), g = gpu_forward_backward(case, dev, grads)
+    co, (c2, r2, d2, a2), g2 = util.run_c_oracle(case, "f64", grads=grads)
+    z = case["means3D"][:, 2].numpy()
+    xz = np.abs(case["means3D"][:, 0].numpy() / z)
+    assert (z <= 0.2).sum() > 10 and r2.max() > 100 and ((xz > 1.3 * case["tanfovx"]) & (r2 > 0)).sum() > 10
+    assert (r != r2).sum() <= 2
+    util.assert_image_close("color", c, c2, flip_frac=1e-3)
+    util.assert_image_close("depth", d, d2, flip_frac=1e-3)
+    for k in ("means3D", "means2D", "opacities", "shs", "scales", "rotations"):
+        util.assert_grad_close(k, g[k], g2[k].reshape(g[k].shape), flip_frac=3e-3)
+    report("near_plane", culled=int((r2 == 0).sum()), max_radius=int(r2.max()), R=int(co.num_rendered))
 
 
 def test_precomputed_colour_and_covariance_paths(dev):
