@@ -200,10 +200,11 @@ depth_hist_kernel(const uint32_t* __restrict__ keys, int n, uint32_t* __restrict
 
 // peers of this lane = lanes holding the same (<= 8-bit) digit.  8 independent ballots instead of
 // one MATCH.ANY: VOTE has a short fixed latency and the ballots of all items pipeline.
-__device__ __forceinline__ uint32_t peers_by_ballot(const uint32_t d, const bool valid) {
+__device__ __forceinline__ uint32_t peers_by_ballot(const uint32_t d, const bool valid, const int nbits) {
     uint32_t peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
     for (int b = 0; b < 8; b++) {
+        if (b >= nbits) break;      // warp-uniform: the pass's digit has only nbits bits
         const bool bit = (d >> b) & 1u;
         const uint32_t bal = __ballot_sync(0xffffffffu, bit);
         peers &= bit ? bal : ~bal;
@@ -246,6 +247,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     const uint32_t n = load_count(n_dev, n_host, cap);
     const uint32_t base = tile * RADIX_TILE;
     if (base >= n) return;      // tiles past the end are never waited on
+    const int nbits = __popc(mask);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t in_tile = min((uint32_t)RADIX_TILE, n - base);
 
@@ -274,7 +276,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
         const bool valid = base + w * PER_WARP + it * 32 + lane < n;
         const uint32_t d = (key[it] >> shift) & mask;
         // invalid lanes become singletons that match nobody
-        peers[it] = BALLOT ? peers_by_ballot(d, valid)
+        peers[it] = BALLOT ? peers_by_ballot(d, valid, nbits)
                            : __match_any_sync(0xffffffffu, valid ? d : (0x10000u | (uint32_t)lane));
     }
 #pragma unroll
@@ -428,19 +430,21 @@ struct TilePasses {
 // consecutive threads own consecutive slices, so a warp's stores fall into a few cache lines.
 // Rects of more than 64 tiles (no mask) are handled afterwards by the whole warp: the 32 lanes
 // re-run the exact test on 32 tiles at a time and compact the survivors with a ballot.
+template <int PASSES>
 __global__ void __launch_bounds__(EMIT_THREADS)
 emit_instances_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
                       const uint2* __restrict__ rect, const unsigned long long* __restrict__ tile_mask,
                       const Record* __restrict__ rec, int P, int grid_x, int64_t capacity,
                       int64_t* __restrict__ status, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                       uint32_t* __restrict__ sweep, size_t pass_words, const TilePasses tp) {
-    __shared__ uint32_t s_hist[MAX_TILE_PASSES][RADIX_BINS];
+    __shared__ uint32_t s_hist[PASSES][RADIX_BINS];
     const int64_t R = status[0];
     if (R > capacity) {
         if (blockIdx.x == 0 && threadIdx.x == 0) status[1] = 1;
         return;
     }
-    for (int p = 0; p < tp.passes; p++) s_hist[p][threadIdx.x] = 0u;
+#pragma unroll
+    for (int p = 0; p < PASSES; p++) s_hist[p][threadIdx.x] = 0u;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -457,37 +461,32 @@ emit_instances_kernel(const uint32_t* __restrict__ order, const uint32_t* __rest
         }
     }
     const bool big = rw * rh > 64u;
+    // digit extraction of the partition passes, in registers
+    int sh[PASSES];
+    uint32_t mk[PASSES];
+#pragma unroll
+    for (int p = 0; p < PASSES; p++) { sh[p] = tp.shift[p]; mk[p] = tp.mask[p]; }
     if (end != begin && !big) {
         unsigned long long m = tile_mask[gid];
         uint32_t pos = begin;
-        const uint32_t row_bits = rw >= 32u ? 0xffffffffu : ((1u << rw) - 1u);
-        for (uint32_t ty = 0; ty < rh && m; ty++) {
-            uint32_t row = (uint32_t)m & row_bits;     // rw <= 64 / rh; rows wider than 32 only if rh == 1 or 2
-            if (rw > 32u) {                            // (rare) 33..64-tile wide single/double rows: take 64-bit path
-                unsigned long long row64 = rw >= 64u ? m : (m & ((1ull << rw) - 1ull));
-                while (row64) {
-                    const uint32_t tx = (uint32_t)__ffsll((long long)row64) - 1u;
-                    row64 &= row64 - 1ull;
-                    const uint32_t tile = (y0 + ty) * (uint32_t)grid_x + x0 + tx;
-                    if (pos < end) {
-                        keys[pos] = tile; vals[pos] = gid;
-                        for (int p = 0; p < tp.passes; p++) atomicAdd(&s_hist[p][(tile >> tp.shift[p]) & tp.mask[p]], 1u);
-                    }
-                    pos++;
+        uint32_t rowbase = y0 * (uint32_t)grid_x + x0;     // tile id of the rect's row start
+        const unsigned long long row_bits = rw >= 64u ? ~0ull : ((1ull << rw) - 1ull);
+        while (m) {
+            unsigned long long row = m & row_bits;
+            while (row) {
+                const uint32_t tx = (uint32_t)__ffsll((long long)row) - 1u;
+                row &= row - 1ull;
+                const uint32_t tile = rowbase + tx;
+                if (pos < end) {      // always true: the mask has exactly end - begin bits
+                    keys[pos] = tile;
+                    vals[pos] = gid;
+#pragma unroll
+                    for (int p = 0; p < PASSES; p++) atomicAdd(&s_hist[p][(tile >> sh[p]) & mk[p]], 1u);
                 }
-            } else {
-                while (row) {
-                    const uint32_t tx = (uint32_t)__ffs((int)row) - 1u;
-                    row &= row - 1u;
-                    const uint32_t tile = (y0 + ty) * (uint32_t)grid_x + x0 + tx;
-                    if (pos < end) {      // always true: the mask has exactly end - begin bits
-                        keys[pos] = tile; vals[pos] = gid;
-                        for (int p = 0; p < tp.passes; p++) atomicAdd(&s_hist[p][(tile >> tp.shift[p]) & tp.mask[p]], 1u);
-                    }
-                    pos++;
-                }
+                pos++;
             }
             m = rw >= 64u ? 0ull : (m >> rw);
+            rowbase += (uint32_t)grid_x;
         }
     }
     // large rects, warp-cooperatively
@@ -530,7 +529,8 @@ emit_instances_kernel(const uint32_t* __restrict__ order, const uint32_t* __rest
                     if (pos < e) {      // always true: same bit-exact test as the counting pass
                         keys[pos] = tile;
                         vals[pos] = g;
-                        for (int p = 0; p < tp.passes; p++) atomicAdd(&s_hist[p][(tile >> tp.shift[p]) & tp.mask[p]], 1u);
+#pragma unroll
+                        for (int p = 0; p < PASSES; p++) atomicAdd(&s_hist[p][(tile >> sh[p]) & mk[p]], 1u);
                     }
                 }
                 out += __popc(bal);
@@ -538,7 +538,8 @@ emit_instances_kernel(const uint32_t* __restrict__ order, const uint32_t* __rest
         }
     }
     __syncthreads();
-    for (int p = 0; p < tp.passes; p++) {
+#pragma unroll
+    for (int p = 0; p < PASSES; p++) {
         const uint32_t c = s_hist[p][threadIdx.x];
         if (c) atomicAdd(sweep + p * pass_words + threadIdx.x, c);
     }
@@ -609,8 +610,15 @@ void launch_emit_and_partition(const ScgrView& v, const GeometryLayout& G, const
     cudaMemsetAsync(B.sweep, 0, pw * tp.passes * 4, L.stream);
     const uint32_t* order = G.sort_vals[0];   // 32-bit sort = 4 passes = even number of flips
     begin_kernel("emit_instances", L);
-    emit_instances_kernel<<<(P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, L.stream>>>(
-        order, G.offsets, G.rect, G.tile_mask, G.rec, P, gx, capacity, G.status, B.keys[0], B.vals[0], B.sweep, pw, tp);
+#define SCGR_EMIT(N_) emit_instances_kernel<N_><<<(P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, L.stream>>>( \
+        order, G.offsets, G.rect, G.tile_mask, G.rec, P, gx, capacity, G.status, B.keys[0], B.vals[0], B.sweep, pw, tp)
+    switch (tp.passes) {
+        case 1: SCGR_EMIT(1); break;
+        case 2: SCGR_EMIT(2); break;
+        case 3: SCGR_EMIT(3); break;
+        default: SCGR_EMIT(4); break;
+    }
+#undef SCGR_EMIT
     check_launch("emit_instances", L);
     int cur = 0;
     for (int p = 0; p < tp.passes; p++) {
