@@ -43,6 +43,36 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
+// ---- TMA (cp.async.bulk) + mbarrier plumbing: every lane pulls the 48-byte record of its
+// Gaussian into the warp's staging buffer with one bulk-async copy; completion is a transaction
+// count on an mbarrier, so no register ever holds data in flight. ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SCGR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SCGR_DONE;\n"
+        "bra SCGR_WAIT;\n"
+        "SCGR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 struct Rec {
     float4 q0, q1, q2;
 };
@@ -74,7 +104,7 @@ __device__ __forceinline__ uint32_t slot_mask(const Rec& r, const float X0, cons
 // ------------------------------------------------------------------------------------------
 // WPT warps share a tile: warp w owns slots [w * SLOTS / WPT, (w + 1) * SLOTS / WPT).  The warps of a
 // tile never synchronise with each other (disjoint pixels, private staging buffers).
-template <int WPT, int MINB>
+template <int WPT, int MINB, bool TMA>
 __global__ void __launch_bounds__(32 * WPT, MINB)
 render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                       const Record* __restrict__ rec, int W, int H, const float* __restrict__ bg,
@@ -82,13 +112,17 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                       float* __restrict__ out_depth, float* __restrict__ out_alpha,
                       uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
     constexpr int SPW = SLOTS / WPT;      // slots per warp
-    __shared__ float4 s_q0_[WPT][32], s_q1_[WPT][32], s_q2_[WPT][32];
+    __shared__ __align__(16) float4 s_rec_[WPT][2][96];        // 2 stages x 32 records x {q0, q1, q2}
+    __shared__ __align__(8) unsigned long long s_bar_[WPT][2];
     if (status[0] > capacity) return;   // binning overflowed: caller re-runs with a larger buffer
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int k0 = wid * SPW;             // first slot of this warp
-    float4* const s_q0 = s_q0_[wid];
-    float4* const s_q1 = s_q1_[wid];
-    float4* const s_q2 = s_q2_[wid];
+    unsigned long long* const bars = s_bar_[wid];
+    if (TMA) {
+        if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+        mbar_fence_init();
+        __syncwarp();
+    }
     const int lx = lane & 7, ly = lane >> 3;
     const int X0 = blockIdx.x * TILE, Y0 = blockIdx.y * TILE;
     const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
@@ -106,11 +140,23 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     }
     const float pxf = (float)(X0 + lx), pyf = (float)(Y0 + ly);
 
+    // stage b of the list = entries [32 b, 32 b + 32); buffer b & 1
+    auto issue = [&](const int b) {
+        const int c = min(32, total - 32 * b);
+        if (lane == 0) mbar_expect_tx(&bars[b & 1], 48u * (uint32_t)c);
+        __syncwarp();
+        if (lane < c)
+            bulk_g2s(&s_rec_[wid][b & 1][lane * 3], rec + point_list[range.x + 32 * b + lane], 48u, &bars[b & 1]);
+    };
     Rec nxt;
     nxt.q0 = nxt.q1 = nxt.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < total) nxt = load_rec(rec, point_list[range.x + lane]);
+    const int nbatch = (total + 31) >> 5;
+    if (TMA) { if (nbatch > 0) issue(0); }
+    else if (lane < total) nxt = load_rec(rec, point_list[range.x + lane]);
 
-    for (int base = 0; base < total; base += 32) {
+    int b = 0;
+    for (; b < nbatch; b++) {
+        const int base = 32 * b;
         // slots in which some pixel is still open
         uint32_t live = 0u;
 #pragma unroll
@@ -118,19 +164,28 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
             if (!__all_sync(0xffffffffu, (done >> (k0 + i)) & 1u)) live |= 1u << (k0 + i);
         if (live == 0u) break;
         const int cnt = min(32, total - base);
-        const Rec cur = nxt;
-        __syncwarp();
-        s_q0[lane] = cur.q0; s_q1[lane] = cur.q1; s_q2[lane] = cur.q2;
-        __syncwarp();
-        if (base + 32 + lane < total) nxt = load_rec(rec, point_list[range.x + base + 32 + lane]);
+        const float4* const srec = s_rec_[wid][TMA ? (b & 1) : 0];
+        Rec cur;
+        if (TMA) {
+            mbar_wait(&bars[b & 1], (uint32_t)(b >> 1) & 1u);
+            __syncwarp();                            // (also orders the generic s_id stores of this stage)
+            if (b + 1 < nbatch) issue(b + 1);        // the other buffer was released by the __syncwarp below
+            cur.q0 = srec[lane * 3]; cur.q1 = srec[lane * 3 + 1]; cur.q2 = srec[lane * 3 + 2];
+        } else {
+            cur = nxt;
+            __syncwarp();
+            s_rec_[wid][0][lane * 3] = cur.q0; s_rec_[wid][0][lane * 3 + 1] = cur.q1; s_rec_[wid][0][lane * 3 + 2] = cur.q2;
+            __syncwarp();
+            if (base + 32 + lane < total) nxt = load_rec(rec, point_list[range.x + base + 32 + lane]);
+        }
         const uint32_t mymask = lane < cnt ? slot_mask(cur, (float)X0, (float)Y0, live) : 0u;
 
         for (int j = 0; j < cnt; j++) {
             const uint32_t mj = __shfl_sync(0xffffffffu, mymask, j);
             if (mj == 0u) continue;
-            const float4 q0 = s_q0[j];
-            const float4 q1 = s_q1[j];
-            const float4 q2 = s_q2[j];
+            const float4 q0 = srec[j * 3];
+            const float4 q1 = srec[j * 3 + 1];
+            const float4 q2 = srec[j * 3 + 2];
             const float dx0 = q0.x - pxf, dy0 = q0.y - pyf;
             const float thr = q1.w - PREFILTER_MARGIN;
 #pragma unroll
@@ -153,7 +208,9 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                 last[i] = go ? (uint32_t)(base + j + 1) : last[i];
             }
         }
+        __syncwarp();      // every lane is done with this stage before it is refilled
     }
+    if (TMA && b < nbatch) mbar_wait(&bars[b & 1], (uint32_t)(b >> 1) & 1u);   // drain the copy in flight before exiting
     const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
     const size_t N = (size_t)W * H;
 #pragma unroll
@@ -220,7 +277,7 @@ __device__ __forceinline__ float transpose_reduce10(const float v[10], const int
     return d;
 }
 
-template <int WPT, int MINB, bool PRED>
+template <int WPT, int MINB, bool PRED, bool TMA>
 __global__ void __launch_bounds__(32 * WPT, MINB)
 render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                        const Record* __restrict__ rec, int W, int H, const float* __restrict__ bg,
@@ -229,16 +286,19 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
                        const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
                        const float* __restrict__ dL_dalpha, ScreenGrad* __restrict__ screen_grad) {
     constexpr int SPW = SLOTS / WPT;      // slots per warp
-    __shared__ float4 s_q0_[WPT][32], s_q1_[WPT][32], s_q2_[WPT][32];
-    __shared__ uint32_t s_id_[WPT][32];
+    __shared__ __align__(16) float4 s_rec_[WPT][2][96];        // 2 stages x 32 records x {q0, q1, q2}
+    __shared__ uint32_t s_id_[WPT][2][32];
+    __shared__ __align__(8) unsigned long long s_bar_[WPT][2];
     __shared__ float4 s_g4[TILE_PIX];       // upstream gradients of the tile: r, g, b, depth
     if (status[0] > capacity) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int k0 = wid * SPW;             // first slot of this warp
-    float4* const s_q0 = s_q0_[wid];
-    float4* const s_q1 = s_q1_[wid];
-    float4* const s_q2 = s_q2_[wid];
-    uint32_t* const s_id = s_id_[wid];
+    unsigned long long* const bars = s_bar_[wid];
+    if (TMA) {
+        if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+        mbar_fence_init();
+        __syncwarp();
+    }
     const int lx = lane & 7, ly = lane >> 3;
     const int X0 = blockIdx.x * TILE, Y0 = blockIdx.y * TILE;
     const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
@@ -274,22 +334,47 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     // (each lane only ever reads back the s_g4 entries it wrote itself: no barrier needed)
 
     // batch entry j  <->  0-based list position  pos = toDo - 1 - (base + j)   (back to front)
+    // stage b = batch entries [32 b, 32 b + 32) of the back-to-front walk; buffer b & 1
+    auto issue = [&](const int b) {
+        const int c = min(32, toDo - 32 * b);
+        if (lane == 0) mbar_expect_tx(&bars[b & 1], 48u * (uint32_t)c);
+        __syncwarp();
+        if (lane < c) {
+            const uint32_t id = point_list[range.x + (toDo - 1 - (32 * b + lane))];
+            s_id_[wid][b & 1][lane] = id;
+            bulk_g2s(&s_rec_[wid][b & 1][lane * 3], rec + id, 48u, &bars[b & 1]);
+        }
+    };
     Rec nxt;
     uint32_t nxt_id = 0u;
     nxt.q0 = nxt.q1 = nxt.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < toDo) {
+    const int nbatch = (toDo + 31) >> 5;
+    if (TMA) { if (nbatch > 0) issue(0); }
+    else if (lane < toDo) {
         nxt_id = point_list[range.x + (toDo - 1 - lane)];
         nxt = load_rec(rec, nxt_id);
     }
-    for (int base = 0; base < toDo; base += 32) {
+    for (int b = 0; b < nbatch; b++) {
+        const int base = 32 * b;
         const int cnt = min(32, toDo - base);
-        const Rec cur = nxt;
-        __syncwarp();
-        s_q0[lane] = cur.q0; s_q1[lane] = cur.q1; s_q2[lane] = cur.q2; s_id[lane] = nxt_id;
-        __syncwarp();
-        if (base + 32 + lane < toDo) {
-            nxt_id = point_list[range.x + (toDo - 1 - (base + 32 + lane))];
-            nxt = load_rec(rec, nxt_id);
+        const float4* const srec = s_rec_[wid][TMA ? (b & 1) : 0];
+        const uint32_t* const s_id = s_id_[wid][TMA ? (b & 1) : 0];
+        Rec cur;
+        if (TMA) {
+            mbar_wait(&bars[b & 1], (uint32_t)(b >> 1) & 1u);
+            __syncwarp();                            // (also orders the generic s_id stores of this stage)
+            if (b + 1 < nbatch) issue(b + 1);        // the other buffer was released by the __syncwarp below
+            cur.q0 = srec[lane * 3]; cur.q1 = srec[lane * 3 + 1]; cur.q2 = srec[lane * 3 + 2];
+        } else {
+            cur = nxt;
+            __syncwarp();
+            s_rec_[wid][0][lane * 3] = cur.q0; s_rec_[wid][0][lane * 3 + 1] = cur.q1; s_rec_[wid][0][lane * 3 + 2] = cur.q2;
+            s_id_[wid][0][lane] = nxt_id;
+            __syncwarp();
+            if (base + 32 + lane < toDo) {
+                nxt_id = point_list[range.x + (toDo - 1 - (base + 32 + lane))];
+                nxt = load_rec(rec, nxt_id);
+            }
         }
         uint32_t mymask = 0u;
         if (lane < cnt) {
@@ -304,9 +389,9 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
             const uint32_t mj = __shfl_sync(0xffffffffu, mymask, j);
             if (mj == 0u) continue;
             const int pos = toDo - 1 - (base + j);
-            const float4 q0 = s_q0[j];
-            const float4 q1 = s_q1[j];
-            const float4 q2 = s_q2[j];
+            const float4 q0 = srec[j * 3];
+            const float4 q1 = srec[j * 3 + 1];
+            const float4 q2 = srec[j * 3 + 2];
             const float dx0 = q0.x - pxf, dy0 = q0.y - pyf;
             const float thr = q1.w - PREFILTER_MARGIN;
             float v[10];
@@ -363,6 +448,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
             if (slot >= 0 && sum != 0.f)
                 atomicAdd(reinterpret_cast<float*>(screen_grad + s_id[j]) + slot, sum);   // RED.E.ADD.F32
         }
+        __syncwarp();      // every lane is done with this stage before it is refilled
     }
 }
 
@@ -381,10 +467,12 @@ void launch_render_forward(const ScgrView& v, const GeometryLayout& G, const Bin
     static const int wpt = env_int("SCGR_FWD_WPT", 1);
     begin_kernel("render_forward", L);
     static const int minb = env_int("SCGR_FWD_MINB", 20);
-#define SCGR_FWD(W_, M_) render_forward_kernel<W_, M_><<<grid, 32 * W_, 0, L.stream>>>(B.ranges, point_list, G.rec, \
+    static const int tma = env_int("SCGR_TMA", 0);
+#define SCGR_FWD(W_, M_, T_) render_forward_kernel<W_, M_, T_><<<grid, 32 * W_, 0, L.stream>>>(B.ranges, point_list, G.rec, \
         v.image_width, v.image_height, v.bg, G.status, capacity, out_color, out_depth, out_alpha, I.n_contrib, I.final_T)
-    if (wpt == 2) SCGR_FWD(2, 1); else if (wpt == 4) SCGR_FWD(4, 1); else if (minb == 20) SCGR_FWD(1, 20);
-    else if (minb == 24) SCGR_FWD(1, 24); else SCGR_FWD(1, 1);
+    if (wpt == 2) SCGR_FWD(2, 1, false); else if (wpt == 4) SCGR_FWD(4, 1, false);
+    else if (!tma) { if (minb == 20) SCGR_FWD(1, 20, false); else SCGR_FWD(1, 1, false); }
+    else if (minb == 20) SCGR_FWD(1, 20, true); else if (minb == 24) SCGR_FWD(1, 24, true); else SCGR_FWD(1, 1, true);
 #undef SCGR_FWD
     check_launch("render_forward", L);
 }
@@ -400,13 +488,15 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
     begin_kernel("render_backward", L);
     static const int minb = env_int("SCGR_BWD_MINB", 14);
     static const int pred = env_int("SCGR_BWD_PRED", 1);
-#define SCGR_BWD(W_, M_, P_) render_backward_kernel<W_, M_, P_><<<grid, 32 * W_, 0, L.stream>>>(B.ranges, point_list, \
+    static const int tma = env_int("SCGR_TMA", 0);
+#define SCGR_BWD(W_, M_, P_, T_) render_backward_kernel<W_, M_, P_, T_><<<grid, 32 * W_, 0, L.stream>>>(B.ranges, point_list, \
         G.rec, v.image_width, v.image_height, v.bg, G.status, capacity, I.n_contrib, I.final_T, dL_dcolor, dL_ddepth, \
         dL_dalpha, G.screen_grad)
-    if (wpt == 2) SCGR_BWD(2, 1, true); else if (wpt == 4) SCGR_BWD(4, 1, true);
-    else if (!pred) SCGR_BWD(1, 1, false);
-    else if (minb == 16) SCGR_BWD(1, 16, true); else if (minb == 14) SCGR_BWD(1, 14, true);
-    else SCGR_BWD(1, 1, true);
+    if (wpt == 2) SCGR_BWD(2, 1, true, false); else if (wpt == 4) SCGR_BWD(4, 1, true, false);
+    else if (!pred) SCGR_BWD(1, 1, false, false);
+    else if (!tma) { if (minb == 14) SCGR_BWD(1, 14, true, false); else SCGR_BWD(1, 1, true, false); }
+    else if (minb == 16) SCGR_BWD(1, 16, true, true); else if (minb == 14) SCGR_BWD(1, 14, true, true);
+    else SCGR_BWD(1, 1, true, true);
 #undef SCGR_BWD
     check_launch("render_backward", L);
 }
