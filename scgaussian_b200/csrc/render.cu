@@ -29,7 +29,6 @@ namespace scgr {
 namespace {
 
 constexpr int SLOTS = 8;
-constexpr float PREFILTER_MARGIN = CULL_MARGIN;
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
@@ -128,15 +127,17 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
     const int total = range.y > range.x ? (int)(range.y - range.x) : 0;   // empty tiles hold (0xffffffff, 0)
 
-    float T[SPW], Cr[SPW], Cg[SPW], Cb[SPW], Dd[SPW];
+    // Tt = transmittance of the pixel while it is open; a finished pixel (saturated, or outside the
+    // image) keeps its final transmittance NEGATED: test_T of a finished pixel is then negative, so
+    // it can never blend again and no separate "done" flag is tested or updated in the inner loop.
+    float Tt[SPW], Cr[SPW], Cg[SPW], Cb[SPW], Dd[SPW];
     uint32_t last[SPW];
-    uint32_t done = 0u;    // bit k: this lane's pixel of slot k is finished
 #pragma unroll
     for (int i = 0; i < SPW; i++) {
         const int k = k0 + i;
-        T[i] = 1.f; Cr[i] = 0.f; Cg[i] = 0.f; Cb[i] = 0.f; Dd[i] = 0.f; last[i] = 0u;
+        Cr[i] = 0.f; Cg[i] = 0.f; Cb[i] = 0.f; Dd[i] = 0.f; last[i] = 0u;
         const int px = X0 + ((k & 1) << 3) + lx, py = Y0 + ((k >> 1) << 2) + ly;
-        if (px >= W || py >= H) done |= 1u << k;
+        Tt[i] = (px >= W || py >= H) ? -1.f : 1.f;
     }
     const float pxf = (float)(X0 + lx), pyf = (float)(Y0 + ly);
 
@@ -161,7 +162,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         uint32_t live = 0u;
 #pragma unroll
         for (int i = 0; i < SPW; i++)
-            if (!__all_sync(0xffffffffu, (done >> (k0 + i)) & 1u)) live |= 1u << (k0 + i);
+            if (__any_sync(0xffffffffu, Tt[i] > 0.f)) live |= 1u << (k0 + i);
         if (live == 0u) break;
         const int cnt = min(32, total - base);
         const float4* const srec = s_rec_[wid][TMA ? (b & 1) : 0];
@@ -186,26 +187,36 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
             const float4 q0 = srec[j * 3];
             const float4 q1 = srec[j * 3 + 1];
             const float4 q2 = srec[j * 3 + 2];
-            const float dx0 = q0.x - pxf, dy0 = q0.y - pyf;
-            const float thr = q1.w - PREFILTER_MARGIN;
+            // power(dx, dy) = cA dx^2 + dy (cB dx + cC dy): the dx-only terms are shared by the 4 slots of
+            // a column and hoisted, leaving 2 FFMA per pixel
+            const float dxa = q0.x - pxf, dxb = dxa - 8.f;
+            const float ax[2] = {(q0.z * dxa) * dxa, (q0.z * dxb) * dxb};
+            const float bx[2] = {q0.w * dxa, q0.w * dxb};
+            const float dy0 = q0.y - pyf;
+            const float dys[4] = {dy0, dy0 - 4.f, dy0 - 8.f, dy0 - 12.f};
+            const uint32_t idx = (uint32_t)(base + j + 1);
 #pragma unroll
             for (int i = 0; i < SPW; i++) {
                 const int k = k0 + i;
                 if (!(mj & (1u << k))) continue;      // warp-uniform
-                const float dx = dx0 - (float)((k & 1) << 3), dy = dy0 - (float)((k >> 1) << 2);
-                const float power = dx * (q0.z * dx + q0.w * dy) + q1.x * dy * dy;
-                // straight-line, predicated: the reference's skip chain (A.8) without divergent branches
-                const float alpha = fminf(ALPHA_MAX, q1.y * ex2(power));
-                const float test_T = T[i] * (1.f - alpha);
-                const bool cand = !((done >> k) & 1u) && power <= 0.f && power >= thr && alpha >= ALPHA_MIN;
-                const bool stop = cand && test_T < T_EPS;      // pixel saturated: this Gaussian is NOT blended
-                const bool go = cand && !stop;
-                if (stop) done |= 1u << k;
-                const float w = go ? alpha * T[i] : 0.f;
-                Cr[i] += q2.x * w; Cg[i] += q2.y * w; Cb[i] += q2.z * w;
-                Dd[i] += q1.z * w;
-                T[i] = go ? test_T : T[i];
-                last[i] = go ? (uint32_t)(base + j + 1) : last[i];
+                const float dy = dys[k >> 1];
+                const float power = fmaf(dy, fmaf(q1.x, dy, bx[k & 1]), ax[k & 1]);
+                // straight-line, predicated: the reference's skip chain (A.8) without divergent branches.
+                // (alpha >= 1/255 implies power >= pmin2 - margin: the slot bound needs no per-pixel twin.)
+                const float araw = fminf(ALPHA_MAX, q1.y * ex2(power));
+                const bool cand = power <= 0.f && araw >= ALPHA_MIN;
+                const float alpha = cand ? araw : 0.f;
+                const float w0 = alpha * Tt[i];
+                const float test_T = Tt[i] - w0;               // T (1 - alpha); == T if skipped; < 0 if finished
+                // open & (skipped | blended) -> test_T >= T_EPS.  Otherwise the pixel is finished, or saturates
+                // right here (this Gaussian is then NOT blended): keep -|T|.
+                const bool open = test_T >= T_EPS;
+                const bool go = cand && open;
+                const float w = open ? w0 : 0.f;
+                Cr[i] = fmaf(q2.x, w, Cr[i]); Cg[i] = fmaf(q2.y, w, Cg[i]); Cb[i] = fmaf(q2.z, w, Cb[i]);
+                Dd[i] = fmaf(q1.z, w, Dd[i]);
+                Tt[i] = open ? test_T : -fabsf(Tt[i]);
+                last[i] = go ? idx : last[i];
             }
         }
         __syncwarp();      // every lane is done with this stage before it is refilled
@@ -219,13 +230,14 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         const int px = X0 + ((k & 1) << 3) + lx, py = Y0 + ((k >> 1) << 2) + ly;
         if (px < W && py < H) {
             const size_t pid = (size_t)py * W + px;
-            out_color[pid] = Cr[i] + T[i] * bg0;
-            out_color[N + pid] = Cg[i] + T[i] * bg1;
-            out_color[2 * N + pid] = Cb[i] + T[i] * bg2;
+            const float T = fabsf(Tt[i]);
+            out_color[pid] = Cr[i] + T * bg0;
+            out_color[N + pid] = Cg[i] + T * bg1;
+            out_color[2 * N + pid] = Cb[i] + T * bg2;
             out_depth[pid] = Dd[i];
-            out_alpha[pid] = 1.f - T[i];      // == sum alpha_i T_i (telescoping), A.8
+            out_alpha[pid] = 1.f - T;         // == sum alpha_i T_i (telescoping), A.8
             n_contrib[pid] = last[i];
-            final_T[pid] = T[i];
+            final_T[pid] = T;
         }
     }
 }
@@ -277,7 +289,7 @@ __device__ __forceinline__ float transpose_reduce10(const float v[10], const int
     return d;
 }
 
-template <int WPT, int MINB, bool PRED, bool TMA>
+template <int WPT, int MINB, bool TMA>
 __global__ void __launch_bounds__(32 * WPT, MINB)
 render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                        const Record* __restrict__ rec, int W, int H, const float* __restrict__ bg,
@@ -305,7 +317,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
     const size_t N = (size_t)W * H;
 
-    float T[SPW], Ar[SPW], Ag[SPW], Ab[SPW], Ad[SPW], tfb[SPW];
+    float T[SPW], Bs[SPW], tfb[SPW];
     int lc[SPW];
     int slot_lc[SPW];
     int toDo = 0;
@@ -326,7 +338,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
         s_g4[k * 32 + lane] = make_float4(gr, gg, gb, gd);
         T[i] = Tf;
         tfb[i] = Tf * (ga - (bg0 * gr + bg1 * gg + bg2 * gb));
-        Ar[i] = 0.f; Ag[i] = 0.f; Ab[i] = 0.f; Ad[i] = 0.f;
+        Bs[i] = 0.f;
         slot_lc[i] = __reduce_max_sync(0xffffffffu, lc[i]);
         toDo = max(toDo, slot_lc[i]);
     }
@@ -392,57 +404,54 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
             const float4 q0 = srec[j * 3];
             const float4 q1 = srec[j * 3 + 1];
             const float4 q2 = srec[j * 3 + 2];
-            const float dx0 = q0.x - pxf, dy0 = q0.y - pyf;
-            const float thr = q1.w - PREFILTER_MARGIN;
+            // hoisted per-column / per-row terms of the exponent, as in the forward
+            const float dxa = q0.x - pxf, dxb = dxa - 8.f;
+            const float dxs[2] = {dxa, dxb};
+            const float ax[2] = {(q0.z * dxa) * dxa, (q0.z * dxb) * dxb};
+            const float bx[2] = {q0.w * dxa, q0.w * dxb};
+            const float dy0 = q0.y - pyf;
+            const float dys[4] = {dy0, dy0 - 4.f, dy0 - 8.f, dy0 - 12.f};
             float v[10];
 #pragma unroll
             for (int i = 0; i < 10; i++) v[i] = 0.f;
-            bool touched = false;
+            float tsum = 0.f;                                // > 0 <=> some pixel of this lane took the pair
 #pragma unroll
             for (int i = 0; i < SPW; i++) {
                 const int k = k0 + i;
                 if (!(mj & (1u << k))) continue;      // warp-uniform
-                const float dx = dx0 - (float)((k & 1) << 3), dy = dy0 - (float)((k >> 1) << 2);
-                const float power = dx * (q0.z * dx + q0.w * dy) + q1.x * dy * dy;
-                float og, alpha;       // og = opacity * G (un-capped), alpha = min(0.99, og)
-                if (PRED) {
-                    // straight-line: a pair that fails the reference's tests (A.9) runs with og = alpha = 0,
-                    // which makes every term below vanish and leaves the pixel state untouched
-                    const float ograw = q1.y * ex2(power);
-                    const float araw = fminf(ALPHA_MAX, ograw);
-                    const bool ok = pos < lc[i] && power <= 0.f && power >= thr && araw >= ALPHA_MIN;
-                    touched |= ok;
-                    og = ok ? ograw : 0.f;
-                    alpha = ok ? araw : 0.f;
-                } else {
-                    if (pos >= lc[i] || power > 0.f || power < thr) continue;
-                    og = q1.y * ex2(power);
-                    alpha = fminf(ALPHA_MAX, og);
-                    if (alpha < ALPHA_MIN) continue;
-                    touched = true;
-                }
-                const float ra = rcp_approx(1.f - alpha);   // 1 - alpha >= 0.01
+                const float dx = dxs[k & 1], dy = dys[k >> 1];
+                const float power = fmaf(dy, fmaf(q1.x, dy, bx[k & 1]), ax[k & 1]);
+                // straight-line: a pair that fails the reference's tests (A.9) runs with og = alpha = 0, which
+                // makes every term below vanish and leaves the pixel state untouched.
+                // min(0.99, og) >= 1/255  <=>  og >= 1/255
+                const float ograw = q1.y * ex2(power);
+                const bool ok = pos < lc[i] && power <= 0.f && ograw >= ALPHA_MIN;
+                const float og = ok ? ograw : 0.f;           // opacity * G, un-capped
+                tsum += og;
+                const float alpha = fminf(ALPHA_MAX, og);
+                const float ra = rcp_approx(1.f - alpha);    // 1 - alpha >= 0.01
                 T[i] *= ra;                                  // transmittance in front of this Gaussian
-                const float4 g4 = s_g4[k * 32 + lane];      // upstream dL/d{r, g, b, depth} of this pixel
-                // suffix-blended values behind this Gaussian: A* <- alpha c + (1 - alpha) A*   (after use)
-                const float er = q2.x - Ar[i], eg = q2.y - Ag[i], eb = q2.z - Ab[i], ed = q1.z - Ad[i];
-                float dL_dalpha_ = er * g4.x + eg * g4.y + eb * g4.z + ed * g4.w;
-                Ar[i] += alpha * er; Ag[i] += alpha * eg; Ab[i] += alpha * eb; Ad[i] += alpha * ed;
+                const float4 g4 = s_g4[k * 32 + lane];       // upstream dL/d{r, g, b, depth} of this pixel
+                // Only the upstream-weighted sum over channels of the suffix blend is needed:
+                //   Bs = sum_ch g_ch A_ch,  A_ch <- alpha c_ch + (1 - alpha) A_ch   =>   Bs <- Bs + alpha (g.c - Bs)
+                const float cg = fmaf(q1.z, g4.w, fmaf(q2.z, g4.z, fmaf(q2.y, g4.y, q2.x * g4.x)));
+                const float e = cg - Bs[i];
+                Bs[i] = fmaf(alpha, e, Bs[i]);
                 // the alpha output and the background enter as T_final / (1 - alpha) * (dL/dalpha_pix - bg . dL/dC)
-                dL_dalpha_ = dL_dalpha_ * T[i] + tfb[i] * ra;
+                const float dL_dalpha_ = fmaf(e, T[i], tfb[i] * ra);
                 const float w = alpha * T[i];
                 const float uG = og * dL_dalpha_;            // G * dL/dG; propagated even when alpha was capped (A.9)
                 const float ux = uG * dx, uy = uG * dy;
                 v[0] += ux;                                  // preprocess-backward rebuilds dL/dmean from these two
                 v[1] += uy;
-                v[2] += ux * dx;                             // * -0.5 = dL/dconic_A
-                v[3] += ux * dy;                             // * -1   = dL/dconic_B
-                v[4] += uy * dy;                             // * -0.5 = dL/dconic_C
+                v[2] = fmaf(ux, dx, v[2]);                   // * -0.5 = dL/dconic_A
+                v[3] = fmaf(ux, dy, v[3]);                   // * -1   = dL/dconic_B
+                v[4] = fmaf(uy, dy, v[4]);                   // * -0.5 = dL/dconic_C
                 v[5] += uG;                                  // / opacity = dL/dopacity
-                v[6] += w * g4.w;                            // dL/ddepth
-                v[7] += w * g4.x; v[8] += w * g4.y; v[9] += w * g4.z;
+                v[6] = fmaf(w, g4.w, v[6]);                  // dL/ddepth
+                v[7] = fmaf(w, g4.x, v[7]); v[8] = fmaf(w, g4.y, v[8]); v[9] = fmaf(w, g4.z, v[9]);
             }
-            if (!__any_sync(0xffffffffu, touched)) continue;
+            if (!__any_sync(0xffffffffu, tsum > 0.f)) continue;
             int slot;
             const float sum = transpose_reduce10(v, lane, &slot);
             if (slot >= 0 && sum != 0.f)
@@ -487,16 +496,14 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
     static const int wpt = env_int("SCGR_BWD_WPT", 1);
     begin_kernel("render_backward", L);
     static const int minb = env_int("SCGR_BWD_MINB", 14);
-    static const int pred = env_int("SCGR_BWD_PRED", 1);
     static const int tma = env_int("SCGR_TMA", 0);
-#define SCGR_BWD(W_, M_, P_, T_) render_backward_kernel<W_, M_, P_, T_><<<grid, 32 * W_, 0, L.stream>>>(B.ranges, point_list, \
+#define SCGR_BWD(W_, M_, T_) render_backward_kernel<W_, M_, T_><<<grid, 32 * W_, 0, L.stream>>>(B.ranges, point_list, \
         G.rec, v.image_width, v.image_height, v.bg, G.status, capacity, I.n_contrib, I.final_T, dL_dcolor, dL_ddepth, \
         dL_dalpha, G.screen_grad)
-    if (wpt == 2) SCGR_BWD(2, 1, true, false); else if (wpt == 4) SCGR_BWD(4, 1, true, false);
-    else if (!pred) SCGR_BWD(1, 1, false, false);
-    else if (!tma) { if (minb == 14) SCGR_BWD(1, 14, true, false); else SCGR_BWD(1, 1, true, false); }
-    else if (minb == 16) SCGR_BWD(1, 16, true, true); else if (minb == 14) SCGR_BWD(1, 14, true, true);
-    else SCGR_BWD(1, 1, true, true);
+    if (wpt == 2) SCGR_BWD(2, 1, false); else if (wpt == 4) SCGR_BWD(4, 1, false);
+    else if (!tma) { if (minb == 14) SCGR_BWD(1, 14, false); else if (minb == 16) SCGR_BWD(1, 16, false); else SCGR_BWD(1, 1, false); }
+    else if (minb == 16) SCGR_BWD(1, 16, true); else if (minb == 14) SCGR_BWD(1, 14, true);
+    else SCGR_BWD(1, 1, true);
 #undef SCGR_BWD
     check_launch("render_backward", L);
 }
