@@ -217,8 +217,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    R_seen = set()
     for _ in range(K):
         state = step()
+        R_seen.add(int(state.num_rendered))     # host int already read by the forward: free
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -358,7 +360,8 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "P": P_GAUSS, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEG,
-                   "num_rendered_R": R_inst, "views_per_step": world, "parallelism": f"view-sharded dp{world}",
+                   "num_rendered_R": R_inst, "num_rendered_distinct_over_steps": len(R_seen),
+                   "views_per_step": world, "parallelism": f"view-sharded dp{world}",
                    "collective": "1 NCCL all-reduce of the flat gradient buffer per step" if world > 1 else "none (1 GPU)",
                    "grad_allreduce_bytes": flat.nbytes() if world > 1 else 0,
                    "l2": "no explicit flush: one step streams >1 GB (inputs 236 MB + gradients 232 MB + scratch) through the 126 MB L2"},

@@ -7,6 +7,9 @@
 // Design (differs from the reference's one-thread-per-pixel, 256-thread CTA):
 //   * ONE WARP per 16x16 tile.  The tile is cut into 8 "slots" of 8x4 pixels; lane l owns pixel
 //     (l % 8, l / 8) of every slot, i.e. 8 pixels per thread held in registers.
+//   * Work items are dispatched longest first: most tiles whole (8 slots per warp), then a share of
+//     the tiles as two 16x8 halves, the last ones as four 16x4 quarters -- the tail of the grid is
+//     made of short items, so no SM idles while a few warps finish whole tiles.
 //   * The tile's depth-ordered list is consumed 32 Gaussians at a time: lane l gathers the packed
 //     48-byte record of the l-th one (3 x 128-bit loads; the NEXT batch is prefetched into
 //     registers while the current one is processed) and computes, for its Gaussian, an exact
@@ -20,6 +23,7 @@
 //   * exp() is one MUFU.EX2: the conic is stored pre-multiplied by -0.5*log2(e).
 // No block-level barriers at all (a warp never waits for another); no tensor cores (blend is not a
 // contraction).
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -28,7 +32,6 @@ namespace scgr {
 
 namespace {
 
-constexpr int SLOTS = 8;
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
@@ -85,46 +88,50 @@ __device__ __forceinline__ Rec load_rec(const Record* __restrict__ rec, uint32_t
     return r;
 }
 
-// slot mask of one Gaussian: bit k set <=> slot k may receive a contribution
-__device__ __forceinline__ uint32_t slot_mask(const Rec& r, const float X0, const float Y0, const uint32_t live_slots) {
+// slot mask of one Gaussian over a region of SPW slots whose first pixel is (X0, Yr):
+// bit i set <=> local slot i (column i & 1, row i >> 1) may receive a contribution
+template <int SPW>
+__device__ __forceinline__ uint32_t slot_mask(const Rec& r, const float X0, const float Yr, const uint32_t live_slots) {
     const CullParams c = make_cull(r.q0, r.q1);
     uint32_t m = 0u;
 #pragma unroll
-    for (int k = 0; k < SLOTS; k++) {
-        const float x0 = X0 + (float)((k & 1) << 3), y0 = Y0 + (float)((k >> 1) << 2);
+    for (int i = 0; i < SPW; i++) {
+        const float x0 = X0 + (float)((i & 1) << 3), y0 = Yr + (float)((i >> 1) << 2);
         const float mp = max_power_over_rect(c.cA, c.cB, c.cC, c.kx, c.ky, c.mx, c.my, x0, x0 + 7.f, y0, y0 + 3.f);
-        if (mp >= c.thr) m |= 1u << k;
+        if (mp >= c.thr) m |= 1u << i;
     }
     return m & live_slots;
 }
 
+// Work items of a render launch, in dispatch order: tiles [0, n8) whole, tiles [n8, n8 + n4) as two
+// halves each, tiles [n8 + n4, n8 + n4 + n2) as four quarters each.
+struct WorkSplit {
+    int n8, n4, n2;
+    int items() const { return n8 + 2 * n4 + 4 * n2; }
+};
+
 // ------------------------------------------------------------------------------------------
 // forward (A.8)
 // ------------------------------------------------------------------------------------------
-// WPT warps share a tile: warp w owns slots [w * SLOTS / WPT, (w + 1) * SLOTS / WPT).  The warps of a
-// tile never synchronise with each other (disjoint pixels, private staging buffers).
-template <int WPT, int MINB, bool TMA>
-__global__ void __launch_bounds__(32 * WPT, MINB)
-render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                      const Record* __restrict__ rec, int W, int H, const float* __restrict__ bg,
-                      const int64_t* __restrict__ status, int64_t capacity, float* __restrict__ out_color,
-                      float* __restrict__ out_depth, float* __restrict__ out_alpha,
-                      uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
-    constexpr int SPW = SLOTS / WPT;      // slots per warp
-    __shared__ __align__(16) float4 s_rec_[WPT][2][96];        // 2 stages x 32 records x {q0, q1, q2}
-    __shared__ __align__(8) unsigned long long s_bar_[WPT][2];
-    if (status[0] > capacity) return;   // binning overflowed: caller re-runs with a larger buffer
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int k0 = wid * SPW;             // first slot of this warp
-    unsigned long long* const bars = s_bar_[wid];
+// One warp renders a region of SPW slots (SPW = 8: the whole tile, 4: a 16x8 half, 2: a 16x4 quarter)
+// whose first slot is slot k0 of the tile.  Warps that share a tile never synchronise with each
+// other (disjoint pixels, private staging buffers).
+template <int SPW, bool TMA>
+__device__ __forceinline__ void
+forward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[96], unsigned long long* bars,
+               const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+               const Record* __restrict__ rec, const int W, const int H, const float* __restrict__ bg,
+               float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha,
+               uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
+    const int lane = threadIdx.x & 31;
     if (TMA) {
         if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
         mbar_fence_init();
         __syncwarp();
     }
     const int lx = lane & 7, ly = lane >> 3;
-    const int X0 = blockIdx.x * TILE, Y0 = blockIdx.y * TILE;
-    const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
+    const int X0 = (tile % tiles_x) * TILE, Yr = (tile / tiles_x) * TILE + ((k0 >> 1) << 2);
+    const uint2 range = ranges[tile];
     const int total = range.y > range.x ? (int)(range.y - range.x) : 0;   // empty tiles hold (0xffffffff, 0)
 
     // Tt = transmittance of the pixel while it is open; a finished pixel (saturated, or outside the
@@ -134,12 +141,11 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     uint32_t last[SPW];
 #pragma unroll
     for (int i = 0; i < SPW; i++) {
-        const int k = k0 + i;
         Cr[i] = 0.f; Cg[i] = 0.f; Cb[i] = 0.f; Dd[i] = 0.f; last[i] = 0u;
-        const int px = X0 + ((k & 1) << 3) + lx, py = Y0 + ((k >> 1) << 2) + ly;
+        const int px = X0 + ((i & 1) << 3) + lx, py = Yr + ((i >> 1) << 2) + ly;
         Tt[i] = (px >= W || py >= H) ? -1.f : 1.f;
     }
-    const float pxf = (float)(X0 + lx), pyf = (float)(Y0 + ly);
+    const float pxf = (float)(X0 + lx), pyf = (float)(Yr + ly);
 
     // stage b of the list = entries [32 b, 32 b + 32); buffer b & 1
     auto issue = [&](const int b) {
@@ -147,7 +153,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         if (lane == 0) mbar_expect_tx(&bars[b & 1], 48u * (uint32_t)c);
         __syncwarp();
         if (lane < c)
-            bulk_g2s(&s_rec_[wid][b & 1][lane * 3], rec + point_list[range.x + 32 * b + lane], 48u, &bars[b & 1]);
+            bulk_g2s(&s_rec[b & 1][lane * 3], rec + point_list[range.x + 32 * b + lane], 48u, &bars[b & 1]);
     };
     Rec nxt;
     nxt.q0 = nxt.q1 = nxt.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -162,24 +168,24 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         uint32_t live = 0u;
 #pragma unroll
         for (int i = 0; i < SPW; i++)
-            if (__any_sync(0xffffffffu, Tt[i] > 0.f)) live |= 1u << (k0 + i);
+            if (__any_sync(0xffffffffu, Tt[i] > 0.f)) live |= 1u << i;
         if (live == 0u) break;
         const int cnt = min(32, total - base);
-        const float4* const srec = s_rec_[wid][TMA ? (b & 1) : 0];
+        const float4* const srec = s_rec[TMA ? (b & 1) : 0];
         Rec cur;
         if (TMA) {
             mbar_wait(&bars[b & 1], (uint32_t)(b >> 1) & 1u);
-            __syncwarp();                            // (also orders the generic s_id stores of this stage)
+            __syncwarp();
             if (b + 1 < nbatch) issue(b + 1);        // the other buffer was released by the __syncwarp below
             cur.q0 = srec[lane * 3]; cur.q1 = srec[lane * 3 + 1]; cur.q2 = srec[lane * 3 + 2];
         } else {
             cur = nxt;
             __syncwarp();
-            s_rec_[wid][0][lane * 3] = cur.q0; s_rec_[wid][0][lane * 3 + 1] = cur.q1; s_rec_[wid][0][lane * 3 + 2] = cur.q2;
+            s_rec[0][lane * 3] = cur.q0; s_rec[0][lane * 3 + 1] = cur.q1; s_rec[0][lane * 3 + 2] = cur.q2;
             __syncwarp();
             if (base + 32 + lane < total) nxt = load_rec(rec, point_list[range.x + base + 32 + lane]);
         }
-        const uint32_t mymask = lane < cnt ? slot_mask(cur, (float)X0, (float)Y0, live) : 0u;
+        const uint32_t mymask = lane < cnt ? slot_mask<SPW>(cur, (float)X0, (float)Yr, live) : 0u;
 
         for (int j = 0; j < cnt; j++) {
             const uint32_t mj = __shfl_sync(0xffffffffu, mymask, j);
@@ -187,7 +193,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
             const float4 q0 = srec[j * 3];
             const float4 q1 = srec[j * 3 + 1];
             const float4 q2 = srec[j * 3 + 2];
-            // power(dx, dy) = cA dx^2 + dy (cB dx + cC dy): the dx-only terms are shared by the 4 slots of
+            // power(dx, dy) = cA dx^2 + dy (cB dx + cC dy): the dx-only terms are shared by the slots of
             // a column and hoisted, leaving 2 FFMA per pixel
             const float dxa = q0.x - pxf, dxb = dxa - 8.f;
             const float ax[2] = {(q0.z * dxa) * dxa, (q0.z * dxb) * dxb};
@@ -195,12 +201,9 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
             const float dy0 = q0.y - pyf;
             const float dys[4] = {dy0, dy0 - 4.f, dy0 - 8.f, dy0 - 12.f};
             const uint32_t idx = (uint32_t)(base + j + 1);
-#pragma unroll
-            for (int i = 0; i < SPW; i++) {
-                const int k = k0 + i;
-                if (!(mj & (1u << k))) continue;      // warp-uniform
-                const float dy = dys[k >> 1];
-                const float power = fmaf(dy, fmaf(q1.x, dy, bx[k & 1]), ax[k & 1]);
+            auto blend = [&](const int i) {
+                const float dy = dys[i >> 1];
+                const float power = fmaf(dy, fmaf(q1.x, dy, bx[i & 1]), ax[i & 1]);
                 // straight-line, predicated: the reference's skip chain (A.8) without divergent branches.
                 // (alpha >= 1/255 implies power >= pmin2 - margin: the slot bound needs no per-pixel twin.)
                 const float araw = fminf(ALPHA_MAX, q1.y * ex2(power));
@@ -217,7 +220,10 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                 Dd[i] = fmaf(q1.z, w, Dd[i]);
                 Tt[i] = open ? test_T : -fabsf(Tt[i]);
                 last[i] = go ? idx : last[i];
-            }
+            };
+#pragma unroll
+            for (int i = 0; i < SPW; i++)
+                if (mj & (1u << i)) blend(i);      // warp-uniform branch
         }
         __syncwarp();      // every lane is done with this stage before it is refilled
     }
@@ -226,8 +232,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const size_t N = (size_t)W * H;
 #pragma unroll
     for (int i = 0; i < SPW; i++) {
-        const int k = k0 + i;
-        const int px = X0 + ((k & 1) << 3) + lx, py = Y0 + ((k >> 1) << 2) + ly;
+        const int px = X0 + ((i & 1) << 3) + lx, py = Yr + ((i >> 1) << 2) + ly;
         if (px < W && py < H) {
             const size_t pid = (size_t)py * W + px;
             const float T = fabsf(Tt[i]);
@@ -240,6 +245,26 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
             final_T[pid] = T;
         }
     }
+}
+
+template <int MINB, bool TMA>
+__global__ void __launch_bounds__(32, MINB)
+render_forward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __restrict__ ranges,
+                      const uint32_t* __restrict__ point_list, const Record* __restrict__ rec, int W, int H,
+                      const float* __restrict__ bg, const int64_t* __restrict__ status, int64_t capacity,
+                      float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha,
+                      uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
+    __shared__ __align__(16) float4 s_rec[2][96];        // 2 stages x 32 records x {q0, q1, q2}
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    if (status[0] > capacity) return;   // binning overflowed: caller re-runs with a larger buffer
+    int b = blockIdx.x;
+#define SCGR_ARGS s_rec, s_bar, ranges, point_list, rec, W, H, bg, out_color, out_depth, out_alpha, n_contrib, final_T
+    if (b < ws.n8) { forward_region<8, TMA>(b, tiles_x, 0, SCGR_ARGS); return; }
+    b -= ws.n8;
+    if (b < 2 * ws.n4) { forward_region<4, TMA>(ws.n8 + (b >> 1), tiles_x, (b & 1) << 2, SCGR_ARGS); return; }
+    b -= 2 * ws.n4;
+    forward_region<2, TMA>(ws.n8 + ws.n4 + (b >> 2), tiles_x, (b & 3) << 1, SCGR_ARGS);
+#undef SCGR_ARGS
 }
 
 // ------------------------------------------------------------------------------------------
@@ -289,31 +314,24 @@ __device__ __forceinline__ float transpose_reduce10(const float v[10], const int
     return d;
 }
 
-template <int WPT, int MINB, bool TMA>
-__global__ void __launch_bounds__(32 * WPT, MINB)
-render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                       const Record* __restrict__ rec, int W, int H, const float* __restrict__ bg,
-                       const int64_t* __restrict__ status, int64_t capacity,
-                       const uint32_t* __restrict__ n_contrib, const float* __restrict__ final_T,
-                       const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
-                       const float* __restrict__ dL_dalpha, ScreenGrad* __restrict__ screen_grad) {
-    constexpr int SPW = SLOTS / WPT;      // slots per warp
-    __shared__ __align__(16) float4 s_rec_[WPT][2][96];        // 2 stages x 32 records x {q0, q1, q2}
-    __shared__ uint32_t s_id_[WPT][2][32];
-    __shared__ __align__(8) unsigned long long s_bar_[WPT][2];
-    __shared__ float4 s_g4[TILE_PIX];       // upstream gradients of the tile: r, g, b, depth
-    if (status[0] > capacity) return;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int k0 = wid * SPW;             // first slot of this warp
-    unsigned long long* const bars = s_bar_[wid];
+template <int SPW, bool TMA>
+__device__ __forceinline__ void
+backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[96], uint32_t (*s_idb)[32],
+                unsigned long long* bars, float4* s_g4, const uint2* __restrict__ ranges,
+                const uint32_t* __restrict__ point_list, const Record* __restrict__ rec, const int W, const int H,
+                const float* __restrict__ bg, const uint32_t* __restrict__ n_contrib,
+                const float* __restrict__ final_T, const float* __restrict__ dL_dcolor,
+                const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha,
+                ScreenGrad* __restrict__ screen_grad) {
+    const int lane = threadIdx.x & 31;
     if (TMA) {
         if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
         mbar_fence_init();
         __syncwarp();
     }
     const int lx = lane & 7, ly = lane >> 3;
-    const int X0 = blockIdx.x * TILE, Y0 = blockIdx.y * TILE;
-    const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
+    const int X0 = (tile % tiles_x) * TILE, Yr = (tile / tiles_x) * TILE + ((k0 >> 1) << 2);
+    const uint2 range = ranges[tile];
     const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
     const size_t N = (size_t)W * H;
 
@@ -323,8 +341,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     int toDo = 0;
 #pragma unroll
     for (int i = 0; i < SPW; i++) {
-        const int k = k0 + i;
-        const int px = X0 + ((k & 1) << 3) + lx, py = Y0 + ((k >> 1) << 2) + ly;
+        const int px = X0 + ((i & 1) << 3) + lx, py = Yr + ((i >> 1) << 2) + ly;
         float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f, Tf = 0.f;
         lc[i] = 0;
         if (px < W && py < H) {
@@ -335,14 +352,14 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
             gd = dL_ddepth[pid];
             ga = dL_dalpha[pid];
         }
-        s_g4[k * 32 + lane] = make_float4(gr, gg, gb, gd);
+        s_g4[i * 32 + lane] = make_float4(gr, gg, gb, gd);
         T[i] = Tf;
         tfb[i] = Tf * (ga - (bg0 * gr + bg1 * gg + bg2 * gb));
         Bs[i] = 0.f;
         slot_lc[i] = __reduce_max_sync(0xffffffffu, lc[i]);
         toDo = max(toDo, slot_lc[i]);
     }
-    const float pxf = (float)(X0 + lx), pyf = (float)(Y0 + ly);
+    const float pxf = (float)(X0 + lx), pyf = (float)(Yr + ly);
     // (each lane only ever reads back the s_g4 entries it wrote itself: no barrier needed)
 
     // batch entry j  <->  0-based list position  pos = toDo - 1 - (base + j)   (back to front)
@@ -353,8 +370,8 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
         __syncwarp();
         if (lane < c) {
             const uint32_t id = point_list[range.x + (toDo - 1 - (32 * b + lane))];
-            s_id_[wid][b & 1][lane] = id;
-            bulk_g2s(&s_rec_[wid][b & 1][lane * 3], rec + id, 48u, &bars[b & 1]);
+            s_idb[b & 1][lane] = id;
+            bulk_g2s(&s_rec[b & 1][lane * 3], rec + id, 48u, &bars[b & 1]);
         }
     };
     Rec nxt;
@@ -369,8 +386,8 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     for (int b = 0; b < nbatch; b++) {
         const int base = 32 * b;
         const int cnt = min(32, toDo - base);
-        const float4* const srec = s_rec_[wid][TMA ? (b & 1) : 0];
-        const uint32_t* const s_id = s_id_[wid][TMA ? (b & 1) : 0];
+        const float4* const srec = s_rec[TMA ? (b & 1) : 0];
+        const uint32_t* const s_id = s_idb[TMA ? (b & 1) : 0];
         Rec cur;
         if (TMA) {
             mbar_wait(&bars[b & 1], (uint32_t)(b >> 1) & 1u);
@@ -380,8 +397,8 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
         } else {
             cur = nxt;
             __syncwarp();
-            s_rec_[wid][0][lane * 3] = cur.q0; s_rec_[wid][0][lane * 3 + 1] = cur.q1; s_rec_[wid][0][lane * 3 + 2] = cur.q2;
-            s_id_[wid][0][lane] = nxt_id;
+            s_rec[0][lane * 3] = cur.q0; s_rec[0][lane * 3 + 1] = cur.q1; s_rec[0][lane * 3 + 2] = cur.q2;
+            s_idb[0][lane] = nxt_id;
             __syncwarp();
             if (base + 32 + lane < toDo) {
                 nxt_id = point_list[range.x + (toDo - 1 - (base + 32 + lane))];
@@ -394,8 +411,8 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
             uint32_t live = 0u;
 #pragma unroll
             for (int i = 0; i < SPW; i++)
-                if (mypos < slot_lc[i]) live |= 1u << (k0 + i);
-            mymask = slot_mask(cur, (float)X0, (float)Y0, live);
+                if (mypos < slot_lc[i]) live |= 1u << i;
+            mymask = slot_mask<SPW>(cur, (float)X0, (float)Yr, live);
         }
         for (int j = 0; j < cnt; j++) {
             const uint32_t mj = __shfl_sync(0xffffffffu, mymask, j);
@@ -415,12 +432,9 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 #pragma unroll
             for (int i = 0; i < 10; i++) v[i] = 0.f;
             float tsum = 0.f;                                // > 0 <=> some pixel of this lane took the pair
-#pragma unroll
-            for (int i = 0; i < SPW; i++) {
-                const int k = k0 + i;
-                if (!(mj & (1u << k))) continue;      // warp-uniform
-                const float dx = dxs[k & 1], dy = dys[k >> 1];
-                const float power = fmaf(dy, fmaf(q1.x, dy, bx[k & 1]), ax[k & 1]);
+            auto pair_grad = [&](const int i) {
+                const float dx = dxs[i & 1], dy = dys[i >> 1];
+                const float power = fmaf(dy, fmaf(q1.x, dy, bx[i & 1]), ax[i & 1]);
                 // straight-line: a pair that fails the reference's tests (A.9) runs with og = alpha = 0, which
                 // makes every term below vanish and leaves the pixel state untouched.
                 // min(0.99, og) >= 1/255  <=>  og >= 1/255
@@ -431,7 +445,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
                 const float alpha = fminf(ALPHA_MAX, og);
                 const float ra = rcp_approx(1.f - alpha);    // 1 - alpha >= 0.01
                 T[i] *= ra;                                  // transmittance in front of this Gaussian
-                const float4 g4 = s_g4[k * 32 + lane];       // upstream dL/d{r, g, b, depth} of this pixel
+                const float4 g4 = s_g4[i * 32 + lane];       // upstream dL/d{r, g, b, depth} of this pixel
                 // Only the upstream-weighted sum over channels of the suffix blend is needed:
                 //   Bs = sum_ch g_ch A_ch,  A_ch <- alpha c_ch + (1 - alpha) A_ch   =>   Bs <- Bs + alpha (g.c - Bs)
                 const float cg = fmaf(q1.z, g4.w, fmaf(q2.z, g4.z, fmaf(q2.y, g4.y, q2.x * g4.x)));
@@ -450,7 +464,10 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
                 v[5] += uG;                                  // / opacity = dL/dopacity
                 v[6] = fmaf(w, g4.w, v[6]);                  // dL/ddepth
                 v[7] = fmaf(w, g4.x, v[7]); v[8] = fmaf(w, g4.y, v[8]); v[9] = fmaf(w, g4.z, v[9]);
-            }
+            };
+#pragma unroll
+            for (int i = 0; i < SPW; i++)
+                if (mj & (1u << i)) pair_grad(i);  // warp-uniform branch
             if (!__any_sync(0xffffffffu, tsum > 0.f)) continue;
             int slot;
             const float sum = transpose_reduce10(v, lane, &slot);
@@ -461,9 +478,46 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     }
 }
 
+template <int MINB, bool TMA>
+__global__ void __launch_bounds__(32, MINB)
+render_backward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __restrict__ ranges,
+                       const uint32_t* __restrict__ point_list, const Record* __restrict__ rec, int W, int H,
+                       const float* __restrict__ bg, const int64_t* __restrict__ status, int64_t capacity,
+                       const uint32_t* __restrict__ n_contrib, const float* __restrict__ final_T,
+                       const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
+                       const float* __restrict__ dL_dalpha, ScreenGrad* __restrict__ screen_grad) {
+    __shared__ __align__(16) float4 s_rec[2][96];        // 2 stages x 32 records x {q0, q1, q2}
+    __shared__ uint32_t s_id[2][32];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ float4 s_g4[TILE_PIX];       // upstream gradients of the region: r, g, b, depth
+    if (status[0] > capacity) return;
+    int b = blockIdx.x;
+#define SCGR_ARGS s_rec, s_id, s_bar, s_g4, ranges, point_list, rec, W, H, bg, n_contrib, final_T, dL_dcolor, dL_ddepth, \
+                  dL_dalpha, screen_grad
+    if (b < ws.n8) { backward_region<8, TMA>(b, tiles_x, 0, SCGR_ARGS); return; }
+    b -= ws.n8;
+    if (b < 2 * ws.n4) { backward_region<4, TMA>(ws.n8 + (b >> 1), tiles_x, (b & 1) << 2, SCGR_ARGS); return; }
+    b -= 2 * ws.n4;
+    backward_region<2, TMA>(ws.n8 + ws.n4 + (b >> 2), tiles_x, (b & 3) << 1, SCGR_ARGS);
+#undef SCGR_ARGS
+}
+
 int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
+}
+
+// tiles rendered whole / in halves / in quarters: SCGR_SPLIT="h,q" = percent of the tiles (by index,
+// from the end) cut in halves and in quarters
+WorkSplit make_split(const int n_tiles, const char* env, const int dflt_half, const int dflt_quarter) {
+    int ph = dflt_half, pq = dflt_quarter;
+    if (const char* e = getenv(env)) sscanf(e, "%d,%d", &ph, &pq);
+    WorkSplit ws;
+    ws.n2 = (int)((int64_t)n_tiles * pq / 100);
+    ws.n4 = (int)((int64_t)n_tiles * ph / 100);
+    if (ws.n2 + ws.n4 > n_tiles) { ws.n2 = 0; ws.n4 = n_tiles; }
+    ws.n8 = n_tiles - ws.n4 - ws.n2;
+    return ws;
 }
 
 }  // namespace
@@ -471,17 +525,16 @@ int env_int(const char* name, int dflt) {
 void launch_render_forward(const ScgrView& v, const GeometryLayout& G, const BinningLayout& B,
                            const uint32_t* point_list, int64_t capacity, const ImageLayout& I,
                            float* out_color, float* out_depth, float* out_alpha, const Launch& L) {
-    const dim3 grid((v.image_width + TILE - 1) / TILE, (v.image_height + TILE - 1) / TILE);
-    if (grid.x == 0 || grid.y == 0) return;
-    static const int wpt = env_int("SCGR_FWD_WPT", 1);
-    begin_kernel("render_forward", L);
+    const int tx = (v.image_width + TILE - 1) / TILE, ty = (v.image_height + TILE - 1) / TILE;
+    if (tx == 0 || ty == 0) return;
     static const int minb = env_int("SCGR_FWD_MINB", 20);
     static const int tma = env_int("SCGR_TMA", 0);
-#define SCGR_FWD(W_, M_, T_) render_forward_kernel<W_, M_, T_><<<grid, 32 * W_, 0, L.stream>>>(B.ranges, point_list, G.rec, \
+    const WorkSplit ws = make_split(tx * ty, "SCGR_FWD_SPLIT", 10, 5);
+    begin_kernel("render_forward", L);
+#define SCGR_FWD(M_, T_) render_forward_kernel<M_, T_><<<ws.items(), 32, 0, L.stream>>>(ws, tx, B.ranges, point_list, G.rec, \
         v.image_width, v.image_height, v.bg, G.status, capacity, out_color, out_depth, out_alpha, I.n_contrib, I.final_T)
-    if (wpt == 2) SCGR_FWD(2, 1, false); else if (wpt == 4) SCGR_FWD(4, 1, false);
-    else if (!tma) { if (minb == 20) SCGR_FWD(1, 20, false); else SCGR_FWD(1, 1, false); }
-    else if (minb == 20) SCGR_FWD(1, 20, true); else if (minb == 24) SCGR_FWD(1, 24, true); else SCGR_FWD(1, 1, true);
+    if (!tma) { if (minb == 20) SCGR_FWD(20, false); else if (minb == 24) SCGR_FWD(24, false); else SCGR_FWD(1, false); }
+    else if (minb == 20) SCGR_FWD(20, true); else if (minb == 24) SCGR_FWD(24, true); else SCGR_FWD(1, true);
 #undef SCGR_FWD
     check_launch("render_forward", L);
 }
@@ -490,20 +543,18 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
                             const uint32_t* point_list, int64_t capacity, const ImageLayout& I,
                             const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                             int32_t P, const Launch& L) {
-    const dim3 grid((v.image_width + TILE - 1) / TILE, (v.image_height + TILE - 1) / TILE);
+    const int tx = (v.image_width + TILE - 1) / TILE, ty = (v.image_height + TILE - 1) / TILE;
     cudaMemsetAsync(G.screen_grad, 0, (size_t)(P > 0 ? P : 0) * sizeof(ScreenGrad), L.stream);
-    if (grid.x == 0 || grid.y == 0) return;
-    static const int wpt = env_int("SCGR_BWD_WPT", 1);
-    begin_kernel("render_backward", L);
-    static const int minb = env_int("SCGR_BWD_MINB", 14);
+    if (tx == 0 || ty == 0) return;
+    static const int minb = env_int("SCGR_BWD_MINB", 16);
     static const int tma = env_int("SCGR_TMA", 0);
-#define SCGR_BWD(W_, M_, T_) render_backward_kernel<W_, M_, T_><<<grid, 32 * W_, 0, L.stream>>>(B.ranges, point_list, \
+    const WorkSplit ws = make_split(tx * ty, "SCGR_BWD_SPLIT", 0, 0);
+    begin_kernel("render_backward", L);
+#define SCGR_BWD(M_, T_) render_backward_kernel<M_, T_><<<ws.items(), 32, 0, L.stream>>>(ws, tx, B.ranges, point_list, \
         G.rec, v.image_width, v.image_height, v.bg, G.status, capacity, I.n_contrib, I.final_T, dL_dcolor, dL_ddepth, \
         dL_dalpha, G.screen_grad)
-    if (wpt == 2) SCGR_BWD(2, 1, false); else if (wpt == 4) SCGR_BWD(4, 1, false);
-    else if (!tma) { if (minb == 14) SCGR_BWD(1, 14, false); else if (minb == 16) SCGR_BWD(1, 16, false); else SCGR_BWD(1, 1, false); }
-    else if (minb == 16) SCGR_BWD(1, 16, true); else if (minb == 14) SCGR_BWD(1, 14, true);
-    else SCGR_BWD(1, 1, true);
+    if (!tma) { if (minb == 16) SCGR_BWD(16, false); else if (minb == 14) SCGR_BWD(14, false); else SCGR_BWD(1, false); }
+    else if (minb == 16) SCGR_BWD(16, true); else if (minb == 14) SCGR_BWD(14, true); else SCGR_BWD(1, true);
 #undef SCGR_BWD
     check_launch("render_backward", L);
 }
