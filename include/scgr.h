@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SCGR_VERSION 100   /* major*10000 + minor*100 + patch */
+#define SCGR_VERSION 101   /* major*10000 + minor*100 + patch */
 #define SCGR_TILE 16        /* BLOCK_X = BLOCK_Y of the external rasterizer's config.h */
 
 typedef void* scgr_stream_t;   /* cudaStream_t */
@@ -115,6 +115,22 @@ int scgr_forward_render(const ScgrView* view, const ScgrGaussians* g, void* geom
                         void* binning_scratch, int64_t capacity, void* image_scratch,
                         float* out_color, float* out_depth, float* out_alpha,
                         int64_t* status_host, scgr_stream_t stream);
+
+/* GaussianRasterizer.forward in ONE call: stage 1, the forward's single host wait (for R; the
+ * reference's forward blocks at the same point on a D2H copy), stage 2 -- without returning to the
+ * caller in between.  `status_host` (required) is int64[2] in pinned host memory; when it is
+ * device-mapped (cudaHostAlloc memory under unified addressing is) the device stores R into it
+ * directly and the host spins on the word instead of synchronising the stream.  `binning_scratch`
+ * must have been sized for `capacity` instances by the caller *before* the call (e.g. from the
+ * previous view's R plus headroom); it may be NULL with capacity 0.
+ * Returns 0 when the images were rendered, SCGR_NEED_CAPACITY when stage 1 completed but
+ * R = status_host[0] exceeds `capacity`: the geometry scratch is valid, nothing of stage 2 ran; the
+ * caller allocates >= R and finishes with scgr_forward_render().  Any other value is an error. */
+#define SCGR_NEED_CAPACITY 3
+int scgr_forward(const ScgrView* view, const ScgrGaussians* g, void* geometry_scratch, int32_t* radii,
+                 void* binning_scratch, int64_t capacity, void* image_scratch,
+                 float* out_color, float* out_depth, float* out_alpha,
+                 int64_t* status_host, scgr_stream_t stream);
 
 /* _RasterizeGaussians.backward: needs the inputs and the three scratch buffers of the matching
  * forward, untouched. */

@@ -51,6 +51,9 @@ SYMBOLS = {
     "scgr_forward_render": (C.c_int, [C.POINTER(ScgrView), C.POINTER(ScgrGaussians), C.c_void_p,
                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scgr_forward": (C.c_int, [C.POINTER(ScgrView), C.POINTER(ScgrGaussians), C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p]),
     "scgr_backward": (C.c_int, [C.POINTER(ScgrView), C.POINTER(ScgrGaussians), C.c_void_p, C.c_void_p,
                                 C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.POINTER(ScgrGrads), C.c_void_p]),
@@ -61,6 +64,8 @@ SYMBOLS = {
     "scgr_debug_views": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.POINTER(ScgrDebugViews)]),
 }
+
+NEED_CAPACITY = 3   # SCGR_NEED_CAPACITY (include/scgr.h)
 
 _lib = None
 

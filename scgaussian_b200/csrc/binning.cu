@@ -81,7 +81,8 @@ __device__ __forceinline__ void st_volatile64(unsigned long long* p, unsigned lo
 
 __global__ void __launch_bounds__(SCAN_BLOCK)
 scan_offsets_kernel(const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ order, int P,
-                    uint32_t* __restrict__ offsets, int64_t* __restrict__ status, unsigned long long* __restrict__ state) {
+                    uint32_t* __restrict__ offsets, int64_t* __restrict__ status, unsigned long long* __restrict__ state,
+                    volatile int64_t* status_mapped) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_prefix;
@@ -129,6 +130,12 @@ scan_offsets_kernel(const uint32_t* __restrict__ tiles_touched, const uint32_t* 
             if ((int)tile == ntiles - 1) {
                 status[0] = (int64_t)(excl + total);   // R = num_rendered
                 status[1] = 0;                         // overflow flag, raised later by the emission kernel
+                if (status_mapped) {
+                    // zero-copy store into the caller's pinned host word: scgr_forward() spins on it
+                    // instead of paying a D2H copy + stream synchronisation
+                    status_mapped[0] = (int64_t)(excl + total);
+                    __threadfence_system();
+                }
             }
         }
     }
@@ -574,7 +581,7 @@ int tile_partition_final_buffer(uint32_t n_tiles) { return plan_tile_passes(n_ti
 
 // depth order of the Gaussians (ascending depth bits, ties by index; culled ones last), then the
 // inclusive prefix sum of tiles touched in that order and R.
-void launch_depth_order(const GeometryLayout& G, int32_t P, const Launch& L) {
+void launch_depth_order(const GeometryLayout& G, int32_t P, int64_t* status_mapped, const Launch& L) {
     if (P <= 0) return;
     // preprocess already wrote sort_keys[0] (= depth_key) and sort_vals[0] (= 0..P-1)
     const size_t pw = sweep_pass_words(P);
@@ -593,7 +600,8 @@ void launch_depth_order(const GeometryLayout& G, int32_t P, const Launch& L) {
     const uint32_t* order = G.sort_vals[0];
     const int nblk = (P + SCAN_TILE - 1) / SCAN_TILE;
     begin_kernel("scan_offsets", L);
-    scan_offsets_kernel<<<nblk, SCAN_BLOCK, 0, L.stream>>>(G.tiles_touched, order, P, G.offsets, G.status, G.scan_state);
+    scan_offsets_kernel<<<nblk, SCAN_BLOCK, 0, L.stream>>>(G.tiles_touched, order, P, G.offsets, G.status, G.scan_state,
+                                                           status_mapped);
     check_launch("scan_offsets", L);
 }
 

@@ -3,6 +3,7 @@
 // RasterizeGaussiansCUDA / RasterizeGaussiansBackwardCUDA / markVisible + Rasterizer::forward /
 // backward without torch types, allocations or host syncs.
 #include <atomic>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -127,11 +128,34 @@ int scgr_forward_geometry(const ScgrView* view, const ScgrGaussians* g, void* ge
         } else {
             require(radii != nullptr, "null radii");
             launch_preprocess_forward(*view, *g, G, radii, L);
-            launch_depth_order(G, g->P, L);
+            launch_depth_order(G, g->P, nullptr, L);
         }
         copy_status(G, status_host, L.stream);
         check_stage("forward_geometry", L);
     });
+}
+
+// stage 2 proper (shared by scgr_forward_render and scgr_forward)
+static void enqueue_render_stage(const ScgrView* view, const ScgrGaussians* g, void* geometry_scratch,
+                                 void* binning_scratch, int64_t capacity, void* image_scratch, float* out_color,
+                                 float* out_depth, float* out_alpha, const Launch& L) {
+    const int W = view->image_width, H = view->image_height;
+    const GeometryLayout G = carve_geometry(geometry_scratch, g->P);
+    const BinningLayout B = carve_binning(binning_scratch, W, H, capacity);
+    const ImageLayout I = carve_image(image_scratch, W, H);
+    if (g->P == 0) {
+        // section 8b: P = 0 returns all-zero images (not background-filled)
+        const size_t N = (size_t)W * H;
+        cudaMemsetAsync(out_color, 0, 3 * N * sizeof(float), L.stream);
+        cudaMemsetAsync(out_depth, 0, N * sizeof(float), L.stream);
+        cudaMemsetAsync(out_alpha, 0, N * sizeof(float), L.stream);
+        cudaMemsetAsync(I.n_contrib, 0, N * sizeof(uint32_t), L.stream);
+        cudaMemsetAsync(I.final_T, 0, N * sizeof(float), L.stream);
+    } else {
+        int fin = 0;
+        launch_emit_and_partition(*view, G, B, g->P, capacity, &fin, L);
+        launch_render_forward(*view, G, B, B.vals[fin], capacity, I, out_color, out_depth, out_alpha, L);
+    }
 }
 
 int scgr_forward_render(const ScgrView* view, const ScgrGaussians* g, void* geometry_scratch,
@@ -144,26 +168,86 @@ int scgr_forward_render(const ScgrView* view, const ScgrGaussians* g, void* geom
         require(out_color && out_depth && out_alpha, "null outputs");
         require(capacity >= 0 && capacity < (int64_t)0xFFFFFFFFll, "capacity out of range");
         const Launch L{(cudaStream_t)stream, view->debug != 0};
-        const int W = view->image_width, H = view->image_height;
-        const GeometryLayout G = carve_geometry(geometry_scratch, g->P);
-        const BinningLayout B = carve_binning(binning_scratch, W, H, capacity);
-        const ImageLayout I = carve_image(image_scratch, W, H);
-        if (g->P == 0) {
-            // section 8b: P = 0 returns all-zero images (not background-filled)
-            const size_t N = (size_t)W * H;
-            cudaMemsetAsync(out_color, 0, 3 * N * sizeof(float), L.stream);
-            cudaMemsetAsync(out_depth, 0, N * sizeof(float), L.stream);
-            cudaMemsetAsync(out_alpha, 0, N * sizeof(float), L.stream);
-            cudaMemsetAsync(I.n_contrib, 0, N * sizeof(uint32_t), L.stream);
-            cudaMemsetAsync(I.final_T, 0, N * sizeof(float), L.stream);
-        } else {
-            int fin = 0;
-            launch_emit_and_partition(*view, G, B, g->P, capacity, &fin, L);
-            launch_render_forward(*view, G, B, B.vals[fin], capacity, I, out_color, out_depth, out_alpha, L);
-        }
-        copy_status(G, status_host, L.stream);
+        enqueue_render_stage(view, g, geometry_scratch, binning_scratch, capacity, image_scratch, out_color,
+                             out_depth, out_alpha, L);
+        copy_status(carve_geometry(geometry_scratch, g->P), status_host, L.stream);
         check_stage("forward_render", L);
     });
+}
+
+// Host wait for R between the two stages of scgr_forward().  The scan kernel stores R straight into
+// the caller's pinned word (zero-copy), so the host sees it a PCIe write after the kernel retires
+// and stage 2 is enqueued a few microseconds later -- no D2H memcpy, no stream synchronisation, no
+// return to the caller's language in between.  A failed stream is detected by polling it.
+static int64_t wait_for_count(volatile int64_t* word, int64_t sentinel, cudaStream_t stream) {
+    for (uint64_t spins = 1;; spins++) {
+        const int64_t v = *word;
+        if (v != sentinel) return v;
+        if ((spins & 0x3ff) == 0) {
+            const cudaError_t q = cudaStreamQuery(stream);
+            if (q == cudaErrorNotReady) continue;
+            if (q != cudaSuccess) throw std::runtime_error(std::string("scgr: forward stage 1: ") + cudaGetErrorString(q));
+            const int64_t w = *word;   // stream drained: the store must be visible by now
+            if (w != sentinel) return w;
+            throw std::runtime_error("scgr: forward stage 1 finished without publishing num_rendered");
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+}
+
+int scgr_forward(const ScgrView* view, const ScgrGaussians* g, void* geometry_scratch, int32_t* radii,
+                 void* binning_scratch, int64_t capacity, void* image_scratch, float* out_color,
+                 float* out_depth, float* out_alpha, int64_t* status_host, scgr_stream_t stream) {
+    bool need_capacity = false;
+    const int rc = guarded([&] {
+        validate(view, g);
+        require(geometry_scratch && image_scratch, "null scratch");
+        require((reinterpret_cast<uintptr_t>(geometry_scratch) & 255) == 0, "geometry scratch must be 256-byte aligned");
+        require(out_color && out_depth && out_alpha, "null outputs");
+        require(status_host != nullptr, "scgr_forward needs a pinned host status word");
+        require(capacity >= 0 && capacity < (int64_t)0xFFFFFFFFll, "capacity out of range");
+        const Launch L{(cudaStream_t)stream, view->debug != 0};
+        const GeometryLayout G = carve_geometry(geometry_scratch, g->P);
+        int64_t R = 0;
+        if (g->P == 0) {
+            cudaMemsetAsync(G.status, 0, 2 * sizeof(int64_t), L.stream);
+            status_host[0] = 0;
+            status_host[1] = 0;
+        } else {
+            require(radii != nullptr, "null radii");
+            constexpr int64_t kSentinel = INT64_MIN;
+            void* mapped = nullptr;
+            const bool zero_copy = cudaHostGetDevicePointer(&mapped, status_host, 0) == cudaSuccess && mapped != nullptr;
+            if (!zero_copy) (void)cudaGetLastError();
+            status_host[1] = 0;
+            *(volatile int64_t*)status_host = kSentinel;
+            launch_preprocess_forward(*view, *g, G, radii, L);
+            launch_depth_order(G, g->P, zero_copy ? (int64_t*)mapped : nullptr, L);
+            if (zero_copy) {
+                R = wait_for_count((volatile int64_t*)status_host, kSentinel, L.stream);
+            } else {   // status_host is not device-mapped: the reference's protocol (copy + synchronise)
+                copy_status(G, status_host, L.stream);
+                const cudaError_t e = cudaStreamSynchronize(L.stream);
+                if (e != cudaSuccess) throw std::runtime_error(std::string("scgr: forward stage 1: ") + cudaGetErrorString(e));
+                R = status_host[0];
+            }
+        }
+        if (g->P != 0 && (binning_scratch == nullptr || R > capacity)) {
+            need_capacity = true;     // stage 1 is complete and stays valid: size the buffer, call scgr_forward_render
+            return;
+        }
+        require(binning_scratch != nullptr, "null binning scratch");
+        enqueue_render_stage(view, g, geometry_scratch, binning_scratch, capacity, image_scratch, out_color, out_depth,
+                             out_alpha, L);
+        check_stage("forward", L);
+    });
+    if (rc == 0 && need_capacity) {
+        g_last_error = "scgr: binning capacity too small (not an error: call scgr_forward_render with capacity >= status_host[0])";
+        return SCGR_NEED_CAPACITY;
+    }
+    return rc;
 }
 
 int scgr_backward(const ScgrView* view, const ScgrGaussians* g, const void* geometry_scratch,

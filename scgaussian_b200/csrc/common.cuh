@@ -167,6 +167,8 @@ inline BinningLayout carve_binning(void* base, int32_t W, int32_t H, int64_t cap
 struct ImageLayout {
     uint32_t* n_contrib;      // [H*W]
     float* final_T;           // [H*W]
+    uint4* tile_todo;         // [tiles] max n_contrib of the (up to 4) forward work items of the tile
+    uint32_t* tile_order;     // [tiles] tiles by descending work, built by the backward (longest first)
     size_t bytes;
 };
 
@@ -179,6 +181,10 @@ inline ImageLayout carve_image(void* base, int32_t W, int32_t H) {
     auto take = [&](size_t n) { char* p = b + o; o += align_up(n); return (void*)p; };
     L.n_contrib = (uint32_t*)take(N * 4);
     L.final_T = (float*)take(N * 4);
+    size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    if (tiles == 0) tiles = 1;
+    L.tile_todo = (uint4*)take(tiles * sizeof(uint4));
+    L.tile_order = (uint32_t*)take(tiles * 4);
     L.bytes = o;
     return L;
 }
@@ -196,7 +202,7 @@ void launch_preprocess_backward(const ScgrView& v, const ScgrGaussians& g, const
 void launch_mark_visible(const float* means3D, int32_t P, const float* viewmatrix, uint8_t* present,
                          const Launch& L);
 
-void launch_depth_order(const GeometryLayout& G, int32_t P, const Launch& L);
+void launch_depth_order(const GeometryLayout& G, int32_t P, int64_t* status_mapped, const Launch& L);
 void launch_emit_and_partition(const ScgrView& v, const GeometryLayout& G, const BinningLayout& B,
                                int32_t P, int64_t capacity, int* final_buffer, const Launch& L);
 

@@ -39,6 +39,22 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
+// (pos < lc && power <= 0 && og_raw >= 1/255) ? og_raw : 0  as three chained SETP and one SELP
+// (left to itself the compiler materialises each test with its own select)
+__device__ __forceinline__ float gate_pair(const float og_raw, const float power, const int pos, const int lc) {
+    float og;
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.lt.s32 p, %2, %3;\n\t"
+        "setp.le.and.f32 p, %4, 0f00000000, p;\n\t"
+        "setp.ge.and.f32 p, %1, 0f3B808081, p;\n\t"      // 1/255
+        "selp.f32 %0, %1, 0f00000000, p;\n\t"
+        "}"
+        : "=f"(og)
+        : "f"(og_raw), "r"(pos), "r"(lc), "f"(power));
+    return og;
+}
+
 __device__ __forceinline__ float rcp_approx(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -78,6 +94,28 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 struct Rec {
     float4 q0, q1, q2;
 };
+
+// ---- optional work counters (tools/render_stats.py builds a separate library with -DSCGR_STATS;
+// the product build compiles none of this) ----
+#ifdef SCGR_STATS
+__device__ unsigned long long d_render_stats[32];
+#define SCGR_STAT_DECL(n_) uint32_t st_##n_ = 0u
+#define SCGR_STAT_ADD(n_, v_) st_##n_ += (uint32_t)(v_)
+#define SCGR_STAT_FLUSH_WARP(slot_, n_)                                                              \
+    do {                                                                                             \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&d_render_stats[slot_], (unsigned long long)st_##n_); \
+    } while (0)
+#define SCGR_STAT_FLUSH_LANES(slot_, n_)                                                         \
+    do {                                                                                         \
+        const uint32_t t_ = __reduce_add_sync(0xffffffffu, st_##n_);                             \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&d_render_stats[slot_], (unsigned long long)t_); \
+    } while (0)
+#else
+#define SCGR_STAT_DECL(n_)
+#define SCGR_STAT_ADD(n_, v_)
+#define SCGR_STAT_FLUSH_WARP(slot_, n_)
+#define SCGR_STAT_FLUSH_LANES(slot_, n_)
+#endif
 
 __device__ __forceinline__ Rec load_rec(const Record* __restrict__ rec, uint32_t id) {
     const float4* p = reinterpret_cast<const float4*>(rec + id);
@@ -122,7 +160,7 @@ forward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[
                const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                const Record* __restrict__ rec, const int W, const int H, const float* __restrict__ bg,
                float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha,
-               uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
+               uint32_t* __restrict__ n_contrib, float* __restrict__ final_T, uint4* __restrict__ tile_todo) {
     const int lane = threadIdx.x & 31;
     if (TMA) {
         if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
@@ -161,6 +199,8 @@ forward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[
     if (TMA) { if (nbatch > 0) issue(0); }
     else if (lane < total) nxt = load_rec(rec, point_list[range.x + lane]);
 
+    SCGR_STAT_DECL(batches); SCGR_STAT_DECL(scanned); SCGR_STAT_DECL(hit); SCGR_STAT_DECL(slots);
+    SCGR_STAT_DECL(cand); SCGR_STAT_DECL(go);
     int b = 0;
     for (; b < nbatch; b++) {
         const int base = 32 * b;
@@ -186,10 +226,12 @@ forward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[
             if (base + 32 + lane < total) nxt = load_rec(rec, point_list[range.x + base + 32 + lane]);
         }
         const uint32_t mymask = lane < cnt ? slot_mask<SPW>(cur, (float)X0, (float)Yr, live) : 0u;
+        SCGR_STAT_ADD(batches, 1); SCGR_STAT_ADD(scanned, cnt);
 
         for (int j = 0; j < cnt; j++) {
             const uint32_t mj = __shfl_sync(0xffffffffu, mymask, j);
             if (mj == 0u) continue;
+            SCGR_STAT_ADD(hit, 1); SCGR_STAT_ADD(slots, __popc(mj));
             const float4 q0 = srec[j * 3];
             const float4 q1 = srec[j * 3 + 1];
             const float4 q2 = srec[j * 3 + 2];
@@ -214,12 +256,15 @@ forward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[
                 // open & (skipped | blended) -> test_T >= T_EPS.  Otherwise the pixel is finished, or saturates
                 // right here (this Gaussian is then NOT blended): keep -|T|.
                 const bool open = test_T >= T_EPS;
+#ifdef SCGR_STATS
                 const bool go = cand && open;
+#endif
                 const float w = open ? w0 : 0.f;
                 Cr[i] = fmaf(q2.x, w, Cr[i]); Cg[i] = fmaf(q2.y, w, Cg[i]); Cb[i] = fmaf(q2.z, w, Cb[i]);
                 Dd[i] = fmaf(q1.z, w, Dd[i]);
                 Tt[i] = open ? test_T : -fabsf(Tt[i]);
-                last[i] = go ? idx : last[i];
+                last[i] = w > 0.f ? idx : last[i];             // w > 0  <=>  cand && open (alpha >= 1/255, T >= 1e-4)
+                SCGR_STAT_ADD(cand, cand ? 1 : 0); SCGR_STAT_ADD(go, go ? 1 : 0);
             };
 #pragma unroll
             for (int i = 0; i < SPW; i++)
@@ -228,8 +273,27 @@ forward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[
         __syncwarp();      // every lane is done with this stage before it is refilled
     }
     if (TMA && b < nbatch) mbar_wait(&bars[b & 1], (uint32_t)(b >> 1) & 1u);   // drain the copy in flight before exiting
+    SCGR_STAT_FLUSH_WARP(0, batches); SCGR_STAT_FLUSH_WARP(1, scanned); SCGR_STAT_FLUSH_WARP(2, hit);
+    SCGR_STAT_FLUSH_WARP(3, slots); SCGR_STAT_FLUSH_LANES(4, cand); SCGR_STAT_FLUSH_LANES(5, go);
+#ifdef SCGR_STATS
+    if (lane == 0) { atomicAdd(&d_render_stats[6], 1ull); atomicAdd(&d_render_stats[7], (unsigned long long)total); }
+#endif
     const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
     const size_t N = (size_t)W * H;
+    {
+        // depth of the backward's walk over this region (max n_contrib): the backward dispatches tiles
+        // longest first.  Every work item of a tile owns its own words of the tile's uint4: no init pass.
+        uint32_t deepest = 0u;
+#pragma unroll
+        for (int i = 0; i < SPW; i++) deepest = max(deepest, last[i]);
+        deepest = __reduce_max_sync(0xffffffffu, deepest);
+        if (lane == 0) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(tile_todo + tile);
+            if (SPW == 8) tile_todo[tile] = make_uint4(deepest, 0u, 0u, 0u);
+            else if (SPW == 4) { w[k0 >> 1] = deepest; w[(k0 >> 1) + 1] = 0u; }
+            else w[k0 >> 1] = deepest;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < SPW; i++) {
         const int px = X0 + ((i & 1) << 3) + lx, py = Yr + ((i >> 1) << 2) + ly;
@@ -253,12 +317,12 @@ render_forward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __rest
                       const uint32_t* __restrict__ point_list, const Record* __restrict__ rec, int W, int H,
                       const float* __restrict__ bg, const int64_t* __restrict__ status, int64_t capacity,
                       float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha,
-                      uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
+                      uint32_t* __restrict__ n_contrib, float* __restrict__ final_T, uint4* __restrict__ tile_todo) {
     __shared__ __align__(16) float4 s_rec[2][96];        // 2 stages x 32 records x {q0, q1, q2}
     __shared__ __align__(8) unsigned long long s_bar[2];
     if (status[0] > capacity) return;   // binning overflowed: caller re-runs with a larger buffer
     int b = blockIdx.x;
-#define SCGR_ARGS s_rec, s_bar, ranges, point_list, rec, W, H, bg, out_color, out_depth, out_alpha, n_contrib, final_T
+#define SCGR_ARGS s_rec, s_bar, ranges, point_list, rec, W, H, bg, out_color, out_depth, out_alpha, n_contrib, final_T, tile_todo
     if (b < ws.n8) { forward_region<8, TMA>(b, tiles_x, 0, SCGR_ARGS); return; }
     b -= ws.n8;
     if (b < 2 * ws.n4) { forward_region<4, TMA>(ws.n8 + (b >> 1), tiles_x, (b & 1) << 2, SCGR_ARGS); return; }
@@ -383,9 +447,12 @@ backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)
         nxt_id = point_list[range.x + (toDo - 1 - lane)];
         nxt = load_rec(rec, nxt_id);
     }
+    SCGR_STAT_DECL(batches); SCGR_STAT_DECL(scanned); SCGR_STAT_DECL(hit); SCGR_STAT_DECL(slots);
+    SCGR_STAT_DECL(ok); SCGR_STAT_DECL(red); SCGR_STAT_DECL(atom);
     for (int b = 0; b < nbatch; b++) {
         const int base = 32 * b;
         const int cnt = min(32, toDo - base);
+        SCGR_STAT_ADD(batches, 1); SCGR_STAT_ADD(scanned, cnt);
         const float4* const srec = s_rec[TMA ? (b & 1) : 0];
         const uint32_t* const s_id = s_idb[TMA ? (b & 1) : 0];
         Rec cur;
@@ -417,6 +484,7 @@ backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)
         for (int j = 0; j < cnt; j++) {
             const uint32_t mj = __shfl_sync(0xffffffffu, mymask, j);
             if (mj == 0u) continue;
+            SCGR_STAT_ADD(hit, 1); SCGR_STAT_ADD(slots, __popc(mj));
             const int pos = toDo - 1 - (base + j);
             const float4 q0 = srec[j * 3];
             const float4 q1 = srec[j * 3 + 1];
@@ -431,7 +499,6 @@ backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)
             float v[10];
 #pragma unroll
             for (int i = 0; i < 10; i++) v[i] = 0.f;
-            float tsum = 0.f;                                // > 0 <=> some pixel of this lane took the pair
             auto pair_grad = [&](const int i) {
                 const float dx = dxs[i & 1], dy = dys[i >> 1];
                 const float power = fmaf(dy, fmaf(q1.x, dy, bx[i & 1]), ax[i & 1]);
@@ -439,9 +506,8 @@ backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)
                 // makes every term below vanish and leaves the pixel state untouched.
                 // min(0.99, og) >= 1/255  <=>  og >= 1/255
                 const float ograw = q1.y * ex2(power);
-                const bool ok = pos < lc[i] && power <= 0.f && ograw >= ALPHA_MIN;
-                const float og = ok ? ograw : 0.f;           // opacity * G, un-capped
-                tsum += og;
+                const float og = gate_pair(ograw, power, pos, lc[i]);   // opacity * G, un-capped
+                SCGR_STAT_ADD(ok, og > 0.f ? 1 : 0);
                 const float alpha = fminf(ALPHA_MAX, og);
                 const float ra = rcp_approx(1.f - alpha);    // 1 - alpha >= 0.01
                 T[i] *= ra;                                  // transmittance in front of this Gaussian
@@ -468,14 +534,21 @@ backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)
 #pragma unroll
             for (int i = 0; i < SPW; i++)
                 if (mj & (1u << i)) pair_grad(i);  // warp-uniform branch
-            if (!__any_sync(0xffffffffu, tsum > 0.f)) continue;
+            // (97 % of the pairs that get here have a contributing pixel: reduce unconditionally)
             int slot;
             const float sum = transpose_reduce10(v, lane, &slot);
+            SCGR_STAT_ADD(red, 1); SCGR_STAT_ADD(atom, (slot >= 0 && sum != 0.f) ? 1 : 0);
             if (slot >= 0 && sum != 0.f)
                 atomicAdd(reinterpret_cast<float*>(screen_grad + s_id[j]) + slot, sum);   // RED.E.ADD.F32
         }
         __syncwarp();      // every lane is done with this stage before it is refilled
     }
+    SCGR_STAT_FLUSH_WARP(8, batches); SCGR_STAT_FLUSH_WARP(9, scanned); SCGR_STAT_FLUSH_WARP(10, hit);
+    SCGR_STAT_FLUSH_WARP(11, slots); SCGR_STAT_FLUSH_LANES(12, ok); SCGR_STAT_FLUSH_WARP(13, red);
+    SCGR_STAT_FLUSH_LANES(14, atom);
+#ifdef SCGR_STATS
+    if (lane == 0) { atomicAdd(&d_render_stats[15], 1ull); atomicAdd(&d_render_stats[16], (unsigned long long)toDo); }
+#endif
 }
 
 template <int MINB, bool TMA>
@@ -485,21 +558,80 @@ render_backward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __res
                        const float* __restrict__ bg, const int64_t* __restrict__ status, int64_t capacity,
                        const uint32_t* __restrict__ n_contrib, const float* __restrict__ final_T,
                        const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
-                       const float* __restrict__ dL_dalpha, ScreenGrad* __restrict__ screen_grad) {
+                       const float* __restrict__ dL_dalpha, ScreenGrad* __restrict__ screen_grad,
+                       const uint32_t* __restrict__ tile_order) {
     __shared__ __align__(16) float4 s_rec[2][96];        // 2 stages x 32 records x {q0, q1, q2}
     __shared__ uint32_t s_id[2][32];
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ float4 s_g4[TILE_PIX];       // upstream gradients of the region: r, g, b, depth
     if (status[0] > capacity) return;
     int b = blockIdx.x;
+    // work item -> tile through the longest-first permutation built from the forward's per-tile depths
 #define SCGR_ARGS s_rec, s_id, s_bar, s_g4, ranges, point_list, rec, W, H, bg, n_contrib, final_T, dL_dcolor, dL_ddepth, \
                   dL_dalpha, screen_grad
-    if (b < ws.n8) { backward_region<8, TMA>(b, tiles_x, 0, SCGR_ARGS); return; }
+    if (b < ws.n8) { backward_region<8, TMA>((int)tile_order[b], tiles_x, 0, SCGR_ARGS); return; }
     b -= ws.n8;
-    if (b < 2 * ws.n4) { backward_region<4, TMA>(ws.n8 + (b >> 1), tiles_x, (b & 1) << 2, SCGR_ARGS); return; }
+    if (b < 2 * ws.n4) { backward_region<4, TMA>((int)tile_order[ws.n8 + (b >> 1)], tiles_x, (b & 1) << 2, SCGR_ARGS); return; }
     b -= 2 * ws.n4;
-    backward_region<2, TMA>(ws.n8 + ws.n4 + (b >> 2), tiles_x, (b & 3) << 1, SCGR_ARGS);
+    backward_region<2, TMA>((int)tile_order[ws.n8 + ws.n4 + (b >> 2)], tiles_x, (b & 3) << 1, SCGR_ARGS);
 #undef SCGR_ARGS
+}
+
+// Tiles by descending depth of their backward walk (counting sort on 1024 buckets, one CTA): the
+// grid is dispatched in block order, so the long tiles start first and the tail of the launch is
+// made of short ones (longest-processing-time-first).  Order inside a bucket is arbitrary.
+constexpr int ORDER_THREADS = 1024;
+constexpr int ORDER_BINS = 1024;
+__global__ void __launch_bounds__(ORDER_THREADS)
+tile_order_kernel(const uint4* __restrict__ tile_todo, const int n_tiles, uint32_t* __restrict__ tile_order) {
+    __shared__ uint32_t s_bin[ORDER_BINS];
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_max;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    uint32_t mx = 0u;
+    for (int i = t; i < n_tiles; i += ORDER_THREADS) {
+        const uint4 d = tile_todo[i];
+        mx = max(mx, max(max(d.x, d.y), max(d.z, d.w)));
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0) s_warp[w] = mx;
+    s_bin[t] = 0u;
+    __syncthreads();
+    if (w == 0) {
+        const uint32_t m = __reduce_max_sync(0xffffffffu, s_warp[lane]);
+        if (lane == 0) s_max = m;
+    }
+    __syncthreads();
+    int shift = 0;
+    while ((s_max >> shift) >= (uint32_t)ORDER_BINS) shift++;
+    // bucket 0 = deepest
+    auto bucket = [&](const uint4 d) { return (ORDER_BINS - 1) - (int)(max(max(d.x, d.y), max(d.z, d.w)) >> shift); };
+    for (int i = t; i < n_tiles; i += ORDER_THREADS) atomicAdd(&s_bin[bucket(tile_todo[i])], 1u);
+    __syncthreads();
+    // exclusive scan of the 1024 buckets (one per thread)
+    const uint32_t c = s_bin[t];
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t x = s_warp[lane], xi = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, xi, o);
+            if (lane >= o) xi += n;
+        }
+        s_warp[lane] = xi - x;
+    }
+    __syncthreads();
+    s_bin[t] = s_warp[w] + inc - c;
+    __syncthreads();
+    for (int i = t; i < n_tiles; i += ORDER_THREADS) tile_order[atomicAdd(&s_bin[bucket(tile_todo[i])], 1u)] = (uint32_t)i;
 }
 
 int env_int(const char* name, int dflt) {
@@ -532,7 +664,8 @@ void launch_render_forward(const ScgrView& v, const GeometryLayout& G, const Bin
     const WorkSplit ws = make_split(tx * ty, "SCGR_FWD_SPLIT", 10, 5);
     begin_kernel("render_forward", L);
 #define SCGR_FWD(M_, T_) render_forward_kernel<M_, T_><<<ws.items(), 32, 0, L.stream>>>(ws, tx, B.ranges, point_list, G.rec, \
-        v.image_width, v.image_height, v.bg, G.status, capacity, out_color, out_depth, out_alpha, I.n_contrib, I.final_T)
+        v.image_width, v.image_height, v.bg, G.status, capacity, out_color, out_depth, out_alpha, I.n_contrib, I.final_T, \
+        I.tile_todo)
     if (!tma) { if (minb == 20) SCGR_FWD(20, false); else if (minb == 24) SCGR_FWD(24, false); else SCGR_FWD(1, false); }
     else if (minb == 20) SCGR_FWD(20, true); else if (minb == 24) SCGR_FWD(24, true); else SCGR_FWD(1, true);
 #undef SCGR_FWD
@@ -549,10 +682,13 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
     static const int minb = env_int("SCGR_BWD_MINB", 16);
     static const int tma = env_int("SCGR_TMA", 0);
     const WorkSplit ws = make_split(tx * ty, "SCGR_BWD_SPLIT", 0, 0);
+    begin_kernel("tile_order", L);
+    tile_order_kernel<<<1, ORDER_THREADS, 0, L.stream>>>(I.tile_todo, tx * ty, I.tile_order);
+    check_launch("tile_order", L);
     begin_kernel("render_backward", L);
 #define SCGR_BWD(M_, T_) render_backward_kernel<M_, T_><<<ws.items(), 32, 0, L.stream>>>(ws, tx, B.ranges, point_list, \
         G.rec, v.image_width, v.image_height, v.bg, G.status, capacity, I.n_contrib, I.final_T, dL_dcolor, dL_ddepth, \
-        dL_dalpha, G.screen_grad)
+        dL_dalpha, G.screen_grad, I.tile_order)
     if (!tma) { if (minb == 16) SCGR_BWD(16, false); else if (minb == 14) SCGR_BWD(14, false); else SCGR_BWD(1, false); }
     else if (minb == 16) SCGR_BWD(16, true); else if (minb == 14) SCGR_BWD(14, true); else SCGR_BWD(1, true);
 #undef SCGR_BWD
@@ -560,3 +696,15 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
 }
 
 }  // namespace scgr
+
+#ifdef SCGR_STATS
+// tools-only entry point of the -DSCGR_STATS build (not part of include/scgr.h)
+extern "C" int scgr_debug_render_stats(unsigned long long* out32, int reset) {
+    if (cudaMemcpyFromSymbol(out32, scgr::d_render_stats, 32 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+    if (reset) {
+        unsigned long long z[32] = {0};
+        if (cudaMemcpyToSymbol(scgr::d_render_stats, z, sizeof(z)) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+#endif

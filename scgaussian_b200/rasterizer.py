@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from typing import NamedTuple, Optional
 
 import torch
@@ -40,14 +41,20 @@ class GaussianRasterizationSettings(NamedTuple):
 # --------------------------------------------------------------------------------------------
 # scratch / capacity management
 # --------------------------------------------------------------------------------------------
-_BINNING_MODE = os.environ.get("SCGR_BINNING", "sync")   # "sync" | "optimistic"
+# How the forward learns R (the instance count) to size the binning buffer:
+#   "fused"      (default) one scgr_forward() call: the binning buffer is pre-sized from the previous
+#                view's R (+25 %), the library waits for R on a zero-copy pinned word between its two
+#                stages and goes straight on; a view that outgrows the headroom falls back to "sync"
+#   "sync"       the reference's protocol in two calls: blocking read of R, exactly sized buffer
+#   "optimistic" both stages enqueued blind with the pre-sized buffer, one validation sync at the end
+_BINNING_MODE = os.environ.get("SCGR_BINNING", "fused")
 _capacity_hint = {}        # device index -> last num_rendered
-_pinned_status = {}        # device index -> pinned int64[2]
+_pinned_status = {}        # (device index, thread id) -> pinned int64[2]
 launch_counter = 0         # number of libscgr stage calls (bench.py reports kernels from this)
 
 
 def _status_buffer(device: torch.device) -> torch.Tensor:
-    key = device.index if device.index is not None else torch.cuda.current_device()
+    key = (device.index if device.index is not None else torch.cuda.current_device(), threading.get_ident())
     buf = _pinned_status.get(key)
     if buf is None:
         buf = torch.zeros(2, dtype=torch.int64).pin_memory()
@@ -134,8 +141,22 @@ def rasterize_forward_raw(means3D, opacities, sh, colors_precomp, scales, rotati
             launch_counter += 1
             return binning
 
-        hint = _capacity_hint.get(key) if _BINNING_MODE == "optimistic" else None
-        if hint is not None:
+        hint = _capacity_hint.get(key) if _BINNING_MODE in ("optimistic", "fused") else None
+        if hint is not None and _BINNING_MODE == "fused":
+            capacity = max(int(hint * 1.25) + 4096, 4096)
+            binning = _scratch(lib.scgr_binning_bytes(P, W, H, capacity), device)
+            rc = lib.scgr_forward(C.byref(view), C.byref(g), geometry.data_ptr(), radii.data_ptr(),
+                                  binning.data_ptr(), capacity, image.data_ptr(), color.data_ptr(),
+                                  depth.data_ptr(), alpha.data_ptr(), status.data_ptr(), stream)
+            launch_counter += 1
+            if rc == _lib.NEED_CAPACITY:      # this view outgrew the headroom: stage 1 is done, R is known
+                R = int(status[0])
+                capacity = R
+                binning = run_render(capacity)
+            else:
+                check(rc)
+                R = int(status[0])
+        elif hint is not None:
             # both stages back to back, one validation sync at the end (GPU never idles mid-forward)
             capacity = max(int(hint * 1.25) + 4096, 4096)
             check(lib.scgr_forward_geometry(C.byref(view), C.byref(g), geometry.data_ptr(), radii.data_ptr(),

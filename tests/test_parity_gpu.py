@@ -329,6 +329,39 @@ def test_mark_visible(dev):
     assert vis.dtype == torch.bool and torch.equal(vis.cpu(), want)
 
 
+def test_binning_modes_agree(dev, monkeypatch):
+    """The three protocols for learning R (fused single call with a zero-copy host wait, the
+    reference's two-call sync, optimistic) produce bit-identical images and the same R; a fused call
+    whose pre-sized buffer is too small comes back with SCGR_NEED_CAPACITY and is completed."""
+    from scgaussian_b200 import rasterizer as R
+    case = util.make_case(4000, 160, 120, scale_median=0.05)
+    s = settings_for(case, dev)
+    t = {k: case[k].to(dev).contiguous() for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+    args = (t["means3D"], t["opacities"], t["shs"], None, t["scales"], t["rotations"], None, s)
+    monkeypatch.setattr(R, "_BINNING_MODE", "sync")
+    ref = R.rasterize_forward_raw(*args)
+    monkeypatch.setattr(R, "_BINNING_MODE", "fused")
+    R._capacity_hint[dev.index] = 16          # headroom far too small -> SCGR_NEED_CAPACITY -> completed
+    small = R.rasterize_forward_raw(*args)
+    assert small[4].num_rendered == ref[4].num_rendered and small[4].capacity == small[4].num_rendered
+    fused = R.rasterize_forward_raw(*args)    # hint is now right: one call, over-allocated buffer
+    assert fused[4].num_rendered == ref[4].num_rendered and fused[4].capacity > fused[4].num_rendered
+    for out in (small, fused):
+        for a, b in zip(out[:4], ref[:4]):
+            assert torch.equal(a, b)
+    # the backward works off an over-allocated binning buffer too
+    gC, gD, gA = [x.to(dev) for x in O.synth_upstream_grads(case["W"], case["H"])]
+    g_ref = R.rasterize_backward_raw(ref[4], *args[:-1], s, gC, gD, gA)
+    g_fused = R.rasterize_backward_raw(fused[4], *args[:-1], s, gC, gD, gA)
+    for k in g_ref:
+        util.assert_grad_close(k, g_fused[k].cpu().numpy(), g_ref[k].cpu().numpy())
+    # P = 0 through the fused entry point
+    z = torch.zeros(0, 3, device=dev)
+    e = R.rasterize_forward_raw(z, torch.zeros(0, 1, device=dev), torch.zeros(0, 16, 3, device=dev), None, z,
+                                torch.zeros(0, 4, device=dev), None, s)
+    assert e[4].num_rendered == 0 and float(e[0].abs().max()) == 0.0
+
+
 def test_binning_capacity_overflow_is_recovered(dev, monkeypatch):
     from scgaussian_b200 import rasterizer as R
     case = util.make_case(4000, 160, 120, scale_median=0.05)
