@@ -171,40 +171,6 @@ __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// global digit histograms of the 4 byte-digits of the depth keys -> sweep[pass][0..255]
-constexpr int HIST_ITEMS = 8;
-__global__ void __launch_bounds__(256)
-depth_hist_kernel(const uint32_t* __restrict__ keys, int n, uint32_t* __restrict__ sweep, size_t pass_words) {
-    __shared__ uint32_t s_hist[4][RADIX_BINS];
-#pragma unroll
-    for (int p = 0; p < 4; p++) s_hist[p][threadIdx.x] = 0u;
-    __syncthreads();
-    const int base = blockIdx.x * 256 * HIST_ITEMS;
-    uint32_t kk[HIST_ITEMS];
-#pragma unroll
-    for (int it = 0; it < HIST_ITEMS; it++) {
-        const int idx = base + it * 256 + threadIdx.x;
-        kk[it] = idx < n ? keys[idx] : 0u;
-    }
-#pragma unroll
-    for (int it = 0; it < HIST_ITEMS; it++) {
-        const int idx = base + it * 256 + threadIdx.x;
-        if (idx < n) {
-            const uint32_t k = kk[it];
-            atomicAdd(&s_hist[0][k & 255u], 1u);
-            atomicAdd(&s_hist[1][(k >> 8) & 255u], 1u);
-            atomicAdd(&s_hist[2][(k >> 16) & 255u], 1u);
-            atomicAdd(&s_hist[3][k >> 24], 1u);
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int p = 0; p < 4; p++) {
-        const uint32_t c = s_hist[p][threadIdx.x];
-        if (c) atomicAdd(sweep + p * pass_words + threadIdx.x, c);
-    }
-}
-
 // peers of this lane = lanes holding the same (<= 8-bit) digit.  8 independent ballots instead of
 // one MATCH.ANY: VOTE has a short fixed latency and the ballots of all items pipeline.
 __device__ __forceinline__ uint32_t peers_by_ballot(const uint32_t d, const bool valid, const int nbits) {
@@ -432,9 +398,26 @@ struct TilePasses {
     uint32_t mask[MAX_TILE_PASSES];
 };
 
-// One thread per depth-ordered Gaussian expands the survivor bit mask written by preprocess into
-// (tile id, Gaussian id) pairs at its slice [offsets[s-1], offsets[s]) of the instance arrays --
-// consecutive threads own consecutive slices, so a warp's stores fall into a few cache lines.
+// position of the k-th (0-based) set bit of w; k < popc(w)
+__device__ __forceinline__ uint32_t select_bit32(uint32_t w, uint32_t k) {
+    uint32_t pos = 0u;
+    uint32_t c = __popc(w & 0xFFFFu);
+    if (k >= c) { k -= c; pos = 16u; w >>= 16; }
+    c = __popc(w & 0xFFu);
+    if (k >= c) { k -= c; pos += 8u; w >>= 8; }
+    c = __popc(w & 0xFu);
+    if (k >= c) { k -= c; pos += 4u; w >>= 4; }
+    c = __popc(w & 0x3u);
+    if (k >= c) { k -= c; pos += 2u; w >>= 2; }
+    if (k >= (w & 1u)) pos += 1u;
+    return pos;
+}
+
+// A warp owns 32 depth-ordered Gaussians, whose instance slices [offsets[s-1], offsets[s]) are one
+// contiguous run of the output.  The run is produced 32 instances at a time, ONE INSTANCE PER LANE:
+// the lane finds the Gaussian that owns its output position (5-step search over the 32 slice ends),
+// fetches that Gaussian's survivor mask by shuffle and selects the k-th set bit -- so the work is
+// balanced however uneven the rects are, and the (tile id, id) stores are fully coalesced.
 // Rects of more than 64 tiles (no mask) are handled afterwards by the whole warp: the 32 lanes
 // re-run the exact test on 32 tiles at a time and compact the survivors with a ballot.
 template <int PASSES>
@@ -456,7 +439,7 @@ emit_instances_kernel(const uint32_t* __restrict__ order, const uint32_t* __rest
     const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int s = blockIdx.x * EMIT_THREADS + threadIdx.x;
-    uint32_t gid = 0u, end = 0u, begin = 0u, x0 = 0u, y0 = 0u, rw = 0u, rh = 0u;
+    uint32_t gid = 0u, end = 0xFFFFFFFFu, begin = 0u, x0 = 0u, y0 = 0u, rw = 0u, rh = 0u;
     if (s < P) {
         gid = order[s];
         end = offsets[s];
@@ -467,40 +450,57 @@ emit_instances_kernel(const uint32_t* __restrict__ order, const uint32_t* __rest
             rw = (rc.y & 0xffffu) - x0; rh = (rc.y >> 16) - y0;
         }
     }
+    const bool has = s < P && end != begin;
     const bool big = rw * rh > 64u;
     // digit extraction of the partition passes, in registers
     int sh[PASSES];
     uint32_t mk[PASSES];
 #pragma unroll
     for (int p = 0; p < PASSES; p++) { sh[p] = tp.shift[p]; mk[p] = tp.mask[p]; }
-    if (end != begin && !big) {
-        unsigned long long m = tile_mask[gid];
-        uint32_t pos = begin;
-        uint32_t rowbase = y0 * (uint32_t)grid_x + x0;     // tile id of the rect's row start
-        const unsigned long long row_bits = rw >= 64u ? ~0ull : ((1ull << rw) - 1ull);
-        while (m) {
-            unsigned long long row = m & row_bits;
-            while (row) {
-                const uint32_t tx = (uint32_t)__ffsll((long long)row) - 1u;
-                row &= row - 1ull;
-                const uint32_t tile = rowbase + tx;
-                if (pos < end) {      // always true: the mask has exactly end - begin bits
-                    keys[pos] = tile;
-                    vals[pos] = gid;
+    {
+        unsigned long long m = 0ull;
+        if (has && !big) m = tile_mask[gid];
+        const uint32_t mlo = (uint32_t)m, mhi = (uint32_t)(m >> 32);
+        const uint32_t rowbase = y0 * (uint32_t)grid_x + x0;                        // tile id of the rect's origin
+        // rw (7 bits) | ceil(2^16 / rw) (17 bits): ty = (bit * inv) >> 16 is exact for bit < 64
+        const uint32_t geom = rw | ((rw ? (65536u + rw - 1u) / rw : 0u) << 7) | (big ? 0x80000000u : 0u);
+        const uint32_t run_begin = __shfl_sync(0xffffffffu, begin, 0);
+        const uint32_t run_end = __reduce_max_sync(0xffffffffu, s < P ? end : 0u);
+        for (uint32_t base = run_begin; base < run_end; base += 32u) {
+            const uint32_t pos = base + (uint32_t)lane;
+            // owner = number of slices that end at or before pos (ends are non-decreasing; lanes past P hold +inf)
+            int owner = 0;
 #pragma unroll
-                    for (int p = 0; p < PASSES; p++) atomicAdd(&s_hist[p][(tile >> sh[p]) & mk[p]], 1u);
-                }
-                pos++;
+            for (int step = 16; step > 0; step >>= 1) {
+                const uint32_t e = __shfl_sync(0xffffffffu, end, owner + step - 1);
+                if (e <= pos) owner += step;
             }
-            m = rw >= 64u ? 0ull : (m >> rw);
-            rowbase += (uint32_t)grid_x;
+            owner &= 31;                                                               // (lanes past run_end)
+            const uint32_t ob = __shfl_sync(0xffffffffu, begin, owner);
+            const uint32_t olo = __shfl_sync(0xffffffffu, mlo, owner), ohi = __shfl_sync(0xffffffffu, mhi, owner);
+            const uint32_t obase = __shfl_sync(0xffffffffu, rowbase, owner);
+            const uint32_t ogeom = __shfl_sync(0xffffffffu, geom, owner);
+            const uint32_t og = __shfl_sync(0xffffffffu, gid, owner);
+            if (pos < run_end && !(ogeom >> 31)) {
+                uint32_t k = pos - ob;
+                const uint32_t clo = __popc(olo);
+                const bool upper = k >= clo;
+                const uint32_t bit = select_bit32(upper ? ohi : olo, upper ? k - clo : k) + (upper ? 32u : 0u);
+                const uint32_t orw = ogeom & 127u, inv = (ogeom >> 7) & 0x1FFFFu;
+                const uint32_t ty = (bit * inv) >> 16, tx = bit - ty * orw;
+                const uint32_t tile = obase + ty * (uint32_t)grid_x + tx;
+                keys[pos] = tile;
+                vals[pos] = og;
+#pragma unroll
+                for (int p = 0; p < PASSES; p++) atomicAdd(&s_hist[p][(tile >> sh[p]) & mk[p]], 1u);
+            }
         }
     }
     // large rects, warp-cooperatively
-    uint32_t todo = __ballot_sync(0xffffffffu, end != begin && big);
+    uint32_t todo = __ballot_sync(0xffffffffu, has && big);
     if (todo) {
         float4 q0 = make_float4(0.f, 0.f, -1.f, 0.f), q1 = make_float4(-1.f, 0.f, 0.f, 0.f);
-        if (end != begin && big) {
+        if (has && big) {
             const float4* r = reinterpret_cast<const float4*>(rec + gid);
             q0 = __ldg(r);
             q1 = __ldg(r + 1);
@@ -579,17 +579,15 @@ TilePasses plan_tile_passes(uint32_t n_tiles) {
 // backward to find the final point list without any saved host state).
 int tile_partition_final_buffer(uint32_t n_tiles) { return plan_tile_passes(n_tiles).passes & 1; }
 
-// depth order of the Gaussians (ascending depth bits, ties by index; culled ones last), then the
-// inclusive prefix sum of tiles touched in that order and R.
-void launch_depth_order(const GeometryLayout& G, int32_t P, int64_t* status_mapped, const Launch& L) {
+// Depth order of the Gaussians (ascending depth bits, ties by index; near-plane-culled ones last).
+// `L` is the auxiliary stream: key generation + the four radix passes run beside the preprocess.
+void launch_depth_sort(const ScgrView& v, const ScgrGaussians& g, const GeometryLayout& G, const Launch& L) {
+    const int32_t P = g.P;
     if (P <= 0) return;
-    // preprocess already wrote sort_keys[0] (= depth_key) and sort_vals[0] (= 0..P-1)
     const size_t pw = sweep_pass_words(P);
     // one memset clears the onesweep state of the 4 passes and the scan state behind it
     cudaMemsetAsync(G.sweep, 0, (size_t)((char*)G.scan_state - (char*)G.sweep) + scan_state_bytes(P), L.stream);
-    begin_kernel("depth_hist", L);
-    depth_hist_kernel<<<(P + 256 * HIST_ITEMS - 1) / (256 * HIST_ITEMS), 256, 0, L.stream>>>(G.sort_keys[0], P, G.sweep, pw);
-    check_launch("depth_hist", L);
+    launch_depth_keys(v, g, G, L);      // writes sort_keys[0] (= depth_key), sort_vals[0] (= 0..P-1), the 4 histograms
     int cur = 0;
     for (int p = 0; p < 4; p++) {
         launch_onesweep<false>("depth_sort_pass", G.sort_keys[cur], G.sort_vals[cur], G.sort_keys[cur ^ 1],
@@ -597,6 +595,12 @@ void launch_depth_order(const GeometryLayout& G, int32_t P, int64_t* status_mapp
         cur ^= 1;
     }
     // 4 passes -> result is back in buffer 0
+}
+
+// Inclusive prefix sum of tiles touched in depth order, and R.  Needs both the depth order
+// (auxiliary stream) and tiles_touched (preprocess).
+void launch_scan_offsets(const GeometryLayout& G, int32_t P, int64_t* status_mapped, const Launch& L) {
+    if (P <= 0) return;
     const uint32_t* order = G.sort_vals[0];
     const int nblk = (P + SCAN_TILE - 1) / SCAN_TILE;
     begin_kernel("scan_offsets", L);
@@ -605,17 +609,26 @@ void launch_depth_order(const GeometryLayout& G, int32_t P, int64_t* status_mapp
     check_launch("scan_offsets", L);
 }
 
-void launch_emit_and_partition(const ScgrView& v, const GeometryLayout& G, const BinningLayout& B,
-                               int32_t P, int64_t capacity, int* final_buffer, const Launch& L) {
+// State of the tile partition that does not depend on R: empty ranges, zeroed onesweep words.
+// Split off so that scgr_forward() can enqueue it before it waits for R.
+void launch_binning_prologue(const ScgrView& v, const BinningLayout& B, int32_t P, int64_t capacity, const Launch& L) {
     const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
     const uint32_t n_tiles = (uint32_t)gx * gy;
     begin_kernel("init_ranges", L);
     init_ranges_kernel<<<(n_tiles + 255) / 256, 256, 0, L.stream>>>(B.ranges, n_tiles);
     check_launch("init_ranges", L);
+    if (P <= 0) return;
+    const TilePasses tp = plan_tile_passes(n_tiles);
+    cudaMemsetAsync(B.sweep, 0, sweep_pass_words(capacity) * tp.passes * 4, L.stream);
+}
+
+void launch_emit_and_partition(const ScgrView& v, const GeometryLayout& G, const BinningLayout& B,
+                               int32_t P, int64_t capacity, int* final_buffer, const Launch& L) {
+    const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
+    const uint32_t n_tiles = (uint32_t)gx * gy;
     if (P <= 0) { if (final_buffer) *final_buffer = 0; return; }
     const TilePasses tp = plan_tile_passes(n_tiles);
     const size_t pw = sweep_pass_words(capacity);
-    cudaMemsetAsync(B.sweep, 0, pw * tp.passes * 4, L.stream);
     const uint32_t* order = G.sort_vals[0];   // 32-bit sort = 4 passes = even number of flips
     begin_kernel("emit_instances", L);
 #define SCGR_EMIT(N_) emit_instances_kernel<N_><<<(P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, L.stream>>>( \

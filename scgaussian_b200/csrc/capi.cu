@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <mutex>
@@ -95,6 +96,54 @@ static int guarded(F&& f) {
     }
 }
 
+// ---- auxiliary stream: stage 1 forks -- depth keys + depth sort run beside the heavy preprocess
+// kernel and join it before the prefix sum.  One stream and one fork/join event pair per host
+// thread and device (thread-local: concurrent callers never share events), created on first use
+// and kept for the life of the thread. ----
+struct AuxStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static AuxStream& aux_stream() {
+    constexpr int kMaxDevices = 64;
+    static thread_local AuxStream aux[kMaxDevices];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) throw std::runtime_error("scgr: cannot query the current device");
+    AuxStream& a = aux[dev];
+    if (!a.stream) {
+        // highest priority: the sort's few, short CTAs must not queue behind the thousands of preprocess CTAs
+        int least = 0, greatest = 0;
+        if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { (void)cudaGetLastError(); greatest = 0; }
+        if (cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, greatest) != cudaSuccess ||
+            cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) {
+            a = AuxStream{};
+            throw std::runtime_error(std::string("scgr: cannot create the auxiliary stream: ") + cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    return a;
+}
+
+// stage 1 proper (shared by scgr_forward_geometry and scgr_forward): P > 0
+static void enqueue_geometry_stage(const ScgrView* view, const ScgrGaussians* g, const GeometryLayout& G, int32_t* radii,
+                                   int64_t* status_mapped, const Launch& L) {
+    static const bool serial = getenv("SCGR_SERIAL_STAGE1") != nullptr;    // A/B switch: everything on the caller's stream
+    if (serial) {
+        launch_depth_sort(*view, *g, G, L);
+        launch_preprocess_forward(*view, *g, G, radii, L);
+    } else {
+        AuxStream& a = aux_stream();
+        const Launch La{a.stream, L.debug};
+        cudaEventRecord(a.fork, L.stream);                 // inputs are ready at this point of the caller's stream
+        cudaStreamWaitEvent(a.stream, a.fork, 0);
+        launch_depth_sort(*view, *g, G, La);               // aux:  sweep memset, depth keys + histograms, 4 radix passes
+        cudaEventRecord(a.join, a.stream);
+        launch_preprocess_forward(*view, *g, G, radii, L); // main: project, covariance, SH, tile counts
+        cudaStreamWaitEvent(L.stream, a.join, 0);
+    }
+    launch_scan_offsets(G, g->P, status_mapped, L);
+}
+
 static void copy_status(const GeometryLayout& G, int64_t* status_host, cudaStream_t s) {
     if (status_host) cudaMemcpyAsync(status_host, G.status, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s);
 }
@@ -127,8 +176,7 @@ int scgr_forward_geometry(const ScgrView* view, const ScgrGaussians* g, void* ge
             cudaMemsetAsync(G.status, 0, 2 * sizeof(int64_t), L.stream);
         } else {
             require(radii != nullptr, "null radii");
-            launch_preprocess_forward(*view, *g, G, radii, L);
-            launch_depth_order(G, g->P, nullptr, L);
+            enqueue_geometry_stage(view, g, G, radii, nullptr, L);
         }
         copy_status(G, status_host, L.stream);
         check_stage("forward_geometry", L);
@@ -138,11 +186,12 @@ int scgr_forward_geometry(const ScgrView* view, const ScgrGaussians* g, void* ge
 // stage 2 proper (shared by scgr_forward_render and scgr_forward)
 static void enqueue_render_stage(const ScgrView* view, const ScgrGaussians* g, void* geometry_scratch,
                                  void* binning_scratch, int64_t capacity, void* image_scratch, float* out_color,
-                                 float* out_depth, float* out_alpha, const Launch& L) {
+                                 float* out_depth, float* out_alpha, bool prologue_done, const Launch& L) {
     const int W = view->image_width, H = view->image_height;
     const GeometryLayout G = carve_geometry(geometry_scratch, g->P);
     const BinningLayout B = carve_binning(binning_scratch, W, H, capacity);
     const ImageLayout I = carve_image(image_scratch, W, H);
+    if (!prologue_done) launch_binning_prologue(*view, B, g->P, capacity, L);
     if (g->P == 0) {
         // section 8b: P = 0 returns all-zero images (not background-filled)
         const size_t N = (size_t)W * H;
@@ -169,7 +218,7 @@ int scgr_forward_render(const ScgrView* view, const ScgrGaussians* g, void* geom
         require(capacity >= 0 && capacity < (int64_t)0xFFFFFFFFll, "capacity out of range");
         const Launch L{(cudaStream_t)stream, view->debug != 0};
         enqueue_render_stage(view, g, geometry_scratch, binning_scratch, capacity, image_scratch, out_color,
-                             out_depth, out_alpha, L);
+                             out_depth, out_alpha, false, L);
         copy_status(carve_geometry(geometry_scratch, g->P), status_host, L.stream);
         check_stage("forward_render", L);
     });
@@ -211,6 +260,7 @@ int scgr_forward(const ScgrView* view, const ScgrGaussians* g, void* geometry_sc
         const Launch L{(cudaStream_t)stream, view->debug != 0};
         const GeometryLayout G = carve_geometry(geometry_scratch, g->P);
         int64_t R = 0;
+        bool prologue_done = false;
         if (g->P == 0) {
             cudaMemsetAsync(G.status, 0, 2 * sizeof(int64_t), L.stream);
             status_host[0] = 0;
@@ -223,8 +273,12 @@ int scgr_forward(const ScgrView* view, const ScgrGaussians* g, void* geometry_sc
             if (!zero_copy) (void)cudaGetLastError();
             status_host[1] = 0;
             *(volatile int64_t*)status_host = kSentinel;
-            launch_preprocess_forward(*view, *g, G, radii, L);
-            launch_depth_order(G, g->P, zero_copy ? (int64_t*)mapped : nullptr, L);
+            enqueue_geometry_stage(view, g, G, radii, zero_copy ? (int64_t*)mapped : nullptr, L);
+            if (binning_scratch) {   // R-independent part of stage 2: runs while the host waits for R
+                launch_binning_prologue(*view, carve_binning(binning_scratch, view->image_width, view->image_height, capacity),
+                                        g->P, capacity, L);
+                prologue_done = true;
+            }
             if (zero_copy) {
                 R = wait_for_count((volatile int64_t*)status_host, kSentinel, L.stream);
             } else {   // status_host is not device-mapped: the reference's protocol (copy + synchronise)
@@ -240,7 +294,7 @@ int scgr_forward(const ScgrView* view, const ScgrGaussians* g, void* geometry_sc
         }
         require(binning_scratch != nullptr, "null binning scratch");
         enqueue_render_stage(view, g, geometry_scratch, binning_scratch, capacity, image_scratch, out_color, out_depth,
-                             out_alpha, L);
+                             out_alpha, prologue_done, L);
         check_stage("forward", L);
     });
     if (rc == 0 && need_capacity) {

@@ -104,7 +104,7 @@ inline size_t scan_state_bytes(int64_t n) { return ((size_t)(n > 0 ? n : 1) / 40
 
 struct GeometryLayout {
     Record* rec;              // [P]
-    uint32_t* depth_key;      // == sort_keys[0]: float bits of view depth, CULLED_KEY if culled
+    uint32_t* depth_key;      // == sort_keys[0]: float bits of view depth, CULLED_KEY behind the near plane
     uint32_t* tiles_touched;  // [P]
     uint2* rect;              // [P] {minx | miny << 16, maxx | maxy << 16}
     unsigned long long* tile_mask;  // [P] bit (ty * rect_w + tx) = tile of the rect survives culling (rects <= 64 tiles)
@@ -131,7 +131,7 @@ inline GeometryLayout carve_geometry(void* base, int32_t P) {
     L.tile_mask = (unsigned long long*)take(Pa * 8);
     for (int i = 0; i < 2; i++) L.sort_keys[i] = (uint32_t*)take(Pa * 4);
     for (int i = 0; i < 2; i++) L.sort_vals[i] = (uint32_t*)take(Pa * 4);
-    L.depth_key = L.sort_keys[0];   // preprocess writes the sort input in place
+    L.depth_key = L.sort_keys[0];   // the depth-key kernel writes the sort input in place
     L.offsets = (uint32_t*)take(Pa * 4);
     L.sweep = (uint32_t*)take(align_up(sweep_words(Pa, 4) * 4));
     L.scan_state = (unsigned long long*)take(scan_state_bytes(Pa));   // contiguous with sweep (both 256-B multiples)
@@ -202,7 +202,10 @@ void launch_preprocess_backward(const ScgrView& v, const ScgrGaussians& g, const
 void launch_mark_visible(const float* means3D, int32_t P, const float* viewmatrix, uint8_t* present,
                          const Launch& L);
 
-void launch_depth_order(const GeometryLayout& G, int32_t P, int64_t* status_mapped, const Launch& L);
+void launch_depth_keys(const ScgrView& v, const ScgrGaussians& g, const GeometryLayout& G, const Launch& L);
+void launch_depth_sort(const ScgrView& v, const ScgrGaussians& g, const GeometryLayout& G, const Launch& L);
+void launch_scan_offsets(const GeometryLayout& G, int32_t P, int64_t* status_mapped, const Launch& L);
+void launch_binning_prologue(const ScgrView& v, const BinningLayout& B, int32_t P, int64_t capacity, const Launch& L);
 void launch_emit_and_partition(const ScgrView& v, const GeometryLayout& G, const BinningLayout& B,
                                int32_t P, int64_t capacity, int* final_buffer, const Launch& L);
 

@@ -161,6 +161,63 @@ __device__ __forceinline__ float3 load3(const float* p, int i) {
     return make_float3(__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2));
 }
 
+// View-space depth (A.1).  Explicit fused operations: the depth-key kernel and the preprocess
+// kernel -- two kernels on two streams -- must derive bit-identical depths from the same point.
+__device__ __forceinline__ float view_depth(const float3 p, const float v2, const float v6, const float v10,
+                                            const float v14) {
+    return __fmaf_rn(p.x, v2, __fmaf_rn(p.y, v6, __fmaf_rn(p.z, v10, v14)));
+}
+
+// ------------------------------------------------------------------------------------------
+// depth keys (the sort input) + the digit histograms of the four radix passes.  Reads 12 B and
+// writes 8 B per Gaussian; runs on the auxiliary stream together with the depth sort while the
+// main stream does the heavy preprocess.  Only the near-plane cull (A.1) is known here: Gaussians
+// dropped later (degenerate covariance, empty tile rectangle) keep their depth key and simply own
+// zero instances.
+// ------------------------------------------------------------------------------------------
+constexpr int KEY_THREADS = 256;
+constexpr int KEY_ITEMS = 8;
+__global__ void __launch_bounds__(KEY_THREADS)
+depth_key_kernel(const float* __restrict__ means3D, const int P, const float* __restrict__ V,
+                 uint32_t* __restrict__ depth_key, uint32_t* __restrict__ order_init,
+                 uint32_t* __restrict__ sweep, const size_t pass_words) {
+    __shared__ uint32_t s_hist[4][RADIX_BINS];
+#pragma unroll
+    for (int p = 0; p < 4; p++) s_hist[p][threadIdx.x] = 0u;
+    __syncthreads();
+    const float v2 = __ldg(V + 2), v6 = __ldg(V + 6), v10 = __ldg(V + 10), v14 = __ldg(V + 14);
+    const int base = blockIdx.x * KEY_THREADS * KEY_ITEMS;
+    uint32_t kk[KEY_ITEMS];
+#pragma unroll
+    for (int it = 0; it < KEY_ITEMS; it++) {
+        const int i = base + it * KEY_THREADS + threadIdx.x;
+        kk[it] = CULLED_KEY;
+        if (i < P) {
+            const float zv = view_depth(load3(means3D, i), v2, v6, v10, v14);
+            if (zv > NEAR_Z) kk[it] = __float_as_uint(zv);   // zv > 0.2 => bit order == numeric order (A.6)
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < KEY_ITEMS; it++) {
+        const int i = base + it * KEY_THREADS + threadIdx.x;
+        if (i < P) {
+            const uint32_t k = kk[it];
+            depth_key[i] = k;
+            order_init[i] = (uint32_t)i;      // value array of the depth sort
+            atomicAdd(&s_hist[0][k & 255u], 1u);
+            atomicAdd(&s_hist[1][(k >> 8) & 255u], 1u);
+            atomicAdd(&s_hist[2][(k >> 16) & 255u], 1u);
+            atomicAdd(&s_hist[3][k >> 24], 1u);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const uint32_t c = s_hist[p][threadIdx.x];
+        if (c) atomicAdd(sweep + p * pass_words + threadIdx.x, c);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
@@ -168,9 +225,8 @@ __device__ __forceinline__ float3 load3(const float* p, int i) {
 template <bool SH_FAST>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __restrict__ rec,
-                          uint32_t* __restrict__ depth_key, uint32_t* __restrict__ tiles_touched,
+                          uint32_t* __restrict__ tiles_touched,
                           uint2* __restrict__ rect, unsigned long long* __restrict__ tile_mask,
-                          uint32_t* __restrict__ order_init,
                           int32_t* __restrict__ radii) {
     __shared__ float4 s_sh[SH_FAST ? PRE_THREADS * SH_ROW_F4_PAD : 1];
     const int P = g.P;
@@ -190,12 +246,11 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
         __syncthreads();
     }
     if (i >= P) return;
-    order_init[i] = (uint32_t)i;   // value array of the depth sort
 
     Camera cam;
     load_camera(v, cam);
     const float3 p = load3(g.means3D, i);
-    const float zv = p.x * cam.V[2] + p.y * cam.V[6] + p.z * cam.V[10] + cam.V[14];
+    const float zv = view_depth(p, cam.V[2], cam.V[6], cam.V[10], cam.V[14]);
 
     bool alive = zv > NEAR_Z;   // A.1
     if (!alive && v.prefiltered) {
@@ -240,7 +295,6 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
     if (!alive) {
         radii[i] = 0;
         tiles_touched[i] = 0;
-        depth_key[i] = CULLED_KEY;
         rect[i] = make_uint2(0u, 0u);
         tile_mask[i] = 0ull;
         rec[i].q2 = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));   // radius 0 marks "culled" for the backward
@@ -314,7 +368,6 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
             }
     tiles_touched[i] = touched;
     tile_mask[i] = mask;
-    depth_key[i] = __float_as_uint(zv);   // zv > 0.2 => bit order == numeric order (A.6)
     rect[i] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
 }
 
@@ -559,7 +612,7 @@ __global__ void mark_visible_kernel(const float* __restrict__ means3D, int P, co
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     const float3 p = load3(means3D, i);
-    const float zv = p.x * __ldg(V + 2) + p.y * __ldg(V + 6) + p.z * __ldg(V + 10) + __ldg(V + 14);
+    const float zv = view_depth(p, __ldg(V + 2), __ldg(V + 6), __ldg(V + 10), __ldg(V + 14));
     present[i] = zv > NEAR_Z ? 1 : 0;
 }
 
@@ -576,10 +629,19 @@ void launch_preprocess_forward(const ScgrView& v, const ScgrGaussians& g, const 
     const int blocks = (g.P + PRE_THREADS - 1) / PRE_THREADS;
     begin_kernel("preprocess_forward", L);
     if (sh_fast_ok(g, nullptr))
-        preprocess_forward_kernel<true><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.depth_key, G.tiles_touched, G.rect, G.tile_mask, G.sort_vals[0], radii);
+        preprocess_forward_kernel<true><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.tiles_touched, G.rect, G.tile_mask, radii);
     else
-        preprocess_forward_kernel<false><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.depth_key, G.tiles_touched, G.rect, G.tile_mask, G.sort_vals[0], radii);
+        preprocess_forward_kernel<false><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.tiles_touched, G.rect, G.tile_mask, radii);
     check_launch("preprocess_forward", L);
+}
+
+void launch_depth_keys(const ScgrView& v, const ScgrGaussians& g, const GeometryLayout& G, const Launch& L) {
+    if (g.P <= 0) return;
+    const int per_cta = KEY_THREADS * KEY_ITEMS;
+    begin_kernel("depth_keys", L);
+    depth_key_kernel<<<(g.P + per_cta - 1) / per_cta, KEY_THREADS, 0, L.stream>>>(
+        g.means3D, g.P, v.viewmatrix, G.depth_key, G.sort_vals[0], G.sweep, sweep_pass_words(g.P));
+    check_launch("depth_keys", L);
 }
 
 void launch_preprocess_backward(const ScgrView& v, const ScgrGaussians& g, const GeometryLayout& G,

@@ -577,21 +577,40 @@ render_backward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __res
 #undef SCGR_ARGS
 }
 
-// Tiles by descending depth of their backward walk (counting sort on 1024 buckets, one CTA): the
-// grid is dispatched in block order, so the long tiles start first and the tail of the launch is
-// made of short ones (longest-processing-time-first).  Order inside a bucket is arbitrary.
+// Backward prologue, one launch: CTA 0 orders the tiles by descending depth of their backward
+// walk (counting sort on 1024 buckets: the grid is dispatched in block order, so the long tiles
+// start first and the tail of the launch is made of short ones -- longest-processing-time-first;
+// order inside a bucket is arbitrary); all other CTAs zero the per-Gaussian gradient accumulators.
 constexpr int ORDER_THREADS = 1024;
 constexpr int ORDER_BINS = 1024;
+constexpr int ORDER_CACHE = 8192;          // tile depths kept in shared memory (larger images re-read them)
+constexpr int ZERO_F4_PER_CTA = 4096;      // 64 KB of zeros per CTA
 __global__ void __launch_bounds__(ORDER_THREADS)
-tile_order_kernel(const uint4* __restrict__ tile_todo, const int n_tiles, uint32_t* __restrict__ tile_order) {
+backward_prologue_kernel(const uint4* __restrict__ tile_todo, const int n_tiles, uint32_t* __restrict__ tile_order,
+                         float4* __restrict__ zero_dst, const size_t zero_f4) {
+    if (blockIdx.x > 0) {
+        const size_t base = (size_t)(blockIdx.x - 1) * ZERO_F4_PER_CTA;
+#pragma unroll
+        for (int k = 0; k < ZERO_F4_PER_CTA / ORDER_THREADS; k++) {
+            const size_t i = base + (size_t)k * ORDER_THREADS + threadIdx.x;
+            if (i < zero_f4) zero_dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        return;
+    }
     __shared__ uint32_t s_bin[ORDER_BINS];
+    __shared__ uint32_t s_key[ORDER_CACHE];
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_max;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    auto depth_of = [&](const int i) {
+        const uint4 d = tile_todo[i];
+        return max(max(d.x, d.y), max(d.z, d.w));
+    };
     uint32_t mx = 0u;
     for (int i = t; i < n_tiles; i += ORDER_THREADS) {
-        const uint4 d = tile_todo[i];
-        mx = max(mx, max(max(d.x, d.y), max(d.z, d.w)));
+        const uint32_t k = depth_of(i);
+        if (i < ORDER_CACHE) s_key[i] = k;
+        mx = max(mx, k);
     }
     mx = __reduce_max_sync(0xffffffffu, mx);
     if (lane == 0) s_warp[w] = mx;
@@ -605,8 +624,8 @@ tile_order_kernel(const uint4* __restrict__ tile_todo, const int n_tiles, uint32
     int shift = 0;
     while ((s_max >> shift) >= (uint32_t)ORDER_BINS) shift++;
     // bucket 0 = deepest
-    auto bucket = [&](const uint4 d) { return (ORDER_BINS - 1) - (int)(max(max(d.x, d.y), max(d.z, d.w)) >> shift); };
-    for (int i = t; i < n_tiles; i += ORDER_THREADS) atomicAdd(&s_bin[bucket(tile_todo[i])], 1u);
+    auto bucket = [&](const int i) { return (ORDER_BINS - 1) - (int)((i < ORDER_CACHE ? s_key[i] : depth_of(i)) >> shift); };
+    for (int i = t; i < n_tiles; i += ORDER_THREADS) atomicAdd(&s_bin[bucket(i)], 1u);
     __syncthreads();
     // exclusive scan of the 1024 buckets (one per thread)
     const uint32_t c = s_bin[t];
@@ -631,7 +650,7 @@ tile_order_kernel(const uint4* __restrict__ tile_todo, const int n_tiles, uint32
     __syncthreads();
     s_bin[t] = s_warp[w] + inc - c;
     __syncthreads();
-    for (int i = t; i < n_tiles; i += ORDER_THREADS) tile_order[atomicAdd(&s_bin[bucket(tile_todo[i])], 1u)] = (uint32_t)i;
+    for (int i = t; i < n_tiles; i += ORDER_THREADS) tile_order[atomicAdd(&s_bin[bucket(i)], 1u)] = (uint32_t)i;
 }
 
 int env_int(const char* name, int dflt) {
@@ -677,14 +696,21 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
                             const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                             int32_t P, const Launch& L) {
     const int tx = (v.image_width + TILE - 1) / TILE, ty = (v.image_height + TILE - 1) / TILE;
-    cudaMemsetAsync(G.screen_grad, 0, (size_t)(P > 0 ? P : 0) * sizeof(ScreenGrad), L.stream);
-    if (tx == 0 || ty == 0) return;
+    if (tx == 0 || ty == 0) {
+        cudaMemsetAsync(G.screen_grad, 0, (size_t)(P > 0 ? P : 0) * sizeof(ScreenGrad), L.stream);
+        return;
+    }
     static const int minb = env_int("SCGR_BWD_MINB", 16);
     static const int tma = env_int("SCGR_TMA", 0);
     const WorkSplit ws = make_split(tx * ty, "SCGR_BWD_SPLIT", 0, 0);
-    begin_kernel("tile_order", L);
-    tile_order_kernel<<<1, ORDER_THREADS, 0, L.stream>>>(I.tile_todo, tx * ty, I.tile_order);
-    check_launch("tile_order", L);
+    {
+        const size_t zero_f4 = (size_t)(P > 0 ? P : 0) * (sizeof(ScreenGrad) / sizeof(float4));
+        const unsigned zero_ctas = (unsigned)((zero_f4 + ZERO_F4_PER_CTA - 1) / ZERO_F4_PER_CTA);
+        begin_kernel("backward_prologue", L);
+        backward_prologue_kernel<<<1 + zero_ctas, ORDER_THREADS, 0, L.stream>>>(
+            I.tile_todo, tx * ty, I.tile_order, reinterpret_cast<float4*>(G.screen_grad), zero_f4);
+        check_launch("backward_prologue", L);
+    }
     begin_kernel("render_backward", L);
 #define SCGR_BWD(M_, T_) render_backward_kernel<M_, T_><<<ws.items(), 32, 0, L.stream>>>(ws, tx, B.ranges, point_list, \
         G.rec, v.image_width, v.image_height, v.bg, G.status, capacity, I.n_contrib, I.final_T, dL_dcolor, dL_ddepth, \

@@ -116,12 +116,16 @@ def test_forward_stages_match_oracle(dev):
     report("stages", radii_mismatch=n_rad, e_xy=e_xy, e_conic=e_conic, e_rgb=e_rgb, e_depth=e_depth,
            R_gpu=int(state.num_rendered), R_cpu=int(co.num_rendered))
     assert e_xy < 1e-5 and e_conic < 1e-4 and e_rgb < 1e-5 and e_depth < 1e-6
-    # depth order: ascending (depth, id), culled last
+    # depth order: ascending (depth, id); Gaussians behind the near plane (A.1) last.  (Gaussians culled
+    # later -- degenerate covariance, empty tile rectangle -- keep their place and own zero instances.)
     order = dv["depth_order"].astype(np.int64)
     assert np.array_equal(np.sort(order), np.arange(case["P"]))
     dkey = np.where(radii > 0, rec[:, 6], np.inf)[order]
     assert (np.diff(dkey[np.isfinite(dkey)]) >= 0).all()
-    assert np.isfinite(dkey[: int((radii > 0).sum())]).all()
+    zview = (case["means3D"].double() @ case["viewmatrix"].double()[:3, 2] + case["viewmatrix"].double()[3, 2]).numpy()
+    n_front = int((zview > 0.2 + 1e-6).sum())
+    assert (zview[order[:n_front]] > 0.2 - 1e-6).all() and (zview[order[n_front + 8:]] <= 0.2 + 1e-6).all()
+    assert (radii[order[n_front + 8:]] == 0).all()
     # tile lists.  Ours = the reference's per-tile lists (A.6/A.7, the oracle's) MINUS the (Gaussian,
     # tile) pairs in which no pixel can pass the reference's alpha >= 1/255 test: a subsequence, in
     # the same depth order, and every dropped pair is checked to be non-contributing.
