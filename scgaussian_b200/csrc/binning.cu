@@ -521,6 +521,28 @@ emit_instances_kernel(const uint32_t* __restrict__ order, const uint32_t* __rest
             c.my = __shfl_sync(0xffffffffu, mine.my, j); c.thr = __shfl_sync(0xffffffffu, mine.thr, j);
             const uint32_t ntiles = brw * brh;
             uint32_t out = b;
+            const SpanParams sp = make_span(c);      // same decision path as the counting pass (preprocess)
+            if (sp.robust) {
+                // a lane per tile row: closed-form column span, prefix sum over the rows, each lane writes its run
+                for (uint32_t r0 = 0; r0 < brh; r0 += 32) {
+                    const uint32_t r = r0 + lane;
+                    int first = 0, n = 0;
+                    if (r < brh) n = row_span(sp, (int)(by0 + r), (int)bx0, (int)(bx0 + brw), &first);
+                    const uint32_t inc = warp_inclusive_scan((uint32_t)n, lane);
+                    uint32_t pos = out + inc - (uint32_t)n;
+                    for (int t = 0; t < n; t++, pos++) {
+                        if (pos < e) {      // always true: same bit-exact spans as the counting pass
+                            const uint32_t tile = (by0 + r) * (uint32_t)grid_x + (uint32_t)(first + t);
+                            keys[pos] = tile;
+                            vals[pos] = g;
+#pragma unroll
+                            for (int p = 0; p < PASSES; p++) atomicAdd(&s_hist[p][(tile >> sh[p]) & mk[p]], 1u);
+                        }
+                    }
+                    out += __shfl_sync(0xffffffffu, inc, 31);
+                }
+                continue;
+            }
             for (uint32_t k0 = 0; k0 < ntiles; k0 += 32) {
                 const uint32_t k = k0 + lane;
                 bool pass = false;

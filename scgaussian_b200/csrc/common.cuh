@@ -73,6 +73,63 @@ __device__ __forceinline__ CullParams make_cull(const float4 q0, const float4 q1
     c.thr = __fsub_rn(q1.w, CULL_MARGIN);
     return c;
 }
+// ---- the same test for a whole ROW of tiles at once: which tiles of tile row `ty` does the ellipse
+//   { d : p2(d) >= thr }   (the region in which alpha >= 1/255 is possible, with the margin)
+// intersect?  Over the row band dy in [dyl, dyh] the ellipse's extreme dx are reached at the dy of its
+// right-/leftmost point clamped into the band (dx_max(dy) = kx dy + sqrt(E - D dy^2) / (-2 cA) is
+// concave), so one row costs two square roots instead of one rectangle test per tile.
+// D = 4 cA cC - cB^2 suffers cancellation for needle-shaped Gaussians: `robust` is false then and the
+// callers fall back to the per-tile test.  Explicit rounding + one hardware sqrt: the counting pass
+// (preprocess) and the emission pass take bit-identical decisions.
+__device__ __forceinline__ float sqrt_hw(const float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float SPAN_SLACK = 0.01f;      // pixels; on top of CULL_MARGIN
+struct SpanParams {
+    float mx, my, kx, hA, D, E, dyT, dyR;
+    bool any;       // false: no pixel anywhere can reach the threshold
+    bool robust;    // false: use tile_may_contribute() per tile
+};
+__device__ __forceinline__ SpanParams make_span(const CullParams& c) {
+    SpanParams s;
+    s.mx = c.mx; s.my = c.my; s.kx = c.kx;
+    const float ac4 = __fmul_rn(__fmul_rn(4.f, c.cA), c.cC);
+    s.D = __fsub_rn(ac4, __fmul_rn(c.cB, c.cB));
+    s.E = __fmul_rn(__fmul_rn(4.f, c.cA), c.thr);
+    s.hA = __fdiv_rn(-0.5f, c.cA);
+    s.any = c.thr < 0.f;
+    s.robust = s.D > __fmul_rn(1e-3f, ac4) && s.D > 0.f;
+    const float invD = __fdiv_rn(1.f, s.D);
+    s.dyT = __fadd_rn(sqrt_hw(fmaxf(0.f, __fmul_rn(s.E, invD))), SPAN_SLACK);
+    const float dxR = sqrt_hw(fmaxf(0.f, __fmul_rn(__fmul_rn(__fmul_rn(4.f, c.cC), c.thr), invD)));
+    s.dyR = __fmul_rn(c.ky, dxR);
+    return s;
+}
+// tiles [*first, *first + return value) of tile row ty, clipped to the rect columns [x0r, x1r)
+__device__ __forceinline__ int row_span(const SpanParams& s, const int ty, const int x0r, const int x1r, int* first) {
+    const float y0 = (float)(ty * TILE);
+    const float dyl = __fsub_rn(s.my, y0 + (float)(TILE - 1)), dyh = __fsub_rn(s.my, y0);
+    *first = x0r;
+    if (!s.any || dyl > s.dyT || dyh < -s.dyT) return 0;
+    const float d1 = fminf(fmaxf(s.dyR, dyl), dyh);
+    const float d2 = fminf(fmaxf(-s.dyR, dyl), dyh);
+    const float r1 = sqrt_hw(fmaxf(0.f, __fmaf_rn(-s.D, __fmul_rn(d1, d1), s.E)));
+    const float r2 = sqrt_hw(fmaxf(0.f, __fmaf_rn(-s.D, __fmul_rn(d2, d2), s.E)));
+    const float dxmax = __fmaf_rn(s.kx, d1, __fmul_rn(r1, s.hA));
+    const float dxmin = __fmaf_rn(s.kx, d2, -__fmul_rn(r2, s.hA));
+    const float xa = __fsub_rn(__fsub_rn(s.mx, dxmax), SPAN_SLACK);      // leftmost / rightmost pixel abscissa reached
+    const float xb = __fadd_rn(__fsub_rn(s.mx, dxmin), SPAN_SLACK);
+    // tile tx covers pixels [16 tx, 16 tx + 15]
+    const float fa = ceilf(__fmul_rn(__fsub_rn(xa, (float)(TILE - 1)), 1.f / TILE));
+    const float fb = floorf(__fmul_rn(xb, 1.f / TILE));
+    const int a = max(x0r, (int)fmaxf(fa, -1.f));
+    const int b = min(x1r - 1, (int)fminf(fb, 70000.f));
+    *first = a;
+    return max(0, b - a + 1);
+}
+
 // may any pixel of tile (tx, ty) see alpha >= 1/255 from this Gaussian?
 __device__ __forceinline__ bool tile_may_contribute(const CullParams& c, const int tx, const int ty) {
     const float x0 = (float)(tx * TILE), y0 = (float)(ty * TILE);

@@ -356,16 +356,28 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
     // For rects of <= 64 tiles the survivors are also recorded as a bit mask, so that the emission
     // kernel expands bits instead of repeating the test.
     const CullParams cp = make_cull(r.q0, r.q1);
+    const SpanParams sp = make_span(cp);
     uint32_t touched = 0u;
     unsigned long long mask = 0ull;
     const int rw = x1 - x0;
     const bool small_rect = rw * (y1 - y0) <= 64;
-    for (int ty = y0; ty < y1; ty++)
-        for (int tx = x0; tx < x1; tx++)
-            if (tile_may_contribute(cp, tx, ty)) {
-                touched++;
-                if (small_rect) mask |= 1ull << ((ty - y0) * rw + (tx - x0));
-            }
+    if (sp.robust) {
+        // one closed-form column span per tile row (common.cuh)
+        for (int ty = y0; ty < y1; ty++) {
+            int first;
+            const int n = row_span(sp, ty, x0, x1, &first);
+            touched += (uint32_t)n;
+            if (small_rect && n > 0)
+                mask |= (n >= 64 ? ~0ull : ((1ull << n) - 1ull)) << ((ty - y0) * rw + (first - x0));
+        }
+    } else {
+        for (int ty = y0; ty < y1; ty++)
+            for (int tx = x0; tx < x1; tx++)
+                if (tile_may_contribute(cp, tx, ty)) {
+                    touched++;
+                    if (small_rect) mask |= 1ull << ((ty - y0) * rw + (tx - x0));
+                }
+    }
     tiles_touched[i] = touched;
     tile_mask[i] = mask;
     rect[i] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));

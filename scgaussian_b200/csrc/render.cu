@@ -246,24 +246,22 @@ forward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[
             auto blend = [&](const int i) {
                 const float dy = dys[i >> 1];
                 const float power = fmaf(dy, fmaf(q1.x, dy, bx[i & 1]), ax[i & 1]);
-                // straight-line, predicated: the reference's skip chain (A.8) without divergent branches.
+                // The reference's skip chain (A.8), written so that it compiles to predicated instructions
+                // (no divergent branch, no selects: the compare/select pipe is the busy one in this loop).
                 // (alpha >= 1/255 implies power >= pmin2 - margin: the slot bound needs no per-pixel twin.)
                 const float araw = fminf(ALPHA_MAX, q1.y * ex2(power));
-                const bool cand = power <= 0.f && araw >= ALPHA_MIN;
-                const float alpha = cand ? araw : 0.f;
-                const float w0 = alpha * Tt[i];
-                const float test_T = Tt[i] - w0;               // T (1 - alpha); == T if skipped; < 0 if finished
-                // open & (skipped | blended) -> test_T >= T_EPS.  Otherwise the pixel is finished, or saturates
-                // right here (this Gaussian is then NOT blended): keep -|T|.
-                const bool open = test_T >= T_EPS;
-#ifdef SCGR_STATS
-                const bool go = cand && open;
-#endif
-                const float w = open ? w0 : 0.f;
-                Cr[i] = fmaf(q2.x, w, Cr[i]); Cg[i] = fmaf(q2.y, w, Cg[i]); Cb[i] = fmaf(q2.z, w, Cb[i]);
-                Dd[i] = fmaf(q1.z, w, Dd[i]);
-                Tt[i] = open ? test_T : -fabsf(Tt[i]);
-                last[i] = w > 0.f ? idx : last[i];             // w > 0  <=>  cand && open (alpha >= 1/255, T >= 1e-4)
+                const float w0 = araw * Tt[i];
+                const float test_T = Tt[i] - w0;               // T (1 - alpha); negative for a finished pixel
+                const bool cand = araw >= ALPHA_MIN && power <= 0.f;
+                const bool go = cand && test_T >= T_EPS;       // open pixel, blended
+                const bool sat = cand && test_T < T_EPS;       // saturates right here (NOT blended), or was finished
+                if (go) {
+                    Cr[i] = fmaf(q2.x, w0, Cr[i]); Cg[i] = fmaf(q2.y, w0, Cg[i]); Cb[i] = fmaf(q2.z, w0, Cb[i]);
+                    Dd[i] = fmaf(q1.z, w0, Dd[i]);
+                    Tt[i] = test_T;
+                    last[i] = idx;
+                }
+                if (sat) Tt[i] = -fabsf(Tt[i]);                // finished pixels keep -|T|: test_T < 0 from now on
                 SCGR_STAT_ADD(cand, cand ? 1 : 0); SCGR_STAT_ADD(go, go ? 1 : 0);
             };
 #pragma unroll
