@@ -13,6 +13,7 @@
 // for the per-thread 128-bit reads/writes; the backward fuses cov2D-, projection-, depth-, SH-
 // and cov3D-backward in one pass and writes every gradient tensor in full (zeros for culled
 // Gaussians), so the host never memsets them.
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -234,7 +235,9 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
     const bool use_sh = g.shs != nullptr;
 
     if (SH_FAST && use_sh) {
-        // rows [block0, block0 + 128) are one contiguous run of 128*12 float4 in HBM
+        // rows [block0, block0 + 128) are one contiguous run of 128*12 float4 in HBM.  (Fetching only the
+        // rows of Gaussians in front of the near plane was tried: the test needs means3D first, and the
+        // serialised load latencies cost 25 % on an all-visible scene.)
         const int row0 = blockIdx.x * PRE_THREADS;
         const int nrows = min(PRE_THREADS, P - row0);
         const float4* src = reinterpret_cast<const float4*>(g.shs) + (size_t)row0 * SH_ROW_F4;
@@ -386,26 +389,106 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
 // ------------------------------------------------------------------------------------------
 // backward (A.10), fused: conic->cov2D->{Sigma, t}, NDC mean, depth, SH, Sigma->{scale, rot}
 // ------------------------------------------------------------------------------------------
-template <bool SH_FAST>
-__global__ void __launch_bounds__(PRE_THREADS)
+template <bool SH_FAST, int MINB>
+__global__ void __launch_bounds__(PRE_THREADS, MINB)
 preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record* __restrict__ rec,
                            const ScreenGrad* __restrict__ sg, const ScgrGrads out) {
     __shared__ float4 s_sh[SH_FAST ? PRE_THREADS * SH_ROW_F4_PAD : 1];
+    __shared__ float4 s_acc[PRE_THREADS][3];      // screen-space gradient sums of the live Gaussians
+    __shared__ uint32_t s_bits[PRE_THREADS];      // record word {radius | flags << 28} of the live Gaussians
+    __shared__ uint8_t s_live[PRE_THREADS];
+    __shared__ uint8_t s_list[PRE_THREADS];       // local indices of the live Gaussians, compacted
+    __shared__ int s_wcnt[PRE_THREADS / 32];
     const int P = g.P;
-    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int own = blockIdx.x * PRE_THREADS + tid;
     const bool use_sh = g.shs != nullptr;
     const int row0 = blockIdx.x * PRE_THREADS;
     const int nrows = min(PRE_THREADS, P - row0);
 
+    // ---- phase 1: which Gaussians of this block of 128 receive any gradient?  A Gaussian contributes
+    // only if it survived the forward's culling AND render-backward deposited something for it: culled
+    // ones, and the many that sit behind saturated pixels, have an all-zero accumulator -- every output
+    // is then exactly zero and none of their inputs is read.  The live ones are compacted so that the
+    // arithmetic below runs in full warps.
+    bool own_live = false;
+    if (own < P) {
+        const float4 q2 = rec[own].q2;
+        if ((__float_as_uint(q2.w) & 0x0FFFFFFFu) != 0u) {
+            const ScreenGrad A0 = sg[own];
+            own_live = A0.a0.x != 0.f || A0.a0.y != 0.f || A0.a0.z != 0.f || A0.a0.w != 0.f || A0.a1.x != 0.f ||
+                       A0.a1.y != 0.f || A0.a1.z != 0.f || A0.a2.x != 0.f || A0.a2.y != 0.f || A0.a2.z != 0.f;
+            if (own_live) {
+                s_acc[tid][0] = A0.a0; s_acc[tid][1] = A0.a1; s_acc[tid][2] = A0.a2;
+                s_bits[tid] = __float_as_uint(q2.w);
+            }
+        }
+    }
+    s_live[tid] = own_live ? 1 : 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, own_live);
+    if (lane == 0) s_wcnt[wid] = __popc(bal);
+    __syncthreads();
+    int before = 0, n_live = 0;
+#pragma unroll
+    for (int k = 0; k < PRE_THREADS / 32; k++) {
+        if (k < wid) before += s_wcnt[k];
+        n_live += s_wcnt[k];
+    }
+    if (own_live) s_list[before + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)tid;
+    // a Gaussian without gradient: zeros, written by its own thread
+    if (own < P && !own_live) {
+        out.dL_dmeans3D[3 * (size_t)own] = 0.f; out.dL_dmeans3D[3 * (size_t)own + 1] = 0.f; out.dL_dmeans3D[3 * (size_t)own + 2] = 0.f;
+        out.dL_dmeans2D[3 * (size_t)own] = 0.f; out.dL_dmeans2D[3 * (size_t)own + 1] = 0.f; out.dL_dmeans2D[3 * (size_t)own + 2] = 0.f;
+        out.dL_dopacities[own] = 0.f;
+        if (out.dL_dcolors_precomp) {
+            out.dL_dcolors_precomp[3 * (size_t)own] = 0.f; out.dL_dcolors_precomp[3 * (size_t)own + 1] = 0.f; out.dL_dcolors_precomp[3 * (size_t)own + 2] = 0.f;
+        }
+        if (out.dL_dscales) {
+            out.dL_dscales[3 * (size_t)own] = 0.f; out.dL_dscales[3 * (size_t)own + 1] = 0.f; out.dL_dscales[3 * (size_t)own + 2] = 0.f;
+        }
+        if (out.dL_drotations) reinterpret_cast<float4*>(out.dL_drotations)[own] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (out.dL_dcov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) out.dL_dcov3D_precomp[6 * (size_t)own + k] = 0.f;
+        }
+        if (use_sh) {
+            if (SH_FAST) {
+                float4* row = s_sh + tid * SH_ROW_F4_PAD;
+#pragma unroll
+                for (int cc = 0; cc < SH_ROW_F4; cc++) row[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                float* orow = out.dL_dshs + (size_t)own * g.sh_coeffs * 3;
+                for (int k = 0; k < 3 * g.sh_coeffs; k++) orow[k] = 0.f;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: thread t takes the t-th live Gaussian; the SH rows of the live ones are staged ----
+    const bool live = tid < n_live;
+    const int jl = live ? (int)s_list[tid] : 0;      // local index of the Gaussian this thread processes
+    const int i = row0 + jl;
     if (SH_FAST && use_sh) {
         const float4* src = reinterpret_cast<const float4*>(g.shs) + (size_t)row0 * SH_ROW_F4;
         const int nf4 = nrows * SH_ROW_F4;
-        for (int f = threadIdx.x; f < nf4; f += PRE_THREADS) {
+        for (int f = tid; f < nf4; f += PRE_THREADS) {
             const int r = f / SH_ROW_F4, c = f - r * SH_ROW_F4;
-            s_sh[r * SH_ROW_F4_PAD + c] = __ldg(src + f);
+            if (s_live[r]) s_sh[r * SH_ROW_F4_PAD + c] = __ldg(src + f);
         }
-        __syncthreads();
     }
+    // (the per-Gaussian inputs below are fetched while the SH rows are in flight)
+    float3 p_in = make_float3(0.f, 0.f, 0.f), sc_in = make_float3(0.f, 0.f, 0.f);
+    float4 q_in = make_float4(1.f, 0.f, 0.f, 0.f), rq0 = make_float4(0.f, 0.f, 0.f, 0.f), rq1 = rq0;
+    if (live) {
+        p_in = load3(g.means3D, i);
+        rq0 = rec[i].q0;
+        rq1 = rec[i].q1;
+        if (!g.cov3D_precomp) {
+            q_in = __ldg(reinterpret_cast<const float4*>(g.rotations) + i);
+            sc_in = load3(g.scales, i);
+        }
+    }
+    if (SH_FAST && use_sh) __syncthreads();
 
     float dmean[3] = {0.f, 0.f, 0.f};
     float dm2x = 0.f, dm2y = 0.f, dop = 0.f;
@@ -413,21 +496,17 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     float dscale[3] = {0.f, 0.f, 0.f};
     float drot[4] = {0.f, 0.f, 0.f, 0.f};
     float dcol[3] = {0.f, 0.f, 0.f};
-    bool live = false;
-    if (i < P) {
-        live = (__float_as_uint(rec[i].q2.w) & 0x0FFFFFFFu) != 0u;
-    }
     if (live) {
         Camera cam;
         load_camera(v, cam);
-        const uint32_t flags = __float_as_uint(rec[i].q2.w) >> 28;
-        const ScreenGrad A = sg[i];
-        const float3 p = load3(g.means3D, i);
+        const uint32_t flags = s_bits[jl] >> 28;
+        ScreenGrad A;
+        A.a0 = s_acc[jl][0]; A.a1 = s_acc[jl][1]; A.a2 = s_acc[jl][2];
+        const float3 p = p_in;
         const float* V = cam.V;
         const float* PM = cam.PM;
         // render-backward stores raw sums (render.cu): scale them into true derivatives here
         constexpr float LN2 = 0.6931471805599453f;
-        const float4 rq0 = rec[i].q0, rq1 = rec[i].q1;
         const float Sx = A.a0.x, Sy = A.a0.y;            // sum u G dx, sum u G dy
         dm2x = LN2 * (2.f * rq0.z * Sx + rq0.w * Sy) * (0.5f * v.image_width);    // NDC units (A.9)
         dm2y = LN2 * (2.f * rq1.x * Sy + rq0.w * Sx) * (0.5f * v.image_height);
@@ -440,8 +519,8 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
 #pragma unroll
             for (int k = 0; k < 6; k++) c6[k] = __ldg(g.cov3D_precomp + 6 * (size_t)i + k);
         } else {
-            q = __ldg(reinterpret_cast<const float4*>(g.rotations) + i);
-            sc = load3(g.scales, i);
+            q = q_in;
+            sc = sc_in;
             cov3d_from_scale_rot(sc, v.scale_modifier, q, c6);
         }
         Proj pr;
@@ -508,8 +587,8 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
             sh_basis_grad(D, d, bx, by, bz);
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;
             if (SH_FAST) {
-                // in place: this thread's staged input row becomes its gradient row
-                float4* row = s_sh + threadIdx.x * SH_ROW_F4_PAD;
+                // in place: the staged input row of the Gaussian becomes its gradient row
+                float4* row = s_sh + jl * SH_ROW_F4_PAD;
                 const float gch[3] = {gr, gg, gb};
 #pragma unroll
                 for (int cc = 0; cc < SH_ROW_F4; cc++) {
@@ -578,18 +657,9 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
             drot[2] = 2.f * (-2.f * y * Dm[0] + x * Dm[1] + r * Dm[2] + x * Dm[3] + z * Dm[5] - r * Dm[6] + z * Dm[7] - 2.f * y * Dm[8]);
             drot[3] = 2.f * (-2.f * z * Dm[0] - r * Dm[1] + x * Dm[2] + r * Dm[3] - 2.f * z * Dm[4] + y * Dm[5] + x * Dm[6] + y * Dm[7]);
         }
-    } else if (i < P && use_sh) {
-        if (SH_FAST) {
-            float4* row = s_sh + threadIdx.x * SH_ROW_F4_PAD;
-#pragma unroll
-            for (int cc = 0; cc < SH_ROW_F4; cc++) row[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            float* orow = out.dL_dshs + (size_t)i * g.sh_coeffs * 3;
-            for (int k = 0; k < 3 * g.sh_coeffs; k++) orow[k] = 0.f;
-        }
     }
 
-    if (i < P) {
+    if (live) {
         out.dL_dmeans3D[3 * (size_t)i] = dmean[0]; out.dL_dmeans3D[3 * (size_t)i + 1] = dmean[1]; out.dL_dmeans3D[3 * (size_t)i + 2] = dmean[2];
         out.dL_dmeans2D[3 * (size_t)i] = dm2x; out.dL_dmeans2D[3 * (size_t)i + 1] = dm2y; out.dL_dmeans2D[3 * (size_t)i + 2] = 0.f;
         out.dL_dopacities[i] = dop;
@@ -661,10 +731,14 @@ void launch_preprocess_backward(const ScgrView& v, const ScgrGaussians& g, const
     if (g.P <= 0) return;
     const int blocks = (g.P + PRE_THREADS - 1) / PRE_THREADS;
     begin_kernel("preprocess_backward", L);
-    if (sh_fast_ok(g, out.dL_dshs))
-        preprocess_backward_kernel<true><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-    else
-        preprocess_backward_kernel<false><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+    static const int minb = getenv("SCGR_PREB_MINB") ? atoi(getenv("SCGR_PREB_MINB")) : 6;
+    if (sh_fast_ok(g, out.dL_dshs)) {
+        if (minb == 6) preprocess_backward_kernel<true, 6><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (minb == 8) preprocess_backward_kernel<true, 8><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else preprocess_backward_kernel<true, 1><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+    } else {
+        preprocess_backward_kernel<false, 1><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+    }
     check_launch("preprocess_backward", L);
 }
 

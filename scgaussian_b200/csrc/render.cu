@@ -713,7 +713,7 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
 #define SCGR_BWD(M_, T_) render_backward_kernel<M_, T_><<<ws.items(), 32, 0, L.stream>>>(ws, tx, B.ranges, point_list, \
         G.rec, v.image_width, v.image_height, v.bg, G.status, capacity, I.n_contrib, I.final_T, dL_dcolor, dL_ddepth, \
         dL_dalpha, G.screen_grad, I.tile_order)
-    if (!tma) { if (minb == 16) SCGR_BWD(16, false); else if (minb == 14) SCGR_BWD(14, false); else SCGR_BWD(1, false); }
+    if (!tma) { if (minb == 16) SCGR_BWD(16, false); else if (minb == 14) SCGR_BWD(14, false); else if (minb == 20) SCGR_BWD(20, false); else if (minb == 18) SCGR_BWD(18, false); else SCGR_BWD(1, false); }
     else if (minb == 16) SCGR_BWD(16, true); else if (minb == 14) SCGR_BWD(14, true); else SCGR_BWD(1, true);
 #undef SCGR_BWD
     check_launch("render_backward", L);
