@@ -335,7 +335,21 @@ render_forward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __rest
 // 10 per-lane partial sums -> lane (h, b8, b4, b2, 0) ends up holding the full 32-lane sum of ONE
 // of them.  12 shuffles instead of 50.  Returns the value; `*slot` = float offset inside ScreenGrad
 // (or -1 if this lane holds nothing).
-__device__ __forceinline__ float transpose_reduce10(const float v[10], const int lane, int* slot) {
+// ScreenGrad float offset of the value lane `lane` holds after transpose_reduce10 (-1: none); lane-only,
+// computed once per kernel
+__device__ __forceinline__ int reduce10_slot(const int lane) {
+    const bool h = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
+    int idx = -1;
+    if (!(lane & 1)) {
+        if (!b8) idx = b4 ? (b2 ? -1 : 2) : (b2 ? 1 : 0);
+        else idx = b4 ? -1 : (b2 ? 4 : 3);
+        if (idx >= 0 && h) idx += 5;
+    }
+    // value order {mx, my, A, B, C, opacity, depth, r, g, b} -> ScreenGrad float offsets
+    return idx < 0 ? -1 : (idx < 7 ? idx : idx + 1);
+}
+
+__device__ __forceinline__ float transpose_reduce10(const float v[10], const int lane) {
     const bool h = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
     float a[5];
 #pragma unroll
@@ -364,15 +378,6 @@ __device__ __forceinline__ float transpose_reduce10(const float v[10], const int
     const float send = b2 ? c[0] : c[1];
     float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
     d += __shfl_xor_sync(0xffffffffu, d, 1);
-    // which of the 10 values does this lane hold?
-    int idx = -1;
-    if (!(lane & 1)) {
-        if (!b8) idx = b4 ? (b2 ? -1 : 2) : (b2 ? 1 : 0);
-        else idx = b4 ? -1 : (b2 ? 4 : 3);
-        if (idx >= 0 && h) idx += 5;
-    }
-    // value order {mx, my, A, B, C, opacity, depth, r, g, b} -> ScreenGrad float offsets
-    *slot = idx < 0 ? -1 : (idx < 7 ? idx : idx + 1);
     return d;
 }
 
@@ -423,6 +428,8 @@ backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)
     }
     const float pxf = (float)(X0 + lx), pyf = (float)(Yr + ly);
     // (each lane only ever reads back the s_g4 entries it wrote itself: no barrier needed)
+    const int slot = reduce10_slot(lane);                         // which of the 10 sums this lane deposits
+    float* const my_grad = reinterpret_cast<float*>(screen_grad) + (slot >= 0 ? slot : 0);
 
     // batch entry j  <->  0-based list position  pos = toDo - 1 - (base + j)   (back to front)
     // stage b = batch entries [32 b, 32 b + 32) of the back-to-front walk; buffer b & 1
@@ -533,11 +540,10 @@ backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)
             for (int i = 0; i < SPW; i++)
                 if (mj & (1u << i)) pair_grad(i);  // warp-uniform branch
             // (97 % of the pairs that get here have a contributing pixel: reduce unconditionally)
-            int slot;
-            const float sum = transpose_reduce10(v, lane, &slot);
+            const float sum = transpose_reduce10(v, lane);
             SCGR_STAT_ADD(red, 1); SCGR_STAT_ADD(atom, (slot >= 0 && sum != 0.f) ? 1 : 0);
             if (slot >= 0 && sum != 0.f)
-                atomicAdd(reinterpret_cast<float*>(screen_grad + s_id[j]) + slot, sum);   // RED.E.ADD.F32
+                atomicAdd(my_grad + (size_t)s_id[j] * (sizeof(ScreenGrad) / sizeof(float)), sum);   // RED.E.ADD.F32
         }
         __syncwarp();      // every lane is done with this stage before it is refilled
     }
