@@ -168,6 +168,7 @@ def main():
     import torch.distributed as dist
     from scgaussian_b200 import GaussianRasterizationSettings, GaussianRasterizer, _lib
     from scgaussian_b200 import rasterizer as R
+    from scgaussian_b200.losses import photometric_loss
     from scgaussian_b200.parallel import FlatGradBuffer
 
     lib = _lib.load()                      # raises if libscgr.so is missing: no fallback
@@ -293,7 +294,9 @@ def main():
             color, radii, depth, alpha = GaussianRasterizer(s2)(
                 means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"], shs=leaves["shs"],
                 scales=leaves["scales"], rotations=leaves["rotations"])
-            loss = (color - gt_dev[b]).abs().mean() + 0.01 * depth.mean() + 0.01 * alpha.mean()
+            # the reference's training loss (train.py:160-161: L1 + 0.2 D-SSIM, fused: scgaussian_b200/losses.py)
+            # plus terms that send gradient into the depth and alpha outputs (train.py:164-168 use both)
+            loss = photometric_loss(color, gt_dev[b], 0.2) + 0.01 * depth.mean() + 0.01 * alpha.mean()
             loss.backward()
             m2d.grad = None
             if world > 1:
@@ -338,7 +341,7 @@ def main():
             dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
         e2e = {"value": world * 1000.0 * ke / float(ms_e.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4, "steps": ke,
-               "what": "GaussianRasterizer + L1/depth/alpha loss + autograd backward through the public operator; every step uploads "
+               "what": "GaussianRasterizer + the reference's L1 + 0.2 D-SSIM loss (fused) + depth/alpha means + autograd backward through the public operators; every step uploads "
                        "its camera (38 floats, one packed copy) and ground-truth image from pinned host memory and reads its loss "
                        "back; uploads of step k+1 are prefetched on a copy stream while step k runs and the loss of step k is "
                        "read (pinned + event) after step k+1 is enqueued -- all inside the timed region; Gaussian parameters "

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SCGR_VERSION 101   /* major*10000 + minor*100 + patch */
+#define SCGR_VERSION 102   /* major*10000 + minor*100 + patch */
 #define SCGR_TILE 16        /* BLOCK_X = BLOCK_Y of the external rasterizer's config.h */
 
 typedef void* scgr_stream_t;   /* cudaStream_t */
@@ -142,6 +142,24 @@ int scgr_backward(const ScgrView* view, const ScgrGaussians* g, const void* geom
 /* GaussianRasterizer.markVisible: present[i] = view-space z of means3D[i] > 0.2. */
 int scgr_mark_visible(const float* means3D, int32_t P, const float* viewmatrix, uint8_t* present,
                       scgr_stream_t stream);
+
+/* ---- the photometric loss of reference train.py:160-161, fused ----
+ *   Ll1  = l1_loss(image, gt)                                   reference utils/loss_utils.py:40-41
+ *   loss = (1 - lambda_dssim) * Ll1 + lambda_dssim * (1 - ssim(image, gt))
+ *   ssim = reference utils/loss_utils.py:56-94 (window 11, sigma 1.5, zero padding, mean over all elements)
+ * image / gt: [C,H,W] fp32 device (a batch folds into C: the filter is depthwise).
+ * scgr_photometric_forward writes out3 = {Ll1, ssim, loss} (device) and, when want_grad != 0, keeps the
+ * per-pixel SSIM partial derivatives in `scratch` (scgr_photometric_scratch_bytes, 256-byte aligned).
+ * scgr_photometric_backward writes dL_dimage[C,H,W] = upstream * d loss / d image, `upstream` being a
+ * device scalar (NULL = 1): the autograd scalar is consumed without a host synchronisation.
+ * gt receives no gradient (the reference's gt image is data). */
+size_t scgr_photometric_scratch_bytes(int32_t C, int32_t H, int32_t W);
+int scgr_photometric_forward(const float* image, const float* gt, int32_t C, int32_t H, int32_t W,
+                             float lambda_dssim, void* scratch, int32_t want_grad, float* out3,
+                             scgr_stream_t stream);
+int scgr_photometric_backward(const float* image, const float* gt, int32_t C, int32_t H, int32_t W,
+                              float lambda_dssim, const void* scratch, const float* upstream,
+                              float* dL_dimage, scgr_stream_t stream);
 
 /* Launch accounting and per-kernel timing (the reference has no tracing at all, SURVEY.md section 5;
  * bench.py uses this for the live roofline numbers).  scgr_kernel_launch_count(): kernels this

@@ -57,6 +57,11 @@ SYMBOLS = {
     "scgr_backward": (C.c_int, [C.POINTER(ScgrView), C.POINTER(ScgrGaussians), C.c_void_p, C.c_void_p,
                                 C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.POINTER(ScgrGrads), C.c_void_p]),
+    "scgr_photometric_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "scgr_photometric_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                           C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "scgr_photometric_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scgr_mark_visible": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scgr_kernel_launch_count": (C.c_longlong, []),
     "scgr_profile_enable": (C.c_int, [C.c_int]),

@@ -345,6 +345,33 @@ int scgr_mark_visible(const float* means3D, int32_t P, const float* viewmatrix, 
     });
 }
 
+size_t scgr_photometric_scratch_bytes(int32_t C, int32_t H, int32_t W) {
+    if (C <= 0 || H <= 0 || W <= 0) return 256;
+    return photometric_scratch_bytes(C, H, W);
+}
+
+int scgr_photometric_forward(const float* image, const float* gt, int32_t C, int32_t H, int32_t W, float lambda_dssim,
+                             void* scratch, int32_t want_grad, float* out3, scgr_stream_t stream) {
+    return guarded([&] {
+        require(C > 0 && H > 0 && W > 0, "photometric loss: empty image");
+        require((int64_t)C * (((int64_t)H + 15) / 16) < 65536 * 1024ll, "photometric loss: too many planes");
+        require(image && gt && scratch && out3, "photometric loss: null argument");
+        require((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "photometric loss: scratch must be 256-byte aligned");
+        const Launch L{(cudaStream_t)stream, false};
+        launch_photometric_forward(image, gt, C, H, W, lambda_dssim, scratch, want_grad != 0, out3, L);
+    });
+}
+
+int scgr_photometric_backward(const float* image, const float* gt, int32_t C, int32_t H, int32_t W, float lambda_dssim,
+                              const void* scratch, const float* upstream, float* dL_dimage, scgr_stream_t stream) {
+    return guarded([&] {
+        require(C > 0 && H > 0 && W > 0, "photometric loss: empty image");
+        require(image && gt && scratch && dL_dimage, "photometric loss: null argument");
+        const Launch L{(cudaStream_t)stream, false};
+        launch_photometric_backward(image, gt, C, H, W, lambda_dssim, scratch, upstream, dL_dimage, L);
+    });
+}
+
 long long scgr_kernel_launch_count(void) { return g_kernel_launches.load(); }
 
 int scgr_profile_enable(int on) {

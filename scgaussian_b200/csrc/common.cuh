@@ -275,6 +275,13 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
                             int32_t P, const Launch& L);
 int tile_partition_final_buffer(uint32_t n_tiles);
 
+// fused photometric loss (loss.cu)
+size_t photometric_scratch_bytes(int C, int H, int W);
+void launch_photometric_forward(const float* img, const float* gt, int C, int H, int W, float lambda, void* scratch,
+                                bool want_grad, float* out3, const Launch& L);
+void launch_photometric_backward(const float* img, const float* gt, int C, int H, int W, float lambda,
+                                 const void* scratch, const float* upstream, float* dL_dimg, const Launch& L);
+
 // Every kernel launch is bracketed:  begin_kernel(name, L); kernel<<<...>>>(...); check_launch(name, L);
 // begin_kernel records a start event when profiling is on (scgr_profile_enable); check_launch
 // counts the launch, records the stop event, and turns CUDA errors into std::runtime_error

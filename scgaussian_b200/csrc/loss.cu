@@ -1,0 +1,326 @@
+// loss.cu -- fused photometric loss, forward + backward (sm_100a).  SURVEY.md section 8(f), row f1.
+//
+// Replaces what reference train.py:160-161 computes with a dozen torch kernels per direction:
+//     Ll1  = l1_loss(image, gt)                                  reference utils/loss_utils.py:40-41
+//     loss = (1 - lambda) * Ll1 + lambda * (1 - ssim(image, gt)) reference utils/loss_utils.py:56-94
+// ssim(): 11x11 Gaussian window (sigma 1.5, reference :46-54), zero padding 5, depthwise, C1 = 0.01^2,
+// C2 = 0.03^2, mean over every element.  The 2-D window is the outer product of the 1-D one (:52), so
+// the five windowed moments E[x], E[y], E[x^2], E[y^2], E[xy] are computed separably.
+//
+// Forward (one kernel): a CTA owns a 32x32 pixel tile of one channel; both images are staged with a
+// 5-pixel halo in shared memory (42x42), filtered horizontally (5 moments x 42 rows x 32 columns), then
+// vertically; each thread produces 4 adjacent outputs per pass from 14 loaded values (register blocking:
+// shared-memory loads are the bottleneck of a separable 11-tap filter).  The thread evaluates |x - y| and the SSIM value,
+// and -- when a gradient is wanted -- the three partial derivatives of its SSIM value with respect to
+// the windowed moments that depend on x:  dS/dE[x], dS/dE[x^2], dS/dE[xy].  Block-reduced sums go
+// to a partial array; the last CTA to finish adds them up in a fixed order (deterministic) and
+// writes {Ll1, ssim, loss}.
+// Backward (one kernel): dL/dx(q) = (G * dS/dE[x])(q) + 2 x(q) (G * dS/dE[x^2])(q) + y(q) (G * dS/dE[xy])(q)
+// (G symmetric, zero padding = sum over valid pixels), i.e. three more separable filters of the
+// stored derivative maps, plus the L1 term sign(x - y); everything scaled by the weights of the two
+// means and by the upstream scalar read from device memory (no host synchronisation).
+// HBM-bound streaming work on fp32: no tensor cores.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace scgr {
+
+namespace {
+
+constexpr int LT = 32;               // tile edge: a CTA of 256 threads owns 32x32 pixels, 4 per thread
+constexpr int LTHREADS = 256;
+constexpr int LPT = 4;               // outputs per thread along the filtered direction (register blocking)
+constexpr int LHALO = 5;             // window 11
+constexpr int LWIN = 2 * LHALO + 1;
+constexpr int LE = LT + 2 * LHALO;   // 42: staged edge
+constexpr int LSX = 45;              // staged row stride: = 1 mod 4, conflict-free for the 4-column groups
+constexpr int LSH = LT + 1;          // filtered row stride
+constexpr float SSIM_C1 = 0.01f * 0.01f;
+constexpr float SSIM_C2 = 0.03f * 0.03f;
+
+struct Window {
+    float g[LWIN];
+};
+
+// reference utils/loss_utils.py:46-48: exp(-(x - 5)^2 / (2 sigma^2)) as float32, normalised in float32
+Window make_window() {
+    Window w;
+    float sum = 0.f;
+    for (int x = 0; x < LWIN; x++) {
+        w.g[x] = (float)std::exp(-(double)((x - LWIN / 2) * (x - LWIN / 2)) / (2.0 * 1.5 * 1.5));
+        sum += w.g[x];
+    }
+    for (int x = 0; x < LWIN; x++) w.g[x] /= sum;
+    return w;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Shared memory is the scarce resource of a separable 11-tap filter (one LDS per tap and output
+// otherwise): every thread produces LPT = 4 adjacent outputs from 14 loaded inputs, in both passes.
+template <bool WANT_GRAD>
+__global__ void __launch_bounds__(LTHREADS)
+photometric_forward_kernel(const float* __restrict__ img, const float* __restrict__ gt, const int H, const int W,
+                           const Window win, float* __restrict__ d_mu, float* __restrict__ d_e11,
+                           float* __restrict__ d_e12, float2* __restrict__ partial, unsigned int* __restrict__ counter,
+                           const float lambda, const double inv_count, float* __restrict__ out3) {
+    __shared__ float s_x[LE][LSX], s_y[LE][LSX];
+    __shared__ float s_h[4][LE][LSH];       // E[x], E[y], E[x^2 + y^2], E[xy]: SSIM only needs sigma_1^2 + sigma_2^2
+    __shared__ double s_red[2][LTHREADS / 32];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
+    const size_t plane = (size_t)blockIdx.z * H * W;
+    const float* __restrict__ ip = img + plane;
+    const float* __restrict__ gp = gt + plane;
+
+    for (int idx = tid; idx < LE * LE; idx += LTHREADS) {
+        const int r = idx / LE, c = idx - r * LE;
+        const int gy = y0 + r - LHALO, gx = x0 + c - LHALO;
+        float a = 0.f, b = 0.f;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            a = __ldg(ip + (size_t)gy * W + gx);
+            b = __ldg(gp + (size_t)gy * W + gx);
+        }
+        s_x[r][c] = a;
+        s_y[r][c] = b;
+    }
+    __syncthreads();
+    // horizontal: item = (row r, group of 4 columns)
+    for (int idx = tid; idx < LE * (LT / LPT); idx += LTHREADS) {
+        const int r = idx / (LT / LPT), c0 = (idx - r * (LT / LPT)) * LPT;
+        float xa[LWIN + LPT - 1], ya[LWIN + LPT - 1];
+#pragma unroll
+        for (int k = 0; k < LWIN + LPT - 1; k++) { xa[k] = s_x[r][c0 + k]; ya[k] = s_y[r][c0 + k]; }
+#pragma unroll
+        for (int j = 0; j < LPT; j++) {
+            float m1 = 0.f, m2 = 0.f, ess = 0.f, e12 = 0.f;
+#pragma unroll
+            for (int k = 0; k < LWIN; k++) {
+                const float a = xa[j + k], b = ya[j + k], g = win.g[k];
+                const float ga = g * a, gb = g * b;
+                m1 += ga; m2 += gb;
+                ess = fmaf(ga, a, fmaf(gb, b, ess)); e12 = fmaf(ga, b, e12);
+            }
+            s_h[0][r][c0 + j] = m1; s_h[1][r][c0 + j] = m2; s_h[2][r][c0 + j] = ess; s_h[3][r][c0 + j] = e12;
+        }
+    }
+    __syncthreads();
+    // vertical: thread = (column tx, group of 4 rows)
+    const int tx = tid & (LT - 1), r0 = (tid >> 5) * LPT;
+    float acc[4][LPT];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        float col[LWIN + LPT - 1];
+#pragma unroll
+        for (int k = 0; k < LWIN + LPT - 1; k++) col[k] = s_h[m][r0 + k][tx];
+#pragma unroll
+        for (int j = 0; j < LPT; j++) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < LWIN; k++) a = fmaf(win.g[k], col[j + k], a);
+            acc[m][j] = a;
+        }
+    }
+    const int px = x0 + tx;
+    float l1 = 0.f, ss_sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < LPT; j++) {
+        const int py = y0 + r0 + j;
+        if (px < W && py < H) {
+            const float x = s_x[r0 + j + LHALO][tx + LHALO], y = s_y[r0 + j + LHALO][tx + LHALO];
+            l1 += fabsf(x - y);
+            // reference utils/loss_utils.py:76-90
+            const float mu1 = acc[0][j], mu2 = acc[1][j];
+            const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+            const float s12 = acc[3][j] - mu12;
+            const float A1 = 2.f * mu12 + SSIM_C1, A2 = 2.f * s12 + SSIM_C2;
+            const float B1 = mu1_sq + mu2_sq + SSIM_C1, B2 = (acc[2][j] - mu1_sq - mu2_sq) + SSIM_C2;   // sigma_1^2 + sigma_2^2 + C2
+            const float inv = 1.f / (B1 * B2);
+            const float ss = A1 * A2 * inv;
+            ss_sum += ss;
+            if (WANT_GRAD) {
+                // partials of S(mu1, E[x^2], E[xy]) with sigma_1^2 = E[x^2] - mu1^2, sigma_12 = E[xy] - mu1 mu2
+                const size_t o = plane + (size_t)py * W + px;
+                d_mu[o] = 2.f * mu2 * (A2 - A1) * inv - 2.f * mu1 * ss / B1 + 2.f * mu1 * ss / B2;
+                d_e11[o] = -ss / B2;
+                d_e12[o] = 2.f * A1 * inv;
+            }
+        }
+    }
+    // CTA sums -> partial[]; the last CTA to finish adds the partials up in a fixed order (deterministic)
+    const int lane = tid & 31, wid = tid >> 5;
+    double dl1 = warp_sum((double)l1), dss = warp_sum((double)ss_sum);
+    if (lane == 0) { s_red[0][wid] = dl1; s_red[1][wid] = dss; }
+    __syncthreads();
+    const unsigned int n_ctas = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int me = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (tid == 0) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int k = 0; k < LTHREADS / 32; k++) { a += s_red[0][k]; b += s_red[1][k]; }
+        partial[me] = make_float2((float)a, (float)b);
+        __threadfence();
+        s_last = atomicAdd(counter, 1u) == n_ctas - 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    for (unsigned int i = tid; i < n_ctas; i += LTHREADS) {
+        const float2 p = __ldcg(partial + i);
+        a += (double)p.x;
+        b += (double)p.y;
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) { s_red[0][wid] = a; s_red[1][wid] = b; }
+    __syncthreads();
+    if (tid == 0) {
+        double ta = 0.0, tb = 0.0;
+#pragma unroll
+        for (int k = 0; k < LTHREADS / 32; k++) { ta += s_red[0][k]; tb += s_red[1][k]; }
+        const float ll1 = (float)(ta * inv_count), ssim = (float)(tb * inv_count);
+        out3[0] = ll1;
+        out3[1] = ssim;
+        out3[2] = (1.f - lambda) * ll1 + lambda * (1.f - ssim);   // reference train.py:161
+        *counter = 0u;                                              // ready for the next launch
+    }
+}
+
+__global__ void __launch_bounds__(LTHREADS)
+photometric_backward_kernel(const float* __restrict__ img, const float* __restrict__ gt, const int H, const int W,
+                            const Window win, const float* __restrict__ d_mu, const float* __restrict__ d_e11,
+                            const float* __restrict__ d_e12, const float w_l1, const float w_ssim,
+                            const float* __restrict__ upstream, float* __restrict__ dL_dimg) {
+    __shared__ float s_m[3][LE][LSX];
+    __shared__ float s_h[3][LE][LSH];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
+    const size_t plane = (size_t)blockIdx.z * H * W;
+    for (int idx = tid; idx < LE * LE; idx += LTHREADS) {
+        const int r = idx / LE, c = idx - r * LE;
+        const int gy = y0 + r - LHALO, gx = x0 + c - LHALO;
+        float a = 0.f, b = 0.f, d = 0.f;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            const size_t o = plane + (size_t)gy * W + gx;
+            a = __ldg(d_mu + o); b = __ldg(d_e11 + o); d = __ldg(d_e12 + o);
+        }
+        s_m[0][r][c] = a; s_m[1][r][c] = b; s_m[2][r][c] = d;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < LE * (LT / LPT); idx += LTHREADS) {
+        const int r = idx / (LT / LPT), c0 = (idx - r * (LT / LPT)) * LPT;
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            float in[LWIN + LPT - 1];
+#pragma unroll
+            for (int k = 0; k < LWIN + LPT - 1; k++) in[k] = s_m[m][r][c0 + k];
+#pragma unroll
+            for (int j = 0; j < LPT; j++) {
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < LWIN; k++) a = fmaf(win.g[k], in[j + k], a);
+                s_h[m][r][c0 + j] = a;
+            }
+        }
+    }
+    __syncthreads();
+    const int tx = tid & (LT - 1), r0 = (tid >> 5) * LPT;
+    float acc[3][LPT];
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        float col[LWIN + LPT - 1];
+#pragma unroll
+        for (int k = 0; k < LWIN + LPT - 1; k++) col[k] = s_h[m][r0 + k][tx];
+#pragma unroll
+        for (int j = 0; j < LPT; j++) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < LWIN; k++) a = fmaf(win.g[k], col[j + k], a);
+            acc[m][j] = a;
+        }
+    }
+    const int px = x0 + tx;
+    if (px >= W) return;
+    const float up = upstream ? __ldg(upstream) : 1.f;
+#pragma unroll
+    for (int j = 0; j < LPT; j++) {
+        const int py = y0 + r0 + j;
+        if (py >= H) break;
+        const size_t o = plane + (size_t)py * W + px;
+        const float x = __ldg(img + o), y = __ldg(gt + o);
+        const float diff = x - y;
+        const float sgn = (diff > 0.f ? 1.f : 0.f) - (diff < 0.f ? 1.f : 0.f);   // d|u|/du, 0 at 0 (torch.abs)
+        dL_dimg[o] = up * (w_ssim * (acc[0][j] + 2.f * x * acc[1][j] + y * acc[2][j]) + w_l1 * sgn);
+    }
+}
+
+}  // namespace
+
+size_t loss_scratch_bytes(int64_t elems, int64_t ctas) {
+    return align_up((size_t)elems * 4) * 3 + align_up((size_t)ctas * sizeof(float2)) + 256;
+}
+
+struct LossLayout {
+    float *d_mu, *d_e11, *d_e12;
+    float2* partial;
+    unsigned int* counter;
+};
+static LossLayout carve_loss(void* base, int64_t elems, int64_t ctas) {
+    LossLayout L;
+    char* b = (char*)base;
+    size_t o = 0;
+    auto take = [&](size_t n) { char* p = b + o; o += align_up(n); return (void*)p; };
+    L.d_mu = (float*)take((size_t)elems * 4);
+    L.d_e11 = (float*)take((size_t)elems * 4);
+    L.d_e12 = (float*)take((size_t)elems * 4);
+    L.partial = (float2*)take((size_t)ctas * sizeof(float2));
+    L.counter = (unsigned int*)take(256);
+    return L;
+}
+
+static dim3 loss_grid(int C, int H, int W) { return dim3((W + LT - 1) / LT, (H + LT - 1) / LT, C); }
+
+size_t photometric_scratch_bytes(int C, int H, int W) {
+    const dim3 g = loss_grid(C, H, W);
+    return loss_scratch_bytes((int64_t)C * H * W, (int64_t)g.x * g.y * g.z);
+}
+
+void launch_photometric_forward(const float* img, const float* gt, int C, int H, int W, float lambda, void* scratch,
+                                bool want_grad, float* out3, const Launch& L) {
+    static const Window win = make_window();
+    const dim3 g = loss_grid(C, H, W);
+    const LossLayout S = carve_loss(scratch, (int64_t)C * H * W, (int64_t)g.x * g.y * g.z);
+    cudaMemsetAsync(S.counter, 0, sizeof(unsigned int), L.stream);
+    const double inv_count = 1.0 / ((double)C * H * W);
+    begin_kernel("photometric_forward", L);
+    if (want_grad)
+        photometric_forward_kernel<true><<<g, LTHREADS, 0, L.stream>>>(img, gt, H, W, win, S.d_mu, S.d_e11, S.d_e12, S.partial,
+                                                                     S.counter, lambda, inv_count, out3);
+    else
+        photometric_forward_kernel<false><<<g, LTHREADS, 0, L.stream>>>(img, gt, H, W, win, S.d_mu, S.d_e11, S.d_e12, S.partial,
+                                                                      S.counter, lambda, inv_count, out3);
+    check_launch("photometric_forward", L);
+}
+
+void launch_photometric_backward(const float* img, const float* gt, int C, int H, int W, float lambda,
+                                 const void* scratch, const float* upstream, float* dL_dimg, const Launch& L) {
+    static const Window win = make_window();
+    const dim3 g = loss_grid(C, H, W);
+    const LossLayout S = carve_loss(const_cast<void*>(scratch), (int64_t)C * H * W, (int64_t)g.x * g.y * g.z);
+    const float inv_count = (float)(1.0 / ((double)C * H * W));
+    begin_kernel("photometric_backward", L);
+    // loss = (1 - lambda) mean|x - y| + lambda (1 - mean S)
+    photometric_backward_kernel<<<g, LTHREADS, 0, L.stream>>>(img, gt, H, W, win, S.d_mu, S.d_e11, S.d_e12,
+                                                             (1.f - lambda) * inv_count, -lambda * inv_count, upstream, dL_dimg);
+    check_launch("photometric_backward", L);
+}
+
+}  // namespace scgr

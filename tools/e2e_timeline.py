@@ -13,6 +13,7 @@ from torch.profiler import ProfilerActivity, profile  # noqa: E402
 import bench as B  # noqa: E402
 from scgaussian_b200 import GaussianRasterizationSettings, GaussianRasterizer  # noqa: E402
 from scgaussian_b200 import rasterizer as R  # noqa: E402
+from scgaussian_b200.losses import photometric_loss  # noqa: E402
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "e2e"
 dev = torch.device("cuda", 0)
@@ -44,7 +45,7 @@ def e2e_step():
         means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"], shs=leaves["shs"],
         scales=leaves["scales"], rotations=leaves["rotations"])
     torch.cuda.current_stream(dev).wait_stream(copy_stream)
-    loss = (color - gt_dev).abs().mean() + 0.01 * depth.mean() + 0.01 * alpha.mean()
+    loss = photometric_loss(color, gt_dev, 0.2) + 0.01 * depth.mean() + 0.01 * alpha.mean()
     loss.backward()
     m2d.grad = None
     loss_host.copy_(loss.detach().reshape(1), non_blocking=False)
