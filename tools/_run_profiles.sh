@@ -1,0 +1,12 @@
+set -x
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/pytest_gpu.log
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/launches_bench.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:scgr -s 60 -c 15 -o gpurun_out/prof_all -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/prof_all.log 2>&1
+cat gpurun_out/pytest_gpu.log
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_final.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"])
+PY
+ls -la gpurun_out | tail -8
