@@ -20,6 +20,7 @@
 // stored derivative maps, plus the L1 term sign(x - y); everything scaled by the weights of the two
 // means and by the upstream scalar read from device memory (no host synchronisation).
 // HBM-bound streaming work on fp32: no tensor cores.
+#include <climits>
 #include <cmath>
 
 #include "common.cuh"
@@ -36,6 +37,9 @@ constexpr int LWIN = 2 * LHALO + 1;
 constexpr int LE = LT + 2 * LHALO;   // 42: staged edge
 constexpr int LSX = 45;              // staged row stride: = 1 mod 4, conflict-free for the 4-column groups
 constexpr int LSH = LT + 1;          // filtered row stride
+constexpr int LTILES = 2;            // consecutive tiles of a tile row walked by one CTA (register-prefetched)
+constexpr int LNONE = INT_MIN;       // "no image row" marker of the staging offsets
+constexpr int LSTAGE = (LE * LE + LTHREADS - 1) / LTHREADS;   // staged elements per thread
 constexpr float SSIM_C1 = 0.01f * 0.01f;
 constexpr float SSIM_C2 = 0.03f * 0.03f;
 
@@ -64,7 +68,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Shared memory is the scarce resource of a separable 11-tap filter (one LDS per tap and output
 // otherwise): every thread produces LPT = 4 adjacent outputs from 14 loaded inputs, in both passes.
 template <bool WANT_GRAD>
-__global__ void __launch_bounds__(LTHREADS)
+__global__ void __launch_bounds__(LTHREADS, 3)
 photometric_forward_kernel(const float* __restrict__ img, const float* __restrict__ gt, const int H, const int W,
                            const Window win, float* __restrict__ d_mu, float* __restrict__ d_e11,
                            float* __restrict__ d_e12, float2* __restrict__ partial, unsigned int* __restrict__ counter,
@@ -74,23 +78,55 @@ photometric_forward_kernel(const float* __restrict__ img, const float* __restric
     __shared__ double s_red[2][LTHREADS / 32];
     __shared__ bool s_last;
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
+    const int y0 = blockIdx.y * LT;
     const size_t plane = (size_t)blockIdx.z * H * W;
     const float* __restrict__ ip = img + plane;
     const float* __restrict__ gp = gt + plane;
+    const int tiles_x = (W + LT - 1) / LT;
+    const int t_first = blockIdx.x * LTILES, t_end = min(tiles_x, t_first + LTILES);
 
-    for (int idx = tid; idx < LE * LE; idx += LTHREADS) {
+    // A CTA walks LTILES consecutive tiles of a tile row.  The global loads of the NEXT tile are issued
+    // into registers before the current tile is filtered, so their latency hides behind the arithmetic.
+    float pre_a[LSTAGE], pre_b[LSTAGE];
+    // staged element `it` of this thread: its place in the staging arrays and in the image row do not
+    // depend on the tile -- computed once (soff < 0: nothing to stage / row outside the image)
+    int soff[LSTAGE], goff[LSTAGE], scol[LSTAGE];
+#pragma unroll
+    for (int it = 0; it < LSTAGE; it++) {
+        const int idx = tid + it * LTHREADS;
         const int r = idx / LE, c = idx - r * LE;
-        const int gy = y0 + r - LHALO, gx = x0 + c - LHALO;
-        float a = 0.f, b = 0.f;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            a = __ldg(ip + (size_t)gy * W + gx);
-            b = __ldg(gp + (size_t)gy * W + gx);
+        const int gy = y0 + r - LHALO;
+        scol[it] = c - LHALO;
+        soff[it] = idx < LE * LE ? r * LSX + c : -1;
+        goff[it] = (idx < LE * LE && gy >= 0 && gy < H) ? gy * W + c - LHALO : LNONE;   // (may be negative in row 0)
+    }
+    auto fetch = [&](const int t) {
+        const int x0 = t * LT;
+#pragma unroll
+        for (int it = 0; it < LSTAGE; it++) {
+            const int gx = x0 + scol[it];
+            float a = 0.f, b = 0.f;
+            if (goff[it] != LNONE && gx >= 0 && gx < W) {
+                a = __ldg(ip + goff[it] + x0);
+                b = __ldg(gp + goff[it] + x0);
+            }
+            pre_a[it] = a;
+            pre_b[it] = b;
         }
-        s_x[r][c] = a;
-        s_y[r][c] = b;
+    };
+    float l1 = 0.f, ss_sum = 0.f;
+    fetch(t_first);
+    for (int t = t_first; t < t_end; t++) {
+    const int x0 = t * LT;
+#pragma unroll
+    for (int it = 0; it < LSTAGE; it++) {
+        if (soff[it] >= 0) {
+            (&s_x[0][0])[soff[it]] = pre_a[it];
+            (&s_y[0][0])[soff[it]] = pre_b[it];
+        }
     }
     __syncthreads();
+    if (t + 1 < t_end) fetch(t + 1);
     // horizontal: item = (row r, group of 4 columns)
     for (int idx = tid; idx < LE * (LT / LPT); idx += LTHREADS) {
         const int r = idx / (LT / LPT), c0 = (idx - r * (LT / LPT)) * LPT;
@@ -128,7 +164,6 @@ photometric_forward_kernel(const float* __restrict__ img, const float* __restric
         }
     }
     const int px = x0 + tx;
-    float l1 = 0.f, ss_sum = 0.f;
 #pragma unroll
     for (int j = 0; j < LPT; j++) {
         const int py = y0 + r0 + j;
@@ -141,18 +176,21 @@ photometric_forward_kernel(const float* __restrict__ img, const float* __restric
             const float s12 = acc[3][j] - mu12;
             const float A1 = 2.f * mu12 + SSIM_C1, A2 = 2.f * s12 + SSIM_C2;
             const float B1 = mu1_sq + mu2_sq + SSIM_C1, B2 = (acc[2][j] - mu1_sq - mu2_sq) + SSIM_C2;   // sigma_1^2 + sigma_2^2 + C2
-            const float inv = 1.f / (B1 * B2);
+            const float iB1 = __frcp_rn(B1), iB2 = __frcp_rn(B2);   // B1 >= C1, B2 >= C2 up to rounding: well away from 0
+            const float inv = iB1 * iB2;
             const float ss = A1 * A2 * inv;
             ss_sum += ss;
             if (WANT_GRAD) {
                 // partials of S(mu1, E[x^2], E[xy]) with sigma_1^2 = E[x^2] - mu1^2, sigma_12 = E[xy] - mu1 mu2
                 const size_t o = plane + (size_t)py * W + px;
-                d_mu[o] = 2.f * mu2 * (A2 - A1) * inv - 2.f * mu1 * ss / B1 + 2.f * mu1 * ss / B2;
-                d_e11[o] = -ss / B2;
+                d_mu[o] = 2.f * (mu2 * (A2 - A1) * inv + mu1 * ss * (iB2 - iB1));
+                d_e11[o] = -ss * iB2;
                 d_e12[o] = 2.f * A1 * inv;
             }
         }
     }
+    __syncthreads();      // the staged tile is dead: the next iteration overwrites it
+    }   // tiles of this CTA
     // CTA sums -> partial[]; the last CTA to finish adds the partials up in a fixed order (deterministic)
     const int lane = tid & 31, wid = tid >> 5;
     double dl1 = warp_sum((double)l1), dss = warp_sum((double)ss_sum);
@@ -194,7 +232,7 @@ photometric_forward_kernel(const float* __restrict__ img, const float* __restric
     }
 }
 
-__global__ void __launch_bounds__(LTHREADS)
+__global__ void __launch_bounds__(LTHREADS, 3)
 photometric_backward_kernel(const float* __restrict__ img, const float* __restrict__ gt, const int H, const int W,
                             const Window win, const float* __restrict__ d_mu, const float* __restrict__ d_e11,
                             const float* __restrict__ d_e12, const float w_l1, const float w_ssim,
@@ -202,19 +240,50 @@ photometric_backward_kernel(const float* __restrict__ img, const float* __restri
     __shared__ float s_m[3][LE][LSX];
     __shared__ float s_h[3][LE][LSH];
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
+    const int y0 = blockIdx.y * LT;
     const size_t plane = (size_t)blockIdx.z * H * W;
-    for (int idx = tid; idx < LE * LE; idx += LTHREADS) {
+    const int tiles_x = (W + LT - 1) / LT;
+    const int t_first = blockIdx.x * LTILES, t_end = min(tiles_x, t_first + LTILES);
+    const float up = upstream ? __ldg(upstream) : 1.f;
+    float pre[3][LSTAGE];
+    int soff[LSTAGE], goff[LSTAGE], scol[LSTAGE];      // as in the forward: tile-independent staging indices
+#pragma unroll
+    for (int it = 0; it < LSTAGE; it++) {
+        const int idx = tid + it * LTHREADS;
         const int r = idx / LE, c = idx - r * LE;
-        const int gy = y0 + r - LHALO, gx = x0 + c - LHALO;
-        float a = 0.f, b = 0.f, d = 0.f;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            const size_t o = plane + (size_t)gy * W + gx;
-            a = __ldg(d_mu + o); b = __ldg(d_e11 + o); d = __ldg(d_e12 + o);
+        const int gy = y0 + r - LHALO;
+        scol[it] = c - LHALO;
+        soff[it] = idx < LE * LE ? r * LSX + c : -1;
+        goff[it] = (idx < LE * LE && gy >= 0 && gy < H) ? gy * W + c - LHALO : LNONE;   // (may be negative in row 0)
+    }
+    const float* __restrict__ m0 = d_mu + plane;
+    const float* __restrict__ m1 = d_e11 + plane;
+    const float* __restrict__ m2 = d_e12 + plane;
+    auto fetch = [&](const int t) {
+        const int x0 = t * LT;
+#pragma unroll
+        for (int it = 0; it < LSTAGE; it++) {
+            const int gx = x0 + scol[it];
+            float a = 0.f, b = 0.f, d = 0.f;
+            if (goff[it] != LNONE && gx >= 0 && gx < W) {
+                a = __ldg(m0 + goff[it] + x0); b = __ldg(m1 + goff[it] + x0); d = __ldg(m2 + goff[it] + x0);
+            }
+            pre[0][it] = a; pre[1][it] = b; pre[2][it] = d;
         }
-        s_m[0][r][c] = a; s_m[1][r][c] = b; s_m[2][r][c] = d;
+    };
+    fetch(t_first);
+    for (int t = t_first; t < t_end; t++) {
+    const int x0 = t * LT;
+#pragma unroll
+    for (int it = 0; it < LSTAGE; it++) {
+        if (soff[it] >= 0) {
+            (&s_m[0][0][0])[soff[it]] = pre[0][it];
+            (&s_m[1][0][0])[soff[it]] = pre[1][it];
+            (&s_m[2][0][0])[soff[it]] = pre[2][it];
+        }
     }
     __syncthreads();
+    if (t + 1 < t_end) fetch(t + 1);
     for (int idx = tid; idx < LE * (LT / LPT); idx += LTHREADS) {
         const int r = idx / (LT / LPT), c0 = (idx - r * (LT / LPT)) * LPT;
 #pragma unroll
@@ -248,18 +317,19 @@ photometric_backward_kernel(const float* __restrict__ img, const float* __restri
         }
     }
     const int px = x0 + tx;
-    if (px >= W) return;
-    const float up = upstream ? __ldg(upstream) : 1.f;
 #pragma unroll
     for (int j = 0; j < LPT; j++) {
         const int py = y0 + r0 + j;
-        if (py >= H) break;
-        const size_t o = plane + (size_t)py * W + px;
-        const float x = __ldg(img + o), y = __ldg(gt + o);
-        const float diff = x - y;
-        const float sgn = (diff > 0.f ? 1.f : 0.f) - (diff < 0.f ? 1.f : 0.f);   // d|u|/du, 0 at 0 (torch.abs)
-        dL_dimg[o] = up * (w_ssim * (acc[0][j] + 2.f * x * acc[1][j] + y * acc[2][j]) + w_l1 * sgn);
+        if (px < W && py < H) {
+            const size_t o = plane + (size_t)py * W + px;
+            const float x = __ldg(img + o), y = __ldg(gt + o);
+            const float diff = x - y;
+            const float sgn = (diff > 0.f ? 1.f : 0.f) - (diff < 0.f ? 1.f : 0.f);   // d|u|/du, 0 at 0 (torch.abs)
+            dL_dimg[o] = up * (w_ssim * (acc[0][j] + 2.f * x * acc[1][j] + y * acc[2][j]) + w_l1 * sgn);
+        }
     }
+    __syncthreads();      // the staged tile is dead: the next iteration overwrites it
+    }   // tiles of this CTA
 }
 
 }  // namespace
@@ -286,7 +356,10 @@ static LossLayout carve_loss(void* base, int64_t elems, int64_t ctas) {
     return L;
 }
 
-static dim3 loss_grid(int C, int H, int W) { return dim3((W + LT - 1) / LT, (H + LT - 1) / LT, C); }
+static dim3 loss_grid(int C, int H, int W) {
+    const int tiles_x = (W + LT - 1) / LT;
+    return dim3((tiles_x + LTILES - 1) / LTILES, (H + LT - 1) / LT, C);
+}
 
 size_t photometric_scratch_bytes(int C, int H, int W) {
     const dim3 g = loss_grid(C, H, W);
