@@ -123,8 +123,11 @@ int scgr_forward_render(const ScgrView* view, const ScgrGaussians* g, void* geom
  * directly and the host spins on the word instead of synchronising the stream.  `binning_scratch`
  * must have been sized for `capacity` instances by the caller *before* the call (e.g. from the
  * previous view's R plus headroom); it may be NULL with capacity 0.
+ * With a device-mapped status word stage 2 is enqueued before R is known (its kernels read R on the
+ * device and refuse to run past `capacity`), so the GPU does not idle between the stages; the host
+ * wait only decides the return value.
  * Returns 0 when the images were rendered, SCGR_NEED_CAPACITY when stage 1 completed but
- * R = status_host[0] exceeds `capacity`: the geometry scratch is valid, nothing of stage 2 ran; the
+ * R = status_host[0] exceeds `capacity`: the geometry scratch is valid, stage 2 did nothing; the
  * caller allocates >= R and finishes with scgr_forward_render().  Any other value is an error. */
 #define SCGR_NEED_CAPACITY 3
 int scgr_forward(const ScgrView* view, const ScgrGaussians* g, void* geometry_scratch, int32_t* radii,

@@ -380,6 +380,7 @@ void launch_onesweep(const char* name, const uint32_t* kin, const uint32_t* vin,
     switch (variant) {
         case 0: launch_onesweep_variant<256, 16, false, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
         case 1: launch_onesweep_variant<256, 16, true, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
+        case 3: launch_onesweep_variant<512, 8, false, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
         case 4: launch_onesweep_variant<1024, 4, true, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
         default: launch_onesweep_variant<512, 8, true, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
     }

@@ -260,7 +260,7 @@ int scgr_forward(const ScgrView* view, const ScgrGaussians* g, void* geometry_sc
         const Launch L{(cudaStream_t)stream, view->debug != 0};
         const GeometryLayout G = carve_geometry(geometry_scratch, g->P);
         int64_t R = 0;
-        bool prologue_done = false;
+        bool prologue_done = false, stage2_enqueued = false;
         if (g->P == 0) {
             cudaMemsetAsync(G.status, 0, 2 * sizeof(int64_t), L.stream);
             status_host[0] = 0;
@@ -279,6 +279,14 @@ int scgr_forward(const ScgrView* view, const ScgrGaussians* g, void* geometry_sc
                                         g->P, capacity, L);
                 prologue_done = true;
             }
+            if (zero_copy && binning_scratch) {
+                // Stage 2 is enqueued BEFORE R is known: its kernels read R from device memory and do nothing
+                // when it exceeds `capacity`, so the GPU never idles between the stages.  The host then only
+                // waits (briefly: R lands while stage 2 is still running) to tell the caller which case it was.
+                enqueue_render_stage(view, g, geometry_scratch, binning_scratch, capacity, image_scratch, out_color,
+                                     out_depth, out_alpha, prologue_done, L);
+                stage2_enqueued = true;
+            }
             if (zero_copy) {
                 R = wait_for_count((volatile int64_t*)status_host, kSentinel, L.stream);
             } else {   // status_host is not device-mapped: the reference's protocol (copy + synchronise)
@@ -290,11 +298,12 @@ int scgr_forward(const ScgrView* view, const ScgrGaussians* g, void* geometry_sc
         }
         if (g->P != 0 && (binning_scratch == nullptr || R > capacity)) {
             need_capacity = true;     // stage 1 is complete and stays valid: size the buffer, call scgr_forward_render
-            return;
+            return;                   // (an eagerly enqueued stage 2 has refused to run on the device)
         }
         require(binning_scratch != nullptr, "null binning scratch");
-        enqueue_render_stage(view, g, geometry_scratch, binning_scratch, capacity, image_scratch, out_color, out_depth,
-                             out_alpha, prologue_done, L);
+        if (!stage2_enqueued)
+            enqueue_render_stage(view, g, geometry_scratch, binning_scratch, capacity, image_scratch, out_color, out_depth,
+                                 out_alpha, prologue_done, L);
         check_stage("forward", L);
     });
     if (rc == 0 && need_capacity) {

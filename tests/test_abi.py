@@ -79,6 +79,21 @@ def test_argument_errors_come_back_through_the_c_abi():
     assert rc != 0 and b"dL_dshs must match shs" in lib.scgr_last_error()
     # null pointers
     assert lib.scgr_mark_visible(None, 3, None, None, None) != 0
+    # the single-call forward needs its pinned status word; the same input validation applies
+    rc = lib.scgr_forward(C.byref(v), C.byref(g), 256, 256, 256, 16, 256, 256, 256, 256, None, None)
+    assert rc not in (0, _lib.NEED_CAPACITY) and b"pinned host status word" in lib.scgr_last_error()
+    bad = ScgrGaussians(P=4, sh_coeffs=1, means3D=256, opacities=256, shs=256, colors_precomp=256,
+                        scales=256, rotations=256, cov3D_precomp=None)
+    rc = lib.scgr_forward(C.byref(v), C.byref(bad), 256, 256, 256, 16, 256, 256, 256, 256, 256, None)
+    assert rc not in (0, _lib.NEED_CAPACITY) and b"exactly one of shs / colors_precomp" in lib.scgr_last_error()
+    # photometric loss: shapes and pointers are checked before anything is launched
+    assert lib.scgr_photometric_scratch_bytes(3, 1080, 1920) >= 3 * 4 * 3 * 1080 * 1920
+    rc = lib.scgr_photometric_forward(256, 256, 3, 0, 16, 0.2, 256, 1, 256, None)
+    assert rc != 0 and b"empty image" in lib.scgr_last_error()
+    rc = lib.scgr_photometric_forward(256, None, 3, 16, 16, 0.2, 256, 1, 256, None)
+    assert rc != 0 and b"null argument" in lib.scgr_last_error()
+    rc = lib.scgr_photometric_backward(256, 256, 3, 16, 16, 0.2, None, None, 256, None)
+    assert rc != 0 and b"null argument" in lib.scgr_last_error()
 
 
 def test_host_api_mirrors_reference_operator_surface():
