@@ -296,7 +296,7 @@ def main():
                 scales=leaves["scales"], rotations=leaves["rotations"])
             # the reference's training loss (train.py:160-161: L1 + 0.2 D-SSIM, fused: scgaussian_b200/losses.py)
             # plus terms that send gradient into the depth and alpha outputs (train.py:164-168 use both)
-            loss = photometric_loss(color, gt_dev[b], 0.2) + 0.01 * depth.mean() + 0.01 * alpha.mean()
+            loss = photometric_loss(color, gt_dev[b], 0.2) + (depth.sum() + alpha.sum()) * (0.01 / (HEIGHT * WIDTH))
             loss.backward()
             m2d.grad = None
             if world > 1:

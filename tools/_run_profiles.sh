@@ -2,7 +2,7 @@ set -x
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/pytest_gpu.log
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/launches_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:scgr -s 60 -c 15 -o gpurun_out/prof_all -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/prof_all.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"^(backward_prologue|depth_key|emit_instances|init_ranges|onesweep_pass|preprocess_|render_|scan_offsets)" -s 60 -c 15 -o gpurun_out/prof_all -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/prof_all.log 2>&1
 cat gpurun_out/pytest_gpu.log
 python - <<PY
 import json

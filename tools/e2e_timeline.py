@@ -45,7 +45,7 @@ def e2e_step():
         means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"], shs=leaves["shs"],
         scales=leaves["scales"], rotations=leaves["rotations"])
     torch.cuda.current_stream(dev).wait_stream(copy_stream)
-    loss = photometric_loss(color, gt_dev, 0.2) + 0.01 * depth.mean() + 0.01 * alpha.mean()
+    loss = photometric_loss(color, gt_dev, 0.2) + (depth.sum() + alpha.sum()) * (0.01 / (H * W))
     loss.backward()
     m2d.grad = None
     loss_host.copy_(loss.detach().reshape(1), non_blocking=False)
