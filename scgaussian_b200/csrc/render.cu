@@ -664,8 +664,18 @@ int env_int(const char* name, int dflt) {
 
 // tiles rendered whole / in halves / in quarters: SCGR_SPLIT="h,q" = percent of the tiles (by index,
 // from the end) cut in halves and in quarters
+// Small images do not have enough tiles to fill 148 SMs with one warp each (504x378, the reference's
+// own LLFF resolution, has 768): below ~16 warps per SM every tile is cut in halves, below ~8 in quarters,
+// trading per-(tile, Gaussian) overhead for parallelism in what is then a latency-bound launch.
 WorkSplit make_split(const int n_tiles, const char* env, const int dflt_half, const int dflt_quarter) {
     int ph = dflt_half, pq = dflt_quarter;
+    static const int sm_count = [] {
+        int dev = 0, n = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n > 0 ? n : 148;
+    }();
+    if (n_tiles < 8 * sm_count) { ph = 0; pq = 100; }
+    else if (n_tiles < 16 * sm_count) { ph = 100; pq = 0; }
     if (const char* e = getenv(env)) sscanf(e, "%d,%d", &ph, &pq);
     WorkSplit ws;
     ws.n2 = (int)((int64_t)n_tiles * pq / 100);

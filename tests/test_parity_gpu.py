@@ -477,3 +477,42 @@ def test_config3_full_view_against_cpu_oracle(dev, config3):
             for k in ("means3D", "means2D", "opacities", "shs", "scales", "rotations")}
     report("config3_oracle", radii_mismatch=n_rad, color=ec, depth=ed, alpha=ea, grads=errs,
            R_gpu=int(state.num_rendered), R_cpu=int(co.num_rendered))
+
+
+def test_config4_resolution_properties(dev):
+    """BASELINE config 4's image size (3840x2160: 32 400 tiles, 15-bit tile ids, the backward's tile
+    order beyond its shared-memory cache) with 1.5M Gaussians: the size-independent properties."""
+    from scgaussian_b200 import rasterizer as R
+    case = util.make_case(1_500_000, 3840, 2160, sh_degree=3, scale_median=0.005)
+    s = settings_for(case, dev)
+    t = {k: case[k].to(dev).contiguous() for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+    args = (t["means3D"], t["opacities"], t["shs"], None, t["scales"], t["rotations"], None)
+    color, radii, depth, alpha, state = R.rasterize_forward_raw(*args, s)
+    dv = R.debug_views(state, case["P"], s)
+    Rn = state.num_rendered
+    ranges = dv["ranges"].cpu().numpy().astype(np.int64)
+    assert len(ranges) == 240 * 135
+    ne = ranges[:, 1] > ranges[:, 0]
+    starts, ends = ranges[ne, 0], ranges[ne, 1]
+    assert starts[0] == 0 and ends[-1] == Rn and np.array_equal(starts[1:], ends[:-1])
+    assert int(dv["tiles_touched"].sum()) == Rn
+    pl = dv["point_list"].to(dev).long()
+    depth_of = dv["record"][:, 6].to(dev)[pl]
+    tile_of = torch.repeat_interleave(torch.arange(len(ranges), device=dev),
+                                      torch.from_numpy(ranges[:, 1] - ranges[:, 0]).to(dev))
+    assert bool(((depth_of[1:] >= depth_of[:-1]) | (tile_of[1:] != tile_of[:-1])).all())
+    fT = dv["final_T"].to(dev)
+    assert float((alpha[0] - (1 - fT)).abs().max()) < 2e-5
+    assert torch.equal(R.rasterize_forward_raw(*args, s)[0], color)
+    # backward: finite, linear in the upstream gradients, zero for culled Gaussians
+    W, H = case["W"], case["H"]
+    g1 = [g.to(dev) for g in O.synth_upstream_grads(W, H, seed=1)]
+    g2 = [g.to(dev) for g in O.synth_upstream_grads(W, H, seed=2)]
+    b1 = R.rasterize_backward_raw(state, *args, s, *g1)
+    b2 = R.rasterize_backward_raw(state, *args, s, *g2)
+    b12 = R.rasterize_backward_raw(state, *args, s, *[a + b for a, b in zip(g1, g2)])
+    for k in b1:
+        assert bool(torch.isfinite(b1[k]).all()), k
+        num = float((b12[k] - (b1[k] + b2[k])).abs().max())
+        assert num / (float(b12[k].abs().max()) + 1e-30) < 1e-4, k
+    report("config4_resolution", R=Rn, visible=int((radii > 0).sum()))
