@@ -1,3 +1,4 @@
+# GPU box: parity tests + default bench + serial-stage-1 A/B (run as: gpurun -- bash tools/gpu_check.sh)
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/pytest_gpu.log
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_c.json 2> gpurun_out/bench_c.err
 python - <<PY

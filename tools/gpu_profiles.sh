@@ -1,3 +1,4 @@
+# GPU box: tests, default bench, ncu launch list and ncu --set full capture of one step -> gpurun_out/ (then: python tools/summarize_ncu.py r01)
 set -x
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/pytest_gpu.log
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
@@ -10,3 +11,4 @@ d=json.loads(open("gpurun_out/bench_final.json").read().strip().splitlines()[-1]
 print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"])
 PY
 ls -la gpurun_out | tail -8
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
