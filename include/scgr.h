@@ -14,13 +14,16 @@
  * gradients and the three scratch buffers (geometry / binning / image -- the counterparts of the
  * reference extension's geomBuffer / binningBuffer / imgBuffer), whose sizes it queries with
  * scgr_*_bytes().  The library keeps no global mutable state besides a thread-local error string,
- * a launch counter and the (off by default) profiling log.
+ * the thread-local auxiliary streams, a launch counter and the (off by default) profiling log.
  *
- * Streams: every entry point only enqueues work on `stream` and returns; nothing blocks the host
- * (the reference extension blocks once per forward on a D2H copy of num_rendered).  The number of
- * (Gaussian, tile) instances R is produced on the device; scgr_forward_geometry() also copies it
- * asynchronously to `num_rendered_host` (pinned host memory) so that the caller can size the
- * binning buffer.  scgr_forward_render() takes the *capacity* of the binning buffer; when R >
+ * Streams: every entry point enqueues its work on `stream` and returns; only scgr_forward() waits
+ * on the host, once, for the instance count (the reference extension blocks at the same point of
+ * every forward on a D2H copy of num_rendered).  Stage 1 additionally uses a library-owned,
+ * highest-priority auxiliary stream (one per host thread and device) for the depth sort; it is
+ * forked from and joined back into `stream` with events, so callers see plain stream semantics.
+ * The number of (Gaussian, tile) instances R is produced on the device; scgr_forward_geometry()
+ * also copies it asynchronously to status_host (pinned host memory) so that the caller can size
+ * the binning buffer.  scgr_forward_render() takes the *capacity* of the binning buffer; when R >
  * capacity it renders nothing and raises the overflow flag readable at status_host[1] after the
  * stream has been synchronised -- the caller then grows the buffer and calls it again.
  *

@@ -31,7 +31,7 @@ def _oracle_all(img, gt, dtype):
     g_loss, = torch.autograd.grad(loss, x, retain_graph=True)
     g_ssim, = torch.autograd.grad(s, x, retain_graph=True)
     g_l1, = torch.autograd.grad(ll1, x)
-    return float(ll1), float(s), float(loss), g_loss.numpy(), g_ssim.numpy(), g_l1.numpy()
+    return float(ll1.detach()), float(s.detach()), float(loss.detach()), g_loss.numpy(), g_ssim.numpy(), g_l1.numpy()
 
 
 @pytest.mark.parametrize("name", ["a", "b", "c"])
@@ -86,7 +86,8 @@ def _fused_all(img, gt, dev, lam=0.2):
     g_loss, = torch.autograd.grad(loss, x)
     g_ssim, = torch.autograd.grad(s, x)
     g_l1, = torch.autograd.grad(ll1, x)
-    return float(ll1), float(s), float(loss), g_loss.cpu().numpy(), g_ssim.cpu().numpy(), g_l1.cpu().numpy()
+    return (float(ll1.detach()), float(s.detach()), float(loss.detach()), g_loss.cpu().numpy(), g_ssim.cpu().numpy(),
+            g_l1.cpu().numpy())
 
 
 @pytest.mark.gpu
