@@ -737,7 +737,7 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
         G.rec, v.image_width, v.image_height, v.bg, G.status, capacity, I.n_contrib, I.final_T, dL_dcolor, dL_ddepth, \
         dL_dalpha, G.screen_grad, I.tile_order)
     if (!tma) { if (minb == 16) SCGR_BWD(16, false); else if (minb == 14) SCGR_BWD(14, false); else if (minb == 20) SCGR_BWD(20, false); else if (minb == 18) SCGR_BWD(18, false); else SCGR_BWD(1, false); }
-    else if (minb == 16) SCGR_BWD(16, true); else if (minb == 14) SCGR_BWD(14, true); else if (minb == 20) SCGR_BWD(20, true); else if (minb == 18) SCGR_BWD(18, true); else SCGR_BWD(1, true);
+    else if (minb == 16) SCGR_BWD(16, true); else if (minb == 14) SCGR_BWD(14, true); else if (minb == 20) SCGR_BWD(20, true); else if (minb == 18) SCGR_BWD(18, true); else if (minb == 19) SCGR_BWD(19, true); else if (minb == 17) SCGR_BWD(17, true); else SCGR_BWD(1, true);
 #undef SCGR_BWD
     check_launch("render_backward", L);
 }
