@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscgr.so")
+# SCGR_LIB selects another build of the same library (compile-time A/B variants, tools/ab.py)
+LIB_PATH = os.environ.get("SCGR_LIB") or os.path.join(_HERE, "libscgr.so")
 
 
 class ScgrView(C.Structure):

@@ -24,6 +24,10 @@ namespace scgr {
 namespace {
 
 constexpr int PRE_THREADS = 128;
+#ifndef SCGR_PREB_THREADS
+#define SCGR_PREB_THREADS 128
+#endif
+constexpr int PREB_THREADS = SCGR_PREB_THREADS;   // backward block size (Gaussians per CTA)
 constexpr int SH_ROW_F4 = 12;       // 48 floats = 12 float4 per Gaussian at M = 16
 constexpr int SH_ROW_F4_PAD = 13;   // padded row stride (float4 units): conflict-free LDS.128/STS.128
 
@@ -390,21 +394,21 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
 // backward (A.10), fused: conic->cov2D->{Sigma, t}, NDC mean, depth, SH, Sigma->{scale, rot}
 // ------------------------------------------------------------------------------------------
 template <bool SH_FAST, int MINB>
-__global__ void __launch_bounds__(PRE_THREADS, MINB)
+__global__ void __launch_bounds__(PREB_THREADS, MINB * (128 / PREB_THREADS))
 preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record* __restrict__ rec,
                            const ScreenGrad* __restrict__ sg, const ScgrGrads out) {
-    __shared__ float4 s_sh[SH_FAST ? PRE_THREADS * SH_ROW_F4_PAD : 1];
-    __shared__ float4 s_acc[PRE_THREADS][3];      // screen-space gradient sums of the live Gaussians
-    __shared__ uint32_t s_bits[PRE_THREADS];      // record word {radius | flags << 28} of the live Gaussians
-    __shared__ uint8_t s_live[PRE_THREADS];
-    __shared__ uint8_t s_list[PRE_THREADS];       // local indices of the live Gaussians, compacted
-    __shared__ int s_wcnt[PRE_THREADS / 32];
+    __shared__ float4 s_sh[SH_FAST ? PREB_THREADS * SH_ROW_F4_PAD : 1];
+    __shared__ float4 s_acc[PREB_THREADS][3];      // screen-space gradient sums of the live Gaussians
+    __shared__ uint32_t s_bits[PREB_THREADS];      // record word {radius | flags << 28} of the live Gaussians
+    __shared__ uint8_t s_live[PREB_THREADS];
+    __shared__ uint8_t s_list[PREB_THREADS];       // local indices of the live Gaussians, compacted
+    __shared__ int s_wcnt[PREB_THREADS / 32];
     const int P = g.P;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int own = blockIdx.x * PRE_THREADS + tid;
+    const int own = blockIdx.x * PREB_THREADS + tid;
     const bool use_sh = g.shs != nullptr;
-    const int row0 = blockIdx.x * PRE_THREADS;
-    const int nrows = min(PRE_THREADS, P - row0);
+    const int row0 = blockIdx.x * PREB_THREADS;
+    const int nrows = min(PREB_THREADS, P - row0);
 
     // ---- phase 1: which Gaussians of this block of 128 receive any gradient?  A Gaussian contributes
     // only if it survived the forward's culling AND render-backward deposited something for it: culled
@@ -430,7 +434,7 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     __syncthreads();
     int before = 0, n_live = 0;
 #pragma unroll
-    for (int k = 0; k < PRE_THREADS / 32; k++) {
+    for (int k = 0; k < PREB_THREADS / 32; k++) {
         if (k < wid) before += s_wcnt[k];
         n_live += s_wcnt[k];
     }
@@ -471,7 +475,7 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     if (SH_FAST && use_sh) {
         const float4* src = reinterpret_cast<const float4*>(g.shs) + (size_t)row0 * SH_ROW_F4;
         const int nf4 = nrows * SH_ROW_F4;
-        for (int f = tid; f < nf4; f += PRE_THREADS) {
+        for (int f = tid; f < nf4; f += PREB_THREADS) {
             const int r = f / SH_ROW_F4, c = f - r * SH_ROW_F4;
             if (s_live[r]) s_sh[r * SH_ROW_F4_PAD + c] = __ldg(src + f);
         }
@@ -682,7 +686,7 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
         __syncthreads();
         float4* dst = reinterpret_cast<float4*>(out.dL_dshs) + (size_t)row0 * SH_ROW_F4;
         const int nf4 = nrows * SH_ROW_F4;
-        for (int f = threadIdx.x; f < nf4; f += PRE_THREADS) {
+        for (int f = threadIdx.x; f < nf4; f += PREB_THREADS) {
             const int r = f / SH_ROW_F4, c = f - r * SH_ROW_F4;
             dst[f] = s_sh[r * SH_ROW_F4_PAD + c];
         }
@@ -729,15 +733,15 @@ void launch_depth_keys(const ScgrView& v, const ScgrGaussians& g, const Geometry
 void launch_preprocess_backward(const ScgrView& v, const ScgrGaussians& g, const GeometryLayout& G,
                                 const ScgrGrads& out, const Launch& L) {
     if (g.P <= 0) return;
-    const int blocks = (g.P + PRE_THREADS - 1) / PRE_THREADS;
+    const int blocks = (g.P + PREB_THREADS - 1) / PREB_THREADS;
     begin_kernel("preprocess_backward", L);
     static const int minb = getenv("SCGR_PREB_MINB") ? atoi(getenv("SCGR_PREB_MINB")) : 6;
     if (sh_fast_ok(g, out.dL_dshs)) {
-        if (minb == 6) preprocess_backward_kernel<true, 6><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (minb == 8) preprocess_backward_kernel<true, 8><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else preprocess_backward_kernel<true, 1><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        if (minb == 6) preprocess_backward_kernel<true, 6><<<blocks, PREB_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (minb == 8) preprocess_backward_kernel<true, 8><<<blocks, PREB_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else preprocess_backward_kernel<true, 1><<<blocks, PREB_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     } else {
-        preprocess_backward_kernel<false, 1><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        preprocess_backward_kernel<false, 1><<<blocks, PREB_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     }
     check_launch("preprocess_backward", L);
 }
