@@ -25,9 +25,15 @@ namespace {
 
 constexpr int PRE_THREADS = 128;
 #ifndef SCGR_PREB_THREADS
-#define SCGR_PREB_THREADS 128
+#define SCGR_PREB_THREADS 64
 #endif
-constexpr int PREB_THREADS = SCGR_PREB_THREADS;   // backward block size (Gaussians per CTA)
+#ifndef SCGR_PREB_GAUSS
+#define SCGR_PREB_GAUSS 128
+#endif
+constexpr int PB_G = SCGR_PREB_GAUSS;      // backward: Gaussians classified per CTA
+constexpr int PB_T = SCGR_PREB_THREADS;    // backward: threads per CTA = live Gaussians processed per round
+constexpr int PB_K = PB_G / PB_T;
+static_assert(PB_G % PB_T == 0 && PB_T % 32 == 0 && PB_G <= 256, "backward block shape");
 constexpr int SH_ROW_F4 = 12;       // 48 floats = 12 float4 per Gaussian at M = 16
 constexpr int SH_ROW_F4_PAD = 13;   // padded row stride (float4 units): conflict-free LDS.128/STS.128
 
@@ -394,90 +400,106 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
 // backward (A.10), fused: conic->cov2D->{Sigma, t}, NDC mean, depth, SH, Sigma->{scale, rot}
 // ------------------------------------------------------------------------------------------
 template <bool SH_FAST, int MINB>
-__global__ void __launch_bounds__(PREB_THREADS, MINB * (128 / PREB_THREADS))
+__global__ void __launch_bounds__(PB_T, MINB)
 preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record* __restrict__ rec,
                            const ScreenGrad* __restrict__ sg, const ScgrGrads out) {
-    __shared__ float4 s_sh[SH_FAST ? PREB_THREADS * SH_ROW_F4_PAD : 1];
-    __shared__ float4 s_acc[PREB_THREADS][3];      // screen-space gradient sums of the live Gaussians
-    __shared__ uint32_t s_bits[PREB_THREADS];      // record word {radius | flags << 28} of the live Gaussians
-    __shared__ uint8_t s_live[PREB_THREADS];
-    __shared__ uint8_t s_list[PREB_THREADS];       // local indices of the live Gaussians, compacted
-    __shared__ int s_wcnt[PREB_THREADS / 32];
+    __shared__ float4 s_sh[SH_FAST ? PB_T * SH_ROW_F4_PAD : 1];   // SH rows (then gradient rows) of one round, compact
+    __shared__ float4 s_acc[PB_G][3];             // screen-space gradient sums of the live Gaussians
+    __shared__ uint32_t s_bits[PB_G];             // record word {radius | flags << 28} of the live Gaussians
+    __shared__ uint8_t s_live[PB_G];
+    __shared__ uint8_t s_list[PB_G];              // local indices of the live Gaussians, compacted
+    __shared__ int s_wcnt[PB_K][PB_T / 32];
     const int P = g.P;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int own = blockIdx.x * PREB_THREADS + tid;
     const bool use_sh = g.shs != nullptr;
-    const int row0 = blockIdx.x * PREB_THREADS;
-    const int nrows = min(PREB_THREADS, P - row0);
+    const int row0 = blockIdx.x * PB_G;
+    const int nrows = min(PB_G, P - row0);
 
-    // ---- phase 1: which Gaussians of this block of 128 receive any gradient?  A Gaussian contributes
+    // ---- phase 1: which Gaussians of this block of PB_G receive any gradient?  A Gaussian contributes
     // only if it survived the forward's culling AND render-backward deposited something for it: culled
     // ones, and the many that sit behind saturated pixels, have an all-zero accumulator -- every output
-    // is then exactly zero and none of their inputs is read.  The live ones are compacted so that the
-    // arithmetic below runs in full warps.
-    bool own_live = false;
-    if (own < P) {
-        const float4 q2 = rec[own].q2;
-        if ((__float_as_uint(q2.w) & 0x0FFFFFFFu) != 0u) {
-            const ScreenGrad A0 = sg[own];
-            own_live = A0.a0.x != 0.f || A0.a0.y != 0.f || A0.a0.z != 0.f || A0.a0.w != 0.f || A0.a1.x != 0.f ||
-                       A0.a1.y != 0.f || A0.a1.z != 0.f || A0.a2.x != 0.f || A0.a2.y != 0.f || A0.a2.z != 0.f;
-            if (own_live) {
-                s_acc[tid][0] = A0.a0; s_acc[tid][1] = A0.a1; s_acc[tid][2] = A0.a2;
-                s_bits[tid] = __float_as_uint(q2.w);
+    // is then exactly zero and none of their inputs is read.  Each of the PB_T threads classifies PB_K
+    // Gaussians; the live ones are compacted and processed PB_T at a time, so that the arithmetic runs
+    // in full warps and a CTA's registers and staging buffer are sized for the live fraction.
+    uint32_t bal[PB_K];
+    bool own_live[PB_K];
+#pragma unroll
+    for (int k = 0; k < PB_K; k++) {
+        const int local = k * PB_T + tid, own = row0 + local;
+        own_live[k] = false;
+        if (own < P) {
+            const float4 q2 = rec[own].q2;
+            if ((__float_as_uint(q2.w) & 0x0FFFFFFFu) != 0u) {
+                const ScreenGrad A0 = sg[own];
+                own_live[k] = A0.a0.x != 0.f || A0.a0.y != 0.f || A0.a0.z != 0.f || A0.a0.w != 0.f || A0.a1.x != 0.f ||
+                              A0.a1.y != 0.f || A0.a1.z != 0.f || A0.a2.x != 0.f || A0.a2.y != 0.f || A0.a2.z != 0.f;
+                if (own_live[k]) {
+                    s_acc[local][0] = A0.a0; s_acc[local][1] = A0.a1; s_acc[local][2] = A0.a2;
+                    s_bits[local] = __float_as_uint(q2.w);
+                }
             }
         }
+        s_live[local] = own_live[k] ? 1 : 0;
+        bal[k] = __ballot_sync(0xffffffffu, own_live[k]);
+        if (lane == 0) s_wcnt[k][wid] = __popc(bal[k]);
     }
-    s_live[tid] = own_live ? 1 : 0;
-    const uint32_t bal = __ballot_sync(0xffffffffu, own_live);
-    if (lane == 0) s_wcnt[wid] = __popc(bal);
     __syncthreads();
-    int before = 0, n_live = 0;
+    int n_live = 0;
 #pragma unroll
-    for (int k = 0; k < PREB_THREADS / 32; k++) {
-        if (k < wid) before += s_wcnt[k];
-        n_live += s_wcnt[k];
+    for (int k = 0; k < PB_K; k++) {
+        int before = n_live;
+#pragma unroll
+        for (int w = 0; w < PB_T / 32; w++) {
+            if (w < wid) before += s_wcnt[k][w];
+            n_live += s_wcnt[k][w];
+        }
+        if (own_live[k]) s_list[before + __popc(bal[k] & ((1u << lane) - 1u))] = (uint8_t)(k * PB_T + tid);
     }
-    if (own_live) s_list[before + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)tid;
-    // a Gaussian without gradient: zeros, written by its own thread
-    if (own < P && !own_live) {
-        out.dL_dmeans3D[3 * (size_t)own] = 0.f; out.dL_dmeans3D[3 * (size_t)own + 1] = 0.f; out.dL_dmeans3D[3 * (size_t)own + 2] = 0.f;
-        out.dL_dmeans2D[3 * (size_t)own] = 0.f; out.dL_dmeans2D[3 * (size_t)own + 1] = 0.f; out.dL_dmeans2D[3 * (size_t)own + 2] = 0.f;
-        out.dL_dopacities[own] = 0.f;
-        if (out.dL_dcolors_precomp) {
-            out.dL_dcolors_precomp[3 * (size_t)own] = 0.f; out.dL_dcolors_precomp[3 * (size_t)own + 1] = 0.f; out.dL_dcolors_precomp[3 * (size_t)own + 2] = 0.f;
-        }
-        if (out.dL_dscales) {
-            out.dL_dscales[3 * (size_t)own] = 0.f; out.dL_dscales[3 * (size_t)own + 1] = 0.f; out.dL_dscales[3 * (size_t)own + 2] = 0.f;
-        }
-        if (out.dL_drotations) reinterpret_cast<float4*>(out.dL_drotations)[own] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (out.dL_dcov3D_precomp) {
+    // Gaussians without gradient: zeros.  The small tensors by the classifying thread, the 192-byte
+    // dL/dSH rows by the whole CTA (coalesced).
 #pragma unroll
-            for (int k = 0; k < 6; k++) out.dL_dcov3D_precomp[6 * (size_t)own + k] = 0.f;
-        }
-        if (use_sh) {
-            if (SH_FAST) {
-                float4* row = s_sh + tid * SH_ROW_F4_PAD;
+    for (int k = 0; k < PB_K; k++) {
+        const int own = row0 + k * PB_T + tid;
+        if (own < P && !own_live[k]) {
+            out.dL_dmeans3D[3 * (size_t)own] = 0.f; out.dL_dmeans3D[3 * (size_t)own + 1] = 0.f; out.dL_dmeans3D[3 * (size_t)own + 2] = 0.f;
+            out.dL_dmeans2D[3 * (size_t)own] = 0.f; out.dL_dmeans2D[3 * (size_t)own + 1] = 0.f; out.dL_dmeans2D[3 * (size_t)own + 2] = 0.f;
+            out.dL_dopacities[own] = 0.f;
+            if (out.dL_dcolors_precomp) {
+                out.dL_dcolors_precomp[3 * (size_t)own] = 0.f; out.dL_dcolors_precomp[3 * (size_t)own + 1] = 0.f; out.dL_dcolors_precomp[3 * (size_t)own + 2] = 0.f;
+            }
+            if (out.dL_dscales) {
+                out.dL_dscales[3 * (size_t)own] = 0.f; out.dL_dscales[3 * (size_t)own + 1] = 0.f; out.dL_dscales[3 * (size_t)own + 2] = 0.f;
+            }
+            if (out.dL_drotations) reinterpret_cast<float4*>(out.dL_drotations)[own] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (out.dL_dcov3D_precomp) {
 #pragma unroll
-                for (int cc = 0; cc < SH_ROW_F4; cc++) row[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
+                for (int c = 0; c < 6; c++) out.dL_dcov3D_precomp[6 * (size_t)own + c] = 0.f;
+            }
+            if (use_sh && !SH_FAST) {
                 float* orow = out.dL_dshs + (size_t)own * g.sh_coeffs * 3;
-                for (int k = 0; k < 3 * g.sh_coeffs; k++) orow[k] = 0.f;
+                for (int c = 0; c < 3 * g.sh_coeffs; c++) orow[c] = 0.f;
             }
         }
+    }
+    if (SH_FAST && use_sh) {
+        float4* dst = reinterpret_cast<float4*>(out.dL_dshs) + (size_t)row0 * SH_ROW_F4;
+        const int nf4 = nrows * SH_ROW_F4;
+        for (int f = tid; f < nf4; f += PB_T)
+            if (!s_live[f / SH_ROW_F4]) dst[f] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
 
-    // ---- phase 2: thread t takes the t-th live Gaussian; the SH rows of the live ones are staged ----
-    const bool live = tid < n_live;
-    const int jl = live ? (int)s_list[tid] : 0;      // local index of the Gaussian this thread processes
+    // ---- phase 2..4, PB_T live Gaussians per round: thread t takes the t-th of the round ----
+    for (int first = 0; first < n_live; first += PB_T) {
+    const int in_round = min(PB_T, n_live - first);
+    const bool live = tid < in_round;
+    const int jl = live ? (int)s_list[first + tid] : 0;      // local index of the Gaussian this thread processes
     const int i = row0 + jl;
     if (SH_FAST && use_sh) {
         const float4* src = reinterpret_cast<const float4*>(g.shs) + (size_t)row0 * SH_ROW_F4;
-        const int nf4 = nrows * SH_ROW_F4;
-        for (int f = tid; f < nf4; f += PREB_THREADS) {
+        for (int f = tid; f < in_round * SH_ROW_F4; f += PB_T) {
             const int r = f / SH_ROW_F4, c = f - r * SH_ROW_F4;
-            if (s_live[r]) s_sh[r * SH_ROW_F4_PAD + c] = __ldg(src + f);
+            s_sh[r * SH_ROW_F4_PAD + c] = __ldg(src + (int)s_list[first + r] * SH_ROW_F4 + c);
         }
     }
     // (the per-Gaussian inputs below are fetched while the SH rows are in flight)
@@ -592,7 +614,7 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;
             if (SH_FAST) {
                 // in place: the staged input row of the Gaussian becomes its gradient row
-                float4* row = s_sh + jl * SH_ROW_F4_PAD;
+                float4* row = s_sh + tid * SH_ROW_F4_PAD;
                 const float gch[3] = {gr, gg, gb};
 #pragma unroll
                 for (int cc = 0; cc < SH_ROW_F4; cc++) {
@@ -681,16 +703,17 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
         }
     }
     if (SH_FAST && use_sh) {
-        // the 192-byte gradient rows sit in smem (written in place above): stream them out
-        // fully coalesced
+        // the 192-byte gradient rows of the round sit in smem (written in place above): stream them out,
+        // 12 consecutive 128-bit stores per row
         __syncthreads();
         float4* dst = reinterpret_cast<float4*>(out.dL_dshs) + (size_t)row0 * SH_ROW_F4;
-        const int nf4 = nrows * SH_ROW_F4;
-        for (int f = threadIdx.x; f < nf4; f += PREB_THREADS) {
+        for (int f = tid; f < in_round * SH_ROW_F4; f += PB_T) {
             const int r = f / SH_ROW_F4, c = f - r * SH_ROW_F4;
-            dst[f] = s_sh[r * SH_ROW_F4_PAD + c];
+            dst[(int)s_list[first + r] * SH_ROW_F4 + c] = s_sh[r * SH_ROW_F4_PAD + c];
         }
+        __syncthreads();      // the staging buffer is reused by the next round
     }
+    }   // rounds
 }
 
 __global__ void mark_visible_kernel(const float* __restrict__ means3D, int P, const float* __restrict__ V,
@@ -733,15 +756,15 @@ void launch_depth_keys(const ScgrView& v, const ScgrGaussians& g, const Geometry
 void launch_preprocess_backward(const ScgrView& v, const ScgrGaussians& g, const GeometryLayout& G,
                                 const ScgrGrads& out, const Launch& L) {
     if (g.P <= 0) return;
-    const int blocks = (g.P + PREB_THREADS - 1) / PREB_THREADS;
+    const int blocks = (g.P + PB_G - 1) / PB_G;
     begin_kernel("preprocess_backward", L);
-    static const int minb = getenv("SCGR_PREB_MINB") ? atoi(getenv("SCGR_PREB_MINB")) : 6;
+    static const int minb = getenv("SCGR_PREB_MINB") ? atoi(getenv("SCGR_PREB_MINB")) : 1;
     if (sh_fast_ok(g, out.dL_dshs)) {
-        if (minb == 6) preprocess_backward_kernel<true, 6><<<blocks, PREB_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (minb == 8) preprocess_backward_kernel<true, 8><<<blocks, PREB_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else preprocess_backward_kernel<true, 1><<<blocks, PREB_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        if (minb == 12) preprocess_backward_kernel<true, 12><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (minb == 10) preprocess_backward_kernel<true, 10><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else preprocess_backward_kernel<true, 1><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     } else {
-        preprocess_backward_kernel<false, 1><<<blocks, PREB_THREADS, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        preprocess_backward_kernel<false, 1><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     }
     check_launch("preprocess_backward", L);
 }
