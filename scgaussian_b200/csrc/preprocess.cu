@@ -405,7 +405,6 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
                            const ScreenGrad* __restrict__ sg, const ScgrGrads out) {
     __shared__ float4 s_sh[SH_FAST ? PB_T * SH_ROW_F4_PAD : 1];   // SH rows (then gradient rows) of one round, compact
     __shared__ float4 s_acc[PB_G][3];             // screen-space gradient sums of the live Gaussians
-    __shared__ uint32_t s_bits[PB_G];             // record word {radius | flags << 28} of the live Gaussians
     __shared__ uint8_t s_live[PB_G];
     __shared__ uint8_t s_list[PB_G];              // local indices of the live Gaussians, compacted
     __shared__ int s_wcnt[PB_K][PB_T / 32];
@@ -428,16 +427,12 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
         const int local = k * PB_T + tid, own = row0 + local;
         own_live[k] = false;
         if (own < P) {
-            const float4 q2 = rec[own].q2;
-            if ((__float_as_uint(q2.w) & 0x0FFFFFFFu) != 0u) {
-                const ScreenGrad A0 = sg[own];
-                own_live[k] = A0.a0.x != 0.f || A0.a0.y != 0.f || A0.a0.z != 0.f || A0.a0.w != 0.f || A0.a1.x != 0.f ||
-                              A0.a1.y != 0.f || A0.a1.z != 0.f || A0.a2.x != 0.f || A0.a2.y != 0.f || A0.a2.z != 0.f;
-                if (own_live[k]) {
-                    s_acc[local][0] = A0.a0; s_acc[local][1] = A0.a1; s_acc[local][2] = A0.a2;
-                    s_bits[local] = __float_as_uint(q2.w);
-                }
-            }
+            // (a culled Gaussian owns no instances, so nothing was ever added to its accumulator: the
+            // all-zero test covers it, and the record is not read here)
+            const ScreenGrad A0 = sg[own];
+            own_live[k] = A0.a0.x != 0.f || A0.a0.y != 0.f || A0.a0.z != 0.f || A0.a0.w != 0.f || A0.a1.x != 0.f ||
+                          A0.a1.y != 0.f || A0.a1.z != 0.f || A0.a2.x != 0.f || A0.a2.y != 0.f || A0.a2.z != 0.f;
+            if (own_live[k]) { s_acc[local][0] = A0.a0; s_acc[local][1] = A0.a1; s_acc[local][2] = A0.a2; }
         }
         s_live[local] = own_live[k] ? 1 : 0;
         bal[k] = __ballot_sync(0xffffffffu, own_live[k]);
@@ -505,10 +500,12 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     // (the per-Gaussian inputs below are fetched while the SH rows are in flight)
     float3 p_in = make_float3(0.f, 0.f, 0.f), sc_in = make_float3(0.f, 0.f, 0.f);
     float4 q_in = make_float4(1.f, 0.f, 0.f, 0.f), rq0 = make_float4(0.f, 0.f, 0.f, 0.f), rq1 = rq0;
+    uint32_t rbits = 0u;                              // record word {radius | flags << 28}
     if (live) {
         p_in = load3(g.means3D, i);
         rq0 = rec[i].q0;
         rq1 = rec[i].q1;
+        rbits = __float_as_uint(rec[i].q2.w);
         if (!g.cov3D_precomp) {
             q_in = __ldg(reinterpret_cast<const float4*>(g.rotations) + i);
             sc_in = load3(g.scales, i);
@@ -525,7 +522,7 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     if (live) {
         Camera cam;
         load_camera(v, cam);
-        const uint32_t flags = s_bits[jl] >> 28;
+        const uint32_t flags = rbits >> 28;
         ScreenGrad A;
         A.a0 = s_acc[jl][0]; A.a1 = s_acc[jl][1]; A.a2 = s_acc[jl][2];
         const float3 p = p_in;
