@@ -130,18 +130,21 @@ photometric_forward_kernel(const float* __restrict__ img, const float* __restric
     // horizontal: item = (row r, group of 4 columns)
     for (int idx = tid; idx < LE * (LT / LPT); idx += LTHREADS) {
         const int r = idx / (LT / LPT), c0 = (idx - r * (LT / LPT)) * LPT;
-        float xa[LWIN + LPT - 1], ya[LWIN + LPT - 1];
+        // the 14 inputs of this item and their products x^2 + y^2, x y, formed once: 4 FMA per tap and output
+        float xa[LWIN + LPT - 1], ya[LWIN + LPT - 1], qa[LWIN + LPT - 1], pa[LWIN + LPT - 1];
 #pragma unroll
-        for (int k = 0; k < LWIN + LPT - 1; k++) { xa[k] = s_x[r][c0 + k]; ya[k] = s_y[r][c0 + k]; }
+        for (int k = 0; k < LWIN + LPT - 1; k++) {
+            xa[k] = s_x[r][c0 + k]; ya[k] = s_y[r][c0 + k];
+            qa[k] = fmaf(xa[k], xa[k], ya[k] * ya[k]); pa[k] = xa[k] * ya[k];
+        }
 #pragma unroll
         for (int j = 0; j < LPT; j++) {
             float m1 = 0.f, m2 = 0.f, ess = 0.f, e12 = 0.f;
 #pragma unroll
             for (int k = 0; k < LWIN; k++) {
-                const float a = xa[j + k], b = ya[j + k], g = win.g[k];
-                const float ga = g * a, gb = g * b;
-                m1 += ga; m2 += gb;
-                ess = fmaf(ga, a, fmaf(gb, b, ess)); e12 = fmaf(ga, b, e12);
+                const float g = win.g[k];
+                m1 = fmaf(g, xa[j + k], m1); m2 = fmaf(g, ya[j + k], m2);
+                ess = fmaf(g, qa[j + k], ess); e12 = fmaf(g, pa[j + k], e12);
             }
             s_h[0][r][c0 + j] = m1; s_h[1][r][c0 + j] = m2; s_h[2][r][c0 + j] = ess; s_h[3][r][c0 + j] = e12;
         }
