@@ -399,7 +399,7 @@ def main():
         "config": {"workload": WORKLOAD, "P": P_GAUSS, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEG,
                    "num_rendered_R": R_inst, "num_rendered_distinct_over_steps": len(R_seen),
                    "views_per_step": world, "parallelism": f"view-sharded dp{world}",
-                   "collective": "1 NCCL all-reduce of the flat gradient buffer per step" if world > 1 else "none (1 GPU)",
+                   "collective": f"1 all-reduce of the flat gradient buffer per step ({flat.collective})" if world > 1 else "none (1 GPU)",
                    "grad_allreduce_bytes": flat.nbytes() if world > 1 else 0,
                    "l2": "no explicit flush: one step streams >1 GB (inputs 236 MB + gradients 232 MB + scratch) through the 126 MB L2"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SCGR_VERSION 102   /* major*10000 + minor*100 + patch */
+#define SCGR_VERSION 103   /* major*10000 + minor*100 + patch */
 #define SCGR_TILE 16        /* BLOCK_X = BLOCK_Y of the external rasterizer's config.h */
 
 typedef void* scgr_stream_t;   /* cudaStream_t */
@@ -166,6 +166,16 @@ int scgr_photometric_forward(const float* image, const float* gt, int32_t C, int
 int scgr_photometric_backward(const float* image, const float* gt, int32_t C, int32_t H, int32_t W,
                               float lambda_dssim, const void* scratch, const float* upstream,
                               float* dL_dimage, scgr_stream_t stream);
+
+/* ---- the path's single collective (sum of the per-view gradients over the ranks) as
+ * a two-shot all-reduce through NVSwitch multicast: rank r reduces its 1/world of the buffer with
+ * multimem.ld_reduce (in-switch fp32 sum of the replicas) and broadcasts it with multimem.st.
+ * `multicast_ptr` is the multicast address of a symmetric-memory buffer of n_floats fp32 (n_floats a
+ * multiple of 4 * world) replicated on every rank; the caller brackets the call with cross-rank barriers
+ * on the same stream (replicas complete before, all shards broadcast after).  Without multicast
+ * support the host side falls back to ncclAllReduce on the same buffer. */
+int scgr_nvls_allreduce(void* multicast_ptr, size_t n_floats, int32_t rank, int32_t world,
+                        scgr_stream_t stream);
 
 /* Launch accounting and per-kernel timing (the reference has no tracing at all, SURVEY.md section 5;
  * bench.py uses this for the live roofline numbers).  scgr_kernel_launch_count(): kernels this

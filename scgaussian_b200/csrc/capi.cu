@@ -381,6 +381,17 @@ int scgr_photometric_backward(const float* image, const float* gt, int32_t C, in
     });
 }
 
+int scgr_nvls_allreduce(void* multicast_ptr, size_t n_floats, int32_t rank, int32_t world, scgr_stream_t stream) {
+    return guarded([&] {
+        require(multicast_ptr != nullptr, "nvls all-reduce: null multicast pointer");
+        require(world >= 1 && rank >= 0 && rank < world, "nvls all-reduce: bad rank / world size");
+        require((reinterpret_cast<uintptr_t>(multicast_ptr) & 15) == 0, "nvls all-reduce: buffer must be 16-byte aligned");
+        require(n_floats % (4 * (size_t)world) == 0, "nvls all-reduce: element count must be a multiple of 4 * world");
+        const Launch L{(cudaStream_t)stream, false};
+        launch_nvls_allreduce(multicast_ptr, n_floats, rank, world, L);
+    });
+}
+
 long long scgr_kernel_launch_count(void) { return g_kernel_launches.load(); }
 
 int scgr_profile_enable(int on) {

@@ -275,6 +275,9 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
                             int32_t P, const Launch& L);
 int tile_partition_final_buffer(uint32_t n_tiles);
 
+// the gradient all-reduce through NVSwitch multicast (collective.cu)
+void launch_nvls_allreduce(void* multicast_ptr, size_t n_floats, int rank, int world, const Launch& L);
+
 // fused photometric loss (loss.cu)
 size_t photometric_scratch_bytes(int C, int H, int W);
 void launch_photometric_forward(const float* img, const float* gt, int C, int H, int W, float lambda, void* scratch,
