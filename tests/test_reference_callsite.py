@@ -1,0 +1,166 @@
+"""The reference's own call site against the drop-in package (build container only: needs /root/reference).
+
+`gaussian_renderer/__init__.py` is imported UNMODIFIED with this repo on sys.path, so its line 15
+(`from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer`) resolves to
+the B200 operator, and its `render()` is run on a small hybrid-style model up to the operator call:
+the 12 settings fields (:38-51), the constructor (:53), the keyword arguments and the 4-tuple unpacking of
+the call (:100-108) and the returned dict (:113-118) are exercised with the reference's own code.
+No GPU here, so the operator's compute is replaced by a recorder for the duration of the call (the real
+operator refuses CPU tensors: there is no CPU path) -- what is checked is the boundary, not the pixels.
+The reference's unrelated, uninstalled dependencies (plyfile, simple_knn, pytorch3d, skimage, imageio,
+matplotlib) are stubbed for the import."""
+import importlib.abc
+import importlib.machinery
+import math
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "gaussian_renderer")),
+                                reason="the reference tree exists in the build container only")
+
+_STUB_ROOTS = ("plyfile", "simple_knn", "pytorch3d", "skimage", "imageio", "matplotlib", "dkm", "lpips")
+
+
+class _Stub(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return lambda *a, **k: None
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path, target=None):
+        if fullname.split(".")[0] in _STUB_ROOTS:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        m = _Stub(spec.name)
+        m.__path__ = []
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+@pytest.fixture()
+def reference_renderer(monkeypatch):
+    finder = _StubFinder()
+    sys.meta_path.append(finder)         # last: only packages that are really missing get stubbed
+    monkeypatch.syspath_prepend(REF)
+    monkeypatch.syspath_prepend(ROOT)
+    before = set(sys.modules)
+    try:
+        import gaussian_renderer
+        yield gaussian_renderer
+    finally:
+        sys.meta_path.remove(finder)
+        for name in set(sys.modules) - before:     # forget the stubs and the reference's own modules, nothing else
+            if isinstance(sys.modules[name], _Stub) or \
+                    name.split(".")[0] in ("gaussian_renderer", "scene", "utils", "arguments", "lpipsPyTorch"):
+                sys.modules.pop(name, None)
+
+
+def test_reference_render_reaches_the_drop_in_operator(reference_renderer, monkeypatch):
+    import diff_gaussian_rasterization as D
+    from scgaussian_b200 import rasterizer as R
+    G = reference_renderer
+    assert G.GaussianRasterizer is R.GaussianRasterizer is D.GaussianRasterizer          # reference line 15
+    assert G.GaussianRasterizationSettings is R.GaussianRasterizationSettings
+
+    P, H, W = 7, 12, 20
+    g = torch.Generator().manual_seed(0)
+
+    class Cam:                                   # what reference scene/cameras.py:54-63 exposes
+        FoVx, FoVy = 1.0, 0.7
+        image_height, image_width = H, W
+        world_view_transform = torch.eye(4)
+        full_proj_transform = torch.eye(4)
+        camera_center = torch.zeros(3)
+
+    class PC:                                    # accessors of reference scene/gaussian_model.py:105-152
+        active_sh_degree = 2
+        max_sh_degree = 3
+        get_xyz = torch.randn(P, 3, generator=g).requires_grad_(True)
+        get_opacity = torch.rand(P, 1, generator=g)
+        get_scaling = torch.rand(P, 3, generator=g)
+        get_rotation = torch.nn.functional.normalize(torch.randn(P, 4, generator=g))
+        get_features = torch.randn(P, 16, 3, generator=g)
+
+    class Pipe:                                  # reference arguments/__init__.py:66-68
+        convert_SHs_python = False
+        compute_cov3D_python = False
+        debug = False
+
+    # reference line 28 hard-codes device="cuda"; on this CPU-only box map it to the tensors' own device
+    real_zeros_like = torch.zeros_like
+    monkeypatch.setattr(torch, "zeros_like", lambda t, **k: real_zeros_like(t, **{**k, "device": t.device}))
+
+    seen = {}
+
+    def recorder(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                 cov3D_precomp=None):
+        seen.update(settings=self.raster_settings, means3D=means3D, means2D=means2D, opacities=opacities, shs=shs,
+                    colors_precomp=colors_precomp, scales=scales, rotations=rotations, cov3D_precomp=cov3D_precomp)
+        s = self.raster_settings
+        color = means3D.sum() * torch.ones(3, s.image_height, s.image_width)           # keeps autograd connected
+        return color, torch.arange(P, dtype=torch.int32) % 3, torch.ones(1, s.image_height, s.image_width), \
+            torch.zeros(1, s.image_height, s.image_width)
+
+    monkeypatch.setattr(R.GaussianRasterizer, "forward", recorder)
+    bg = torch.tensor([0.1, 0.2, 0.3])
+    out = G.render(Cam(), PC(), Pipe(), bg, scaling_modifier=0.5)
+
+    s = seen["settings"]                          # reference lines 38-51
+    assert isinstance(s, R.GaussianRasterizationSettings)
+    assert (s.image_height, s.image_width, s.sh_degree, s.prefiltered, s.debug) == (H, W, 2, False, False)
+    assert s.scale_modifier == 0.5 and s.bg is bg
+    assert abs(s.tanfovx - math.tan(0.5)) < 1e-12 and abs(s.tanfovy - math.tan(0.35)) < 1e-12
+    assert s.viewmatrix is Cam.world_view_transform and s.projmatrix is Cam.full_proj_transform
+    assert s.campos is Cam.camera_center
+    # reference lines 100-108: SH + scale/rotation path, nothing precomputed
+    assert seen["shs"] is PC.get_features and seen["colors_precomp"] is None
+    assert seen["scales"] is PC.get_scaling and seen["rotations"] is PC.get_rotation and seen["cov3D_precomp"] is None
+    assert seen["means3D"] is PC.get_xyz and seen["opacities"] is PC.get_opacity
+    assert seen["means2D"].shape == (P, 3) and seen["means2D"].requires_grad               # the gradient hook (:28-32)
+    # reference lines 113-118: the dict train.py / render.py consume
+    assert set(out) >= {"render", "rendered_depth", "rendered_alpha", "viewspace_points", "visibility_filter", "radii"}
+    assert out["render"].shape == (3, H, W) and out["rendered_depth"].shape == (1, H, W)
+    assert out["viewspace_points"] is seen["means2D"]
+    assert torch.equal(out["visibility_filter"], out["radii"] > 0)
+
+
+def test_the_real_operator_refuses_the_cpu_call(reference_renderer, monkeypatch):
+    """Same call without the recorder: the product has no CPU path and says so."""
+    from scgaussian_b200 import ScgrError
+    G = reference_renderer
+    real_zeros_like = torch.zeros_like
+    monkeypatch.setattr(torch, "zeros_like", lambda t, **k: real_zeros_like(t, **{**k, "device": t.device}))
+
+    class Cam:
+        FoVx, FoVy = 1.0, 0.7
+        image_height, image_width = 8, 8
+        world_view_transform = torch.eye(4)
+        full_proj_transform = torch.eye(4)
+        camera_center = torch.zeros(3)
+
+    class PC:
+        active_sh_degree = 0
+        max_sh_degree = 0
+        get_xyz = torch.zeros(3, 3)
+        get_opacity = torch.ones(3, 1)
+        get_scaling = torch.ones(3, 3)
+        get_rotation = torch.tensor([[1.0, 0, 0, 0]]).repeat(3, 1)
+        get_features = torch.zeros(3, 1, 3)
+
+    class Pipe:
+        convert_SHs_python = compute_cov3D_python = debug = False
+
+    with pytest.raises(ScgrError, match="CUDA"):
+        G.render(Cam(), PC(), Pipe(), torch.zeros(3))
