@@ -389,7 +389,7 @@ __device__ __forceinline__ float transpose_reduce10(const float v[10], const int
 template <int SPW, bool TMA>
 __device__ __forceinline__ void
 backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[96], uint32_t (*s_idb)[32],
-                unsigned long long* bars, float4* s_g4, float* s_tr, const uint2* __restrict__ ranges,
+                unsigned long long* bars, float4* s_g4, const uint2* __restrict__ ranges,
                 const uint32_t* __restrict__ point_list, const Record* __restrict__ rec, const int W, const int H,
                 const float* __restrict__ bg, const uint32_t* __restrict__ n_contrib,
                 const float* __restrict__ final_T, const float* __restrict__ dL_dcolor,
@@ -433,14 +433,7 @@ backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)
     }
     const float pxf = (float)(X0 + lx), pyf = (float)(Yr + ly);
     // (each lane only ever reads back the s_g4 entries it wrote itself: no barrier needed)
-#ifdef SCGR_BWD_SMEM_REDUCE
-    const int slot = lane < 10 ? (lane < 7 ? lane : lane + 1) : -1;   // lane k < 10 deposits value k
-    const int tr_base = (lane % 10) * 33 + 11 * min(lane / 10, 2);
-    if (lane < 10) s_tr[lane * 33 + 32] = 0.f;                          // the pad column read by group 2 at t = 10
-    __syncwarp();
-#else
     const int slot = reduce10_slot(lane);                         // which of the 10 sums this lane deposits
-#endif
     float* const my_grad = reinterpret_cast<float*>(screen_grad) + (slot >= 0 ? slot : 0);
 
     // batch entry j  <->  0-based list position  pos = toDo - 1 - (base + j)   (back to front)
@@ -552,21 +545,7 @@ backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)
             for (int i = 0; i < SPW; i++)
                 if (mj & (1u << i)) pair_grad(i);  // warp-uniform branch
             // (97 % of the pairs that get here have a contributing pixel: reduce unconditionally)
-#ifdef SCGR_BWD_SMEM_REDUCE
-            // A/B variant: transpose through a skewed (stride 33) shared-memory tile instead of the shuffle
-            // butterfly -- 10 conflict-free stores, then lane (k, g) = (lane % 10, lane / 10) adds 11 lanes'
-            // worth of value k (conflict-free: banks k + 11 g + t are distinct), two shuffles fold the 3 groups
-#pragma unroll
-            for (int k = 0; k < 10; k++) s_tr[k * 33 + lane] = v[k];
-            __syncwarp();
-            float part = 0.f;
-#pragma unroll
-            for (int t = 0; t < 11; t++) part += s_tr[tr_base + t];      // (row pad [32] is zero; lanes 30, 31 read row 0/1 harmlessly)
-            __syncwarp();
-            const float sum = part + __shfl_down_sync(0xffffffffu, part, 10) + __shfl_down_sync(0xffffffffu, part, 20);
-#else
             const float sum = transpose_reduce10(v, lane);
-#endif
             SCGR_STAT_ADD(red, 1); SCGR_STAT_ADD(atom, (slot >= 0 && sum != 0.f) ? 1 : 0);
             if (slot >= 0 && sum != 0.f)
                 atomicAdd(my_grad + (size_t)s_id[j] * (sizeof(ScreenGrad) / sizeof(float)), sum);   // RED.E.ADD.F32
@@ -594,15 +573,10 @@ render_backward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __res
     __shared__ uint32_t s_id[2][32];
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ float4 s_g4[TILE_PIX];       // upstream gradients of the region: r, g, b, depth
-#ifdef SCGR_BWD_SMEM_REDUCE
-    __shared__ float s_tr[10 * 33];
-#else
-    float* const s_tr = nullptr;
-#endif
     if (status[0] > capacity) return;
     int b = blockIdx.x;
     // work item -> tile through the longest-first permutation built from the forward's per-tile depths
-#define SCGR_ARGS s_rec, s_id, s_bar, s_g4, s_tr, ranges, point_list, rec, W, H, bg, n_contrib, final_T, dL_dcolor, dL_ddepth, \
+#define SCGR_ARGS s_rec, s_id, s_bar, s_g4, ranges, point_list, rec, W, H, bg, n_contrib, final_T, dL_dcolor, dL_ddepth, \
                   dL_dalpha, screen_grad
     if (b < ws.n8) { backward_region<8, TMA>((int)tile_order[b], tiles_x, 0, SCGR_ARGS); return; }
     b -= ws.n8;
