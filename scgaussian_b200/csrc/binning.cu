@@ -18,7 +18,7 @@
 //               Gaussian can reach alpha >= 1/255 (exact closed-form test, common.cuh).
 //
 // Every radix pass is ONE kernel ("onesweep"): the global digit histograms are produced up front
-// (by a histogram kernel for the depth keys, by the emission kernel for the tile ids), each CTA
+// (by the depth-key kernel for the depth keys, by the emission kernel for the tile ids), each CTA
 // takes a dynamic tile ticket, ranks its 4096 items stably with warp match + per-warp counters,
 // obtains its global digit offsets by decoupled look-back over the preceding CTAs, reorders the
 // items through shared memory and writes them out in coalesced runs.

@@ -43,8 +43,10 @@ class GaussianRasterizationSettings(NamedTuple):
 # --------------------------------------------------------------------------------------------
 # How the forward learns R (the instance count) to size the binning buffer:
 #   "fused"      (default) one scgr_forward() call: the binning buffer is pre-sized from the previous
-#                view's R (+25 %), the library waits for R on a zero-copy pinned word between its two
-#                stages and goes straight on; a view that outgrows the headroom falls back to "sync"
+#                view's R (+25 %); the library enqueues both stages (stage 2 reads R on the device and
+#                refuses to run past the buffer) and waits for R on a zero-copy pinned word only to
+#                report which case it was; a view that outgrew the headroom is finished with an
+#                exactly sized buffer (scgr_forward_render), stage 1 being kept
 #   "sync"       the reference's protocol in two calls: blocking read of R, exactly sized buffer
 #   "optimistic" both stages enqueued blind with the pre-sized buffer, one validation sync at the end
 _BINNING_MODE = os.environ.get("SCGR_BINNING", "fused")
