@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SCGR_VERSION 103   /* major*10000 + minor*100 + patch */
+#define SCGR_VERSION 104   /* major*10000 + minor*100 + patch */
 #define SCGR_TILE 16        /* BLOCK_X = BLOCK_Y of the external rasterizer's config.h */
 
 typedef void* scgr_stream_t;   /* cudaStream_t */
@@ -176,6 +176,11 @@ int scgr_photometric_backward(const float* image, const float* gt, int32_t C, in
  * support the host side falls back to ncclAllReduce on the same buffer. */
 int scgr_nvls_allreduce(void* multicast_ptr, size_t n_floats, int32_t rank, int32_t world,
                         scgr_stream_t stream);
+
+/* ---- simple_knn._C.distCUDA2 (reference scene/gaussian_model.py:20, :444) ----
+ * out[i] = mean over the 3 nearest other points of |p_i - p_j|^2; points [n,3] fp32 device, out [n].
+ * One-shot initialisation helper (exact tiled all-pairs scan, n <= 2^20), not on the per-step path. */
+int scgr_knn3_mean_dist2(const float* points, int32_t n, float* out, scgr_stream_t stream);
 
 /* Launch accounting and per-kernel timing (the reference has no tracing at all, SURVEY.md section 5;
  * bench.py uses this for the live roofline numbers).  scgr_kernel_launch_count(): kernels this

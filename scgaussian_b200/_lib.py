@@ -64,6 +64,7 @@ SYMBOLS = {
     "scgr_photometric_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scgr_nvls_allreduce": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p]),
+    "scgr_knn3_mean_dist2": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "scgr_mark_visible": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scgr_kernel_launch_count": (C.c_longlong, []),
     "scgr_profile_enable": (C.c_int, [C.c_int]),

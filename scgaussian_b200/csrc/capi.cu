@@ -392,6 +392,17 @@ int scgr_nvls_allreduce(void* multicast_ptr, size_t n_floats, int32_t rank, int3
     });
 }
 
+int scgr_knn3_mean_dist2(const float* points, int32_t n, float* out, scgr_stream_t stream) {
+    return guarded([&] {
+        require(n >= 0, "knn3: negative point count");
+        if (n == 0) return;
+        require(points && out, "knn3: null argument");
+        require(n <= (1 << 20), "knn3: exact all-pairs scan is meant for initial clouds of up to 2^20 points");
+        const Launch L{(cudaStream_t)stream, false};
+        launch_knn3(points, n, out, L);
+    });
+}
+
 long long scgr_kernel_launch_count(void) { return g_kernel_launches.load(); }
 
 int scgr_profile_enable(int on) {

@@ -278,6 +278,9 @@ int tile_partition_final_buffer(uint32_t n_tiles);
 // the gradient all-reduce through NVSwitch multicast (collective.cu)
 void launch_nvls_allreduce(void* multicast_ptr, size_t n_floats, int rank, int world, const Launch& L);
 
+// mean squared distance to the 3 nearest neighbours (knn.cu)
+void launch_knn3(const float* points, int32_t n, float* out, const Launch& L);
+
 // fused photometric loss (loss.cu)
 size_t photometric_scratch_bytes(int C, int H, int W);
 void launch_photometric_forward(const float* img, const float* gt, int C, int H, int W, float lambda, void* scratch,
