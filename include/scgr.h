@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SCGR_VERSION 104   /* major*10000 + minor*100 + patch */
+#define SCGR_VERSION 105   /* major*10000 + minor*100 + patch */
 #define SCGR_TILE 16        /* BLOCK_X = BLOCK_Y of the external rasterizer's config.h */
 
 typedef void* scgr_stream_t;   /* cudaStream_t */
@@ -181,6 +181,83 @@ int scgr_nvls_allreduce(void* multicast_ptr, size_t n_floats, int32_t rank, int3
  * out[i] = mean over the 3 nearest other points of |p_i - p_j|^2; points [n,3] fp32 device, out [n].
  * One-shot initialisation helper (exact tiled all-pairs scan, n <= 2^20), not on the per-step path. */
 int scgr_knn3_mean_dist2(const float* points, int32_t n, float* out, scgr_stream_t stream);
+
+/* ---- activations + hybrid assembly, fused ----
+ * What GaussianModel.get_xyz / get_scaling / get_rotation / get_opacity / get_features compute on every
+ * render() call (reference scene/gaussian_model.py:105-152), one launch forward and one backward:
+ *   means3D = cat(rayo + rayd * zval, bg_xyz)            :124-129
+ *   scales  = cat(exp(_scaling), exp(bg_scaling))        :105-113
+ *   rotations = cat(normalize(_rotation), normalize(bg_rotation))   :115-122 (F.normalize, eps 1e-12)
+ *   opacities = cat(sigmoid(_opacity), sigmoid(bg_opacity))         :142-150
+ *   shs     = cat(cat(_features_dc, bg_features_dc), cat(_features_rest, bg_features_rest), dim=1)  :131-140
+ * The model is two sets of raw (pre-activation) parameters; set[0] comes first in the assembled arrays.
+ * A set with rayo != NULL is ray-based (position = rayo + rayd * zval, only zval trained: reference :493);
+ * otherwise its position is `xyz`.  A set with n == 0 may leave its pointers NULL (the reference's model before
+ * bg Gaussians exist / a plain 3DGS model with the ray set empty). */
+typedef struct ScgrModelSet {
+    int32_t n;
+    const float* xyz;            /* [n,3]   free positions (reference bg_xyz), or NULL */
+    const float* rayo;           /* [n,3]   ray origins (reference _rayo), or NULL */
+    const float* rayd;           /* [n,3]   ray directions (reference _rayd) */
+    const float* zval;           /* [n,1]   depth along the ray (reference _zval) */
+    const float* scaling;        /* [n,3]   log scale */
+    const float* rotation;       /* [n,4]   unnormalised quaternion (r,x,y,z) */
+    const float* opacity;        /* [n,1]   logit */
+    const float* features_dc;    /* [n,1,3] */
+    const float* features_rest;  /* [n,sh_rest,3], NULL when sh_rest == 0 */
+} ScgrModelSet;
+typedef struct ScgrModel {
+    int32_t sh_rest;             /* (max_sh_degree + 1)^2 - 1 rows of features_rest: 15 at degree 3 */
+    ScgrModelSet set[2];
+} ScgrModel;
+typedef struct ScgrActivated {   /* the operator's inputs, P = set[0].n + set[1].n (16-byte aligned) */
+    float* means3D;              /* [P,3] */
+    float* scales;               /* [P,3] */
+    float* rotations;            /* [P,4] */
+    float* opacities;            /* [P,1] */
+    float* shs;                  /* [P,sh_rest+1,3] */
+} ScgrActivated;
+typedef struct ScgrActivatedGrads {   /* what scgr_backward produced (ScgrGrads), all required */
+    const float* dL_dmeans3D;
+    const float* dL_dscales;
+    const float* dL_drotations;
+    const float* dL_dopacities;
+    const float* dL_dshs;
+} ScgrActivatedGrads;
+typedef struct ScgrModelSetGrads {    /* written in full for a set with n > 0 */
+    float* dL_dxyz;              /* [n,3] free set only */
+    float* dL_dzval;             /* [n,1] ray-based set only */
+    float* dL_dscaling;          /* [n,3] */
+    float* dL_drotation;         /* [n,4] */
+    float* dL_dopacity;          /* [n,1] */
+    float* dL_dfeatures_dc;      /* [n,1,3] */
+    float* dL_dfeatures_rest;    /* [n,sh_rest,3] */
+} ScgrModelSetGrads;
+typedef struct ScgrModelGrads {
+    ScgrModelSetGrads set[2];
+} ScgrModelGrads;
+int scgr_assemble_forward(const ScgrModel* model, const ScgrActivated* out, scgr_stream_t stream);
+int scgr_assemble_backward(const ScgrModel* model, const ScgrActivatedGrads* grads, const ScgrModelGrads* out,
+                           scgr_stream_t stream);
+
+/* ---- the optimizer step, fused ----
+ * torch.optim.Adam(groups, lr=0.0, eps=1e-15).step() as the reference runs it on its two optimizers every
+ * iteration (reference scene/gaussian_model.py:491-510, train.py:204-208): no weight decay, no amsgrad.  All groups
+ * in ONE launch.  `step` is the group's step count AFTER this update (torch increments first); bias corrections
+ * are formed in double on the host exactly as torch/optim/adam.py does.  param / exp_avg / exp_avg_sq are updated
+ * in place; n < 2^31 per group; groups with n == 0 are skipped. */
+#define SCGR_ADAM_MAX_GROUPS 16
+typedef struct ScgrAdamGroup {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int64_t n;
+    float lr;
+    int32_t step;
+} ScgrAdamGroup;
+int scgr_adam_step(const ScgrAdamGroup* groups, int32_t n_groups, double beta1, double beta2, double eps,
+                   scgr_stream_t stream);
 
 /* Launch accounting and per-kernel timing (the reference has no tracing at all, SURVEY.md section 5;
  * bench.py uses this for the live roofline numbers).  scgr_kernel_launch_count(): kernels this

@@ -40,6 +40,43 @@ class ScgrDebugViews(C.Structure):
                 ("final_T", C.c_void_p), ("num_rendered", C.c_void_p)]
 
 
+class ScgrModelSet(C.Structure):
+    _fields_ = [("n", C.c_int32), ("xyz", C.c_void_p), ("rayo", C.c_void_p), ("rayd", C.c_void_p),
+                ("zval", C.c_void_p), ("scaling", C.c_void_p), ("rotation", C.c_void_p), ("opacity", C.c_void_p),
+                ("features_dc", C.c_void_p), ("features_rest", C.c_void_p)]
+
+
+class ScgrModel(C.Structure):
+    _fields_ = [("sh_rest", C.c_int32), ("set", ScgrModelSet * 2)]
+
+
+class ScgrActivated(C.Structure):
+    _fields_ = [("means3D", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
+                ("opacities", C.c_void_p), ("shs", C.c_void_p)]
+
+
+class ScgrActivatedGrads(C.Structure):
+    _fields_ = [("dL_dmeans3D", C.c_void_p), ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p),
+                ("dL_dopacities", C.c_void_p), ("dL_dshs", C.c_void_p)]
+
+
+class ScgrModelSetGrads(C.Structure):
+    _fields_ = [("dL_dxyz", C.c_void_p), ("dL_dzval", C.c_void_p), ("dL_dscaling", C.c_void_p),
+                ("dL_drotation", C.c_void_p), ("dL_dopacity", C.c_void_p), ("dL_dfeatures_dc", C.c_void_p),
+                ("dL_dfeatures_rest", C.c_void_p)]
+
+
+class ScgrModelGrads(C.Structure):
+    _fields_ = [("set", ScgrModelSetGrads * 2)]
+
+
+class ScgrAdamGroup(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("n", C.c_int64), ("lr", C.c_float), ("step", C.c_int32)]
+
+
+ADAM_MAX_GROUPS = 16   # SCGR_ADAM_MAX_GROUPS (include/scgr.h)
+
 # every symbol include/scgr.h declares: (restype, argtypes)
 SYMBOLS = {
     "scgr_version": (C.c_int, []),
@@ -65,6 +102,11 @@ SYMBOLS = {
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scgr_nvls_allreduce": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p]),
     "scgr_knn3_mean_dist2": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "scgr_assemble_forward": (C.c_int, [C.POINTER(ScgrModel), C.POINTER(ScgrActivated), C.c_void_p]),
+    "scgr_assemble_backward": (C.c_int, [C.POINTER(ScgrModel), C.POINTER(ScgrActivatedGrads),
+                                         C.POINTER(ScgrModelGrads), C.c_void_p]),
+    "scgr_adam_step": (C.c_int, [C.POINTER(ScgrAdamGroup), C.c_int32, C.c_double, C.c_double, C.c_double,
+                                 C.c_void_p]),
     "scgr_mark_visible": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scgr_kernel_launch_count": (C.c_longlong, []),
     "scgr_profile_enable": (C.c_int, [C.c_int]),

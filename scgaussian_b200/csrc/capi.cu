@@ -403,6 +403,82 @@ int scgr_knn3_mean_dist2(const float* points, int32_t n, float* out, scgr_stream
     });
 }
 
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static void validate_model(const ScgrModel* m) {
+    require(m != nullptr, "assemble: null model");
+    require(m->sh_rest >= 0 && m->sh_rest <= 4095, "assemble: sh_rest out of range");
+    int64_t P = 0;
+    for (int k = 0; k < 2; k++) {
+        const ScgrModelSet& s = m->set[k];
+        require(s.n >= 0, "assemble: negative set size");
+        P += s.n;
+        if (s.n == 0) continue;
+        require((s.rayo != nullptr) != (s.xyz != nullptr), "assemble: a set has either xyz or (rayo, rayd, zval)");
+        if (s.rayo) require(s.rayd && s.zval, "assemble: ray-based set needs rayo, rayd and zval");
+        require(s.scaling && s.rotation && s.opacity && s.features_dc, "assemble: null parameter array");
+        require(m->sh_rest == 0 || s.features_rest, "assemble: null features_rest");
+        require(aligned16(s.rotation), "assemble: rotation must be 16-byte aligned");
+    }
+    require(P * 3 * (int64_t)(m->sh_rest + 1) < (int64_t(1) << 31), "assemble: model too large for 32-bit SH indexing");
+}
+
+int scgr_assemble_forward(const ScgrModel* model, const ScgrActivated* out, scgr_stream_t stream) {
+    return guarded([&] {
+        validate_model(model);
+        if (model->set[0].n + model->set[1].n == 0) return;
+        require(out && out->means3D && out->scales && out->rotations && out->opacities && out->shs,
+                "assemble: null output array");
+        require(aligned16(out->rotations) && aligned16(out->shs), "assemble: outputs must be 16-byte aligned");
+        const Launch L{(cudaStream_t)stream, false};
+        launch_assemble_forward(*model, *out, L);
+    });
+}
+
+int scgr_assemble_backward(const ScgrModel* model, const ScgrActivatedGrads* grads, const ScgrModelGrads* out,
+                           scgr_stream_t stream) {
+    return guarded([&] {
+        validate_model(model);
+        if (model->set[0].n + model->set[1].n == 0) return;
+        require(grads && grads->dL_dmeans3D && grads->dL_dscales && grads->dL_drotations && grads->dL_dopacities &&
+                    grads->dL_dshs, "assemble: null incoming gradient");
+        require(aligned16(grads->dL_drotations) && aligned16(grads->dL_dshs),
+                "assemble: incoming gradients must be 16-byte aligned");
+        require(out != nullptr, "assemble: null gradient outputs");
+        for (int k = 0; k < 2; k++) {
+            const ScgrModelSet& s = model->set[k];
+            const ScgrModelSetGrads& d = out->set[k];
+            if (s.n == 0) continue;
+            require(s.rayo ? d.dL_dzval != nullptr : d.dL_dxyz != nullptr, "assemble: null position gradient output");
+            require(d.dL_dscaling && d.dL_drotation && d.dL_dopacity && d.dL_dfeatures_dc,
+                    "assemble: null gradient output");
+            require(model->sh_rest == 0 || d.dL_dfeatures_rest, "assemble: null dL_dfeatures_rest");
+            require(aligned16(d.dL_drotation), "assemble: dL_drotation must be 16-byte aligned");
+        }
+        const Launch L{(cudaStream_t)stream, false};
+        launch_assemble_backward(*model, *grads, *out, L);
+    });
+}
+
+int scgr_adam_step(const ScgrAdamGroup* groups, int32_t n_groups, double beta1, double beta2, double eps,
+                   scgr_stream_t stream) {
+    return guarded([&] {
+        require(n_groups >= 0 && n_groups <= SCGR_ADAM_MAX_GROUPS, "adam: 0..SCGR_ADAM_MAX_GROUPS groups per call");
+        if (n_groups == 0) return;
+        require(groups != nullptr, "adam: null group table");
+        require(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0, "adam: bad betas / eps");
+        for (int i = 0; i < n_groups; i++) {
+            const ScgrAdamGroup& G = groups[i];
+            require(G.n >= 0 && G.n < (int64_t(1) << 31), "adam: group size must be in [0, 2^31)");
+            if (G.n == 0) continue;
+            require(G.param && G.grad && G.exp_avg && G.exp_avg_sq, "adam: null array in a group");
+            require(G.step >= 1, "adam: step counts from 1 (torch increments before the update)");
+        }
+        const Launch L{(cudaStream_t)stream, false};
+        launch_adam(groups, n_groups, beta1, beta2, eps, L);
+    });
+}
+
 long long scgr_kernel_launch_count(void) { return g_kernel_launches.load(); }
 
 int scgr_profile_enable(int on) {

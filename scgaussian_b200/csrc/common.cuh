@@ -281,6 +281,13 @@ void launch_nvls_allreduce(void* multicast_ptr, size_t n_floats, int rank, int w
 // mean squared distance to the 3 nearest neighbours (knn.cu)
 void launch_knn3(const float* points, int32_t n, float* out, const Launch& L);
 
+// activations + hybrid assembly, Adam (model.cu)
+void launch_assemble_forward(const ScgrModel& m, const ScgrActivated& out, const Launch& L);
+void launch_assemble_backward(const ScgrModel& m, const ScgrActivatedGrads& g, const ScgrModelGrads& out,
+                              const Launch& L);
+void launch_adam(const ScgrAdamGroup* groups, int32_t n_groups, double beta1, double beta2, double eps,
+                 const Launch& L);
+
 // fused photometric loss (loss.cu)
 size_t photometric_scratch_bytes(int C, int H, int W);
 void launch_photometric_forward(const float* img, const float* gt, int C, int H, int W, float lambda, void* scratch,

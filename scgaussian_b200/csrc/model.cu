@@ -1,0 +1,360 @@
+// model.cu -- the two elementwise passes either side of the rasterizer in a training step (sm_100a).
+// SURVEY.md section 8(f), rows f2 and f3.  Both are pure HBM streams: no reuse, no shared memory, 128-bit accesses.
+//
+// (f2) assemble_forward / assemble_backward: what SCGaussian's `GaussianModel.get_xyz / get_scaling /
+//      get_rotation / get_opacity / get_features` compute on every render() call
+//      (reference scene/gaussian_model.py:105-152) -- xyz = rayo + rayd * zval for the ray-based set,
+//      exp / normalize / sigmoid activations, the cat of the ray-based and the free ("bg_") set and the
+//      cat of features_dc with features_rest -- in ONE launch each way instead of ~20 torch kernels
+//      (each activation, each cat and every autograd node is its own launch and its own round trip through
+//      HBM: ~2x the bytes).  Output layout = exactly what GaussianRasterizer takes: [P,3] [P,3] [P,4] [P,1]
+//      [P,K,3] with P = n_ray + n_bg, ray-based set first.
+//      algorithmic bytes / Gaussian (K = 16): forward 252 in (ray set; 240 free set) + 236 out;
+//      backward 236 in + 44 raw re-read + 228 out.
+// (f3) adam: `torch.optim.Adam(groups, lr=0.0, eps=1e-15).step()` as the reference runs it twice per
+//      iteration (reference scene/gaussian_model.py:491-510, train.py:204-208), all parameter groups of
+//      both optimizers in ONE launch; per element 16 B read (param, grad, exp_avg, exp_avg_sq) + 12 B
+//      written = 28 B.
+#include "common.cuh"
+
+namespace scgr {
+
+namespace {
+
+constexpr int MODEL_THREADS = 256;
+constexpr int SH_VEC_PER_THREAD = 2;                                   // float4 outputs per thread
+constexpr int SH_VEC_PER_BLOCK = MODEL_THREADS * SH_VEC_PER_THREAD;
+
+__device__ __forceinline__ float sigmoid_f(const float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// the per-Gaussian arrays of one of the two sets, picked field by field (static indices into the kernel
+// parameters: they stay in constant memory)
+struct RawSet {
+    const float *xyz, *rayo, *rayd, *zval, *scaling, *rotation, *opacity;
+};
+__device__ __forceinline__ RawSet select_set(const ScgrModel& m, const bool first) {
+    RawSet s;
+    s.xyz = first ? m.set[0].xyz : m.set[1].xyz;
+    s.rayo = first ? m.set[0].rayo : m.set[1].rayo;
+    s.rayd = first ? m.set[0].rayd : m.set[1].rayd;
+    s.zval = first ? m.set[0].zval : m.set[1].zval;
+    s.scaling = first ? m.set[0].scaling : m.set[1].scaling;
+    s.rotation = first ? m.set[0].rotation : m.set[1].rotation;
+    s.opacity = first ? m.set[0].opacity : m.set[1].opacity;
+    return s;
+}
+__device__ __forceinline__ ScgrModelSetGrads select_grads(const ScgrModelGrads& g, const bool first) {
+    ScgrModelSetGrads d;
+    d.dL_dxyz = first ? g.set[0].dL_dxyz : g.set[1].dL_dxyz;
+    d.dL_dzval = first ? g.set[0].dL_dzval : g.set[1].dL_dzval;
+    d.dL_dscaling = first ? g.set[0].dL_dscaling : g.set[1].dL_dscaling;
+    d.dL_drotation = first ? g.set[0].dL_drotation : g.set[1].dL_drotation;
+    d.dL_dopacity = first ? g.set[0].dL_dopacity : g.set[1].dL_dopacity;
+    d.dL_dfeatures_dc = first ? g.set[0].dL_dfeatures_dc : g.set[1].dL_dfeatures_dc;
+    d.dL_dfeatures_rest = first ? g.set[0].dL_dfeatures_rest : g.set[1].dL_dfeatures_rest;
+    return d;
+}
+
+// element k (0 .. 3K-1) of the [K,3] SH block of Gaussian i of the assembled model
+__device__ __forceinline__ float load_sh(const ScgrModel& m, const uint32_t i, const uint32_t k, const uint32_t n3k) {
+    const bool ray = i < (uint32_t)m.set[0].n;
+    const uint32_t ii = ray ? i : i - (uint32_t)m.set[0].n;
+    const float* dc = ray ? m.set[0].features_dc : m.set[1].features_dc;
+    const float* rest = ray ? m.set[0].features_rest : m.set[1].features_rest;
+    return k < 3 ? __ldg(dc + (size_t)ii * 3 + k) : __ldg(rest + (size_t)ii * (n3k - 3) + (k - 3));
+}
+
+__global__ void __launch_bounds__(MODEL_THREADS)
+assemble_forward_kernel(const __grid_constant__ ScgrModel m, const __grid_constant__ ScgrActivated o,
+                        const uint32_t sh_blocks, const uint32_t n3k, const uint32_t sh_total) {
+    if (blockIdx.x < sh_blocks) {
+        // ---- get_features (reference scene/gaussian_model.py:131-140): flat over the P*K*3 output floats,
+        // one aligned float4 store per 4 of them; consecutive lanes read consecutive source addresses
+        float r[SH_VEC_PER_THREAD][4];
+        uint32_t e0[SH_VEC_PER_THREAD];
+#pragma unroll
+        for (int u = 0; u < SH_VEC_PER_THREAD; u++) {
+            e0[u] = (blockIdx.x * SH_VEC_PER_BLOCK + u * MODEL_THREADS + threadIdx.x) * 4u;
+            uint32_t i = e0[u] / n3k, k = e0[u] - i * n3k;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                r[u][j] = (e0[u] + j < sh_total) ? load_sh(m, i, k, n3k) : 0.f;
+                if (++k == n3k) { k = 0; i++; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SH_VEC_PER_THREAD; u++) {
+            if (e0[u] + 3 < sh_total) {
+                *reinterpret_cast<float4*>(o.shs + e0[u]) = make_float4(r[u][0], r[u][1], r[u][2], r[u][3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (e0[u] + j < sh_total) o.shs[e0[u] + j] = r[u][j];
+            }
+        }
+        return;
+    }
+    // ---- one thread per Gaussian: position, scale, rotation, opacity
+    const uint32_t P = (uint32_t)m.set[0].n + (uint32_t)m.set[1].n;
+    const uint32_t i = (blockIdx.x - sh_blocks) * MODEL_THREADS + threadIdx.x;
+    if (i >= P) return;
+    const bool ray = i < (uint32_t)m.set[0].n;
+    const size_t ii = ray ? i : i - (uint32_t)m.set[0].n;
+    const RawSet s = select_set(m, ray);
+
+    float x, y, z;
+    if (s.rayo) {     // get_xyz, reference :124: rayo + rayd * zval (product rounded, then the sum: two torch kernels)
+        const float t = __ldg(s.zval + ii);
+        x = __fadd_rn(__ldg(s.rayo + 3 * ii + 0), __fmul_rn(__ldg(s.rayd + 3 * ii + 0), t));
+        y = __fadd_rn(__ldg(s.rayo + 3 * ii + 1), __fmul_rn(__ldg(s.rayd + 3 * ii + 1), t));
+        z = __fadd_rn(__ldg(s.rayo + 3 * ii + 2), __fmul_rn(__ldg(s.rayd + 3 * ii + 2), t));
+    } else {
+        x = __ldg(s.xyz + 3 * ii + 0); y = __ldg(s.xyz + 3 * ii + 1); z = __ldg(s.xyz + 3 * ii + 2);
+    }
+    o.means3D[3 * (size_t)i + 0] = x; o.means3D[3 * (size_t)i + 1] = y; o.means3D[3 * (size_t)i + 2] = z;
+
+    // get_scaling, reference :105-113: exp
+    o.scales[3 * (size_t)i + 0] = expf(__ldg(s.scaling + 3 * ii + 0));
+    o.scales[3 * (size_t)i + 1] = expf(__ldg(s.scaling + 3 * ii + 1));
+    o.scales[3 * (size_t)i + 2] = expf(__ldg(s.scaling + 3 * ii + 2));
+
+    // get_rotation, reference :115-122: torch.nn.functional.normalize = q / max(|q|, 1e-12)
+    const float4 q = __ldg(reinterpret_cast<const float4*>(s.rotation) + ii);
+    const float nrm = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    const float d = fmaxf(nrm, 1e-12f);
+    reinterpret_cast<float4*>(o.rotations)[i] = make_float4(q.x / d, q.y / d, q.z / d, q.w / d);
+
+    // get_opacity, reference :142-150: sigmoid
+    o.opacities[i] = sigmoid_f(__ldg(s.opacity + ii));
+}
+
+__global__ void __launch_bounds__(MODEL_THREADS)
+assemble_backward_kernel(const __grid_constant__ ScgrModel m, const __grid_constant__ ScgrActivatedGrads g,
+                         const __grid_constant__ ScgrModelGrads out, const uint32_t sh_blocks, const uint32_t n3k,
+                         const uint32_t sh_total) {
+    const uint32_t n0 = (uint32_t)m.set[0].n;
+    if (blockIdx.x < sh_blocks) {
+        // ---- dL/dshs [P,K,3] split into dL/dfeatures_dc [n,1,3] and dL/dfeatures_rest [n,K-1,3] of the two sets:
+        // one aligned float4 load per 4 floats, scalar stores to consecutive addresses across the warp
+        float4 r[SH_VEC_PER_THREAD];
+        uint32_t e0[SH_VEC_PER_THREAD];
+#pragma unroll
+        for (int u = 0; u < SH_VEC_PER_THREAD; u++) {
+            e0[u] = (blockIdx.x * SH_VEC_PER_BLOCK + u * MODEL_THREADS + threadIdx.x) * 4u;
+            r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e0[u] + 3 < sh_total) {
+                r[u] = __ldg(reinterpret_cast<const float4*>(g.dL_dshs + e0[u]));
+            } else if (e0[u] < sh_total) {
+                r[u].x = __ldg(g.dL_dshs + e0[u]);
+                if (e0[u] + 1 < sh_total) r[u].y = __ldg(g.dL_dshs + e0[u] + 1);
+                if (e0[u] + 2 < sh_total) r[u].z = __ldg(g.dL_dshs + e0[u] + 2);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SH_VEC_PER_THREAD; u++) {
+            const float v[4] = {r[u].x, r[u].y, r[u].z, r[u].w};
+            uint32_t i = e0[u] / n3k, k = e0[u] - i * n3k;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (e0[u] + j < sh_total) {
+                    const bool ray = i < n0;
+                    const size_t ii = ray ? i : i - n0;
+                    float* dc = ray ? out.set[0].dL_dfeatures_dc : out.set[1].dL_dfeatures_dc;
+                    float* rest = ray ? out.set[0].dL_dfeatures_rest : out.set[1].dL_dfeatures_rest;
+                    if (k < 3) dc[ii * 3 + k] = v[j];
+                    else rest[ii * (n3k - 3) + (k - 3)] = v[j];
+                }
+                if (++k == n3k) { k = 0; i++; }
+            }
+        }
+        return;
+    }
+    const uint32_t P = n0 + (uint32_t)m.set[1].n;
+    const uint32_t i = (blockIdx.x - sh_blocks) * MODEL_THREADS + threadIdx.x;
+    if (i >= P) return;
+    const bool ray = i < n0;
+    const size_t ii = ray ? i : i - n0;
+    const RawSet s = select_set(m, ray);
+    const ScgrModelSetGrads d = select_grads(out, ray);
+
+    // position: d zval = <rayd, dL/dxyz> (rayo, rayd are fixed ray geometry: reference :493 optimises zval only)
+    const float gx = __ldg(g.dL_dmeans3D + 3 * (size_t)i + 0), gy = __ldg(g.dL_dmeans3D + 3 * (size_t)i + 1),
+                gz = __ldg(g.dL_dmeans3D + 3 * (size_t)i + 2);
+    if (s.rayo) {
+        const float px = __fmul_rn(gx, __ldg(s.rayd + 3 * ii + 0)), py = __fmul_rn(gy, __ldg(s.rayd + 3 * ii + 1)),
+                    pz = __fmul_rn(gz, __ldg(s.rayd + 3 * ii + 2));
+        d.dL_dzval[ii] = __fadd_rn(__fadd_rn(px, py), pz);
+    } else {
+        d.dL_dxyz[3 * ii + 0] = gx; d.dL_dxyz[3 * ii + 1] = gy; d.dL_dxyz[3 * ii + 2] = gz;
+    }
+
+    // exp: dL/draw = dL/dscale * scale
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+        d.dL_dscaling[3 * ii + c] = __ldg(g.dL_dscales + 3 * (size_t)i + c) * expf(__ldg(s.scaling + 3 * ii + c));
+
+    // normalize: y = q / max(|q|, eps);  dL/dq = (g - y <y, g>) / |q|  (clamp active: dL/dq = g / eps)
+    const float4 q = __ldg(reinterpret_cast<const float4*>(s.rotation) + ii);
+    const float4 gr = __ldg(reinterpret_cast<const float4*>(g.dL_drotations) + i);
+    const float nrm = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    float4 dq;
+    if (nrm > 1e-12f) {
+        const float inv = 1.0f / nrm;
+        const float4 y = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+        const float dot = y.x * gr.x + y.y * gr.y + y.z * gr.z + y.w * gr.w;
+        dq = make_float4((gr.x - y.x * dot) * inv, (gr.y - y.y * dot) * inv, (gr.z - y.z * dot) * inv,
+                         (gr.w - y.w * dot) * inv);
+    } else {
+        dq = make_float4(gr.x * 1e12f, gr.y * 1e12f, gr.z * 1e12f, gr.w * 1e12f);
+    }
+    reinterpret_cast<float4*>(d.dL_drotation)[ii] = dq;
+
+    // sigmoid: dL/draw = dL/dopacity * (1 - y) * y
+    const float y = sigmoid_f(__ldg(s.opacity + ii));
+    d.dL_dopacity[ii] = __ldg(g.dL_dopacities + i) * (1.0f - y) * y;
+}
+
+// ------------------------------------------------------------------------------------------------------
+constexpr int ADAM_THREADS = 256;
+constexpr int ADAM_VEC = 4;                                    // float4 per thread per array
+constexpr int ADAM_CHUNK = ADAM_THREADS * ADAM_VEC * 4;        // elements per CTA
+
+struct AdamSeg {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    uint32_t n;
+    uint32_t first_block;
+    float step_size;      // lr / (1 - beta1^step)
+    float bc2_sqrt;       // sqrt(1 - beta2^step)
+};
+struct AdamTable {
+    AdamSeg seg[SCGR_ADAM_MAX_GROUPS];
+    int n_seg;
+    float beta2, w1, w2, eps;   // w1 = 1 - beta1, w2 = 1 - beta2
+};
+
+// torch/optim/adam.py _single_tensor_adam, in its order of operations:
+//   exp_avg.lerp_(grad, 1 - beta1);  exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
+//   denom = exp_avg_sq.sqrt() / sqrt(bias_correction2) + eps;  param.addcdiv_(exp_avg, denom, value = -lr / bias_correction1)
+__device__ __forceinline__ void adam_update(float& p, const float g, float& m, float& v, const float beta2,
+                                            const float w1, const float w2, const float eps, const float step_size,
+                                            const float bc2_sqrt) {
+    m = m + w1 * (g - m);
+    v = v * beta2 + w2 * g * g;
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    p = p - step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(ADAM_THREADS)
+adam_kernel(const __grid_constant__ AdamTable t) {
+    // which parameter group does this CTA work on?  (static indices only: the table stays in constant memory)
+    float* p = t.seg[0].p; const float* g = t.seg[0].g; float* m = t.seg[0].m; float* v = t.seg[0].v;
+    uint32_t n = t.seg[0].n, first = 0;
+    float step_size = t.seg[0].step_size, bc2_sqrt = t.seg[0].bc2_sqrt;
+#pragma unroll
+    for (int k = 1; k < SCGR_ADAM_MAX_GROUPS; k++) {
+        if (k < t.n_seg && blockIdx.x >= t.seg[k].first_block) {
+            p = t.seg[k].p; g = t.seg[k].g; m = t.seg[k].m; v = t.seg[k].v;
+            n = t.seg[k].n; first = t.seg[k].first_block;
+            step_size = t.seg[k].step_size; bc2_sqrt = t.seg[k].bc2_sqrt;
+        }
+    }
+    const uint32_t base = (blockIdx.x - first) * (uint32_t)ADAM_CHUNK;
+    const bool aligned = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15u) == 0;
+    if (aligned && base + ADAM_CHUNK <= n) {
+        // full chunk: all loads of the 4 rounds in flight before the first store
+        float4 P4[ADAM_VEC], G4[ADAM_VEC], M4[ADAM_VEC], V4[ADAM_VEC];
+#pragma unroll
+        for (int u = 0; u < ADAM_VEC; u++) {
+            const uint32_t e = base + (u * ADAM_THREADS + threadIdx.x) * 4u;
+            P4[u] = *reinterpret_cast<const float4*>(p + e);
+            G4[u] = __ldg(reinterpret_cast<const float4*>(g + e));
+            M4[u] = *reinterpret_cast<const float4*>(m + e);
+            V4[u] = *reinterpret_cast<const float4*>(v + e);
+        }
+#pragma unroll
+        for (int u = 0; u < ADAM_VEC; u++) {
+            const uint32_t e = base + (u * ADAM_THREADS + threadIdx.x) * 4u;
+            adam_update(P4[u].x, G4[u].x, M4[u].x, V4[u].x, t.beta2, t.w1, t.w2, t.eps, step_size, bc2_sqrt);
+            adam_update(P4[u].y, G4[u].y, M4[u].y, V4[u].y, t.beta2, t.w1, t.w2, t.eps, step_size, bc2_sqrt);
+            adam_update(P4[u].z, G4[u].z, M4[u].z, V4[u].z, t.beta2, t.w1, t.w2, t.eps, step_size, bc2_sqrt);
+            adam_update(P4[u].w, G4[u].w, M4[u].w, V4[u].w, t.beta2, t.w1, t.w2, t.eps, step_size, bc2_sqrt);
+            *reinterpret_cast<float4*>(p + e) = P4[u];
+            *reinterpret_cast<float4*>(m + e) = M4[u];
+            *reinterpret_cast<float4*>(v + e) = V4[u];
+        }
+        return;
+    }
+    // ragged last chunk of a group, or a group that is not 16-byte aligned (a view at an odd offset)
+    const uint32_t end = min(n, base + (uint32_t)ADAM_CHUNK);
+    for (uint32_t e = base + threadIdx.x; e < end; e += ADAM_THREADS) {
+        float pe = p[e], me = m[e], ve = v[e];
+        adam_update(pe, __ldg(g + e), me, ve, t.beta2, t.w1, t.w2, t.eps, step_size, bc2_sqrt);
+        p[e] = pe; m[e] = me; v[e] = ve;
+    }
+}
+
+uint32_t sh_block_count(uint64_t sh_total) {
+    const uint64_t vecs = (sh_total + 3) / 4;
+    return (uint32_t)((vecs + SH_VEC_PER_BLOCK - 1) / SH_VEC_PER_BLOCK);
+}
+
+}  // namespace
+
+void launch_assemble_forward(const ScgrModel& m, const ScgrActivated& out, const Launch& L) {
+    const uint64_t P = (uint64_t)m.set[0].n + (uint64_t)m.set[1].n;
+    if (P == 0) return;
+    const uint32_t n3k = 3u * (uint32_t)(m.sh_rest + 1);
+    const uint64_t sh_total = P * n3k;
+    const uint32_t sh_blocks = sh_block_count(sh_total);
+    const uint32_t blocks = sh_blocks + (uint32_t)((P + MODEL_THREADS - 1) / MODEL_THREADS);
+    begin_kernel("assemble_forward", L);
+    assemble_forward_kernel<<<blocks, MODEL_THREADS, 0, L.stream>>>(m, out, sh_blocks, n3k, (uint32_t)sh_total);
+    check_launch("assemble_forward", L);
+}
+
+void launch_assemble_backward(const ScgrModel& m, const ScgrActivatedGrads& g, const ScgrModelGrads& out,
+                              const Launch& L) {
+    const uint64_t P = (uint64_t)m.set[0].n + (uint64_t)m.set[1].n;
+    if (P == 0) return;
+    const uint32_t n3k = 3u * (uint32_t)(m.sh_rest + 1);
+    const uint64_t sh_total = P * n3k;
+    const uint32_t sh_blocks = sh_block_count(sh_total);
+    const uint32_t blocks = sh_blocks + (uint32_t)((P + MODEL_THREADS - 1) / MODEL_THREADS);
+    begin_kernel("assemble_backward", L);
+    assemble_backward_kernel<<<blocks, MODEL_THREADS, 0, L.stream>>>(m, g, out, sh_blocks, n3k, (uint32_t)sh_total);
+    check_launch("assemble_backward", L);
+}
+
+void launch_adam(const ScgrAdamGroup* groups, int32_t n_groups, double beta1, double beta2, double eps,
+                 const Launch& L) {
+    AdamTable t{};
+    uint64_t blocks = 0;
+    int k = 0;
+    for (int i = 0; i < n_groups; i++) {
+        const ScgrAdamGroup& G = groups[i];
+        if (G.n == 0) continue;
+        const double bc1 = 1.0 - pow(beta1, (double)G.step);
+        const double bc2 = 1.0 - pow(beta2, (double)G.step);
+        AdamSeg& s = t.seg[k++];
+        s.p = G.param; s.g = G.grad; s.m = G.exp_avg; s.v = G.exp_avg_sq;
+        s.n = (uint32_t)G.n;
+        s.first_block = (uint32_t)blocks;
+        s.step_size = (float)((double)G.lr / bc1);
+        s.bc2_sqrt = (float)sqrt(bc2);
+        blocks += ((uint64_t)G.n + ADAM_CHUNK - 1) / ADAM_CHUNK;
+    }
+    if (k == 0) return;
+    t.n_seg = k;
+    t.beta2 = (float)beta2;
+    t.w1 = (float)(1.0 - beta1);
+    t.w2 = (float)(1.0 - beta2);
+    t.eps = (float)eps;
+    begin_kernel("adam", L);
+    adam_kernel<<<(uint32_t)blocks, ADAM_THREADS, 0, L.stream>>>(t);
+    check_launch("adam", L);
+}
+
+}  // namespace scgr
