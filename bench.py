@@ -54,7 +54,7 @@ def peaks():
 
 
 def make_inputs(rank: int, device):
-    from oracle import torch_oracle as O   # the seed-0 generator is shared with the tests
+    from scgaussian_b200 import synthetic as O   # the seed-0 generator, shared with the tests
     cam = O.make_camera(WIDTH, HEIGHT, w2c=O.yaw_w2c((rank - 3.5) * 2.0 if int(os.environ.get("WORLD_SIZE", "1")) > 1 else 0.0))
     sc = O.synth_scene(P_GAUSS, WIDTH, HEIGHT, sh_degree=SH_DEG, scale_median=SCALE_MED, seed=0)
     grads = O.synth_upstream_grads(WIDTH, HEIGHT, seed=1)

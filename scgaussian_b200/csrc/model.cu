@@ -1,5 +1,5 @@
 // model.cu -- the two elementwise passes either side of the rasterizer in a training step (sm_100a).
-// SURVEY.md section 8(f), rows f2 and f3.  Both are pure HBM streams: no reuse, no shared memory, 128-bit accesses.
+// SURVEY.md section 8(f), rows f2 and f3.  Both are pure HBM streams: no reuse, no shared memory.
 //
 // (f2) assemble_forward / assemble_backward: what SCGaussian's `GaussianModel.get_xyz / get_scaling /
 //      get_rotation / get_opacity / get_features` compute on every render() call
@@ -22,8 +22,8 @@ namespace scgr {
 namespace {
 
 constexpr int MODEL_THREADS = 256;
-constexpr int SH_VEC_PER_THREAD = 2;                                   // float4 outputs per thread
-constexpr int SH_VEC_PER_BLOCK = MODEL_THREADS * SH_VEC_PER_THREAD;
+constexpr int SH_PER_THREAD = 8;                                        // SH floats per thread, stride MODEL_THREADS
+constexpr int SH_PER_BLOCK = MODEL_THREADS * SH_PER_THREAD;
 
 __device__ __forceinline__ float sigmoid_f(const float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -67,31 +67,23 @@ __device__ __forceinline__ float load_sh(const ScgrModel& m, const uint32_t i, c
 __global__ void __launch_bounds__(MODEL_THREADS)
 assemble_forward_kernel(const __grid_constant__ ScgrModel m, const __grid_constant__ ScgrActivated o,
                         const uint32_t sh_blocks, const uint32_t n3k, const uint32_t sh_total) {
+    const uint32_t step_i = MODEL_THREADS / n3k, step_k = MODEL_THREADS - step_i * n3k;   // (i, k) of element e + 256
     if (blockIdx.x < sh_blocks) {
-        // ---- get_features (reference scene/gaussian_model.py:131-140): flat over the P*K*3 output floats,
-        // one aligned float4 store per 4 of them; consecutive lanes read consecutive source addresses
-        float r[SH_VEC_PER_THREAD][4];
-        uint32_t e0[SH_VEC_PER_THREAD];
+        // ---- get_features (reference scene/gaussian_model.py:131-140): flat over the P*K*3 output floats; consecutive
+        // lanes read consecutive source floats and write consecutive output floats (the [n,K-1,3] source rows are 4
+        // bytes off 16-byte alignment for every other Gaussian, so wider accesses would need staging), 8 per thread in flight
+        float r[SH_PER_THREAD];
+        const uint32_t e = blockIdx.x * SH_PER_BLOCK + threadIdx.x;
+        uint32_t i = e / n3k, k = e - i * n3k;
 #pragma unroll
-        for (int u = 0; u < SH_VEC_PER_THREAD; u++) {
-            e0[u] = (blockIdx.x * SH_VEC_PER_BLOCK + u * MODEL_THREADS + threadIdx.x) * 4u;
-            uint32_t i = e0[u] / n3k, k = e0[u] - i * n3k;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                r[u][j] = (e0[u] + j < sh_total) ? load_sh(m, i, k, n3k) : 0.f;
-                if (++k == n3k) { k = 0; i++; }
-            }
+        for (int u = 0; u < SH_PER_THREAD; u++) {
+            r[u] = (e + u * MODEL_THREADS < sh_total) ? load_sh(m, i, k, n3k) : 0.f;
+            k += step_k; i += step_i;
+            if (k >= n3k) { k -= n3k; i++; }
         }
 #pragma unroll
-        for (int u = 0; u < SH_VEC_PER_THREAD; u++) {
-            if (e0[u] + 3 < sh_total) {
-                *reinterpret_cast<float4*>(o.shs + e0[u]) = make_float4(r[u][0], r[u][1], r[u][2], r[u][3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (e0[u] + j < sh_total) o.shs[e0[u] + j] = r[u][j];
-            }
-        }
+        for (int u = 0; u < SH_PER_THREAD; u++)
+            if (e + u * MODEL_THREADS < sh_total) o.shs[e + u * MODEL_THREADS] = r[u];
         return;
     }
     // ---- one thread per Gaussian: position, scale, rotation, opacity
@@ -133,39 +125,28 @@ assemble_backward_kernel(const __grid_constant__ ScgrModel m, const __grid_const
                          const __grid_constant__ ScgrModelGrads out, const uint32_t sh_blocks, const uint32_t n3k,
                          const uint32_t sh_total) {
     const uint32_t n0 = (uint32_t)m.set[0].n;
+    const uint32_t step_i = MODEL_THREADS / n3k, step_k = MODEL_THREADS - step_i * n3k;   // (i, k) of element e + 256
     if (blockIdx.x < sh_blocks) {
         // ---- dL/dshs [P,K,3] split into dL/dfeatures_dc [n,1,3] and dL/dfeatures_rest [n,K-1,3] of the two sets:
-        // one aligned float4 load per 4 floats, scalar stores to consecutive addresses across the warp
-        float4 r[SH_VEC_PER_THREAD];
-        uint32_t e0[SH_VEC_PER_THREAD];
+        // the mirror image of the forward copy, coalesced 4-byte accesses on both sides
+        float v[SH_PER_THREAD];
+        const uint32_t e = blockIdx.x * SH_PER_BLOCK + threadIdx.x;
 #pragma unroll
-        for (int u = 0; u < SH_VEC_PER_THREAD; u++) {
-            e0[u] = (blockIdx.x * SH_VEC_PER_BLOCK + u * MODEL_THREADS + threadIdx.x) * 4u;
-            r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e0[u] + 3 < sh_total) {
-                r[u] = __ldg(reinterpret_cast<const float4*>(g.dL_dshs + e0[u]));
-            } else if (e0[u] < sh_total) {
-                r[u].x = __ldg(g.dL_dshs + e0[u]);
-                if (e0[u] + 1 < sh_total) r[u].y = __ldg(g.dL_dshs + e0[u] + 1);
-                if (e0[u] + 2 < sh_total) r[u].z = __ldg(g.dL_dshs + e0[u] + 2);
+        for (int u = 0; u < SH_PER_THREAD; u++)
+            v[u] = (e + u * MODEL_THREADS < sh_total) ? __ldg(g.dL_dshs + e + u * MODEL_THREADS) : 0.f;
+        uint32_t i = e / n3k, k = e - i * n3k;
+#pragma unroll
+        for (int u = 0; u < SH_PER_THREAD; u++) {
+            if (e + u * MODEL_THREADS < sh_total) {
+                const bool ray = i < n0;
+                const size_t ii = ray ? i : i - n0;
+                float* dc = ray ? out.set[0].dL_dfeatures_dc : out.set[1].dL_dfeatures_dc;
+                float* rest = ray ? out.set[0].dL_dfeatures_rest : out.set[1].dL_dfeatures_rest;
+                if (k < 3) dc[ii * 3 + k] = v[u];
+                else rest[ii * (n3k - 3) + (k - 3)] = v[u];
             }
-        }
-#pragma unroll
-        for (int u = 0; u < SH_VEC_PER_THREAD; u++) {
-            const float v[4] = {r[u].x, r[u].y, r[u].z, r[u].w};
-            uint32_t i = e0[u] / n3k, k = e0[u] - i * n3k;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (e0[u] + j < sh_total) {
-                    const bool ray = i < n0;
-                    const size_t ii = ray ? i : i - n0;
-                    float* dc = ray ? out.set[0].dL_dfeatures_dc : out.set[1].dL_dfeatures_dc;
-                    float* rest = ray ? out.set[0].dL_dfeatures_rest : out.set[1].dL_dfeatures_rest;
-                    if (k < 3) dc[ii * 3 + k] = v[j];
-                    else rest[ii * (n3k - 3) + (k - 3)] = v[j];
-                }
-                if (++k == n3k) { k = 0; i++; }
-            }
+            k += step_k; i += step_i;
+            if (k >= n3k) { k -= n3k; i++; }
         }
         return;
     }
@@ -296,10 +277,7 @@ adam_kernel(const __grid_constant__ AdamTable t) {
     }
 }
 
-uint32_t sh_block_count(uint64_t sh_total) {
-    const uint64_t vecs = (sh_total + 3) / 4;
-    return (uint32_t)((vecs + SH_VEC_PER_BLOCK - 1) / SH_VEC_PER_BLOCK);
-}
+uint32_t sh_block_count(uint64_t sh_total) { return (uint32_t)((sh_total + SH_PER_BLOCK - 1) / SH_PER_BLOCK); }
 
 }  // namespace
 

@@ -11,6 +11,7 @@ kernels (scgaussian_b200/csrc/model.cu, through the C ABI) against the golden ve
 optimizer.  Tolerances: activations are single fp32 operations (exp, sigmoid, divide) -> 2e-6 relative;
 gradients 1e-5; Adam 1e-6 of the parameter scale per step (a few ulp: torch's CUDA kernels contract a*b+c
 differently from its CPU ones as well)."""
+import copy
 import os
 
 import numpy as np
@@ -387,7 +388,7 @@ def test_adam_matches_torch_adam_on_ragged_and_unaligned_groups():
                        lr=0.0, eps=1e-15)
     for a, b in zip(ours_p, ref_p):
         a.data.copy_(b.data)
-    again.load_state_dict(ref.state_dict())
+    again.load_state_dict(copy.deepcopy(ref.state_dict()))    # load_state_dict itself shares the tensors it is given
     for a, b in zip(ours_p, ref_p):
         gr = torch.randn(a.shape, generator=gen)
         a.grad, b.grad = gr.cuda(), gr.cuda()

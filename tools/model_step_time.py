@@ -102,6 +102,26 @@ res["adam_torch_us"] = timed(lambda: (ref_a.step(), ref_b.step()))
 n_el = sum(raw[k].numel() for k in trained)
 res["adam_elements"] = n_el
 res["adam_fused_gbs"] = n_el * 28 / res["adam_fused_us"] / 1e3
+# per-kernel times of the fused passes (CUDA events bracketing each launch inside the library)
+import ctypes as C  # noqa: E402
+from scgaussian_b200 import _lib  # noqa: E402
+lib = _lib.load()
+lib.scgr_profile_enable(1)
+for _ in range(10):
+    fwd_bwd(lambda: model.assemble(**raw))
+    for k in trained:
+        raw[k].grad = torch.zeros_like(raw[k])
+    optim.step_all(ours_a, ours_b)
+torch.cuda.synchronize()
+names, msarr = (C.c_char_p * 256)(), (C.c_float * 256)()
+n = lib.scgr_profile_fetch(names, msarr, 256)
+lib.scgr_profile_enable(0)
+per = {}
+for i in range(max(n, 0)):
+    per.setdefault(names[i].decode(), []).append(float(msarr[i]) * 1e3)
+res["kernel_us_median"] = {k: sorted(v)[len(v) // 2] for k, v in per.items()}
+res["assemble_backward_kernel_gbs"] = bwd_bytes / res["kernel_us_median"]["assemble_backward"] / 1e3
+res["assemble_forward_kernel_gbs"] = fwd_bytes / res["kernel_us_median"]["assemble_forward"] / 1e3
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
 res["hbm_peak_gbs"] = peaks["hbm_gbs"]
 res["assemble_forward_frac"] = res["assemble_forward_gbs"] / peaks["hbm_gbs"]

@@ -41,7 +41,7 @@ def main():
     _lib.LIB_PATH = STATS_LIB
     from scgaussian_b200 import GaussianRasterizationSettings
     from scgaussian_b200 import rasterizer as R
-    from oracle import torch_oracle as O
+    from scgaussian_b200 import synthetic as O
 
     a = [x for x in sys.argv[1:] if not x.startswith("--")]
     P, W, H = (int(a[0]), int(a[1]), int(a[2])) if len(a) >= 3 else (1_000_000, 1920, 1080)

@@ -4,7 +4,7 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
-from oracle import torch_oracle as O
+from scgaussian_b200 import synthetic as O
 from scgaussian_b200 import GaussianRasterizationSettings, GaussianRasterizer
 from scgaussian_b200 import rasterizer as R
 

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from oracle import torch_oracle as O  # noqa: E402  (input generator only)
+from scgaussian_b200 import synthetic as O  # noqa: E402
 from scgaussian_b200 import GaussianRasterizationSettings  # noqa: E402
 from scgaussian_b200 import rasterizer as R  # noqa: E402
 
