@@ -9,7 +9,7 @@ chain of ~12 launches per optimizer.
     step_all(gaussians.optimizer, gaussians.optimizer_bg)      # both optimizers of the reference in one launch
 
 `Adam` is a `torch.optim.Optimizer`: `param_groups` (lr scheduling, reference :514-527), `state` with torch's own
-keys `step` / `exp_avg` / `exp_avg_sq` (what the reference's densification edits in place, :682-757), `state_dict`
+keys `step` / `exp_avg` / `exp_avg_sq` (what the reference's densification edits in place, :758-843), `state_dict`
 / `load_state_dict` (checkpoints, :83, :103) and `zero_grad` are inherited and interchangeable with torch's.
 No CPU / eager fallback: the update runs in libscgr.so or raises.
 """

@@ -106,7 +106,7 @@ def test_no_cpu_path():
 
 def test_fused_adam_keeps_torch_optimizer_surface():
     """What the reference does to its optimizers besides step(): per-group lr scheduling by name
-    (scene/gaussian_model.py:514-527), state surgery by parameter (:682-757), state_dict round trips (:83, :103)."""
+    (scene/gaussian_model.py:514-527), state surgery by parameter (:758-843), state_dict round trips (:83, :103)."""
     from scgaussian_b200 import optim
     a, b = torch.nn.Parameter(torch.randn(7, 3)), torch.nn.Parameter(torch.randn(7, 1))
     groups = [{"params": [a], "lr": 0.5, "name": "zval"}, {"params": [b], "lr": 0.25, "name": "opacity"}]

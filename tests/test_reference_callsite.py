@@ -164,3 +164,42 @@ def test_the_real_operator_refuses_the_cpu_call(reference_renderer, monkeypatch)
 
     with pytest.raises(ScgrError, match="CUDA"):
         G.render(Cam(), PC(), Pipe(), torch.zeros(3))
+
+
+def test_reference_optimizer_surgery_runs_on_the_fused_adam(reference_renderer):
+    """The reference's densification edits its optimizers through `param_groups` / `state` (reference
+    scene/gaussian_model.py:758-843: replace_tensor_to_optimizer, _prune_optimizer, cat_tensors_to_optimizer).
+    Those methods, UNMODIFIED, are run here on scgaussian_b200.optim.Adam and on
+    torch.optim.Adam side by side: same parameters, same state afterwards.  (Host logic only: no step() on the CPU.)"""
+    from scene.gaussian_model import GaussianModel      # importable once the fixture has installed the stubs
+    from scgaussian_b200 import optim
+    g = torch.Generator().manual_seed(4)
+
+    def build(cls):
+        ps = {"zval": torch.nn.Parameter(torch.randn(6, 1, generator=torch.Generator().manual_seed(1))),
+              "opacity": torch.nn.Parameter(torch.randn(6, 1, generator=torch.Generator().manual_seed(2)))}
+        opt = cls([{"params": [p], "lr": 0.01, "name": n} for n, p in ps.items()], lr=0.0, eps=1e-15)
+        for n, p in ps.items():       # a state as after one step (torch's key set)
+            opt.state[p] = {"step": torch.tensor(1.0), "exp_avg": torch.full_like(p, 0.5),
+                            "exp_avg_sq": torch.full_like(p, 0.25)}
+        return opt
+
+    pc = GaussianModel(3)
+    mask = torch.tensor([True, False, True, True, False, True])
+    ext = {"zval": torch.randn(2, 1, generator=g), "opacity": torch.randn(2, 1, generator=g)}
+    results = []
+    for cls in (optim.Adam, torch.optim.Adam):
+        opt = build(cls)
+        a = pc._prune_optimizer(mask, opt)
+        assert a["zval"].shape == (4, 1) and opt.state[a["zval"]]["exp_avg"].shape == (4, 1)
+        b = pc.cat_tensors_to_optimizer({k: v.clone() for k, v in ext.items()}, opt)
+        assert b["opacity"].shape == (6, 1) and float(opt.state[b["opacity"]]["exp_avg"][-1]) == 0.0
+        c = pc.replace_tensor_to_optimizer(torch.full((6, 1), -2.0), "opacity", opt)
+        st = opt.state[c["opacity"]]
+        assert float(st["exp_avg"].abs().max()) == 0.0 and float(st["step"]) == 1.0
+        assert [grp["name"] for grp in opt.param_groups] == ["zval", "opacity"]
+        results.append({grp["name"]: (grp["params"][0].detach().clone(), opt.state[grp["params"][0]]["exp_avg"].clone())
+                        for grp in opt.param_groups})
+    for name in ("zval", "opacity"):
+        assert torch.equal(results[0][name][0], results[1][name][0])
+        assert torch.equal(results[0][name][1], results[1][name][1])

@@ -2,6 +2,8 @@
 profiles/:  python tools/summarize_ncu.py <round-tag>
   gpurun_out/launches.csv   (ncu --metrics gpu__time_duration.sum ... bench.py)  -> profiles/<tag>_launches.md
   gpurun_out/prof_all.ncu-rep (ncu --set full ... one step)                       -> profiles/<tag>_kernels.md / traffic.json
+A second argument names another capture (e.g. gpurun_out/prof_model.ncu-rep of tools/model_ncu.py): its kernels go to
+profiles/<tag>_kernels.md and are merged into traffic.json.
 """
 import csv
 import io
@@ -59,7 +61,9 @@ if os.path.exists(lp):
     print("wrote", f"{tag}_launches.md")
 
 # ---------------- full-set capture ----------------
-rp = os.path.join(ROOT, "gpurun_out", "prof_all.ncu-rep")
+rp = os.path.join(ROOT, sys.argv[2]) if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "prof_all.ncu-rep")
+what = "One step of config 3 (1M Gaussians, 1920x1080, SH3)" if len(sys.argv) <= 2 else \
+    f"`{os.path.basename(rp)}` (1M Gaussians, SH3)"
 if os.path.exists(rp):
     raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -74,7 +78,7 @@ if os.path.exists(rp):
     stall = [h for h in hdr if "average_warps_issue_stalled" in h and "per_issue_active" in h]
     traffic = {}
     with open(os.path.join(out_dir, f"{tag}_kernels.md"), "w") as f:
-        f.write(f"# ncu --set full summary ({tag})\n\nOne step of config 3 (1M Gaussians, 1920x1080, SH3) under "
+        f.write(f"# ncu --set full summary ({tag})\n\n{what} under "
                 "`ncu --set full --clock-control none --import-source on`.  Numbers under the profiler are NOT bench values.\n\n")
         for r in rows[2:]:
             d = dict(zip(hdr, r))
@@ -95,5 +99,8 @@ if os.path.exists(rp):
                 traffic.setdefault(base, []).append(t)
             except Exception:
                 pass
-    json.dump({k: sum(v) / len(v) for k, v in traffic.items()}, open(os.path.join(out_dir, "traffic.json"), "w"), indent=1)
+    tp = os.path.join(out_dir, "traffic.json")
+    merged = json.load(open(tp)) if len(sys.argv) > 2 and os.path.exists(tp) else {}
+    merged.update({k: sum(v) / len(v) for k, v in traffic.items()})
+    json.dump(merged, open(tp, "w"), indent=1)
     print("wrote", f"{tag}_kernels.md", "traffic.json")
