@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SCGR_VERSION 105   /* major*10000 + minor*100 + patch */
+#define SCGR_VERSION 106   /* major*10000 + minor*100 + patch */
 #define SCGR_TILE 16        /* BLOCK_X = BLOCK_Y of the external rasterizer's config.h */
 
 typedef void* scgr_stream_t;   /* cudaStream_t */
@@ -239,6 +239,17 @@ typedef struct ScgrModelGrads {
 int scgr_assemble_forward(const ScgrModel* model, const ScgrActivated* out, scgr_stream_t stream);
 int scgr_assemble_backward(const ScgrModel* model, const ScgrActivatedGrads* grads, const ScgrModelGrads* out,
                            scgr_stream_t stream);
+
+/* ---- the per-iteration consumers of radii / screenspace_points.grad ----
+ * reference train.py:192-193 and scene/gaussian_model.py:932-934, for every Gaussian i with update_filter[i]
+ * (NULL: radii[i] > 0, which is what the reference passes as visibility_filter):
+ *   max_radii2D[i] = max(max_radii2D[i], radii[i]);  xyz_gradient_accum[i] += |dL_dmeans2D[i, 0:2]|;  denom[i] += 1
+ * in place, one launch, no host synchronisation (each boolean-mask statement of the reference is a nonzero + D2H).
+ * dL_dmeans2D [P,3] (screenspace_points.grad), update_filter [P] bytes (torch.bool) or NULL, radii [P] int32 or
+ * NULL (then max_radii2D is left alone and update_filter is required), xyz_gradient_accum / denom [P,1] or both NULL,
+ * max_radii2D [P] fp32 or NULL. */
+int scgr_densification_stats(const float* dL_dmeans2D, const uint8_t* update_filter, const int32_t* radii, int32_t P,
+                             float* xyz_gradient_accum, float* denom, float* max_radii2D, scgr_stream_t stream);
 
 /* ---- the optimizer step, fused ----
  * torch.optim.Adam(groups, lr=0.0, eps=1e-15).step() as the reference runs it on its two optimizers every

@@ -60,3 +60,16 @@ def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, dtype=np.f
     denom = np.sqrt(v) / f(bc2 ** 0.5) + f(eps)
     p = p - f(step_size) * (m / denom)                                # param.addcdiv_(exp_avg, denom, value=-step_size)
     return p.astype(dtype), m.astype(dtype), v.astype(dtype)
+
+
+def densification_stats(grad2d, update_filter, radii, accum, denom, max_radii):
+    """reference train.py:192 + scene/gaussian_model.py:932-934 on numpy arrays; returns the updated copies."""
+    f = np.asarray(update_filter, dtype=bool)
+    accum, denom = np.array(accum, dtype=np.float32), np.array(denom, dtype=np.float32)
+    max_radii = np.array(max_radii, dtype=np.float32)
+    if radii is not None:
+        max_radii[f] = np.maximum(max_radii[f], np.asarray(radii)[f].astype(np.float32))        # train.py:192
+    g = np.asarray(grad2d, dtype=np.float32)
+    accum[f] += np.sqrt(g[f, 0:1] * g[f, 0:1] + g[f, 1:2] * g[f, 1:2])                          # :933
+    denom[f] += 1                                                                               # :934
+    return accum, denom, max_radii

@@ -105,6 +105,8 @@ SYMBOLS = {
     "scgr_assemble_forward": (C.c_int, [C.POINTER(ScgrModel), C.POINTER(ScgrActivated), C.c_void_p]),
     "scgr_assemble_backward": (C.c_int, [C.POINTER(ScgrModel), C.POINTER(ScgrActivatedGrads),
                                          C.POINTER(ScgrModelGrads), C.c_void_p]),
+    "scgr_densification_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]),
     "scgr_adam_step": (C.c_int, [C.POINTER(ScgrAdamGroup), C.c_int32, C.c_double, C.c_double, C.c_double,
                                  C.c_void_p]),
     "scgr_mark_visible": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -460,6 +460,21 @@ int scgr_assemble_backward(const ScgrModel* model, const ScgrActivatedGrads* gra
     });
 }
 
+int scgr_densification_stats(const float* dL_dmeans2D, const uint8_t* update_filter, const int32_t* radii, int32_t P,
+                             float* xyz_gradient_accum, float* denom, float* max_radii2D, scgr_stream_t stream) {
+    return guarded([&] {
+        require(P >= 0, "densification_stats: negative P");
+        if (P == 0) return;
+        require(update_filter || radii, "densification_stats: need update_filter or radii");
+        require((xyz_gradient_accum != nullptr) == (denom != nullptr),
+                "densification_stats: xyz_gradient_accum and denom go together");
+        require(!xyz_gradient_accum || dL_dmeans2D, "densification_stats: null dL_dmeans2D");
+        require(xyz_gradient_accum || (max_radii2D && radii), "densification_stats: nothing to update");
+        const Launch L{(cudaStream_t)stream, false};
+        launch_densification_stats(dL_dmeans2D, update_filter, radii, P, xyz_gradient_accum, denom, max_radii2D, L);
+    });
+}
+
 int scgr_adam_step(const ScgrAdamGroup* groups, int32_t n_groups, double beta1, double beta2, double eps,
                    scgr_stream_t stream) {
     return guarded([&] {

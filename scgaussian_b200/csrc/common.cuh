@@ -287,6 +287,8 @@ void launch_assemble_backward(const ScgrModel& m, const ScgrActivatedGrads& g, c
                               const Launch& L);
 void launch_adam(const ScgrAdamGroup* groups, int32_t n_groups, double beta1, double beta2, double eps,
                  const Launch& L);
+void launch_densification_stats(const float* dL_dmeans2D, const uint8_t* update_filter, const int32_t* radii, int32_t P,
+                                float* xyz_gradient_accum, float* denom, float* max_radii2D, const Launch& L);
 
 // fused photometric loss (loss.cu)
 size_t photometric_scratch_bytes(int C, int H, int W);

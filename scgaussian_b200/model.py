@@ -176,6 +176,45 @@ def assemble_model(pc):
     return assemble(**ray, **bg)
 
 
+def add_densification_stats(pc, viewspace_point_tensor, update_filter=None, radii=None) -> None:
+    """reference scene/gaussian_model.py:932-934 (`pc.add_densification_stats(viewspace_point_tensor, update_filter)`)
+    and, when `radii` is given, reference train.py:192 (`max_radii2D[vis] = max(max_radii2D[vis], radii[vis])`) in
+    the same launch -- in place on pc.xyz_gradient_accum / pc.denom / pc.max_radii2D, without the nonzero + host
+    synchronisation each boolean-mask statement of the reference costs.  `update_filter=None` means `radii > 0`
+    (what the reference passes)."""
+    lib = _lib.load()
+    grad = viewspace_point_tensor.grad
+    if grad is None:
+        raise ScgrError("add_densification_stats: viewspace_point_tensor has no .grad (call backward first)")
+    if grad.device.type != "cuda":
+        raise ScgrError("add_densification_stats runs on CUDA tensors only (no CPU path exists)")
+    if update_filter is None and radii is None:
+        raise ScgrError("add_densification_stats needs update_filter or radii")
+    P = int(grad.shape[0])
+    accum, denom = pc.xyz_gradient_accum, pc.denom
+    max_radii = pc.max_radii2D if radii is not None else None
+    state = [accum, denom] + ([max_radii] if max_radii is not None else [])
+    for t in state:
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.shape[0] != P or t.device != grad.device:
+            raise ScgrError("add_densification_stats: statistics tensors must be contiguous fp32 [P, ...] on the gradient's device")
+    grad = grad if grad.dtype == torch.float32 and grad.is_contiguous() else grad.float().contiguous()
+    keep = [grad]
+    if update_filter is not None:
+        if update_filter.dtype != torch.bool or update_filter.shape[0] != P:
+            raise ScgrError("add_densification_stats: update_filter must be a bool mask of length P")
+        update_filter = update_filter.contiguous()
+        keep.append(update_filter)
+    if radii is not None:
+        if radii.dtype != torch.int32 or radii.shape[0] != P:
+            raise ScgrError("add_densification_stats: radii must be the operator's int32 [P] output")
+        radii = radii.contiguous()
+        keep.append(radii)
+    with torch.cuda.device(grad.device):
+        stream = C.c_void_p(torch.cuda.current_stream(grad.device).cuda_stream)
+        check(lib.scgr_densification_stats(grad.data_ptr(), _p(update_filter), _p(radii), P, accum.data_ptr(),
+                                           denom.data_ptr(), _p(max_radii), stream))
+
+
 def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None):
     """reference gaussian_renderer/__init__.py:20-118 with the model read through `assemble_model`: same
     arguments (minus the point-cloud dump switches :87-96, file I/O), same returned dict.  The two debug switches

@@ -6,7 +6,9 @@
     (SURVEY.md section 8f row f2);
   * the two optimizers exactly as `training_setup` builds them (:486-512: torch.optim.Adam(l, lr=0.0, eps=1e-15),
     learning rates from arguments/__init__.py OptimizationParams) stepped 3 times with `update_learning_rate`
-    (:514-527) and seeded gradients (row f3).
+    (:514-527) and seeded gradients (row f3);
+  * the per-iteration statistics update of train.py:192-193 (the statement at :192 is read from the file and executed
+    verbatim; :193 calls GaussianModel.add_densification_stats :932-934) (row a17).
 
 Run in the build container only (the GPU box has no /root/reference):
 
@@ -147,6 +149,27 @@ def main():
         out[f"adam_v3{n}"] = st["exp_avg_sq"].numpy().copy()
     out["adam_eps"] = np.float64(pc.optimizer.defaults["eps"])
     out["adam_betas"] = np.array(pc.optimizer.defaults["betas"], dtype=np.float64)
+
+    # ---- a17: the per-iteration densification statistics (train.py:192-193 -> gaussian_model.py:932-934)
+    n = 57
+    pc = GaussianModel(3)
+    pc.xyz_gradient_accum = torch.rand(n, 1, generator=g)
+    pc.denom = torch.randint(0, 5, (n, 1), generator=g).float()
+    pc.max_radii2D = torch.randint(0, 30, (n,), generator=g).float()
+    radii = torch.randint(-1, 40, (n,), generator=g).to(torch.int32).clamp_min(0)
+    radii[::5] = 0
+    vsp = torch.zeros(n, 3, requires_grad=True)
+    vsp.grad = torch.randn(n, 3, generator=g) * 1e-3
+    out["stats_accum0"], out["stats_denom0"] = pc.xyz_gradient_accum.numpy().copy(), pc.denom.numpy().copy()
+    out["stats_maxr0"], out["stats_radii"], out["stats_grad"] = pc.max_radii2D.numpy().copy(), radii.numpy(), vsp.grad.numpy()
+    lines = open(os.path.join(REF, "train.py")).read().splitlines()
+    stmt = [ln.strip() for ln in lines if ln.strip().startswith("gaussians.max_radii2D[visibility_filter] =")]
+    assert len(stmt) == 1, stmt                      # train.py:192, executed verbatim
+    scope = {"gaussians": pc, "visibility_filter": radii > 0, "radii": radii, "torch": torch}
+    exec(stmt[0], scope)
+    pc.add_densification_stats(vsp, radii > 0)       # train.py:193 -> gaussian_model.py:932-934
+    out["stats_accum1"], out["stats_denom1"] = pc.xyz_gradient_accum.numpy().copy(), pc.denom.numpy().copy()
+    out["stats_maxr1"] = pc.max_radii2D.numpy().copy()
 
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "model_golden.npz")
     np.savez_compressed(path, **out)

@@ -82,6 +82,15 @@ def test_adam_oracle_matches_reference_golden():
     assert g["adam_lr_zval"][2] < g["adam_lr_zval"][0] and g["adam_lrbg_xyz"][2] == g["adam_lrbg_xyz"][0]
 
 
+def test_stats_oracle_matches_reference_golden():
+    g = np.load(GOLD)
+    radii = g["stats_radii"]
+    a, d, m = MO.densification_stats(g["stats_grad"], radii > 0, radii, g["stats_accum0"], g["stats_denom0"], g["stats_maxr0"])
+    assert np.array_equal(d, g["stats_denom1"]) and np.array_equal(m, g["stats_maxr1"])
+    assert _rel(a, g["stats_accum1"]) < 1e-6
+    assert (radii == 0).any() and (g["stats_maxr1"] != g["stats_maxr0"]).any()
+
+
 # ------------------------------------------------------------------------------------------ CPU: host logic
 def test_no_cpu_path():
     from scgaussian_b200 import model, optim
@@ -396,3 +405,53 @@ def test_adam_matches_torch_adam_on_ragged_and_unaligned_groups():
     ref.step()
     for k, (a, b) in enumerate(zip(ours_p, ref_p)):
         assert float((a.detach() - b.detach()).abs().max()) <= 2e-6 * (float(b.detach().abs().max()) + lrs[k]), k
+
+
+class _Stats:
+    pass
+
+
+@pytest.mark.gpu
+def test_densification_stats_match_reference_golden_and_oracle():
+    """reference train.py:192-193 / scene/gaussian_model.py:932-934 in one launch."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from scgaussian_b200 import model
+    g = np.load(GOLD)
+
+    def run(grad, radii, accum, denom, maxr, with_filter):
+        pc = _Stats()
+        pc.xyz_gradient_accum = torch.tensor(accum, device="cuda")
+        pc.denom = torch.tensor(denom, device="cuda")
+        pc.max_radii2D = torch.tensor(maxr, device="cuda")
+        vsp = torch.zeros(grad.shape, device="cuda", requires_grad=True)
+        vsp.grad = torch.tensor(grad, device="cuda")
+        r = torch.tensor(radii, device="cuda")
+        model.add_densification_stats(pc, vsp, (r > 0) if with_filter else None, r)
+        return pc.xyz_gradient_accum.cpu().numpy(), pc.denom.cpu().numpy(), pc.max_radii2D.cpu().numpy()
+
+    for with_filter in (False, True):
+        a, d, m = run(g["stats_grad"], g["stats_radii"], g["stats_accum0"], g["stats_denom0"], g["stats_maxr0"], with_filter)
+        assert np.array_equal(d, g["stats_denom1"]) and np.array_equal(m, g["stats_maxr1"])
+        assert _rel(a, g["stats_accum1"]) < 1e-6
+    # a large ragged case against the oracle; update_filter only (no radii): max_radii2D untouched
+    gen = torch.Generator().manual_seed(8)
+    P = 100_003
+    grad = (torch.randn(P, 3, generator=gen) * 1e-3).numpy()
+    radii = torch.randint(0, 50, (P,), generator=gen).to(torch.int32).numpy()
+    radii[::3] = 0
+    accum, denom = torch.rand(P, 1, generator=gen).numpy(), torch.randint(0, 9, (P, 1), generator=gen).float().numpy()
+    maxr = torch.randint(0, 60, (P,), generator=gen).float().numpy()
+    a, d, m = run(grad, radii, accum, denom, maxr, False)
+    wa, wd, wm = MO.densification_stats(grad, radii > 0, radii, accum, denom, maxr)
+    assert np.array_equal(d, wd) and np.array_equal(m, wm) and _rel(a, wa) < 1e-6
+    pc = _Stats()
+    pc.xyz_gradient_accum, pc.denom = torch.tensor(accum, device="cuda"), torch.tensor(denom, device="cuda")
+    pc.max_radii2D = torch.tensor(maxr, device="cuda")
+    vsp = torch.zeros(P, 3, device="cuda", requires_grad=True)
+    vsp.grad = torch.tensor(grad, device="cuda")
+    filt = torch.tensor(radii > 7, device="cuda")
+    model.add_densification_stats(pc, vsp, filt)
+    wa, wd, _ = MO.densification_stats(grad, radii > 7, None, accum, denom, maxr)
+    assert np.array_equal(pc.denom.cpu().numpy(), wd) and _rel(pc.xyz_gradient_accum.cpu().numpy(), wa) < 1e-6
+    assert np.array_equal(pc.max_radii2D.cpu().numpy(), maxr)
