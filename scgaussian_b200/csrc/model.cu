@@ -86,29 +86,33 @@ assemble_forward_kernel(const __grid_constant__ ScgrModel m, const __grid_consta
             if (e + u * MODEL_THREADS < sh_total) o.shs[e + u * MODEL_THREADS] = r[u];
         return;
     }
-    // ---- one thread per Gaussian: position, scale, rotation, opacity
+    // ---- a CTA per 256 Gaussians.  Position and scale are [P,3] arrays: walked as flat streams of 768 floats
+    // (consecutive lanes on consecutive floats, in and out) rather than 3 strided floats per thread
     const uint32_t P = (uint32_t)m.set[0].n + (uint32_t)m.set[1].n;
-    const uint32_t i = (blockIdx.x - sh_blocks) * MODEL_THREADS + threadIdx.x;
-    if (i >= P) return;
-    const bool ray = i < (uint32_t)m.set[0].n;
-    const size_t ii = ray ? i : i - (uint32_t)m.set[0].n;
-    const RawSet s = select_set(m, ray);
-
-    float x, y, z;
-    if (s.rayo) {     // get_xyz, reference :124: rayo + rayd * zval (product rounded, then the sum: two torch kernels)
-        const float t = __ldg(s.zval + ii);
-        x = __fadd_rn(__ldg(s.rayo + 3 * ii + 0), __fmul_rn(__ldg(s.rayd + 3 * ii + 0), t));
-        y = __fadd_rn(__ldg(s.rayo + 3 * ii + 1), __fmul_rn(__ldg(s.rayd + 3 * ii + 1), t));
-        z = __fadd_rn(__ldg(s.rayo + 3 * ii + 2), __fmul_rn(__ldg(s.rayd + 3 * ii + 2), t));
-    } else {
-        x = __ldg(s.xyz + 3 * ii + 0); y = __ldg(s.xyz + 3 * ii + 1); z = __ldg(s.xyz + 3 * ii + 2);
+    const uint32_t n0 = (uint32_t)m.set[0].n;
+    const uint32_t g0 = (blockIdx.x - sh_blocks) * MODEL_THREADS;
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+        const uint32_t e = 3 * g0 + u * MODEL_THREADS + threadIdx.x;       // flat index into the [P,3] outputs
+        if (e < 3 * P) {
+            const uint32_t j = e / 3;
+            const bool jr = j < n0;
+            const size_t ee = jr ? e : e - 3 * n0, jj = jr ? j : j - n0;
+            const RawSet sj = select_set(m, jr);
+            float v;
+            if (sj.rayo)    // get_xyz, reference :124: rayo + rayd * zval (product rounded, then the sum: two torch kernels)
+                v = __fadd_rn(__ldg(sj.rayo + ee), __fmul_rn(__ldg(sj.rayd + ee), __ldg(sj.zval + jj)));
+            else
+                v = __ldg(sj.xyz + ee);
+            o.means3D[e] = v;
+            o.scales[e] = expf(__ldg(sj.scaling + ee));                     // get_scaling, reference :105-113
+        }
     }
-    o.means3D[3 * (size_t)i + 0] = x; o.means3D[3 * (size_t)i + 1] = y; o.means3D[3 * (size_t)i + 2] = z;
-
-    // get_scaling, reference :105-113: exp
-    o.scales[3 * (size_t)i + 0] = expf(__ldg(s.scaling + 3 * ii + 0));
-    o.scales[3 * (size_t)i + 1] = expf(__ldg(s.scaling + 3 * ii + 1));
-    o.scales[3 * (size_t)i + 2] = expf(__ldg(s.scaling + 3 * ii + 2));
+    const uint32_t i = g0 + threadIdx.x;
+    if (i >= P) return;
+    const bool ray = i < n0;
+    const size_t ii = ray ? i : i - n0;
+    const RawSet s = select_set(m, ray);
 
     // get_rotation, reference :115-122: torch.nn.functional.normalize = q / max(|q|, 1e-12)
     const float4 q = __ldg(reinterpret_cast<const float4*>(s.rotation) + ii);
@@ -150,29 +154,36 @@ assemble_backward_kernel(const __grid_constant__ ScgrModel m, const __grid_const
         }
         return;
     }
+    // ---- a CTA per 256 Gaussians; the [n,3] gradients (free positions, log scales) as flat streams of 768 floats
     const uint32_t P = n0 + (uint32_t)m.set[1].n;
-    const uint32_t i = (blockIdx.x - sh_blocks) * MODEL_THREADS + threadIdx.x;
+    const uint32_t g0 = (blockIdx.x - sh_blocks) * MODEL_THREADS;
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+        const uint32_t e = 3 * g0 + u * MODEL_THREADS + threadIdx.x;
+        if (e < 3 * P) {
+            const uint32_t j = e / 3;
+            const bool jr = j < n0;
+            const size_t ee = jr ? e : e - 3 * n0;
+            const RawSet sj = select_set(m, jr);
+            const ScgrModelSetGrads dj = select_grads(out, jr);
+            if (!sj.rayo) dj.dL_dxyz[ee] = __ldg(g.dL_dmeans3D + e);                                  // free position
+            dj.dL_dscaling[ee] = __ldg(g.dL_dscales + e) * expf(__ldg(sj.scaling + ee));              // exp: dL/draw = dL/dscale * scale
+        }
+    }
+    const uint32_t i = g0 + threadIdx.x;
     if (i >= P) return;
     const bool ray = i < n0;
     const size_t ii = ray ? i : i - n0;
     const RawSet s = select_set(m, ray);
     const ScgrModelSetGrads d = select_grads(out, ray);
 
-    // position: d zval = <rayd, dL/dxyz> (rayo, rayd are fixed ray geometry: reference :493 optimises zval only)
-    const float gx = __ldg(g.dL_dmeans3D + 3 * (size_t)i + 0), gy = __ldg(g.dL_dmeans3D + 3 * (size_t)i + 1),
-                gz = __ldg(g.dL_dmeans3D + 3 * (size_t)i + 2);
+    // ray-based position: d zval = <rayd, dL/dxyz> (rayo, rayd are fixed ray geometry: reference :493 optimises zval only)
     if (s.rayo) {
-        const float px = __fmul_rn(gx, __ldg(s.rayd + 3 * ii + 0)), py = __fmul_rn(gy, __ldg(s.rayd + 3 * ii + 1)),
-                    pz = __fmul_rn(gz, __ldg(s.rayd + 3 * ii + 2));
+        const float px = __fmul_rn(__ldg(g.dL_dmeans3D + 3 * (size_t)i + 0), __ldg(s.rayd + 3 * ii + 0)),
+                    py = __fmul_rn(__ldg(g.dL_dmeans3D + 3 * (size_t)i + 1), __ldg(s.rayd + 3 * ii + 1)),
+                    pz = __fmul_rn(__ldg(g.dL_dmeans3D + 3 * (size_t)i + 2), __ldg(s.rayd + 3 * ii + 2));
         d.dL_dzval[ii] = __fadd_rn(__fadd_rn(px, py), pz);
-    } else {
-        d.dL_dxyz[3 * ii + 0] = gx; d.dL_dxyz[3 * ii + 1] = gy; d.dL_dxyz[3 * ii + 2] = gz;
     }
-
-    // exp: dL/draw = dL/dscale * scale
-#pragma unroll
-    for (int c = 0; c < 3; c++)
-        d.dL_dscaling[3 * ii + c] = __ldg(g.dL_dscales + 3 * (size_t)i + c) * expf(__ldg(s.scaling + 3 * ii + c));
 
     // normalize: y = q / max(|q|, eps);  dL/dq = (g - y <y, g>) / |q|  (clamp active: dL/dq = g / eps)
     const float4 q = __ldg(reinterpret_cast<const float4*>(s.rotation) + ii);

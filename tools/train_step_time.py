@@ -1,9 +1,11 @@
 """One full training step at BASELINE config 3 (1M Gaussians, 1920x1080, SH degree 3) on the GPU box, the way reference
 train.py:135-208 runs it -- raw parameters -> activations + assembly -> rasterizer -> L1 + D-SSIM loss -> backward ->
-Adam on the 12 parameter groups -- in two variants over the SAME rasterizer and loss kernels:
+densification statistics (train.py:192-193) -> Adam on the 12 parameter groups -- in two variants over the SAME rasterizer and loss kernels:
 
-  fused      scgaussian_b200.model.render (one assembly kernel each way) + optim.step_all (one Adam launch)
-  torch      the reference's chain of torch activations / cats and its two torch.optim.Adam optimizers
+  fused      scgaussian_b200.model.render (one assembly kernel each way) + model.add_densification_stats (one launch,
+             no host sync) + optim.step_all (one Adam launch)
+  torch      the reference's chain of torch activations / cats, its boolean-mask statistics statements and its two
+             torch.optim.Adam optimizers
 
 CUDA events over back-to-back steps after warm-up.  Prints one JSON object (also to gpurun_out/train_step.json).
 The hybrid model is a stand-in (70 % of the synthetic Gaussians parameterised as rays through the origin)."""
@@ -46,6 +48,8 @@ def make_pc():
     pc._opacity, pc.bg_opacity = par(op[:n_ray]), par(op[n_ray:])
     pc._features_dc, pc.bg_features_dc = par(sh[:n_ray, :1]), par(sh[n_ray:, :1])
     pc._features_rest, pc.bg_features_rest = par(sh[:n_ray, 1:]), par(sh[n_ray:, 1:])
+    pc.xyz_gradient_accum, pc.denom = torch.zeros(P, 1, device=dev), torch.zeros(P, 1, device=dev)
+    pc.max_radii2D = torch.zeros(P, device=dev)
     return pc
 
 
@@ -89,7 +93,7 @@ def render_torch(pc):
     color, radii, depth, alpha = GaussianRasterizer(raster_settings=rs)(
         means3D=xyz, means2D=ssp, shs=shs, colors_precomp=None, opacities=opa, scales=scal, rotations=rot,
         cov3D_precomp=None)
-    return {"render": color, "radii": radii}
+    return {"render": color, "radii": radii, "viewspace_points": ssp, "visibility_filter": radii > 0}
 
 
 def run(variant, steps=20, warm=5):
@@ -105,6 +109,14 @@ def run(variant, steps=20, warm=5):
         out = model.render(cam, pc, pipe, bg) if variant == "fused" else render_torch(pc)
         loss = photometric_loss(out["render"], gt, 0.2)
         loss.backward()
+        # reference train.py:190-193 (every iteration while iteration < densify_until_iter = the whole default run)
+        if variant == "fused":
+            model.add_densification_stats(pc, out["viewspace_points"], None, out["radii"])
+        else:
+            vis, radii = out["visibility_filter"], out["radii"]
+            pc.max_radii2D[vis] = torch.max(pc.max_radii2D[vis], radii[vis])
+            pc.xyz_gradient_accum[vis] += torch.norm(out["viewspace_points"].grad[vis, :2], dim=-1, keepdim=True)
+            pc.denom[vis] += 1
         if variant == "fused":
             optim.step_all(oa, ob)
         else:
