@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SCGR_VERSION 106   /* major*10000 + minor*100 + patch */
+#define SCGR_VERSION 107   /* major*10000 + minor*100 + patch */
 #define SCGR_TILE 16        /* BLOCK_X = BLOCK_Y of the external rasterizer's config.h */
 
 typedef void* scgr_stream_t;   /* cudaStream_t */
@@ -269,6 +269,23 @@ typedef struct ScgrAdamGroup {
 } ScgrAdamGroup;
 int scgr_adam_step(const ScgrAdamGroup* groups, int32_t n_groups, double beta1, double beta2, double eps,
                    scgr_stream_t stream);
+
+/* ---- SURVEY.md section 8(f) row f4, second half: prune compaction ----
+ * reference scene/gaussian_model.py:777-820 (`_prune_optimizer`, `prune_points`) evaluates `t[valid_points_mask]` on
+ * every per-Gaussian array of the model -- 12 parameters, their exp_avg / exp_avg_sq, _rayo, _rayd,
+ * xyz_gradient_accum, denom, max_radii2D -- each a nonzero + host synchronisation + gather.  Here: ONE launch for
+ * all arrays from one index list:  dst[a][j, 0:row_floats] = src[a][index[j], 0:row_floats],  j < n_out.
+ * `index` is a device int64 array (what torch.nonzero returns); rows are fp32 (int / bool state is compacted by the
+ * host side).  src and dst must not overlap.  n_out * row_floats < 2^40 per array; arrays with row_floats == 0 are
+ * skipped. */
+#define SCGR_GATHER_MAX_ARRAYS 48
+typedef struct ScgrRowGather {
+    const float* src;
+    float* dst;
+    int32_t row_floats;
+} ScgrRowGather;
+int scgr_gather_rows(const ScgrRowGather* arrays, int32_t n_arrays, const int64_t* index, int64_t n_out,
+                     scgr_stream_t stream);
 
 /* Launch accounting and per-kernel timing (the reference has no tracing at all, SURVEY.md section 5;
  * bench.py uses this for the live roofline numbers).  scgr_kernel_launch_count(): kernels this

@@ -75,6 +75,11 @@ class ScgrAdamGroup(C.Structure):
                 ("n", C.c_int64), ("lr", C.c_float), ("step", C.c_int32)]
 
 
+class ScgrRowGather(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("row_floats", C.c_int32)]
+
+
+GATHER_MAX_ARRAYS = 48   # SCGR_GATHER_MAX_ARRAYS (include/scgr.h)
 ADAM_MAX_GROUPS = 16   # SCGR_ADAM_MAX_GROUPS (include/scgr.h)
 
 # every symbol include/scgr.h declares: (restype, argtypes)
@@ -107,6 +112,7 @@ SYMBOLS = {
                                          C.POINTER(ScgrModelGrads), C.c_void_p]),
     "scgr_densification_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p]),
+    "scgr_gather_rows": (C.c_int, [C.POINTER(ScgrRowGather), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "scgr_adam_step": (C.c_int, [C.POINTER(ScgrAdamGroup), C.c_int32, C.c_double, C.c_double, C.c_double,
                                  C.c_void_p]),
     "scgr_mark_visible": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -475,6 +475,24 @@ int scgr_densification_stats(const float* dL_dmeans2D, const uint8_t* update_fil
     });
 }
 
+int scgr_gather_rows(const ScgrRowGather* arrays, int32_t n_arrays, const int64_t* index, int64_t n_out,
+                     scgr_stream_t stream) {
+    return guarded([&] {
+        require(n_arrays >= 0 && n_arrays <= SCGR_GATHER_MAX_ARRAYS, "gather_rows: 0..SCGR_GATHER_MAX_ARRAYS arrays per call");
+        require(n_out >= 0 && n_out < (int64_t(1) << 31), "gather_rows: n_out must be in [0, 2^31)");
+        if (n_arrays == 0 || n_out == 0) return;
+        require(arrays && index, "gather_rows: null argument");
+        for (int a = 0; a < n_arrays; a++) {
+            require(arrays[a].row_floats >= 0 && arrays[a].row_floats <= 65536, "gather_rows: row_floats out of range");
+            if (arrays[a].row_floats == 0) continue;
+            require(arrays[a].src && arrays[a].dst, "gather_rows: null array");
+            require(n_out * (int64_t)arrays[a].row_floats < (int64_t(1) << 40), "gather_rows: array too large");
+        }
+        const Launch L{(cudaStream_t)stream, false};
+        launch_gather_rows(arrays, n_arrays, index, n_out, L);
+    });
+}
+
 int scgr_adam_step(const ScgrAdamGroup* groups, int32_t n_groups, double beta1, double beta2, double eps,
                    scgr_stream_t stream) {
     return guarded([&] {

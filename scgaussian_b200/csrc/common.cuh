@@ -287,6 +287,8 @@ void launch_assemble_backward(const ScgrModel& m, const ScgrActivatedGrads& g, c
                               const Launch& L);
 void launch_adam(const ScgrAdamGroup* groups, int32_t n_groups, double beta1, double beta2, double eps,
                  const Launch& L);
+void launch_gather_rows(const ScgrRowGather* arrays, int32_t n_arrays, const int64_t* index, int64_t n_out,
+                        const Launch& L);
 void launch_densification_stats(const float* dL_dmeans2D, const uint8_t* update_filter, const int32_t* radii, int32_t P,
                                 float* xyz_gradient_accum, float* denom, float* max_radii2D, const Launch& L);
 

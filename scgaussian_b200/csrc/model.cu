@@ -310,6 +310,52 @@ adam_kernel(const __grid_constant__ AdamTable t) {
     }
 }
 
+// ---- prune compaction (reference scene/gaussian_model.py:777-820 `_prune_optimizer` / `prune_points`; SURVEY.md section
+// 8f row f4): dst[a][j, :] = src[a][index[j], :] for EVERY per-Gaussian array a of the model -- the 12 parameters, their
+// exp_avg / exp_avg_sq, the ray geometry and the densification statistics -- in one launch from one index list, where
+// the reference evaluates `t[mask]` (a nonzero + host synchronisation + gather) ~45 times.  Flat over the output floats
+// of each array: coalesced stores, loads coalesced within a row.
+constexpr int GATHER_PER_THREAD = 8;
+constexpr int GATHER_PER_BLOCK = MODEL_THREADS * GATHER_PER_THREAD;
+
+struct GatherSeg {
+    const float* src;
+    float* dst;
+    uint32_t row;           // floats per row
+    uint32_t first_block;
+};
+struct GatherTable {
+    GatherSeg seg[SCGR_GATHER_MAX_ARRAYS];
+    int n_seg;
+};
+
+__global__ void __launch_bounds__(MODEL_THREADS)
+gather_rows_kernel(const __grid_constant__ GatherTable t, const int64_t* __restrict__ index, const uint32_t n_out) {
+    const float* src = t.seg[0].src; float* dst = t.seg[0].dst;
+    uint32_t row = t.seg[0].row, first = 0;
+#pragma unroll
+    for (int k = 1; k < SCGR_GATHER_MAX_ARRAYS; k++) {
+        if (k < t.n_seg && blockIdx.x >= t.seg[k].first_block) {
+            src = t.seg[k].src; dst = t.seg[k].dst; row = t.seg[k].row; first = t.seg[k].first_block;
+        }
+    }
+    const uint64_t total = (uint64_t)n_out * row;
+    const uint64_t e = (uint64_t)(blockIdx.x - first) * GATHER_PER_BLOCK + threadIdx.x;
+    uint32_t j = (uint32_t)(e / row), c = (uint32_t)(e - (uint64_t)j * row);
+    const uint32_t step_j = MODEL_THREADS / row, step_c = MODEL_THREADS - step_j * row;
+    float v[GATHER_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < GATHER_PER_THREAD; u++) {
+        v[u] = 0.f;
+        if (e + (uint64_t)u * MODEL_THREADS < total) v[u] = __ldg(src + (size_t)__ldg(index + j) * row + c);
+        c += step_c; j += step_j;
+        if (c >= row) { c -= row; j++; }
+    }
+#pragma unroll
+    for (int u = 0; u < GATHER_PER_THREAD; u++)
+        if (e + (uint64_t)u * MODEL_THREADS < total) dst[e + (uint64_t)u * MODEL_THREADS] = v[u];
+}
+
 uint32_t sh_block_count(uint64_t sh_total) { return (uint32_t)((sh_total + SH_PER_BLOCK - 1) / SH_PER_BLOCK); }
 
 }  // namespace
@@ -346,6 +392,26 @@ void launch_densification_stats(const float* dL_dmeans2D, const uint8_t* update_
     densification_stats_kernel<<<(P + MODEL_THREADS - 1) / MODEL_THREADS, MODEL_THREADS, 0, L.stream>>>(
         dL_dmeans2D, update_filter, radii, P, xyz_gradient_accum, denom, max_radii2D);
     check_launch("densification_stats", L);
+}
+
+void launch_gather_rows(const ScgrRowGather* arrays, int32_t n_arrays, const int64_t* index, int64_t n_out,
+                        const Launch& L) {
+    GatherTable t{};
+    uint64_t blocks = 0;
+    int k = 0;
+    for (int a = 0; a < n_arrays; a++) {
+        if (arrays[a].row_floats == 0) continue;
+        GatherSeg& s = t.seg[k++];
+        s.src = arrays[a].src; s.dst = arrays[a].dst;
+        s.row = (uint32_t)arrays[a].row_floats;
+        s.first_block = (uint32_t)blocks;
+        blocks += ((uint64_t)n_out * s.row + GATHER_PER_BLOCK - 1) / GATHER_PER_BLOCK;
+    }
+    if (k == 0 || n_out == 0) return;
+    t.n_seg = k;
+    begin_kernel("gather_rows", L);
+    gather_rows_kernel<<<(uint32_t)blocks, MODEL_THREADS, 0, L.stream>>>(t, index, (uint32_t)n_out);
+    check_launch("gather_rows", L);
 }
 
 void launch_adam(const ScgrAdamGroup* groups, int32_t n_groups, double beta1, double beta2, double eps,

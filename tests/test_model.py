@@ -455,3 +455,76 @@ def test_densification_stats_match_reference_golden_and_oracle():
     wa, wd, _ = MO.densification_stats(grad, radii > 7, None, accum, denom, maxr)
     assert np.array_equal(pc.denom.cpu().numpy(), wd) and _rel(pc.xyz_gradient_accum.cpu().numpy(), wa) < 1e-6
     assert np.array_equal(pc.max_radii2D.cpu().numpy(), maxr)
+
+
+@pytest.mark.gpu
+def test_prune_points_matches_torch_indexing():
+    """scgaussian_b200.densify.prune_points (reference scene/gaussian_model.py:777-820) on the GPU: every per-Gaussian
+    array equals `t[valid_mask]` (what the reference evaluates) bit for bit, in 3 launches."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from scgaussian_b200 import _lib, densify, optim
+    gen = torch.Generator().manual_seed(13)
+    n_ray, n_bg, K = 20011, 9973, 16
+    P = n_ray + n_bg
+
+    def rnd(*s):
+        return torch.randn(*s, generator=gen).cuda()
+    pc = _Stats()
+    par = torch.nn.Parameter
+    pc._rayo, pc._rayd, pc._zval = rnd(n_ray, 3), rnd(n_ray, 3), par(rnd(n_ray, 1))
+    pc._features_dc, pc._features_rest = par(rnd(n_ray, 1, 3)), par(rnd(n_ray, K - 1, 3))
+    pc._scaling, pc._rotation, pc._opacity = par(rnd(n_ray, 3)), par(rnd(n_ray, 4)), par(rnd(n_ray, 1))
+    pc.bg_xyz, pc.bg_features_dc, pc.bg_features_rest = par(rnd(n_bg, 3)), par(rnd(n_bg, 1, 3)), par(rnd(n_bg, K - 1, 3))
+    pc.bg_scaling, pc.bg_rotation, pc.bg_opacity = par(rnd(n_bg, 3)), par(rnd(n_bg, 4)), par(rnd(n_bg, 1))
+    inv = {v: k for k, v in densify.GROUP_ATTR.items()}
+    main = [a for a in densify.GROUP_ATTR.values() if a.startswith("_")]
+    free = [a for a in densify.GROUP_ATTR.values() if a.startswith("bg_")]
+    pc.optimizer = optim.Adam([{"params": [getattr(pc, a)], "lr": 1e-3, "name": inv[a]} for a in main], lr=0.0, eps=1e-15)
+    pc.optimizer_bg = torch.optim.Adam([{"params": [getattr(pc, a)], "lr": 1e-3, "name": inv[a]} for a in free],
+                                       lr=0.0, eps=1e-15)          # torch's optimizer works as well
+    for a in main + free:
+        getattr(pc, a).grad = rnd(*getattr(pc, a).shape)
+    pc.optimizer.step()
+    pc.optimizer_bg.step()
+    pc.xyz_gradient_accum, pc.denom, pc.max_radii2D = rnd(P, 1), rnd(P, 1).abs(), rnd(P).abs()
+    mask = (torch.rand(P, generator=gen) < 0.3).cuda()
+    mask[:5] = True
+    valid = ~mask
+    want = {a: getattr(pc, a).detach()[valid[:n_ray]] for a in main + ["_rayo", "_rayd"]}
+    want.update({a: getattr(pc, a).detach()[valid[n_ray:]] for a in free})
+    want.update({a: getattr(pc, a)[valid] for a in ("xyz_gradient_accum", "denom", "max_radii2D")})
+    want_state = {}
+    for opt, names, v in ((pc.optimizer, main, valid[:n_ray]), (pc.optimizer_bg, free, valid[n_ray:])):
+        for a in names:
+            st = opt.state[getattr(pc, a)]
+            want_state[a] = (st["exp_avg"][v], st["exp_avg_sq"][v])
+    lib = _lib.load()
+    before = lib.scgr_kernel_launch_count()
+    densify.prune_points(pc, mask)
+    assert lib.scgr_kernel_launch_count() - before == 3
+    for a, w in want.items():
+        got = getattr(pc, a)
+        assert got.shape == w.shape and torch.equal(got.detach(), w), a
+    for opt, names in ((pc.optimizer, main), (pc.optimizer_bg, free)):
+        for grp in opt.param_groups:
+            a = densify.GROUP_ATTR[grp["name"]]
+            p = grp["params"][0]
+            assert p is getattr(pc, a) and isinstance(p, torch.nn.Parameter) and p.requires_grad
+            st = opt.state[p]
+            assert torch.equal(st["exp_avg"], want_state[a][0]) and torch.equal(st["exp_avg_sq"], want_state[a][1]), a
+            assert float(st["step"]) == 1.0
+        assert len(opt.state) == 6
+    # the pruned model keeps training: one more step on both optimizers
+    for a in main + free:
+        getattr(pc, a).grad = torch.ones_like(getattr(pc, a))
+    pc.optimizer.step()
+    pc.optimizer_bg.step()
+    assert float(pc.optimizer.state[pc._zval]["step"]) == 2.0
+    # nothing pruned / everything of one set pruned
+    densify.prune_points(pc, torch.zeros(pc._zval.shape[0] + pc.bg_xyz.shape[0], dtype=torch.bool, device="cuda"))
+    assert pc._zval.shape[0] == int(valid[:n_ray].sum())
+    m2 = torch.zeros(pc._zval.shape[0] + pc.bg_xyz.shape[0], dtype=torch.bool, device="cuda")
+    m2[pc._zval.shape[0]:] = True
+    densify.prune_points(pc, m2)
+    assert pc.bg_xyz.shape == (0, 3) and pc.bg_features_rest.shape == (0, K - 1, 3) and pc.max_radii2D.shape[0] == pc._zval.shape[0]

@@ -203,3 +203,87 @@ def test_reference_optimizer_surgery_runs_on_the_fused_adam(reference_renderer):
     for name in ("zval", "opacity"):
         assert torch.equal(results[0][name][0], results[1][name][0])
         assert torch.equal(results[0][name][1], results[1][name][1])
+
+
+def test_prune_points_mirror_matches_the_reference_method(reference_renderer, monkeypatch):
+    """scgaussian_b200.densify.prune_points against the reference's own
+    `GaussianModel.prune_points` (scene/gaussian_model.py:795-820), both on the same CPU model built by the reference's
+    `training_setup`.  HOST LOGIC ONLY: there is no GPU here and the product has no CPU path, so for this one test the
+    C entry point is replaced by a numpy test double that honours the same ScgrRowGather table (the real kernel is
+    compared with torch indexing on the GPU: tests/test_model.py::test_prune_points_matches_torch_indexing)."""
+    import argparse
+    import contextlib
+    import ctypes as C
+    import types
+    import numpy as np
+    from scene.gaussian_model import GaussianModel
+    from arguments import OptimizationParams
+    from scgaussian_b200 import densify, optim
+
+    class FakeLib:
+        calls = 0
+
+        def scgr_gather_rows(self, table, n_arrays, index_ptr, n_out, stream):
+            FakeLib.calls += 1
+            idx = np.ctypeslib.as_array((C.c_int64 * n_out).from_address(index_ptr))
+            for a in range(n_arrays):
+                row = table[a].row_floats
+                src = np.ctypeslib.as_array((C.c_float * ((int(idx.max()) + 1) * row)).from_address(table[a].src)).reshape(-1, row)
+                dst = np.ctypeslib.as_array((C.c_float * (n_out * row)).from_address(table[a].dst)).reshape(-1, row)
+                dst[:] = src[idx]
+            return 0
+
+    monkeypatch.setattr(densify._lib, "load", lambda: FakeLib())
+    monkeypatch.setattr(densify, "_require_cuda", lambda device, what: None)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: types.SimpleNamespace(cuda_stream=0))
+    real_zeros = torch.zeros
+    monkeypatch.setattr(torch, "zeros", lambda *a, **k: real_zeros(*a, **{kk: vv for kk, vv in k.items() if kk != "device"}))
+
+    def build(adam_cls):
+        g = torch.Generator().manual_seed(21)
+        n_ray, n_bg, K = 9, 6, 16
+        pc = GaussianModel(3)
+        P = torch.nn.Parameter
+        rnd = lambda *s: torch.randn(*s, generator=g)     # noqa: E731
+        pc._rayo, pc._rayd, pc._zval = rnd(n_ray, 3), rnd(n_ray, 3), P(rnd(n_ray, 1))
+        pc._features_dc, pc._features_rest = P(rnd(n_ray, 1, 3)), P(rnd(n_ray, K - 1, 3))
+        pc._scaling, pc._rotation, pc._opacity = P(rnd(n_ray, 3)), P(rnd(n_ray, 4)), P(rnd(n_ray, 1))
+        pc.bg_xyz, pc.bg_features_dc, pc.bg_features_rest = P(rnd(n_bg, 3)), P(rnd(n_bg, 1, 3)), P(rnd(n_bg, K - 1, 3))
+        pc.bg_scaling, pc.bg_rotation, pc.bg_opacity = P(rnd(n_bg, 3)), P(rnd(n_bg, 4)), P(rnd(n_bg, 1))
+        pc.spatial_lr_scale = 1.0
+        pc.training_setup(OptimizationParams(argparse.ArgumentParser()))       # reference :486-512
+        if adam_cls is not None:                                                # same groups on the fused optimizer
+            pc.optimizer = adam_cls(pc.optimizer.param_groups, lr=0.0, eps=1e-15)
+            pc.optimizer_bg = adam_cls(pc.optimizer_bg.param_groups, lr=0.0, eps=1e-15)
+        for opt in (pc.optimizer, pc.optimizer_bg):                             # moments as after some steps
+            for grp in opt.param_groups:
+                p = grp["params"][0]
+                if grp["name"] != "f_rest":                                     # one group without state (:790-792)
+                    opt.state[p] = {"step": torch.tensor(3.0), "exp_avg": rnd(*p.shape), "exp_avg_sq": rnd(*p.shape).abs()}
+        pc.xyz_gradient_accum, pc.denom = rnd(n_ray + n_bg, 1), rnd(n_ray + n_bg, 1).abs()
+        pc.max_radii2D = rnd(n_ray + n_bg).abs()
+        return pc
+
+    mask = torch.tensor([0, 1, 0, 0, 0, 1, 0, 0, 1, 0, 0, 1, 1, 0, 0], dtype=torch.bool)
+    ref = build(None)
+    ref.prune_points(mask.clone())                                              # the reference's own method
+    ours = build(optim.Adam)
+    densify.prune_points(ours, mask.clone())
+    assert FakeLib.calls == 3                                                   # ray set, free set, statistics
+    attrs = ["_rayo", "_rayd", "xyz_gradient_accum", "denom", "max_radii2D"] + list(densify.GROUP_ATTR.values())
+    for a in attrs:
+        x, y = getattr(ours, a), getattr(ref, a)
+        assert x.shape == y.shape and torch.equal(x.detach(), y.detach()), a
+    for o_opt, r_opt in ((ours.optimizer, ref.optimizer), (ours.optimizer_bg, ref.optimizer_bg)):
+        for og, rg in zip(o_opt.param_groups, r_opt.param_groups):
+            assert og["name"] == rg["name"] and og["lr"] == rg["lr"]
+            op, rp = og["params"][0], rg["params"][0]
+            assert isinstance(op, torch.nn.Parameter) and op.requires_grad
+            assert getattr(ours, densify.GROUP_ATTR[og["name"]]) is op           # the model holds the optimizer's tensor
+            assert (op in o_opt.state) == (rp in r_opt.state), og["name"]
+            if rp in r_opt.state:
+                for k in ("exp_avg", "exp_avg_sq"):
+                    assert torch.equal(o_opt.state[op][k], r_opt.state[rp][k]), (og["name"], k)
+                assert float(o_opt.state[op]["step"]) == 3.0
+        assert len(o_opt.state) == len(r_opt.state)
