@@ -15,6 +15,8 @@
 //      iteration (reference scene/gaussian_model.py:491-510, train.py:204-208), all parameter groups of
 //      both optimizers in ONE launch; per element 16 B read (param, grad, exp_avg, exp_avg_sq) + 12 B
 //      written = 28 B.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace scgr {
@@ -64,10 +66,92 @@ __device__ __forceinline__ float load_sh(const ScgrModel& m, const uint32_t i, c
     return k < 3 ? __ldg(dc + (size_t)ii * 3 + k) : __ldg(rest + (size_t)ii * (n3k - 3) + (k - 3));
 }
 
+// ---- the SH copy staged through shared memory (K = 16 or 4 coefficients: rows of 48 / 12 floats, a multiple of 16 bytes).
+// A CTA owns 64 Gaussians of ONE set: their features_rest rows are one contiguous run of the source and their SH rows
+// one contiguous, 16-byte aligned run of the assembled array.  The interleaved side (dc | rest, rows of 3 / N3K-3
+// floats, no 16-byte alignment) is walked one float per lane on consecutive addresses; the assembled side moves as
+// float4; shared memory converts between the two (both sides of it conflict-free: consecutive lanes on consecutive words).
+constexpr int STAGE_G = 64;
+
+template <int N3K>
+__device__ __forceinline__ void staged_sh_forward(const ScgrModel& m, float* __restrict__ shs, const uint32_t blocks0) {
+    constexpr int REST = N3K - 3;
+    constexpr int REST_ITERS = (STAGE_G * REST + MODEL_THREADS - 1) / MODEL_THREADS;
+    constexpr int OUT_ITERS = (STAGE_G * N3K / 4 + MODEL_THREADS - 1) / MODEL_THREADS;
+    __shared__ __align__(16) float s[STAGE_G * N3K];
+    const bool first = blockIdx.x < blocks0;
+    const uint32_t n = (uint32_t)(first ? m.set[0].n : m.set[1].n);
+    const uint32_t ii0 = (first ? blockIdx.x : blockIdx.x - blocks0) * STAGE_G;
+    const uint32_t cnt = min((uint32_t)STAGE_G, n - ii0);
+    const float* dc = (first ? m.set[0].features_dc : m.set[1].features_dc) + (size_t)ii0 * 3;
+    const float* rest = (first ? m.set[0].features_rest : m.set[1].features_rest) + (size_t)ii0 * REST;
+    float* out = shs + ((size_t)(first ? 0 : m.set[0].n) + ii0) * N3K;
+    float v[REST_ITERS];
+#pragma unroll
+    for (int u = 0; u < REST_ITERS; u++) {
+        const uint32_t r = u * MODEL_THREADS + threadIdx.x;
+        v[u] = r < cnt * REST ? __ldg(rest + r) : 0.f;
+    }
+    const float d = threadIdx.x < cnt * 3 ? __ldg(dc + threadIdx.x) : 0.f;
+#pragma unroll
+    for (int u = 0; u < REST_ITERS; u++) {
+        const uint32_t r = u * MODEL_THREADS + threadIdx.x;
+        if (r < cnt * REST) { const uint32_t gi = r / REST; s[gi * N3K + 3 + (r - gi * REST)] = v[u]; }
+    }
+    if (threadIdx.x < cnt * 3) { const uint32_t gi = threadIdx.x / 3; s[gi * N3K + (threadIdx.x - gi * 3)] = d; }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < OUT_ITERS; u++) {
+        const uint32_t q = u * MODEL_THREADS + threadIdx.x;
+        if (q < cnt * (N3K / 4)) reinterpret_cast<float4*>(out)[q] = reinterpret_cast<const float4*>(s)[q];
+    }
+}
+
+template <int N3K>
+__device__ __forceinline__ void staged_sh_backward(const ScgrModel& m, const float* __restrict__ dL_dshs,
+                                                   const ScgrModelGrads& g, const uint32_t blocks0) {
+    constexpr int REST = N3K - 3;
+    constexpr int REST_ITERS = (STAGE_G * REST + MODEL_THREADS - 1) / MODEL_THREADS;
+    constexpr int IN_ITERS = (STAGE_G * N3K / 4 + MODEL_THREADS - 1) / MODEL_THREADS;
+    __shared__ __align__(16) float s[STAGE_G * N3K];
+    const bool first = blockIdx.x < blocks0;
+    const uint32_t n = (uint32_t)(first ? m.set[0].n : m.set[1].n);
+    const uint32_t ii0 = (first ? blockIdx.x : blockIdx.x - blocks0) * STAGE_G;
+    const uint32_t cnt = min((uint32_t)STAGE_G, n - ii0);
+    float* dc = (first ? g.set[0].dL_dfeatures_dc : g.set[1].dL_dfeatures_dc) + (size_t)ii0 * 3;
+    float* rest = (first ? g.set[0].dL_dfeatures_rest : g.set[1].dL_dfeatures_rest) + (size_t)ii0 * REST;
+    const float* in = dL_dshs + ((size_t)(first ? 0 : m.set[0].n) + ii0) * N3K;
+    float4 v[IN_ITERS];
+#pragma unroll
+    for (int u = 0; u < IN_ITERS; u++) {
+        const uint32_t q = u * MODEL_THREADS + threadIdx.x;
+        v[u] = q < cnt * (N3K / 4) ? __ldg(reinterpret_cast<const float4*>(in) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < IN_ITERS; u++) {
+        const uint32_t q = u * MODEL_THREADS + threadIdx.x;
+        if (q < cnt * (N3K / 4)) reinterpret_cast<float4*>(s)[q] = v[u];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < REST_ITERS; u++) {
+        const uint32_t r = u * MODEL_THREADS + threadIdx.x;
+        if (r < cnt * REST) { const uint32_t gi = r / REST; rest[r] = s[gi * N3K + 3 + (r - gi * REST)]; }
+    }
+    if (threadIdx.x < cnt * 3) { const uint32_t gi = threadIdx.x / 3; dc[threadIdx.x] = s[gi * N3K + (threadIdx.x - gi * 3)]; }
+}
+
+template <int STAGED>      // 0: flat copy for any K; 48 / 12: staged_sh_* above
 __global__ void __launch_bounds__(MODEL_THREADS)
 assemble_forward_kernel(const __grid_constant__ ScgrModel m, const __grid_constant__ ScgrActivated o,
                         const uint32_t sh_blocks, const uint32_t n3k, const uint32_t sh_total) {
     const uint32_t step_i = MODEL_THREADS / n3k, step_k = MODEL_THREADS - step_i * n3k;   // (i, k) of element e + 256
+    if constexpr (STAGED != 0) {
+        if (blockIdx.x < sh_blocks) {       // get_features (reference scene/gaussian_model.py:131-140)
+            staged_sh_forward<STAGED>(m, o.shs, ((uint32_t)m.set[0].n + STAGE_G - 1) / STAGE_G);
+            return;
+        }
+    }
     if (blockIdx.x < sh_blocks) {
         // ---- get_features (reference scene/gaussian_model.py:131-140): flat over the P*K*3 output floats; consecutive
         // lanes read consecutive source floats and write consecutive output floats (the [n,K-1,3] source rows are 4
@@ -124,12 +208,19 @@ assemble_forward_kernel(const __grid_constant__ ScgrModel m, const __grid_consta
     o.opacities[i] = sigmoid_f(__ldg(s.opacity + ii));
 }
 
+template <int STAGED>
 __global__ void __launch_bounds__(MODEL_THREADS)
 assemble_backward_kernel(const __grid_constant__ ScgrModel m, const __grid_constant__ ScgrActivatedGrads g,
                          const __grid_constant__ ScgrModelGrads out, const uint32_t sh_blocks, const uint32_t n3k,
                          const uint32_t sh_total) {
     const uint32_t n0 = (uint32_t)m.set[0].n;
     const uint32_t step_i = MODEL_THREADS / n3k, step_k = MODEL_THREADS - step_i * n3k;   // (i, k) of element e + 256
+    if constexpr (STAGED != 0) {
+        if (blockIdx.x < sh_blocks) {
+            staged_sh_backward<STAGED>(m, g.dL_dshs, out, (n0 + STAGE_G - 1) / STAGE_G);
+            return;
+        }
+    }
     if (blockIdx.x < sh_blocks) {
         // ---- dL/dshs [P,K,3] split into dL/dfeatures_dc [n,1,3] and dL/dfeatures_rest [n,K-1,3] of the two sets:
         // the mirror image of the forward copy, coalesced 4-byte accesses on both sides
@@ -360,15 +451,28 @@ uint32_t sh_block_count(uint64_t sh_total) { return (uint32_t)((sh_total + SH_PE
 
 }  // namespace
 
+// SCGR_ASSEMBLE_STAGED=0 keeps the flat copy for every K (A/B switch)
+static int staged_rows(uint32_t n3k) {
+    static const bool off = getenv("SCGR_ASSEMBLE_STAGED") && atoi(getenv("SCGR_ASSEMBLE_STAGED")) == 0;
+    return (!off && (n3k == 48 || n3k == 12)) ? (int)n3k : 0;
+}
+
 void launch_assemble_forward(const ScgrModel& m, const ScgrActivated& out, const Launch& L) {
     const uint64_t P = (uint64_t)m.set[0].n + (uint64_t)m.set[1].n;
     if (P == 0) return;
     const uint32_t n3k = 3u * (uint32_t)(m.sh_rest + 1);
     const uint64_t sh_total = P * n3k;
-    const uint32_t sh_blocks = sh_block_count(sh_total);
+    const int staged = staged_rows(n3k);
+    const uint32_t sh_blocks = staged ? (uint32_t)((m.set[0].n + STAGE_G - 1) / STAGE_G + (m.set[1].n + STAGE_G - 1) / STAGE_G)
+                                      : sh_block_count(sh_total);
     const uint32_t blocks = sh_blocks + (uint32_t)((P + MODEL_THREADS - 1) / MODEL_THREADS);
     begin_kernel("assemble_forward", L);
-    assemble_forward_kernel<<<blocks, MODEL_THREADS, 0, L.stream>>>(m, out, sh_blocks, n3k, (uint32_t)sh_total);
+    if (staged == 48)
+        assemble_forward_kernel<48><<<blocks, MODEL_THREADS, 0, L.stream>>>(m, out, sh_blocks, n3k, (uint32_t)sh_total);
+    else if (staged == 12)
+        assemble_forward_kernel<12><<<blocks, MODEL_THREADS, 0, L.stream>>>(m, out, sh_blocks, n3k, (uint32_t)sh_total);
+    else
+        assemble_forward_kernel<0><<<blocks, MODEL_THREADS, 0, L.stream>>>(m, out, sh_blocks, n3k, (uint32_t)sh_total);
     check_launch("assemble_forward", L);
 }
 
@@ -378,10 +482,17 @@ void launch_assemble_backward(const ScgrModel& m, const ScgrActivatedGrads& g, c
     if (P == 0) return;
     const uint32_t n3k = 3u * (uint32_t)(m.sh_rest + 1);
     const uint64_t sh_total = P * n3k;
-    const uint32_t sh_blocks = sh_block_count(sh_total);
+    const int staged = staged_rows(n3k);
+    const uint32_t sh_blocks = staged ? (uint32_t)((m.set[0].n + STAGE_G - 1) / STAGE_G + (m.set[1].n + STAGE_G - 1) / STAGE_G)
+                                      : sh_block_count(sh_total);
     const uint32_t blocks = sh_blocks + (uint32_t)((P + MODEL_THREADS - 1) / MODEL_THREADS);
     begin_kernel("assemble_backward", L);
-    assemble_backward_kernel<<<blocks, MODEL_THREADS, 0, L.stream>>>(m, g, out, sh_blocks, n3k, (uint32_t)sh_total);
+    if (staged == 48)
+        assemble_backward_kernel<48><<<blocks, MODEL_THREADS, 0, L.stream>>>(m, g, out, sh_blocks, n3k, (uint32_t)sh_total);
+    else if (staged == 12)
+        assemble_backward_kernel<12><<<blocks, MODEL_THREADS, 0, L.stream>>>(m, g, out, sh_blocks, n3k, (uint32_t)sh_total);
+    else
+        assemble_backward_kernel<0><<<blocks, MODEL_THREADS, 0, L.stream>>>(m, g, out, sh_blocks, n3k, (uint32_t)sh_total);
     check_launch("assemble_backward", L);
 }
 

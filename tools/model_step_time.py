@@ -126,6 +126,7 @@ peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
 res["hbm_peak_gbs"] = peaks["hbm_gbs"]
 res["assemble_forward_frac"] = res["assemble_forward_gbs"] / peaks["hbm_gbs"]
 res["adam_fused_frac"] = res["adam_fused_gbs"] / peaks["hbm_gbs"]
-print(json.dumps(res))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(res, open(os.path.join(ROOT, "gpurun_out", "model_time.json"), "w"), indent=1)
+res["sh_copy"] = "flat" if os.environ.get("SCGR_ASSEMBLE_STAGED") == "0" else "staged"
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", os.environ.get("OUT", "model_time.json")), "w"), indent=1)
+print(json.dumps(res))
