@@ -434,6 +434,9 @@ emit_instances_kernel(const uint32_t* __restrict__ order, const uint32_t* __rest
         if (blockIdx.x == 0 && threadIdx.x == 0) status[1] = 1;
         return;
     }
+    // the flag describes THIS emission: a re-run with a large enough buffer (SCGR_NEED_CAPACITY / optimistic
+    // recovery, which skip stage 1 and its reset) clears what the refused attempt raised
+    if (blockIdx.x == 0 && threadIdx.x == 0) status[1] = 0;
 #pragma unroll
     for (int p = 0; p < PASSES; p++) s_hist[p][threadIdx.x] = 0u;
     __syncthreads();
