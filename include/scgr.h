@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SCGR_VERSION 107   /* major*10000 + minor*100 + patch */
+#define SCGR_VERSION 108   /* major*10000 + minor*100 + patch */
 #define SCGR_TILE 16        /* BLOCK_X = BLOCK_Y of the external rasterizer's config.h */
 
 typedef void* scgr_stream_t;   /* cudaStream_t */
@@ -286,6 +286,19 @@ typedef struct ScgrRowGather {
 } ScgrRowGather;
 int scgr_gather_rows(const ScgrRowGather* arrays, int32_t n_arrays, const int64_t* index, int64_t n_out,
                      scgr_stream_t stream);
+
+/* ---- SURVEY.md section 8(f) row f4, third part: densification append ----
+ * reference scene/gaussian_model.py:822-862 (`cat_tensors_to_optimizer`, `densification_postfix`) appends the new
+ * Gaussians to the 6 parameter groups of the free set, extends exp_avg / exp_avg_sq with zeros and resets the
+ * statistics: 18 torch.cat + 15 zero fills.  Here: ONE launch over flat segments, dst[0:n_floats] = src[0:n_floats]
+ * (src == NULL: zeros).  Segments must not overlap; n_floats < 2^40; empty segments are skipped. */
+#define SCGR_COPY_MAX_SEGMENTS 48
+typedef struct ScgrSegmentCopy {
+    float* dst;
+    const float* src;
+    int64_t n_floats;
+} ScgrSegmentCopy;
+int scgr_copy_segments(const ScgrSegmentCopy* segments, int32_t n_segments, scgr_stream_t stream);
 
 /* Launch accounting and per-kernel timing (the reference has no tracing at all, SURVEY.md section 5;
  * bench.py uses this for the live roofline numbers).  scgr_kernel_launch_count(): kernels this

@@ -79,6 +79,11 @@ class ScgrRowGather(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("row_floats", C.c_int32)]
 
 
+class ScgrSegmentCopy(C.Structure):
+    _fields_ = [("dst", C.c_void_p), ("src", C.c_void_p), ("n_floats", C.c_int64)]
+
+
+COPY_MAX_SEGMENTS = 48   # SCGR_COPY_MAX_SEGMENTS (include/scgr.h)
 GATHER_MAX_ARRAYS = 48   # SCGR_GATHER_MAX_ARRAYS (include/scgr.h)
 ADAM_MAX_GROUPS = 16   # SCGR_ADAM_MAX_GROUPS (include/scgr.h)
 
@@ -113,6 +118,7 @@ SYMBOLS = {
     "scgr_densification_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p]),
     "scgr_gather_rows": (C.c_int, [C.POINTER(ScgrRowGather), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "scgr_copy_segments": (C.c_int, [C.POINTER(ScgrSegmentCopy), C.c_int32, C.c_void_p]),
     "scgr_adam_step": (C.c_int, [C.POINTER(ScgrAdamGroup), C.c_int32, C.c_double, C.c_double, C.c_double,
                                  C.c_void_p]),
     "scgr_mark_visible": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

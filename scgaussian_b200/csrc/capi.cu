@@ -493,6 +493,20 @@ int scgr_gather_rows(const ScgrRowGather* arrays, int32_t n_arrays, const int64_
     });
 }
 
+int scgr_copy_segments(const ScgrSegmentCopy* segments, int32_t n_segments, scgr_stream_t stream) {
+    return guarded([&] {
+        require(n_segments >= 0 && n_segments <= SCGR_COPY_MAX_SEGMENTS, "copy_segments: 0..SCGR_COPY_MAX_SEGMENTS segments per call");
+        if (n_segments == 0) return;
+        require(segments != nullptr, "copy_segments: null segment table");
+        for (int i = 0; i < n_segments; i++) {
+            require(segments[i].n_floats >= 0 && segments[i].n_floats < (int64_t(1) << 40), "copy_segments: segment size out of range");
+            require(segments[i].n_floats == 0 || segments[i].dst != nullptr, "copy_segments: null destination");
+        }
+        const Launch L{(cudaStream_t)stream, false};
+        launch_copy_segments(segments, n_segments, L);
+    });
+}
+
 int scgr_adam_step(const ScgrAdamGroup* groups, int32_t n_groups, double beta1, double beta2, double eps,
                    scgr_stream_t stream) {
     return guarded([&] {

@@ -289,6 +289,7 @@ void launch_adam(const ScgrAdamGroup* groups, int32_t n_groups, double beta1, do
                  const Launch& L);
 void launch_gather_rows(const ScgrRowGather* arrays, int32_t n_arrays, const int64_t* index, int64_t n_out,
                         const Launch& L);
+void launch_copy_segments(const ScgrSegmentCopy* segs, int32_t n_segs, const Launch& L);
 void launch_densification_stats(const float* dL_dmeans2D, const uint8_t* update_filter, const int32_t* radii, int32_t P,
                                 float* xyz_gradient_accum, float* denom, float* max_radii2D, const Launch& L);
 

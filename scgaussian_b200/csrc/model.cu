@@ -447,6 +447,55 @@ gather_rows_kernel(const __grid_constant__ GatherTable t, const int64_t* __restr
         if (e + (uint64_t)u * MODEL_THREADS < total) dst[e + (uint64_t)u * MODEL_THREADS] = v[u];
 }
 
+// ---- densification append (reference scene/gaussian_model.py:822-862 `cat_tensors_to_optimizer` /
+// `densification_postfix`): the new Gaussians are appended to the 6 parameter groups of
+// the free set, their moments are extended with zeros and the statistics are reset -- 18 torch.cat + 15 zero fills in
+// the reference.  Here: ONE launch over a table of flat segments {dst, src or NULL (= zeros), n}.
+constexpr int COPY_THREADS = 256;
+constexpr int COPY_CHUNK = COPY_THREADS * 4 * 4;     // floats per CTA: 4 float4 per thread
+
+struct CopySeg {
+    float* dst;
+    const float* src;
+    uint64_t n;
+    uint32_t first_block;
+};
+struct CopyTable {
+    CopySeg seg[SCGR_COPY_MAX_SEGMENTS];
+    int n_seg;
+};
+
+__global__ void __launch_bounds__(COPY_THREADS)
+copy_segments_kernel(const __grid_constant__ CopyTable t) {
+    float* dst = t.seg[0].dst; const float* src = t.seg[0].src;
+    uint64_t n = t.seg[0].n;
+    uint32_t first = 0;
+#pragma unroll
+    for (int k = 1; k < SCGR_COPY_MAX_SEGMENTS; k++) {
+        if (k < t.n_seg && blockIdx.x >= t.seg[k].first_block) {
+            dst = t.seg[k].dst; src = t.seg[k].src; n = t.seg[k].n; first = t.seg[k].first_block;
+        }
+    }
+    const uint64_t base = (uint64_t)(blockIdx.x - first) * COPY_CHUNK;
+    const bool aligned = ((((uintptr_t)dst) | ((uintptr_t)src)) & 15u) == 0;     // a NULL src counts as aligned
+    if (aligned && base + COPY_CHUNK <= n) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint64_t e = base + (uint64_t)(u * COPY_THREADS + threadIdx.x) * 4u;
+            v[u] = src ? __ldg(reinterpret_cast<const float4*>(src + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint64_t e = base + (uint64_t)(u * COPY_THREADS + threadIdx.x) * 4u;
+            *reinterpret_cast<float4*>(dst + e) = v[u];
+        }
+        return;
+    }
+    const uint64_t end = min(n, base + (uint64_t)COPY_CHUNK);
+    for (uint64_t e = base + threadIdx.x; e < end; e += COPY_THREADS) dst[e] = src ? __ldg(src + e) : 0.f;
+}
+
 uint32_t sh_block_count(uint64_t sh_total) { return (uint32_t)((sh_total + SH_PER_BLOCK - 1) / SH_PER_BLOCK); }
 
 }  // namespace
@@ -523,6 +572,25 @@ void launch_gather_rows(const ScgrRowGather* arrays, int32_t n_arrays, const int
     begin_kernel("gather_rows", L);
     gather_rows_kernel<<<(uint32_t)blocks, MODEL_THREADS, 0, L.stream>>>(t, index, (uint32_t)n_out);
     check_launch("gather_rows", L);
+}
+
+void launch_copy_segments(const ScgrSegmentCopy* segs, int32_t n_segs, const Launch& L) {
+    CopyTable t{};
+    uint64_t blocks = 0;
+    int k = 0;
+    for (int i = 0; i < n_segs; i++) {
+        if (segs[i].n_floats == 0) continue;
+        CopySeg& c = t.seg[k++];
+        c.dst = segs[i].dst; c.src = segs[i].src;
+        c.n = (uint64_t)segs[i].n_floats;
+        c.first_block = (uint32_t)blocks;
+        blocks += (c.n + COPY_CHUNK - 1) / COPY_CHUNK;
+    }
+    if (k == 0) return;
+    t.n_seg = k;
+    begin_kernel("copy_segments", L);
+    copy_segments_kernel<<<(uint32_t)blocks, COPY_THREADS, 0, L.stream>>>(t);
+    check_launch("copy_segments", L);
 }
 
 void launch_adam(const ScgrAdamGroup* groups, int32_t n_groups, double beta1, double beta2, double eps,

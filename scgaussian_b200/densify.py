@@ -6,8 +6,13 @@ The reference evaluates `t[valid_points_mask]` once per per-Gaussian array -- 12
 nonzero + host synchronisation + gather kernel.  Here the two masks (ray-based set, free set) are turned into index
 lists once, and every array that shares an index list is compacted by ONE launch (include/scgr.h: scgr_gather_rows).
 
-    from scgaussian_b200.densify import prune_points
+    from scgaussian_b200.densify import prune_points, densification_postfix
     prune_points(gaussians, prune_mask)          # instead of gaussians.prune_points(prune_mask)
+    densification_postfix(gaussians, new_xyz, new_features_dc, new_features_rest, new_opacities, new_scaling,
+                          new_rotation)          # instead of gaussians.densification_postfix(...): one launch
+
+The append side (reference :822-862 `cat_tensors_to_optimizer` / `densification_postfix`: 18 torch.cat + 15 zero
+fills) is one launch over flat segments (include/scgr.h: scgr_copy_segments).
 
 Same effect on the model: new `nn.Parameter`s in `optimizer.param_groups` (one parameter per named group), optimizer
 state re-keyed to them with compacted moments and the step count kept, model attributes replaced.  Works on
@@ -22,7 +27,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._lib import GATHER_MAX_ARRAYS, ScgrError, ScgrRowGather, check
+from ._lib import COPY_MAX_SEGMENTS, GATHER_MAX_ARRAYS, ScgrError, ScgrRowGather, ScgrSegmentCopy, check
 
 # optimizer group name -> model attribute (reference scene/gaussian_model.py:493-510 and :803-817)
 GROUP_ATTR = {"zval": "_zval", "f_dc": "_features_dc", "f_rest": "_features_rest", "opacity": "_opacity",
@@ -118,3 +123,80 @@ def prune_points(pc, mask: torch.Tensor) -> None:
         setattr(pc, GROUP_ATTR[name], t)
     pc.xyz_gradient_accum, pc.denom, pc.max_radii2D = gather_rows(
         [pc.xyz_gradient_accum, pc.denom, pc.max_radii2D], torch.cat([idx_ray, idx_bg + n_ray]))
+
+
+def _copy_segments(segments: List[Tuple[torch.Tensor, Optional[torch.Tensor]]], device) -> None:
+    """dst.flatten()[:] = src.flatten() (src None: zeros) for every pair, in one launch per 48 segments."""
+    lib = _lib.load()
+    table = []
+    for dst, src in segments:
+        if not dst.is_contiguous() or dst.dtype != torch.float32 or (src is not None and (
+                not src.is_contiguous() or src.dtype != torch.float32 or src.numel() != dst.numel())):
+            raise ScgrError("copy_segments: fp32 contiguous tensors of equal size expected")
+        if dst.numel():
+            table.append(ScgrSegmentCopy(dst.data_ptr(), None if src is None else src.data_ptr(), dst.numel()))
+    with torch.cuda.device(device):
+        stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        for i in range(0, len(table), COPY_MAX_SEGMENTS):
+            chunk = table[i:i + COPY_MAX_SEGMENTS]
+            check(lib.scgr_copy_segments((ScgrSegmentCopy * len(chunk))(*chunk), len(chunk), stream))
+
+
+def cat_tensors_to_optimizer(tensors_dict: Dict[str, torch.Tensor], optimizer,
+                             zeros: Optional[List[torch.Tensor]] = None) -> Dict[str, nn.Parameter]:
+    """reference scene/gaussian_model.py:822-842: every group's parameter extended with `tensors_dict[name]`, its
+    moments with zeros; `zeros` are extra tensors to clear in the same launch."""
+    device = optimizer.param_groups[0]["params"][0].device
+    _require_cuda(device, "cat_tensors_to_optimizer")
+    segments, jobs = [], []
+    for group in optimizer.param_groups:
+        if len(group["params"]) != 1:
+            raise ScgrError("cat_tensors_to_optimizer expects one parameter per group (reference scene/gaussian_model.py:824)")
+        old = group["params"][0]
+        ext = tensors_dict[group["name"]]
+        if ext.device != device or tuple(ext.shape[1:]) != tuple(old.shape[1:]):
+            raise ScgrError(f"cat_tensors_to_optimizer: extension of group {group['name']!r} does not match its parameter")
+        ext = ext.detach().to(torch.float32).contiguous()
+        n_old, n_new = int(old.shape[0]), int(ext.shape[0])
+        shape = (n_old + n_new,) + tuple(old.shape[1:])
+        st = optimizer.state.get(old, None)
+
+        def extended(src_old, src_new):
+            t = torch.empty(shape, dtype=torch.float32, device=device)
+            segments.append((t[:n_old], src_old.detach().contiguous()))
+            segments.append((t[n_old:], src_new))
+            return t
+        new_p = extended(old, ext)
+        moments = (extended(st["exp_avg"], None), extended(st["exp_avg_sq"], None)) if st is not None else None
+        jobs.append((group, old, st, new_p, moments))
+    for z in zeros or []:
+        segments.append((z, None))
+    _copy_segments(segments, device)
+    optimizable = {}
+    for group, old, st, new_p, moments in jobs:
+        new = nn.Parameter(new_p.requires_grad_(True))
+        if st is not None:
+            st["exp_avg"], st["exp_avg_sq"] = moments
+            del optimizer.state[old]
+            optimizer.state[new] = st
+        group["params"][0] = new
+        optimizable[group["name"]] = new
+    return optimizable
+
+
+def densification_postfix(pc, new_xyz, new_features_dc, new_features_rest, new_opacities, new_scaling,
+                          new_rotation) -> None:
+    """reference scene/gaussian_model.py:844-862: the new Gaussians join the free set (`pc.optimizer_bg`) and the
+    densification statistics restart from zero."""
+    d = {"bg_xyz": new_xyz, "bg_f_dc": new_features_dc, "bg_f_rest": new_features_rest, "bg_opacity": new_opacities,
+         "bg_scaling": new_scaling, "bg_rotation": new_rotation}
+    device = new_xyz.device
+    _require_cuda(device, "densification_postfix")
+    P = int(pc._zval.shape[0]) + int(pc.bg_xyz.shape[0]) + int(new_xyz.shape[0])
+    accum = torch.empty(P, 1, dtype=torch.float32, device=device)
+    denom = torch.empty(P, 1, dtype=torch.float32, device=device)
+    max_radii = torch.empty(P, dtype=torch.float32, device=device)
+    tensors = cat_tensors_to_optimizer(d, pc.optimizer_bg, zeros=[accum, denom, max_radii])
+    for name, t in tensors.items():
+        setattr(pc, GROUP_ATTR[name], t)
+    pc.xyz_gradient_accum, pc.denom, pc.max_radii2D = accum, denom, max_radii

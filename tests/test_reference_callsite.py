@@ -205,44 +205,57 @@ def test_reference_optimizer_surgery_runs_on_the_fused_adam(reference_renderer):
         assert torch.equal(results[0][name][1], results[1][name][1])
 
 
-def test_prune_points_mirror_matches_the_reference_method(reference_renderer, monkeypatch):
-    """scgaussian_b200.densify.prune_points (SURVEY.md section 8f row f4) against the reference's own
-    `GaussianModel.prune_points` (scene/gaussian_model.py:795-820), both on the same CPU model built by the reference's
-    `training_setup`.  HOST LOGIC ONLY: there is no GPU here and the product has no CPU path, so for this one test the
-    C entry point is replaced by a numpy test double that honours the same ScgrRowGather table (the real kernel is
-    compared with torch indexing on the GPU: tests/test_model.py::test_prune_points_matches_torch_indexing)."""
+class _NumpyDouble:
+    """Test double of the two data-movement entry points of libscgr.so (scgr_gather_rows, scgr_copy_segments) on HOST
+    pointers, honouring the same ctypes tables.  The build container has no GPU and the product has no CPU path: this
+    double exists so that the HOST LOGIC of scgaussian_b200/densify.py can be run next to the reference's own methods;
+    the kernels themselves are compared with torch on the GPU (tests/test_model.py)."""
+    calls = 0
+
+    def scgr_gather_rows(self, table, n_arrays, index_ptr, n_out, stream):
+        import ctypes as C
+        import numpy as np
+        _NumpyDouble.calls += 1
+        idx = np.ctypeslib.as_array((C.c_int64 * n_out).from_address(index_ptr))
+        for a in range(n_arrays):
+            row = table[a].row_floats
+            src = np.ctypeslib.as_array((C.c_float * ((int(idx.max()) + 1) * row)).from_address(table[a].src)).reshape(-1, row)
+            dst = np.ctypeslib.as_array((C.c_float * (n_out * row)).from_address(table[a].dst)).reshape(-1, row)
+            dst[:] = src[idx]
+        return 0
+
+    def scgr_copy_segments(self, table, n_segments, stream):
+        import ctypes as C
+        import numpy as np
+        _NumpyDouble.calls += 1
+        for a in range(n_segments):
+            n = table[a].n_floats
+            dst = np.ctypeslib.as_array((C.c_float * n).from_address(table[a].dst))
+            dst[:] = np.ctypeslib.as_array((C.c_float * n).from_address(table[a].src)) if table[a].src else 0.0
+        return 0
+
+
+@pytest.fixture()
+def densify_on_host(reference_renderer, monkeypatch):
+    """scgaussian_b200.densify with the C entry points replaced by _NumpyDouble, and a builder of a small CPU model
+    through the reference's own GaussianModel / training_setup."""
     import argparse
     import contextlib
-    import ctypes as C
     import types
-    import numpy as np
     from scene.gaussian_model import GaussianModel
     from arguments import OptimizationParams
-    from scgaussian_b200 import densify, optim
+    from scgaussian_b200 import densify
 
-    class FakeLib:
-        calls = 0
-
-        def scgr_gather_rows(self, table, n_arrays, index_ptr, n_out, stream):
-            FakeLib.calls += 1
-            idx = np.ctypeslib.as_array((C.c_int64 * n_out).from_address(index_ptr))
-            for a in range(n_arrays):
-                row = table[a].row_floats
-                src = np.ctypeslib.as_array((C.c_float * ((int(idx.max()) + 1) * row)).from_address(table[a].src)).reshape(-1, row)
-                dst = np.ctypeslib.as_array((C.c_float * (n_out * row)).from_address(table[a].dst)).reshape(-1, row)
-                dst[:] = src[idx]
-            return 0
-
-    monkeypatch.setattr(densify._lib, "load", lambda: FakeLib())
+    _NumpyDouble.calls = 0
+    monkeypatch.setattr(densify._lib, "load", lambda: _NumpyDouble())
     monkeypatch.setattr(densify, "_require_cuda", lambda device, what: None)
     monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: types.SimpleNamespace(cuda_stream=0))
     real_zeros = torch.zeros
     monkeypatch.setattr(torch, "zeros", lambda *a, **k: real_zeros(*a, **{kk: vv for kk, vv in k.items() if kk != "device"}))
 
-    def build(adam_cls):
+    def build(adam_cls, n_ray=9, n_bg=6, K=16):
         g = torch.Generator().manual_seed(21)
-        n_ray, n_bg, K = 9, 6, 16
         pc = GaussianModel(3)
         P = torch.nn.Parameter
         rnd = lambda *s: torch.randn(*s, generator=g)     # noqa: E731
@@ -259,18 +272,16 @@ def test_prune_points_mirror_matches_the_reference_method(reference_renderer, mo
         for opt in (pc.optimizer, pc.optimizer_bg):                             # moments as after some steps
             for grp in opt.param_groups:
                 p = grp["params"][0]
-                if grp["name"] != "f_rest":                                     # one group without state (:790-792)
+                if grp["name"] not in ("f_rest", "bg_scaling"):                 # two groups without state (:790, :838)
                     opt.state[p] = {"step": torch.tensor(3.0), "exp_avg": rnd(*p.shape), "exp_avg_sq": rnd(*p.shape).abs()}
         pc.xyz_gradient_accum, pc.denom = rnd(n_ray + n_bg, 1), rnd(n_ray + n_bg, 1).abs()
         pc.max_radii2D = rnd(n_ray + n_bg).abs()
         return pc
 
-    mask = torch.tensor([0, 1, 0, 0, 0, 1, 0, 0, 1, 0, 0, 1, 1, 0, 0], dtype=torch.bool)
-    ref = build(None)
-    ref.prune_points(mask.clone())                                              # the reference's own method
-    ours = build(optim.Adam)
-    densify.prune_points(ours, mask.clone())
-    assert FakeLib.calls == 3                                                   # ray set, free set, statistics
+    return densify, build
+
+
+def _same_model(ours, ref, densify):
     attrs = ["_rayo", "_rayd", "xyz_gradient_accum", "denom", "max_radii2D"] + list(densify.GROUP_ATTR.values())
     for a in attrs:
         x, y = getattr(ours, a), getattr(ref, a)
@@ -287,3 +298,43 @@ def test_prune_points_mirror_matches_the_reference_method(reference_renderer, mo
                     assert torch.equal(o_opt.state[op][k], r_opt.state[rp][k]), (og["name"], k)
                 assert float(o_opt.state[op]["step"]) == 3.0
         assert len(o_opt.state) == len(r_opt.state)
+
+
+def test_prune_points_mirror_matches_the_reference_method(densify_on_host):
+    """scgaussian_b200.densify.prune_points (SURVEY.md section 8f row f4) against the reference's own
+    `GaussianModel.prune_points` (scene/gaussian_model.py:795-820), both on the same CPU model built by the reference's
+    `training_setup`.  Host logic only (see _NumpyDouble)."""
+    from scgaussian_b200 import optim
+    densify, build = densify_on_host
+    mask = torch.tensor([0, 1, 0, 0, 0, 1, 0, 0, 1, 0, 0, 1, 1, 0, 0], dtype=torch.bool)
+    ref = build(None)
+    ref.prune_points(mask.clone())                                              # the reference's own method
+    ours = build(optim.Adam)
+    densify.prune_points(ours, mask.clone())
+    assert _NumpyDouble.calls == 3                                              # ray set, free set, statistics
+    _same_model(ours, ref, densify)
+
+
+def test_densification_postfix_mirror_matches_the_reference_method(densify_on_host):
+    """scgaussian_b200.densify.densification_postfix against the reference's own method
+    (scene/gaussian_model.py:844-862 -> cat_tensors_to_optimizer :822-842): the new Gaussians appended to the free set,
+    moments extended with zeros, statistics reset -- one launch."""
+    from scgaussian_b200 import optim
+    densify, build = densify_on_host
+    g = torch.Generator().manual_seed(5)
+    n_new, K = 5, 16
+    new = [torch.randn(n_new, 3, generator=g), torch.randn(n_new, 1, 3, generator=g), torch.randn(n_new, K - 1, 3, generator=g),
+           torch.randn(n_new, 1, generator=g), torch.randn(n_new, 3, generator=g), torch.randn(n_new, 4, generator=g)]
+    ref = build(None)
+    ref.densification_postfix(*[t.clone() for t in new])                        # the reference's own method
+    ours = build(optim.Adam)
+    densify.densification_postfix(ours, *[t.clone() for t in new])
+    assert _NumpyDouble.calls == 1
+    _same_model(ours, ref, densify)
+    assert ours.bg_xyz.shape == (11, 3) and float(ours.denom.abs().max()) == 0.0 and ours.max_radii2D.shape == (20,)
+    # and then the pruning of :915-930 on the grown model
+    mask = torch.zeros(20, dtype=torch.bool)
+    mask[[10, 16, 19]] = True
+    ref.prune_points(mask.clone())
+    densify.prune_points(ours, mask.clone())
+    _same_model(ours, ref, densify)
