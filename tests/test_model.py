@@ -528,65 +528,3 @@ def test_prune_points_matches_torch_indexing():
     m2[pc._zval.shape[0]:] = True
     densify.prune_points(pc, m2)
     assert pc.bg_xyz.shape == (0, 3) and pc.bg_features_rest.shape == (0, K - 1, 3) and pc.max_radii2D.shape[0] == pc._zval.shape[0]
-
-
-@pytest.mark.gpu
-def test_densification_postfix_matches_torch_cat():
-    """scgaussian_b200.densify.densification_postfix (reference scene/gaussian_model.py:822-862) on the GPU: parameters
-    = torch.cat(old, new), moments = torch.cat(old, zeros), statistics reset -- bit for bit, in one launch."""
-    if not torch.cuda.is_available():
-        pytest.skip("needs a GPU")
-    from scgaussian_b200 import _lib, densify, optim
-    gen = torch.Generator().manual_seed(17)
-    n_ray, n_bg, n_new, K = 3001, 4099, 1234, 16
-
-    def rnd(*s):
-        return torch.randn(*s, generator=gen).cuda()
-    pc = _Stats()
-    par = torch.nn.Parameter
-    pc._zval = par(rnd(n_ray, 1))
-    pc.bg_xyz, pc.bg_features_dc, pc.bg_features_rest = par(rnd(n_bg, 3)), par(rnd(n_bg, 1, 3)), par(rnd(n_bg, K - 1, 3))
-    pc.bg_scaling, pc.bg_rotation, pc.bg_opacity = par(rnd(n_bg, 3)), par(rnd(n_bg, 4)), par(rnd(n_bg, 1))
-    inv = {v: k for k, v in densify.GROUP_ATTR.items()}
-    free = [a for a in densify.GROUP_ATTR.values() if a.startswith("bg_")]
-    pc.optimizer_bg = optim.Adam([{"params": [getattr(pc, a)], "lr": 1e-3, "name": inv[a]} for a in free], lr=0.0, eps=1e-15)
-    for a in free:
-        if a != "bg_opacity":                       # one group that has never been stepped: no state to extend
-            getattr(pc, a).grad = rnd(*getattr(pc, a).shape)
-    pc.optimizer_bg.step()
-    pc.xyz_gradient_accum, pc.denom, pc.max_radii2D = rnd(n_ray + n_bg, 1), rnd(n_ray + n_bg, 1), rnd(n_ray + n_bg)
-    new = {"bg_xyz": rnd(n_new, 3), "bg_features_dc": rnd(n_new, 1, 3), "bg_features_rest": rnd(n_new, K - 1, 3),
-           "bg_opacity": rnd(n_new, 1), "bg_scaling": rnd(n_new, 3), "bg_rotation": rnd(n_new, 4)}
-    want_p = {a: torch.cat((getattr(pc, a).detach(), new[a])) for a in free}
-    want_m = {a: tuple(torch.cat((pc.optimizer_bg.state[getattr(pc, a)][k], torch.zeros_like(new[a])))
-                       for k in ("exp_avg", "exp_avg_sq")) for a in free if a != "bg_opacity"}
-    lib = _lib.load()
-    before = lib.scgr_kernel_launch_count()
-    densify.densification_postfix(pc, new["bg_xyz"], new["bg_features_dc"], new["bg_features_rest"], new["bg_opacity"],
-                                  new["bg_scaling"], new["bg_rotation"])
-    assert lib.scgr_kernel_launch_count() - before == 1
-    P = n_ray + n_bg + n_new
-    for a in free:
-        p = getattr(pc, a)
-        assert isinstance(p, torch.nn.Parameter) and p.requires_grad and torch.equal(p.detach(), want_p[a]), a
-        grp = [g for g in pc.optimizer_bg.param_groups if g["name"] == inv[a]][0]
-        assert grp["params"][0] is p
-        if a == "bg_opacity":
-            assert p not in pc.optimizer_bg.state
-        else:
-            st = pc.optimizer_bg.state[p]
-            assert torch.equal(st["exp_avg"], want_m[a][0]) and torch.equal(st["exp_avg_sq"], want_m[a][1]), a
-            assert float(st["step"]) == 1.0
-    assert len(pc.optimizer_bg.state) == 5
-    for t, shape in ((pc.xyz_gradient_accum, (P, 1)), (pc.denom, (P, 1)), (pc.max_radii2D, (P,))):
-        assert tuple(t.shape) == shape and float(t.abs().max()) == 0.0
-    # the grown model keeps training
-    for a in free:
-        getattr(pc, a).grad = torch.ones_like(getattr(pc, a))
-    pc.optimizer_bg.step()
-    assert float(pc.optimizer_bg.state[pc.bg_xyz]["step"]) == 2.0 and float(pc.optimizer_bg.state[pc.bg_opacity]["step"]) == 1.0
-    # nothing to append
-    empty = {a: new[a][:0] for a in free}
-    densify.densification_postfix(pc, empty["bg_xyz"], empty["bg_features_dc"], empty["bg_features_rest"], empty["bg_opacity"],
-                                  empty["bg_scaling"], empty["bg_rotation"])
-    assert pc.bg_xyz.shape == (n_bg + n_new, 3)

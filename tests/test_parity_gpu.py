@@ -520,26 +520,3 @@ def test_config4_resolution_properties(dev):
         num = float((b12[k] - (b1[k] + b2[k])).abs().max())
         assert num / (float(b12[k].abs().max()) + 1e-30) < 1e-4, k
     report("config4_resolution", R=Rn, visible=int((radii > 0).sum()))
-
-
-def test_overflow_flag_describes_the_last_emission(dev, monkeypatch):
-    """A fused call whose pre-sized buffer is too small raises the device overflow flag and returns
-    SCGR_NEED_CAPACITY; the completing scgr_forward_render (stage 1 kept) must leave {R, 0} behind, with the same
-    tile lists as a forward that never overflowed."""
-    from scgaussian_b200 import rasterizer as R
-    case = util.make_case(4000, 160, 120, scale_median=0.05)      # test_binning_modes_agree's scene: R >> 4096 + 20
-    s = settings_for(case, dev)
-    t = {k: case[k].to(dev).contiguous() for k in ("means3D", "opacities", "shs", "scales", "rotations")}
-    args = (t["means3D"], t["opacities"], t["shs"], None, t["scales"], t["rotations"], None, s)
-    monkeypatch.setattr(R, "_BINNING_MODE", "sync")
-    ref = R.rasterize_forward_raw(*args)
-    dv_ref = R.debug_views(ref[4], case["P"], s)
-    monkeypatch.setattr(R, "_BINNING_MODE", "fused")
-    R._capacity_hint[dev.index] = 16
-    out = R.rasterize_forward_raw(*args)
-    torch.cuda.synchronize()
-    assert out[4].capacity == out[4].num_rendered == ref[4].num_rendered
-    dv = R.debug_views(out[4], case["P"], s)
-    assert int(dv["status"][0]) == ref[4].num_rendered and int(dv["status"][1]) == 0
-    assert torch.equal(dv["point_list"], dv_ref["point_list"]) and torch.equal(dv["ranges"], dv_ref["ranges"])
-    assert torch.equal(out[0], ref[0])
