@@ -1,5 +1,6 @@
-// model.cu -- the two elementwise passes either side of the rasterizer in a training step (sm_100a).
-// SURVEY.md section 8(f), rows f2 and f3.  Both are pure HBM streams: no reuse, no shared memory.
+// model.cu -- the elementwise / data-movement passes either side of the rasterizer in a training step (sm_100a).
+// SURVEY.md section 8(f) rows f2, f3, f4 and 8(a) row a17.  All of them are pure HBM streams with no reuse; shared
+// memory appears once, as the layout converter of the SH copy.  Measured: profiles/r01_model_passes.md.
 //
 // (f2) assemble_forward / assemble_backward: what SCGaussian's `GaussianModel.get_xyz / get_scaling /
 //      get_rotation / get_opacity / get_features` compute on every render() call
@@ -15,6 +16,11 @@
 //      iteration (reference scene/gaussian_model.py:491-510, train.py:204-208), all parameter groups of
 //      both optimizers in ONE launch; per element 16 B read (param, grad, exp_avg, exp_avg_sq) + 12 B
 //      written = 28 B.
+// (a17) densification_stats: reference train.py:192-193 -> scene/gaussian_model.py:932-934, one launch, no host sync.
+// (f4) gather_rows / copy_segments: the prune compaction (reference scene/gaussian_model.py:777-820) and the
+//      densification append (:822-862) over every per-Gaussian array of the model, one launch per index list / per
+//      append.
+// tests/test_kernel_emulation.py compiles THIS FILE for the host and runs every kernel thread for thread.
 #include <cstdlib>
 
 #include "common.cuh"
