@@ -1,11 +1,11 @@
 // host_cuda_shim.h -- TEST INFRASTRUCTURE (tests/ only; the product never builds or loads this).
 //
-// Just enough of the CUDA programming model to execute the kernels of scgaussian_b200/csrc/model.cu on the HOST,
+// Just enough of the CUDA programming model to execute the kernels of scgaussian_b200/csrc/model.cu and preprocess.cu on the HOST,
 // thread for thread: every block of a launch is run by `blockDim.x` real threads, `__syncthreads()` is a real barrier,
 // `__shared__` arrays are per-process statics (blocks run one after the other).  What this checks before a GPU is
 // available: indexing, bounds, the segment tables, the shared-memory staging and its barrier placement -- against
 // the same oracle and golden vectors as the GPU tests.  What it cannot check: warp intrinsics (none are used by
-// these kernels), memory-model subtleties, performance.
+// these kernels beyond full-mask __ballot_sync), memory-model subtleties, performance.
 #pragma once
 #include <algorithm>
 #include <barrier>
@@ -13,6 +13,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <thread>
@@ -22,19 +23,36 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 #define __grid_constant__
 #define __restrict__
 #define __align__(x) __attribute__((aligned(x)))
 #define __shared__ static
+#define __constant__ static
 
-struct float4 { float x, y, z, w; };
+struct float2 { float x, y; };
+struct float3 { float x, y, z; };
+struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
+struct __attribute__((aligned(8))) uint2 { unsigned x, y; };
+struct __attribute__((aligned(16))) uint4 { unsigned x, y, z, w; };
+static inline float2 make_float2(float a, float b) { return {a, b}; }
+static inline float3 make_float3(float a, float b, float c) { return {a, b, c}; }
 static inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
+static inline uint2 make_uint2(unsigned a, unsigned b) { return {a, b}; }
+static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return {a, b, c, d}; }
 struct EmuDim3 { unsigned x = 0, y = 0, z = 0; };
-static thread_local EmuDim3 blockIdx, threadIdx;
+static thread_local EmuDim3 blockIdx, threadIdx, blockDim;
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline float __fadd_rn(float a, float b) { return a + b; }      // compiled with -ffp-contract=off
 static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline void __trap() { std::abort(); }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 using std::max;
 using std::min;
 typedef void* cudaStream_t;
@@ -42,18 +60,39 @@ typedef void* cudaStream_t;
 static std::unique_ptr<std::barrier<>> g_block_barrier;
 static inline void __syncthreads() { g_block_barrier->arrive_and_wait(); }
 
+// warp votes: the 32 threads of a warp meet at a per-warp barrier, publish their predicate, and read all 32
+// (full-mask votes only: every lane of the warp must take part, which is what the kernels do)
+static std::vector<std::unique_ptr<std::barrier<>>> g_warp_barrier;
+static unsigned g_votes[64][32];
+static unsigned g_warp_lanes[64];
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    const unsigned w = threadIdx.x / 32, lane = threadIdx.x % 32;
+    g_votes[w][lane] = pred ? 1u : 0u;
+    g_warp_barrier[w]->arrive_and_wait();
+    unsigned r = 0;
+    for (unsigned l = 0; l < g_warp_lanes[w]; l++) r |= g_votes[w][l] << l;
+    g_warp_barrier[w]->arrive_and_wait();
+    return r;
+}
+
 // kernel<<<grid, threads, 0, stream>>>(args) is rewritten (tests/emulation/build.py) into
 // emu_launch(grid, threads, [=] { kernel(args); }).  `threads` workers walk the blocks in order; a barrier closes
 // every block, so a kernel must use __syncthreads() uniformly within a block (as CUDA requires anyway).
 template <class F>
 static void emu_launch(unsigned grid, unsigned threads, F f) {
     g_block_barrier.reset(new std::barrier<>(threads));
+    g_warp_barrier.clear();
+    for (unsigned w = 0; w * 32 < threads; w++) {
+        g_warp_lanes[w] = std::min(32u, threads - w * 32);
+        g_warp_barrier.emplace_back(new std::barrier<>(g_warp_lanes[w]));
+    }
     std::vector<std::thread> pool;
     for (unsigned t = 0; t < threads; t++)
         pool.emplace_back([=] {
             for (unsigned b = 0; b < grid; b++) {
                 blockIdx.x = b;
                 threadIdx.x = t;
+                blockDim.x = threads;
                 f();
                 g_block_barrier->arrive_and_wait();
             }

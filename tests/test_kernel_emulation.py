@@ -1,6 +1,8 @@
-"""The kernels of scgaussian_b200/csrc/model.cu executed on the HOST, thread for thread (tests/emulation/: the .cu
-source compiled with g++ through a small CUDA shim -- real threads per block, real barriers, shared memory as
-statics), against the same oracle and reference-generated golden vectors as the GPU tests.
+"""The kernels of scgaussian_b200/csrc/model.cu and preprocess.cu executed on the HOST, thread for thread
+(tests/emulation/: the .cu sources compiled with g++ through a small CUDA shim -- real threads per block, real
+barriers, warp votes, shared memory as statics), against the same oracles and reference-generated golden vectors as
+the GPU tests: the model passes (assembly, Adam, statistics, gather, copy) and the per-Gaussian half of the rasterizer
+(preprocess forward / backward, depth keys, markVisible: SURVEY.md section 8a rows a9, a16).
 
 TEST INFRASTRUCTURE, CPU suite only: it catches indexing / bounds / table / staging mistakes before a GPU is
 available.  It is NOT a CPU path of the product (nothing under scgaussian_b200/ can reach it) and it proves nothing
@@ -184,3 +186,168 @@ def test_copy_segments_kernel_on_host(emu):
         covered[o:o + n] = True
     assert torch.isnan(big[~covered]).all()                                      # nothing written outside the segments
     assert {o % 4 for o, n, s in segs if n} > {0}                                # both the float4 and the scalar path ran
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# scgaussian_b200/csrc/preprocess.cu on the host: the per-Gaussian half of the rasterizer (SURVEY.md section 8a rows
+# a9 / a16, Appendix A.1-A.5 and A.10) against the torch oracle's differentiable `preprocess`
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emu_pre():
+    from tests.emulation import build
+    try:
+        path = build.build_preprocess()
+    except Exception as e:      # pragma: no cover
+        pytest.skip(f"host emulation library not buildable here: {e}")
+    lib = C.CDLL(path)
+    lib.emu_geometry_bytes.restype = C.c_size_t
+    return lib
+
+
+def _host_scene(P, W, H, sh_degree, seed, max_sh_degree=3, **kw):
+    from tests import util
+    case = util.make_case(P, W, H, sh_degree=sh_degree, max_sh_degree=max_sh_degree, seed=seed, **kw)
+    t = {k: case[k].contiguous() for k in ("means3D", "opacities", "shs", "scales", "rotations", "bg", "viewmatrix",
+                                           "projmatrix", "campos")}
+    view = L.ScgrView(H, W, case["tanfovx"], case["tanfovy"], t["bg"].data_ptr(), case["scale_modifier"],
+                      t["viewmatrix"].data_ptr(), t["projmatrix"].data_ptr(), sh_degree, t["campos"].data_ptr(), 0, 0)
+    g = L.ScgrGaussians(P, int(t["shs"].shape[1]), t["means3D"].data_ptr(), t["opacities"].data_ptr(), t["shs"].data_ptr(),
+                        None, t["scales"].data_ptr(), t["rotations"].data_ptr(), None)
+    return case, t, view, g
+
+
+def _geometry(emu_pre, P):
+    geom = torch.zeros(int(emu_pre.emu_geometry_bytes(P)) + 64, dtype=torch.uint8)
+    base = (-geom.data_ptr()) % 64                      # 64-byte aligned start inside the tensor
+    off = (C.c_size_t * 8)()
+    emu_pre.emu_geometry_offsets(P, off)
+
+    def view(k, nbytes, dtype):
+        return geom[base + off[k]: base + off[k] + nbytes].view(dtype)
+    return geom, geom.data_ptr() + base, view
+
+
+@pytest.mark.parametrize("P,W,H,deg,max_deg,smed,yaw", [(1500, 203, 149, 3, 3, 0.04, 8.0), (700, 64, 48, 1, 1, 0.08, 0.0),
+                                                        (900, 160, 120, 0, 2, 0.05, -5.0)])
+def test_preprocess_forward_on_host_matches_oracle(emu_pre, P, W, H, deg, max_deg, smed, yaw):
+    from oracle import torch_oracle as O
+    from tests import util
+    case, t, view, g = _host_scene(P, W, H, deg, seed=P, max_sh_degree=max_deg, scale_median=smed, w2c=O.yaw_w2c(yaw),
+                                   z_shift=-1.9)          # some Gaussians behind the near plane
+    geom, gptr, gv = _geometry(emu_pre, P)
+    radii = torch.full((P,), -7, dtype=torch.int32)
+    emu_pre.emu_preprocess_forward(C.byref(view), C.byref(g), C.c_void_p(gptr), C.c_void_p(radii.data_ptr()))
+    want = O.preprocess(t["means3D"], t["opacities"], util.oracle_settings(case), shs=t["shs"], scales=t["scales"],
+                        rotations=t["rotations"])
+    rec = gv(0, P * 48, torch.float32).view(P, 12).numpy()
+    r2 = want.radii.numpy()
+    n_rad = int((radii.numpy() != r2).sum())
+    assert n_rad <= max(2, P // 1000) and np.abs(radii.numpy() - r2).max() <= 1, n_rad      # ceil() of a last-bit difference
+    both = (r2 > 0) & (radii.numpy() > 0)
+    assert both.sum() > P // 3 and (r2 == 0).sum() > 0
+    log2e = 1.4426950408889634
+    conic = want.conic.numpy()
+    assert util.rel_err(rec[both][:, 0:2], want.means2D.numpy()[both]) < 1e-5
+    assert util.rel_err(rec[both][:, 2] / (-0.5 * log2e), conic[both][:, 0]) < 1e-4
+    assert util.rel_err(rec[both][:, 3] / -log2e, conic[both][:, 1]) < 1e-4
+    assert util.rel_err(rec[both][:, 4] / (-0.5 * log2e), conic[both][:, 2]) < 1e-4
+    assert np.array_equal(rec[both][:, 5], t["opacities"].numpy()[both, 0])
+    assert util.rel_err(rec[both][:, 6], want.depth.numpy()[both]) < 1e-6
+    assert util.rel_err(rec[both][:, 8:11], want.rgb.numpy()[both]) < 1e-5
+    bits = rec[:, 11].copy().view(np.uint32)
+    assert np.array_equal((bits & 0x0FFFFFFF).astype(np.int32)[both], radii.numpy()[both])
+    flags = (bits >> 28)[both]
+    clamped = want.clamped.numpy()[both]
+    agree = ((flags & 1) > 0) == clamped[:, 0]
+    assert agree.mean() > 0.995                          # a colour within rounding of 0 may clamp on one side only
+    # culling only removes tiles: never more than the reference's rectangle, and the mask agrees with the count
+    touched = gv(1, P * 4, torch.int32).numpy()
+    assert (touched[radii.numpy() == r2] <= want.tiles_touched.numpy()[radii.numpy() == r2]).all() and touched.sum() > 0
+    assert (touched[radii.numpy() == 0] == 0).all()
+    rect = gv(2, P * 8, torch.int32).view(P, 2).numpy().astype(np.int64)
+    x0, y0, x1, y1 = rect[:, 0] & 0xFFFF, rect[:, 0] >> 16, rect[:, 1] & 0xFFFF, rect[:, 1] >> 16
+    same = radii.numpy() == r2
+    assert np.array_equal(np.stack([x0, y0], 1)[both & same], want.rect_min.numpy()[both & same])
+    assert np.array_equal(np.stack([x1, y1], 1)[both & same], want.rect_max.numpy()[both & same])
+    mask = gv(3, P * 8, torch.int64).numpy()
+    small = ((x1 - x0) * (y1 - y0) <= 64) & (radii.numpy() > 0)
+    popc = np.array([bin(int(m) & (2 ** 64 - 1)).count("1") for m in mask])
+    assert np.array_equal(popc[small], touched[small])
+
+    # depth keys + the digit histograms of the four radix passes (the other kernel that must agree bit for bit)
+    emu_pre.emu_depth_keys(C.byref(view), C.byref(g), C.c_void_p(gptr))
+    keys = gv(4, P * 4, torch.int32).numpy().view(np.uint32)
+    front = rec[:, 6].view(np.uint32)
+    vis = radii.numpy() > 0
+    assert np.array_equal(keys[vis], front[vis])         # record depth and sort key: identical bits
+    zview = (t["means3D"].double() @ t["viewmatrix"].double()[:3, 2] + t["viewmatrix"].double()[3, 2]).numpy()
+    assert (keys[zview <= 0.2 - 1e-6] == 0xFFFFFFFF).all()
+    assert np.array_equal(gv(5, P * 4, torch.int32).numpy(), np.arange(P))
+    words = 260 + 256 * ((P + 4095) // 4096)
+    sweep = gv(7, 4 * words * 4, torch.int32).view(4, words).numpy()
+    for p in range(4):
+        assert np.array_equal(sweep[p, :256], np.bincount((keys >> (8 * p)) & 255, minlength=256))
+
+    # markVisible (A.1 only)
+    present = torch.zeros(P, dtype=torch.uint8)
+    emu_pre.emu_mark_visible(C.c_void_p(t["means3D"].data_ptr()), P, C.c_void_p(t["viewmatrix"].data_ptr()),
+                             C.c_void_p(present.data_ptr()))
+    assert np.array_equal(present.numpy().astype(bool), keys != 0xFFFFFFFF)
+
+
+@pytest.mark.parametrize("P,W,H,deg,max_deg,smed", [(1100, 203, 149, 3, 3, 0.04), (500, 64, 48, 1, 1, 0.08), (640, 120, 90, 2, 3, 0.05)])
+def test_preprocess_backward_on_host_matches_autograd_of_the_oracle(emu_pre, P, W, H, deg, max_deg, smed):
+    """A.10 in isolation.  The kernel's input is the per-Gaussian accumulator render-backward leaves behind (raw sums
+    over pixel pairs, scgaussian_b200/csrc/common.cuh `ScreenGrad`); for random accumulators its outputs must equal the
+    autograd gradients of the (fp64) oracle's `preprocess` under the linear functional those sums stand for:
+        dL/dmean2D = -(A Sx + B Sy, C Sy + B Sx) px,  dL/dconic = (-SA/2, -SB, -SC/2),  dL/dopacity = Su / opacity."""
+    from oracle import torch_oracle as O
+    from tests import util
+    case, t, view, g = _host_scene(P, W, H, deg, seed=P + 1, max_sh_degree=max_deg, scale_median=smed, w2c=O.yaw_w2c(6.0),
+                                   z_shift=-1.9)
+    # push some Gaussians beyond 1.3 tan(fov) sideways and make them large enough to still reach the image: the A.4
+    # clamp is active for them (A.10: their t.x / t.y are constants in the backward)
+    t["means3D"][5:60, 0] *= 1.6
+    t["means3D"][60:90, 1] *= 1.7
+    t["scales"][5:90] *= 12.0
+    geom, gptr, gv = _geometry(emu_pre, P)
+    radii = torch.zeros(P, dtype=torch.int32)
+    emu_pre.emu_preprocess_forward(C.byref(view), C.byref(g), C.c_void_p(gptr), C.c_void_p(radii.data_ptr()))
+    gen = torch.Generator().manual_seed(3)
+    acc = torch.randn(P, 12, generator=gen, dtype=torch.float32) * torch.tensor(
+        [1e-2, 1e-2, 1e-1, 1e-1, 1e-1, 1e-2, 1e-3, 0, 1e-2, 1e-2, 1e-2, 0])
+    acc[::7] = 0.0                                   # Gaussians nothing blended: the kernel skips them and writes zeros
+    acc[radii == 0] = 0.0
+    gv(6, P * 48, torch.float32).view(P, 12).copy_(acc)
+    M = int(t["shs"].shape[1])
+    outs = {"means3D": torch.full((P, 3), float("nan")), "means2D": torch.full((P, 3), float("nan")),
+            "shs": torch.full((P, M, 3), float("nan")), "opacities": torch.full((P, 1), float("nan")),
+            "scales": torch.full((P, 3), float("nan")), "rotations": torch.full((P, 4), float("nan"))}
+    grads = L.ScgrGrads(outs["means3D"].data_ptr(), outs["means2D"].data_ptr(), outs["shs"].data_ptr(), None,
+                        outs["opacities"].data_ptr(), outs["scales"].data_ptr(), outs["rotations"].data_ptr(), None)
+    emu_pre.emu_preprocess_backward(C.byref(view), C.byref(g), C.c_void_p(gptr), C.byref(grads))
+    for k, v in outs.items():
+        assert not torch.isnan(v).any(), k            # every gradient tensor is written in full
+
+    leaves = {k: t[k].double().clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+    geo = O.preprocess(leaves["means3D"], leaves["opacities"], util.oracle_settings(case, torch.float64), shs=leaves["shs"],
+                       scales=leaves["scales"], rotations=leaves["rotations"])
+    vis = torch.from_numpy(radii.numpy() > 0) & geo.visible
+    pv = torch.cat([t["means3D"].double(), torch.ones(P, 1, dtype=torch.float64)], 1) @ t["viewmatrix"].double()
+    clamp_active = ((pv[:, 0] / pv[:, 2]).abs() > 1.3 * case["tanfovx"]) | ((pv[:, 1] / pv[:, 2]).abs() > 1.3 * case["tanfovy"])
+    assert int((clamp_active & vis & (acc.abs().sum(1) > 0)).sum()) >= 10
+    a = acc.double()
+    A, B, Cc = (geo.conic[:, k].detach() for k in range(3))
+    gmx, gmy = -(A * a[:, 0] + B * a[:, 1]), -(Cc * a[:, 1] + B * a[:, 0])
+    per = (gmx * geo.means2D[:, 0] + gmy * geo.means2D[:, 1]
+           - 0.5 * a[:, 2] * geo.conic[:, 0] - a[:, 3] * geo.conic[:, 1] - 0.5 * a[:, 4] * geo.conic[:, 2]
+           + a[:, 6] * geo.depth + (a[:, 8:11] * geo.rgb).sum(1)
+           + a[:, 5] / leaves["opacities"][:, 0].detach() * leaves["opacities"][:, 0])
+    torch.where(vis, per, torch.zeros_like(per)).sum().backward()
+    for k in ("means3D", "opacities", "shs", "scales", "rotations"):
+        util.assert_grad_close(k, outs[k].numpy(), leaves[k].grad.numpy(), flip_frac=0.0)
+    want2d = torch.stack([gmx * 0.5 * W, gmy * 0.5 * H, torch.zeros_like(gmx)], 1) * vis[:, None]
+    util.assert_grad_close("means2D", outs["means2D"].numpy(), want2d.numpy(), flip_frac=0.0)
+    assert float(outs["shs"][:, (deg + 1) ** 2:].abs().max() if M > (deg + 1) ** 2 else 0.0) == 0.0   # rows beyond the active degree
+    skipped = (acc.abs().sum(1) == 0).numpy()
+    assert skipped.sum() > P // 8 and float(outs["means3D"][torch.from_numpy(skipped)].abs().max()) == 0.0
