@@ -79,5 +79,33 @@ def build_preprocess() -> str:
     return LIB_PRE
 
 
+def _common_host() -> None:
+    c = open(os.path.join(CSRC, "common.cuh")).read().replace("#include <cuda_runtime.h>", "")
+    c = c.replace('#include "../../include/scgr.h"', '#include "../../../include/scgr.h"')
+    c, n = re.subn(r'asm\("sqrt\.approx\.ftz\.f32 %0, %1;"[^;]*;', "y = sqrtf(x);", c)
+    assert n == 1 and "asm" not in c, "common.cuh: expected exactly one inline-PTX statement (sqrt.approx)"
+    with open(os.path.join(OUT_DIR, "common_host.cuh"), "w") as f:
+        f.write(c)
+
+
+LIB_LOSS = os.path.join(OUT_DIR, "libemu_loss_knn.so")
+
+
+def build_loss_knn() -> str:
+    srcs = [os.path.join(CSRC, "loss.cu"), os.path.join(CSRC, "knn.cu")]
+    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "host_cuda_shim.h"),
+                   os.path.join(HERE, "emu_loss_knn.cpp"), __file__, os.path.join(ROOT, "include", "scgr.h")]
+    if os.path.exists(LIB_LOSS) and all(os.path.getmtime(d) <= os.path.getmtime(LIB_LOSS) for d in deps):
+        return LIB_LOSS
+    os.makedirs(OUT_DIR, exist_ok=True)
+    _common_host()
+    for src, name, n in ((srcs[0], "loss_body.inc", 3), (srcs[1], "knn_body.inc", 1)):
+        body = open(src).read().replace('#include "common.cuh"', "")
+        with open(os.path.join(OUT_DIR, name), "w") as f:
+            f.write(_rewrite_launches(body, n))
+    _compile(LIB_LOSS, "emu_loss_knn.cpp")
+    return LIB_LOSS
+
+
 if __name__ == "__main__":
-    print(build(), build_preprocess())
+    print(build(), build_preprocess(), build_loss_knn())

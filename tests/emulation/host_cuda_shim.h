@@ -1,11 +1,11 @@
 // host_cuda_shim.h -- TEST INFRASTRUCTURE (tests/ only; the product never builds or loads this).
 //
-// Just enough of the CUDA programming model to execute the kernels of scgaussian_b200/csrc/model.cu and preprocess.cu on the HOST,
+// Just enough of the CUDA programming model to execute the kernels of scgaussian_b200/csrc/{model,preprocess,loss,knn}.cu on the HOST,
 // thread for thread: every block of a launch is run by `blockDim.x` real threads, `__syncthreads()` is a real barrier,
 // `__shared__` arrays are per-process statics (blocks run one after the other).  What this checks before a GPU is
 // available: indexing, bounds, the segment tables, the shared-memory staging and its barrier placement -- against
 // the same oracle and golden vectors as the GPU tests.  What it cannot check: warp intrinsics (none are used by
-// these kernels beyond full-mask __ballot_sync), memory-model subtleties, performance.
+// these kernels beyond full-mask __ballot_sync / __shfl_xor_sync), memory-model subtleties, performance.
 #pragma once
 #include <algorithm>
 #include <barrier>
@@ -40,8 +40,12 @@ static inline float3 make_float3(float a, float b, float c) { return {a, b, c}; 
 static inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
 static inline uint2 make_uint2(unsigned a, unsigned b) { return {a, b}; }
 static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return {a, b, c, d}; }
-struct EmuDim3 { unsigned x = 0, y = 0, z = 0; };
-static thread_local EmuDim3 blockIdx, threadIdx, blockDim;
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+static thread_local dim3 blockIdx(0, 0, 0), threadIdx(0, 0, 0), blockDim, gridDim;
+typedef void* cudaStream_t;
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline float __fadd_rn(float a, float b) { return a + b; }      // compiled with -ffp-contract=off
 static inline float __fmul_rn(float a, float b) { return a * b; }
@@ -52,10 +56,13 @@ static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f
 static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline void __trap() { std::abort(); }
+static inline float __frcp_rn(float x) { return 1.0f / x; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline int cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return 0; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 using std::max;
 using std::min;
-typedef void* cudaStream_t;
 
 static std::unique_ptr<std::barrier<>> g_block_barrier;
 static inline void __syncthreads() { g_block_barrier->arrive_and_wait(); }
@@ -74,12 +81,28 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     g_warp_barrier[w]->arrive_and_wait();
     return r;
 }
+// warp shuffles (xor pattern): every lane publishes its value, the warp meets, every lane reads its partner's
+static unsigned long long g_shfl[64][32];
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+    static_assert(sizeof(T) <= 8, "shuffle of a type wider than 64 bits");
+    const unsigned w = threadIdx.x / 32, lane = threadIdx.x % 32;
+    unsigned long long bits = 0;
+    std::memcpy(&bits, &v, sizeof(T));
+    g_shfl[w][lane] = bits;
+    g_warp_barrier[w]->arrive_and_wait();
+    const unsigned src = lane ^ (unsigned)lane_mask;
+    T out = v;
+    if (src < g_warp_lanes[w]) std::memcpy(&out, &g_shfl[w][src], sizeof(T));
+    g_warp_barrier[w]->arrive_and_wait();
+    return out;
+}
 
 // kernel<<<grid, threads, 0, stream>>>(args) is rewritten (tests/emulation/build.py) into
 // emu_launch(grid, threads, [=] { kernel(args); }).  `threads` workers walk the blocks in order; a barrier closes
 // every block, so a kernel must use __syncthreads() uniformly within a block (as CUDA requires anyway).
 template <class F>
-static void emu_launch(unsigned grid, unsigned threads, F f) {
+static void emu_launch(dim3 grid, unsigned threads, F f) {
     g_block_barrier.reset(new std::barrier<>(threads));
     g_warp_barrier.clear();
     for (unsigned w = 0; w * 32 < threads; w++) {
@@ -89,13 +112,16 @@ static void emu_launch(unsigned grid, unsigned threads, F f) {
     std::vector<std::thread> pool;
     for (unsigned t = 0; t < threads; t++)
         pool.emplace_back([=] {
-            for (unsigned b = 0; b < grid; b++) {
-                blockIdx.x = b;
-                threadIdx.x = t;
-                blockDim.x = threads;
-                f();
-                g_block_barrier->arrive_and_wait();
-            }
+            threadIdx = dim3(t, 0, 0);
+            blockDim = dim3(threads, 1, 1);
+            gridDim = grid;
+            for (unsigned bz = 0; bz < grid.z; bz++)
+                for (unsigned by = 0; by < grid.y; by++)
+                    for (unsigned bx = 0; bx < grid.x; bx++) {
+                        blockIdx = dim3(bx, by, bz);
+                        f();
+                        g_block_barrier->arrive_and_wait();
+                    }
         });
     for (auto& th : pool) th.join();
 }

@@ -1,8 +1,9 @@
-"""The kernels of scgaussian_b200/csrc/model.cu and preprocess.cu executed on the HOST, thread for thread
+"""The kernels of scgaussian_b200/csrc/{model,preprocess,loss,knn}.cu executed on the HOST, thread for thread
 (tests/emulation/: the .cu sources compiled with g++ through a small CUDA shim -- real threads per block, real
 barriers, warp votes, shared memory as statics), against the same oracles and reference-generated golden vectors as
 the GPU tests: the model passes (assembly, Adam, statistics, gather, copy) and the per-Gaussian half of the rasterizer
-(preprocess forward / backward, depth keys, markVisible: SURVEY.md section 8a rows a9, a16).
+(preprocess forward / backward, depth keys, markVisible: SURVEY.md section 8a rows a9, a16), the photometric loss
+(section 8f row f1) and distCUDA2 (row f4).
 
 TEST INFRASTRUCTURE, CPU suite only: it catches indexing / bounds / table / staging mistakes before a GPU is
 available.  It is NOT a CPU path of the product (nothing under scgaussian_b200/ can reach it) and it proves nothing
@@ -351,3 +352,75 @@ def test_preprocess_backward_on_host_matches_autograd_of_the_oracle(emu_pre, P, 
     assert float(outs["shs"][:, (deg + 1) ** 2:].abs().max() if M > (deg + 1) ** 2 else 0.0) == 0.0   # rows beyond the active degree
     skipped = (acc.abs().sum(1) == 0).numpy()
     assert skipped.sum() > P // 8 and float(outs["means3D"][torch.from_numpy(skipped)].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# scgaussian_b200/csrc/loss.cu and knn.cu on the host
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emu_loss():
+    from tests.emulation import build
+    try:
+        path = build.build_loss_knn()
+    except Exception as e:      # pragma: no cover
+        pytest.skip(f"host emulation library not buildable here: {e}")
+    lib = C.CDLL(path)
+    lib.emu_photometric_scratch_bytes.restype = C.c_size_t
+    return lib
+
+
+def _host_loss(emu_loss, img, gt, lam, upstream=None):
+    """(Ll1, ssim, loss, dL/dimage) of the photometric kernels run on the host; upstream: device-scalar stand-in."""
+    x = torch.tensor(np.asarray(img), dtype=torch.float32).contiguous()
+    y = torch.tensor(np.asarray(gt), dtype=torch.float32).contiguous()
+    c, h, w = x.shape
+    scratch = torch.zeros(int(emu_loss.emu_photometric_scratch_bytes(c, h, w)) + 256, dtype=torch.uint8)
+    sptr = scratch.data_ptr() + (-scratch.data_ptr()) % 256
+    out3 = torch.full((3,), float("nan"))
+    emu_loss.emu_photometric_forward(_p(x), _p(y), c, h, w, C.c_float(lam), C.c_void_p(sptr), 1, _p(out3))
+    grad = torch.full_like(x, float("nan"))
+    up = None if upstream is None else torch.tensor([upstream], dtype=torch.float32)
+    emu_loss.emu_photometric_backward(_p(x), _p(y), c, h, w, C.c_float(lam), C.c_void_p(sptr), _p(up), _p(grad))
+    return float(out3[0]), float(out3[1]), float(out3[2]), grad.numpy()
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_photometric_kernels_on_host_match_reference_golden(emu_loss, name):
+    """reference train.py:160-161 with utils/loss_utils.py l1_loss / ssim: the vectors in tests/golden/loss_golden.npz were
+    produced by the reference's own functions + autograd."""
+    from tests import test_loss as TL
+    g = np.load(TL.GOLD)
+    ll1, s, loss, g_loss = _host_loss(emu_loss, g[f"{name}_img"], g[f"{name}_gt"], 0.2)
+    assert abs(ll1 - float(g[f"{name}_l1"])) < TL.TOL_VAL
+    assert abs(s - float(g[f"{name}_ssim"])) < TL.TOL_VAL
+    assert abs(loss - float(g[f"{name}_loss"])) < TL.TOL_VAL
+    assert TL._rel(g_loss, g[f"{name}_g_loss"]) < TL.RTOL_GRAD
+    # the two parts through the (lambda, upstream) pairs the host side uses: ssim alone = lambda 1, upstream -1
+    _, _, _, g_ssim = _host_loss(emu_loss, g[f"{name}_img"], g[f"{name}_gt"], 1.0, upstream=-1.0)
+    _, _, _, g_l1 = _host_loss(emu_loss, g[f"{name}_img"], g[f"{name}_gt"], 0.0)
+    assert TL._rel(g_ssim, g[f"{name}_g_ssim"]) < TL.RTOL_GRAD and TL._rel(g_l1, g[f"{name}_g_l1"]) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(3, 1, 1), (3, 5, 7), (1, 16, 16), (3, 17, 33), (6, 40, 24), (2, 70, 131)])
+def test_photometric_kernels_on_host_match_oracle_f64(emu_loss, shape):
+    from tests import test_loss as TL
+    gen = torch.Generator().manual_seed(sum(shape))
+    gt = torch.rand(*shape, generator=gen)
+    img = (gt + 0.2 * torch.randn(*shape, generator=gen)).clamp(0, 1)
+    o = TL._oracle_all(img.numpy(), gt.numpy(), torch.float64)
+    ll1, s, loss, g_loss = _host_loss(emu_loss, img.numpy(), gt.numpy(), 0.2)
+    for got, want in zip((ll1, s, loss), o[:3]):
+        assert abs(got - want) < 5e-6
+    assert TL._rel(g_loss, o[3]) < TL.RTOL_GRAD
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 257, 1100])
+def test_knn_kernel_on_host_matches_oracle(emu_loss, n):
+    from oracle.knn_oracle import dist2_knn3
+    gen = torch.Generator().manual_seed(n)
+    pts = torch.randn(n, 3, generator=gen)
+    if n >= 5:
+        pts[3] = pts[1]
+    out = torch.full((n,), float("nan"))
+    emu_loss.emu_knn3(_p(pts), n, _p(out))
+    assert np.allclose(out.numpy(), dist2_knn3(pts.numpy()), rtol=1e-5, atol=1e-7)
