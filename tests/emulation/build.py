@@ -27,10 +27,8 @@ def build() -> str:
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
     body = open(SRC).read().replace('#include "common.cuh"', "")
-    body, n = _LAUNCH.subn(lambda m: f"emu_launch(({m.group(2)}), ({m.group(3)}), [=] {{ {m.group(1)}({m.group(4)}); }});", body)
-    assert n >= 9 and "<<<" not in body, f"launch rewrite incomplete ({n} launches rewritten)"
     with open(os.path.join(OUT_DIR, "model_body.inc"), "w") as f:
-        f.write(body)
+        f.write(_rewrite_launches(body, 9))
     gxx = shutil.which("g++")
     if gxx is None:
         raise RuntimeError("g++ not found")
@@ -43,7 +41,44 @@ def build() -> str:
 
 
 def _rewrite_launches(text: str, at_least: int) -> str:
-    text, n = _LAUNCH.subn(lambda m: f"emu_launch(({m.group(2)}), ({m.group(3)}), [=] {{ {m.group(1)}({m.group(4)}); }});", text)
+    """NAME<TEMPLATE ARGS><<<grid, threads, smem, L.stream>>>(ARGS)  ->  emu_launch((grid), (threads), [=] { NAME<..>(ARGS); })
+    with balanced parentheses, so that launches inside macros and over several lines are handled as well."""
+    out, pos, n = [], 0, 0
+    while True:
+        k = text.find("<<<", pos)
+        if k < 0:
+            break
+        # kernel name (+ template arguments) right before <<<
+        j = k
+        if text[j - 1] == ">":
+            depth = 0
+            while True:
+                j -= 1
+                depth += text[j] == ">"
+                depth -= text[j] == "<"
+                if depth == 0:
+                    break
+        i = j
+        while text[i - 1].isalnum() or text[i - 1] == "_":
+            i -= 1
+        name = text[i:k]
+        e = text.index(">>>", k)
+        cfg = [c.strip() for c in text[k + 3:e].rsplit(",", 3)]          # grid, threads, smem, stream
+        assert len(cfg) == 4 and cfg[3] == "L.stream", cfg
+        a = text.index("(", e)
+        depth, b = 0, a
+        while True:
+            depth += text[b] == "("
+            depth -= text[b] == ")"
+            if depth == 0:
+                break
+            b += 1
+        out.append(text[pos:i])
+        out.append(f"emu_launch(({cfg[0]}), ({cfg[1]}), [=] {{ {name}({text[a + 1:b]}); }})")
+        pos = b + 1
+        n += 1
+    out.append(text[pos:])
+    text = "".join(out)
     assert n >= at_least and "<<<" not in text, f"launch rewrite incomplete ({n} launches rewritten)"
     return text
 
@@ -59,22 +94,35 @@ def _compile(lib: str, cpp: str) -> None:
                            os.path.join(HERE, cpp)], env=env, cwd=HERE)
 
 
+_VOLATILE = [   # binning.cu's four inline-PTX statements: volatile global loads / stores of the look-back words
+    (r'asm volatile\("ld\.volatile\.global\.u64 %0, \[%1\];"[^;]*;', "v = *(volatile const unsigned long long*)p;"),
+    (r'asm volatile\("st\.volatile\.global\.u64 \[%0\], %1;"[^;]*;', "*(volatile unsigned long long*)p = v;"),
+    (r'asm volatile\("ld\.volatile\.global\.u32 %0, \[%1\];"[^;]*;', "v = *(volatile const uint32_t*)p;"),
+    (r'asm volatile\("st\.volatile\.global\.u32 \[%0\], %1;"[^;]*;', "*(volatile uint32_t*)p = v;"),
+]
+
+
 def build_preprocess() -> str:
-    src, common = os.path.join(CSRC, "preprocess.cu"), os.path.join(CSRC, "common.cuh")
-    deps = [src, common, os.path.join(HERE, "host_cuda_shim.h"), os.path.join(HERE, "emu_preprocess.cpp"), __file__,
-            os.path.join(ROOT, "include", "scgr.h")]
+    """preprocess.cu + binning.cu: the whole forward up to the per-tile lists."""
+    srcs = [os.path.join(CSRC, "preprocess.cu"), os.path.join(CSRC, "binning.cu")]
+    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "host_cuda_shim.h"),
+                   os.path.join(HERE, "emu_preprocess.cpp"), __file__, os.path.join(ROOT, "include", "scgr.h")]
     if os.path.exists(LIB_PRE) and all(os.path.getmtime(d) <= os.path.getmtime(LIB_PRE) for d in deps):
         return LIB_PRE
     os.makedirs(OUT_DIR, exist_ok=True)
-    c = open(common).read().replace("#include <cuda_runtime.h>", "")
-    c = c.replace('#include "../../include/scgr.h"', '#include "../../../include/scgr.h"')
-    c, n = re.subn(r'asm\("sqrt\.approx\.ftz\.f32 %0, %1;"[^;]*;', "y = sqrtf(x);", c)
-    assert n == 1 and "asm" not in c, "common.cuh: expected exactly one inline-PTX statement (sqrt.approx)"
-    with open(os.path.join(OUT_DIR, "common_host.cuh"), "w") as f:
-        f.write(c)
-    body = open(src).read().replace('#include "common.cuh"', "")
+    _common_host()
+    body = open(srcs[0]).read().replace('#include "common.cuh"', "")
     with open(os.path.join(OUT_DIR, "preprocess_body.inc"), "w") as f:
         f.write(_rewrite_launches(body, 8))
+    body = open(srcs[1]).read().replace('#include "common.cuh"', "")
+    for pat, rep in _VOLATILE:
+        body, n = re.subn(pat, rep, body)
+        assert n == 1, pat
+    assert "asm" not in body
+    body, n = re.subn(r"extern __shared__ __align__\(16\) uint32_t (\w+)\[\];", r"uint32_t* \1 = reinterpret_cast<uint32_t*>(g_dyn_smem);", body)
+    assert n == 1, "binning.cu: expected one dynamic shared-memory array"
+    with open(os.path.join(OUT_DIR, "binning_body.inc"), "w") as f:
+        f.write(_rewrite_launches(body, 4))
     _compile(LIB_PRE, "emu_preprocess.cpp")
     return LIB_PRE
 

@@ -17,6 +17,7 @@ void check_stage(const char*, const Launch&) {}
 }  // namespace scgr
 
 #include "_build/preprocess_body.inc"
+#include "_build/binning_body.inc"
 
 static const scgr::Launch kHost{nullptr, false};
 
@@ -39,6 +40,32 @@ int emu_depth_keys(const ScgrView* v, const ScgrGaussians* g, void* geometry) {
 int emu_preprocess_backward(const ScgrView* v, const ScgrGaussians* g, void* geometry, const ScgrGrads* out) {
     scgr::launch_preprocess_backward(*v, *g, scgr::carve_geometry(geometry, g->P), *out, kHost);
     return 0;
+}
+size_t emu_binning_bytes(int32_t W, int32_t H, int64_t capacity) { return scgr::carve_binning(nullptr, W, H, capacity).bytes; }
+// byte offsets into the binning scratch: ranges, the final (tile id, Gaussian id) buffers
+void emu_binning_offsets(int32_t W, int32_t H, int64_t capacity, size_t* off) {
+    const scgr::BinningLayout B = scgr::carve_binning(nullptr, W, H, capacity);
+    const uint32_t n_tiles = (uint32_t)((W + 15) / 16) * (uint32_t)((H + 15) / 16);
+    const int fin = scgr::tile_partition_final_buffer(n_tiles);
+    off[0] = (size_t)B.ranges; off[1] = (size_t)B.vals[fin]; off[2] = (size_t)B.keys[0]; off[3] = (size_t)B.vals[0];
+}
+size_t emu_offsets_offset(int32_t P) { return (size_t)scgr::carve_geometry(nullptr, P).offsets; }
+size_t emu_status_offset(int32_t P) { return (size_t)scgr::carve_geometry(nullptr, P).status; }
+// depth sort (4 radix passes) + scan: everything of stage 1 that follows the preprocess kernel
+int emu_depth_sort_and_scan(const ScgrView* v, const ScgrGaussians* g, void* geometry) {
+    const scgr::GeometryLayout G = scgr::carve_geometry(geometry, g->P);
+    scgr::launch_depth_sort(*v, *g, G, kHost);
+    scgr::launch_scan_offsets(G, g->P, nullptr, kHost);
+    return 0;
+}
+// stage 2 up to the per-tile lists: empty ranges, emission, tile partition (+ ranges in its last pass)
+int emu_emit_and_partition(const ScgrView* v, const ScgrGaussians* g, void* geometry, void* binning, int64_t capacity) {
+    const scgr::GeometryLayout G = scgr::carve_geometry(geometry, g->P);
+    const scgr::BinningLayout B = scgr::carve_binning(binning, v->image_width, v->image_height, capacity);
+    scgr::launch_binning_prologue(*v, B, g->P, capacity, kHost);
+    int fin = -1;
+    scgr::launch_emit_and_partition(*v, G, B, g->P, capacity, &fin, kHost);
+    return fin;
 }
 int emu_mark_visible(const float* means3D, int32_t P, const float* viewmatrix, uint8_t* present) {
     scgr::launch_mark_visible(means3D, P, viewmatrix, present, kHost);

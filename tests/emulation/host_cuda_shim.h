@@ -1,11 +1,11 @@
 // host_cuda_shim.h -- TEST INFRASTRUCTURE (tests/ only; the product never builds or loads this).
 //
-// Just enough of the CUDA programming model to execute the kernels of scgaussian_b200/csrc/{model,preprocess,loss,knn}.cu on the HOST,
+// Just enough of the CUDA programming model to execute the kernels of scgaussian_b200/csrc/{model,preprocess,binning,loss,knn}.cu on the HOST,
 // thread for thread: every block of a launch is run by `blockDim.x` real threads, `__syncthreads()` is a real barrier,
 // `__shared__` arrays are per-process statics (blocks run one after the other).  What this checks before a GPU is
 // available: indexing, bounds, the segment tables, the shared-memory staging and its barrier placement -- against
 // the same oracle and golden vectors as the GPU tests.  What it cannot check: warp intrinsics (none are used by
-// these kernels beyond full-mask __ballot_sync / __shfl_xor_sync), memory-model subtleties, performance.
+// these kernels beyond full-mask votes / shuffles / match / reduce), memory-model subtleties, performance.
 #pragma once
 #include <algorithm>
 #include <barrier>
@@ -60,7 +60,24 @@ static inline float __frcp_rn(float x) { return 1.0f / x; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline int cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return 0; }
-static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicMin(unsigned* p, unsigned v) {
+    unsigned old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+static inline unsigned atomicMax(unsigned* p, unsigned v) {
+    unsigned old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+// dynamic shared memory: `extern __shared__ T name[];` is rewritten to a pointer into this buffer
+alignas(16) static unsigned char g_dyn_smem[256 * 1024];
+#define cudaFuncAttributeMaxDynamicSharedMemorySize 0
+template <class F> static inline int cudaFuncSetAttribute(F, int, int) { return 0; }
 using std::max;
 using std::min;
 
@@ -81,21 +98,41 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     g_warp_barrier[w]->arrive_and_wait();
     return r;
 }
-// warp shuffles (xor pattern): every lane publishes its value, the warp meets, every lane reads its partner's
+// warp shuffles: every lane publishes its value, the warp meets, every lane reads the lane it names (its own value
+// when that lane does not exist, as the hardware does)
 static unsigned long long g_shfl[64][32];
 template <class T>
-static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+static inline T emu_shfl(T v, int src) {
     static_assert(sizeof(T) <= 8, "shuffle of a type wider than 64 bits");
     const unsigned w = threadIdx.x / 32, lane = threadIdx.x % 32;
     unsigned long long bits = 0;
     std::memcpy(&bits, &v, sizeof(T));
     g_shfl[w][lane] = bits;
     g_warp_barrier[w]->arrive_and_wait();
-    const unsigned src = lane ^ (unsigned)lane_mask;
     T out = v;
-    if (src < g_warp_lanes[w]) std::memcpy(&out, &g_shfl[w][src], sizeof(T));
+    if (src >= 0 && (unsigned)src < g_warp_lanes[w]) std::memcpy(&out, &g_shfl[w][src], sizeof(T));
     g_warp_barrier[w]->arrive_and_wait();
     return out;
+}
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return emu_shfl(v, (int)((threadIdx.x % 32) ^ (unsigned)lane_mask)); }
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl(v, src & 31); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
+    const int lane = (int)(threadIdx.x % 32);
+    return emu_shfl(v, lane >= (int)delta ? lane - (int)delta : -1);
+}
+static inline void __syncwarp(unsigned = 0xffffffffu) { g_warp_barrier[threadIdx.x / 32]->arrive_and_wait(); }
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+    unsigned m = v;
+    for (int o = 16; o > 0; o >>= 1) m = std::max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    return m;
+}
+static inline unsigned __match_any_sync(unsigned, unsigned v) {
+    unsigned peers = 0;
+    for (int l = 0; l < 32; l++) {
+        const unsigned other = __shfl_sync(0xffffffffu, v, l);
+        if (other == v && (unsigned)l < g_warp_lanes[threadIdx.x / 32]) peers |= 1u << l;
+    }
+    return peers;
 }
 
 // kernel<<<grid, threads, 0, stream>>>(args) is rewritten (tests/emulation/build.py) into

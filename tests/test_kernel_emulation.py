@@ -1,8 +1,9 @@
-"""The kernels of scgaussian_b200/csrc/{model,preprocess,loss,knn}.cu executed on the HOST, thread for thread
+"""The kernels of scgaussian_b200/csrc/{model,preprocess,binning,loss,knn}.cu executed on the HOST, thread for thread
 (tests/emulation/: the .cu sources compiled with g++ through a small CUDA shim -- real threads per block, real
 barriers, warp votes, shared memory as statics), against the same oracles and reference-generated golden vectors as
 the GPU tests: the model passes (assembly, Adam, statistics, gather, copy) and the per-Gaussian half of the rasterizer
-(preprocess forward / backward, depth keys, markVisible: SURVEY.md section 8a rows a9, a16), the photometric loss
+(preprocess forward / backward, depth keys, markVisible, depth sort, scan, emission, tile partition + ranges:
+SURVEY.md section 8a rows a9-a13, a16), the photometric loss
 (section 8f row f1) and distCUDA2 (row f4).
 
 TEST INFRASTRUCTURE, CPU suite only: it catches indexing / bounds / table / staging mistakes before a GPU is
@@ -424,3 +425,91 @@ def test_knn_kernel_on_host_matches_oracle(emu_loss, n):
     out = torch.full((n,), float("nan"))
     emu_loss.emu_knn3(_p(pts), n, _p(out))
     assert np.allclose(out.numpy(), dist2_knn3(pts.numpy()), rtol=1e-5, atol=1e-7)
+
+
+# 130 tiles (one partition pass); 5000 Gaussians = two radix tiles per pass; rectangles of more than 64 tiles (no survivor
+# mask: the per-row path of the emission); 475 tiles = two partition passes
+@pytest.mark.parametrize("P,W,H,smed,yaw", [(1500, 203, 149, 0.04, 8.0), (5000, 96, 64, 0.05, 0.0), (400, 330, 80, 0.3, -4.0),
+                                            (2500, 400, 300, 0.03, 3.0)])
+def test_binning_on_host_matches_oracle_lists(emu_pre, P, W, H, smed, yaw):
+    """scgaussian_b200/csrc/binning.cu on the host, fed by the emulated preprocess: depth sort (4 onesweep passes with
+    decoupled look-back), chained scan, instance emission, tile partition + ranges (SURVEY.md section 8a rows a10-a13,
+    Appendix A.6 / A.7).  Exact where the algorithm is exact (stable depth order, prefix sums, R), and against the C
+    oracle's per-tile lists the same way the GPU stage test does: ours = the reference's lists minus pairs in which no
+    pixel can reach alpha >= 1/255, in the same order."""
+    from oracle import torch_oracle as O
+    from tests import util
+    case, t, view, g = _host_scene(P, W, H, 3, seed=P + 2, scale_median=smed, w2c=O.yaw_w2c(yaw), z_shift=-1.9)
+    geom, gptr, gv = _geometry(emu_pre, P)
+    radii = torch.zeros(P, dtype=torch.int32)
+    emu_pre.emu_preprocess_forward(C.byref(view), C.byref(g), C.c_void_p(gptr), C.c_void_p(radii.data_ptr()))
+    touched = gv(1, P * 4, torch.int32).numpy().astype(np.int64).copy()
+    emu_pre.emu_depth_sort_and_scan(C.byref(view), C.byref(g), C.c_void_p(gptr))
+    keys_sorted = gv(4, P * 4, torch.int32).numpy().view(np.uint32).copy()      # buffer 0 holds the sorted keys after 4 passes
+    order = gv(5, P * 4, torch.int32).numpy().astype(np.int64).copy()
+    rec = gv(0, P * 48, torch.float32).view(P, 12).numpy()
+    zv = (t["means3D"] @ t["viewmatrix"][:3, 2] + t["viewmatrix"][3, 2]).numpy()
+    # the keys the sort started from: record depth bits in front of the near plane, CULLED behind it
+    emu_lib_keys = np.where(radii.numpy() > 0, rec[:, 6].view(np.uint32), 0)
+    assert np.array_equal(np.sort(order), np.arange(P))
+    assert (np.diff(keys_sorted.astype(np.int64)) >= 0).all()
+    vis = radii.numpy() > 0
+    assert np.array_equal(keys_sorted[np.isin(order, np.nonzero(vis)[0])], emu_lib_keys[order][np.isin(order, np.nonzero(vis)[0])])
+    ties = np.diff(keys_sorted.astype(np.int64)) == 0
+    assert (np.diff(order)[ties] > 0).all()                                       # stable: equal depths keep index order
+    emu_pre.emu_offsets_offset.restype = emu_pre.emu_status_offset.restype = C.c_size_t
+    base = gptr - geom.data_ptr()
+    o_off, s_off = int(emu_pre.emu_offsets_offset(P)), int(emu_pre.emu_status_offset(P))
+    offsets = geom[base + o_off: base + o_off + P * 4].view(torch.int32).numpy().astype(np.int64)
+    status = geom[base + s_off: base + s_off + 16].view(torch.int64).numpy()
+    assert np.array_equal(offsets, np.cumsum(touched[order]))
+    R = int(status[0])
+    assert R == int(touched.sum()) and R > 0 and int(status[1]) == 0
+
+    emu_pre.emu_binning_bytes.restype = C.c_size_t
+    binning = torch.zeros(int(emu_pre.emu_binning_bytes(W, H, C.c_int64(R))) + 64, dtype=torch.uint8)
+    bptr = binning.data_ptr() + (-binning.data_ptr()) % 64
+    emu_pre.emu_emit_and_partition(C.byref(view), C.byref(g), C.c_void_p(gptr), C.c_void_p(bptr), C.c_int64(R))
+    boff = (C.c_size_t * 4)()
+    emu_pre.emu_binning_offsets(W, H, C.c_int64(R), boff)
+    bb = bptr - binning.data_ptr()
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    rg = binning[bb + boff[0]: bb + boff[0] + tiles * 8].view(torch.int32).view(tiles, 2).numpy().astype(np.int64).copy()
+    rg[rg[:, 1] == 0] = 0                                                          # empty tiles are stored as (0xffffffff, 0)
+    pl = binning[bb + boff[1]: bb + boff[1] + R * 4].view(torch.int32).numpy().astype(np.int64)
+    assert int(geom[base + s_off: base + s_off + 16].view(torch.int64)[1]) == 0   # no overflow
+
+    co, (c2, r2, d2, a2), _ = util.run_c_oracle(case)
+    st = co.state()
+    n_rad = int((radii.numpy() != r2).sum())
+    ne = rg[:, 1] > rg[:, 0]
+    assert rg[ne, 0][0] == 0 and rg[ne, 1][-1] == R and np.array_equal(rg[ne, 0][1:], rg[ne, 1][:-1])
+    gx = (W + 15) // 16
+    rank = np.empty(P, dtype=np.int64)
+    rank[order] = np.arange(P)
+    kept = dropped = 0
+    for tile in range(tiles):
+        mine = pl[rg[tile, 0]:rg[tile, 1]]
+        assert (np.diff(rank[mine]) > 0).all(), f"tile {tile}: not in depth order"
+        ref = st["point_list"][st["ranges"][tile, 0]:st["ranges"][tile, 1]].astype(np.int64)
+        if n_rad == 0:
+            pos = {gid: i for i, gid in enumerate(ref)}
+            idx = np.array([pos[gid] for gid in mine], dtype=np.int64)           # KeyError = not a subset of the reference's list
+            assert (np.diff(idx) > 0).all(), f"tile {tile}: order differs from the reference's"
+        gone = np.setdiff1d(ref, mine)
+        kept += len(mine)
+        dropped += len(gone)
+        if len(gone):
+            ty, tx = divmod(tile, gx)
+            ys, xs = np.meshgrid(np.arange(ty * 16, ty * 16 + 16), np.arange(tx * 16, tx * 16 + 16), indexing="ij")
+            dx = st["means2D"][gone, 0][:, None, None] - xs[None]
+            dy = st["means2D"][gone, 1][:, None, None] - ys[None]
+            cn = st["conic"][gone].astype(np.float64)
+            power = -0.5 * (cn[:, 0, None, None] * dx * dx + cn[:, 2, None, None] * dy * dy) - cn[:, 1, None, None] * dx * dy
+            al = t["opacities"].numpy()[gone, 0][:, None, None] * np.exp(power)
+            assert ((al < 1.0 / 255.0) | (power > 0)).all(), f"tile {tile}: a contributing pair was culled"
+    assert kept == R and R <= co.num_rendered and dropped == co.num_rendered - R or n_rad > 0
+    rect = gv(2, P * 8, torch.int32).view(P, 2).numpy().astype(np.int64)
+    area = ((rect[:, 1] & 0xFFFF) - (rect[:, 0] & 0xFFFF)) * ((rect[:, 1] >> 16) - (rect[:, 0] >> 16))
+    if (W, H) == (330, 80):
+        assert (area[vis] > 64).sum() >= 20                                        # the no-mask path was exercised
