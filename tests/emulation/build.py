@@ -102,9 +102,38 @@ _VOLATILE = [   # binning.cu's four inline-PTX statements: volatile global loads
 ]
 
 
+def _replace_fn_body(text: str, name: str, body: str) -> str:
+    """Replaces the body of the (unique) function definition `... name(args) { ... }`."""
+    m = re.search(r"\b" + re.escape(name) + r"\([^)]*\)\s*\{", text)
+    assert m, name
+    a = m.end() - 1
+    depth, b = 0, a
+    while True:
+        depth += text[b] == "{"
+        depth -= text[b] == "}"
+        if depth == 0:
+            break
+        b += 1
+    return text[:a] + "{ " + body + " }" + text[b + 1:]
+
+
+# render.cu's inline PTX, function by function.  The TMA plumbing becomes a synchronous copy: the data is in the
+# staging buffer when bulk_g2s returns, so the mbarrier protocol has nothing left to wait for.
+_RENDER_PTX = {
+    "ex2": "return exp2f(x);",
+    "rcp_approx": "return 1.0f / x;",
+    "gate_pair": "return (pos < lc && power <= 0.f && og_raw >= 1.0f / 255.0f) ? og_raw : 0.f;",
+    "mbar_init": "(void)bar; (void)count;",
+    "mbar_fence_init": "",
+    "mbar_expect_tx": "(void)bar; (void)bytes;",
+    "bulk_g2s": "std::memcpy(dst, src, bytes); (void)bar;",
+    "mbar_wait": "(void)bar; (void)parity;",
+}
+
+
 def build_preprocess() -> str:
-    """preprocess.cu + binning.cu: the whole forward up to the per-tile lists."""
-    srcs = [os.path.join(CSRC, "preprocess.cu"), os.path.join(CSRC, "binning.cu")]
+    """preprocess.cu + binning.cu + render.cu: the whole operator, forward and backward."""
+    srcs = [os.path.join(CSRC, "preprocess.cu"), os.path.join(CSRC, "binning.cu"), os.path.join(CSRC, "render.cu")]
     deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "host_cuda_shim.h"),
                    os.path.join(HERE, "emu_preprocess.cpp"), __file__, os.path.join(ROOT, "include", "scgr.h")]
     if os.path.exists(LIB_PRE) and all(os.path.getmtime(d) <= os.path.getmtime(LIB_PRE) for d in deps):
@@ -123,6 +152,17 @@ def build_preprocess() -> str:
     assert n == 1, "binning.cu: expected one dynamic shared-memory array"
     with open(os.path.join(OUT_DIR, "binning_body.inc"), "w") as f:
         f.write(_rewrite_launches(body, 4))
+    body = open(srcs[2]).read().replace('#include "common.cuh"', "")
+    for name, new in _RENDER_PTX.items():
+        body = _replace_fn_body(body, name, new)
+    assert "asm" not in body, "render.cu: an inline-PTX statement is not covered by _RENDER_PTX"
+    # the variant switches are read once per process in the product; the tests flip them between launches
+    body, n = re.subn(r"static const int (minb|tma) = env_int", r"const int \1 = env_int", body)
+    assert n == 4, n
+    body = body.replace("int env_int(const char* name, int dflt) {", "int env_int_render(const char* name, int dflt) {").replace(
+        "env_int(", "env_int_render(").replace("int env_int_render_render(", "int env_int_render(")
+    with open(os.path.join(OUT_DIR, "render_body.inc"), "w") as f:
+        f.write(_rewrite_launches(body, 3))
     _compile(LIB_PRE, "emu_preprocess.cpp")
     return LIB_PRE
 

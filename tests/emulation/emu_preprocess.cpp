@@ -1,5 +1,5 @@
-// emu_preprocess.cpp -- TEST INFRASTRUCTURE: scgaussian_b200/csrc/preprocess.cu (+ the device helpers of common.cuh)
-// compiled for the host (see host_cuda_shim.h).  `_build/common_host.cuh` and `_build/preprocess_body.inc` are the two
+// emu_preprocess.cpp -- TEST INFRASTRUCTURE: scgaussian_b200/csrc/preprocess.cu, binning.cu and render.cu (+ the device
+// helpers of common.cuh) compiled for the host (see host_cuda_shim.h).  `_build/common_host.cuh` and `_build/preprocess_body.inc` are the two
 // sources with the include of <cuda_runtime.h> dropped, the one inline-PTX statement (sqrt.approx) replaced by sqrtf
 // and the launches rewritten by tests/emulation/build.py; nothing else is changed.
 #define __CUDACC__ 1
@@ -18,6 +18,7 @@ void check_stage(const char*, const Launch&) {}
 
 #include "_build/preprocess_body.inc"
 #include "_build/binning_body.inc"
+#include "_build/render_body.inc"
 
 static const scgr::Launch kHost{nullptr, false};
 
@@ -66,6 +67,32 @@ int emu_emit_and_partition(const ScgrView* v, const ScgrGaussians* g, void* geom
     int fin = -1;
     scgr::launch_emit_and_partition(*v, G, B, g->P, capacity, &fin, kHost);
     return fin;
+}
+size_t emu_image_bytes(int32_t W, int32_t H) { return scgr::carve_image(nullptr, W, H).bytes; }
+void emu_image_offsets(int32_t W, int32_t H, size_t* off) {
+    const scgr::ImageLayout I = scgr::carve_image(nullptr, W, H);
+    off[0] = (size_t)I.n_contrib; off[1] = (size_t)I.final_T;
+}
+static const uint32_t* final_list(const ScgrView* v, const scgr::BinningLayout& B) {
+    const uint32_t n_tiles = (uint32_t)((v->image_width + 15) / 16) * (uint32_t)((v->image_height + 15) / 16);
+    return B.vals[scgr::tile_partition_final_buffer(n_tiles)];
+}
+int emu_render_forward(const ScgrView* v, const ScgrGaussians* g, void* geometry, void* binning, int64_t capacity, void* image,
+                       float* color, float* depth, float* alpha) {
+    const scgr::GeometryLayout G = scgr::carve_geometry(geometry, g->P);
+    const scgr::BinningLayout B = scgr::carve_binning(binning, v->image_width, v->image_height, capacity);
+    const scgr::ImageLayout I = scgr::carve_image(image, v->image_width, v->image_height);
+    scgr::launch_render_forward(*v, G, B, final_list(v, B), capacity, I, color, depth, alpha, kHost);
+    return 0;
+}
+// backward prologue (tile order + zeroed accumulators) + render backward: fills the per-Gaussian ScreenGrad sums
+int emu_render_backward(const ScgrView* v, const ScgrGaussians* g, void* geometry, void* binning, int64_t capacity, void* image,
+                        const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha) {
+    const scgr::GeometryLayout G = scgr::carve_geometry(geometry, g->P);
+    const scgr::BinningLayout B = scgr::carve_binning(binning, v->image_width, v->image_height, capacity);
+    const scgr::ImageLayout I = scgr::carve_image(image, v->image_width, v->image_height);
+    scgr::launch_render_backward(*v, G, B, final_list(v, B), capacity, I, dL_dcolor, dL_ddepth, dL_dalpha, g->P, kHost);
+    return 0;
 }
 int emu_mark_visible(const float* means3D, int32_t P, const float* viewmatrix, uint8_t* present) {
     scgr::launch_mark_visible(means3D, P, viewmatrix, present, kHost);

@@ -1,6 +1,6 @@
 // host_cuda_shim.h -- TEST INFRASTRUCTURE (tests/ only; the product never builds or loads this).
 //
-// Just enough of the CUDA programming model to execute the kernels of scgaussian_b200/csrc/{model,preprocess,binning,loss,knn}.cu on the HOST,
+// Just enough of the CUDA programming model to execute the kernels of scgaussian_b200/csrc/{model,preprocess,binning,render,loss,knn}.cu on the HOST,
 // thread for thread: every block of a launch is run by `blockDim.x` real threads, `__syncthreads()` is a real barrier,
 // `__shared__` arrays are per-process statics (blocks run one after the other).  What this checks before a GPU is
 // available: indexing, bounds, the segment tables, the shared-memory staging and its barrier placement -- against
@@ -72,6 +72,22 @@ static inline unsigned atomicMax(unsigned* p, unsigned v) {
     while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
     return old;
 }
+static inline float atomicAdd(float* p, float v) {
+    unsigned old = __atomic_load_n(reinterpret_cast<unsigned*>(p), __ATOMIC_SEQ_CST), want;
+    float f;
+    do {
+        std::memcpy(&f, &old, 4);
+        f += v;
+        std::memcpy(&want, &f, 4);
+    } while (!__atomic_compare_exchange_n(reinterpret_cast<unsigned*>(p), &old, want, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+    std::memcpy(&f, &old, 4);
+    return f;
+}
+static inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }
+// no device here: callers fall back to their defaults (e.g. 148 SMs)
+enum { cudaSuccess = 0, cudaErrorNoDevice = 100, cudaDevAttrMultiProcessorCount = 16 };
+static inline int cudaGetDevice(int*) { return cudaErrorNoDevice; }
+static inline int cudaDeviceGetAttribute(int*, int, int) { return cudaErrorNoDevice; }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 // dynamic shared memory: `extern __shared__ T name[];` is rewritten to a pointer into this buffer
@@ -126,6 +142,12 @@ static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
     for (int o = 16; o > 0; o >>= 1) m = std::max(m, __shfl_xor_sync(0xffffffffu, m, o));
     return m;
 }
+static inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+    unsigned m = v;
+    for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+    return m;
+}
+static inline int __any_sync(unsigned, int pred) { return __ballot_sync(0xffffffffu, pred) != 0u; }
 static inline unsigned __match_any_sync(unsigned, unsigned v) {
     unsigned peers = 0;
     for (int l = 0; l < 32; l++) {
