@@ -572,3 +572,42 @@ def test_whole_operator_on_host_matches_oracle(emu_pre, monkeypatch, P, W, H, sm
         assert not torch.isnan(v).any(), k
         util.assert_grad_close(k, v.numpy(), np.asarray(want[k]).reshape(v.shape))
         assert float(v.abs().max()) > 0.0, k
+
+
+def test_overflow_flag_on_host_describes_the_last_emission(emu_pre):
+    """The recovery path of SCGR_NEED_CAPACITY at kernel level: an emission into a binning buffer that is too small
+    writes nothing and raises the device flag; the re-run with a large enough buffer (stage 1 kept) clears it and
+    produces the same lists as a first-time run."""
+    from oracle import torch_oracle as O
+    P, W, H = 1200, 160, 120
+    case, t, view, g = _host_scene(P, W, H, 3, seed=9, scale_median=0.05)
+    geom, gptr, gv = _geometry(emu_pre, P)
+    radii = torch.zeros(P, dtype=torch.int32)
+    emu_pre.emu_preprocess_forward(C.byref(view), C.byref(g), C.c_void_p(gptr), C.c_void_p(radii.data_ptr()))
+    emu_pre.emu_depth_sort_and_scan(C.byref(view), C.byref(g), C.c_void_p(gptr))
+    emu_pre.emu_status_offset.restype = emu_pre.emu_binning_bytes.restype = C.c_size_t
+    s_off = (gptr - geom.data_ptr()) + int(emu_pre.emu_status_offset(P))
+    status = geom[s_off: s_off + 16].view(torch.int64)
+    R = int(status[0])
+    assert R > 2000 and int(status[1]) == 0
+
+    def run(capacity):
+        binning = torch.full((int(emu_pre.emu_binning_bytes(W, H, C.c_int64(capacity))) + 64,), 0xAB, dtype=torch.uint8)
+        bptr = binning.data_ptr() + (-binning.data_ptr()) % 64
+        emu_pre.emu_emit_and_partition(C.byref(view), C.byref(g), C.c_void_p(gptr), C.c_void_p(bptr), C.c_int64(capacity))
+        boff = (C.c_size_t * 4)()
+        emu_pre.emu_binning_offsets(W, H, C.c_int64(capacity), boff)
+        bb = bptr - binning.data_ptr()
+        tiles = ((W + 15) // 16) * ((H + 15) // 16)
+        n = min(capacity, R)
+        return (binning[bb + boff[0]: bb + boff[0] + tiles * 8].view(torch.int32).clone(),
+                binning[bb + boff[1]: bb + boff[1] + n * 4].view(torch.int32).clone(),
+                binning[bb + boff[2]: bb + boff[2] + n * 4].clone())
+    _, _, raw_small = run(R // 2)
+    assert int(status[0]) == R and int(status[1]) == 1
+    assert (raw_small == 0xAB).all()                       # nothing was written into the undersized buffer
+    ranges_a, list_a, _ = run(R)
+    assert int(status[1]) == 0                             # the flag describes THIS emission
+    ranges_b, list_b, _ = run(R + 777)                     # over-allocated, as the fused protocol does
+    assert int(status[1]) == 0
+    assert torch.equal(ranges_a, ranges_b) and torch.equal(list_a, list_b)
