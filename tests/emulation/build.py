@@ -10,14 +10,21 @@ import re
 import shutil
 import subprocess
 
+# SCGR_EMU_ASAN=1: AddressSanitizer build (a memcheck of the kernels on the host).  Run the tests as
+#   LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 SCGR_EMU_ASAN=1 \
+#       python -m pytest tests/test_kernel_emulation.py -p no:cacheprovider
+# so that torch's own allocations carry red zones as well: an access past the end of any tensor aborts with the
+# offending line of the kernel source.
+ASAN = os.environ.get("SCGR_EMU_ASAN") == "1"
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(ROOT, "scgaussian_b200", "csrc", "model.cu")
 OUT_DIR = os.path.join(HERE, "_build")
-LIB = os.path.join(OUT_DIR, "libemu_model.so")
+_SUFFIX = "_asan.so" if ASAN else ".so"
+LIB = os.path.join(OUT_DIR, "libemu_model" + _SUFFIX)
 _LAUNCH = re.compile(r"(\w+(?:<[^<>;]*>)?)<<<([^;]+?), (\w+), 0, L\.stream>>>\(\s*([^;]*)\);", re.S)
 CSRC = os.path.join(ROOT, "scgaussian_b200", "csrc")
-LIB_PRE = os.path.join(OUT_DIR, "libemu_preprocess.so")
+LIB_PRE = os.path.join(OUT_DIR, "libemu_preprocess" + _SUFFIX)
 
 
 def build() -> str:
@@ -29,14 +36,7 @@ def build() -> str:
     body = open(SRC).read().replace('#include "common.cuh"', "")
     with open(os.path.join(OUT_DIR, "model_body.inc"), "w") as f:
         f.write(_rewrite_launches(body, 9))
-    gxx = shutil.which("g++")
-    if gxx is None:
-        raise RuntimeError("g++ not found")
-    env = dict(os.environ)
-    env.pop("CC", None)
-    env.pop("CXX", None)
-    subprocess.check_call([gxx, "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-w", "-o", LIB,
-                           os.path.join(HERE, "emu_model.cpp")], env=env, cwd=HERE)
+    _compile(LIB, "emu_model.cpp")
     return LIB
 
 
@@ -90,7 +90,8 @@ def _compile(lib: str, cpp: str) -> None:
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
-    subprocess.check_call([gxx, "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-w", "-o", lib,
+    extra = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if ASAN else []
+    subprocess.check_call([gxx, "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-w", *extra, "-o", lib,
                            os.path.join(HERE, cpp)], env=env, cwd=HERE)
 
 
@@ -176,7 +177,7 @@ def _common_host() -> None:
         f.write(c)
 
 
-LIB_LOSS = os.path.join(OUT_DIR, "libemu_loss_knn.so")
+LIB_LOSS = os.path.join(OUT_DIR, "libemu_loss_knn" + _SUFFIX)
 
 
 def build_loss_knn() -> str:
