@@ -611,3 +611,52 @@ def test_overflow_flag_on_host_describes_the_last_emission(emu_pre):
     ranges_b, list_b, _ = run(R + 777)                     # over-allocated, as the fused protocol does
     assert int(status[1]) == 0
     assert torch.equal(ranges_a, ranges_b) and torch.equal(list_a, list_b)
+
+
+@pytest.mark.parametrize("mode", ["precomp", "sh_deg1_of_2"])
+def test_operator_input_variants_on_host(emu_pre, monkeypatch, mode):
+    """The other input paths of the operator (reference gaussian_renderer/__init__.py:61-87) through the host-emulated
+    kernels: precomputed colour + covariance (no SH, no scale / rotation), and an SH layout other than 16
+    coefficients with the active degree below the maximum (the non-staged SH path)."""
+    from oracle import torch_oracle as O
+    from tests import util
+    monkeypatch.setenv("SCGR_FWD_SPLIT", "50,20")
+    monkeypatch.setenv("SCGR_BWD_SPLIT", "50,20")
+    monkeypatch.setenv("SCGR_TMA", "1")
+    P, W, H = 600, 96, 64
+    if mode == "precomp":
+        case, t, view, g = _host_scene(P, W, H, 2, seed=31, scale_median=0.08, bg=(0.1, 0.1, 0.4), scale_modifier=1.2)
+        gen = torch.Generator().manual_seed(3)
+        col = torch.rand(P, 3, generator=gen)
+        c3 = O.cov3d_from_scale_rot(case["scales"], case["rotations"], case["scale_modifier"])
+        c6 = torch.stack([c3[:, 0, 0], c3[:, 0, 1], c3[:, 0, 2], c3[:, 1, 1], c3[:, 1, 2], c3[:, 2, 2]], -1).contiguous()
+        g = L.ScgrGaussians(P, 0, t["means3D"].data_ptr(), t["opacities"].data_ptr(), None, col.data_ptr(), None, None,
+                            c6.data_ptr())
+        kw = dict(colors_precomp=col, cov3D_precomp=c6)
+        keys = ("means3D", "means2D", "opacities", "colors_precomp", "cov3D_precomp")
+    else:
+        case, t, view, g = _host_scene(P, W, H, 1, seed=32, max_sh_degree=2, scale_median=0.08)      # M = 9, degree 1 active
+        kw = {}
+        keys = ("means3D", "means2D", "opacities", "shs", "scales", "rotations")
+    f = _host_forward(emu_pre, case, t, view, g, P, W, H)
+    grads_up = O.synth_upstream_grads(W, H)
+    co, (c2, r2, d2, a2), want = util.run_c_oracle(case, grads=grads_up, **kw)
+    util.assert_image_close("color", f["color"].numpy(), c2)
+    util.assert_image_close("depth", f["depth"].numpy(), d2)
+    util.assert_image_close("alpha", f["alpha"].numpy(), a2)
+    gC, gD, gA = [x.contiguous() for x in grads_up]
+    emu_pre.emu_render_backward(C.byref(view), C.byref(g), C.c_void_p(f["gptr"]), C.c_void_p(f["bptr"]), C.c_int64(f["R"]),
+                                C.c_void_p(f["iptr"]), _p(gC), _p(gD), _p(gA))
+    M = int(t["shs"].shape[1])
+    shapes = {"means3D": (P, 3), "means2D": (P, 3), "shs": (P, M, 3), "colors_precomp": (P, 3), "opacities": (P, 1),
+              "scales": (P, 3), "rotations": (P, 4), "cov3D_precomp": (P, 6)}
+    outs = {k: torch.full(shapes[k], float("nan")) for k in keys}
+    ptr = lambda k: outs[k].data_ptr() if k in outs else None      # noqa: E731
+    sg = L.ScgrGrads(ptr("means3D"), ptr("means2D"), ptr("shs"), ptr("colors_precomp"), ptr("opacities"), ptr("scales"),
+                     ptr("rotations"), ptr("cov3D_precomp"))
+    emu_pre.emu_preprocess_backward(C.byref(view), C.byref(g), C.c_void_p(f["gptr"]), C.byref(sg))
+    for k, v in outs.items():
+        assert not torch.isnan(v).any(), k
+        util.assert_grad_close(k, v.numpy(), np.asarray(want[k]).reshape(v.shape))
+    if mode != "precomp":
+        assert float(outs["shs"][:, 4:].abs().max()) == 0.0       # rows beyond the active degree stay zero
