@@ -196,5 +196,52 @@ def build_loss_knn() -> str:
     return LIB_LOSS
 
 
+LIB_FULL = os.path.join(OUT_DIR, "libemu_scgr" + _SUFFIX)
+
+
+def build_full() -> str:
+    """The WHOLE library on the host behind its real C entry points -- capi.cu included -- with every exported symbol
+    renamed scgr_* -> emu_scgr_* so that nothing but a test can bind it (scgaussian_b200/_lib.py resolves scgr_* names
+    only: this file cannot stand in for libscgr.so).  One translation unit per .cu file, as in the product build."""
+    names = ["capi", "preprocess", "binning", "render", "loss", "knn", "model"]
+    srcs = [os.path.join(CSRC, n + ".cu") for n in names]
+    header = os.path.join(ROOT, "include", "scgr.h")
+    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "host_cuda_shim.h"), __file__, header]
+    if os.path.exists(LIB_FULL) and all(os.path.getmtime(d) <= os.path.getmtime(LIB_FULL) for d in deps):
+        return LIB_FULL
+    os.makedirs(OUT_DIR, exist_ok=True)
+    build_preprocess()          # writes common_host.cuh and the preprocess / binning / render bodies
+    build_loss_knn()
+    build()
+    hdr = re.sub(r"/\*.*?\*/", "", open(header).read(), flags=re.S)
+    symbols = sorted(set(re.findall(r"\b(scgr_[a-z0-9_]+)\s*\(", hdr)))
+    with open(os.path.join(OUT_DIR, "rename_abi.h"), "w") as f:
+        f.write("// generated: the emulated library exports emu_scgr_* only\n")
+        f.writelines(f"#define {s} emu_{s}\n" for s in symbols)
+    body = open(srcs[0]).read().replace('#include "common.cuh"', "")
+    with open(os.path.join(OUT_DIR, "capi_body.inc"), "w") as f:
+        f.write(body)
+    gxx = shutil.which("g++")
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    extra = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if ASAN else []
+    objs = []
+    for n in names:
+        tu = os.path.join(OUT_DIR, f"tu_{n}.cpp")
+        with open(tu, "w") as f:
+            f.write('#define __CUDACC__ 1\n#include "rename_abi.h"\n#include "../host_cuda_shim.h"\n#include <stdexcept>\n#include <string>\n'
+                    f'#include "common_host.cuh"\n#include "{n}_body.inc"\n')
+            if n == "capi":     # the one launcher that is not emulated: NVSwitch multicast PTX
+                f.write("namespace scgr { void launch_nvls_allreduce(void*, size_t, int, int, const Launch&) {\n"
+                        '    throw std::runtime_error("scgr: the NVLS collective is not part of the host emulation"); } }\n')
+        obj = os.path.join(OUT_DIR, f"tu_{n}{'_asan' if ASAN else ''}.o")
+        subprocess.check_call([gxx, "-O1", "-std=c++20", "-pthread", "-fPIC", "-ffp-contract=off", "-w", *extra, "-c", "-o", obj, tu],
+                              env=env, cwd=OUT_DIR)
+        objs.append(obj)
+    subprocess.check_call([gxx, "-shared", "-pthread", *extra, "-o", LIB_FULL, *objs], env=env, cwd=OUT_DIR)
+    return LIB_FULL
+
+
 if __name__ == "__main__":
-    print(build(), build_preprocess(), build_loss_knn())
+    print(build(), build_preprocess(), build_loss_knn(), build_full())

@@ -84,10 +84,32 @@ static inline float atomicAdd(float* p, float v) {
     return f;
 }
 static inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }
-// no device here: callers fall back to their defaults (e.g. 148 SMs)
-enum { cudaSuccess = 0, cudaErrorNoDevice = 100, cudaDevAttrMultiProcessorCount = 16 };
-static inline int cudaGetDevice(int*) { return cudaErrorNoDevice; }
-static inline int cudaDeviceGetAttribute(int*, int, int) { return cudaErrorNoDevice; }
+// ---- the slice of the CUDA runtime the host side of the library uses.  Everything is synchronous here: a kernel has
+// finished when its launch returns, so streams and events have nothing to order and a "mapped" pinned pointer is the
+// host pointer itself.
+typedef int cudaError_t;
+typedef void* cudaEvent_t;
+enum { cudaSuccess = 0, cudaErrorNotReady = 600, cudaErrorNoDevice = 100, cudaDevAttrMultiProcessorCount = 16,
+       cudaMemcpyDeviceToHost = 2, cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+// device queries: device 0 exists as far as stream bookkeeping goes; attribute queries fail, so callers fall back to
+// their defaults (e.g. 148 SMs)
+static inline cudaError_t cudaGetDevice(int* d) { if (d) *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetAttribute(int*, int, int) { return cudaErrorNoDevice; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "host emulation: no CUDA error"; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = 0; return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = reinterpret_cast<cudaStream_t>(1); return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = reinterpret_cast<cudaEvent_t>(1); return cudaSuccess; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = reinterpret_cast<cudaEvent_t>(1); return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, int, cudaStream_t) { std::memcpy(dst, src, n); return cudaSuccess; }
+static inline cudaError_t cudaHostGetDevicePointer(void** dev, void* host, unsigned) { *dev = host; return cudaSuccess; }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 // dynamic shared memory: `extern __shared__ T name[];` is rewritten to a pointer into this buffer

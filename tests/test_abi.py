@@ -96,6 +96,58 @@ def test_argument_errors_come_back_through_the_c_abi():
     assert rc != 0 and b"null argument" in lib.scgr_last_error()
 
 
+def test_argument_errors_of_the_model_pass_entry_points():
+    """scgr_assemble_* / scgr_adam_step / scgr_densification_stats / scgr_gather_rows / scgr_copy_segments /
+    scgr_knn3_mean_dist2: everything is validated before anything is launched, so this runs without a GPU."""
+    from scgaussian_b200._lib import (ScgrActivated, ScgrAdamGroup, ScgrModel, ScgrModelSet, ScgrRowGather,
+                                      ScgrSegmentCopy)
+    lib = _lib.load()
+    empty = ScgrModelSet(0, *[None] * 9)
+    # a set needs exactly one position source, and every parameter array
+    both = ScgrModelSet(4, 256, 256, 256, 256, 256, 256, 256, 256, 256)
+    m = ScgrModel(15, (ScgrModelSet * 2)(both, empty))
+    out = ScgrActivated(256, 256, 256, 256, 256)
+    assert lib.scgr_assemble_forward(C.byref(m), C.byref(out), None) != 0
+    assert b"either xyz or (rayo, rayd, zval)" in lib.scgr_last_error()
+    no_rest = ScgrModelSet(4, 256, None, None, None, 256, 256, 256, 256, None)
+    m = ScgrModel(15, (ScgrModelSet * 2)(empty, no_rest))
+    assert lib.scgr_assemble_forward(C.byref(m), C.byref(out), None) != 0 and b"features_rest" in lib.scgr_last_error()
+    unaligned = ScgrModelSet(4, 256, None, None, None, 256, 260, 256, 256, 256)
+    m = ScgrModel(15, (ScgrModelSet * 2)(empty, unaligned))
+    assert lib.scgr_assemble_forward(C.byref(m), C.byref(out), None) != 0 and b"16-byte aligned" in lib.scgr_last_error()
+    m = ScgrModel(15, (ScgrModelSet * 2)(empty, empty))
+    assert lib.scgr_assemble_forward(C.byref(m), C.byref(out), None) == 0          # an empty model is a no-op
+    assert lib.scgr_assemble_forward(None, C.byref(out), None) != 0
+    # Adam: table size, step counted from 1, null arrays
+    g = (ScgrAdamGroup * 1)(ScgrAdamGroup(256, 256, 256, 256, 8, 0.1, 0))
+    assert lib.scgr_adam_step(g, 1, 0.9, 0.999, 1e-15, None) != 0 and b"step counts from 1" in lib.scgr_last_error()
+    g = (ScgrAdamGroup * 1)(ScgrAdamGroup(256, None, 256, 256, 8, 0.1, 1))
+    assert lib.scgr_adam_step(g, 1, 0.9, 0.999, 1e-15, None) != 0 and b"null array" in lib.scgr_last_error()
+    assert lib.scgr_adam_step(g, 17, 0.9, 0.999, 1e-15, None) != 0 and b"SCGR_ADAM_MAX_GROUPS" in lib.scgr_last_error()
+    assert lib.scgr_adam_step(g, 1, 1.0, 0.999, 1e-15, None) != 0 and b"betas" in lib.scgr_last_error()
+    assert lib.scgr_adam_step(None, 0, 0.9, 0.999, 1e-15, None) == 0
+    g = (ScgrAdamGroup * 1)(ScgrAdamGroup(None, None, None, None, 0, 0.1, 1))
+    assert lib.scgr_adam_step(g, 1, 0.9, 0.999, 1e-15, None) == 0                   # empty groups are skipped
+    # statistics
+    assert lib.scgr_densification_stats(256, None, None, 4, 256, 256, None, None) != 0
+    assert b"update_filter or radii" in lib.scgr_last_error()
+    assert lib.scgr_densification_stats(256, 256, None, 4, 256, None, None, None) != 0
+    assert lib.scgr_densification_stats(None, None, None, 0, None, None, None, None) == 0
+    # gather / copy
+    a = (ScgrRowGather * 1)(ScgrRowGather(256, None, 3))
+    assert lib.scgr_gather_rows(a, 1, 256, 5, None) != 0 and b"null array" in lib.scgr_last_error()
+    assert lib.scgr_gather_rows(a, 49, 256, 5, None) != 0 and lib.scgr_gather_rows(a, 1, None, 5, None) != 0
+    assert lib.scgr_gather_rows(a, 1, 256, 0, None) == 0
+    c = (ScgrSegmentCopy * 1)(ScgrSegmentCopy(None, 256, 5))
+    assert lib.scgr_copy_segments(c, 1, None) != 0 and b"null destination" in lib.scgr_last_error()
+    c = (ScgrSegmentCopy * 1)(ScgrSegmentCopy(256, 256, -1))
+    assert lib.scgr_copy_segments(c, 1, None) != 0 and lib.scgr_copy_segments(c, 49, None) != 0
+    # distCUDA2
+    assert lib.scgr_knn3_mean_dist2(None, 5, 256, None) != 0 and lib.scgr_knn3_mean_dist2(256, -1, 256, None) != 0
+    assert lib.scgr_knn3_mean_dist2(None, 0, None, None) == 0
+    assert lib.scgr_knn3_mean_dist2(256, (1 << 20) + 1, 256, None) != 0 and b"2^20" in lib.scgr_last_error()
+
+
 def test_host_api_mirrors_reference_operator_surface():
     import diff_gaussian_rasterization as D
     from scgaussian_b200 import GaussianRasterizationSettings, GaussianRasterizer, ScgrError

@@ -703,3 +703,117 @@ def test_whole_operator_on_host_random_scenes(emu_pre, monkeypatch):
             assert not torch.isnan(v).any(), (k, cfg)
             util.assert_grad_close(f"{k} {cfg}", v.numpy(), np.asarray(want[k]).reshape(v.shape))
     assert seen_empty                                  # the sweep includes a view in which nothing is rendered
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The whole library behind its real C entry points (capi.cu included), on the host.  Every exported symbol of this
+# build is renamed scgr_* -> emu_scgr_*: only a test can bind it.
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emu_abi():
+    from tests.emulation import build
+    try:
+        path = build.build_full()
+    except Exception as e:      # pragma: no cover
+        pytest.skip(f"host emulation library not buildable here: {e}")
+    lib = C.CDLL(path)
+    ns = type("EmuAbi", (), {})()
+    for name, (res, args) in L.SYMBOLS.items():
+        fn = getattr(lib, "emu_" + name)          # AttributeError: an entry point of include/scgr.h is missing
+        fn.restype, fn.argtypes = res, args
+        setattr(ns, name, fn)
+    assert not hasattr(lib, "scgr_forward") or True   # (dlsym would find nothing: see the nm check in the test below)
+    ns.path = path
+    return ns
+
+
+def _aligned(nbytes, fill=0):
+    buf = torch.full((int(nbytes) + 256,), fill, dtype=torch.uint8)
+    return buf, buf.data_ptr() + (-buf.data_ptr()) % 256
+
+
+def test_c_abi_on_host_protocols_and_overflow_recovery(emu_abi, monkeypatch):
+    """scgr_forward (both stages, host wait for R on the status word), SCGR_NEED_CAPACITY when the pre-sized binning
+    buffer is too small, completion by scgr_forward_render with stage 1 kept, scgr_backward -- the C-level orchestration
+    of scgaussian_b200/csrc/capi.cu, against the C oracle.  After the recovery the device status reads {R, 0}."""
+    import subprocess
+    from oracle import torch_oracle as O
+    from tests import util
+    exported = subprocess.run(["nm", "-D", "--defined-only", emu_abi.path], capture_output=True, text=True).stdout
+    assert " emu_scgr_forward" in exported and " scgr_forward" not in exported       # cannot stand in for libscgr.so
+    monkeypatch.setenv("SCGR_FWD_SPLIT", "0,0")
+    monkeypatch.setenv("SCGR_BWD_SPLIT", "0,0")
+    P, W, H = 900, 120, 90
+    case, t, view, g = _host_scene(P, W, H, 3, seed=77, scale_median=0.06, bg=(0.1, 0.2, 0.3), z_shift=-1.5)
+    grads_up = O.synth_upstream_grads(W, H)
+    co, (c2, r2, d2, a2), want = util.run_c_oracle(case, grads=grads_up)
+
+    def forward(capacity):
+        geom, gptr = _aligned(emu_abi.scgr_geometry_bytes(P))
+        image, iptr = _aligned(emu_abi.scgr_image_bytes(W, H))
+        binning, bptr = _aligned(emu_abi.scgr_binning_bytes(P, W, H, capacity))
+        radii = torch.zeros(P, dtype=torch.int32)
+        color, depth, alpha = (torch.full((c, H, W), float("nan")) for c in (3, 1, 1))
+        status = torch.zeros(2, dtype=torch.int64)
+        rc = emu_abi.scgr_forward(C.byref(view), C.byref(g), gptr, radii.data_ptr(), bptr, capacity, iptr, color.data_ptr(),
+                                  depth.data_ptr(), alpha.data_ptr(), status.data_ptr(), None)
+        return rc, dict(geom=geom, gptr=gptr, image=image, iptr=iptr, binning=binning, bptr=bptr, radii=radii, color=color,
+                        depth=depth, alpha=alpha, status=status, capacity=capacity)
+
+    rc, big = forward(co.num_rendered + 5000)                       # ample capacity: one call
+    assert rc == 0, emu_abi.scgr_last_error()
+    R = int(big["status"][0])
+    assert 0 < R <= co.num_rendered
+    util.assert_image_close("color", big["color"].numpy(), c2)
+    util.assert_image_close("depth", big["depth"].numpy(), d2)
+    util.assert_image_close("alpha", big["alpha"].numpy(), a2)
+
+    rc, small = forward(R // 3)                                     # too small: stage 1 done, stage 2 refused
+    assert rc == L.NEED_CAPACITY and int(small["status"][0]) == R
+    assert torch.isnan(small["color"]).all()                        # nothing was rendered
+    dv = L.ScgrDebugViews()
+    assert emu_abi.scgr_debug_views(P, W, H, R // 3, small["gptr"], small["bptr"], small["iptr"], C.byref(dv)) == 0
+    dev_status = (C.c_int64 * 2).from_address(C.cast(dv.num_rendered, C.c_void_p).value)
+    assert (dev_status[0], dev_status[1]) == (R, 1)                 # the refused emission raised the flag
+    binning, bptr = _aligned(emu_abi.scgr_binning_bytes(P, W, H, R))
+    rc = emu_abi.scgr_forward_render(C.byref(view), C.byref(g), small["gptr"], bptr, R, small["iptr"], small["color"].data_ptr(),
+                                     small["depth"].data_ptr(), small["alpha"].data_ptr(), small["status"].data_ptr(), None)
+    assert rc == 0, emu_abi.scgr_last_error()
+    assert (dev_status[0], dev_status[1]) == (R, 0)                 # ... and the completed one cleared it
+    assert int(small["status"][0]) == R and int(small["status"][1]) == 0
+    for k in ("color", "depth", "alpha"):
+        assert torch.equal(small[k], big[k]), k                     # bit-identical to the run that never overflowed
+    assert torch.equal(small["radii"], big["radii"])
+
+    gC, gD, gA = [x.contiguous() for x in grads_up]
+    M = int(t["shs"].shape[1])
+    outs = {"means3D": torch.full((P, 3), float("nan")), "means2D": torch.full((P, 3), float("nan")),
+            "shs": torch.full((P, M, 3), float("nan")), "opacities": torch.full((P, 1), float("nan")),
+            "scales": torch.full((P, 3), float("nan")), "rotations": torch.full((P, 4), float("nan"))}
+    sg = L.ScgrGrads(outs["means3D"].data_ptr(), outs["means2D"].data_ptr(), outs["shs"].data_ptr(), None,
+                     outs["opacities"].data_ptr(), outs["scales"].data_ptr(), outs["rotations"].data_ptr(), None)
+    rc = emu_abi.scgr_backward(C.byref(view), C.byref(g), small["gptr"], bptr, R, small["iptr"], gC.data_ptr(), gD.data_ptr(),
+                               gA.data_ptr(), C.byref(sg), None)
+    assert rc == 0, emu_abi.scgr_last_error()
+    for k, v in outs.items():
+        util.assert_grad_close(k, v.numpy(), np.asarray(want[k]).reshape(v.shape))
+
+    # P = 0 through the fused entry point: zero images, not background-filled (SURVEY 8b)
+    g0 = L.ScgrGaussians(0, 16, None, None, None, None, None, None, None)
+    color = torch.full((3, H, W), float("nan"))
+    depth, alpha = torch.full((1, H, W), float("nan")), torch.full((1, H, W), float("nan"))
+    status = torch.full((2,), -1, dtype=torch.int64)
+    image, iptr = _aligned(emu_abi.scgr_image_bytes(W, H))
+    geom, gptr = _aligned(emu_abi.scgr_geometry_bytes(0))
+    binning0, bptr0 = _aligned(emu_abi.scgr_binning_bytes(0, W, H, 16))
+    rc = emu_abi.scgr_forward(C.byref(view), C.byref(g0), gptr, None, bptr0, 16, iptr, color.data_ptr(), depth.data_ptr(),
+                              alpha.data_ptr(), status.data_ptr(), None)
+    assert rc == 0, emu_abi.scgr_last_error()
+    assert int(status[0]) == 0 and float(color.abs().max()) == 0.0 and float(alpha.abs().max()) == 0.0
+
+    # argument errors come back as a status + message, never as an exception across the boundary
+    bad = L.ScgrGaussians(P, 16, t["means3D"].data_ptr(), t["opacities"].data_ptr(), None, None, t["scales"].data_ptr(),
+                          t["rotations"].data_ptr(), None)              # neither shs nor colors_precomp
+    rc = emu_abi.scgr_forward(C.byref(view), C.byref(bad), big["gptr"], big["radii"].data_ptr(), big["bptr"], 10, big["iptr"],
+                              color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), status.data_ptr(), None)
+    assert rc == 1 and b"exactly one of shs / colors_precomp" in emu_abi.scgr_last_error()
