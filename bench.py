@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -352,6 +353,28 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---------------- the whole training step (SURVEY 8f rows f1-f3 around the operator; N = 1 only) ----------------
+    # Not the metric: an extra entry, measured after the timed regions above.  reference train.py:135-208 at the same
+    # size -- raw parameters -> activations + assembly -> operator -> L1 + D-SSIM -> backward -> statistics -> Adam --
+    # with the fused passes of this repo and with the reference's chain of torch ops, same rasterizer and loss kernels.
+    train_step = None
+    if world == 1 and not args.no_train_step:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("scgr_train_step_time", os.path.join(ROOT, "tools", "train_step_time.py"))
+            tst = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(tst)
+            torch.cuda.empty_cache()
+            train_step = tst.measure(sc, cam, dev, WIDTH, HEIGHT, steps=10, warm=3)
+            pk, _ = peaks()
+            ku = train_step.get("fused", {}).get("kernel_us_per_step", {})
+            n_ray, n_bg = train_step["n_ray"], train_step["n_bg"]
+            alg = {"assemble_forward": n_ray * 488 + n_bg * 476, "assemble_backward": P_GAUSS * 508,
+                   "adam": (n_ray * 57 + n_bg * 59) * 28}                # csrc/model.cu: algorithmic bytes per launch
+            train_step["hbm_frac"] = {k: alg[k] / (ku[k] * 1e-6) / 1e9 / pk for k in alg if ku.get(k)}
+        except Exception as e:             # pragma: no cover  (never let the extra entry take the metric down)
+            train_step = {"error": repr(e)[:300]}
+
     # ---------------- roofline of the dominant kernel ----------------
     peak, peak_src = peaks()
     N = WIDTH * HEIGHT
@@ -403,7 +426,7 @@ def main():
                    "grad_allreduce_bytes": flat.nbytes() if world > 1 else 0,
                    "l2": "no explicit flush: one step streams >1 GB (inputs 236 MB + gradients 232 MB + scratch) through the 126 MB L2"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "train_step": train_step,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
