@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SCGR_VERSION 108   /* major*10000 + minor*100 + patch */
+#define SCGR_VERSION 200   /* major*10000 + minor*100 + patch */
 #define SCGR_TILE 16        /* BLOCK_X = BLOCK_Y of the external rasterizer's config.h */
 
 typedef void* scgr_stream_t;   /* cudaStream_t */
@@ -264,7 +264,7 @@ typedef struct ScgrAdamGroup {
     float* exp_avg;
     float* exp_avg_sq;
     int64_t n;
-    float lr;
+    double lr;                   /* divided by the bias correction in double, as torch does, before rounding to fp32 */
     int32_t step;
 } ScgrAdamGroup;
 int scgr_adam_step(const ScgrAdamGroup* groups, int32_t n_groups, double beta1, double beta2, double eps,

@@ -72,7 +72,7 @@ class ScgrModelGrads(C.Structure):
 
 class ScgrAdamGroup(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
-                ("n", C.c_int64), ("lr", C.c_float), ("step", C.c_int32)]
+                ("n", C.c_int64), ("lr", C.c_double), ("step", C.c_int32)]
 
 
 class ScgrRowGather(C.Structure):

@@ -613,7 +613,7 @@ void launch_adam(const ScgrAdamGroup* groups, int32_t n_groups, double beta1, do
         s.p = G.param; s.g = G.grad; s.m = G.exp_avg; s.v = G.exp_avg_sq;
         s.n = (uint32_t)G.n;
         s.first_block = (uint32_t)blocks;
-        s.step_size = (float)((double)G.lr / bc1);
+        s.step_size = (float)(G.lr / bc1);
         s.bc2_sqrt = (float)sqrt(bc2);
         blocks += ((uint64_t)G.n + ADAM_CHUNK - 1) / ADAM_CHUNK;
     }

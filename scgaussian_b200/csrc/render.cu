@@ -323,8 +323,29 @@ render_forward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __rest
                       uint32_t* __restrict__ n_contrib, float* __restrict__ final_T, uint4* __restrict__ tile_todo) {
     __shared__ __align__(16) float4 s_rec[2][96];        // 2 stages x 32 records x {q0, q1, q2}
     __shared__ __align__(8) unsigned long long s_bar[2];
-    if (status[0] > capacity) return;   // binning overflowed: caller re-runs with a larger buffer
     int b = blockIdx.x;
+    if (status[0] > capacity) {
+        // Binning overflowed: the caller re-runs stage 2 with a larger buffer.  Until then the images hold NaN,
+        // so a caller that missed the overflow (it is told by the return value / status word) cannot mistake
+        // uninitialised memory for a rendering.
+        int tile, k0, spw;
+        if (b < ws.n8) { tile = b; k0 = 0; spw = 8; }
+        else if ((b -= ws.n8) < 2 * ws.n4) { tile = ws.n8 + (b >> 1); k0 = (b & 1) << 2; spw = 4; }
+        else { b -= 2 * ws.n4; tile = ws.n8 + ws.n4 + (b >> 2); k0 = (b & 3) << 1; spw = 2; }
+        const int lane = threadIdx.x & 31, lx = lane & 7, ly = lane >> 3;
+        const int X0 = (tile % tiles_x) * TILE, Yr = (tile / tiles_x) * TILE + ((k0 >> 1) << 2);
+        const size_t N = (size_t)W * H;
+        const float nan = __uint_as_float(0x7fc00000u);
+        for (int i = 0; i < spw; i++) {
+            const int px = X0 + ((i & 1) << 3) + lx, py = Yr + ((i >> 1) << 2) + ly;
+            if (px < W && py < H) {
+                const size_t pid = (size_t)py * W + px;
+                out_color[pid] = nan; out_color[N + pid] = nan; out_color[2 * N + pid] = nan;
+                out_depth[pid] = nan; out_alpha[pid] = nan;
+            }
+        }
+        return;
+    }
 #define SCGR_ARGS s_rec, s_bar, ranges, point_list, rec, W, H, bg, out_color, out_depth, out_alpha, n_contrib, final_T, tile_todo
     if (b < ws.n8) { forward_region<8, TMA>(b, tiles_x, 0, SCGR_ARGS); return; }
     b -= ws.n8;

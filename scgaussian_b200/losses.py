@@ -44,7 +44,11 @@ class _Photometric(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image, gt, lambda_dssim: float, which: int):
         lib = _lib.load()
-        image, gt = _prep(image), _prep(gt)
+        # (fp32 / contiguity casts happen in _apply, outside the Function, so that autograd itself hands the
+        # gradient back in the dtype of the caller's tensor)
+        if ctx.needs_input_grad[1]:
+            raise ScgrError("the fused photometric loss does not differentiate with respect to its target (the "
+                            "reference's gt image is data, train.py:147); detach it or swap the arguments")
         if image.shape != gt.shape:
             raise ScgrError(f"image {tuple(image.shape)} and gt {tuple(gt.shape)} differ in shape")
         c, h, w = _planes(image)
@@ -81,18 +85,22 @@ class _Photometric(torch.autograd.Function):
         return grad, None, None, None
 
 
+def _apply(image: torch.Tensor, gt: torch.Tensor, lambda_dssim: float, which: int) -> torch.Tensor:
+    return _Photometric.apply(_prep(image), _prep(gt), lambda_dssim, which)
+
+
 def photometric_loss(image: torch.Tensor, gt: torch.Tensor, lambda_dssim: float = 0.2) -> torch.Tensor:
     """reference train.py:160-161: (1 - lambda_dssim) * l1_loss(image, gt) + lambda_dssim * (1 - ssim(image, gt))."""
-    return _Photometric.apply(image, gt, lambda_dssim, 2)
+    return _apply(image, gt, lambda_dssim, 2)
 
 
 def l1_loss(network_output: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
     """reference utils/loss_utils.py:40-41."""
-    return _Photometric.apply(network_output, gt, 0.0, 0)
+    return _apply(network_output, gt, 0.0, 0)
 
 
 def ssim(img1: torch.Tensor, img2: torch.Tensor, window_size: int = 11, size_average: bool = True, mask=None) -> torch.Tensor:
     """reference utils/loss_utils.py:56-94 for the arguments its training step uses."""
     if window_size != 11 or not size_average or mask is not None:
         raise ScgrError("fused ssim supports window_size=11, size_average=True, mask=None (what reference train.py:161 uses)")
-    return _Photometric.apply(img1, img2, 1.0, 1)
+    return _apply(img1, img2, 1.0, 1)

@@ -36,8 +36,11 @@ class Adam(torch.optim.Optimizer):
                         capturable=False, differentiable=False, fused=None)
         super().__init__(params, defaults)
 
-    def _collect(self, work):
-        """Appends this optimizer's updates to `work`: (device, beta1, beta2, eps) -> [ScgrAdamGroup ...]."""
+    def _collect(self, work, bumped):
+        """Appends this optimizer's updates to `work`: (device, beta1, beta2, eps) -> [ScgrAdamGroup ...].
+        Two passes: every parameter is validated (and its state created) first; only then are the step counts
+        advanced -- recorded in `bumped` so that the caller can roll them back if the launch fails."""
+        todo = []
         for group in self.param_groups:
             if group.get("weight_decay", 0) != 0 or group.get("amsgrad", False) or group.get("maximize", False):
                 raise ScgrError("fused Adam: weight_decay / amsgrad / maximize are not implemented")
@@ -63,11 +66,14 @@ class Adam(torch.optim.Optimizer):
                 if m.shape != p.shape or v.shape != p.shape or not m.is_contiguous() or not v.is_contiguous() \
                         or m.dtype != torch.float32 or v.dtype != torch.float32 or m.device != p.device:
                     raise ScgrError("fused Adam: optimizer state does not match its parameter (shape / dtype / device)")
-                state["step"] += 1
-                step = int(state["step"].item()) if isinstance(state["step"], torch.Tensor) else int(state["step"])
-                key = (p.device, float(beta1), float(beta2), float(group["eps"]))
-                work[key].append((ScgrAdamGroup(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(),
-                                                p.numel(), float(group["lr"]), step), grad))
+                todo.append((p, grad, state, m, v, group, float(beta1), float(beta2)))
+        for p, grad, state, m, v, group, beta1, beta2 in todo:
+            state["step"] += 1
+            bumped.append(state)
+            step = int(state["step"].item()) if isinstance(state["step"], torch.Tensor) else int(state["step"])
+            key = (p.device, beta1, beta2, float(group["eps"]))
+            work[key].append((ScgrAdamGroup(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                            p.numel(), float(group["lr"]), step), grad))
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -75,10 +81,20 @@ class Adam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        work = defaultdict(list)
-        self._collect(work)
-        _launch(work)
+        work, bumped = defaultdict(list), []
+        try:
+            self._collect(work, bumped)
+            _launch(work)
+        except Exception:
+            _rollback(bumped)
+            raise
         return loss
+
+
+def _rollback(bumped) -> None:
+    """A failed step leaves every step count where it was (no update was applied for it)."""
+    for state in bumped:
+        state["step"] -= 1
 
 
 def _launch(work) -> None:
@@ -96,9 +112,14 @@ def _launch(work) -> None:
 def step_all(*optimizers: Adam) -> None:
     """Steps several fused optimizers in one launch (reference train.py:204-208 steps `optimizer` and
     `optimizer_bg` back to back: 12 parameter groups, all with the same betas / eps)."""
-    work = defaultdict(list)
+    work, bumped = defaultdict(list), []
     for opt in optimizers:
         if not isinstance(opt, Adam):
             raise ScgrError("step_all takes scgaussian_b200.optim.Adam optimizers")
-        opt._collect(work)
-    _launch(work)
+    try:
+        for opt in optimizers:
+            opt._collect(work, bumped)
+        _launch(work)
+    except Exception:
+        _rollback(bumped)
+        raise

@@ -53,6 +53,7 @@ _BINNING_MODE = os.environ.get("SCGR_BINNING", "fused")
 _capacity_hint = {}        # device index -> last num_rendered
 _pinned_status = {}        # (device index, thread id) -> pinned int64[2]
 launch_counter = 0         # number of libscgr stage calls (bench.py reports kernels from this)
+need_capacity_count = 0    # forwards whose pre-sized binning buffer was too small (finished by a second stage-2 call)
 
 
 def _status_buffer(device: torch.device) -> torch.Tensor:
@@ -113,7 +114,7 @@ def rasterize_forward_raw(means3D, opacities, sh, colors_precomp, scales, rotati
                           s: GaussianRasterizationSettings):
     """Runs the two forward stages of libscgr on the current stream.  Inputs must be contiguous fp32
     CUDA tensors (or None).  Returns (color, radii, depth, alpha, ForwardState)."""
-    global launch_counter
+    global launch_counter, need_capacity_count
     lib = _lib.load()
     device = means3D.device
     if device.type != "cuda":
@@ -134,12 +135,16 @@ def rasterize_forward_raw(means3D, opacities, sh, colors_precomp, scales, rotati
         status = _status_buffer(device)
         key = device.index
 
-        def run_render(capacity: int) -> torch.Tensor:
+        def run_render(capacity: int, want_status: bool = False) -> torch.Tensor:
+            # `status` is the shared pinned word scgr_forward() spins on.  An asynchronous {R, overflow} copy into
+            # it that is still in flight when the NEXT forward stores its sentinel would land on top of the
+            # sentinel and be taken for that view's R (no host sync separates two forwards): it is therefore
+            # requested only by the one protocol that synchronises the stream right after ("optimistic").
             global launch_counter
             binning = _scratch(lib.scgr_binning_bytes(P, W, H, capacity), device)
             check(lib.scgr_forward_render(C.byref(view), C.byref(g), geometry.data_ptr(), binning.data_ptr(),
                                           capacity, image.data_ptr(), color.data_ptr(), depth.data_ptr(),
-                                          alpha.data_ptr(), status.data_ptr(), stream))
+                                          alpha.data_ptr(), status.data_ptr() if want_status else None, stream))
             launch_counter += 1
             return binning
 
@@ -152,6 +157,7 @@ def rasterize_forward_raw(means3D, opacities, sh, colors_precomp, scales, rotati
                                   depth.data_ptr(), alpha.data_ptr(), status.data_ptr(), stream)
             launch_counter += 1
             if rc == _lib.NEED_CAPACITY:      # this view outgrew the headroom: stage 1 is done, R is known
+                need_capacity_count += 1
                 R = int(status[0])
                 capacity = R
                 binning = run_render(capacity)
@@ -164,10 +170,11 @@ def rasterize_forward_raw(means3D, opacities, sh, colors_precomp, scales, rotati
             check(lib.scgr_forward_geometry(C.byref(view), C.byref(g), geometry.data_ptr(), radii.data_ptr(),
                                             None, stream))
             launch_counter += 1
-            binning = run_render(capacity)
+            binning = run_render(capacity, want_status=True)
             torch.cuda.current_stream(device).synchronize()
             R, overflow = int(status[0]), int(status[1])
             if overflow or R > capacity:
+                need_capacity_count += 1
                 capacity = R
                 binning = run_render(capacity)
         else:

@@ -32,7 +32,7 @@ def test_library_exports_every_header_symbol():
 
 def test_version_and_scratch_sizes():
     lib = _lib.load()
-    assert lib.scgr_version() == 108
+    assert lib.scgr_version() == 200
     g1, g2 = lib.scgr_geometry_bytes(1000), lib.scgr_geometry_bytes(1_000_000)
     assert 0 < g1 < g2 and g2 % 256 == 0
     # per-Gaussian footprint stays well under the reference's own geomBuffer + our gradient staging

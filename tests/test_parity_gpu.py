@@ -370,6 +370,39 @@ def test_binning_modes_agree(dev, monkeypatch):
     assert e[4].num_rendered == 0 and float(e[0].abs().max()) == 0.0
 
 
+def test_back_to_back_views_without_host_sync(dev, monkeypatch):
+    """Two different views enqueued back to back with no host synchronisation in between (round-1 ADVICE: an
+    asynchronous {R, overflow} copy of view A still in flight could land on the sentinel view B's forward
+    spins on, and be taken for B's instance count).  Every entry path that precedes a fused forward is
+    exercised: the very first forward of a device (no hint: two-call protocol) and a NEED_CAPACITY recovery."""
+    from scgaussian_b200 import rasterizer as R
+    A = util.make_case(200_000, 640, 480, scale_median=0.02)                 # R ~ 1e6: stage 2 takes a while
+    B = util.make_case(3000, 640, 480, scale_median=0.02, seed=5)            # a much smaller R
+    sA, sB = settings_for(A, dev), settings_for(B, dev)
+    tA = {k: A[k].to(dev).contiguous() for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+    tB = {k: B[k].to(dev).contiguous() for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+    aA = (tA["means3D"], tA["opacities"], tA["shs"], None, tA["scales"], tA["rotations"], None, sA)
+    aB = (tB["means3D"], tB["opacities"], tB["shs"], None, tB["scales"], tB["rotations"], None, sB)
+    monkeypatch.setattr(R, "_BINNING_MODE", "sync")
+    refA, refB = R.rasterize_forward_raw(*aA), R.rasterize_forward_raw(*aB)
+    torch.cuda.synchronize()
+    monkeypatch.setattr(R, "_BINNING_MODE", "fused")
+    for prime in ("first_forward", "need_capacity"):
+        if prime == "first_forward":
+            R._capacity_hint.pop(dev.index, None)        # view A goes through geometry + sync + run_render
+        else:
+            R._capacity_hint[dev.index] = 16             # view A comes back with SCGR_NEED_CAPACITY -> run_render
+        for _ in range(3):
+            outA = R.rasterize_forward_raw(*aA)
+            outB = R.rasterize_forward_raw(*aB)          # no .item(), no synchronize in between
+            assert outA[4].num_rendered == refA[4].num_rendered, prime
+            assert outB[4].num_rendered == refB[4].num_rendered, prime
+            assert torch.equal(outB[0], refB[0]) and torch.equal(outA[0], refA[0]), prime
+            if prime == "need_capacity":
+                R._capacity_hint[dev.index] = 16
+    report("back_to_back", R_A=int(refA[4].num_rendered), R_B=int(refB[4].num_rendered))
+
+
 def test_binning_capacity_overflow_is_recovered(dev, monkeypatch):
     from scgaussian_b200 import rasterizer as R
     case = util.make_case(4000, 160, 120, scale_median=0.05)
