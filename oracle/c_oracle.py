@@ -48,7 +48,7 @@ class COracle:
         self.lib.scgo_forward.restype = C.c_void_p
         self.lib.scgo_num_rendered.restype = C.c_int64
         for f in ("scgo_point_list", "scgo_ranges", "scgo_means2D", "scgo_conic", "scgo_rgb",
-                  "scgo_depths", "scgo_tiles_touched", "scgo_n_contrib"):
+                  "scgo_depths", "scgo_tiles_touched", "scgo_n_contrib", "scgo_geom_margin"):
             getattr(self.lib, f).restype = C.c_void_p
         self._state = None
         self._keep = None
@@ -125,6 +125,20 @@ class COracle:
                     depths=self._view("scgo_depths", self.np_real, P),
                     tiles_touched=self._view("scgo_tiles_touched", np.int32, P),
                     n_contrib=self._view("scgo_n_contrib", np.int32, W * H).reshape(H, W))
+
+    def margins(self, eps_alpha=2e-3, eps_T=2e-3, eps_power=1e-4, eps_geom=2e-3):
+        """Which outputs a flipped discrete decision could touch (scg_oracle.c: scgo_margins).  Returns
+        pix_margin [3,H,W] (minima of |255 alpha - 1|, |T / 1e-4 - 1|, |power| over the entries a pixel visits),
+        pix_flag [H,W] bool (flip-prone pixels), gauss_flag [P] bool (flip-affected Gaussians), geom_margin [P]."""
+        P, M, W, H = self._dims
+        pm = np.zeros((3, H, W), self.np_real)
+        pf = np.zeros((H, W), np.uint8)
+        gf = np.zeros(max(P, 1), np.uint8)
+        self.lib.scgo_margins(self._state, C.c_double(eps_alpha), C.c_double(eps_T), C.c_double(eps_power),
+                              C.c_double(eps_geom), self._p(pm), pf.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                              gf.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        return dict(pix_margin=pm, pix_flag=pf.astype(bool), gauss_flag=gf[:P].astype(bool),
+                    geom_margin=self._view("scgo_geom_margin", self.np_real, P))
 
     def free(self):
         if self._state is not None:

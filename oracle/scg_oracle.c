@@ -61,6 +61,8 @@ typedef struct {
     REAL *depth, *xy, *conic, *rgb, *cov3D;
     int *radii, *rect, *tiles;
     unsigned char *clamped;
+    REAL *geom_margin;         /* distance (pixels) of the pre-ceil radius and of the four rect edges to the value at
+                                  which the integer decision (ceil / truncation to a tile index) would change */
     /* binning */
     int64_t R;
     uint32_t *point_list;
@@ -181,7 +183,7 @@ void scgo_free(scgo_state *s) {
     if (!s) return;
     free(s->depth); free(s->xy); free(s->conic); free(s->rgb); free(s->cov3D); free(s->radii);
     free(s->rect); free(s->tiles); free(s->clamped); free(s->point_list); free(s->ranges);
-    free(s->n_contrib); free(s->final_T); free(s);
+    free(s->n_contrib); free(s->final_T); free(s->geom_margin); free(s);
 }
 
 int scgo_real_size(void) { return (int)sizeof(REAL); }
@@ -209,6 +211,7 @@ scgo_state *scgo_forward(const scgo_inputs *in, REAL *out_color, REAL *out_depth
     s->cov3D = (REAL *)calloc(6 * Pa, sizeof(REAL)); s->radii = (int *)calloc(Pa, sizeof(int));
     s->rect = (int *)calloc(4 * Pa, sizeof(int)); s->tiles = (int *)calloc(Pa, sizeof(int));
     s->clamped = (unsigned char *)calloc(3 * Pa, 1);
+    s->geom_margin = (REAL *)calloc(Pa, sizeof(REAL));
     s->ranges = (int64_t *)calloc(2 * (size_t)Tn, sizeof(int64_t));
     s->n_contrib = (int *)calloc((size_t)W * H, sizeof(int));
     s->final_T = (REAL *)calloc((size_t)W * H, sizeof(REAL));
@@ -247,6 +250,12 @@ scgo_state *scgo_forward(const scgo_inputs *in, REAL *out_color, REAL *out_depth
         REAL px = ((ndcx + 1) * W - 1) * (REAL)0.5, py = ((ndcy + 1) * H - 1) * (REAL)0.5;
         int x0 = iclamp((int)((px - rad) / BLK), 0, s->gx), y0 = iclamp((int)((py - rad) / BLK), 0, s->gy);
         int x1 = iclamp((int)((px + rad + BLK - 1) / BLK), 0, s->gx), y1 = iclamp((int)((py + rad + BLK - 1) / BLK), 0, s->gy);
+        {   /* margins of the integer decisions above (test infrastructure: scgo_margins) */
+            double rv = 3.0 * sqrt((double)lam), gm = fabs(rv - floor(rv + 0.5));
+            double e[4] = {(double)px - rad, (double)py - rad, (double)px + rad + BLK - 1, (double)py + rad + BLK - 1};
+            for (int q = 0; q < 4; q++) { double f = e[q] / BLK, d = fabs(f - floor(f + 0.5)) * BLK; if (d < gm) gm = d; }
+            s->geom_margin[i] = (REAL)gm;
+        }
         if ((x1 - x0) * (y1 - y0) == 0) continue;
         if (use_sh) {                                                 /* A.5 */
             double dx = p[0] - in->campos[0], dy = p[1] - in->campos[1], dz = p[2] - in->campos[2];
@@ -526,3 +535,96 @@ void scgo_backward(const scgo_state *s, const REAL *gC, const REAL *gD, const RE
     }
     free(acc);
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Margins of the discrete decisions (parity-test support).  The rasterizer takes four kinds of yes/no decisions
+ * whose outcome a 1-ulp difference in fp32 arithmetic can flip:
+ *   (a) alpha = opacity * exp(power) >= 1/255           (A.8 skip)            margin: |alpha_raw * 255 - 1|
+ *   (b) test_T = T (1 - alpha) >= 1e-4                  (A.8 early stop)      margin: |test_T / 1e-4 - 1|
+ *   (c) power <= 0                                      (A.8 skip)            margin: |power|
+ *   (d) radius = ceil(3 sqrt(lambda)), tile rect = trunc((pix -/+ radius) / 16)   margin: pixels (geom_margin)
+ * A pixel is FLIP-PRONE when some list entry it visits (the terminating one included) comes within eps of (a), (b)
+ * or (c), or when a Gaussian within eps of (d) could reach it with alpha >= (1 - eps_alpha) / 255.  A Gaussian is
+ * FLIP-AFFECTED when it (nearly) contributes to a flip-prone pixel -- every gradient of such a Gaussian changes
+ * with the flip (through T and through the suffix blend) -- or is itself within eps of (d).
+ * pix_margin[3][H*W] receives the per-pixel minima of (a), (b), (c); pix_flag[H*W] / gauss_flag[P] the two sets. */
+void scgo_margins(const scgo_state *s, double eps_alpha, double eps_T, double eps_power, double eps_geom,
+                  REAL *pix_margin, unsigned char *pix_flag, unsigned char *gauss_flag) {
+    const scgo_inputs *in = &s->in;
+    const int P = in->P, W = in->W, H = in->H, Tn = s->gx * s->gy;
+    const size_t N = (size_t)W * H;
+    for (size_t i = 0; i < 3 * N; i++) pix_margin[i] = (REAL)1e30;
+    memset(pix_flag, 0, N);
+    memset(gauss_flag, 0, P > 0 ? P : 0);
+    if (P == 0) return;
+    /* pass 1: per-pixel minima over the entries the forward visits */
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int t = 0; t < Tn; t++) {
+        int tx = t % s->gx, ty = t / s->gx;
+        int64_t r0 = s->ranges[2 * t], r1 = s->ranges[2 * t + 1];
+        for (int ly = 0; ly < BLK; ly++) for (int lx = 0; lx < BLK; lx++) {
+            int px = tx * BLK + lx, py = ty * BLK + ly;
+            if (px >= W || py >= H) continue;
+            double ma = 1e30, mt = 1e30, mp = 1e30;
+            REAL T = 1;
+            for (int64_t j = r0; j < r1; j++) {
+                uint32_t g = s->point_list[j];
+                REAL dx = s->xy[2 * g] - px, dy = s->xy[2 * g + 1] - py;
+                const REAL *co = s->conic + 3 * g;
+                REAL power = (REAL)-0.5 * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+                double araw = (double)in->opacities[g] * exp((double)power);
+                if (araw * 255.0 >= 1.0 - eps_alpha && fabs((double)power) < mp) mp = fabs((double)power);
+                if (power > 0) continue;
+                double da = fabs(araw * 255.0 - 1.0);
+                if (da < ma) ma = da;
+                REAL alpha = rmin(ALPHA_MAX, (REAL)araw);
+                if (alpha < ALPHA_MIN) continue;
+                REAL test_T = T * (1 - alpha);
+                double dt = fabs((double)test_T / 1e-4 - 1.0);
+                if (dt < mt) mt = dt;
+                if (test_T < T_EPS) break;
+                T = test_T;
+            }
+            size_t pid = (size_t)py * W + px;
+            pix_margin[pid] = (REAL)ma; pix_margin[N + pid] = (REAL)mt; pix_margin[2 * N + pid] = (REAL)mp;
+            if (ma < eps_alpha || mt < eps_T || mp < eps_power) pix_flag[pid] = 1;
+        }
+    }
+    /* (d): Gaussians whose radius / rect could differ by one: every pixel of the rect grown by one tile that
+     * they could reach is flip-prone, and they are flip-affected themselves */
+    for (int i = 0; i < P; i++) {
+        if (s->radii[i] <= 0 || (double)s->geom_margin[i] >= eps_geom) continue;
+        gauss_flag[i] = 1;
+        int x0 = iclamp(s->rect[4 * i] - 1, 0, s->gx) * BLK, y0 = iclamp(s->rect[4 * i + 1] - 1, 0, s->gy) * BLK;
+        int x1 = iclamp(s->rect[4 * i + 2] + 1, 0, s->gx) * BLK, y1 = iclamp(s->rect[4 * i + 3] + 1, 0, s->gy) * BLK;
+        if (x1 > W) x1 = W;
+        if (y1 > H) y1 = H;
+        const REAL *co = s->conic + 3 * i;
+        for (int py = y0; py < y1; py++) for (int px = x0; px < x1; px++) {
+            REAL dx = s->xy[2 * i] - px, dy = s->xy[2 * i + 1] - py;
+            REAL power = (REAL)-0.5 * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+            if ((double)in->opacities[i] * exp((double)power) * 255.0 >= 1.0 - eps_alpha) pix_flag[(size_t)py * W + px] = 1;
+        }
+    }
+    /* pass 2: Gaussians that (nearly) contribute to a flip-prone pixel.  The whole list is walked: a flipped early
+     * stop lets entries behind the oracle's terminating one contribute. */
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int t = 0; t < Tn; t++) {
+        int tx = t % s->gx, ty = t / s->gx;
+        int64_t r0 = s->ranges[2 * t], r1 = s->ranges[2 * t + 1];
+        for (int ly = 0; ly < BLK; ly++) for (int lx = 0; lx < BLK; lx++) {
+            int px = tx * BLK + lx, py = ty * BLK + ly;
+            if (px >= W || py >= H || !pix_flag[(size_t)py * W + px]) continue;
+            for (int64_t j = r0; j < r1; j++) {
+                uint32_t g = s->point_list[j];
+                if (gauss_flag[g]) continue;
+                REAL dx = s->xy[2 * g] - px, dy = s->xy[2 * g + 1] - py;
+                const REAL *co = s->conic + 3 * g;
+                REAL power = (REAL)-0.5 * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+                if ((double)power > eps_power) continue;
+                if ((double)in->opacities[g] * exp((double)power) * 255.0 >= 1.0 - eps_alpha) gauss_flag[g] = 1;   /* benign race: all writers store 1 */
+            }
+        }
+    }
+}
+const REAL *scgo_geom_margin(const scgo_state *s) { return s->geom_margin; }

@@ -305,17 +305,25 @@ def test_fused_render_matches_reference_style_render():
     loss_of(out2).backward()
 
     assert set(out1) == {"render", "rendered_depth", "rendered_alpha", "viewspace_points", "visibility_filter", "radii"}
-    assert out1["radii"].dtype == torch.int32 and int((out1["radii"] != radii).sum()) <= 2   # ceil() of a last-bit change
     assert torch.equal(out1["visibility_filter"], out1["radii"] > 0)
-    # activations may differ in the last bit between the fused kernel and torch's: same allowance for isolated
-    # discrete flips (alpha < 1/255, T < 1e-4) as the rasterizer parity tests
+    # activations may differ in the last bit between the fused kernel and torch's, which can flip a discrete decision
+    # of the rasterizer (alpha < 1/255, T < 1e-4, ceil of the radius): the C oracle, run on the torch-activated
+    # inputs, says which pixels / Gaussians sit that close to a threshold -- nothing else may differ (tests/util.py)
+    from tests.util import assert_radii_match, flip_sets, run_c_oracle
+    act = dict(case, means3D=xyz.detach().cpu(), scales=scal.detach().cpu(), rotations=rot.detach().cpu(),
+               opacities=opa.detach().cpu(), shs=shs.detach().cpu(), bg=bgc.cpu())
+    flips = flip_sets(run_c_oracle(act)[0])
+    assert out1["radii"].dtype == torch.int32
+    assert_radii_match("radii", out1["radii"].cpu().numpy(), radii.cpu().numpy(), flips)
     for k in out2:
-        assert_image_close(k, out1[k].detach().cpu().numpy(), out2[k].detach().cpu().numpy())
-    assert_grad_close("viewspace_points", out1["viewspace_points"].grad.cpu().numpy(), ssp.grad.cpu().numpy())
+        assert_image_close(k, out1[k].detach().cpu().numpy(), out2[k].detach().cpu().numpy(), flips)
+    assert_grad_close("viewspace_points", out1["viewspace_points"].grad.cpu().numpy(), ssp.grad.cpu().numpy(), flips)
+    n_ray_flags = {True: flips["gauss_flag"][:n_ray], False: flips["gauss_flag"][n_ray:]}
     for n in TRAINED:
         a, b = getattr(pc1, n).grad, getattr(pc2, n).grad
         assert a is not None and b is not None, n
-        assert_grad_close(n, a.cpu().numpy(), b.cpu().numpy())
+        part = dict(flips, gauss_flag=n_ray_flags[not n.startswith("bg_")])
+        assert_grad_close(n, a.cpu().numpy(), b.cpu().numpy(), part)
 
 
 @pytest.mark.gpu

@@ -184,19 +184,29 @@ def test_edge_cases_cpu():
     ct, rt, dt_, at = O.rasterize(case["means3D"], None, case["opacities"], so, shs=case["shs"],
                                   scales=case["scales"], rotations=case["rotations"])
     co, (c2, r2, d2, a2), _ = util.run_c_oracle(case)
-    util.assert_image_close("ragged color", c2, ct.numpy())
+    util.assert_image_close("ragged color", c2, ct.numpy(), util.flip_sets(co))
     assert (np.abs(r2 - rt.numpy()) <= 1).all() and (r2 != rt.numpy()).mean() < 0.02
     assert math.isfinite(float(c2.sum()))
 
 
-def test_f32_f64_oracles_differ_only_by_isolated_flips():
-    """Documents why the GPU-vs-oracle gradient check allows a few outliers: the two builds of the
-    SAME C oracle differ by isolated discrete flips in fp32."""
+def test_f32_f64_oracles_differ_only_where_a_decision_sits_on_its_threshold():
+    """Why the parity compares carry a flip allowance at all, and that the allowance is PROVEN per element: the
+    float32 and float64 builds of the SAME C oracle differ beyond 1e-3 on a few gradient rows of this scene -- and
+    every one of them belongs to a Gaussian that touches a pixel in which a discrete decision (alpha >= 1/255,
+    T >= 1e-4) sits within EPS of its threshold (oracle/scg_oracle.c: scgo_margins).  Nothing else is excused."""
     case = util.make_case(5000, 378, 504, sh_degree=0, scale_median=0.03, w2c=O.yaw_w2c(5.0))
     grads = O.synth_upstream_grads(378, 504)
-    _, _, g32 = util.run_c_oracle(case, "f32", grads=grads)
-    _, _, g64 = util.run_c_oracle(case, "f64", grads=grads)
+    co32, img32, g32 = util.run_c_oracle(case, "f32", grads=grads)
+    co64, img64, g64 = util.run_c_oracle(case, "f64", grads=grads)
+    flips = util.flip_sets(co32)
+    assert 0 < flips["pix_flag"].mean() < 0.01 and 0 < flips["gauss_flag"].mean() < 0.15
+    beyond = 0
     for k in ("means3D", "means2D", "opacities", "shs", "scales", "rotations"):
-        util.assert_grad_close(k, g32[k], g64[k])
-        err = np.abs(g32[k] - g64[k]) / np.abs(g64[k]).max()
-        assert (err > 1e-4).mean() < 2e-3
+        st = util.assert_grad_close(k, g32[k], g64[k], flips)
+        beyond += st["n_beyond_rtol"]
+        assert st["max_err_unexcusable"] < 3e-4, (k, st)
+    assert beyond > 0          # the scene does contain flips: without the proof this test would fail
+    for a, b, name in zip(img32, img64, ("color", "radii", "depth", "alpha")):
+        if name != "radii":
+            util.assert_image_close(name, a, b, flips)
+    util.assert_radii_match("radii", img32[1], img64[1], flips)

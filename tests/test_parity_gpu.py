@@ -1,8 +1,11 @@
 """GPU parity tests: the CUDA path, called through the reference-facing operator
 (GaussianRasterizer -> ctypes -> C ABI of libscgr.so), against the CPU oracle on the same seeded
 inputs.  Tolerances are the north_star's: 1e-4 rel on RGB / depth / alpha, 1e-3 rel on every
-returned gradient (rel = max|a-b| / max|b|); integer outputs (radii, tile lists, ranges) are
-compared exactly up to the documented fp32 rounding allowance.
+returned gradient, read element-wise (tests/util.py); an element beyond them is accepted only when the
+oracle proves that a discrete decision it depends on sits within a stated epsilon of its threshold
+(util.flip_sets); integer outputs (radii, tile lists, ranges) are compared exactly, radii within the
+same proof.  Every measured figure is appended to gpurun_out/parity_report.jsonl (the copy of the last
+B200 run is tracked as profiles/r02_parity.jsonl).
 
 Run on the B200 box:  python -m pytest tests -m gpu -x -q
 """
@@ -104,8 +107,8 @@ def test_forward_stages_match_oracle(dev):
     vis = r2 > 0
     rec = dv["record"]
     radii = radii.cpu().numpy()
-    n_rad = int((radii != r2).sum())
-    assert n_rad <= max(2, case["P"] // 2000) and np.abs(radii - r2).max() <= 1, n_rad
+    flips = util.flip_sets(co)
+    n_rad = util.assert_radii_match("radii", radii, r2, flips)
     both = vis & (radii > 0)
     e_xy = util.rel_err(rec[both][:, 0:2], st["means2D"][both])
     log2e = 1.4426950408889634       # record holds the render-ready conic (include/scgr.h)
@@ -163,9 +166,10 @@ def test_forward_stages_match_oracle(dev):
             assert ((al < 1.0 / 255.0) | (power > 0)).all(), f"tile {t}: a contributing pair was culled"
     report("stages_lists", kept=kept, dropped=dropped)
     assert kept == state.num_rendered and dropped > 0
-    util.assert_image_close("color", color.cpu().numpy(), c2)
-    util.assert_image_close("depth", depth.cpu().numpy(), d2)
-    util.assert_image_close("alpha", alpha.cpu().numpy(), a2)
+    st_img = {"color": util.assert_image_close("color", color.cpu().numpy(), c2, flips),
+              "depth": util.assert_image_close("depth", depth.cpu().numpy(), d2, flips),
+              "alpha": util.assert_image_close("alpha", alpha.cpu().numpy(), a2, flips)}
+    report("stages_images", **st_img)
 
 
 CASES = [
@@ -176,6 +180,7 @@ CASES = [
     (5000, 378, 504, 0, 0.03, (0.0, 0.0, 0.0), 1.0, 5.0),      # config-2 resolution (504x378 transposed)
     (40, 16, 16, 3, 0.30, (0.3, 0.3, 0.3), 1.0, 0.0),          # a single tile, huge overlapping splats
     (600, 256, 192, 2, 0.60, (0.1, 0.0, 0.2), 1.0, 10.0),      # rects of > 64 tiles: warp-cooperative emission path
+    (30000, 504, 378, 3, 0.03, (0.0, 0.0, 0.0), 1.0, 0.0),     # BASELINE config 2 at its stated size (30k, 504x378, SH3)
     (3000, 4096, 4096, 1, 0.02, (0.0, 0.0, 0.0), 1.0, 0.0),    # 65536 tiles = 17-bit tile ids: 3 partition passes
 ]
 
@@ -187,16 +192,20 @@ def test_forward_backward_match_oracle(dev, P, W, H, deg, smed, bg, mod, yaw):
     (c, r, d, a), g = gpu_forward_backward(case, dev, grads)
     co, (c2, r2, d2, a2), g2 = util.run_c_oracle(case, "f32", grads=grads)
     co64, _, g64 = util.run_c_oracle(case, "f64", grads=grads)
-    assert (r != r2).sum() <= max(2, P // 2000) and np.abs(r - r2).max() <= 1
-    ec = util.assert_image_close("color", c, c2)
-    ed = util.assert_image_close("depth", d, d2)
-    ea = util.assert_image_close("alpha", a, a2)
-    errs = {}
+    flips = util.flip_sets(co)
+    n_rad = util.assert_radii_match("radii", r, r2, flips)
+    ec = util.assert_image_close("color", c, c2, flips)
+    ed = util.assert_image_close("depth", d, d2, flips)
+    ea = util.assert_image_close("alpha", a, a2, flips)
+    errs, errs32 = {}, {}
     for k in ("means3D", "means2D", "opacities", "shs", "scales", "rotations"):
         assert g[k] is not None, k
-        errs[k] = util.assert_grad_close(k, g[k], g64[k].reshape(g[k].shape))
+        errs[k] = util.assert_grad_close(k, g[k], g64[k].reshape(g[k].shape), flips)            # gradient truth: f64
+        errs32[k] = util.assert_grad_close(k, g[k], g2[k].reshape(g[k].shape), flips)           # same-rounding twin: f32
     assert np.all(g["means2D"][:, 2] == 0)
-    report("fwd_bwd", P=P, W=W, H=H, deg=deg, color=ec, depth=ed, alpha=ea, grads=errs, R=int(co.num_rendered))
+    report("fwd_bwd", P=P, W=W, H=H, deg=deg, radii_mismatch=n_rad, color=ec, depth=ed, alpha=ea, grads_vs_f64=errs,
+           grads_vs_f32=errs32, R=int(co.num_rendered), flip_prone_pixels=float(flips["pix_flag"].mean()),
+           flip_affected_gaussians=float(flips["gauss_flag"].mean()))
 
 
 @pytest.mark.parametrize("deg,max_deg", [(1, 1), (2, 2), (0, 2)])
@@ -206,10 +215,12 @@ def test_sh_layouts_other_than_16_coefficients(dev, deg, max_deg):
     grads = O.synth_upstream_grads(case["W"], case["H"])
     (c, r, d, a), g = gpu_forward_backward(case, dev, grads)
     co, (c2, r2, d2, a2), g2 = util.run_c_oracle(case, "f64", grads=grads)
-    util.assert_image_close("color", c, c2)
+    flips = util.flip_sets(co)
+    st = {"color": util.assert_image_close("color", c, c2, flips)}
     for k in ("means3D", "means2D", "opacities", "shs", "scales", "rotations"):
-        util.assert_grad_close(k, g[k], g2[k].reshape(g[k].shape))
+        st[k] = util.assert_grad_close(k, g[k], g2[k].reshape(g[k].shape), flips)
     assert g["shs"].shape == (2500, (max_deg + 1) ** 2, 3)
+    report("sh_layouts", deg=deg, max_deg=max_deg, **st)
 
 
 def test_near_plane_and_lateral_clamp(dev):
@@ -223,12 +234,13 @@ def test_near_plane_and_lateral_clamp(dev):
     z = case["means3D"][:, 2].numpy()
     xz = np.abs(case["means3D"][:, 0].numpy() / z)
     assert (z <= 0.2).sum() > 10 and r2.max() > 100 and ((xz > 1.3 * case["tanfovx"]) & (r2 > 0)).sum() > 10
-    assert (r != r2).sum() <= 2
-    util.assert_image_close("color", c, c2, flip_frac=1e-3)
-    util.assert_image_close("depth", d, d2, flip_frac=1e-3)
+    flips = util.flip_sets(co)
+    n_rad = util.assert_radii_match("radii", r, r2, flips)
+    st = {"color": util.assert_image_close("color", c, c2, flips), "depth": util.assert_image_close("depth", d, d2, flips)}
     for k in ("means3D", "means2D", "opacities", "shs", "scales", "rotations"):
-        util.assert_grad_close(k, g[k], g2[k].reshape(g[k].shape), flip_frac=3e-3)
-    report("near_plane", culled=int((r2 == 0).sum()), max_radius=int(r2.max()), R=int(co.num_rendered))
+        st[k] = util.assert_grad_close(k, g[k], g2[k].reshape(g[k].shape), flips)
+    report("near_plane", culled=int((r2 == 0).sum()), max_radius=int(r2.max()), R=int(co.num_rendered),
+           radii_mismatch=n_rad, **st)
 
 
 def test_precomputed_colour_and_covariance_paths(dev):
@@ -241,11 +253,12 @@ def test_precomputed_colour_and_covariance_paths(dev):
     grads = O.synth_upstream_grads(case["W"], case["H"])
     (c, r, d, a), g = gpu_forward_backward(case, dev, grads, colors_precomp=col, cov3D_precomp=c6)
     co, (c2, r2, d2, a2), g2 = util.run_c_oracle(case, "f64", grads=grads, colors_precomp=col, cov3D_precomp=c6)
-    util.assert_image_close("color", c, c2)
-    util.assert_image_close("depth", d, d2)
+    flips = util.flip_sets(co)
+    st = {"color": util.assert_image_close("color", c, c2, flips), "depth": util.assert_image_close("depth", d, d2, flips)}
     for k in ("means3D", "means2D", "opacities", "colors_precomp", "cov3D_precomp"):
-        util.assert_grad_close(k, g[k], g2[k].reshape(g[k].shape))
+        st[k] = util.assert_grad_close(k, g[k], g2[k].reshape(g[k].shape), flips)
     assert g["shs"] is None and g["scales"] is None and g["rotations"] is None
+    report("precomp_paths", **st)
 
 
 def test_reference_self_consistency_switches(dev):
@@ -259,12 +272,16 @@ def test_reference_self_consistency_switches(dev):
     dirs = dirs / dirs.norm(dim=1, keepdim=True)
     col = torch.clamp_min(O.eval_sh_rgb(3, case["shs"], dirs) + 0.5, 0.0)
     (c1, r1, d1, a1), _ = gpu_forward_backward(case, dev, colors_precomp=col)
-    util.assert_image_close("convert_SHs_python", c1, c0, rtol=1e-5)
+    # colours do not enter any discrete decision: no flip allowance at all
+    st = {"convert_SHs_python": util.assert_image_close("convert_SHs_python", c1, c0, None, rtol=1e-5)}
+    assert np.array_equal(r1, r0)
     c3 = O.cov3d_from_scale_rot(case["scales"], case["rotations"], case["scale_modifier"])
     c6 = torch.stack([c3[:, 0, 0], c3[:, 0, 1], c3[:, 0, 2], c3[:, 1, 1], c3[:, 1, 2], c3[:, 2, 2]], -1).contiguous()
     (c2, r2, d2, a2), _ = gpu_forward_backward(case, dev, cov3D_precomp=c6)
-    util.assert_image_close("compute_cov3D_python", c2, c0)
-    assert (r2 != r0).sum() <= 2
+    flips = util.flip_sets(util.run_c_oracle(case)[0])      # the covariance is rounded differently: decisions may flip
+    st["compute_cov3D_python"] = util.assert_image_close("compute_cov3D_python", c2, c0, flips)
+    util.assert_radii_match("radii", r2, r0, flips)
+    report("self_consistency", **st)
 
 
 def test_edge_cases(dev):
@@ -289,7 +306,7 @@ def test_edge_cases(dev):
                 shs=case["shs"].to(dev), scales=case["scales"].to(dev), rotations=case["rotations"].to(dev))
     assert not out[0].requires_grad
     co, (c2, r2, d2, a2), _ = util.run_c_oracle(case)
-    util.assert_image_close("no_grad color", out[0].cpu().numpy(), c2)
+    util.assert_image_close("no_grad color", out[0].cpu().numpy(), c2, util.flip_sets(co))
     # non-contiguous / strided inputs are accepted (the reference calls .contiguous())
     big = torch.zeros(800, 6, device=dev)
     big[:, ::2] = case["means3D"].to(dev)
@@ -300,9 +317,10 @@ def test_edge_cases(dev):
     case = util.make_case(1500, 96, 64, sh_degree=1, max_sh_degree=3, scale_median=0.06)
     (c, rad, d, a), g = gpu_forward_backward(case, dev, grads=O.synth_upstream_grads(96, 64))
     co, (c2, r2, d2, a2), g2 = util.run_c_oracle(case, "f64", grads=O.synth_upstream_grads(96, 64))
-    util.assert_image_close("deg1of3 color", c, c2)
+    flips = util.flip_sets(co)
+    util.assert_image_close("deg1of3 color", c, c2, flips)
     assert np.all(g["shs"][:, 4:] == 0)
-    util.assert_grad_close("deg1of3 shs", g["shs"], g2["shs"])
+    util.assert_grad_close("deg1of3 shs", g["shs"], g2["shs"], flips)
     # debug=True path (sync + check after every kernel) gives the same numbers
     (c3, _, _, _), _ = gpu_forward_backward(case, dev, debug=True)
     assert np.array_equal(c3, c)
@@ -322,10 +340,11 @@ def test_alpha_cap_equal_depth_and_saturation(dev):
     st = co.state()
     nc = st["n_contrib"]
     assert (a2 > 0.9998).any() and (nc[a2[0] > 0.9998] < P).any()   # saturation (early stop) really happened
-    util.assert_image_close("color", c, c2)
-    util.assert_image_close("alpha", a, a2)
+    flips = util.flip_sets(co)
+    st = {"color": util.assert_image_close("color", c, c2, flips), "alpha": util.assert_image_close("alpha", a, a2, flips)}
     for k in ("means3D", "opacities", "shs", "scales", "rotations"):
-        util.assert_grad_close(k, g[k], g2[k].reshape(g[k].shape), flip_frac=5e-3)
+        st[k] = util.assert_grad_close(k, g[k], g2[k].reshape(g[k].shape), flips)
+    report("alpha_cap_equal_depth", flip_affected_gaussians=float(flips["gauss_flag"].mean()), **st)
 
 
 def test_mark_visible(dev):
@@ -361,8 +380,8 @@ def test_binning_modes_agree(dev, monkeypatch):
     gC, gD, gA = [x.to(dev) for x in O.synth_upstream_grads(case["W"], case["H"])]
     g_ref = R.rasterize_backward_raw(ref[4], *args[:-1], s, gC, gD, gA)
     g_fused = R.rasterize_backward_raw(fused[4], *args[:-1], s, gC, gD, gA)
-    for k in g_ref:
-        util.assert_grad_close(k, g_fused[k].cpu().numpy(), g_ref[k].cpu().numpy())
+    for k in g_ref:      # same lists, same kernels: only the order of the fp32 atomics differs
+        util.assert_grad_close(k, g_fused[k].cpu().numpy(), g_ref[k].cpu().numpy(), None, rtol=1e-4)
     # P = 0 through the fused entry point
     z = torch.zeros(0, 3, device=dev)
     e = R.rasterize_forward_raw(z, torch.zeros(0, 1, device=dev), torch.zeros(0, 16, 3, device=dev), None, z,
@@ -504,16 +523,18 @@ def test_config3_full_view_against_cpu_oracle(dev, config3):
     case, s, args, (color, radii, depth, alpha, state) = config3
     grads = O.synth_upstream_grads(case["W"], case["H"])
     co, (c2, r2, d2, a2), g2 = util.run_c_oracle(case, "f32", grads=grads)
-    n_rad = int((radii.cpu().numpy() != r2).sum())
-    assert n_rad <= 200
-    ec = util.assert_image_close("color", color.cpu().numpy(), c2, flip_frac=1e-3)
-    ed = util.assert_image_close("depth", depth.cpu().numpy(), d2, flip_frac=1e-3)
-    ea = util.assert_image_close("alpha", alpha.cpu().numpy(), a2, flip_frac=1e-3)
+    flips = util.flip_sets(co)
+    n_rad = util.assert_radii_match("radii", radii.cpu().numpy(), r2, flips)
+    ec = util.assert_image_close("color", color.cpu().numpy(), c2, flips)
+    ed = util.assert_image_close("depth", depth.cpu().numpy(), d2, flips)
+    ea = util.assert_image_close("alpha", alpha.cpu().numpy(), a2, flips)
     b = R.rasterize_backward_raw(state, *args, s, *[g.to(dev) for g in grads])
-    errs = {k: util.assert_grad_close(k, b[k].cpu().numpy(), g2[k].reshape(tuple(b[k].shape)))
+    errs = {k: util.assert_grad_close(k, b[k].cpu().numpy(), g2[k].reshape(tuple(b[k].shape)), flips)
             for k in ("means3D", "means2D", "opacities", "shs", "scales", "rotations")}
     report("config3_oracle", radii_mismatch=n_rad, color=ec, depth=ed, alpha=ea, grads=errs,
-           R_gpu=int(state.num_rendered), R_cpu=int(co.num_rendered))
+           R_gpu=int(state.num_rendered), R_cpu=int(co.num_rendered),
+           flip_prone_pixels=float(flips["pix_flag"].mean()), flip_affected_gaussians=float(flips["gauss_flag"].mean()),
+           eps=flips["eps"])
 
 
 def test_config4_resolution_properties(dev):

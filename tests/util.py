@@ -55,7 +55,7 @@ def run_c_oracle(case, precision="f32", grads=None, colors_precomp=None, cov3D_p
 
 
 def rel_err(a, b):
-    """max |a-b| / max |b|  (norm-wise relative error, the north_star's 'rel')."""
+    """max |a-b| / max |b|  (norm-wise relative error; reported next to the element-wise figure)."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     if a.size == 0:
@@ -63,36 +63,96 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
 
 
-def assert_image_close(name, got, want, rtol=RTOL_IMAGE, flip_frac=2e-4, flip_atol=2e-2):
-    """Images agree within rtol (norm-wise) except for an allowance of isolated pixels where a
-    discrete decision (alpha < 1/255, T < 1e-4, power > 0) flipped because exp()/FMA rounding
-    differs between the CPU oracle and the GPU -- such a flip moves a pixel by up to ~4e-3."""
+# ---------------------------------------------------------------------------------------------------------------
+# Parity compares.  Tolerance (north_star): 1e-4 rel on RGB / depth / alpha, 1e-3 rel on every returned gradient,
+# read ELEMENT-WISE:  |got - want| <= rtol * (|want| + floor)  with a small floor that keeps elements near zero
+# meaningful -- 1 % of the array's RMS for images, the RMS of the non-zero entries for gradients (whose entries are
+# sums of signed per-pixel terms: an entry that cancels to ~0 carries the rounding of terms of typical size).
+#
+# The rasterizer also takes DISCRETE decisions (alpha >= 1/255, T (1 - alpha) >= 1e-4, power <= 0, radius = ceil(..),
+# tile rect = trunc(..)) that a last-bit difference can flip; a flip moves a pixel by up to ~alpha = 4e-3 -- no
+# tolerance on the values can absorb it, the f32 and f64 builds of the oracle differ from EACH OTHER this way.  An
+# element beyond rtol is therefore accepted ONLY when the oracle proves that a decision it depends on sits within
+# EPS of its threshold (oracle/scg_oracle.c: scgo_margins): the pixel is flip-prone, or the Gaussian (nearly)
+# contributes to a flip-prone pixel.  Such elements must still lie within FLIP_BOUND norm-wise -- one flipped
+# contribution is worth at most alpha at the edge of the 3-sigma rect, 0.011 x opacity, of the value range.  Without
+# an oracle state (`flips=None`) nothing is excused.
+# ---------------------------------------------------------------------------------------------------------------
+EPS = dict(eps_alpha=5e-5, eps_T=5e-5, eps_power=1e-6, eps_geom=1e-4)    # relative, relative, absolute, pixels
+FLIP_BOUND = 1.2e-2
+IMAGE_FLOOR = 0.01       # x RMS of the image
+GRAD_FLOOR = 1.0         # x RMS of the non-zero gradient entries
+
+
+def flip_sets(co, **eps):
+    """Flip-prone pixels / flip-affected Gaussians of the view the C oracle `co` last rendered."""
+    kw = dict(EPS)
+    kw.update(eps)
+    m = co.margins(**kw)
+    m["eps"] = kw
+    return m
+
+
+def _elementwise(got, want, floor_frac, nonzero_rms):
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
-    assert got.shape == want.shape, (name, got.shape, want.shape)
-    scale = np.abs(want).max() + 1e-30
-    err = np.abs(got - want) / scale
+    sel = want[want != 0] if nonzero_rms else want
+    rms = float(np.sqrt(np.mean(sel * sel))) if sel.size else 0.0
+    diff = np.abs(got - want)
+    return diff / (np.abs(want) + floor_frac * rms + 1e-300), diff / (np.abs(want).max() + 1e-30)
+
+
+def _judge(name, err, nw, excusable, rtol):
     bad = err > rtol
-    frac = bad.mean() if bad.size else 0.0
-    assert frac <= flip_frac, f"{name}: {bad.sum()} / {bad.size} elements beyond rtol={rtol} (max {err.max():.3e})"
-    assert err.max() <= flip_atol, f"{name}: max rel err {err.max():.3e} > {flip_atol}"
-    return float(err.max()), float(frac)
+    n_bad = int(bad.sum())
+    stats = dict(max_err=float(err.max()) if err.size else 0.0, max_normwise=float(nw.max()) if nw.size else 0.0,
+                 n=int(err.size), n_beyond_rtol=n_bad, excusable_frac=float(excusable.mean()) if excusable.size else 0.0,
+                 max_err_unexcusable=float(err[~excusable].max()) if (~excusable).any() else 0.0)
+    if n_bad:
+        rogue = bad & ~excusable
+        assert not rogue.any(), (f"{name}: {int(rogue.sum())} element(s) beyond rtol={rtol} that no near-threshold "
+                                 f"decision explains (max {err[rogue].max():.3e}; {n_bad} beyond rtol in all)")
+        assert nw[bad].max() <= FLIP_BOUND, f"{name}: a flip-excused element is off by {nw[bad].max():.3e} > {FLIP_BOUND} norm-wise"
+        stats["max_normwise_excused"] = float(nw[bad].max())
+    return stats
 
 
-def assert_grad_close(name, got, want, rtol=RTOL_GRAD, flip_frac=1e-3, flip_atol=2e-2):
-    """Gradients agree within rtol (max|a-b| / max|b|).  Like the images they inherit isolated
-    discrete flips of the fp32 forward (alpha < 1/255, T < 1e-4): the float32 and float64 builds of
-    the CPU oracle differ from EACH OTHER by up to ~6e-3 on 1-4 of 15000 elements on such a case
-    (tests/test_oracle.py::test_f32_f64_oracles_differ_only_by_isolated_flips), so a fraction
-    `flip_frac` of elements may exceed rtol, none may exceed flip_atol."""
-    got = np.asarray(got, dtype=np.float64)
-    want = np.asarray(want, dtype=np.float64)
+def assert_image_close(name, got, want, flips=None, rtol=RTOL_IMAGE):
+    """[C,H,W] images agree element-wise within rtol; elements beyond it must be flip-prone pixels (see above).
+    Returns the measured figures (recorded in profiles/r02_parity.jsonl by the GPU tests)."""
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, (name, got.shape, want.shape)
+    assert np.isfinite(got).all(), f"{name}: non-finite values"
+    err, nw = _elementwise(got, want, IMAGE_FLOOR, False)
+    exc = np.zeros(got.shape, bool) if flips is None else np.broadcast_to(flips["pix_flag"][None], got.shape)
+    return _judge(name, err, nw, exc, rtol)
+
+
+def assert_grad_close(name, got, want, flips=None, rtol=RTOL_GRAD):
+    """[P,...] per-Gaussian gradients agree element-wise within rtol; rows beyond it must belong to flip-affected
+    Gaussians (see above)."""
+    got, want = np.asarray(got), np.asarray(want)
     assert got.shape == want.shape, (name, got.shape, want.shape)
     if got.size == 0:
-        return 0.0
-    err = np.abs(got - want) / (np.abs(want).max() + 1e-30)
-    bad = int((err > rtol).sum())
-    allowed = max(1, int(math.ceil(flip_frac * err.size))) if flip_frac > 0 else 0
-    assert bad <= allowed, f"{name}: {bad} / {err.size} elements beyond rtol={rtol} (max {err.max():.3e})"
-    assert err.max() <= flip_atol, f"{name}: max rel err {err.max():.3e} > {flip_atol}"
-    return float(err.max())
+        return dict(max_err=0.0, max_normwise=0.0, n=0, n_beyond_rtol=0)
+    assert np.isfinite(got).all(), f"{name}: non-finite values"
+    err, nw = _elementwise(got, want, GRAD_FLOOR, True)
+    exc = np.zeros(got.shape, bool)
+    if flips is not None:
+        exc = np.broadcast_to(flips["gauss_flag"].reshape((-1,) + (1,) * (got.ndim - 1)), got.shape)
+    return _judge(name, err, nw, exc, rtol)
+
+
+def assert_radii_match(name, got, want, flips=None):
+    """radii are integers: bit-exact, except where 3 sqrt(lambda) sits within eps_geom of an integer (ceil of a
+    last-bit difference) -- then they may differ by one.  Returns the number of such mismatches."""
+    got, want = np.asarray(got).astype(np.int64), np.asarray(want).astype(np.int64)
+    mis = got != want
+    n = int(mis.sum())
+    if n:
+        assert flips is not None, f"{name}: {n} radii differ"
+        assert np.abs(got - want)[mis].max() <= 1, f"{name}: radii differ by more than one"
+        gm = flips["geom_margin"][mis]
+        assert (gm < flips["eps"]["eps_geom"]).all(), \
+            f"{name}: {n} radii differ, {int((gm >= flips['eps']['eps_geom']).sum())} of them away from a rounding boundary (margin up to {gm.max():.3e} px)"
+    return n
