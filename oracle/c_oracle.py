@@ -46,6 +46,7 @@ class COracle:
         assert self.lib.scgo_real_size() == np.dtype(self.np_real).itemsize
         self.Inputs = _make_struct(self.c_real)
         self.lib.scgo_forward.restype = C.c_void_p
+        self.lib.scgo_forward_ex.restype = C.c_void_p
         self.lib.scgo_num_rendered.restype = C.c_int64
         for f in ("scgo_point_list", "scgo_ranges", "scgo_means2D", "scgo_conic", "scgo_rgb",
                   "scgo_depths", "scgo_tiles_touched", "scgo_n_contrib", "scgo_geom_margin"):
@@ -64,7 +65,9 @@ class COracle:
 
     def forward(self, *, means3D, opacities, W, H, tanfovx, tanfovy, bg, viewmatrix, projmatrix,
                 campos, sh_degree=0, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None, scale_modifier=1.0):
+                cov3D_precomp=None, scale_modifier=1.0, override=None):
+        """override: dict(xy [P,2], conic [P,3], rgb [P,3], depth [P], radii [P] int32, clamped [P,3] uint8) -- per-
+        Gaussian 2D state used instead of the oracle's own preprocess (staged parity, scg_oracle.c: scgo_override)."""
         self.free()
         a = {k: self._arr(v) for k, v in dict(
             bg=bg, viewmatrix=viewmatrix, projmatrix=projmatrix, campos=campos, means3D=means3D,
@@ -80,9 +83,25 @@ class COracle:
         depth = np.zeros((1, H, W), self.np_real)
         alpha = np.zeros((1, H, W), self.np_real)
         radii = np.zeros(P, np.int32)
-        self._keep = (a, inp)
-        self._state = C.c_void_p(self.lib.scgo_forward(
-            C.byref(inp), self._p(color), self._p(depth), self._p(alpha),
+        ovp = None
+        ov_keep = None
+        if override is not None:
+            rp = C.POINTER(self.c_real)
+
+            class Override(C.Structure):
+                _fields_ = [("xy", rp), ("conic", rp), ("rgb", rp), ("depth", rp), ("radii", C.POINTER(C.c_int)),
+                            ("clamped", C.POINTER(C.c_ubyte))]
+            ov_keep = {k: self._arr(override[k]) for k in ("xy", "conic", "rgb", "depth")}
+            ov_keep["radii"] = np.ascontiguousarray(override["radii"], dtype=np.int32)
+            ov_keep["clamped"] = np.ascontiguousarray(override["clamped"], dtype=np.uint8)
+            assert ov_keep["xy"].shape == (P, 2) and ov_keep["conic"].shape == (P, 3) and ov_keep["radii"].shape == (P,)
+            ov = Override(*[self._p(ov_keep[k]) for k in ("xy", "conic", "rgb", "depth")],
+                          ov_keep["radii"].ctypes.data_as(C.POINTER(C.c_int)),
+                          ov_keep["clamped"].ctypes.data_as(C.POINTER(C.c_ubyte)))
+            ovp = C.byref(ov)
+        self._keep = (a, inp, ov_keep)
+        self._state = C.c_void_p(self.lib.scgo_forward_ex(
+            C.byref(inp), ovp, self._p(color), self._p(depth), self._p(alpha),
             radii.ctypes.data_as(C.POINTER(C.c_int))))
         self._dims = (P, M, W, H)
         return color, radii, depth, alpha
@@ -126,19 +145,25 @@ class COracle:
                     tiles_touched=self._view("scgo_tiles_touched", np.int32, P),
                     n_contrib=self._view("scgo_n_contrib", np.int32, W * H).reshape(H, W))
 
-    def margins(self, eps_alpha=2e-3, eps_T=2e-3, eps_power=1e-4, eps_geom=2e-3):
-        """Which outputs a flipped discrete decision could touch (scg_oracle.c: scgo_margins).  Returns
-        pix_margin [3,H,W] (minima of |255 alpha - 1|, |T / 1e-4 - 1|, |power| over the entries a pixel visits),
-        pix_flag [H,W] bool (flip-prone pixels), gauss_flag [P] bool (flip-affected Gaussians), geom_margin [P]."""
+    def margins(self, base_err=2e-6, conic_err=2e-6, pos_ulps=4.0, geom_err=None):
+        """Which outputs a flipped discrete decision could touch (scg_oracle.c: scgo_margins, error model there).
+        pos_ulps: uncertainty of a projected mean in units of 2^-23 x max(W, H) pixels.  Returns
+        pix_margin [H,W] (margin / uncertainty, < 1 <=> flip-prone), pix_flag [H,W] bool, gauss_margin [P],
+        gauss_flag [P] bool (flip-affected), gauss_own [P] bool (the uncertain decision is the Gaussian's own),
+        geom_margin [P] (pixels)."""
         P, M, W, H = self._dims
-        pm = np.zeros((3, H, W), self.np_real)
+        pos_err = pos_ulps * 2.0 ** -23 * max(W, H)
+        geom_err = 4.0 * pos_err if geom_err is None else geom_err
+        pm = np.zeros((H, W), self.np_real)
         pf = np.zeros((H, W), np.uint8)
+        gm = np.zeros(max(P, 1), self.np_real)
         gf = np.zeros(max(P, 1), np.uint8)
-        self.lib.scgo_margins(self._state, C.c_double(eps_alpha), C.c_double(eps_T), C.c_double(eps_power),
-                              C.c_double(eps_geom), self._p(pm), pf.ctypes.data_as(C.POINTER(C.c_ubyte)),
+        self.lib.scgo_margins(self._state, C.c_double(base_err), C.c_double(conic_err), C.c_double(pos_err),
+                              C.c_double(geom_err), self._p(pm), pf.ctypes.data_as(C.POINTER(C.c_ubyte)), self._p(gm),
                               gf.ctypes.data_as(C.POINTER(C.c_ubyte)))
-        return dict(pix_margin=pm, pix_flag=pf.astype(bool), gauss_flag=gf[:P].astype(bool),
-                    geom_margin=self._view("scgo_geom_margin", self.np_real, P))
+        return dict(pix_margin=pm, pix_flag=pf.astype(bool), gauss_margin=gm[:P], gauss_flag=gf[:P] > 0,
+                    gauss_own=gf[:P] == 2, geom_margin=self._view("scgo_geom_margin", self.np_real, P),
+                    model=dict(base_err=base_err, conic_err=conic_err, pos_err_px=pos_err, geom_err_px=geom_err))
 
     def free(self):
         if self._state is not None:

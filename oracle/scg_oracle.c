@@ -197,9 +197,18 @@ const REAL *scgo_depths(const scgo_state *s) { return s->depth; }
 const int *scgo_tiles_touched(const scgo_state *s) { return s->tiles; }
 const int *scgo_n_contrib(const scgo_state *s) { return s->n_contrib; }
 
+/* Optional per-Gaussian 2D state to use INSTEAD of this file's own preprocess (staged parity: the binning, the blend
+ * and the whole backward are then checked on bit-identical 2D parameters, e.g. the ones a CUDA preprocess produced,
+ * while the preprocess itself is compared value by value).  radii[i] <= 0 marks a culled Gaussian. */
+typedef struct {
+    const REAL *xy, *conic, *rgb, *depth;      /* [P,2] [P,3] [P,3] [P] */
+    const int *radii;                          /* [P] */
+    const unsigned char *clamped;              /* [P,3] */
+} scgo_override;
+
 /* A.1-A.8.  out_color[3*H*W], out_depth[H*W], out_alpha[H*W], radii[P]. */
-scgo_state *scgo_forward(const scgo_inputs *in, REAL *out_color, REAL *out_depth, REAL *out_alpha,
-                         int *radii_out) {
+scgo_state *scgo_forward_ex(const scgo_inputs *in, const scgo_override *ov, REAL *out_color, REAL *out_depth,
+                            REAL *out_alpha, int *radii_out) {
     const int P = in->P, W = in->W, H = in->H;
     scgo_state *s = (scgo_state *)calloc(1, sizeof(scgo_state));
     s->in = *in;
@@ -226,8 +235,10 @@ scgo_state *scgo_forward(const scgo_inputs *in, REAL *out_color, REAL *out_depth
     for (int i = 0; i < P; i++) {
         const REAL *p = in->means3D + 3 * i;
         const REAL *V = in->viewmatrix, *PM = in->projmatrix;
+        const int forced = ov != NULL;
+        if (forced && ov->radii[i] <= 0) continue;
         REAL zv = p[0] * V[2] + p[1] * V[6] + p[2] * V[10] + V[14];
-        if (zv <= NEAR_Z) continue;                                   /* A.1 */
+        if (!forced && zv <= NEAR_Z) continue;                        /* A.1 */
         REAL hom[4];
         for (int j = 0; j < 4; j++) hom[j] = p[0] * PM[j] + p[1] * PM[4 + j] + p[2] * PM[8 + j] + PM[12 + j];
         REAL pw = 1 / (hom[3] + (REAL)1e-7);
@@ -237,17 +248,15 @@ scgo_state *scgo_forward(const scgo_inputs *in, REAL *out_color, REAL *out_depth
         else cov3d_of(in->scales + 3 * i, in->scale_modifier, in->rotations + 4 * i, c6);   /* A.3 */
         proj_t pr; project_cov(in, p, c6, &pr);                       /* A.4 */
         REAL det = pr.a * pr.c - pr.b * pr.b;
-        if (det == 0) continue;
+        if (!forced && det == 0) continue;
         REAL dinv = 1 / det;
         REAL mid = (REAL)0.5 * (pr.a + pr.c);
         REAL disc = (REAL)sqrt((double)rmax((REAL)0.1, mid * mid - det));
         REAL lam = rmax(mid + disc, mid - disc);
-        int rad = (int)ceil(3.0 * sqrt((double)lam));
-#if 1
         /* in REAL precision, as a float kernel would evaluate it */
-        rad = (int)ceil((double)((REAL)3 * (REAL)sqrt((double)lam)));
-#endif
+        int rad = (int)ceil((double)((REAL)3 * (REAL)sqrt((double)lam)));
         REAL px = ((ndcx + 1) * W - 1) * (REAL)0.5, py = ((ndcy + 1) * H - 1) * (REAL)0.5;
+        if (forced) { rad = ov->radii[i]; px = ov->xy[2 * i]; py = ov->xy[2 * i + 1]; }
         int x0 = iclamp((int)((px - rad) / BLK), 0, s->gx), y0 = iclamp((int)((py - rad) / BLK), 0, s->gy);
         int x1 = iclamp((int)((px + rad + BLK - 1) / BLK), 0, s->gx), y1 = iclamp((int)((py + rad + BLK - 1) / BLK), 0, s->gy);
         {   /* margins of the integer decisions above (test infrastructure: scgo_margins) */
@@ -257,7 +266,9 @@ scgo_state *scgo_forward(const scgo_inputs *in, REAL *out_color, REAL *out_depth
             s->geom_margin[i] = (REAL)gm;
         }
         if ((x1 - x0) * (y1 - y0) == 0) continue;
-        if (use_sh) {                                                 /* A.5 */
+        if (forced) {
+            for (int ch = 0; ch < 3; ch++) { s->rgb[3 * i + ch] = ov->rgb[3 * i + ch]; s->clamped[3 * i + ch] = ov->clamped[3 * i + ch]; }
+        } else if (use_sh) {                                          /* A.5 */
             double dx = p[0] - in->campos[0], dy = p[1] - in->campos[1], dz = p[2] - in->campos[2];
             double n = sqrt(dx * dx + dy * dy + dz * dz);
             double b[16], db[16][3];
@@ -271,8 +282,9 @@ scgo_state *scgo_forward(const scgo_inputs *in, REAL *out_color, REAL *out_depth
                 s->rgb[3 * i + ch] = rmax(v, 0);
             }
         } else for (int ch = 0; ch < 3; ch++) s->rgb[3 * i + ch] = in->colors_precomp[3 * i + ch];
-        s->depth[i] = zv; s->radii[i] = rad; s->xy[2 * i] = px; s->xy[2 * i + 1] = py;
-        s->conic[3 * i] = pr.c * dinv; s->conic[3 * i + 1] = -pr.b * dinv; s->conic[3 * i + 2] = pr.a * dinv;
+        s->depth[i] = forced ? ov->depth[i] : zv; s->radii[i] = rad; s->xy[2 * i] = px; s->xy[2 * i + 1] = py;
+        if (forced) { s->conic[3 * i] = ov->conic[3 * i]; s->conic[3 * i + 1] = ov->conic[3 * i + 1]; s->conic[3 * i + 2] = ov->conic[3 * i + 2]; }
+        else { s->conic[3 * i] = pr.c * dinv; s->conic[3 * i + 1] = -pr.b * dinv; s->conic[3 * i + 2] = pr.a * dinv; }
         s->rect[4 * i] = x0; s->rect[4 * i + 1] = y0; s->rect[4 * i + 2] = x1; s->rect[4 * i + 3] = y1;
         s->tiles[i] = (x1 - x0) * (y1 - y0);
     }
@@ -336,6 +348,10 @@ scgo_state *scgo_forward(const scgo_inputs *in, REAL *out_color, REAL *out_depth
         }
     }
     return s;
+}
+
+scgo_state *scgo_forward(const scgo_inputs *in, REAL *out_color, REAL *out_depth, REAL *out_alpha, int *radii_out) {
+    return scgo_forward_ex(in, NULL, out_color, out_depth, out_alpha, radii_out);
 }
 
 /* A.9 + A.10.  Upstream: dL_dcolor[3*H*W], dL_ddepth[H*W], dL_dalpha[H*W].
@@ -538,26 +554,41 @@ void scgo_backward(const scgo_state *s, const REAL *gC, const REAL *gD, const RE
 
 /* ------------------------------------------------------------------------------------------------------------
  * Margins of the discrete decisions (parity-test support).  The rasterizer takes four kinds of yes/no decisions
- * whose outcome a 1-ulp difference in fp32 arithmetic can flip:
- *   (a) alpha = opacity * exp(power) >= 1/255           (A.8 skip)            margin: |alpha_raw * 255 - 1|
- *   (b) test_T = T (1 - alpha) >= 1e-4                  (A.8 early stop)      margin: |test_T / 1e-4 - 1|
- *   (c) power <= 0                                      (A.8 skip)            margin: |power|
- *   (d) radius = ceil(3 sqrt(lambda)), tile rect = trunc((pix -/+ radius) / 16)   margin: pixels (geom_margin)
- * A pixel is FLIP-PRONE when some list entry it visits (the terminating one included) comes within eps of (a), (b)
- * or (c), or when a Gaussian within eps of (d) could reach it with alpha >= (1 - eps_alpha) / 255.  A Gaussian is
- * FLIP-AFFECTED when it (nearly) contributes to a flip-prone pixel -- every gradient of such a Gaussian changes
- * with the flip (through T and through the suffix blend) -- or is itself within eps of (d).
- * pix_margin[3][H*W] receives the per-pixel minima of (a), (b), (c); pix_flag[H*W] / gauss_flag[P] the two sets. */
-void scgo_margins(const scgo_state *s, double eps_alpha, double eps_T, double eps_power, double eps_geom,
-                  REAL *pix_margin, unsigned char *pix_flag, unsigned char *gauss_flag) {
+ * whose outcome a last-bit difference in fp32 arithmetic can flip:
+ *   (a) alpha = opacity * exp(power) >= 1/255           (A.8 skip)
+ *   (b) test_T = T (1 - alpha) >= 1e-4                  (A.8 early stop)
+ *   (c) power <= 0                                      (A.8 skip)
+ *   (d) radius = ceil(3 sqrt(lambda)), tile rect = trunc((pix -/+ radius) / 16)
+ * How close is "close enough to flip" follows from an ERROR MODEL of two fp32 implementations of the same formulas
+ * (this file vs a CUDA kernel with FMA contraction and hardware exp2), stated by three constants:
+ *   pos_err    absolute uncertainty of a projected mean, pixels   (a few ulp of the largest pixel coordinate)
+ *   conic_err  relative uncertainty of the conic coefficients (hence of power)
+ *   base_err   relative uncertainty of exp() and of the products around it
+ * For one (Gaussian, pixel) entry the relative uncertainty of alpha is
+ *   u = base_err + conic_err |power| + pos_err (|A dx + B dy| + |B dx + C dy|)          (|grad power| . pos_err)
+ * decision (a) is uncertain when |255 alpha - 1| < u; the relative uncertainty of T accumulates along the walk,
+ * U += u alpha / (1 - alpha) per blended entry, and decision (b) is uncertain when |test_T / 1e-4 - 1| < U + u alpha / (1 - alpha) + base_err;
+ * (c) when |power| < conic_err |power| + pos_err |grad power| + 1e-12 for an entry that would contribute; (d) when the
+ * pre-ceil radius or a rect edge lies within geom_err pixels of the value where the integer changes.
+ * A pixel is FLIP-PRONE when some entry it visits (the terminating one included) has an uncertain decision, or when
+ * a Gaussian uncertain in (d) could reach it.  A Gaussian is FLIP-AFFECTED when it (nearly) contributes to a
+ * flip-prone pixel -- every gradient of such a Gaussian changes with the flip, through T and the suffix blend -- or is
+ * uncertain in (d); it is flagged OWN (value 2) when the uncertain decision is its own.
+ * pix_margin[H*W]: min over the decisions of the pixel of margin / uncertainty (< 1 <=> flip-prone): by how much the
+ * error model would have to be scaled for the pixel to change class (calibration);  gauss_margin[P]: min of
+ * pix_margin over the pixels the Gaussian (nearly) contributes to. */
+void scgo_margins(const scgo_state *s, double base_err, double conic_err, double pos_err, double geom_err,
+                  REAL *pix_margin, unsigned char *pix_flag, REAL *gauss_margin, unsigned char *gauss_flag) {
     const scgo_inputs *in = &s->in;
     const int P = in->P, W = in->W, H = in->H, Tn = s->gx * s->gy;
     const size_t N = (size_t)W * H;
-    for (size_t i = 0; i < 3 * N; i++) pix_margin[i] = (REAL)1e30;
+    for (size_t i = 0; i < N; i++) pix_margin[i] = (REAL)1e30;
+    for (int i = 0; i < P; i++) gauss_margin[i] = (REAL)1e30;
     memset(pix_flag, 0, N);
     memset(gauss_flag, 0, P > 0 ? P : 0);
     if (P == 0) return;
-    /* pass 1: per-pixel minima over the entries the forward visits */
+    unsigned char *own = (unsigned char *)calloc(P, 1);
+    /* pass 1: per-pixel minimum of margin / uncertainty over the entries the forward visits */
 #pragma omp parallel for schedule(dynamic, 4)
     for (int t = 0; t < Tn; t++) {
         int tx = t % s->gx, ty = t / s->gx;
@@ -565,36 +596,46 @@ void scgo_margins(const scgo_state *s, double eps_alpha, double eps_T, double ep
         for (int ly = 0; ly < BLK; ly++) for (int lx = 0; lx < BLK; lx++) {
             int px = tx * BLK + lx, py = ty * BLK + ly;
             if (px >= W || py >= H) continue;
-            double ma = 1e30, mt = 1e30, mp = 1e30;
+            double m = 1e30, U = 0;
             REAL T = 1;
             for (int64_t j = r0; j < r1; j++) {
                 uint32_t g = s->point_list[j];
                 REAL dx = s->xy[2 * g] - px, dy = s->xy[2 * g + 1] - py;
                 const REAL *co = s->conic + 3 * g;
                 REAL power = (REAL)-0.5 * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+                double gp = fabs((double)co[0] * dx + (double)co[1] * dy) + fabs((double)co[1] * dx + (double)co[2] * dy);
+                double up = conic_err * fabs((double)power) + pos_err * gp;       /* absolute uncertainty of power */
+                double u = base_err + up;
                 double araw = (double)in->opacities[g] * exp((double)power);
-                if (araw * 255.0 >= 1.0 - eps_alpha && fabs((double)power) < mp) mp = fabs((double)power);
+                double mine = 1e30;
+                if (araw * 255.0 >= 1.0 - u) { double q = fabs((double)power) / (up + 1e-12); if (q < mine) mine = q; }   /* (c) */
+                if (power <= 0) {
+                    double q = fabs(araw * 255.0 - 1.0) / u;                                                            /* (a) */
+                    if (q < mine) mine = q;
+                }
+                if (mine < 1.0) own[g] = 1;     /* benign race: all writers store 1 */
+                if (mine < m) m = mine;
                 if (power > 0) continue;
-                double da = fabs(araw * 255.0 - 1.0);
-                if (da < ma) ma = da;
                 REAL alpha = rmin(ALPHA_MAX, (REAL)araw);
                 if (alpha < ALPHA_MIN) continue;
                 REAL test_T = T * (1 - alpha);
-                double dt = fabs((double)test_T / 1e-4 - 1.0);
-                if (dt < mt) mt = dt;
+                double ua = (araw < (double)ALPHA_MAX) ? u * alpha / (1 - alpha) : 0.0;     /* the cap is exact */
+                double q = fabs((double)test_T / 1e-4 - 1.0) / (U + ua + base_err);                                      /* (b) */
+                if (q < 1.0) own[g] = 1;
+                if (q < m) m = q;
                 if (test_T < T_EPS) break;
-                T = test_T;
+                T = test_T; U += ua;
             }
             size_t pid = (size_t)py * W + px;
-            pix_margin[pid] = (REAL)ma; pix_margin[N + pid] = (REAL)mt; pix_margin[2 * N + pid] = (REAL)mp;
-            if (ma < eps_alpha || mt < eps_T || mp < eps_power) pix_flag[pid] = 1;
+            pix_margin[pid] = (REAL)m;
+            if (m < 1.0) pix_flag[pid] = 1;
         }
     }
-    /* (d): Gaussians whose radius / rect could differ by one: every pixel of the rect grown by one tile that
-     * they could reach is flip-prone, and they are flip-affected themselves */
+    /* (d): Gaussians whose radius / rect could differ by one: every pixel of the rect grown by one tile that they
+     * could reach is flip-prone, and they are flip-affected themselves */
     for (int i = 0; i < P; i++) {
-        if (s->radii[i] <= 0 || (double)s->geom_margin[i] >= eps_geom) continue;
-        gauss_flag[i] = 1;
+        if (s->radii[i] <= 0 || (double)s->geom_margin[i] >= geom_err) continue;
+        own[i] = 1;
         int x0 = iclamp(s->rect[4 * i] - 1, 0, s->gx) * BLK, y0 = iclamp(s->rect[4 * i + 1] - 1, 0, s->gy) * BLK;
         int x1 = iclamp(s->rect[4 * i + 2] + 1, 0, s->gx) * BLK, y1 = iclamp(s->rect[4 * i + 3] + 1, 0, s->gy) * BLK;
         if (x1 > W) x1 = W;
@@ -603,28 +644,49 @@ void scgo_margins(const scgo_state *s, double eps_alpha, double eps_T, double ep
         for (int py = y0; py < y1; py++) for (int px = x0; px < x1; px++) {
             REAL dx = s->xy[2 * i] - px, dy = s->xy[2 * i + 1] - py;
             REAL power = (REAL)-0.5 * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
-            if ((double)in->opacities[i] * exp((double)power) * 255.0 >= 1.0 - eps_alpha) pix_flag[(size_t)py * W + px] = 1;
-        }
-    }
-    /* pass 2: Gaussians that (nearly) contribute to a flip-prone pixel.  The whole list is walked: a flipped early
-     * stop lets entries behind the oracle's terminating one contribute. */
-#pragma omp parallel for schedule(dynamic, 4)
-    for (int t = 0; t < Tn; t++) {
-        int tx = t % s->gx, ty = t / s->gx;
-        int64_t r0 = s->ranges[2 * t], r1 = s->ranges[2 * t + 1];
-        for (int ly = 0; ly < BLK; ly++) for (int lx = 0; lx < BLK; lx++) {
-            int px = tx * BLK + lx, py = ty * BLK + ly;
-            if (px >= W || py >= H || !pix_flag[(size_t)py * W + px]) continue;
-            for (int64_t j = r0; j < r1; j++) {
-                uint32_t g = s->point_list[j];
-                if (gauss_flag[g]) continue;
-                REAL dx = s->xy[2 * g] - px, dy = s->xy[2 * g + 1] - py;
-                const REAL *co = s->conic + 3 * g;
-                REAL power = (REAL)-0.5 * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
-                if ((double)power > eps_power) continue;
-                if ((double)in->opacities[g] * exp((double)power) * 255.0 >= 1.0 - eps_alpha) gauss_flag[g] = 1;   /* benign race: all writers store 1 */
+            if ((double)in->opacities[i] * exp((double)power) * 255.0 >= 0.99) {
+                pix_flag[(size_t)py * W + px] = 1;
+                pix_margin[(size_t)py * W + px] = (REAL)((double)s->geom_margin[i] / geom_err);
             }
         }
     }
+    /* pass 2: per Gaussian, the smallest pix_margin among the pixels it (nearly) contributes to.  The whole list is
+     * walked: a flipped early stop lets entries behind the oracle's terminating one contribute. */
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int t = 0; t < Tn; t++) {
+        int tx = t % s->gx, ty = t / s->gx;
+        int64_t r0 = s->ranges[2 * t], r1 = s->ranges[2 * t + 1], n = r1 - r0;
+        if (n <= 0) continue;
+        REAL *loc = (REAL *)malloc(sizeof(REAL) * n);
+        for (int64_t j = 0; j < n; j++) loc[j] = (REAL)1e30;
+        for (int ly = 0; ly < BLK; ly++) for (int lx = 0; lx < BLK; lx++) {
+            int px = tx * BLK + lx, py = ty * BLK + ly;
+            if (px >= W || py >= H) continue;
+            REAL pm = pix_margin[(size_t)py * W + px];
+            if (pm > (REAL)64) continue;          /* (margins beyond 64x the error model are not tracked per Gaussian) */
+            for (int64_t j = r0; j < r1; j++) {
+                if (loc[j - r0] <= pm) continue;
+                uint32_t g = s->point_list[j];
+                REAL dx = s->xy[2 * g] - px, dy = s->xy[2 * g + 1] - py;
+                const REAL *co = s->conic + 3 * g;
+                REAL power = (REAL)-0.5 * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+                if ((double)in->opacities[g] * exp((double)power) * 255.0 >= 0.99) loc[j - r0] = pm;
+            }
+        }
+        for (int64_t j = 0; j < n; j++) if (loc[j] < (REAL)1e30) {
+            uint32_t g = s->point_list[r0 + j];
+#pragma omp critical(scgo_gm)
+            { if (loc[j] < gauss_margin[g]) gauss_margin[g] = loc[j]; }
+        }
+        free(loc);
+    }
+    for (int i = 0; i < P; i++) {
+        if (s->radii[i] > 0 && (double)s->geom_margin[i] < geom_err) {
+            REAL q = (REAL)((double)s->geom_margin[i] / geom_err);
+            if (q < gauss_margin[i]) gauss_margin[i] = q;
+        }
+        gauss_flag[i] = own[i] ? 2 : (gauss_margin[i] < (REAL)1 ? 1 : 0);
+    }
+    free(own);
 }
 const REAL *scgo_geom_margin(const scgo_state *s) { return s->geom_margin; }

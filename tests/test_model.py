@@ -318,11 +318,11 @@ def test_fused_render_matches_reference_style_render():
     for k in out2:
         assert_image_close(k, out1[k].detach().cpu().numpy(), out2[k].detach().cpu().numpy(), flips)
     assert_grad_close("viewspace_points", out1["viewspace_points"].grad.cpu().numpy(), ssp.grad.cpu().numpy(), flips)
-    n_ray_flags = {True: flips["gauss_flag"][:n_ray], False: flips["gauss_flag"][n_ray:]}
     for n in TRAINED:
         a, b = getattr(pc1, n).grad, getattr(pc2, n).grad
         assert a is not None and b is not None, n
-        part = dict(flips, gauss_flag=n_ray_flags[not n.startswith("bg_")])
+        sl = slice(n_ray, None) if n.startswith("bg_") else slice(0, n_ray)      # the ray-based set comes first
+        part = dict(flips, **{k: flips[k][sl] for k in ("gauss_flag", "gauss_margin", "gauss_own")})
         assert_grad_close(n, a.cpu().numpy(), b.cpu().numpy(), part)
 
 

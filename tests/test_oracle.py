@@ -193,13 +193,15 @@ def test_f32_f64_oracles_differ_only_where_a_decision_sits_on_its_threshold():
     """Why the parity compares carry a flip allowance at all, and that the allowance is PROVEN per element: the
     float32 and float64 builds of the SAME C oracle differ beyond 1e-3 on a few gradient rows of this scene -- and
     every one of them belongs to a Gaussian that touches a pixel in which a discrete decision (alpha >= 1/255,
-    T >= 1e-4) sits within EPS of its threshold (oracle/scg_oracle.c: scgo_margins).  Nothing else is excused."""
+    T >= 1e-4) lies inside the uncertainty band of its threshold (oracle/scg_oracle.c: scgo_margins).  Nothing else is excused."""
     case = util.make_case(5000, 378, 504, sh_degree=0, scale_median=0.03, w2c=O.yaw_w2c(5.0))
     grads = O.synth_upstream_grads(378, 504)
     co32, img32, g32 = util.run_c_oracle(case, "f32", grads=grads)
     co64, img64, g64 = util.run_c_oracle(case, "f64", grads=grads)
     flips = util.flip_sets(co32)
-    assert 0 < flips["pix_flag"].mean() < 0.01 and 0 < flips["gauss_flag"].mean() < 0.15
+    print("flip-prone pixels", flips["pix_flag"].mean(), "flip-affected Gaussians", flips["gauss_flag"].mean(),
+          "own", flips["gauss_own"].mean())
+    assert 0 < flips["pix_flag"].mean() < 0.05 and 0 < flips["gauss_flag"].mean() < 0.5
     beyond = 0
     for k in ("means3D", "means2D", "opacities", "shs", "scales", "rotations"):
         st = util.assert_grad_close(k, g32[k], g64[k], flips)

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -72,25 +73,29 @@ def rel_err(a, b):
 # The rasterizer also takes DISCRETE decisions (alpha >= 1/255, T (1 - alpha) >= 1e-4, power <= 0, radius = ceil(..),
 # tile rect = trunc(..)) that a last-bit difference can flip; a flip moves a pixel by up to ~alpha = 4e-3 -- no
 # tolerance on the values can absorb it, the f32 and f64 builds of the oracle differ from EACH OTHER this way.  An
-# element beyond rtol is therefore accepted ONLY when the oracle proves that a decision it depends on sits within
-# EPS of its threshold (oracle/scg_oracle.c: scgo_margins): the pixel is flip-prone, or the Gaussian (nearly)
-# contributes to a flip-prone pixel.  Such elements must still lie within FLIP_BOUND norm-wise -- one flipped
-# contribution is worth at most alpha at the edge of the 3-sigma rect, 0.011 x opacity, of the value range.  Without
-# an oracle state (`flips=None`) nothing is excused.
+# element beyond rtol is therefore accepted ONLY when the oracle proves that a decision it depends on lies inside the
+# uncertainty band of its threshold, the band following from a stated fp32 error model (ERROR_MODEL below;
+# oracle/scg_oracle.c: scgo_margins): the pixel is flip-prone, or the Gaussian (nearly) contributes to a flip-prone
+# pixel.  Such elements must still lie within FLIP_BOUND norm-wise -- one flipped contribution is worth at most
+# alpha at the edge of the 3-sigma rect, 0.011 x opacity, of the value range.  Without an oracle state
+# (`flips=None`) nothing is excused.  Every compare returns what it measured, including `model_scale_needed`: the
+# factor by which the error model would have had to be scaled to excuse the worst offending element (< 1 = inside).
+# SCGR_PARITY_CALIBRATE=1 turns the "unexplained element" failure into a record (to size the model from a first run).
 # ---------------------------------------------------------------------------------------------------------------
-EPS = dict(eps_alpha=5e-5, eps_T=5e-5, eps_power=1e-6, eps_geom=1e-4)    # relative, relative, absolute, pixels
+ERROR_MODEL = dict(base_err=2e-6,      # relative: exp() + the products around it (hardware exp2: 2 ulp)
+                   conic_err=2e-6,     # relative: conic coefficients, hence power
+                   pos_ulps=4.0)       # projected mean: 4 ulp of the largest pixel coordinate (2^-23 max(W, H) px each)
 FLIP_BOUND = 1.2e-2
 IMAGE_FLOOR = 0.01       # x RMS of the image
 GRAD_FLOOR = 1.0         # x RMS of the non-zero gradient entries
+CALIBRATE = os.environ.get("SCGR_PARITY_CALIBRATE") == "1"
 
 
-def flip_sets(co, **eps):
+def flip_sets(co, **model):
     """Flip-prone pixels / flip-affected Gaussians of the view the C oracle `co` last rendered."""
-    kw = dict(EPS)
-    kw.update(eps)
-    m = co.margins(**kw)
-    m["eps"] = kw
-    return m
+    kw = dict(ERROR_MODEL)
+    kw.update(model)
+    return co.margins(**kw)
 
 
 def _elementwise(got, want, floor_frac, nonzero_rms):
@@ -102,18 +107,26 @@ def _elementwise(got, want, floor_frac, nonzero_rms):
     return diff / (np.abs(want) + floor_frac * rms + 1e-300), diff / (np.abs(want).max() + 1e-30)
 
 
-def _judge(name, err, nw, excusable, rtol):
+def _judge(name, err, nw, margin, rtol):
+    """margin: per-element margin / uncertainty of the nearest decision the element depends on (None: nothing is
+    excusable).  An element is excusable when margin < 1."""
     bad = err > rtol
     n_bad = int(bad.sum())
+    excusable = np.zeros(err.shape, bool) if margin is None else margin < 1.0
     stats = dict(max_err=float(err.max()) if err.size else 0.0, max_normwise=float(nw.max()) if nw.size else 0.0,
                  n=int(err.size), n_beyond_rtol=n_bad, excusable_frac=float(excusable.mean()) if excusable.size else 0.0,
                  max_err_unexcusable=float(err[~excusable].max()) if (~excusable).any() else 0.0)
     if n_bad:
+        stats["model_scale_needed"] = float(margin[bad].max()) if margin is not None else float("inf")
+        stats["max_normwise_beyond_rtol"] = float(nw[bad].max())
         rogue = bad & ~excusable
-        assert not rogue.any(), (f"{name}: {int(rogue.sum())} element(s) beyond rtol={rtol} that no near-threshold "
-                                 f"decision explains (max {err[rogue].max():.3e}; {n_bad} beyond rtol in all)")
+        if CALIBRATE:
+            stats["n_unexplained"] = int(rogue.sum())
+            return stats
+        assert not rogue.any(), (f"{name}: {int(rogue.sum())} element(s) beyond rtol={rtol} that no decision inside its "
+                                 f"uncertainty band explains (max err {err[rogue].max():.3e}; {n_bad} beyond rtol in all; "
+                                 f"error model would need x{stats['model_scale_needed']:.3g})")
         assert nw[bad].max() <= FLIP_BOUND, f"{name}: a flip-excused element is off by {nw[bad].max():.3e} > {FLIP_BOUND} norm-wise"
-        stats["max_normwise_excused"] = float(nw[bad].max())
     return stats
 
 
@@ -124,8 +137,8 @@ def assert_image_close(name, got, want, flips=None, rtol=RTOL_IMAGE):
     assert got.shape == want.shape, (name, got.shape, want.shape)
     assert np.isfinite(got).all(), f"{name}: non-finite values"
     err, nw = _elementwise(got, want, IMAGE_FLOOR, False)
-    exc = np.zeros(got.shape, bool) if flips is None else np.broadcast_to(flips["pix_flag"][None], got.shape)
-    return _judge(name, err, nw, exc, rtol)
+    margin = None if flips is None else np.broadcast_to(flips["pix_margin"][None].astype(np.float64), got.shape)
+    return _judge(name, err, nw, margin, rtol)
 
 
 def assert_grad_close(name, got, want, flips=None, rtol=RTOL_GRAD):
@@ -137,22 +150,90 @@ def assert_grad_close(name, got, want, flips=None, rtol=RTOL_GRAD):
         return dict(max_err=0.0, max_normwise=0.0, n=0, n_beyond_rtol=0)
     assert np.isfinite(got).all(), f"{name}: non-finite values"
     err, nw = _elementwise(got, want, GRAD_FLOOR, True)
-    exc = np.zeros(got.shape, bool)
+    margin = None
     if flips is not None:
-        exc = np.broadcast_to(flips["gauss_flag"].reshape((-1,) + (1,) * (got.ndim - 1)), got.shape)
-    return _judge(name, err, nw, exc, rtol)
+        gm = np.where(flips["gauss_flag"], np.minimum(flips["gauss_margin"], 0.999), flips["gauss_margin"]).astype(np.float64)
+        margin = np.broadcast_to(gm.reshape((-1,) + (1,) * (got.ndim - 1)), got.shape)
+    st = _judge(name, err, nw, margin, rtol)
+    if flips is not None and st["n_beyond_rtol"]:
+        rows = (err > rtol).reshape(len(err), -1).any(1)
+        st["rows_beyond_rtol"] = int(rows.sum())
+        st["rows_beyond_rtol_own_decision"] = int((rows & flips["gauss_own"]).sum())
+    return st
 
 
 def assert_radii_match(name, got, want, flips=None):
-    """radii are integers: bit-exact, except where 3 sqrt(lambda) sits within eps_geom of an integer (ceil of a
-    last-bit difference) -- then they may differ by one.  Returns the number of such mismatches."""
+    """radii are integers: bit-exact, except where 3 sqrt(lambda) sits within the model's geometric uncertainty of an
+    integer (ceil of a last-bit difference) -- then they may differ by one.  Returns the number of such mismatches."""
     got, want = np.asarray(got).astype(np.int64), np.asarray(want).astype(np.int64)
     mis = got != want
     n = int(mis.sum())
     if n:
         assert flips is not None, f"{name}: {n} radii differ"
         assert np.abs(got - want)[mis].max() <= 1, f"{name}: radii differ by more than one"
-        gm = flips["geom_margin"][mis]
-        assert (gm < flips["eps"]["eps_geom"]).all(), \
-            f"{name}: {n} radii differ, {int((gm >= flips['eps']['eps_geom']).sum())} of them away from a rounding boundary (margin up to {gm.max():.3e} px)"
+        gm, lim = flips["geom_margin"][mis], flips["model"]["geom_err_px"]
+        if not CALIBRATE:
+            assert (gm < lim).all(), (f"{name}: {n} radii differ, {int((gm >= lim).sum())} of them away from a rounding "
+                                      f"boundary (margin up to {gm.max():.3e} px, model {lim:.3e} px)")
     return n
+
+
+# ---- staged parity: the oracle's binning + blend + backward on the 2D state the CUDA preprocess produced ----
+STAGED_MODEL = dict(base_err=2e-6, conic_err=5e-7, pos_ulps=0.0)     # identical means / radii; conic re-scaled once
+
+
+def records_override(record, radii):
+    """libscgr's packed per-Gaussian record [P,12] (include/scgr.h: ScgrDebugViews.record) -> the override arrays of
+    COracle.forward: means2D, conic (un-scaled from the render-ready log2 form), rgb, depth, radii, clamp flags."""
+    rec = np.ascontiguousarray(record, dtype=np.float32)
+    radii = np.ascontiguousarray(radii, dtype=np.int32)
+    log2e = 1.4426950408889634
+    r64 = rec.astype(np.float64)
+    conic = np.stack([r64[:, 2] / (-0.5 * log2e), r64[:, 3] / (-log2e), r64[:, 4] / (-0.5 * log2e)], 1)
+    bits = rec[:, 11].copy().view(np.uint32)
+    flags = (bits >> 28).astype(np.uint8)
+    clamped = np.stack([flags & 1, (flags >> 1) & 1, (flags >> 2) & 1], 1).astype(np.uint8)
+    vis = radii > 0
+    z = lambda a: np.where(vis.reshape((-1,) + (1,) * (a.ndim - 1)), a, 0)
+    return dict(xy=z(r64[:, 0:2]), conic=z(conic), rgb=z(r64[:, 8:11]), depth=z(r64[:, 6]), radii=radii, clamped=z(clamped))
+
+
+def run_c_oracle_staged(case, record, radii, precision="f32", grads=None, colors_precomp=None, cov3D_precomp=None):
+    """run_c_oracle with the 2D state forced to the CUDA preprocess's (see records_override)."""
+    co = COracle(precision)
+    kw = {}
+    if colors_precomp is not None:
+        kw["colors_precomp"] = colors_precomp.numpy()
+    else:
+        kw["shs"] = case["shs"].numpy()
+    if cov3D_precomp is not None:
+        kw["cov3D_precomp"] = cov3D_precomp.numpy()
+    else:
+        kw["scales"] = case["scales"].numpy()
+        kw["rotations"] = case["rotations"].numpy()
+    out = co.forward(means3D=case["means3D"].numpy(), opacities=case["opacities"].numpy(), W=case["W"],
+                     H=case["H"], tanfovx=case["tanfovx"], tanfovy=case["tanfovy"], bg=case["bg"].numpy(),
+                     viewmatrix=case["viewmatrix"].numpy(), projmatrix=case["projmatrix"].numpy(),
+                     campos=case["campos"].numpy(), sh_degree=case["sh_degree"],
+                     scale_modifier=case["scale_modifier"], override=records_override(record, radii), **kw)
+    g = co.backward(*[x.numpy() for x in grads]) if grads is not None else None
+    return co, out, g
+
+
+def preprocess_errors(record, radii, co):
+    """The CUDA preprocess's per-Gaussian values against the oracle's own (A.1-A.5), over the Gaussians both keep."""
+    st = co.state()
+    rec = np.asarray(record, dtype=np.float64)
+    radii = np.asarray(radii)
+    both = (radii > 0) & (st["tiles_touched"] > 0)
+    log2e = 1.4426950408889634
+    conic = np.stack([rec[:, 2] / (-0.5 * log2e), rec[:, 3] / (-log2e), rec[:, 4] / (-0.5 * log2e)], 1)
+    W, H = co._dims[2], co._dims[3]
+    ulp = 2.0 ** -23 * max(W, H)
+    cs = np.abs(st["conic"][both]).max(1, keepdims=True) + 1e-30        # per-Gaussian scale of its conic
+    return dict(n_both=int(both.sum()),
+                xy_px=float(np.abs(rec[both][:, 0:2] - st["means2D"][both]).max()) if both.any() else 0.0,
+                xy_ulps_of_max_coord=float(np.abs(rec[both][:, 0:2] - st["means2D"][both]).max() / ulp) if both.any() else 0.0,
+                conic_rel=float((np.abs(conic[both] - st["conic"][both]) / cs).max()) if both.any() else 0.0,
+                rgb_abs=float(np.abs(rec[both][:, 8:11] - st["rgb"][both]).max()) if both.any() else 0.0,
+                depth_rel=float((np.abs(rec[both][:, 6] - st["depths"][both]) / st["depths"][both]).max()) if both.any() else 0.0)
