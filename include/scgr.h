@@ -83,7 +83,8 @@ typedef struct ScgrGaussians {
 } ScgrGaussians;
 
 /* Gradients returned by _RasterizeGaussians.backward.  Every
- * non-NULL array is written in full (zeros for culled Gaussians): no caller-side memset needed. */
+ * non-NULL array is written in full (zeros for culled Gaussians): no caller-side memset needed
+ * (unless `accumulate` is set, see below). */
 typedef struct ScgrGrads {
     float* dL_dmeans3D;        /* [P,3] */
     float* dL_dmeans2D;        /* [P,3]  NDC-scaled screen-space gradient, z = 0 */
@@ -93,6 +94,16 @@ typedef struct ScgrGrads {
     float* dL_dscales;         /* [P,3] or NULL */
     float* dL_drotations;      /* [P,4] or NULL */
     float* dL_dcov3D_precomp;  /* [P,6] or NULL */
+    /* Optional, for batches of views (the reference accumulates the same quantities over
+     * sequential iterations, scene/gaussian_model.py:932-934):
+     * densification_stats [P,2] receives {|dL_dmeans2D[i, 0:2]| * visible_i, visible_i} with visible_i = radii[i] > 0
+     * -- the two per-view terms of add_densification_stats -- so that one SUM all-reduce over a flat buffer carries
+     * them; it requires `radii` (the forward's int32 [P] output).  With accumulate != 0 every parameter gradient and
+     * the statistics are ADDED to what the arrays hold (gradient accumulation over the views a rank renders before
+     * the single all-reduce); dL_dmeans2D is per view and is always overwritten. */
+    float* densification_stats;
+    const int32_t* radii;
+    int32_t accumulate;
 } ScgrGrads;
 
 int scgr_version(void);

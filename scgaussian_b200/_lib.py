@@ -31,7 +31,8 @@ class ScgrGrads(C.Structure):
     _fields_ = [("dL_dmeans3D", C.c_void_p), ("dL_dmeans2D", C.c_void_p), ("dL_dshs", C.c_void_p),
                 ("dL_dcolors_precomp", C.c_void_p), ("dL_dopacities", C.c_void_p),
                 ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p),
-                ("dL_dcov3D_precomp", C.c_void_p)]
+                ("dL_dcov3D_precomp", C.c_void_p), ("densification_stats", C.c_void_p), ("radii", C.c_void_p),
+                ("accumulate", C.c_int32)]
 
 
 class ScgrDebugViews(C.Structure):

@@ -330,6 +330,10 @@ int scgr_backward(const ScgrView* view, const ScgrGaussians* g, const void* geom
                 (g->rotations != nullptr) == (grads->dL_drotations != nullptr), "dL_dscales / dL_drotations must match inputs");
         require((g->cov3D_precomp != nullptr) == (grads->dL_dcov3D_precomp != nullptr), "dL_dcov3D_precomp must match cov3D_precomp");
         if (grads->dL_drotations) require((reinterpret_cast<uintptr_t>(grads->dL_drotations) & 15) == 0, "dL_drotations must be 16-byte aligned");
+        if (grads->densification_stats) {
+            require(grads->radii != nullptr, "densification_stats needs radii");
+            require((reinterpret_cast<uintptr_t>(grads->densification_stats) & 7) == 0, "densification_stats must be 8-byte aligned");
+        }
         const Launch L{(cudaStream_t)stream, view->debug != 0};
         const int W = view->image_width, H = view->image_height;
         const GeometryLayout G = carve_geometry(const_cast<void*>(geometry_scratch), g->P);

@@ -399,7 +399,9 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
 // ------------------------------------------------------------------------------------------
 // backward (A.10), fused: conic->cov2D->{Sigma, t}, NDC mean, depth, SH, Sigma->{scale, rot}
 // ------------------------------------------------------------------------------------------
-template <bool SH_FAST, int MINB>
+// ACC: gradient accumulation over the views of a batch (ScgrGrads.accumulate): every parameter gradient is added to
+// what the array holds, Gaussians without gradient are not touched at all; dL/dmean2D stays per view.
+template <bool SH_FAST, int MINB, bool ACC>
 __global__ void __launch_bounds__(PB_T, MINB)
 preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record* __restrict__ rec,
                            const ScreenGrad* __restrict__ sg, const ScgrGrads out) {
@@ -456,8 +458,15 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     for (int k = 0; k < PB_K; k++) {
         const int own = row0 + k * PB_T + tid;
         if (own < P && !own_live[k]) {
-            out.dL_dmeans3D[3 * (size_t)own] = 0.f; out.dL_dmeans3D[3 * (size_t)own + 1] = 0.f; out.dL_dmeans3D[3 * (size_t)own + 2] = 0.f;
             out.dL_dmeans2D[3 * (size_t)own] = 0.f; out.dL_dmeans2D[3 * (size_t)own + 1] = 0.f; out.dL_dmeans2D[3 * (size_t)own + 2] = 0.f;
+            if (out.densification_stats) {      // {|dL/dmean2D| visible, visible}: visible without gradient counts in the denominator
+                const float vis = __ldg(out.radii + own) > 0 ? 1.f : 0.f;
+                float2* st = reinterpret_cast<float2*>(out.densification_stats) + own;
+                if (ACC) { if (vis != 0.f) { float2 o = *st; o.y += vis; *st = o; } }
+                else *st = make_float2(0.f, vis);
+            }
+            if (ACC) continue;
+            out.dL_dmeans3D[3 * (size_t)own] = 0.f; out.dL_dmeans3D[3 * (size_t)own + 1] = 0.f; out.dL_dmeans3D[3 * (size_t)own + 2] = 0.f;
             out.dL_dopacities[own] = 0.f;
             if (out.dL_dcolors_precomp) {
                 out.dL_dcolors_precomp[3 * (size_t)own] = 0.f; out.dL_dcolors_precomp[3 * (size_t)own + 1] = 0.f; out.dL_dcolors_precomp[3 * (size_t)own + 2] = 0.f;
@@ -476,7 +485,7 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
             }
         }
     }
-    if (SH_FAST && use_sh) {
+    if (SH_FAST && use_sh && !ACC) {
         float4* dst = reinterpret_cast<float4*>(out.dL_dshs) + (size_t)row0 * SH_ROW_F4;
         const int nf4 = nrows * SH_ROW_F4;
         for (int f = tid; f < nf4; f += PB_T)
@@ -636,10 +645,11 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
                 float* orow = out.dL_dshs + (size_t)i * g.sh_coeffs * 3;
                 for (int k = 0; k < g.sh_coeffs; k++) {
                     if (k < nk) {
-                        orow[3 * k] = bb[k] * gr; orow[3 * k + 1] = bb[k] * gg; orow[3 * k + 2] = bb[k] * gb;
+                        if (ACC) { orow[3 * k] += bb[k] * gr; orow[3 * k + 1] += bb[k] * gg; orow[3 * k + 2] += bb[k] * gb; }
+                        else { orow[3 * k] = bb[k] * gr; orow[3 * k + 1] = bb[k] * gg; orow[3 * k + 2] = bb[k] * gb; }
                         const float w = gr * __ldg(row + 3 * k) + gg * __ldg(row + 3 * k + 1) + gb * __ldg(row + 3 * k + 2);
                         ddx += bx[k] * w; ddy += by[k] * w; ddz += bz[k] * w;
-                    } else {
+                    } else if (!ACC) {
                         orow[3 * k] = 0.f; orow[3 * k + 1] = 0.f; orow[3 * k + 2] = 0.f;
                     }
                 }
@@ -683,20 +693,31 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     }
 
     if (live) {
-        out.dL_dmeans3D[3 * (size_t)i] = dmean[0]; out.dL_dmeans3D[3 * (size_t)i + 1] = dmean[1]; out.dL_dmeans3D[3 * (size_t)i + 2] = dmean[2];
+        auto put = [](float* ptr, const float val) { if (ACC) *ptr += val; else *ptr = val; };
+        put(out.dL_dmeans3D + 3 * (size_t)i, dmean[0]); put(out.dL_dmeans3D + 3 * (size_t)i + 1, dmean[1]); put(out.dL_dmeans3D + 3 * (size_t)i + 2, dmean[2]);
         out.dL_dmeans2D[3 * (size_t)i] = dm2x; out.dL_dmeans2D[3 * (size_t)i + 1] = dm2y; out.dL_dmeans2D[3 * (size_t)i + 2] = 0.f;
-        out.dL_dopacities[i] = dop;
+        put(out.dL_dopacities + i, dop);
+        if (out.densification_stats) {      // a Gaussian with gradient is visible
+            float2* st = reinterpret_cast<float2*>(out.densification_stats) + i;
+            const float nrm = sqrtf(dm2x * dm2x + dm2y * dm2y);
+            if (ACC) { float2 o = *st; o.x += nrm; o.y += 1.f; *st = o; }
+            else *st = make_float2(nrm, 1.f);
+        }
         if (out.dL_dcolors_precomp) {
-            out.dL_dcolors_precomp[3 * (size_t)i] = dcol[0]; out.dL_dcolors_precomp[3 * (size_t)i + 1] = dcol[1]; out.dL_dcolors_precomp[3 * (size_t)i + 2] = dcol[2];
+            put(out.dL_dcolors_precomp + 3 * (size_t)i, dcol[0]); put(out.dL_dcolors_precomp + 3 * (size_t)i + 1, dcol[1]); put(out.dL_dcolors_precomp + 3 * (size_t)i + 2, dcol[2]);
         }
         if (out.dL_dscales) {
-            out.dL_dscales[3 * (size_t)i] = dscale[0]; out.dL_dscales[3 * (size_t)i + 1] = dscale[1]; out.dL_dscales[3 * (size_t)i + 2] = dscale[2];
+            put(out.dL_dscales + 3 * (size_t)i, dscale[0]); put(out.dL_dscales + 3 * (size_t)i + 1, dscale[1]); put(out.dL_dscales + 3 * (size_t)i + 2, dscale[2]);
         }
-        if (out.dL_drotations)
-            reinterpret_cast<float4*>(out.dL_drotations)[i] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+        if (out.dL_drotations) {
+            float4* pr4 = reinterpret_cast<float4*>(out.dL_drotations) + i;
+            float4 o = make_float4(drot[0], drot[1], drot[2], drot[3]);
+            if (ACC) { const float4 h = *pr4; o.x += h.x; o.y += h.y; o.z += h.z; o.w += h.w; }
+            *pr4 = o;
+        }
         if (out.dL_dcov3D_precomp) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) out.dL_dcov3D_precomp[6 * (size_t)i + k] = d6[k];
+            for (int k = 0; k < 6; k++) put(out.dL_dcov3D_precomp + 6 * (size_t)i + k, d6[k]);
         }
     }
     if (SH_FAST && use_sh) {
@@ -706,7 +727,10 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
         float4* dst = reinterpret_cast<float4*>(out.dL_dshs) + (size_t)row0 * SH_ROW_F4;
         for (int f = tid; f < in_round * SH_ROW_F4; f += PB_T) {
             const int r = f / SH_ROW_F4, c = f - r * SH_ROW_F4;
-            dst[(int)s_list[first + r] * SH_ROW_F4 + c] = s_sh[r * SH_ROW_F4_PAD + c];
+            float4* d4 = dst + (int)s_list[first + r] * SH_ROW_F4 + c;
+            float4 o = s_sh[r * SH_ROW_F4_PAD + c];
+            if (ACC) { const float4 h = *d4; o.x += h.x; o.y += h.y; o.z += h.z; o.w += h.w; }
+            *d4 = o;
         }
         __syncthreads();      // the staging buffer is reused by the next round
     }
@@ -756,12 +780,16 @@ void launch_preprocess_backward(const ScgrView& v, const ScgrGaussians& g, const
     const int blocks = (g.P + PB_G - 1) / PB_G;
     begin_kernel("preprocess_backward", L);
     static const int minb = getenv("SCGR_PREB_MINB") ? atoi(getenv("SCGR_PREB_MINB")) : 1;
+    const bool acc = out.accumulate != 0;
     if (sh_fast_ok(g, out.dL_dshs)) {
-        if (minb == 12) preprocess_backward_kernel<true, 12><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (minb == 10) preprocess_backward_kernel<true, 10><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else preprocess_backward_kernel<true, 1><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        if (acc) preprocess_backward_kernel<true, 1, true><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (minb == 12) preprocess_backward_kernel<true, 12, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (minb == 10) preprocess_backward_kernel<true, 10, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else preprocess_backward_kernel<true, 1, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+    } else if (acc) {
+        preprocess_backward_kernel<false, 1, true><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     } else {
-        preprocess_backward_kernel<false, 1><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        preprocess_backward_kernel<false, 1, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     }
     check_launch("preprocess_backward", L);
 }

@@ -68,12 +68,16 @@ class FlatGradBuffer:
         self.means2D = torch.empty(P, 3, dtype=torch.float32, device=device)
 
     def out_dict(self) -> Dict[str, torch.Tensor]:
-        d = {k: v for k, v in self.views.items() if k != "stats"}
+        """What rasterize_backward_raw(out=...) writes into: the parameter gradients AND the per-view densification
+        statistics (scgr_backward produces both: ScgrGrads.densification_stats), all inside the flat buffer."""
+        d = dict(self.views)
         d["means2D"] = self.means2D
         return d
 
     def fill_stats(self, radii: torch.Tensor) -> None:
-        """reference scene/gaussian_model.py:932-934 for this rank's view."""
+        """reference scene/gaussian_model.py:932-934 for this rank's view, from torch ops -- for callers whose backward
+        did not go through out_dict() (e.g. autograd through the public operator); scgr_backward writes the same two
+        columns itself when given the `stats` view."""
         if "stats" not in self.views:
             return
         vis = (radii > 0).to(torch.float32)

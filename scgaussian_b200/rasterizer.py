@@ -108,6 +108,7 @@ class ForwardState(NamedTuple):
     image: torch.Tensor
     capacity: int
     num_rendered: int
+    radii: Optional[torch.Tensor] = None
 
 
 def rasterize_forward_raw(means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp,
@@ -187,15 +188,18 @@ def rasterize_forward_raw(means3D, opacities, sh, colors_precomp, scales, rotati
             capacity = R
             binning = run_render(capacity)
         _capacity_hint[key] = R
-    return color, radii, depth, alpha, ForwardState(geometry, binning, image, capacity, R)
+    return color, radii, depth, alpha, ForwardState(geometry, binning, image, capacity, R, radii)
 
 
 def rasterize_backward_raw(state: ForwardState, means3D, opacities, sh, colors_precomp, scales, rotations,
                            cov3Ds_precomp, s: GaussianRasterizationSettings, grad_color, grad_depth, grad_alpha,
-                           out: Optional[dict] = None) -> dict:
+                           out: Optional[dict] = None, accumulate: bool = False) -> dict:
     """Runs scgr_backward.  `out` may hold pre-allocated gradient tensors (e.g. views into one flat
     all-reduce buffer, scgaussian_b200/parallel.py); missing ones are allocated.  Every returned
-    tensor is fully written by the kernels."""
+    tensor is fully written by the kernels.  out["stats"] ([P,2], optional) receives the two per-view
+    densification terms of reference scene/gaussian_model.py:932-934.  accumulate=True ADDS the parameter
+    gradients (and the statistics) to what `out` holds -- gradient accumulation over the views a rank renders
+    before the batch's single all-reduce; it needs every gradient tensor to be passed in."""
     global launch_counter
     lib = _lib.load()
     device = means3D.device
@@ -203,11 +207,14 @@ def rasterize_backward_raw(state: ForwardState, means3D, opacities, sh, colors_p
     H, W = int(s.image_height), int(s.image_width)
     out = dict(out) if out else {}
 
+    missing = []
+
     def need(name, ref, shape):
         if ref is None or ref.numel() == 0:
             return None
         t = out.get(name)
         if t is None:
+            missing.append(name)
             t = torch.empty(shape, dtype=torch.float32, device=device)
             out[name] = t
         assert t.is_contiguous() and t.dtype == torch.float32 and tuple(t.shape) == tuple(shape), name
@@ -225,11 +232,19 @@ def rasterize_backward_raw(state: ForwardState, means3D, opacities, sh, colors_p
         gsc = need("scales", scales, (P, 3))
         grot = need("rotations", rotations, (P, 4))
         gcov = need("cov3D_precomp", cov3Ds_precomp, (P, 6))
+        stats = out.get("stats")
+        if stats is not None:
+            assert stats.is_contiguous() and stats.dtype == torch.float32 and tuple(stats.shape) == (P, 2), "stats"
+            if state.radii is None:
+                raise ScgrError("densification statistics need the forward's radii (ForwardState.radii)")
+        if accumulate and missing:
+            raise ScgrError(f"accumulate=True needs the gradient tensors to add into: {missing} not in `out`")
         if P == 0:
             return out
         view = _make_view(s, device, keep)
         g = _make_gaussians(means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp)
-        grads = ScgrGrads(_ptr(gm3), _ptr(gm2), _ptr(gsh), _ptr(gcol), _ptr(gop), _ptr(gsc), _ptr(grot), _ptr(gcov))
+        grads = ScgrGrads(_ptr(gm3), _ptr(gm2), _ptr(gsh), _ptr(gcol), _ptr(gop), _ptr(gsc), _ptr(grot), _ptr(gcov),
+                          _ptr(stats), _ptr(state.radii) if stats is not None else None, int(bool(accumulate)))
         gc = _f32c(grad_color, device)
         gd = _f32c(grad_depth, device)
         ga = _f32c(grad_alpha, device)

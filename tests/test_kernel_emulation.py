@@ -575,6 +575,52 @@ def test_whole_operator_on_host_matches_oracle(emu_pre, monkeypatch, P, W, H, sm
         assert float(v.abs().max()) > 0.0, k
 
 
+def test_backward_accumulates_over_views_and_emits_densification_stats_on_host(emu_pre, monkeypatch):
+    """ScgrGrads.accumulate / .densification_stats (include/scgr.h): the backward of a second view ADDS its parameter
+    gradients to the first one's, leaves Gaussians without gradient untouched, keeps dL/dmean2D per view, and the
+    statistics columns hold sum_v |dL/dmean2D_v[:, :2]| * visible_v and sum_v visible_v -- what the reference's
+    add_densification_stats accumulates over sequential views (scene/gaussian_model.py:932-934)."""
+    from oracle import torch_oracle as O
+    monkeypatch.setenv("SCGR_FWD_SPLIT", "0,0")
+    monkeypatch.setenv("SCGR_BWD_SPLIT", "0,0")
+    P, W, H = 900, 120, 90
+    M = 16
+    per_view, keep = [], []
+    acc = {"means3D": torch.full((P, 3), float("nan")), "shs": torch.full((P, M, 3), float("nan")),
+           "opacities": torch.full((P, 1), float("nan")), "scales": torch.full((P, 3), float("nan")),
+           "rotations": torch.full((P, 4), float("nan")), "stats": torch.full((P, 2), float("nan"))}
+    for v, yaw in enumerate((-6.0, 9.0)):
+        case, t, view, g = _host_scene(P, W, H, 3, seed=41, scale_median=0.06, w2c=O.yaw_w2c(yaw), z_shift=-1.2)
+        f = _host_forward(emu_pre, case, t, view, g, P, W, H)
+        gC, gD, gA = [x.contiguous() for x in O.synth_upstream_grads(W, H, seed=3 + v)]
+        emu_pre.emu_render_backward(C.byref(view), C.byref(g), C.c_void_p(f["gptr"]), C.c_void_p(f["bptr"]), C.c_int64(f["R"]),
+                                    C.c_void_p(f["iptr"]), _p(gC), _p(gD), _p(gA))
+        solo = {k: torch.full_like(a, float("nan")) for k, a in acc.items()}
+        m2 = torch.full((P, 3), float("nan"))
+        sg = L.ScgrGrads(solo["means3D"].data_ptr(), m2.data_ptr(), solo["shs"].data_ptr(), None, solo["opacities"].data_ptr(),
+                         solo["scales"].data_ptr(), solo["rotations"].data_ptr(), None, solo["stats"].data_ptr(),
+                         f["radii"].data_ptr(), 0)
+        emu_pre.emu_preprocess_backward(C.byref(view), C.byref(g), C.c_void_p(f["gptr"]), C.byref(sg))
+        vis = (f["radii"] > 0).float()
+        want_stats = torch.stack([torch.linalg.vector_norm(m2[:, :2], dim=-1) * vis, vis], 1)
+        assert torch.allclose(solo["stats"], want_stats, rtol=1e-6, atol=0) and not torch.isnan(solo["stats"]).any()
+        assert (vis.sum() > (solo["opacities"][:, 0] != 0).sum()) and vis.sum() < P      # visible-but-gradient-free and culled both occur
+        per_view.append((solo, m2.clone()))
+        # the same backward into the shared arrays: view 0 overwrites, view 1 accumulates
+        m2b = torch.full((P, 3), float("nan"))
+        sg = L.ScgrGrads(acc["means3D"].data_ptr(), m2b.data_ptr(), acc["shs"].data_ptr(), None, acc["opacities"].data_ptr(),
+                         acc["scales"].data_ptr(), acc["rotations"].data_ptr(), None, acc["stats"].data_ptr(),
+                         f["radii"].data_ptr(), int(v > 0))
+        emu_pre.emu_preprocess_backward(C.byref(view), C.byref(g), C.c_void_p(f["gptr"]), C.byref(sg))
+        assert torch.equal(m2b, m2)                                   # per view, never accumulated
+        keep.append((f, t, case))
+    for k, a in acc.items():
+        want = per_view[0][0][k] + per_view[1][0][k]
+        assert not torch.isnan(a).any(), k
+        assert torch.allclose(a, want, rtol=1e-6, atol=1e-12), k
+    assert float(acc["stats"][:, 1].max()) == 2.0
+
+
 def test_overflow_flag_on_host_describes_the_last_emission(emu_pre):
     """The recovery path of SCGR_NEED_CAPACITY at kernel level: an emission into a binning buffer that is too small
     writes nothing and raises the device flag; the re-run with a large enough buffer (stage 1 kept) clears it and

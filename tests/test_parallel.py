@@ -34,7 +34,8 @@ def _worker(rank, world, port, out_dir):
         radii, g = _view_grads(rank)
         out = buf.out_dict()
         for k in out:                      # what scgr_backward does on the GPU: fill the views in place
-            out[k].copy_(torch.from_numpy(g[k]).reshape(out[k].shape))
+            if k != "stats":
+                out[k].copy_(torch.from_numpy(g[k]).reshape(out[k].shape))
         buf.fill_stats(torch.from_numpy(radii))
         buf.all_reduce()
         np.save(os.path.join(out_dir, f"flat_{rank}.npy"), buf.flat.numpy())
