@@ -1,24 +1,33 @@
 #!/usr/bin/env python
 """bench.py -- views/sec forward+backward of the rasterizer hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 3|4]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload): BASELINE config 3 -- synthetic 1M Gaussians, 1920x1080, SH degree 3,
-seed-0 generator of SURVEY.md section 8d.  A *step* is one forward + backward of one view per GPU
-(weak scaling: rank k renders the k-th yawed camera of the batch) followed, when N > 1, by the
-path's single collective: one NCCL all-reduce over the flat gradient buffer.
+Workload (config.workload): BASELINE config 3 -- synthetic 1M Gaussians, 1920x1080, SH degree 3, seed-0 generator of
+SURVEY.md section 8d.  A *step* is one forward + backward of one view per GPU (weak scaling) followed, when N > 1, by
+the path's single collective: one all-reduce over the flat gradient buffer.  The camera changes EVERY step -- the 8
+yawed cameras of SURVEY 8d, (k - 3.5) * 2 degrees; rank r renders camera (r + step) % 8 -- so the instance count R varies
+from step to step the way it does in training (reference train.py:135 picks a random camera per iteration) and the
+pre-sized binning buffer can miss (`need_capacity_hits`).
 
 Printed JSON line (rank 0):
-  value        views/s over all ranks, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e          the same metric through the public operator (GaussianRasterizer + autograd), with the
-               per-step host inputs of a training step (camera matrices + ground-truth image, pinned
-               host memory -> device) and the loss read back (device -> host) inside the timed region
-  roofline     dominant kernel: algorithmic bytes / its CUDA-event duration
-  kernels      per-kernel average milliseconds of one step (profiled in a separate short loop)
-  cpu_baseline the CPU oracle (scalar C port, OpenMP) timed on this host on one full view
-  --impl reference: the reference has no CPU path and its CUDA rasterizer is not obtainable offline
-  (SURVEY.md section 0); this arm times the oracle port of its algorithm on the host cores.
+  value          views/s over all ranks, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e            the same metric through the public operator (GaussianRasterizer + autograd), with the per-step host
+                 inputs of a training step (camera + ground-truth image, pinned host memory -> device) and the loss
+                 read back (device -> host) inside the timed region
+  roofline       dominant kernel: algorithmic bytes / its CUDA-event duration
+  roofline_issue the render kernels against the SM issue rate (148 SMs x 4 schedulers x f_clk) and per pair evaluation
+  kernels        per-kernel average milliseconds of one step (profiled in a separate short loop)
+  batch8         the north_star's fixed 8-view batch: 8 / N views per rank, gradients accumulated on the device,
+                 ONE all-reduce per batch
+  config4        (N = 8, or --config4) BASELINE config 4: 5M Gaussians, 3840x2160, one view per GPU, 1.22 GB all-reduce
+  gpu_standin_baseline  a deliberately naive CUDA restatement of the published algorithm (baseline/standin: one
+                 thread per Gaussian, cub 64-bit radix sort, 256-thread tiles, 10 atomics per pair) on the same
+                 inputs on the same GPU -- NOT the reference, which is not obtainable offline
+  cpu_baseline   the CPU oracle (scalar C port, OpenMP) timed on this host on full views
+  --impl reference: the reference has no CPU path and its CUDA rasterizer is not obtainable offline (SURVEY.md
+  section 0); this arm times the oracle port of its algorithm on all host cores.
 """
 from __future__ import annotations
 
@@ -37,10 +46,19 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-P_GAUSS, WIDTH, HEIGHT, SH_DEG, SCALE_MED = 1_000_000, 1920, 1080, 3, 0.01
+CONFIGS = {
+    3: dict(P=1_000_000, W=1920, H=1080, sh=3, scale=0.01,
+            name="config3: synthetic 1M Gaussians, 1920x1080, SH deg 3, seed 0 (SURVEY 8d)"),
+    4: dict(P=5_000_000, W=3840, H=2160, sh=3, scale=0.005,
+            name="config4: synthetic 5M Gaussians, 3840x2160, SH deg 3, seed 0 (SURVEY 8d)"),
+}
+N_CAMERAS = 8
 METRIC = "views/sec fwd+bwd @ 1M Gaussians, 1080p, SH3"
 UNIT = "views/s"
-WORKLOAD = "config3: synthetic 1M Gaussians, 1920x1080, SH deg 3, seed 0 (SURVEY 8d)"
+
+
+def camera_yaw(k: int) -> float:
+    return (k - 3.5) * 2.0          # the 8 cameras of a batch
 
 
 def peaks():
@@ -51,14 +69,6 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
-
-
-def make_inputs(rank: int, device):
-    from scgaussian_b200 import synthetic as O   # the seed-0 generator, shared with the tests
-    cam = O.make_camera(WIDTH, HEIGHT, w2c=O.yaw_w2c((rank - 3.5) * 2.0 if int(os.environ.get("WORLD_SIZE", "1")) > 1 else 0.0))
-    sc = O.synth_scene(P_GAUSS, WIDTH, HEIGHT, sh_degree=SH_DEG, scale_median=SCALE_MED, seed=0)
-    grads = O.synth_upstream_grads(WIDTH, HEIGHT, seed=1)
-    return cam, sc, grads
 
 
 class ClockSampler:
@@ -101,38 +111,43 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_views_per_s(reps: int):
-    """Times the scalar C oracle (all host cores, OpenMP) on full views of the workload."""
+# ---------------------------------------------------------------------------------------------------------------
+# the reference arm / cpu_baseline: the CPU oracle port on all host cores
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_oracle_views_per_s(reps: int, cfg: dict):
+    """Times the scalar C oracle (all host cores, OpenMP) on full views of the workload, cycling the cameras."""
     from oracle import torch_oracle as O
     from oracle.c_oracle import COracle
-    cam = O.make_camera(WIDTH, HEIGHT)
-    sc = O.synth_scene(P_GAUSS, WIDTH, HEIGHT, sh_degree=SH_DEG, scale_median=SCALE_MED, seed=0)
-    gC, gD, gA = [g.numpy() for g in O.synth_upstream_grads(WIDTH, HEIGHT, seed=1)]
+    sc = O.synth_scene(cfg["P"], cfg["W"], cfg["H"], sh_degree=cfg["sh"], scale_median=cfg["scale"], seed=0)
+    gC, gD, gA = [g.numpy() for g in O.synth_upstream_grads(cfg["W"], cfg["H"], seed=1)]
+    cores = os.cpu_count() or 1
     co = COracle("f32")
-    kw = dict(means3D=sc["means3D"].numpy(), opacities=sc["opacities"].numpy(), W=WIDTH, H=HEIGHT,
-              tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=[0.0, 0.0, 0.0],
-              viewmatrix=cam["viewmatrix"].numpy(), projmatrix=cam["projmatrix"].numpy(),
-              campos=cam["campos"].numpy(), sh_degree=SH_DEG, shs=sc["shs"].numpy(),
-              scales=sc["scales"].numpy(), rotations=sc["rotations"].numpy())
+    co.set_threads(cores)          # torchrun exports OMP_NUM_THREADS=1: ask OpenMP for every core explicitly
     times = []
-    for _ in range(reps):
+    for i in range(reps):
+        cam = O.make_camera(cfg["W"], cfg["H"], w2c=O.yaw_w2c(camera_yaw(i % N_CAMERAS)))
+        kw = dict(means3D=sc["means3D"].numpy(), opacities=sc["opacities"].numpy(), W=cfg["W"], H=cfg["H"],
+                  tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=[0.0, 0.0, 0.0],
+                  viewmatrix=cam["viewmatrix"].numpy(), projmatrix=cam["projmatrix"].numpy(),
+                  campos=cam["campos"].numpy(), sh_degree=cfg["sh"], shs=sc["shs"].numpy(),
+                  scales=sc["scales"].numpy(), rotations=sc["rotations"].numpy())
         t0 = time.perf_counter()
         co.forward(**kw)
         co.backward(gC, gD, gA)
         times.append(time.perf_counter() - t0)
-    return times, os.cpu_count() or 1
+    return times, cores
 
 
-def run_reference_arm(args, rank):
-    """--impl reference: CPU oracle port of the reference's algorithm (the reference itself has no
-    CPU path and its CUDA package is not in /root/reference nor installable offline)."""
+def run_reference_arm(args, rank, cfg):
+    """--impl reference: CPU oracle port of the reference's algorithm (the reference itself has no CPU path and its
+    CUDA package is not in /root/reference nor installable offline).  Rank 0 alone runs it."""
     if rank != 0:
         return
     from oracle import c_oracle
     c_oracle.build()
     steps = max(1, args.steps)
     warm = max(0, min(args.warmup, 1))       # each step is ~seconds of CPU work: one warm-up is plenty
-    times, cores = cpu_oracle_views_per_s(warm + steps)
+    times, cores = cpu_oracle_views_per_s(warm + steps, cfg)
     times = times[warm:]
     ms = 1000.0 * sum(times) / len(times)
     v = 1000.0 / ms
@@ -140,37 +155,109 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference CUDA rasterizer unavailable offline; this is the CPU oracle port of its algorithm"},
+        "config": {"workload": cfg["name"], "note": "reference CUDA rasterizer unavailable offline; this is the CPU oracle port of its algorithm"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{steps} full view(s) fwd+bwd (1M Gaussians, 1080p), OpenMP over all cores"},
+                         "sample": f"{steps} full view(s) fwd+bwd ({cfg['P']} Gaussians, {cfg['W']}x{cfg['H']}), OpenMP over {cores} threads"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
+class Workload:
+    """Scene + the 8 cameras + upstream gradients + the flat gradient buffer of one config, resident on `dev`."""
+
+    def __init__(self, cfg, dev, rank, world):
+        from scgaussian_b200 import GaussianRasterizationSettings, synthetic as O
+        from scgaussian_b200.parallel import FlatGradBuffer
+        self.cfg, self.dev, self.rank, self.world = cfg, dev, rank, world
+        P, W, H = cfg["P"], cfg["W"], cfg["H"]
+        sc = O.synth_scene(P, W, H, sh_degree=cfg["sh"], scale_median=cfg["scale"], seed=0)
+        self.scene_cpu = sc
+        self.t = {k: v.to(dev).contiguous() for k, v in sc.items()}
+        self.grads = [g.to(dev).contiguous() for g in O.synth_upstream_grads(W, H, seed=1)]
+        self.cams_cpu = [O.make_camera(W, H, w2c=O.yaw_w2c(camera_yaw(k))) for k in range(N_CAMERAS)]
+        bg = torch.zeros(3, device=dev)
+        self.settings = [GaussianRasterizationSettings(
+            image_height=H, image_width=W, tanfovx=c["tanfovx"], tanfovy=c["tanfovy"], bg=bg, scale_modifier=1.0,
+            viewmatrix=c["viewmatrix"].to(dev), projmatrix=c["projmatrix"].to(dev), sh_degree=cfg["sh"],
+            campos=c["campos"].to(dev), prefiltered=False, debug=False) for c in self.cams_cpu]
+        self.args_in = (self.t["means3D"], self.t["opacities"], self.t["shs"], None, self.t["scales"], self.t["rotations"], None)
+        self.flat = FlatGradBuffer(P, sh_coeffs=(cfg["sh"] + 1) ** 2, device=dev)
+        self.out_views = self.flat.out_dict()
+        self.R_seen = []
+
+    def view(self, i):
+        """Forward + backward of camera i (mod 8) into the flat buffer; returns the ForwardState."""
+        from scgaussian_b200 import rasterizer as R
+        s = self.settings[i % N_CAMERAS]
+        color, radii, depth, alpha, state = R.rasterize_forward_raw(*self.args_in, s)
+        R.rasterize_backward_raw(state, *self.args_in, s, *self.grads, out=self.out_views)
+        return state
+
+    def step(self, i, collective=True):
+        state = self.view(self.rank + i)
+        if self.world > 1 and collective:
+            self.flat.all_reduce()               # THE collective of the path (statistics ride in the same buffer)
+        self.R_seen.append(int(state.num_rendered))     # host int already read by the forward: free
+        return state
+
+    def batch(self, i, views_per_rank):
+        """north_star's 8-view batch: this rank renders views_per_rank views, accumulating on the device; one all-reduce."""
+        from scgaussian_b200 import rasterizer as R
+        for v in range(views_per_rank):
+            s = self.settings[(self.rank * views_per_rank + v + i) % N_CAMERAS]
+            color, radii, depth, alpha, state = R.rasterize_forward_raw(*self.args_in, s)
+            R.rasterize_backward_raw(state, *self.args_in, s, *self.grads, out=self.out_views, accumulate=v > 0)
+        if self.world > 1:
+            self.flat.all_reduce()
+
+
+def timed(fn, n, barrier, dev, world):
+    """n calls of fn(i) bracketed by barrier + synchronize on both sides; CUDA events; max over ranks.  ms per call."""
+    import torch.distributed as dist
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(n):
+        fn(i)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / n
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4], help="workload of the headline numbers (default: BASELINE config 3)")
+    ap.add_argument("--config4", action="store_true", help="add the config4 entry at any N (default: only at N = 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train-step", action="store_true")
+    ap.add_argument("--no-standin", action="store_true")
+    ap.add_argument("--no-batch8", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = CONFIGS[args.config]
 
     if args.impl == "reference":
-        run_reference_arm(args, rank)
+        run_reference_arm(args, rank, cfg)
         return
 
     import torch.distributed as dist
-    from scgaussian_b200 import GaussianRasterizationSettings, GaussianRasterizer, _lib
+    from scgaussian_b200 import GaussianRasterizer, _lib
     from scgaussian_b200 import rasterizer as R
     from scgaussian_b200.losses import photometric_loss
-    from scgaussian_b200.parallel import FlatGradBuffer
 
     lib = _lib.load()                      # raises if libscgr.so is missing: no fallback
     assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU"
@@ -179,94 +266,111 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     W_ = max(3, args.warmup)
     K = max(1, args.steps)
-
-    cam, sc, grads = make_inputs(rank, dev)
-    t = {k: v.to(dev).contiguous() for k, v in sc.items()}
-    gC, gD, gA = [g.to(dev).contiguous() for g in grads]
-    bg = torch.zeros(3, device=dev)
-    s = GaussianRasterizationSettings(
-        image_height=HEIGHT, image_width=WIDTH, tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=bg,
-        scale_modifier=1.0, viewmatrix=cam["viewmatrix"].to(dev), projmatrix=cam["projmatrix"].to(dev),
-        sh_degree=SH_DEG, campos=cam["campos"].to(dev), prefiltered=False, debug=False)
-    args_in = (t["means3D"], t["opacities"], t["shs"], None, t["scales"], t["rotations"], None)
-    flat = FlatGradBuffer(P_GAUSS, sh_coeffs=(SH_DEG + 1) ** 2, device=dev)
-    out_views = flat.out_dict()
-
-    def step(collective=True):
-        color, radii, depth, alpha, state = R.rasterize_forward_raw(*args_in, s)
-        R.rasterize_backward_raw(state, *args_in, s, gC, gD, gA, out=out_views)
-        if world > 1 and collective:
-            flat.fill_stats(radii)
-            flat.all_reduce()               # THE collective of the path
-        return state
+    P_GAUSS, WIDTH, HEIGHT, SH_DEG = cfg["P"], cfg["W"], cfg["H"], cfg["sh"]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    wl = Workload(cfg, dev, rank, world)
+    flat = wl.flat
+
+    # ---------------- the collective's result, checked once outside the timed region ----------------
+    allreduce_check = None
+    if world > 1:
+        n = flat.flat.numel()
+        # small dyadic values: every partial sum is exact in fp32, so the result must equal the closed form BIT FOR BIT
+        # whatever order the switch / the ring adds in
+        base = ((torch.arange(n, device=dev, dtype=torch.int64) % 1021) - 510).to(torch.float32) / 64.0
+        flat.flat.copy_(base * (rank + 1))
+        mine = flat.flat.clone()
+        flat.all_reduce()
+        got = flat.flat.clone()
+        dist.all_reduce(mine, op=dist.ReduceOp.SUM)                       # NCCL on a private copy of the same data
+        want = base * (world * (world + 1) // 2)
+        err_nccl = float((got - mine).abs().max())
+        err_exact = float((got - want).abs().max())
+        ok = err_exact == 0.0 and err_nccl == 0.0
+        okt = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        allreduce_check = {"ok": bool(okt.item() == 1.0), "collective": flat.collective, "n_floats": n,
+                           "max_abs_diff_vs_nccl": err_nccl, "max_abs_diff_vs_closed_form": err_exact}
+        del base, mine, got, want
+        assert allreduce_check["ok"], allreduce_check
+
     # ---------------- device-resident throughput (value) ----------------
-    for _ in range(W_):
-        state = step()
+    for i in range(W_):
+        wl.step(i)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    wl.R_seen.clear()
     l0 = lib.scgr_kernel_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    R_seen = set()
-    for _ in range(K):
-        state = step()
-        R_seen.add(int(state.num_rendered))     # host int already read by the forward: free
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    nc0 = R.need_capacity_count
+    ms_step = timed(lambda i: wl.step(W_ + i), K, barrier, dev, world)
     launches = lib.scgr_kernel_launch_count() - l0
+    need_capacity_hits = R.need_capacity_count - nc0
     clocks = sampler.stop() if rank == 0 else None
-    tms = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_step = float(tms.item()) / K
     value = world * 1000.0 / ms_step
-    R_inst = state.num_rendered
+    R_list = list(wl.R_seen)
+    R_mean = sum(R_list) / len(R_list)
 
     # ---------------- per-kernel profile (separate short loop; not the reported value) ----------------
     kernels = {}
     if rank == 0:
         lib.scgr_profile_enable(1)
-        nprof = min(K, 5)
-        for _ in range(nprof):
-            step(collective=False)          # rank 0 only: must not enter a collective
+        nprof = N_CAMERAS
+        wl.R_seen.clear()
+        for i in range(nprof):
+            wl.step(i, collective=False)          # rank 0 only: must not enter a collective
         torch.cuda.synchronize()
+        R_prof = sum(wl.R_seen) / len(wl.R_seen)
         import ctypes as C
-        names = (C.c_char_p * 4096)()
-        msarr = (C.c_float * 4096)()
-        n = lib.scgr_profile_fetch(names, msarr, 4096)
+        names = (C.c_char_p * 8192)()
+        msarr = (C.c_float * 8192)()
+        n = lib.scgr_profile_fetch(names, msarr, 8192)
         lib.scgr_profile_enable(0)
         for i in range(max(n, 0)):
             kernels.setdefault(names[i].decode(), []).append(float(msarr[i]))
         kernels = {k: {"ms_per_step": sum(v) / nprof, "launches_per_step": len(v) / nprof,
                        "ms_per_launch": sum(v) / len(v)} for k, v in kernels.items()}
+        # Gaussians that receive any gradient in one view: what preprocess_backward actually has to read / compute
+        live_frac = float((flat.views["opacities"] != 0).float().mean())
+    if world > 1:
+        barrier()
+
+    # ---------------- the fixed 8-view batch (north_star): 8 / N views per rank, one all-reduce per batch ----------------
+    batch8 = None
+    if not args.no_batch8 and N_CAMERAS % world == 0:
+        vpr = N_CAMERAS // world
+        for i in range(2):
+            wl.batch(i, vpr)
+        nb = max(2, K // 4)
+        ms_b = timed(lambda i: wl.batch(i, vpr), nb, barrier, dev, world)
+        batch8 = {"views_per_batch": N_CAMERAS, "views_per_rank": vpr, "ms_per_batch": ms_b,
+                  "views_s": N_CAMERAS * 1000.0 / ms_b, "batches": nb, "scaling": "strong (fixed 8-view batch)",
+                  "what": "each rank renders 8/N views, scgr_backward accumulates on the device (ScgrGrads.accumulate), "
+                          "one all-reduce of the flat buffer per batch"}
 
     # ---------------- end-to-end through the public operator (e2e) ----------------
     e2e = None
     if not args.no_e2e:
         # per-step host inputs of a training step (reference train.py:135-147): the camera (view / projection
         # matrices, camera centre, background: 38 floats, ONE packed pinned buffer -> one H2D copy) and the
-        # ground-truth image (24.9 MB pinned -> device on a copy stream).  Two host/device buffer pairs: the
-        # uploads of step k+1 are issued while step k is still running (what a prefetching data loader does),
-        # and the loss of step k is read back (D2H into pinned memory + event) after step k+1 has been
-        # enqueued, so the GPU never waits for Python.  Every step's uploads and every step's loss read-back
-        # happen inside the timed region; nothing is cached across steps.
+        # ground-truth image (pinned -> device on a copy stream).  Two device buffer pairs: the uploads of step k+1
+        # are issued while step k is still running (what a prefetching data loader does), and the loss of step k
+        # is read back (D2H into pinned memory + event) after step k+1 has been enqueued, so the GPU never waits
+        # for Python.  Every step's uploads and every step's loss read-back happen inside the timed region;
+        # nothing is cached across steps; the camera changes every step.
         gt_host = [torch.rand(3, HEIGHT, WIDTH).pin_memory() for _ in range(2)]
-        cam_host = [torch.cat([cam["viewmatrix"].reshape(-1), cam["projmatrix"].reshape(-1), cam["campos"].reshape(-1),
-                               torch.zeros(3)]).contiguous().pin_memory() for _ in range(2)]
-        leaves = {k: t[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+        cam_host = [torch.cat([c["viewmatrix"].reshape(-1), c["projmatrix"].reshape(-1), c["campos"].reshape(-1),
+                               torch.zeros(3)]).contiguous().pin_memory() for c in wl.cams_cpu]
+        leaves = {k: wl.t[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
         h2d = gt_host[0].numel() * 4 + cam_host[0].numel() * 4
         loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
         loss_ready = [torch.cuda.Event() for _ in range(2)]
@@ -277,12 +381,13 @@ def main():
         cam_dev = [torch.empty(38, device=dev) for _ in range(2)]
         m2d = torch.zeros(P_GAUSS, 3, device=dev, requires_grad=True)   # never read by the op; only its .grad matters
         losses = []
+        s0 = wl.settings[0]
 
         def upload(k):
             b = k & 1
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(consumed[b])          # the step that last used this buffer pair is done with it
-                cam_dev[b].copy_(cam_host[b], non_blocking=True)
+                cam_dev[b].copy_(cam_host[(rank + k) % N_CAMERAS], non_blocking=True)
                 gt_dev[b].copy_(gt_host[b], non_blocking=True)
                 upload_done[b].record(copy_stream)
 
@@ -291,7 +396,7 @@ def main():
             cur = torch.cuda.current_stream(dev)
             cur.wait_event(upload_done[b])
             c = cam_dev[b]
-            s2 = s._replace(viewmatrix=c[0:16].view(4, 4), projmatrix=c[16:32].view(4, 4), campos=c[32:35], bg=c[35:38])
+            s2 = s0._replace(viewmatrix=c[0:16].view(4, 4), projmatrix=c[16:32].view(4, 4), campos=c[32:35], bg=c[35:38])
             color, radii, depth, alpha = GaussianRasterizer(s2)(
                 means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"], shs=leaves["shs"],
                 scales=leaves["scales"], rotations=leaves["rotations"])
@@ -299,13 +404,14 @@ def main():
             # plus terms that send gradient into the depth and alpha outputs (train.py:164-168 use both)
             loss = photometric_loss(color, gt_dev[b], 0.2) + (depth.sum() + alpha.sum()) * (0.01 / (HEIGHT * WIDTH))
             loss.backward()
-            m2d.grad = None
             if world > 1:
                 # one all-reduce for the public-API path too: pack the leaf gradients into the flat buffer
                 for name, v in leaves.items():
                     flat.views[name].copy_(v.grad.reshape(flat.views[name].shape))
+                flat.means2D.copy_(m2d.grad)
                 flat.fill_stats(radii)
                 flat.all_reduce()
+            m2d.grad = None
             consumed[b].record(cur)
             loss_host[b].copy_(loss.detach().reshape(1), non_blocking=True)   # D2H read of the step's result
             loss_ready[b].record(cur)
@@ -330,7 +436,8 @@ def main():
 
         e2e_run(W_)
         barrier()
-        ke = max(3, K // 2)
+        ke = max(N_CAMERAS, K // 2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
         e2e_run(ke)
@@ -343,10 +450,42 @@ def main():
         e2e = {"value": world * 1000.0 * ke / float(ms_e.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4, "steps": ke,
                "what": "GaussianRasterizer + the reference's L1 + 0.2 D-SSIM loss (fused) + depth/alpha means + autograd backward through the public operators; every step uploads "
-                       "its camera (38 floats, one packed copy) and ground-truth image from pinned host memory and reads its loss "
+                       "its camera (38 floats, one packed copy; a different camera every step) and ground-truth image from pinned host memory and reads its loss "
                        "back; uploads of step k+1 are prefetched on a copy stream while step k runs and the loss of step k is "
                        "read (pinned + event) after step k+1 is enqueued -- all inside the timed region; Gaussian parameters "
                        "stay resident (they are model state, reference train.py)"}
+        del leaves, gt_dev, m2d
+        torch.cuda.empty_cache()
+
+    # ---------------- BASELINE config 4: 5M Gaussians, 3840x2160, one view per GPU, 1.22 GB all-reduce ----------------
+    config4 = None
+    if (world == N_CAMERAS or args.config4) and args.config != 4:
+        try:
+            c4 = CONFIGS[4]
+            del wl.t, wl.args_in, wl.out_views
+            w3_flat = wl.flat
+            wl.flat = None
+            del flat, w3_flat
+            torch.cuda.empty_cache()
+            w4 = Workload(c4, dev, rank, world)
+            for i in range(3):
+                w4.step(i)
+            w4.R_seen.clear()
+            k4 = max(4, K // 3)
+            ms4 = timed(lambda i: w4.step(3 + i), k4, barrier, dev, world)
+            ar_ms = None
+            if world > 1:
+                ar_ms = timed(lambda i: w4.flat.all_reduce(), 5, barrier, dev, world)
+            config4 = {"workload": c4["name"], "views_per_step": world, "ms_per_step": ms4, "views_s": world * 1000.0 / ms4,
+                       "steps": k4, "num_rendered_R_this_rank": w4.R_seen, "allreduce_ms": ar_ms,
+                       "grad_allreduce_bytes": w4.flat.nbytes() if world > 1 else 0, "collective": w4.flat.collective if world > 1 else "none (1 GPU)",
+                       "cameras": "rank r renders camera (r + step) % 8, yaw (k - 3.5) * 2 deg"}
+            del w4
+            torch.cuda.empty_cache()
+        except Exception as e:             # pragma: no cover  (an extra entry must never take the metric down)
+            config4 = {"error": repr(e)[:300]}
+        if world > 1:
+            barrier()
 
     if rank != 0:
         if world > 1:
@@ -358,14 +497,14 @@ def main():
     # size -- raw parameters -> activations + assembly -> operator -> L1 + D-SSIM -> backward -> statistics -> Adam --
     # with the fused passes of this repo and with the reference's chain of torch ops, same rasterizer and loss kernels.
     train_step = None
-    if world == 1 and not args.no_train_step:
+    if world == 1 and not args.no_train_step and args.config == 3:
         try:
             import importlib.util
             spec = importlib.util.spec_from_file_location("scgr_train_step_time", os.path.join(ROOT, "tools", "train_step_time.py"))
             tst = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(tst)
             torch.cuda.empty_cache()
-            train_step = tst.measure(sc, cam, dev, WIDTH, HEIGHT, steps=10, warm=3)
+            train_step = tst.measure(wl.scene_cpu, wl.cams_cpu[3], dev, WIDTH, HEIGHT, steps=10, warm=3)
             pk, _ = peaks()
             ku = train_step.get("fused", {}).get("kernel_us_per_step", {})
             n_ray, n_bg = train_step["n_ray"], train_step["n_bg"]
@@ -375,17 +514,30 @@ def main():
         except Exception as e:             # pragma: no cover  (never let the extra entry take the metric down)
             train_step = {"error": repr(e)[:300]}
 
+    # ---------------- the naive-CUDA stand-in on the same inputs, same GPU (NOT the reference) ----------------
+    standin = None
+    if world == 1 and not args.no_standin and args.config == 3:
+        try:
+            from baseline.standin import standin as SB
+            torch.cuda.empty_cache()
+            standin = SB.measure(wl.scene_cpu, wl.cams_cpu, [g.cpu() for g in wl.grads], WIDTH, HEIGHT, SH_DEG, dev,
+                                 steps=max(4, K // 3), warm=2)
+            standin["speedup_of_this_repo"] = standin["ms_per_step"] / ms_step
+        except Exception as e:             # pragma: no cover
+            standin = {"error": repr(e)[:300]}
+
     # ---------------- roofline of the dominant kernel ----------------
     peak, peak_src = peaks()
     N = WIDTH * HEIGHT
     Tn = ((WIDTH + 15) // 16) * ((HEIGHT + 15) // 16)
-    algo_bytes = {   # SURVEY.md section 8d, per launch (one view)
+    algo_bytes = {   # SURVEY.md section 8d, per launch (one view), at the mean R of the profiled cameras
         "preprocess_forward": 311 * P_GAUSS,
-        "render_forward": 44 * R_inst + 8 * Tn + 24 * N,
-        "render_backward": 84 * R_inst + 8 * Tn + 28 * N,
+        "render_forward": 44 * R_prof + 8 * Tn + 24 * N,
+        "render_backward": 84 * R_prof + 8 * Tn + 28 * N,
         "preprocess_backward": 579 * P_GAUSS,
     }
     roof = None
+    roof_issue = None
     if kernels:
         dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
         share = kernels[dom]["ms_per_step"] / max(sum(v["ms_per_step"] for v in kernels.values()), 1e-9)
@@ -401,32 +553,73 @@ def main():
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": algo_bytes[dom],
                     "share_of_step": share,
-                    "note": "render kernels are SM-issue/MUFU/atomic bound, not HBM bound (SURVEY 8d); HBM fraction reported as BASELINE.json requires"}
+                    "note": "render kernels are SM-issue bound, not HBM bound (SURVEY 8d; see roofline_issue); HBM fraction reported as BASELINE.json requires"}
         for k, v in kernels.items():
             if k in algo_bytes:
                 v["hbm_gbs_algorithmic"] = algo_bytes[k] / (v["ms_per_launch"] * 1e-3) / 1e9
                 v["hbm_frac"] = v["hbm_gbs_algorithmic"] / peak
+        if "preprocess_backward" in kernels:
+            # SURVEY's 579 B/Gaussian assumes every Gaussian is processed; the kernel skips the ones render-backward left
+            # without gradient (they are read as 48 B of accumulator and written as 232 B of zeros): the honest byte
+            # count is the live-weighted one, and the nominal fraction (which can exceed 1) is labelled as such
+            v = kernels["preprocess_backward"]
+            v["hbm_frac_nominal_579B_per_gaussian"] = v.pop("hbm_frac")
+            live_bytes = P_GAUSS * (live_frac * 579 + (1.0 - live_frac) * (48 + 232 + 4))
+            v["live_fraction"] = live_frac
+            v["hbm_gbs_algorithmic"] = live_bytes / (v["ms_per_launch"] * 1e-3) / 1e9
+            v["hbm_frac"] = v["hbm_gbs_algorithmic"] / peak
+        # ---- the bound that actually applies to the render kernels: SM issue slots ----
+        # warp instructions per launch come from an ncu capture of this same command (profiles/r02_issue.json,
+        # smsp__inst_executed.sum, averaged over the 8 cameras); durations are the live CUDA-event ones above
+        f_clk = (clocks or {}).get("sm_mhz") or 1965.0
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        issue_peak = sm_count * 4 * f_clk * 1e6            # warp instructions / s: one per scheduler per cycle
+        lane_peak = sm_count * 128 * f_clk * 1e6           # 148 SMs x 128 lanes x f_clk
+        counts = {}
+        ip = os.path.join(ROOT, "profiles", "r02_issue.json")
+        if os.path.exists(ip):
+            try:
+                counts = json.load(open(ip))
+            except Exception:
+                counts = {}
+        roof_issue = {"peak_warp_instr_per_s": issue_peak, "sm_clock_mhz_used": f_clk, "sm_count": sm_count,
+                      "source_of_instruction_counts": "profiles/r02_issue.json (ncu smsp__inst_executed.sum per launch)" if counts else None}
+        for kname in ("render_forward", "render_backward"):
+            if kname not in kernels:
+                continue
+            t_s = kernels[kname]["ms_per_launch"] * 1e-3
+            pair_evals = 256.0 * R_prof                    # every pixel of a tile against every entry of its list (A.8)
+            ent = {"ms_per_launch": kernels[kname]["ms_per_launch"], "pair_evals_per_s": pair_evals / t_s,
+                   "lane_cycles_per_pair_eval": lane_peak * t_s / pair_evals}
+            wi = (counts.get(kname) or {}).get("warp_instr_per_launch")
+            if wi:
+                ent.update({"warp_instr_per_launch": wi, "warp_instr_per_s": wi / t_s, "frac_of_issue_peak": wi / t_s / issue_peak,
+                            "warp_instr_per_list_entry": wi / R_prof})
+            roof_issue[kname] = ent
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         from oracle import c_oracle
         c_oracle.build()
-        times, cores = cpu_oracle_views_per_s(3)
+        times, cores = cpu_oracle_views_per_s(3, cfg)
         cpu = {"value": 1.0 / (sum(times[1:]) / len(times[1:])), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "2 full views fwd+bwd (1M Gaussians, 1080p) after 1 warm-up, scalar C oracle, OpenMP over all cores"}
+               "sample": f"2 full views fwd+bwd ({P_GAUSS} Gaussians, {WIDTH}x{HEIGHT}) after 1 warm-up, scalar C oracle, OpenMP over {cores} threads"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "P": P_GAUSS, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEG,
-                   "num_rendered_R": R_inst, "num_rendered_distinct_over_steps": len(R_seen),
+        "config": {"workload": cfg["name"], "P": P_GAUSS, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEG,
+                   "cameras": f"{N_CAMERAS} yawed cameras ((k - 3.5) * 2 deg), rank r renders camera (r + step) % {N_CAMERAS}: a different view every step",
+                   "num_rendered_R_mean": R_mean, "num_rendered_R_min": min(R_list), "num_rendered_R_max": max(R_list),
+                   "num_rendered_distinct_over_steps": len(set(R_list)), "need_capacity_hits": int(need_capacity_hits),
                    "views_per_step": world, "parallelism": f"view-sharded dp{world}",
-                   "collective": f"1 all-reduce of the flat gradient buffer per step ({flat.collective})" if world > 1 else "none (1 GPU)",
-                   "grad_allreduce_bytes": flat.nbytes() if world > 1 else 0,
-                   "l2": "no explicit flush: one step streams >1 GB (inputs 236 MB + gradients 232 MB + scratch) through the 126 MB L2"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,
-        "cpu_baseline": cpu, "train_step": train_step,
+                   "collective": f"1 all-reduce of the flat gradient buffer per step ({wl.flat.collective if wl.flat is not None else 'nvls/nccl'})" if world > 1 else "none (1 GPU)",
+                   "grad_allreduce_bytes": (P_GAUSS * 61 * 4) if world > 1 else 0,
+                   "l2": "no explicit flush: one step streams >1 GB (inputs 236 MB + gradients 244 MB + scratch) through the 126 MB L2, and the camera changes every step"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "roofline_issue": roof_issue,
+        "kernels": kernels, "batch8": batch8, "config4": config4, "allreduce_check": allreduce_check,
+        "gpu_standin_baseline": standin, "cpu_baseline": cpu, "train_step": train_step,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -54,6 +54,10 @@ class COracle:
         self._state = None
         self._keep = None
 
+    def set_threads(self, n: int) -> int:
+        """OpenMP threads of the following calls (torchrun exports OMP_NUM_THREADS=1); returns the count in effect."""
+        return int(self.lib.scgo_set_threads(int(n)))
+
     def _arr(self, a, shape=None):
         if a is None:
             return None

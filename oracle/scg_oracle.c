@@ -187,6 +187,16 @@ void scgo_free(scgo_state *s) {
 }
 
 int scgo_real_size(void) { return (int)sizeof(REAL); }
+/* number of OpenMP threads of the following calls (a launcher may have exported OMP_NUM_THREADS=1) */
+int scgo_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 int64_t scgo_num_rendered(const scgo_state *s) { return s->R; }
 const uint32_t *scgo_point_list(const scgo_state *s) { return s->point_list; }
 const int64_t *scgo_ranges(const scgo_state *s) { return s->ranges; }

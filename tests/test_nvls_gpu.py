@@ -1,0 +1,88 @@
+"""The path's single collective on real GPUs (needs >= 2 of them: `gpurun --gpus 2|4|8`; skipped on a 1-GPU box).
+
+libscgr's own two-shot NVSwitch all-reduce (scgaussian_b200/csrc/collective.cu: multimem.ld_reduce + multimem.st over a
+symmetric-memory multicast mapping) must give, on every rank, the sum of the per-rank buffers: it is compared BIT FOR
+BIT with the closed form (dyadic values: every partial sum is exact in fp32, so any summation order gives the same
+bits) and with ncclAllReduce on a private copy of the same data; then once more on random data against NCCL within
+fp32 reassociation.  The buffer is the FlatGradBuffer the backward kernels write into, at BASELINE config 3's size."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, P, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    res = {"rank": rank}
+    try:
+        from scgaussian_b200.parallel import FlatGradBuffer
+        try:
+            buf = FlatGradBuffer(P, sh_coeffs=16, device=dev, symmetric=True)      # force the NVLS path at any world size
+        except Exception as e:
+            res["skip"] = f"symmetric memory / multicast unavailable: {e!r}"[:300]
+            torch.save(res, os.path.join(out_dir, f"r{rank}.pt"))
+            return
+        res["collective"] = buf.collective
+        n = buf.flat.numel()
+        base = ((torch.arange(n, device=dev, dtype=torch.int64) % 1021) - 510).to(torch.float32) / 64.0
+        for rep in range(3):                                   # back-to-back calls reuse the barriers' channels
+            buf.flat.copy_(base * (rank + 1 + rep))
+            mine = buf.flat.clone()
+            buf.all_reduce()
+            dist.all_reduce(mine)
+            want = base * sum(r + 1 + rep for r in range(world))
+            res[f"exact_{rep}"] = bool(torch.equal(buf.flat, want))
+            res[f"equals_nccl_{rep}"] = bool(torch.equal(buf.flat, mine))
+        g = torch.Generator(device=dev).manual_seed(100 + rank)
+        buf.flat.copy_(torch.randn(n, device=dev, generator=g))
+        mine = buf.flat.clone()
+        buf.all_reduce()
+        dist.all_reduce(mine)
+        res["random_max_abs_diff_vs_nccl"] = float((buf.flat - mine).abs().max())
+        res["random_scale"] = float(mine.abs().max())
+        # replicas must be identical on every rank (one reduction per element, then a broadcast)
+        digest = buf.flat.double().sum().reshape(1)
+        lo, hi = digest.clone(), digest.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        res["replicas_identical"] = bool(lo.item() == hi.item())
+        torch.cuda.synchronize()
+    finally:
+        torch.save(res, os.path.join(out_dir, f"r{rank}.pt"))
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("P", [1_000_000, 1001])
+def test_nvls_allreduce_equals_sum_of_rank_buffers(tmp_path, P):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs on one box (gpurun --gpus N)")
+    import torch.multiprocessing as mp
+    world = min(8, torch.cuda.device_count())
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(world, port, P, str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(tmp_path / f"r{r}.pt") for r in range(world)]
+    if any("skip" in r for r in res):
+        pytest.skip(next(r["skip"] for r in res if "skip" in r))
+    for r in res:
+        assert r["collective"].startswith("nvls"), r
+        for rep in range(3):
+            assert r[f"exact_{rep}"] and r[f"equals_nccl_{rep}"], r
+        assert r["random_max_abs_diff_vs_nccl"] <= 1e-5 * r["random_scale"], r
+        assert r["replicas_identical"], r
+    try:
+        import json
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(root, "gpurun_out", "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps({"test": "nvls_allreduce", "world": world, "P": P, "ranks": res}) + "\n")
+    except Exception:
+        pass

@@ -1,4 +1,7 @@
-"""The reference's own call site against the drop-in package (build container only: needs /root/reference).
+"""The reference's own call site against the drop-in package.  Needs the reference's Python files: /root/reference in
+the build container, or the staged copy under oracle/_ref/reference that __graft_entry__.build() makes there (git-
+ignored, never committed, travels to the GPU box with the snapshot) -- so the `-m gpu` tests at the bottom run the
+reference's UNMODIFIED gaussian_renderer.render() and GaussianModel accessors on a B200 against libscgr.so.
 
 `gaussian_renderer/__init__.py` is imported UNMODIFIED with this repo on sys.path, so its line 15
 (`from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer`) resolves to
@@ -19,10 +22,12 @@ import types
 import pytest
 import torch
 
-REF = "/root/reference"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = next((d for d in (os.environ.get("SCGR_REFERENCE_DIR", ""), "/root/reference",
+                        os.path.join(ROOT, "oracle", "_ref", "reference"))
+            if d and os.path.isdir(os.path.join(d, "gaussian_renderer"))), "/root/reference")
 pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "gaussian_renderer")),
-                                reason="the reference tree exists in the build container only")
+                                reason="the reference's Python files are neither at /root/reference nor staged under oracle/_ref")
 
 _STUB_ROOTS = ("plyfile", "simple_knn", "pytorch3d", "skimage", "imageio", "matplotlib", "dkm", "lpips")
 
@@ -338,3 +343,104 @@ def test_densification_postfix_mirror_matches_the_reference_method(densify_on_ho
     ref.prune_points(mask.clone())
     densify.prune_points(ours, mask.clone())
     _same_model(ours, ref, densify)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# On the GPU: the reference's own render() + GaussianModel accessors, unmodified, against the real kernels
+# ---------------------------------------------------------------------------------------------------------------
+def _reference_model(G, case, n_ray, dev, sh_degree=3):
+    """A reference GaussianModel (scene/gaussian_model.py) holding `case` as a hybrid of n_ray ray-based Gaussians
+    (position = rayo + rayd * zval, :124) and free ones (bg_*), raw parameters such that the reference's OWN activations
+    (:105-152) reproduce the case's scales / rotations / opacities."""
+    from scene.gaussian_model import GaussianModel
+    pc = GaussianModel(sh_degree)
+    pc.active_sh_degree = case["sh_degree"]
+    m = case["means3D"]
+    g = torch.Generator().manual_seed(9)
+    rayo = torch.randn(n_ray, 3, generator=g) * 0.1
+    d = m[:n_ray] - rayo
+    z = d.norm(dim=1, keepdim=True)
+    par = lambda t: torch.nn.Parameter(t.clone().to(dev).contiguous())       # noqa: E731
+    pc._rayo, pc._rayd, pc._zval = rayo.to(dev), (d / z).to(dev), par(z)
+    sc, ro, op, sh = case["scales"].log(), case["rotations"] * 1.7, torch.logit(case["opacities"]), case["shs"]
+    pc._scaling, pc._rotation, pc._opacity = par(sc[:n_ray]), par(ro[:n_ray]), par(op[:n_ray])
+    pc._features_dc, pc._features_rest = par(sh[:n_ray, :1]), par(sh[:n_ray, 1:])
+    if n_ray < case["P"]:
+        pc.bg_xyz = par(m[n_ray:])
+        pc.bg_scaling, pc.bg_rotation, pc.bg_opacity = par(sc[n_ray:]), par(ro[n_ray:]), par(op[n_ray:])
+        pc.bg_features_dc, pc.bg_features_rest = par(sh[n_ray:, :1]), par(sh[n_ray:, 1:])
+    return pc
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["default", "convert_SHs_python", "compute_cov3D_python"])
+def test_reference_render_runs_on_the_gpu_against_libscgr(reference_renderer, variant):
+    """SURVEY.md section 8a rows a1 + a2: reference gaussian_renderer/__init__.py:20-118 and the GaussianModel accessors
+    of scene/gaussian_model.py:105-152, imported unmodified, executed on the GPU with `diff_gaussian_rasterization`
+    resolving to this repo -- images and every parameter gradient against the CPU oracle fed with the activations the
+    reference computed, `viewspace_points.grad` against the oracle's NDC-scaled screen gradient, and the two
+    reference-owned switches (`convert_SHs_python`, `compute_cov3D_python`) against the default path."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import math
+    import numpy as np
+    from oracle import torch_oracle as O
+    from tests import util
+    G = reference_renderer
+    dev = torch.device("cuda:0")
+    P, W, H = 4000, 200, 152
+    case = util.make_case(P, W, H, sh_degree=3, scale_median=0.05, bg=(0.1, 0.2, 0.3), w2c=O.yaw_w2c(6.0), seed=11)
+    n_ray = P if variant == "compute_cov3D_python" else 2500     # (the reference's get_covariance ignores the bg set, :152)
+    pc = _reference_model(G, case, n_ray, dev)
+
+    class Cam:                                   # what reference scene/cameras.py:54-63 exposes
+        FoVx, FoVy = 2 * math.atan(case["tanfovx"]), 2 * math.atan(case["tanfovy"])
+        image_height, image_width = H, W
+        world_view_transform = case["viewmatrix"].to(dev)
+        full_proj_transform = case["projmatrix"].to(dev)
+        camera_center = case["campos"].to(dev)
+
+    class Pipe:
+        convert_SHs_python = variant == "convert_SHs_python"
+        compute_cov3D_python = variant == "compute_cov3D_python"
+        debug = False
+
+    out = G.render(Cam(), pc, Pipe(), case["bg"].to(dev))
+    assert set(out) >= {"render", "rendered_depth", "rendered_alpha", "viewspace_points", "visibility_filter", "radii"}
+    gC, gD, gA = O.synth_upstream_grads(W, H)
+    loss = (out["render"] * gC.to(dev)).sum() + (out["rendered_depth"] * gD.to(dev)).sum() + (out["rendered_alpha"] * gA.to(dev)).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    # the oracle sees what the reference's accessors produced
+    with torch.no_grad():
+        act = dict(case, means3D=pc.get_xyz.cpu(), scales=pc.get_scaling.cpu(), rotations=pc.get_rotation.cpu(),
+                   opacities=pc.get_opacity.cpu(), shs=pc.get_features.cpu())
+    co, (c2, r2, d2, a2), g2 = util.run_c_oracle(act, "f32", grads=(gC, gD, gA))
+    flips = util.flip_sets(co)
+    assert out["radii"].dtype == torch.int32 and out["render"].shape == (3, H, W)
+    util.assert_radii_match("radii", out["radii"].cpu().numpy(), r2, flips)
+    assert torch.equal(out["visibility_filter"], out["radii"] > 0)
+    util.assert_image_close("render", out["render"].detach().cpu().numpy(), c2, flips)
+    util.assert_image_close("rendered_depth", out["rendered_depth"].detach().cpu().numpy(), d2, flips)
+    util.assert_image_close("rendered_alpha", out["rendered_alpha"].detach().cpu().numpy(), a2, flips)
+    # screenspace_points.grad: the hook of reference lines 28-32, in NDC units, z = 0 (SURVEY a17)
+    vg = out["viewspace_points"].grad
+    assert vg is not None and float(vg[:, 2].abs().max()) == 0.0
+    util.assert_grad_close("viewspace_points.grad", vg.cpu().numpy(), g2["means2D"], flips)
+    # parameter gradients through the reference's own activations: chain the oracle's gradients through the same torch ops
+    leaves = {k: act[k].clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+    ref = _reference_model(G, case, n_ray, torch.device("cpu"))
+    pairs = [(ref.get_xyz, "means3D"), (ref.get_scaling, "scales"), (ref.get_rotation, "rotations"),
+             (ref.get_opacity, "opacities"), (ref.get_features, "shs")]
+    sur = sum((t * torch.from_numpy(np.asarray(g2[k], dtype=np.float32)).reshape(t.shape)).sum() for t, k in pairs)
+    sur.backward()
+    del leaves
+    names = ["_zval", "_scaling", "_rotation", "_opacity", "_features_dc", "_features_rest"]
+    if n_ray < P:
+        names += ["bg_xyz", "bg_scaling", "bg_rotation", "bg_opacity", "bg_features_dc", "bg_features_rest"]
+    for n in names:
+        got, want = getattr(pc, n).grad, getattr(ref, n).grad
+        assert got is not None and want is not None, n
+        sl = slice(n_ray, None) if n.startswith("bg_") else slice(0, n_ray)
+        part = dict(flips, **{k: flips[k][sl] for k in ("gauss_flag", "gauss_margin", "gauss_own")})
+        util.assert_grad_close(n, got.cpu().numpy(), want.numpy(), part)

@@ -85,6 +85,11 @@ def main() -> int:
         s = s.replace('device="cuda"', 'device="cpu"').replace('dev = "cuda"', 'dev = "cpu"').replace(".cuda()", "")
         s = s.replace("torch.cuda.synchronize()", "None")
         open(f, "w").write(s)
+    # the staged copy of the reference's Python files (oracle/_ref/reference, made by __graft_entry__.build()): CPU too
+    for f in glob.glob(os.path.join(work, "oracle", "_ref", "reference", "**", "*.py"), recursive=True):
+        s = open(f).read()
+        open(f, "w").write(s.replace('device="cuda"', 'device="cpu"').replace("device='cuda'", "device='cpu'").replace(".cuda()", ""))
+    os.environ["SCGR_REFERENCE_DIR"] = os.path.join(work, "oracle", "_ref", "reference")
     p = os.path.join(work, "tests", "conftest.py")
     s = open(p).read().replace("        b.build_library()", "        pass      # pre-flight: the emulated library stands in")
     open(p, "w").write(s)
