@@ -66,6 +66,50 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
+// ---- packed fp32 (sm_100a FFMA2 / FMUL2 / FADD2): ONE instruction works on the two floats of a 64-bit register pair.
+// A lane owns the same pixel position in the two 8-pixel-wide slot columns of a tile row, so everything the blend
+// does per pixel is done for the pair at once; per-lane IEEE semantics are those of fmaf / * / + (round to nearest).
+__device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
+    float2 d;
+    asm("{\n\t"
+        ".reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "mov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t"
+        "}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(const float2 a, const float2 b) {
+    float2 d;
+    asm("{\n\t"
+        ".reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t"
+        "}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
+    float2 d;
+    asm("{\n\t"
+        ".reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t"
+        "}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+
 // ---- TMA (cp.async.bulk) + mbarrier plumbing: every lane pulls the 48-byte record of its
 // Gaussian into the warp's staging buffer with one bulk-async copy; completion is a transaction
 // count on an mbarrier, so no register ever holds data in flight. ----
@@ -144,6 +188,19 @@ __device__ __forceinline__ uint32_t slot_mask(const Rec& r, const float X0, cons
         if (mp >= c.thr) m |= 1u << i;
     }
     return m & live_slots;
+}
+
+// Per-Gaussian values of a staged record, laid out for the packed blend: every scalar the two slot columns share
+// appears twice, so that one 64-bit half of an LDS.128 is a ready-made {s, s} operand of FFMA2 / FMUL2.
+//   d0 = {x, x, cA, cA}   d1 = {cB, cB, cC, cC}   d2 = {opacity, opacity, depth, depth}   d3 = {r, r, g, g}   d4 = {b, b, y, y}
+constexpr int DUP_F4 = 5;
+__device__ __forceinline__ void stage_dup(float4* s_dup, const int lane, const Rec& c) {
+    float4* d = s_dup + lane * DUP_F4;      // 80-byte stride: conflict-free STS.128
+    d[0] = make_float4(c.q0.x, c.q0.x, c.q0.z, c.q0.z);
+    d[1] = make_float4(c.q0.w, c.q0.w, c.q1.x, c.q1.x);
+    d[2] = make_float4(c.q1.y, c.q1.y, c.q1.z, c.q1.z);
+    d[3] = make_float4(c.q2.x, c.q2.x, c.q2.y, c.q2.y);
+    d[4] = make_float4(c.q2.z, c.q2.z, c.q0.y, c.q0.y);
 }
 
 // Work items of a render launch, in dispatch order: tiles [0, n8) whole, tiles [n8, n8 + n4) as two
@@ -242,11 +299,13 @@ forward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[
             const float4 q2 = srec[j * 3 + 2];
             // power(dx, dy) = cA dx^2 + dy (cB dx + cC dy): the dx-only terms are shared by the slots of
             // a column and hoisted, leaving 2 FFMA per pixel
-            const float dxa = q0.x - pxf, dxb = dxa - 8.f;
+            // (dx of the second column is x - (px + 8), dy of row r is dy of row r - 1 minus 4: the same roundings as the
+            // packed kernels below, so that forward and backward see bit-identical exponents)
+            const float dxa = q0.x - pxf, dxb = q0.x - (pxf + 8.f);
             const float ax[2] = {(q0.z * dxa) * dxa, (q0.z * dxb) * dxb};
             const float bx[2] = {q0.w * dxa, q0.w * dxb};
-            const float dy0 = q0.y - pyf;
-            const float dys[4] = {dy0, dy0 - 4.f, dy0 - 8.f, dy0 - 12.f};
+            const float dy0 = q0.y - pyf, dy1 = dy0 - 4.f, dy2_ = dy1 - 4.f;
+            const float dys[4] = {dy0, dy1, dy2_, dy2_ - 4.f};
             const uint32_t idx = (uint32_t)(base + j + 1);
             auto blend = [&](const int i) {
                 const float dy = dys[i >> 1];
@@ -314,14 +373,135 @@ forward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[
     }
 }
 
-template <int MINB, bool TMA>
+// The same region walk with the blend done for the lane's two pixels of a tile row at once (packed fp32: FFMA2 /
+// FMUL2 on register pairs, see fma2 above).  Per pixel the operations and their rounding are exactly those of
+// forward_region: the two variants produce bit-identical images.
+template <int SPW>
+__device__ __forceinline__ void
+forward_region_packed(const int tile, const int tiles_x, const int k0, float4* s_dup,
+                      const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                      const Record* __restrict__ rec, const int W, const int H, const float* __restrict__ bg,
+                      float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha,
+                      uint32_t* __restrict__ n_contrib, float* __restrict__ final_T, uint4* __restrict__ tile_todo) {
+    constexpr int NR = SPW / 2;
+    const int lane = threadIdx.x & 31;
+    const int lx = lane & 7, ly = lane >> 3;
+    const int X0 = (tile % tiles_x) * TILE, Yr = (tile / tiles_x) * TILE + ((k0 >> 1) << 2);
+    const uint2 range = ranges[tile];
+    const int total = range.y > range.x ? (int)(range.y - range.x) : 0;   // empty tiles hold (0xffffffff, 0)
+    // (sign convention of Tt as in forward_region: a finished pixel keeps its final transmittance negated)
+    float2 Tt2[NR], Cr2[NR], Cg2[NR], Cb2[NR], Dd2[NR];
+    uint32_t last[SPW];
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+        Cr2[r] = Cg2[r] = Cb2[r] = Dd2[r] = make_float2(0.f, 0.f);
+        last[2 * r] = last[2 * r + 1] = 0u;
+        const int py = Yr + (r << 2) + ly;
+        Tt2[r] = make_float2((X0 + lx >= W || py >= H) ? -1.f : 1.f, (X0 + 8 + lx >= W || py >= H) ? -1.f : 1.f);
+    }
+    const float2 npx2 = make_float2(-(float)(X0 + lx), -(float)(X0 + lx + 8));
+    const float2 npy2 = make_float2(-(float)(Yr + ly), -(float)(Yr + ly));
+    const float2 kNegOne2 = make_float2(-1.f, -1.f), kNegFour2 = make_float2(-4.f, -4.f);
+    Rec nxt;
+    nxt.q0 = nxt.q1 = nxt.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nbatch = (total + 31) >> 5;
+    if (lane < total) nxt = load_rec(rec, point_list[range.x + lane]);
+    for (int b = 0; b < nbatch; b++) {
+        const int base = 32 * b;
+        uint32_t live = 0u;
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            if (__any_sync(0xffffffffu, Tt2[r].x > 0.f)) live |= 1u << (2 * r);
+            if (__any_sync(0xffffffffu, Tt2[r].y > 0.f)) live |= 2u << (2 * r);
+        }
+        if (live == 0u) break;
+        const int cnt = min(32, total - base);
+        const Rec cur = nxt;
+        __syncwarp();
+        stage_dup(s_dup, lane, cur);
+        __syncwarp();
+        if (base + 32 + lane < total) nxt = load_rec(rec, point_list[range.x + base + 32 + lane]);
+        const uint32_t mymask = lane < cnt ? slot_mask<SPW>(cur, (float)X0, (float)Yr, live) : 0u;
+        for (int j = 0; j < cnt; j++) {
+            const uint32_t mj = __shfl_sync(0xffffffffu, mymask, j);
+            if (mj == 0u) continue;
+            const float4* const dj = s_dup + j * DUP_F4;
+            const float4 d0 = dj[0], d1 = dj[1], d2 = dj[2], d3 = dj[3], d4 = dj[4];
+            const float2 dx2 = add2(make_float2(d0.x, d0.y), npx2);
+            const float2 ax2 = mul2(mul2(make_float2(d0.z, d0.w), dx2), dx2);
+            const float2 bx2 = mul2(make_float2(d1.x, d1.y), dx2);
+            const float2 cC2 = make_float2(d1.z, d1.w), op2 = make_float2(d2.x, d2.y), dep2 = make_float2(d2.z, d2.w);
+            const float2 qr2 = make_float2(d3.x, d3.y), qg2 = make_float2(d3.z, d3.w), qb2 = make_float2(d4.x, d4.y);
+            float2 dy2 = add2(make_float2(d4.z, d4.w), npy2);
+            const uint32_t idx = (uint32_t)(base + j + 1);
+            auto blend_row = [&](const int r) {
+                const float2 power = fma2(dy2, fma2(cC2, dy2, bx2), ax2);
+                const float2 oe = mul2(op2, make_float2(ex2(power.x), ex2(power.y)));
+                const float2 araw = make_float2(fminf(ALPHA_MAX, oe.x), fminf(ALPHA_MAX, oe.y));
+                const float2 w0 = mul2(araw, Tt2[r]);
+                const float2 test_T = fma2(w0, kNegOne2, Tt2[r]);      // T (1 - alpha); negative for a finished pixel
+                // the reference's skip chain (A.8), per pixel: a slot the Gaussian cannot reach fails `cand` by itself
+                const bool cand0 = araw.x >= ALPHA_MIN && power.x <= 0.f, cand1 = araw.y >= ALPHA_MIN && power.y <= 0.f;
+                const bool go0 = cand0 && test_T.x >= T_EPS, go1 = cand1 && test_T.y >= T_EPS;
+                const bool sat0 = cand0 && test_T.x < T_EPS, sat1 = cand1 && test_T.y < T_EPS;
+                const float2 wm = make_float2(go0 ? w0.x : 0.f, go1 ? w0.y : 0.f);     // a masked weight adds exactly nothing
+                Cr2[r] = fma2(qr2, wm, Cr2[r]); Cg2[r] = fma2(qg2, wm, Cg2[r]); Cb2[r] = fma2(qb2, wm, Cb2[r]);
+                Dd2[r] = fma2(dep2, wm, Dd2[r]);
+                if (go0) { Tt2[r].x = test_T.x; last[2 * r] = idx; }
+                if (go1) { Tt2[r].y = test_T.y; last[2 * r + 1] = idx; }
+                if (sat0) Tt2[r].x = -fabsf(Tt2[r].x);               // finished pixels keep -|T|: test_T < 0 from now on
+                if (sat1) Tt2[r].y = -fabsf(Tt2[r].y);
+            };
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+                if ((mj >> (2 * r)) & 3u) blend_row(r);               // warp-uniform branch
+                if (r + 1 < NR) dy2 = add2(dy2, kNegFour2);
+            }
+        }
+        __syncwarp();      // every lane is done with this stage before it is refilled
+    }
+    const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
+    const size_t N = (size_t)W * H;
+    {
+        uint32_t deepest = 0u;
+#pragma unroll
+        for (int i = 0; i < SPW; i++) deepest = max(deepest, last[i]);
+        deepest = __reduce_max_sync(0xffffffffu, deepest);
+        if (lane == 0) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(tile_todo + tile);
+            if (SPW == 8) tile_todo[tile] = make_uint4(deepest, 0u, 0u, 0u);
+            else if (SPW == 4) { w[k0 >> 1] = deepest; w[(k0 >> 1) + 1] = 0u; }
+            else w[k0 >> 1] = deepest;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < SPW; i++) {
+        const int r = i >> 1;
+        const int px = X0 + ((i & 1) << 3) + lx, py = Yr + (r << 2) + ly;
+        if (px < W && py < H) {
+            const size_t pid = (size_t)py * W + px;
+            const bool hi = i & 1;
+            const float T = fabsf(hi ? Tt2[r].y : Tt2[r].x);
+            out_color[pid] = (hi ? Cr2[r].y : Cr2[r].x) + T * bg0;
+            out_color[N + pid] = (hi ? Cg2[r].y : Cg2[r].x) + T * bg1;
+            out_color[2 * N + pid] = (hi ? Cb2[r].y : Cb2[r].x) + T * bg2;
+            out_depth[pid] = hi ? Dd2[r].y : Dd2[r].x;
+            out_alpha[pid] = 1.f - T;         // == sum alpha_i T_i (telescoping), A.8
+            n_contrib[pid] = last[i];
+            final_T[pid] = T;
+        }
+    }
+}
+
+template <int MINB, int MODE>      // MODE 0: register-prefetched gathers, 1: TMA staging, 2: packed-fp32 blend
 __global__ void __launch_bounds__(32, MINB)
 render_forward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __restrict__ ranges,
                       const uint32_t* __restrict__ point_list, const Record* __restrict__ rec, int W, int H,
                       const float* __restrict__ bg, const int64_t* __restrict__ status, int64_t capacity,
                       float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha,
                       uint32_t* __restrict__ n_contrib, float* __restrict__ final_T, uint4* __restrict__ tile_todo) {
-    __shared__ __align__(16) float4 s_rec[2][96];        // 2 stages x 32 records x {q0, q1, q2}
+    constexpr bool TMA = MODE == 1;
+    __shared__ __align__(16) float4 s_rec[MODE == 2 ? 1 : 2][MODE == 2 ? 32 * DUP_F4 : 96];   // record staging (MODE 2: packed-blend layout)
     __shared__ __align__(8) unsigned long long s_bar[2];
     int b = blockIdx.x;
     if (status[0] > capacity) {
@@ -346,13 +526,24 @@ render_forward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __rest
         }
         return;
     }
-#define SCGR_ARGS s_rec, s_bar, ranges, point_list, rec, W, H, bg, out_color, out_depth, out_alpha, n_contrib, final_T, tile_todo
-    if (b < ws.n8) { forward_region<8, TMA>(b, tiles_x, 0, SCGR_ARGS); return; }
-    b -= ws.n8;
-    if (b < 2 * ws.n4) { forward_region<4, TMA>(ws.n8 + (b >> 1), tiles_x, (b & 1) << 2, SCGR_ARGS); return; }
-    b -= 2 * ws.n4;
-    forward_region<2, TMA>(ws.n8 + ws.n4 + (b >> 2), tiles_x, (b & 3) << 1, SCGR_ARGS);
+    if constexpr (MODE == 2) {
+#define SCGR_ARGS &s_rec[0][0], ranges, point_list, rec, W, H, bg, out_color, out_depth, out_alpha, n_contrib, final_T, tile_todo
+        if (b < ws.n8) { forward_region_packed<8>(b, tiles_x, 0, SCGR_ARGS); return; }
+        b -= ws.n8;
+        if (b < 2 * ws.n4) { forward_region_packed<4>(ws.n8 + (b >> 1), tiles_x, (b & 1) << 2, SCGR_ARGS); return; }
+        b -= 2 * ws.n4;
+        forward_region_packed<2>(ws.n8 + ws.n4 + (b >> 2), tiles_x, (b & 3) << 1, SCGR_ARGS);
 #undef SCGR_ARGS
+    } else {
+        float4 (*s_rec2)[96] = reinterpret_cast<float4 (*)[96]>(&s_rec[0][0]);
+#define SCGR_ARGS s_rec2, s_bar, ranges, point_list, rec, W, H, bg, out_color, out_depth, out_alpha, n_contrib, final_T, tile_todo
+        if (b < ws.n8) { forward_region<8, TMA>(b, tiles_x, 0, SCGR_ARGS); return; }
+        b -= ws.n8;
+        if (b < 2 * ws.n4) { forward_region<4, TMA>(ws.n8 + (b >> 1), tiles_x, (b & 1) << 2, SCGR_ARGS); return; }
+        b -= 2 * ws.n4;
+        forward_region<2, TMA>(ws.n8 + ws.n4 + (b >> 2), tiles_x, (b & 3) << 1, SCGR_ARGS);
+#undef SCGR_ARGS
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -409,13 +600,14 @@ __device__ __forceinline__ float transpose_reduce10(const float v[10], const int
 
 template <int SPW, bool TMA>
 __device__ __forceinline__ void
-backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[96], uint32_t (*s_idb)[32],
+backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[96], float4* s_dup, uint32_t (*s_idb)[32],
                 unsigned long long* bars, float4* s_g4, const uint2* __restrict__ ranges,
                 const uint32_t* __restrict__ point_list, const Record* __restrict__ rec, const int W, const int H,
                 const float* __restrict__ bg, const uint32_t* __restrict__ n_contrib,
                 const float* __restrict__ final_T, const float* __restrict__ dL_dcolor,
                 const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha,
                 ScreenGrad* __restrict__ screen_grad) {
+    constexpr int NR = SPW / 2;         // tile rows of this region; a lane owns one pixel in each of the row's two columns
     const int lane = threadIdx.x & 31;
     if (TMA) {
         if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
@@ -428,32 +620,44 @@ backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)
     const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
     const size_t N = (size_t)W * H;
 
-    float T[SPW], Bs[SPW], tfb[SPW];
+    // pixel state, packed over the two columns of a row: transmittance T, suffix blend Bs, background / alpha term tfb
+    float2 T2[NR], Bs2[NR], tfb2[NR];
     int lc[SPW];
     int slot_lc[SPW];
     int toDo = 0;
 #pragma unroll
-    for (int i = 0; i < SPW; i++) {
-        const int px = X0 + ((i & 1) << 3) + lx, py = Yr + ((i >> 1) << 2) + ly;
-        float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f, Tf = 0.f;
-        lc[i] = 0;
-        if (px < W && py < H) {
-            const size_t pid = (size_t)py * W + px;
-            Tf = final_T[pid];
-            lc[i] = (int)n_contrib[pid];
-            gr = dL_dcolor[pid]; gg = dL_dcolor[N + pid]; gb = dL_dcolor[2 * N + pid];
-            gd = dL_ddepth[pid];
-            ga = dL_dalpha[pid];
+    for (int r = 0; r < NR; r++) {
+        float gr[2], gg[2], gb[2], gd[2], tf[2], tb[2];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int i = 2 * r + c;
+            const int px = X0 + (c << 3) + lx, py = Yr + (r << 2) + ly;
+            float ga = 0.f;
+            gr[c] = gg[c] = gb[c] = gd[c] = tf[c] = 0.f;
+            lc[i] = 0;
+            if (px < W && py < H) {
+                const size_t pid = (size_t)py * W + px;
+                tf[c] = final_T[pid];
+                lc[i] = (int)n_contrib[pid];
+                gr[c] = dL_dcolor[pid]; gg[c] = dL_dcolor[N + pid]; gb[c] = dL_dcolor[2 * N + pid];
+                gd[c] = dL_ddepth[pid];
+                ga = dL_dalpha[pid];
+            }
+            tb[c] = tf[c] * (ga - (bg0 * gr[c] + bg1 * gg[c] + bg2 * gb[c]));
+            slot_lc[i] = __reduce_max_sync(0xffffffffu, lc[i]);
+            toDo = max(toDo, slot_lc[i]);
         }
-        s_g4[i * 32 + lane] = make_float4(gr, gg, gb, gd);
-        T[i] = Tf;
-        tfb[i] = Tf * (ga - (bg0 * gr + bg1 * gg + bg2 * gb));
-        Bs[i] = 0.f;
-        slot_lc[i] = __reduce_max_sync(0xffffffffu, lc[i]);
-        toDo = max(toDo, slot_lc[i]);
+        // upstream dL/d{r, g, b, depth} of the lane's two pixels of this row, column-interleaved
+        s_g4[(2 * r) * 32 + lane] = make_float4(gr[0], gr[1], gg[0], gg[1]);
+        s_g4[(2 * r + 1) * 32 + lane] = make_float4(gb[0], gb[1], gd[0], gd[1]);
+        T2[r] = make_float2(tf[0], tf[1]);
+        tfb2[r] = make_float2(tb[0], tb[1]);
+        Bs2[r] = make_float2(0.f, 0.f);
     }
-    const float pxf = (float)(X0 + lx), pyf = (float)(Yr + ly);
     // (each lane only ever reads back the s_g4 entries it wrote itself: no barrier needed)
+    const float2 npx2 = make_float2(-(float)(X0 + lx), -(float)(X0 + lx + 8));    // pixel abscissae of the two columns
+    const float2 npy2 = make_float2(-(float)(Yr + ly), -(float)(Yr + ly));
+    const float2 kOne2 = make_float2(1.f, 1.f), kNegOne2 = make_float2(-1.f, -1.f), kNegFour2 = make_float2(-4.f, -4.f);
     const int slot = reduce10_slot(lane);                         // which of the 10 sums this lane deposits
     float* const my_grad = reinterpret_cast<float*>(screen_grad) + (slot >= 0 ? slot : 0);
 
@@ -484,25 +688,24 @@ backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)
         const int base = 32 * b;
         const int cnt = min(32, toDo - base);
         SCGR_STAT_ADD(batches, 1); SCGR_STAT_ADD(scanned, cnt);
-        const float4* const srec = s_rec[TMA ? (b & 1) : 0];
         const uint32_t* const s_id = s_idb[TMA ? (b & 1) : 0];
         Rec cur;
         if (TMA) {
             mbar_wait(&bars[b & 1], (uint32_t)(b >> 1) & 1u);
             __syncwarp();                            // (also orders the generic s_id stores of this stage)
             if (b + 1 < nbatch) issue(b + 1);        // the other buffer was released by the __syncwarp below
+            const float4* const srec = s_rec[b & 1];
             cur.q0 = srec[lane * 3]; cur.q1 = srec[lane * 3 + 1]; cur.q2 = srec[lane * 3 + 2];
         } else {
             cur = nxt;
-            __syncwarp();
-            s_rec[0][lane * 3] = cur.q0; s_rec[0][lane * 3 + 1] = cur.q1; s_rec[0][lane * 3 + 2] = cur.q2;
             s_idb[0][lane] = nxt_id;
-            __syncwarp();
             if (base + 32 + lane < toDo) {
                 nxt_id = point_list[range.x + (toDo - 1 - (base + 32 + lane))];
                 nxt = load_rec(rec, nxt_id);
             }
         }
+        stage_dup(s_dup, lane, cur);                 // (the previous batch's readers passed the __syncwarp at the loop's end)
+        __syncwarp();
         uint32_t mymask = 0u;
         if (lane < cnt) {
             const int mypos = toDo - 1 - (base + lane);
@@ -517,54 +720,62 @@ backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)
             if (mj == 0u) continue;
             SCGR_STAT_ADD(hit, 1); SCGR_STAT_ADD(slots, __popc(mj));
             const int pos = toDo - 1 - (base + j);
-            const float4 q0 = srec[j * 3];
-            const float4 q1 = srec[j * 3 + 1];
-            const float4 q2 = srec[j * 3 + 2];
-            // hoisted per-column / per-row terms of the exponent, as in the forward
-            const float dxa = q0.x - pxf, dxb = dxa - 8.f;
-            const float dxs[2] = {dxa, dxb};
-            const float ax[2] = {(q0.z * dxa) * dxa, (q0.z * dxb) * dxb};
-            const float bx[2] = {q0.w * dxa, q0.w * dxb};
-            const float dy0 = q0.y - pyf;
-            const float dys[4] = {dy0, dy0 - 4.f, dy0 - 8.f, dy0 - 12.f};
-            float v[10];
+            const float4* const dj = s_dup + j * DUP_F4;
+            const float4 d0 = dj[0], d1 = dj[1], d2 = dj[2], d3 = dj[3], d4 = dj[4];
+            // per-column terms of the exponent, hoisted out of the rows:  power = cA dx^2 + dy (cB dx + cC dy)
+            const float2 dx2 = add2(make_float2(d0.x, d0.y), npx2);
+            const float2 ax2 = mul2(mul2(make_float2(d0.z, d0.w), dx2), dx2);
+            const float2 bx2 = mul2(make_float2(d1.x, d1.y), dx2);
+            const float2 cC2 = make_float2(d1.z, d1.w), op2 = make_float2(d2.x, d2.y), dep2 = make_float2(d2.z, d2.w);
+            const float2 qr2 = make_float2(d3.x, d3.y), qg2 = make_float2(d3.z, d3.w), qb2 = make_float2(d4.x, d4.y);
+            float2 dy2 = add2(make_float2(d4.z, d4.w), npy2);
+            float2 v2[10];
 #pragma unroll
-            for (int i = 0; i < 10; i++) v[i] = 0.f;
-            auto pair_grad = [&](const int i) {
-                const float dx = dxs[i & 1], dy = dys[i >> 1];
-                const float power = fmaf(dy, fmaf(q1.x, dy, bx[i & 1]), ax[i & 1]);
-                // straight-line: a pair that fails the reference's tests (A.9) runs with og = alpha = 0, which
-                // makes every term below vanish and leaves the pixel state untouched.
-                // min(0.99, og) >= 1/255  <=>  og >= 1/255
-                const float ograw = q1.y * ex2(power);
-                const float og = gate_pair(ograw, power, pos, lc[i]);   // opacity * G, un-capped
-                SCGR_STAT_ADD(ok, og > 0.f ? 1 : 0);
-                const float alpha = fminf(ALPHA_MAX, og);
-                const float ra = rcp_approx(1.f - alpha);    // 1 - alpha >= 0.01
-                T[i] *= ra;                                  // transmittance in front of this Gaussian
-                const float4 g4 = s_g4[i * 32 + lane];       // upstream dL/d{r, g, b, depth} of this pixel
+            for (int i = 0; i < 10; i++) v2[i] = make_float2(0.f, 0.f);
+            auto row_grad = [&](const int r) {
+                const float2 power = fma2(dy2, fma2(cC2, dy2, bx2), ax2);
+                // straight-line: a pixel that fails the reference's tests (A.9) -- or whose slot the Gaussian cannot
+                // reach at all -- runs with og = alpha = 0, which makes every term below vanish and leaves its state
+                // untouched.     min(0.99, og) >= 1/255  <=>  og >= 1/255
+                const float2 ograw = mul2(op2, make_float2(ex2(power.x), ex2(power.y)));
+                float2 og;                                              // opacity * G, un-capped
+                og.x = gate_pair(ograw.x, power.x, pos, lc[2 * r]);
+                og.y = gate_pair(ograw.y, power.y, pos, lc[2 * r + 1]);
+                SCGR_STAT_ADD(ok, (og.x > 0.f ? 1 : 0) + (og.y > 0.f ? 1 : 0));
+                const float2 alpha = make_float2(fminf(ALPHA_MAX, og.x), fminf(ALPHA_MAX, og.y));
+                const float2 om = fma2(alpha, kNegOne2, kOne2);          // 1 - alpha >= 0.01
+                const float2 ra = make_float2(rcp_approx(om.x), rcp_approx(om.y));
+                T2[r] = mul2(T2[r], ra);                                 // transmittance in front of this Gaussian
+                const float4 gA = s_g4[(2 * r) * 32 + lane], gB = s_g4[(2 * r + 1) * 32 + lane];
+                const float2 gr2 = make_float2(gA.x, gA.y), gg2 = make_float2(gA.z, gA.w);
+                const float2 gb2 = make_float2(gB.x, gB.y), gd2 = make_float2(gB.z, gB.w);
                 // Only the upstream-weighted sum over channels of the suffix blend is needed:
                 //   Bs = sum_ch g_ch A_ch,  A_ch <- alpha c_ch + (1 - alpha) A_ch   =>   Bs <- Bs + alpha (g.c - Bs)
-                const float cg = fmaf(q1.z, g4.w, fmaf(q2.z, g4.z, fmaf(q2.y, g4.y, q2.x * g4.x)));
-                const float e = cg - Bs[i];
-                Bs[i] = fmaf(alpha, e, Bs[i]);
+                const float2 cg = fma2(dep2, gd2, fma2(qb2, gb2, fma2(qg2, gg2, mul2(qr2, gr2))));
+                const float2 e = fma2(Bs2[r], kNegOne2, cg);
+                Bs2[r] = fma2(alpha, e, Bs2[r]);
                 // the alpha output and the background enter as T_final / (1 - alpha) * (dL/dalpha_pix - bg . dL/dC)
-                const float dL_dalpha_ = fmaf(e, T[i], tfb[i] * ra);
-                const float w = alpha * T[i];
-                const float uG = og * dL_dalpha_;            // G * dL/dG; propagated even when alpha was capped (A.9)
-                const float ux = uG * dx, uy = uG * dy;
-                v[0] += ux;                                  // preprocess-backward rebuilds dL/dmean from these two
-                v[1] += uy;
-                v[2] = fmaf(ux, dx, v[2]);                   // * -0.5 = dL/dconic_A
-                v[3] = fmaf(ux, dy, v[3]);                   // * -1   = dL/dconic_B
-                v[4] = fmaf(uy, dy, v[4]);                   // * -0.5 = dL/dconic_C
-                v[5] += uG;                                  // / opacity = dL/dopacity
-                v[6] = fmaf(w, g4.w, v[6]);                  // dL/ddepth
-                v[7] = fmaf(w, g4.x, v[7]); v[8] = fmaf(w, g4.y, v[8]); v[9] = fmaf(w, g4.z, v[9]);
+                const float2 dL_dalpha_ = fma2(e, T2[r], mul2(tfb2[r], ra));
+                const float2 w = mul2(alpha, T2[r]);
+                const float2 uG = mul2(og, dL_dalpha_);                  // G * dL/dG; propagated even when alpha was capped (A.9)
+                const float2 ux = mul2(uG, dx2), uy = mul2(uG, dy2);
+                v2[0] = add2(v2[0], ux);                                 // preprocess-backward rebuilds dL/dmean from these two
+                v2[1] = add2(v2[1], uy);
+                v2[2] = fma2(ux, dx2, v2[2]);                            // * -0.5 = dL/dconic_A
+                v2[3] = fma2(ux, dy2, v2[3]);                            // * -1   = dL/dconic_B
+                v2[4] = fma2(uy, dy2, v2[4]);                            // * -0.5 = dL/dconic_C
+                v2[5] = add2(v2[5], uG);                                 // / opacity = dL/dopacity
+                v2[6] = fma2(w, gd2, v2[6]);                             // dL/ddepth
+                v2[7] = fma2(w, gr2, v2[7]); v2[8] = fma2(w, gg2, v2[8]); v2[9] = fma2(w, gb2, v2[9]);
             };
 #pragma unroll
-            for (int i = 0; i < SPW; i++)
-                if (mj & (1u << i)) pair_grad(i);  // warp-uniform branch
+            for (int r = 0; r < NR; r++) {
+                if ((mj >> (2 * r)) & 3u) row_grad(r);                  // warp-uniform branch
+                if (r + 1 < NR) dy2 = add2(dy2, kNegFour2);
+            }
+            float v[10];
+#pragma unroll
+            for (int i = 0; i < 10; i++) v[i] = v2[i].x + v2[i].y;
             // (97 % of the pairs that get here have a contributing pixel: reduce unconditionally)
             const float sum = transpose_reduce10(v, lane);
             SCGR_STAT_ADD(red, 1); SCGR_STAT_ADD(atom, (slot >= 0 && sum != 0.f) ? 1 : 0);
@@ -591,13 +802,14 @@ render_backward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __res
                        const float* __restrict__ dL_dalpha, ScreenGrad* __restrict__ screen_grad,
                        const uint32_t* __restrict__ tile_order) {
     __shared__ __align__(16) float4 s_rec[2][96];        // 2 stages x 32 records x {q0, q1, q2}
+    __shared__ __align__(16) float4 s_dup[32 * DUP_F4];  // the batch's records in the packed-blend layout (stage_dup)
     __shared__ uint32_t s_id[2][32];
     __shared__ __align__(8) unsigned long long s_bar[2];
-    __shared__ float4 s_g4[TILE_PIX];       // upstream gradients of the region: r, g, b, depth
+    __shared__ float4 s_g4[TILE_PIX];       // upstream gradients of the region, column-interleaved per tile row
     if (status[0] > capacity) return;
     int b = blockIdx.x;
     // work item -> tile through the longest-first permutation built from the forward's per-tile depths
-#define SCGR_ARGS s_rec, s_id, s_bar, s_g4, ranges, point_list, rec, W, H, bg, n_contrib, final_T, dL_dcolor, dL_ddepth, \
+#define SCGR_ARGS s_rec, s_dup, s_id, s_bar, s_g4, ranges, point_list, rec, W, H, bg, n_contrib, final_T, dL_dcolor, dL_ddepth, \
                   dL_dalpha, screen_grad
     if (b < ws.n8) { backward_region<8, TMA>((int)tile_order[b], tiles_x, 0, SCGR_ARGS); return; }
     b -= ws.n8;
@@ -719,14 +931,16 @@ void launch_render_forward(const ScgrView& v, const GeometryLayout& G, const Bin
     const int tx = (v.image_width + TILE - 1) / TILE, ty = (v.image_height + TILE - 1) / TILE;
     if (tx == 0 || ty == 0) return;
     static const int minb = env_int("SCGR_FWD_MINB", 20);
-    static const int tma = env_int("SCGR_TMA_FWD", env_int("SCGR_TMA", 0));
+    // staging / blend variant: 0 register-prefetched gathers + scalar blend, 1 TMA staging + scalar blend, 2 packed-fp32 blend
+    static const int tma = env_int("SCGR_FWD_PACKED", 1) ? 2 : env_int("SCGR_TMA_FWD", env_int("SCGR_TMA", 0));
     const WorkSplit ws = make_split(tx * ty, "SCGR_FWD_SPLIT", 10, 5);
     begin_kernel("render_forward", L);
 #define SCGR_FWD(M_, T_) render_forward_kernel<M_, T_><<<ws.items(), 32, 0, L.stream>>>(ws, tx, B.ranges, point_list, G.rec, \
         v.image_width, v.image_height, v.bg, G.status, capacity, out_color, out_depth, out_alpha, I.n_contrib, I.final_T, \
         I.tile_todo)
-    if (!tma) { if (minb == 20) SCGR_FWD(20, false); else if (minb == 24) SCGR_FWD(24, false); else SCGR_FWD(1, false); }
-    else if (minb == 20) SCGR_FWD(20, true); else if (minb == 24) SCGR_FWD(24, true); else SCGR_FWD(1, true);
+    if (tma == 0) { if (minb == 20) SCGR_FWD(20, 0); else if (minb == 24) SCGR_FWD(24, 0); else SCGR_FWD(1, 0); }
+    else if (tma == 1) { if (minb == 20) SCGR_FWD(20, 1); else if (minb == 24) SCGR_FWD(24, 1); else SCGR_FWD(1, 1); }
+    else if (minb == 20) SCGR_FWD(20, 2); else if (minb == 24) SCGR_FWD(24, 2); else if (minb == 16) SCGR_FWD(16, 2); else if (minb == 18) SCGR_FWD(18, 2); else SCGR_FWD(1, 2);
 #undef SCGR_FWD
     check_launch("render_forward", L);
 }

@@ -122,6 +122,9 @@ def _replace_fn_body(text: str, name: str, body: str) -> str:
 # staging buffer when bulk_g2s returns, so the mbarrier protocol has nothing left to wait for.
 _RENDER_PTX = {
     "ex2": "return exp2f(x);",
+    "fma2": "return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));",      # fma.rn.f32x2: two IEEE fused ops
+    "mul2": "return make_float2(a.x * b.x, a.y * b.y);",
+    "add2": "return make_float2(a.x + b.x, a.y + b.y);",
     "rcp_approx": "return 1.0f / x;",
     "gate_pair": "return (pos < lc && power <= 0.f && og_raw >= 1.0f / 255.0f) ? og_raw : 0.f;",
     "mbar_init": "(void)bar; (void)count;",

@@ -621,6 +621,26 @@ def test_backward_accumulates_over_views_and_emits_densification_stats_on_host(e
     assert float(acc["stats"][:, 1].max()) == 2.0
 
 
+@pytest.mark.parametrize("split", ["0,0", "40,30"])
+def test_packed_and_scalar_forward_blends_are_bit_identical_on_host(emu_pre, monkeypatch, split):
+    """render.cu's two forward blends -- scalar, and packed fp32 over the two slot columns of a tile row (FFMA2 / FMUL2
+    on sm_100a) -- perform the same per-pixel operations with the same roundings: identical images, n_contrib and
+    final_T, bit for bit (whole tiles, halves and quarters)."""
+    from oracle import torch_oracle as O
+    monkeypatch.setenv("SCGR_FWD_SPLIT", split)
+    P, W, H = 1200, 150, 100
+    case, t, view, g = _host_scene(P, W, H, 3, seed=52, scale_median=0.07, w2c=O.yaw_w2c(-4.0), z_shift=-1.0, bg=(0.2, 0.1, 0.4))
+    outs = []
+    for packed in ("0", "1"):
+        monkeypatch.setenv("SCGR_FWD_PACKED", packed)
+        f = _host_forward(emu_pre, case, t, view, g, P, W, H)
+        img = f["image"][f["iptr"] - f["image"].data_ptr():][: 2 * W * H * 4].clone()      # n_contrib + final_T
+        outs.append((f["color"].clone(), f["depth"].clone(), f["alpha"].clone(), img))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert float(outs[0][2].max()) > 0.5
+
+
 def test_overflow_flag_on_host_describes_the_last_emission(emu_pre):
     """The recovery path of SCGR_NEED_CAPACITY at kernel level: an emission into a binning buffer that is too small
     writes nothing and raises the device flag; the re-run with a large enough buffer (stage 1 kept) clears it and
