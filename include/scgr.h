@@ -96,7 +96,7 @@ typedef struct ScgrGrads {
     float* dL_dcov3D_precomp;  /* [P,6] or NULL */
     /* Optional, for batches of views (the reference accumulates the same quantities over
      * sequential iterations, scene/gaussian_model.py:932-934):
-     * densification_stats [P,2] receives {|dL_dmeans2D[i, 0:2]| * visible_i, visible_i} with visible_i = radii[i] > 0
+     * densification_stats [P,2] (8-byte aligned) receives {|dL_dmeans2D[i, 0:2]| * visible_i, visible_i} with visible_i = radii[i] > 0
      * -- the two per-view terms of add_densification_stats -- so that one SUM all-reduce over a flat buffer carries
      * them; it requires `radii` (the forward's int32 [P] output).  With accumulate != 0 every parameter gradient and
      * the statistics are ADDED to what the arrays hold (gradient accumulation over the views a rank renders before
@@ -104,6 +104,10 @@ typedef struct ScgrGrads {
     float* densification_stats;
     const int32_t* radii;
     int32_t accumulate;
+    /* Optional [P]: 1 for every Gaussian that received any gradient in this view, 0 otherwise (added when `accumulate`
+     * is set): summed over the ranks it tells which rows of the gradient arrays are non-zero anywhere -- the rest need
+     * not cross the NVSwitch (scgr_nvls_allreduce_rows). */
+    float* live_count;
 } ScgrGrads;
 
 int scgr_version(void);
@@ -187,6 +191,13 @@ int scgr_photometric_backward(const float* image, const float* gt, int32_t C, in
  * support the host side falls back to ncclAllReduce on the same buffer. */
 int scgr_nvls_allreduce(void* multicast_ptr, size_t n_floats, int32_t rank, int32_t world,
                         scgr_stream_t stream);
+/* Row-sparse companion: the same two-shot reduction for an array of n_rows rows of row_floats fp32 (a multiple of 4;
+ * rows 16-byte aligned), restricted to the rows i with live_count[i] != 0.  `live_count` is this rank's LOCAL copy of
+ * an array that is already identical on every rank (ScgrGrads.live_count summed by scgr_nvls_allreduce): rows nobody
+ * wrote are exact zeros everywhere and need no traffic.  Rank r reduces rows [r ceil(n / world), (r + 1) ceil(n / world)).
+ * Same bracketing by cross-rank barriers as above. */
+int scgr_nvls_allreduce_rows(void* multicast_rows, const float* live_count, int64_t n_rows, int32_t row_floats,
+                             int32_t rank, int32_t world, scgr_stream_t stream);
 
 /* ---- simple_knn._C.distCUDA2 (reference scene/gaussian_model.py:20, :444) ----
  * out[i] = mean over the 3 nearest other points of |p_i - p_j|^2; points [n,3] fp32 device, out [n].

@@ -32,7 +32,7 @@ class ScgrGrads(C.Structure):
                 ("dL_dcolors_precomp", C.c_void_p), ("dL_dopacities", C.c_void_p),
                 ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p),
                 ("dL_dcov3D_precomp", C.c_void_p), ("densification_stats", C.c_void_p), ("radii", C.c_void_p),
-                ("accumulate", C.c_int32)]
+                ("accumulate", C.c_int32), ("live_count", C.c_void_p)]
 
 
 class ScgrDebugViews(C.Structure):
@@ -112,6 +112,7 @@ SYMBOLS = {
     "scgr_photometric_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scgr_nvls_allreduce": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p]),
+    "scgr_nvls_allreduce_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "scgr_knn3_mean_dist2": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "scgr_assemble_forward": (C.c_int, [C.POINTER(ScgrModel), C.POINTER(ScgrActivated), C.c_void_p]),
     "scgr_assemble_backward": (C.c_int, [C.POINTER(ScgrModel), C.POINTER(ScgrActivatedGrads),

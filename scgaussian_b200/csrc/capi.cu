@@ -396,6 +396,20 @@ int scgr_nvls_allreduce(void* multicast_ptr, size_t n_floats, int32_t rank, int3
     });
 }
 
+int scgr_nvls_allreduce_rows(void* multicast_rows, const float* live_count, int64_t n_rows, int32_t row_floats,
+                             int32_t rank, int32_t world, scgr_stream_t stream) {
+    return guarded([&] {
+        require(world >= 1 && rank >= 0 && rank < world, "nvls all-reduce: bad rank / world size");
+        require(n_rows >= 0, "nvls all-reduce: negative row count");
+        if (n_rows == 0) return;
+        require(multicast_rows != nullptr && live_count != nullptr, "nvls all-reduce: null pointer");
+        require((reinterpret_cast<uintptr_t>(multicast_rows) & 15) == 0, "nvls all-reduce: rows must be 16-byte aligned");
+        require(row_floats > 0 && row_floats % 4 == 0, "nvls all-reduce: row_floats must be a positive multiple of 4");
+        const Launch L{(cudaStream_t)stream, false};
+        launch_nvls_allreduce_rows(multicast_rows, live_count, n_rows, row_floats, rank, world, L);
+    });
+}
+
 int scgr_knn3_mean_dist2(const float* points, int32_t n, float* out, scgr_stream_t stream) {
     return guarded([&] {
         require(n >= 0, "knn3: negative point count");

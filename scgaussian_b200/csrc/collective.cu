@@ -50,7 +50,90 @@ nvls_allreduce_kernel(float4* __restrict__ mc, const size_t first, const size_t 
     for (; i < count; i += stride) multimem_st(mc + first + i, multimem_ld_reduce_add(mc + first + i));
 }
 
+// ---- row-sparse variant: only the rows some rank actually wrote ----
+// In one view most Gaussians receive no gradient at all (hidden behind saturated pixels, or outside the view): their
+// rows of the gradient arrays are exact zeros on every rank.  The backward counts, per Gaussian, the views that gave
+// it a gradient (ScgrGrads.live_count); once that small array has been summed over the ranks (dense shot, above) every
+// rank knows the same set of rows worth reducing, and the 192-byte dL/dSH rows -- 79 % of the payload -- go through
+// the switch only for those.  Rank r owns rows [r n / world, (r + 1) n / world).  A warp takes 128 consecutive rows,
+// compacts the live ones with four ballots, and spreads the (row, float4) items of the live rows over its lanes,
+// UNROLL items per lane in flight.
+__device__ __forceinline__ uint32_t nth_set_bit(uint32_t w, uint32_t k) {      // position of the k-th (0-based) set bit
+    uint32_t pos = 0u;
+    uint32_t c = __popc(w & 0xFFFFu);
+    if (k >= c) { k -= c; pos = 16u; w >>= 16; }
+    c = __popc(w & 0xFFu);
+    if (k >= c) { k -= c; pos += 8u; w >>= 8; }
+    c = __popc(w & 0xFu);
+    if (k >= c) { k -= c; pos += 4u; w >>= 4; }
+    c = __popc(w & 0x3u);
+    if (k >= c) { k -= c; pos += 2u; w >>= 2; }
+    if (k >= (w & 1u)) pos += 1u;
+    return pos;
+}
+
+template <int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS)
+nvls_allreduce_rows_kernel(float4* __restrict__ mc, const float* __restrict__ live, const long long row_first,
+                           const long long row_end, const int row_f4) {
+    constexpr int CHUNK = 128;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * THREADS + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * THREADS) >> 5;
+    for (long long base = row_first + warp * CHUNK; base < row_end; base += n_warps * CHUNK) {
+        uint32_t bal[4], pre[5];
+        pre[0] = 0u;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const long long i = base + 32 * q + lane;
+            bal[q] = __ballot_sync(0xffffffffu, i < row_end && live[i] != 0.f);
+            pre[q + 1] = pre[q] + __popc(bal[q]);
+        }
+        const uint32_t items = pre[4] * (uint32_t)row_f4;
+        for (uint32_t it0 = 0; it0 < items; it0 += 32u * UNROLL) {
+            float4 v[UNROLL];
+            float4* addr[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const uint32_t it = it0 + (uint32_t)u * 32u + (uint32_t)lane;
+                addr[u] = nullptr;
+                if (it < items) {
+                    const uint32_t k = it / (uint32_t)row_f4, c = it - k * (uint32_t)row_f4;
+                    const int q = (k >= pre[1]) + (k >= pre[2]) + (k >= pre[3]);
+                    const uint32_t w = q == 0 ? bal[0] : (q == 1 ? bal[1] : (q == 2 ? bal[2] : bal[3]));
+                    const uint32_t p0 = q == 0 ? pre[0] : (q == 1 ? pre[1] : (q == 2 ? pre[2] : pre[3]));
+                    const long long row = base + 32 * q + (long long)nth_set_bit(w, k - p0);
+                    addr[u] = mc + row * row_f4 + c;
+                    v[u] = multimem_ld_reduce_add(addr[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++)
+                if (addr[u]) multimem_st(addr[u], v[u]);
+        }
+    }
+}
+
 }  // namespace
+
+void launch_nvls_allreduce_rows(void* multicast_rows, const float* live_count, long long n_rows, int row_floats, int rank,
+                                int world, const Launch& L) {
+    if (n_rows <= 0) return;
+    const long long per = (n_rows + world - 1) / world;
+    const long long first = per * rank, end = first + per < n_rows ? first + per : n_rows;
+    if (first >= end) return;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static const int ctas_per_sm = getenv("SCGR_NVLS_CTAS") ? atoi(getenv("SCGR_NVLS_CTAS")) : 2;
+    constexpr int THREADS = 512;
+    const long long chunks = (end - first + 127) / 128;
+    const long long want = (chunks + THREADS / 32 - 1) / (THREADS / 32);
+    const long long cap = (long long)ctas_per_sm * sms;
+    begin_kernel("nvls_allreduce_rows", L);
+    nvls_allreduce_rows_kernel<THREADS, 4><<<(unsigned)(want < cap ? want : cap), THREADS, 0, L.stream>>>(
+        reinterpret_cast<float4*>(multicast_rows), live_count, first, end, row_floats / 4);
+    check_launch("nvls_allreduce_rows", L);
+}
 
 void launch_nvls_allreduce(void* multicast_ptr, size_t n_floats, int rank, int world, const Launch& L) {
     const size_t n4 = n_floats / 4;                       // caller guarantees n_floats % (4 * world) == 0

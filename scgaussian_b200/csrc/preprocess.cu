@@ -465,6 +465,7 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
                 if (ACC) { if (vis != 0.f) { float2 o = *st; o.y += vis; *st = o; } }
                 else *st = make_float2(0.f, vis);
             }
+            if (out.live_count && !ACC) out.live_count[own] = 0.f;
             if (ACC) continue;
             out.dL_dmeans3D[3 * (size_t)own] = 0.f; out.dL_dmeans3D[3 * (size_t)own + 1] = 0.f; out.dL_dmeans3D[3 * (size_t)own + 2] = 0.f;
             out.dL_dopacities[own] = 0.f;
@@ -703,6 +704,7 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
             if (ACC) { float2 o = *st; o.x += nrm; o.y += 1.f; *st = o; }
             else *st = make_float2(nrm, 1.f);
         }
+        if (out.live_count) put(out.live_count + i, 1.f);
         if (out.dL_dcolors_precomp) {
             put(out.dL_dcolors_precomp + 3 * (size_t)i, dcol[0]); put(out.dL_dcolors_precomp + 3 * (size_t)i + 1, dcol[1]); put(out.dL_dcolors_precomp + 3 * (size_t)i + 2, dcol[2]);
         }

@@ -600,7 +600,183 @@ __device__ __forceinline__ float transpose_reduce10(const float v[10], const int
 
 template <int SPW, bool TMA>
 __device__ __forceinline__ void
-backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[96], float4* s_dup, uint32_t (*s_idb)[32],
+backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[96], uint32_t (*s_idb)[32],
+                unsigned long long* bars, float4* s_g4, const uint2* __restrict__ ranges,
+                const uint32_t* __restrict__ point_list, const Record* __restrict__ rec, const int W, const int H,
+                const float* __restrict__ bg, const uint32_t* __restrict__ n_contrib,
+                const float* __restrict__ final_T, const float* __restrict__ dL_dcolor,
+                const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha,
+                ScreenGrad* __restrict__ screen_grad) {
+    const int lane = threadIdx.x & 31;
+    if (TMA) {
+        if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+        mbar_fence_init();
+        __syncwarp();
+    }
+    const int lx = lane & 7, ly = lane >> 3;
+    const int X0 = (tile % tiles_x) * TILE, Yr = (tile / tiles_x) * TILE + ((k0 >> 1) << 2);
+    const uint2 range = ranges[tile];
+    const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
+    const size_t N = (size_t)W * H;
+
+    float T[SPW], Bs[SPW], tfb[SPW];
+    int lc[SPW];
+    int slot_lc[SPW];
+    int toDo = 0;
+#pragma unroll
+    for (int i = 0; i < SPW; i++) {
+        const int px = X0 + ((i & 1) << 3) + lx, py = Yr + ((i >> 1) << 2) + ly;
+        float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f, Tf = 0.f;
+        lc[i] = 0;
+        if (px < W && py < H) {
+            const size_t pid = (size_t)py * W + px;
+            Tf = final_T[pid];
+            lc[i] = (int)n_contrib[pid];
+            gr = dL_dcolor[pid]; gg = dL_dcolor[N + pid]; gb = dL_dcolor[2 * N + pid];
+            gd = dL_ddepth[pid];
+            ga = dL_dalpha[pid];
+        }
+        s_g4[i * 32 + lane] = make_float4(gr, gg, gb, gd);
+        T[i] = Tf;
+        tfb[i] = Tf * (ga - (bg0 * gr + bg1 * gg + bg2 * gb));
+        Bs[i] = 0.f;
+        slot_lc[i] = __reduce_max_sync(0xffffffffu, lc[i]);
+        toDo = max(toDo, slot_lc[i]);
+    }
+    const float pxf = (float)(X0 + lx), pyf = (float)(Yr + ly);
+    // (each lane only ever reads back the s_g4 entries it wrote itself: no barrier needed)
+    const int slot = reduce10_slot(lane);                         // which of the 10 sums this lane deposits
+    float* const my_grad = reinterpret_cast<float*>(screen_grad) + (slot >= 0 ? slot : 0);
+
+    // batch entry j  <->  0-based list position  pos = toDo - 1 - (base + j)   (back to front)
+    // stage b = batch entries [32 b, 32 b + 32) of the back-to-front walk; buffer b & 1
+    auto issue = [&](const int b) {
+        const int c = min(32, toDo - 32 * b);
+        if (lane == 0) mbar_expect_tx(&bars[b & 1], 48u * (uint32_t)c);
+        __syncwarp();
+        if (lane < c) {
+            const uint32_t id = point_list[range.x + (toDo - 1 - (32 * b + lane))];
+            s_idb[b & 1][lane] = id;
+            bulk_g2s(&s_rec[b & 1][lane * 3], rec + id, 48u, &bars[b & 1]);
+        }
+    };
+    Rec nxt;
+    uint32_t nxt_id = 0u;
+    nxt.q0 = nxt.q1 = nxt.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nbatch = (toDo + 31) >> 5;
+    if (TMA) { if (nbatch > 0) issue(0); }
+    else if (lane < toDo) {
+        nxt_id = point_list[range.x + (toDo - 1 - lane)];
+        nxt = load_rec(rec, nxt_id);
+    }
+    SCGR_STAT_DECL(batches); SCGR_STAT_DECL(scanned); SCGR_STAT_DECL(hit); SCGR_STAT_DECL(slots);
+    SCGR_STAT_DECL(ok); SCGR_STAT_DECL(red); SCGR_STAT_DECL(atom);
+    for (int b = 0; b < nbatch; b++) {
+        const int base = 32 * b;
+        const int cnt = min(32, toDo - base);
+        SCGR_STAT_ADD(batches, 1); SCGR_STAT_ADD(scanned, cnt);
+        const float4* const srec = s_rec[TMA ? (b & 1) : 0];
+        const uint32_t* const s_id = s_idb[TMA ? (b & 1) : 0];
+        Rec cur;
+        if (TMA) {
+            mbar_wait(&bars[b & 1], (uint32_t)(b >> 1) & 1u);
+            __syncwarp();                            // (also orders the generic s_id stores of this stage)
+            if (b + 1 < nbatch) issue(b + 1);        // the other buffer was released by the __syncwarp below
+            cur.q0 = srec[lane * 3]; cur.q1 = srec[lane * 3 + 1]; cur.q2 = srec[lane * 3 + 2];
+        } else {
+            cur = nxt;
+            __syncwarp();
+            s_rec[0][lane * 3] = cur.q0; s_rec[0][lane * 3 + 1] = cur.q1; s_rec[0][lane * 3 + 2] = cur.q2;
+            s_idb[0][lane] = nxt_id;
+            __syncwarp();
+            if (base + 32 + lane < toDo) {
+                nxt_id = point_list[range.x + (toDo - 1 - (base + 32 + lane))];
+                nxt = load_rec(rec, nxt_id);
+            }
+        }
+        uint32_t mymask = 0u;
+        if (lane < cnt) {
+            const int mypos = toDo - 1 - (base + lane);
+            uint32_t live = 0u;
+#pragma unroll
+            for (int i = 0; i < SPW; i++)
+                if (mypos < slot_lc[i]) live |= 1u << i;
+            mymask = slot_mask<SPW>(cur, (float)X0, (float)Yr, live);
+        }
+        for (int j = 0; j < cnt; j++) {
+            const uint32_t mj = __shfl_sync(0xffffffffu, mymask, j);
+            if (mj == 0u) continue;
+            SCGR_STAT_ADD(hit, 1); SCGR_STAT_ADD(slots, __popc(mj));
+            const int pos = toDo - 1 - (base + j);
+            const float4 q0 = srec[j * 3];
+            const float4 q1 = srec[j * 3 + 1];
+            const float4 q2 = srec[j * 3 + 2];
+            // hoisted per-column / per-row terms of the exponent, as in the forward
+            const float dxa = q0.x - pxf, dxb = q0.x - (pxf + 8.f);      // (same roundings as the forward)
+            const float dxs[2] = {dxa, dxb};
+            const float ax[2] = {(q0.z * dxa) * dxa, (q0.z * dxb) * dxb};
+            const float bx[2] = {q0.w * dxa, q0.w * dxb};
+            const float dy0 = q0.y - pyf, dy1 = dy0 - 4.f, dy2_ = dy1 - 4.f;
+            const float dys[4] = {dy0, dy1, dy2_, dy2_ - 4.f};
+            float v[10];
+#pragma unroll
+            for (int i = 0; i < 10; i++) v[i] = 0.f;
+            auto pair_grad = [&](const int i) {
+                const float dx = dxs[i & 1], dy = dys[i >> 1];
+                const float power = fmaf(dy, fmaf(q1.x, dy, bx[i & 1]), ax[i & 1]);
+                // straight-line: a pair that fails the reference's tests (A.9) runs with og = alpha = 0, which
+                // makes every term below vanish and leaves the pixel state untouched.
+                // min(0.99, og) >= 1/255  <=>  og >= 1/255
+                const float ograw = q1.y * ex2(power);
+                const float og = gate_pair(ograw, power, pos, lc[i]);   // opacity * G, un-capped
+                SCGR_STAT_ADD(ok, og > 0.f ? 1 : 0);
+                const float alpha = fminf(ALPHA_MAX, og);
+                const float ra = rcp_approx(1.f - alpha);    // 1 - alpha >= 0.01
+                T[i] *= ra;                                  // transmittance in front of this Gaussian
+                const float4 g4 = s_g4[i * 32 + lane];       // upstream dL/d{r, g, b, depth} of this pixel
+                // Only the upstream-weighted sum over channels of the suffix blend is needed:
+                //   Bs = sum_ch g_ch A_ch,  A_ch <- alpha c_ch + (1 - alpha) A_ch   =>   Bs <- Bs + alpha (g.c - Bs)
+                const float cg = fmaf(q1.z, g4.w, fmaf(q2.z, g4.z, fmaf(q2.y, g4.y, q2.x * g4.x)));
+                const float e = cg - Bs[i];
+                Bs[i] = fmaf(alpha, e, Bs[i]);
+                // the alpha output and the background enter as T_final / (1 - alpha) * (dL/dalpha_pix - bg . dL/dC)
+                const float dL_dalpha_ = fmaf(e, T[i], tfb[i] * ra);
+                const float w = alpha * T[i];
+                const float uG = og * dL_dalpha_;            // G * dL/dG; propagated even when alpha was capped (A.9)
+                const float ux = uG * dx, uy = uG * dy;
+                v[0] += ux;                                  // preprocess-backward rebuilds dL/dmean from these two
+                v[1] += uy;
+                v[2] = fmaf(ux, dx, v[2]);                   // * -0.5 = dL/dconic_A
+                v[3] = fmaf(ux, dy, v[3]);                   // * -1   = dL/dconic_B
+                v[4] = fmaf(uy, dy, v[4]);                   // * -0.5 = dL/dconic_C
+                v[5] += uG;                                  // / opacity = dL/dopacity
+                v[6] = fmaf(w, g4.w, v[6]);                  // dL/ddepth
+                v[7] = fmaf(w, g4.x, v[7]); v[8] = fmaf(w, g4.y, v[8]); v[9] = fmaf(w, g4.z, v[9]);
+            };
+#pragma unroll
+            for (int i = 0; i < SPW; i++)
+                if (mj & (1u << i)) pair_grad(i);  // warp-uniform branch
+            // (97 % of the pairs that get here have a contributing pixel: reduce unconditionally)
+            const float sum = transpose_reduce10(v, lane);
+            SCGR_STAT_ADD(red, 1); SCGR_STAT_ADD(atom, (slot >= 0 && sum != 0.f) ? 1 : 0);
+            if (slot >= 0 && sum != 0.f)
+                atomicAdd(my_grad + (size_t)s_id[j] * (sizeof(ScreenGrad) / sizeof(float)), sum);   // RED.E.ADD.F32
+        }
+        __syncwarp();      // every lane is done with this stage before it is refilled
+    }
+    SCGR_STAT_FLUSH_WARP(8, batches); SCGR_STAT_FLUSH_WARP(9, scanned); SCGR_STAT_FLUSH_WARP(10, hit);
+    SCGR_STAT_FLUSH_WARP(11, slots); SCGR_STAT_FLUSH_LANES(12, ok); SCGR_STAT_FLUSH_WARP(13, red);
+    SCGR_STAT_FLUSH_LANES(14, atom);
+#ifdef SCGR_STATS
+    if (lane == 0) { atomicAdd(&d_render_stats[15], 1ull); atomicAdd(&d_render_stats[16], (unsigned long long)toDo); }
+#endif
+}
+
+// The same walk with the blend done for the lane's two pixels of a tile row at once (packed fp32, see fma2 above).
+// MEASURED SLOWER than the scalar blend on B200 (profiles/r02_packed_fp32.md): kept as a switch (SCGR_BWD_PACKED=1).
+template <int SPW, bool TMA>
+__device__ __forceinline__ void
+backward_region_packed(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[96], float4* s_dup, uint32_t (*s_idb)[32],
                 unsigned long long* bars, float4* s_g4, const uint2* __restrict__ ranges,
                 const uint32_t* __restrict__ point_list, const Record* __restrict__ rec, const int W, const int H,
                 const float* __restrict__ bg, const uint32_t* __restrict__ n_contrib,
@@ -792,7 +968,7 @@ backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)
 #endif
 }
 
-template <int MINB, bool TMA>
+template <int MINB, bool TMA, bool PK>
 __global__ void __launch_bounds__(32, MINB)
 render_backward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __restrict__ ranges,
                        const uint32_t* __restrict__ point_list, const Record* __restrict__ rec, int W, int H,
@@ -802,21 +978,32 @@ render_backward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __res
                        const float* __restrict__ dL_dalpha, ScreenGrad* __restrict__ screen_grad,
                        const uint32_t* __restrict__ tile_order) {
     __shared__ __align__(16) float4 s_rec[2][96];        // 2 stages x 32 records x {q0, q1, q2}
-    __shared__ __align__(16) float4 s_dup[32 * DUP_F4];  // the batch's records in the packed-blend layout (stage_dup)
+    __shared__ __align__(16) float4 s_dup[PK ? 32 * DUP_F4 : 1];  // packed blend: the batch's records in its layout (stage_dup)
     __shared__ uint32_t s_id[2][32];
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ float4 s_g4[TILE_PIX];       // upstream gradients of the region, column-interleaved per tile row
     if (status[0] > capacity) return;
     int b = blockIdx.x;
     // work item -> tile through the longest-first permutation built from the forward's per-tile depths
+    if constexpr (PK) {
 #define SCGR_ARGS s_rec, s_dup, s_id, s_bar, s_g4, ranges, point_list, rec, W, H, bg, n_contrib, final_T, dL_dcolor, dL_ddepth, \
                   dL_dalpha, screen_grad
-    if (b < ws.n8) { backward_region<8, TMA>((int)tile_order[b], tiles_x, 0, SCGR_ARGS); return; }
-    b -= ws.n8;
-    if (b < 2 * ws.n4) { backward_region<4, TMA>((int)tile_order[ws.n8 + (b >> 1)], tiles_x, (b & 1) << 2, SCGR_ARGS); return; }
-    b -= 2 * ws.n4;
-    backward_region<2, TMA>((int)tile_order[ws.n8 + ws.n4 + (b >> 2)], tiles_x, (b & 3) << 1, SCGR_ARGS);
+        if (b < ws.n8) { backward_region_packed<8, TMA>((int)tile_order[b], tiles_x, 0, SCGR_ARGS); return; }
+        b -= ws.n8;
+        if (b < 2 * ws.n4) { backward_region_packed<4, TMA>((int)tile_order[ws.n8 + (b >> 1)], tiles_x, (b & 1) << 2, SCGR_ARGS); return; }
+        b -= 2 * ws.n4;
+        backward_region_packed<2, TMA>((int)tile_order[ws.n8 + ws.n4 + (b >> 2)], tiles_x, (b & 3) << 1, SCGR_ARGS);
 #undef SCGR_ARGS
+    } else {
+#define SCGR_ARGS s_rec, s_id, s_bar, s_g4, ranges, point_list, rec, W, H, bg, n_contrib, final_T, dL_dcolor, dL_ddepth, \
+                  dL_dalpha, screen_grad
+        if (b < ws.n8) { backward_region<8, TMA>((int)tile_order[b], tiles_x, 0, SCGR_ARGS); return; }
+        b -= ws.n8;
+        if (b < 2 * ws.n4) { backward_region<4, TMA>((int)tile_order[ws.n8 + (b >> 1)], tiles_x, (b & 1) << 2, SCGR_ARGS); return; }
+        b -= 2 * ws.n4;
+        backward_region<2, TMA>((int)tile_order[ws.n8 + ws.n4 + (b >> 2)], tiles_x, (b & 3) << 1, SCGR_ARGS);
+#undef SCGR_ARGS
+    }
 }
 
 // Backward prologue, one launch: CTA 0 orders the tiles by descending depth of their backward
@@ -932,7 +1119,7 @@ void launch_render_forward(const ScgrView& v, const GeometryLayout& G, const Bin
     if (tx == 0 || ty == 0) return;
     static const int minb = env_int("SCGR_FWD_MINB", 20);
     // staging / blend variant: 0 register-prefetched gathers + scalar blend, 1 TMA staging + scalar blend, 2 packed-fp32 blend
-    static const int tma = env_int("SCGR_FWD_PACKED", 1) ? 2 : env_int("SCGR_TMA_FWD", env_int("SCGR_TMA", 0));
+    static const int tma = env_int("SCGR_FWD_PACKED", 0) ? 2 : env_int("SCGR_TMA_FWD", env_int("SCGR_TMA", 0));
     const WorkSplit ws = make_split(tx * ty, "SCGR_FWD_SPLIT", 10, 5);
     begin_kernel("render_forward", L);
 #define SCGR_FWD(M_, T_) render_forward_kernel<M_, T_><<<ws.items(), 32, 0, L.stream>>>(ws, tx, B.ranges, point_list, G.rec, \
@@ -968,11 +1155,16 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
         check_launch("backward_prologue", L);
     }
     begin_kernel("render_backward", L);
-#define SCGR_BWD(M_, T_) render_backward_kernel<M_, T_><<<ws.items(), 32, 0, L.stream>>>(ws, tx, B.ranges, point_list, \
+#define SCGR_BWD(M_, T_, P_) render_backward_kernel<M_, T_, P_><<<ws.items(), 32, 0, L.stream>>>(ws, tx, B.ranges, point_list, \
         G.rec, v.image_width, v.image_height, v.bg, G.status, capacity, I.n_contrib, I.final_T, dL_dcolor, dL_ddepth, \
         dL_dalpha, G.screen_grad, I.tile_order)
-    if (!tma) { if (minb == 16) SCGR_BWD(16, false); else if (minb == 14) SCGR_BWD(14, false); else if (minb == 20) SCGR_BWD(20, false); else if (minb == 18) SCGR_BWD(18, false); else SCGR_BWD(1, false); }
-    else if (minb == 16) SCGR_BWD(16, true); else if (minb == 14) SCGR_BWD(14, true); else if (minb == 20) SCGR_BWD(20, true); else if (minb == 18) SCGR_BWD(18, true); else if (minb == 19) SCGR_BWD(19, true); else if (minb == 17) SCGR_BWD(17, true); else SCGR_BWD(1, true);
+    static const int packed = env_int("SCGR_BWD_PACKED", 0);      // packed-fp32 blend: measured slower, off by default
+    if (packed) {
+        if (!tma) { if (minb == 16) SCGR_BWD(16, false, true); else SCGR_BWD(1, false, true); }
+        else if (minb == 16) SCGR_BWD(16, true, true); else if (minb == 14) SCGR_BWD(14, true, true); else if (minb == 18) SCGR_BWD(18, true, true); else SCGR_BWD(1, true, true);
+    }
+    else if (!tma) { if (minb == 16) SCGR_BWD(16, false, false); else if (minb == 18) SCGR_BWD(18, false, false); else SCGR_BWD(1, false, false); }
+    else if (minb == 16) SCGR_BWD(16, true, false); else if (minb == 14) SCGR_BWD(14, true, false); else if (minb == 20) SCGR_BWD(20, true, false); else if (minb == 18) SCGR_BWD(18, true, false); else if (minb == 19) SCGR_BWD(19, true, false); else if (minb == 17) SCGR_BWD(17, true, false); else SCGR_BWD(1, true, false);
 #undef SCGR_BWD
     check_launch("render_backward", L);
 }

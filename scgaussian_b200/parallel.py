@@ -16,10 +16,15 @@ that (CPU tensors, no multicast support, fewer than 4 ranks -- where NCCL's dire
 SCGR_ALLREDUCE=nccl) leaves the collective to torch.distributed.all_reduce on the same buffer.
 
 Buffer layout (struct-of-arrays, each block a contiguous [P, k] tensor the C ABI can write):
-    means3D 3 | shs 3M (or colors 3) | opacities 1 | scales 3 | rotations 4 (or cov3D 6) | stats 2
+    means3D 3 | colors 3 (no-SH path) | opacities 1 | scales 3 | rotations 4 (or cov3D 6) | stats 2 | live 1 | shs 3M
 `stats` carries the densification statistics the reference accumulates per view at
 reference scene/gaussian_model.py:932-934: ||dL/dmean2D[:, :2]|| * visible and visible, so that
 the single SUM all-reduce yields exactly what N sequential add_densification_stats calls would.
+`live` counts, per Gaussian, the views that gave it any gradient (ScgrGrads.live_count).  In one view most Gaussians
+receive none (hidden behind saturated pixels, or out of view): their gradient rows are exact zeros on every rank.  The
+NVLS path therefore reduces the small blocks + `live` densely, and then the 192-byte dL/dSH rows -- 79 % of the bytes
+-- only for the Gaussians some rank marked live (scgr_nvls_allreduce_rows): same result as the dense sum, bit for
+bit, a fraction of the traffic.  The NCCL path reduces the whole buffer in one dist.all_reduce.
 """
 from __future__ import annotations
 
@@ -37,7 +42,8 @@ class FlatGradBuffer:
         self.P = P
         self._symm = None            # symmetric-memory handle when the NVLS path is active
         fields = [("means3D", (P, 3))]
-        fields.append(("shs", (P, sh_coeffs, 3)) if use_sh else ("colors_precomp", (P, 3)))
+        if not use_sh:
+            fields.append(("colors_precomp", (P, 3)))
         fields.append(("opacities", (P, 1)))
         if use_cov:
             fields.append(("cov3D_precomp", (P, 6)))
@@ -45,16 +51,28 @@ class FlatGradBuffer:
             fields += [("scales", (P, 3)), ("rotations", (P, 4))]
         if with_stats:
             fields.append(("stats", (P, 2)))
+        fields.append(("live", (P,)))
+        if use_sh:
+            fields.append(("shs", (P, sh_coeffs, 3)))       # last: the block the row-sparse shot covers
         self.fields = fields
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         sizes = []
-        for _, shp in fields:
+        for name, shp in fields:
             n = 1
             for d in shp:
                 n *= d
             sizes.append((n + 3) // 4 * 4)          # keep every block 16-byte aligned
+        # the dense part (everything before shs) is a whole number of float4 per rank
+        dense = sum(sizes[:-1]) if use_sh else sum(sizes)
+        pad = (-dense) % (4 * world)
+        if use_sh:
+            sizes[-2] += pad
+        else:
+            sizes[-1] += pad
         total = sum(sizes)
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         total = (total + 4 * world - 1) // (4 * world) * (4 * world)      # every rank reduces an equal float4 shard
+        self.dense_floats = dense + pad
+        self.row_floats = 3 * sh_coeffs if use_sh and (3 * sh_coeffs) % 4 == 0 else 0      # 0: no row-sparse shot
         self.flat = self._allocate(total, torch.device(device), world, symmetric)
         self.views: Dict[str, torch.Tensor] = {}
         o = 0
@@ -63,6 +81,8 @@ class FlatGradBuffer:
             for d in shp:
                 numel *= d
             self.views[name] = self.flat[o:o + numel].view(*shp)
+            if name == "shs":
+                self.rows_offset = o
             o += n
         # means2D is returned by the op but is not a parameter gradient: keep it outside the flat buffer
         self.means2D = torch.empty(P, 3, dtype=torch.float32, device=device)
@@ -86,10 +106,10 @@ class FlatGradBuffer:
         st[:, 1] = vis
 
     def _allocate(self, total: int, device: torch.device, world: int, symmetric: Optional[bool]) -> torch.Tensor:
-        # measured on 8xB200, 244 MB: NVLS kernel 609 us vs NCCL 661 us at 8 ranks, 645 us vs 481 us at 2 ranks
-        # (NCCL's direct P2P path wins there) -> the switch is used from 4 ranks up unless told otherwise
+        # measured on 8xB200, dense 244 MB: NVLS kernel 609 us vs NCCL 661 us at 8 ranks, 645 us vs 481 us at 2 ranks;
+        # with the row-sparse second shot the switch moves a fraction of that: it is used whenever it is available
         mode = os.environ.get("SCGR_ALLREDUCE", "auto")
-        want = symmetric if symmetric is not None else (mode == "nvls" or (mode == "auto" and world >= 4))
+        want = symmetric if symmetric is not None else (mode == "nvls" or (mode == "auto" and world >= 2))
         if want and world > 1 and device.type == "cuda" and dist.get_backend() == "nccl":
             try:
                 import torch.distributed._symmetric_memory as symm_mem
@@ -106,7 +126,13 @@ class FlatGradBuffer:
 
     @property
     def collective(self) -> str:
-        return "nvls two-shot kernel (libscgr)" if self._symm is not None else "nccl all_reduce"
+        if self._symm is None:
+            return "nccl all_reduce"
+        return "nvls two-shot kernels (libscgr): dense small blocks + row-sparse dL/dSH" if self._sparse() else \
+            "nvls two-shot kernel (libscgr), dense"
+
+    def _sparse(self) -> bool:
+        return self.row_floats > 0 and os.environ.get("SCGR_ALLREDUCE_SPARSE", "1") != "0"
 
     def all_reduce(self, group: Optional[dist.ProcessGroup] = None, async_op: bool = False):
         """THE collective of the path: one SUM all-reduce over the flat buffer."""
@@ -116,12 +142,21 @@ class FlatGradBuffer:
             from . import _lib
             hdl = self._symm
             stream = C.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
+            lib = _lib.load()
+            rank, world = int(hdl.rank), int(hdl.world_size)
             hdl.barrier(channel=0)           # every replica has been written by its rank's backward
             # multicast address of flat[0]: same offset from the multicast base as from this rank's own mapping
-            mc = int(hdl.multicast_ptr) + (self.flat.data_ptr() - int(hdl.buffer_ptrs[int(hdl.rank)]))
-            _lib.check(_lib.load().scgr_nvls_allreduce(C.c_void_p(mc), self.flat.numel(),
-                                                       int(hdl.rank), int(hdl.world_size), stream))
-            hdl.barrier(channel=1)           # every shard has been broadcast
+            mc = int(hdl.multicast_ptr) + (self.flat.data_ptr() - int(hdl.buffer_ptrs[rank]))
+            if not self._sparse():
+                _lib.check(lib.scgr_nvls_allreduce(C.c_void_p(mc), self.flat.numel(), rank, world, stream))
+            else:
+                # shot A (dense): the small blocks, the statistics and the live counts
+                _lib.check(lib.scgr_nvls_allreduce(C.c_void_p(mc), self.dense_floats, rank, world, stream))
+                hdl.barrier(channel=1)       # the summed live counts are in place on every rank
+                # shot B (row-sparse): dL/dSH rows of the Gaussians that are live on some rank
+                _lib.check(lib.scgr_nvls_allreduce_rows(C.c_void_p(mc + 4 * self.rows_offset), self.views["live"].data_ptr(),
+                                                        self.P, self.row_floats, rank, world, stream))
+            hdl.barrier(channel=2)           # every shard has been broadcast
             return None
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 

@@ -197,7 +197,8 @@ def rasterize_backward_raw(state: ForwardState, means3D, opacities, sh, colors_p
     """Runs scgr_backward.  `out` may hold pre-allocated gradient tensors (e.g. views into one flat
     all-reduce buffer, scgaussian_b200/parallel.py); missing ones are allocated.  Every returned
     tensor is fully written by the kernels.  out["stats"] ([P,2], optional) receives the two per-view
-    densification terms of reference scene/gaussian_model.py:932-934.  accumulate=True ADDS the parameter
+    densification terms of reference scene/gaussian_model.py:932-934, out["live"] ([P], optional) 1 / 0 per Gaussian that
+    did / did not receive any gradient (what the row-sparse all-reduce keys on).  accumulate=True ADDS the parameter
     gradients (and the statistics) to what `out` holds -- gradient accumulation over the views a rank renders
     before the batch's single all-reduce; it needs every gradient tensor to be passed in."""
     global launch_counter
@@ -237,6 +238,9 @@ def rasterize_backward_raw(state: ForwardState, means3D, opacities, sh, colors_p
             assert stats.is_contiguous() and stats.dtype == torch.float32 and tuple(stats.shape) == (P, 2), "stats"
             if state.radii is None:
                 raise ScgrError("densification statistics need the forward's radii (ForwardState.radii)")
+        live = out.get("live")
+        if live is not None:
+            assert live.is_contiguous() and live.dtype == torch.float32 and live.numel() == P, "live"
         if accumulate and missing:
             raise ScgrError(f"accumulate=True needs the gradient tensors to add into: {missing} not in `out`")
         if P == 0:
@@ -244,7 +248,8 @@ def rasterize_backward_raw(state: ForwardState, means3D, opacities, sh, colors_p
         view = _make_view(s, device, keep)
         g = _make_gaussians(means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp)
         grads = ScgrGrads(_ptr(gm3), _ptr(gm2), _ptr(gsh), _ptr(gcol), _ptr(gop), _ptr(gsc), _ptr(grot), _ptr(gcov),
-                          _ptr(stats), _ptr(state.radii) if stats is not None else None, int(bool(accumulate)))
+                          _ptr(stats), _ptr(state.radii) if stats is not None else None, int(bool(accumulate)),
+                          _ptr(live))
         gc = _f32c(grad_color, device)
         gd = _f32c(grad_depth, device)
         ga = _f32c(grad_alpha, device)

@@ -161,8 +161,8 @@ def build_preprocess() -> str:
         body = _replace_fn_body(body, name, new)
     assert "asm" not in body, "render.cu: an inline-PTX statement is not covered by _RENDER_PTX"
     # the variant switches are read once per process in the product; the tests flip them between launches
-    body, n = re.subn(r"static const int (minb|tma) = env_int", r"const int \1 = env_int", body)
-    assert n == 4, n
+    body, n = re.subn(r"static const int (minb|tma|packed) = env_int", r"const int \1 = env_int", body)
+    assert n == 5, n
     body = body.replace("int env_int(const char* name, int dflt) {", "int env_int_render(const char* name, int dflt) {").replace(
         "env_int(", "env_int_render(").replace("int env_int_render_render(", "int env_int_render(")
     with open(os.path.join(OUT_DIR, "render_body.inc"), "w") as f:
@@ -237,6 +237,8 @@ def build_full() -> str:
                     f'#include "common_host.cuh"\n#include "{n}_body.inc"\n')
             if n == "capi":     # the one launcher that is not emulated: NVSwitch multicast PTX
                 f.write("namespace scgr { void launch_nvls_allreduce(void*, size_t, int, int, const Launch&) {\n"
+                        '    throw std::runtime_error("scgr: the NVLS collective is not part of the host emulation"); }\n'
+                        "void launch_nvls_allreduce_rows(void*, const float*, long long, int, int, int, const Launch&) {\n"
                         '    throw std::runtime_error("scgr: the NVLS collective is not part of the host emulation"); } }\n')
         obj = os.path.join(OUT_DIR, f"tu_{n}{'_asan' if ASAN else ''}.o")
         subprocess.check_call([gxx, "-O1", "-std=c++20", "-pthread", "-fPIC", "-ffp-contract=off", "-w", *extra, "-c", "-o", obj, tu],

@@ -34,7 +34,9 @@ def _worker(rank, world, port, out_dir):
         radii, g = _view_grads(rank)
         out = buf.out_dict()
         for k in out:                      # what scgr_backward does on the GPU: fill the views in place
-            if k != "stats":
+            if k == "live":                # ScgrGrads.live_count: 1 where the view gave the Gaussian any gradient
+                out[k].copy_(torch.from_numpy((g["opacities"][:, 0] != 0).astype("float32")))
+            elif k != "stats":
                 out[k].copy_(torch.from_numpy(g[k]).reshape(out[k].shape))
         buf.fill_stats(torch.from_numpy(radii))
         buf.all_reduce()
@@ -60,6 +62,8 @@ def test_flat_allreduce_equals_sum_of_view_gradients(tmp_path):
                 vis = torch.from_numpy(radii > 0).float()
                 t[:, 0] += torch.linalg.vector_norm(torch.from_numpy(g["means2D"])[:, :2], dim=-1) * vis
                 t[:, 1] += vis
+            elif k == "live":
+                t += torch.from_numpy((g["opacities"][:, 0] != 0).astype("float32"))
             else:
                 t += torch.from_numpy(g[k]).reshape(t.shape)
     np.testing.assert_allclose(flats[0], ref.flat.numpy(), rtol=1e-6, atol=1e-9)
@@ -68,9 +72,11 @@ def test_flat_allreduce_equals_sum_of_view_gradients(tmp_path):
 
 def test_flat_buffer_layout():
     b = FlatGradBuffer(10, sh_coeffs=16, device="cpu")
-    assert [n for n, _ in b.fields] == ["means3D", "shs", "opacities", "scales", "rotations", "stats"]
-    assert b.flat.numel() >= 10 * (3 + 48 + 1 + 3 + 4 + 2)
+    assert [n for n, _ in b.fields] == ["means3D", "opacities", "scales", "rotations", "stats", "live", "shs"]
+    assert b.flat.numel() >= 10 * (3 + 48 + 1 + 3 + 4 + 2 + 1)
+    assert b.dense_floats % 4 == 0 and b.rows_offset == b.dense_floats and b.row_floats == 48     # the row-sparse shot's block
     for v in b.views.values():
         assert v.is_contiguous() and v.data_ptr() % 16 == 0
     b2 = FlatGradBuffer(10, use_sh=False, use_cov=True, device="cpu", with_stats=False)
-    assert [n for n, _ in b2.fields] == ["means3D", "colors_precomp", "opacities", "cov3D_precomp"]
+    assert [n for n, _ in b2.fields] == ["means3D", "colors_precomp", "opacities", "cov3D_precomp", "live"]
+    assert b2.row_floats == 0                     # no SH block: the whole buffer goes through the dense shot

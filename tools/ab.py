@@ -14,12 +14,13 @@ for v in variants:
         k, val = kv.split("=")
         env[k] = val
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "10", "--warmup", "3",
-                          "--no-e2e", "--no-cpu-baseline"], env=env, capture_output=True, text=True)
+                          "--no-e2e", "--no-cpu-baseline", "--no-train-step", "--no-standin", "--no-batch8"],
+                         env=env, capture_output=True, text=True)
     line = [l for l in out.stdout.splitlines() if l.startswith("{")]
     if not line:
         print("FAILED", v, out.stderr[-2000:])
         continue
     d = json.loads(line[-1])
     rows[v] = d
-    print(f"== [{v}] {d['value']:.1f} views/s  {d['ms_per_step']:.3f} ms/step  R={d['config']['num_rendered_R']}")
+    print(f"== [{v}] {d['value']:.1f} views/s  {d['ms_per_step']:.3f} ms/step  R={d['config']['num_rendered_R_mean']:.0f}")
     print("   " + "  ".join(f"{k}={x['ms_per_step']*1000:.0f}us" for k, x in d["kernels"].items()))
