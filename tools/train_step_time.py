@@ -164,7 +164,9 @@ def main():
     from scgaussian_b200 import synthetic as O  # SURVEY 8d seeded synthetic scene
     dev = torch.device("cuda", 0)
     P, W, H = int(os.environ.get("P", 1_000_000)), 1920, 1080
-    res = measure(O.synth_scene(P, W, H, sh_degree=3, scale_median=0.01, seed=0), O.make_camera(W, H), dev, W, H)
+    variants = tuple(os.environ.get("VARIANTS", "fused,torch").split(","))
+    res = measure(O.synth_scene(P, W, H, sh_degree=3, scale_median=0.01, seed=0), O.make_camera(W, H), dev, W, H,
+                  steps=int(os.environ.get("STEPS", 20)), warm=int(os.environ.get("WARM", 5)), variants=variants)
     print(json.dumps(res))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "train_step.json"), "w"), indent=1)
