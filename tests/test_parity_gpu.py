@@ -477,6 +477,43 @@ def test_back_to_back_views_without_host_sync(dev, monkeypatch):
     report("back_to_back", R_A=int(refA[4].num_rendered), R_B=int(refB[4].num_rendered))
 
 
+def test_async_binning_never_blocks_and_matches(dev, monkeypatch):
+    """SCGR_BINNING=async: both stages enqueued blind, no host wait; same images as the blocking protocols while R
+    fits the headroom; a view that outgrows it is dropped LOUDLY (NaN images, zero gradients, counter) and the next
+    view of that size fits."""
+    from scgaussian_b200 import rasterizer as R
+    A = util.make_case(4000, 160, 120, scale_median=0.05)
+    B = util.make_case(60000, 160, 120, scale_median=0.05, seed=3)          # ~15x the instances of A
+    sA, sB = settings_for(A, dev), settings_for(B, dev)
+    t = lambda c: tuple(c[k].to(dev).contiguous() if k else None
+                        for k in ("means3D", "opacities", "shs", None, "scales", "rotations", None))      # noqa: E731
+    aA, aB = t(A), t(B)
+    monkeypatch.setattr(R, "_BINNING_MODE", "sync")
+    refA, refB = R.rasterize_forward_raw(*aA, sA), R.rasterize_forward_raw(*aB, sB)
+    torch.cuda.synchronize()
+    monkeypatch.setattr(R, "_BINNING_MODE", "async")
+    R._capacity_hint[dev.index] = refA[4].num_rendered
+    R._status_buffer(dev).zero_()
+    dropped0 = R.dropped_views
+    for _ in range(3):
+        out = R.rasterize_forward_raw(*aA, sA)
+        assert out[4].num_rendered == -1 and torch.equal(out[0], refA[0]) and torch.equal(out[2], refA[2])
+    gC, gD, gA = [x.to(dev) for x in O.synth_upstream_grads(160, 120)]
+    g_ref = R.rasterize_backward_raw(refA[4], *aA, sA, gC, gD, gA)
+    g_async = R.rasterize_backward_raw(out[4], *aA, sA, gC, gD, gA)
+    for k in g_ref:
+        util.assert_grad_close(k, g_async[k].cpu().numpy(), g_ref[k].cpu().numpy(), None, rtol=1e-4)
+    R._capacity_hint[dev.index] = 1000                       # a stale, far too small hint: the big view cannot fit 2x + 64k
+    big = R.rasterize_forward_raw(*aB, sB)
+    assert bool(torch.isnan(big[0]).all())                   # dropped: NaN images ...
+    gb = R.rasterize_backward_raw(big[4], *aB, sB, gC, gD, gA)
+    assert all(float(v.abs().max()) == 0.0 for v in gb.values())      # ... and zero gradients
+    torch.cuda.synchronize()
+    again = R.rasterize_forward_raw(*aB, sB)                 # the hint has caught up (R was reported by the dropped view)
+    assert R.dropped_views == dropped0 + 1
+    assert torch.equal(again[0], refB[0])
+
+
 def test_binning_capacity_overflow_is_recovered(dev, monkeypatch):
     from scgaussian_b200 import rasterizer as R
     case = util.make_case(4000, 160, 120, scale_median=0.05)
