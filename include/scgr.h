@@ -182,6 +182,50 @@ int scgr_photometric_backward(const float* image, const float* gt, int32_t C, in
                               float lambda_dssim, const void* scratch, const float* upstream,
                               float* dL_dimage, scgr_stream_t stream);
 
+/* ---- BASELINE config 5's loss path: the match-prior loss on the rendered depth ----
+ * reference scene/gaussian_model.py:241-282 `GaussianModel.get_matchloss_from_renderdepth(cam0, depth0, loss_state)`,
+ * called by reference train.py:164-165 (`loss += render_match_loss * 0.3`).  For the rendered view and each other view
+ * (one ScgrMatchPair): match_depth = grid_sample(depth, uv0 / (width, height) * 2 - 1)  (bilinear, zeros padding,
+ * align_corners False);  world = rays_o + rays_d * (match_depth / cam_rays_d.z);  xyz = intr1 (w2c1 [world; 1]);
+ * xy = xyz[:2] / (xyz[2] + 1e-8);  inside = 0 < xy < (width, height);
+ * pair loss = sum(mean_xy(|xy - uv1| / (width, height)) * inside * valid) / (sum(inside * valid) + 1e-8);
+ * out[0] = sum over the pairs.  All arrays device fp32; matrices by value (row-major).  `scratch`: 8 floats (device)
+ * written by the forward and read by the backward.  The backward zero-fills dL_ddepth [H,W] and scatters
+ * upstream * d loss / d depth into it (`upstream` a device scalar, NULL = 1). */
+#define SCGR_MATCH_MAX_PAIRS 8
+typedef struct ScgrMatchPair {
+    int32_t n;                 /* matches of this pair */
+    const float* uv0;          /* [n,2] matched pixels in the rendered view (match_data["uv"]) */
+    const float* rays_o;       /* [n,3] */
+    const float* rays_d;       /* [n,3] */
+    const float* cam_rays_d;   /* [n,3] (z is used) */
+    const float* uv1;          /* [n,2] the same matches in the other view */
+    const float* valid;        /* [n] blender_mask0 * blender_mask1 (> 0 counts), or NULL: all valid */
+    float w2c1[12];            /* rows 0..2 of the other view's world-to-camera matrix */
+    float intr1[9];            /* the other view's 3x3 intrinsics */
+} ScgrMatchPair;
+int scgr_match_loss_forward(const float* depth, int32_t H, int32_t W, float width, float height, const ScgrMatchPair* pairs,
+                            int32_t n_pairs, float* scratch, float* out, scgr_stream_t stream);
+int scgr_match_loss_backward(const float* depth, int32_t H, int32_t W, float width, float height, const ScgrMatchPair* pairs,
+                             int32_t n_pairs, const float* scratch, const float* upstream, float* dL_ddepth,
+                             scgr_stream_t stream);
+
+/* ---- SURVEY.md section 8(f) row f1, second half: the DTU background term of reference train.py:150-158, :167-168 ----
+ * scgr_bg_mask: mask[y,x] = 1 where max_c gt[c,y,x] < threshold for the pixel AND the (window - 1) pixels above it in
+ * its column that exist (the reference's `for i in range(1, 50): bg_mask[:, i:] *= bg_mask_clone[:, :-i]`, window 50);
+ * gt [C,H,W] is zeroed IN PLACE where masked (`gt_image[bg_mask.repeat(3,1,1)] = 0.`); count[0] (device float) receives
+ * the number of masked pixels.  mask: uint8 [H,W] (a torch.bool tensor's storage).
+ * scgr_masked_mean_forward: out2 = {values[mask].mean(), count}  (`rendered_alpha[bg_mask].mean()`; NaN for an empty
+ * mask, as torch); scratch from scgr_masked_mean_scratch_bytes(n), 256-byte aligned.
+ * scgr_masked_mean_backward: dL_dvalues[i] = mask[i] ? upstream / count : 0  (upstream a device scalar, NULL = 1). */
+int scgr_bg_mask(float* gt, int32_t C, int32_t H, int32_t W, float threshold, int32_t window, uint8_t* mask, float* count,
+                 scgr_stream_t stream);
+size_t scgr_masked_mean_scratch_bytes(int64_t n);
+int scgr_masked_mean_forward(const float* values, const uint8_t* mask, int64_t n, void* scratch, float* out2,
+                             scgr_stream_t stream);
+int scgr_masked_mean_backward(const uint8_t* mask, int64_t n, const float* out2, const float* upstream, float* dL_dvalues,
+                              scgr_stream_t stream);
+
 /* ---- the path's single collective (sum of the per-view gradients over the ranks) as
  * a two-shot all-reduce through NVSwitch multicast: rank r reduces its 1/world of the buffer with
  * multimem.ld_reduce (in-switch fp32 sum of the replicas) and broadcasts it with multimem.st.

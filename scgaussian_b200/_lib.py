@@ -41,6 +41,15 @@ class ScgrDebugViews(C.Structure):
                 ("final_T", C.c_void_p), ("num_rendered", C.c_void_p)]
 
 
+class ScgrMatchPair(C.Structure):
+    _fields_ = [("n", C.c_int32), ("uv0", C.c_void_p), ("rays_o", C.c_void_p), ("rays_d", C.c_void_p),
+                ("cam_rays_d", C.c_void_p), ("uv1", C.c_void_p), ("valid", C.c_void_p), ("w2c1", C.c_float * 12),
+                ("intr1", C.c_float * 9)]
+
+
+MATCH_MAX_PAIRS = 8    # SCGR_MATCH_MAX_PAIRS (include/scgr.h)
+
+
 class ScgrModelSet(C.Structure):
     _fields_ = [("n", C.c_int32), ("xyz", C.c_void_p), ("rayo", C.c_void_p), ("rayd", C.c_void_p),
                 ("zval", C.c_void_p), ("scaling", C.c_void_p), ("rotation", C.c_void_p), ("opacity", C.c_void_p),
@@ -111,6 +120,15 @@ SYMBOLS = {
                                            C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "scgr_photometric_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scgr_match_loss_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.POINTER(ScgrMatchPair),
+                                          C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scgr_match_loss_backward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.POINTER(ScgrMatchPair),
+                                           C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scgr_bg_mask": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_void_p,
+                               C.c_void_p]),
+    "scgr_masked_mean_scratch_bytes": (C.c_size_t, [C.c_int64]),
+    "scgr_masked_mean_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scgr_masked_mean_backward": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scgr_nvls_allreduce": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p]),
     "scgr_nvls_allreduce_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "scgr_knn3_mean_dist2": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),

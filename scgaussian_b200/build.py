@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libscgr.so")
-SOURCES = ["capi.cu", "preprocess.cu", "binning.cu", "render.cu", "loss.cu", "collective.cu", "knn.cu", "model.cu"]
+SOURCES = ["capi.cu", "preprocess.cu", "binning.cu", "render.cu", "loss.cu", "collective.cu", "knn.cu", "model.cu", "prior.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(_HERE, "..", "include", "scgr.h")]
 
 NVCC_FLAGS = [

@@ -385,6 +385,69 @@ int scgr_photometric_backward(const float* image, const float* gt, int32_t C, in
     });
 }
 
+int scgr_match_loss_forward(const float* depth, int32_t H, int32_t W, float width, float height, const ScgrMatchPair* pairs,
+                            int32_t n_pairs, float* scratch, float* out, scgr_stream_t stream) {
+    return guarded([&] {
+        require(H > 0 && W > 0 && width > 0.f && height > 0.f, "match loss: empty image");
+        require(n_pairs >= 0 && n_pairs <= SCGR_MATCH_MAX_PAIRS, "match loss: 0..SCGR_MATCH_MAX_PAIRS pairs per call");
+        require(depth && scratch && out && (pairs || n_pairs == 0), "match loss: null argument");
+        for (int i = 0; i < n_pairs; i++) {
+            require(pairs[i].n >= 0, "match loss: negative match count");
+            if (pairs[i].n > 0)
+                require(pairs[i].uv0 && pairs[i].rays_o && pairs[i].rays_d && pairs[i].cam_rays_d && pairs[i].uv1,
+                        "match loss: null array in a pair");
+        }
+        const Launch L{(cudaStream_t)stream, false};
+        launch_match_loss_forward(depth, H, W, width, height, pairs, n_pairs, scratch, out, L);
+    });
+}
+
+int scgr_match_loss_backward(const float* depth, int32_t H, int32_t W, float width, float height, const ScgrMatchPair* pairs,
+                             int32_t n_pairs, const float* scratch, const float* upstream, float* dL_ddepth,
+                             scgr_stream_t stream) {
+    return guarded([&] {
+        require(H > 0 && W > 0 && width > 0.f && height > 0.f, "match loss: empty image");
+        require(n_pairs >= 0 && n_pairs <= SCGR_MATCH_MAX_PAIRS, "match loss: 0..SCGR_MATCH_MAX_PAIRS pairs per call");
+        require(depth && scratch && dL_ddepth && (pairs || n_pairs == 0), "match loss: null argument");
+        const Launch L{(cudaStream_t)stream, false};
+        launch_match_loss_backward(depth, H, W, width, height, pairs, n_pairs, scratch, upstream, dL_ddepth, L);
+    });
+}
+
+int scgr_bg_mask(float* gt, int32_t C, int32_t H, int32_t W, float threshold, int32_t window, uint8_t* mask, float* count,
+                 scgr_stream_t stream) {
+    return guarded([&] {
+        require(C > 0 && H > 0 && W > 0, "bg mask: empty image");
+        require(window >= 1, "bg mask: window must be >= 1");
+        require(gt && mask && count, "bg mask: null argument");
+        const Launch L{(cudaStream_t)stream, false};
+        launch_bg_mask(gt, C, H, W, threshold, window, mask, count, L);
+    });
+}
+
+size_t scgr_masked_mean_scratch_bytes(int64_t n) { return masked_mean_scratch_bytes(n > 0 ? (size_t)n : 1); }
+
+int scgr_masked_mean_forward(const float* values, const uint8_t* mask, int64_t n, void* scratch, float* out2,
+                             scgr_stream_t stream) {
+    return guarded([&] {
+        require(n > 0, "masked mean: empty input");
+        require(values && mask && scratch && out2, "masked mean: null argument");
+        require((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "masked mean: scratch must be 16-byte aligned");
+        const Launch L{(cudaStream_t)stream, false};
+        launch_masked_mean_forward(values, mask, (size_t)n, scratch, out2, L);
+    });
+}
+
+int scgr_masked_mean_backward(const uint8_t* mask, int64_t n, const float* out2, const float* upstream, float* dL_dvalues,
+                              scgr_stream_t stream) {
+    return guarded([&] {
+        require(n > 0, "masked mean: empty input");
+        require(mask && out2 && dL_dvalues, "masked mean: null argument");
+        const Launch L{(cudaStream_t)stream, false};
+        launch_masked_mean_backward(mask, (size_t)n, out2, upstream, dL_dvalues, L);
+    });
+}
+
 int scgr_nvls_allreduce(void* multicast_ptr, size_t n_floats, int32_t rank, int32_t world, scgr_stream_t stream) {
     return guarded([&] {
         require(multicast_ptr != nullptr, "nvls all-reduce: null multicast pointer");

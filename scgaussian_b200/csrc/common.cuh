@@ -302,6 +302,17 @@ void launch_photometric_forward(const float* img, const float* gt, int C, int H,
 void launch_photometric_backward(const float* img, const float* gt, int C, int H, int W, float lambda,
                                  const void* scratch, const float* upstream, float* dL_dimg, const Launch& L);
 
+// match-prior loss, DTU background term (prior.cu)
+void launch_match_loss_forward(const float* depth, int H, int W, float width, float height, const ScgrMatchPair* pairs,
+                               int n_pairs, float* scratch, float* out, const Launch& L);
+void launch_match_loss_backward(const float* depth, int H, int W, float width, float height, const ScgrMatchPair* pairs,
+                                int n_pairs, const float* scratch, const float* upstream, float* dL_ddepth, const Launch& L);
+void launch_bg_mask(float* gt, int C, int H, int W, float threshold, int window, uint8_t* mask, float* count, const Launch& L);
+size_t masked_mean_scratch_bytes(size_t n);
+void launch_masked_mean_forward(const float* values, const uint8_t* mask, size_t n, void* scratch, float* out2, const Launch& L);
+void launch_masked_mean_backward(const uint8_t* mask, size_t n, const float* out2, const float* upstream, float* dL_dvalues,
+                                 const Launch& L);
+
 // Every kernel launch is bracketed:  begin_kernel(name, L); kernel<<<...>>>(...); check_launch(name, L);
 // begin_kernel records a start event when profiling is on (scgr_profile_enable); check_launch
 // counts the launch, records the stop event, and turns CUDA errors into std::runtime_error

@@ -184,14 +184,14 @@ LIB_LOSS = os.path.join(OUT_DIR, "libemu_loss_knn" + _SUFFIX)
 
 
 def build_loss_knn() -> str:
-    srcs = [os.path.join(CSRC, "loss.cu"), os.path.join(CSRC, "knn.cu")]
+    srcs = [os.path.join(CSRC, "loss.cu"), os.path.join(CSRC, "knn.cu"), os.path.join(CSRC, "prior.cu")]
     deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "host_cuda_shim.h"),
                    os.path.join(HERE, "emu_loss_knn.cpp"), __file__, os.path.join(ROOT, "include", "scgr.h")]
     if os.path.exists(LIB_LOSS) and all(os.path.getmtime(d) <= os.path.getmtime(LIB_LOSS) for d in deps):
         return LIB_LOSS
     os.makedirs(OUT_DIR, exist_ok=True)
     _common_host()
-    for src, name, n in ((srcs[0], "loss_body.inc", 3), (srcs[1], "knn_body.inc", 1)):
+    for src, name, n in ((srcs[0], "loss_body.inc", 3), (srcs[1], "knn_body.inc", 1), (srcs[2], "prior_body.inc", 6)):
         body = open(src).read().replace('#include "common.cuh"', "")
         with open(os.path.join(OUT_DIR, name), "w") as f:
             f.write(_rewrite_launches(body, n))
@@ -206,7 +206,7 @@ def build_full() -> str:
     """The WHOLE library on the host behind its real C entry points -- capi.cu included -- with every exported symbol
     renamed scgr_* -> emu_scgr_* so that nothing but a test can bind it (scgaussian_b200/_lib.py resolves scgr_* names
     only: this file cannot stand in for libscgr.so).  One translation unit per .cu file, as in the product build."""
-    names = ["capi", "preprocess", "binning", "render", "loss", "knn", "model"]
+    names = ["capi", "preprocess", "binning", "render", "loss", "knn", "model", "prior"]
     srcs = [os.path.join(CSRC, n + ".cu") for n in names]
     header = os.path.join(ROOT, "include", "scgr.h")
     deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "host_cuda_shim.h"), __file__, header]

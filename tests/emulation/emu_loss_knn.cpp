@@ -16,6 +16,7 @@ void check_stage(const char*, const Launch&) {}
 
 #include "_build/loss_body.inc"
 #include "_build/knn_body.inc"
+#include "_build/prior_body.inc"
 
 static const scgr::Launch kHost{nullptr, false};
 
@@ -32,4 +33,27 @@ int emu_photometric_backward(const float* img, const float* gt, int C, int H, in
     return 0;
 }
 int emu_knn3(const float* points, int32_t n, float* out) { scgr::launch_knn3(points, n, out, kHost); return 0; }
+int emu_match_loss_forward(const float* depth, int H, int W, float width, float height, const ScgrMatchPair* pairs, int n_pairs,
+                           float* scratch, float* out) {
+    scgr::launch_match_loss_forward(depth, H, W, width, height, pairs, n_pairs, scratch, out, kHost);
+    return 0;
+}
+int emu_match_loss_backward(const float* depth, int H, int W, float width, float height, const ScgrMatchPair* pairs, int n_pairs,
+                            const float* scratch, const float* upstream, float* dL_ddepth) {
+    scgr::launch_match_loss_backward(depth, H, W, width, height, pairs, n_pairs, scratch, upstream, dL_ddepth, kHost);
+    return 0;
+}
+int emu_bg_mask(float* gt, int C, int H, int W, float threshold, int window, uint8_t* mask, float* count) {
+    scgr::launch_bg_mask(gt, C, H, W, threshold, window, mask, count, kHost);
+    return 0;
+}
+size_t emu_masked_mean_scratch_bytes(long long n) { return scgr::masked_mean_scratch_bytes((size_t)n); }
+int emu_masked_mean_forward(const float* values, const uint8_t* mask, long long n, void* scratch, float* out2) {
+    scgr::launch_masked_mean_forward(values, mask, (size_t)n, scratch, out2, kHost);
+    return 0;
+}
+int emu_masked_mean_backward(const uint8_t* mask, long long n, const float* out2, const float* upstream, float* dL_dvalues) {
+    scgr::launch_masked_mean_backward(mask, (size_t)n, out2, upstream, dL_dvalues, kHost);
+    return 0;
+}
 }
