@@ -207,6 +207,7 @@ __device__ __forceinline__ void stage_dup(float4* s_dup, const int lane, const R
 // halves each, tiles [n8 + n4, n8 + n4 + n2) as four quarters each.
 struct WorkSplit {
     int n8, n4, n2;
+    int deep_first;     // backward only: the n2 / n4 tiles cut in quarters / halves are the DEEPEST of the longest-first order
     int items() const { return n8 + 2 * n4 + 4 * n2; }
 };
 
@@ -985,23 +986,32 @@ render_backward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __res
     if (status[0] > capacity) return;
     int b = blockIdx.x;
     // work item -> tile through the longest-first permutation built from the forward's per-tile depths
+    // work item -> (position in the longest-first order, first slot, slots): whole tiles first and the cut ones last, or
+    // (deep_first) the deepest tiles cut in quarters / halves first: their walks are the critical path of the launch
+    int ord, k0, spw;
+    if (!ws.deep_first) {
+        if (b < ws.n8) { ord = b; k0 = 0; spw = 8; }
+        else if ((b -= ws.n8) < 2 * ws.n4) { ord = ws.n8 + (b >> 1); k0 = (b & 1) << 2; spw = 4; }
+        else { b -= 2 * ws.n4; ord = ws.n8 + ws.n4 + (b >> 2); k0 = (b & 3) << 1; spw = 2; }
+    } else {
+        if (b < 4 * ws.n2) { ord = b >> 2; k0 = (b & 3) << 1; spw = 2; }
+        else if ((b -= 4 * ws.n2) < 2 * ws.n4) { ord = ws.n2 + (b >> 1); k0 = (b & 1) << 2; spw = 4; }
+        else { b -= 2 * ws.n4; ord = ws.n2 + ws.n4 + b; k0 = 0; spw = 8; }
+    }
+    const int tile = (int)tile_order[ord];
     if constexpr (PK) {
 #define SCGR_ARGS s_rec, s_dup, s_id, s_bar, s_g4, ranges, point_list, rec, W, H, bg, n_contrib, final_T, dL_dcolor, dL_ddepth, \
                   dL_dalpha, screen_grad
-        if (b < ws.n8) { backward_region_packed<8, TMA>((int)tile_order[b], tiles_x, 0, SCGR_ARGS); return; }
-        b -= ws.n8;
-        if (b < 2 * ws.n4) { backward_region_packed<4, TMA>((int)tile_order[ws.n8 + (b >> 1)], tiles_x, (b & 1) << 2, SCGR_ARGS); return; }
-        b -= 2 * ws.n4;
-        backward_region_packed<2, TMA>((int)tile_order[ws.n8 + ws.n4 + (b >> 2)], tiles_x, (b & 3) << 1, SCGR_ARGS);
+        if (spw == 8) backward_region_packed<8, TMA>(tile, tiles_x, k0, SCGR_ARGS);
+        else if (spw == 4) backward_region_packed<4, TMA>(tile, tiles_x, k0, SCGR_ARGS);
+        else backward_region_packed<2, TMA>(tile, tiles_x, k0, SCGR_ARGS);
 #undef SCGR_ARGS
     } else {
 #define SCGR_ARGS s_rec, s_id, s_bar, s_g4, ranges, point_list, rec, W, H, bg, n_contrib, final_T, dL_dcolor, dL_ddepth, \
                   dL_dalpha, screen_grad
-        if (b < ws.n8) { backward_region<8, TMA>((int)tile_order[b], tiles_x, 0, SCGR_ARGS); return; }
-        b -= ws.n8;
-        if (b < 2 * ws.n4) { backward_region<4, TMA>((int)tile_order[ws.n8 + (b >> 1)], tiles_x, (b & 1) << 2, SCGR_ARGS); return; }
-        b -= 2 * ws.n4;
-        backward_region<2, TMA>((int)tile_order[ws.n8 + ws.n4 + (b >> 2)], tiles_x, (b & 3) << 1, SCGR_ARGS);
+        if (spw == 8) backward_region<8, TMA>(tile, tiles_x, k0, SCGR_ARGS);
+        else if (spw == 4) backward_region<4, TMA>(tile, tiles_x, k0, SCGR_ARGS);
+        else backward_region<2, TMA>(tile, tiles_x, k0, SCGR_ARGS);
 #undef SCGR_ARGS
     }
 }
@@ -1103,6 +1113,7 @@ WorkSplit make_split(const int n_tiles, const char* env, const int dflt_half, co
     else if (n_tiles < 16 * sm_count) { ph = 100; pq = 0; }
     if (const char* e = getenv(env)) sscanf(e, "%d,%d", &ph, &pq);
     WorkSplit ws;
+    ws.deep_first = 0;
     ws.n2 = (int)((int64_t)n_tiles * pq / 100);
     ws.n4 = (int)((int64_t)n_tiles * ph / 100);
     if (ws.n2 + ws.n4 > n_tiles) { ws.n2 = 0; ws.n4 = n_tiles; }
@@ -1145,7 +1156,18 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
     // warps per SM fit without rematerialisation: 450 us vs 464 us for register prefetch at 16 warps
     static const int minb = env_int("SCGR_BWD_MINB", 18);
     static const int tma = env_int("SCGR_TMA_BWD", env_int("SCGR_TMA", 1));
-    const WorkSplit ws = make_split(tx * ty, "SCGR_BWD_SPLIT", 0, 0);
+    WorkSplit ws = make_split(tx * ty, "SCGR_BWD_SPLIT", 0, 0);
+    // SCGR_BWD_DEEP="h,q": cut the DEEPEST q % of the tiles in quarters and the next h % in halves instead
+    if (const char* e = getenv("SCGR_BWD_DEEP")) {
+        int ph = 0, pq = 0;
+        sscanf(e, "%d,%d", &ph, &pq);
+        const int n = tx * ty;
+        ws.n2 = (int)((int64_t)n * pq / 100);
+        ws.n4 = (int)((int64_t)n * ph / 100);
+        if (ws.n2 + ws.n4 > n) { ws.n2 = 0; ws.n4 = n; }
+        ws.n8 = n - ws.n4 - ws.n2;
+        ws.deep_first = 1;
+    }
     {
         const size_t zero_f4 = (size_t)(P > 0 ? P : 0) * (sizeof(ScreenGrad) / sizeof(float4));
         const unsigned zero_ctas = (unsigned)((zero_f4 + ZERO_F4_PER_CTA - 1) / ZERO_F4_PER_CTA);

@@ -34,6 +34,9 @@ def build() -> str:
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
     body = open(SRC).read().replace('#include "common.cuh"', "")
+    body = _replace_fn_body(body, "sqrt_approx", "return sqrtf(x);")       # model.cu's two inline-PTX helpers (Adam)
+    body = _replace_fn_body(body, "div_approx", "return a / b;")
+    assert "asm" not in body
     with open(os.path.join(OUT_DIR, "model_body.inc"), "w") as f:
         f.write(_rewrite_launches(body, 9))
     _compile(LIB, "emu_model.cpp")
