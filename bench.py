@@ -420,6 +420,7 @@ def main():
                     flat.views[name].copy_(v.grad.reshape(flat.views[name].shape))
                 flat.means2D.copy_(m2d.grad)
                 flat.fill_stats(radii)
+                flat.fill_live(leaves["opacities"].grad, leaves["means3D"].grad)      # autograd path: live counts from the gradients
                 flat.all_reduce()
             m2d.grad = None
             consumed[b].record(cur)

@@ -67,7 +67,7 @@ typedef struct ScgrView {
 } ScgrView;
 
 /* The per-Gaussian inputs of GaussianRasterizer.forward (reference
- * gaussian_renderer/__init__.py:100-108).  Exactly one of shs / colors_precomp and exactly one
+ * gaussian_renderer/__init__.py:100-108).  Exactly one of shs / colors_precomp / (sh_dc, sh_rest) and exactly one
  * of (scales, rotations) / cov3D_precomp is non-NULL.  means2D is never read (it only exists on
  * the Python side as the gradient hook) and is therefore absent here. */
 typedef struct ScgrGaussians {
@@ -80,6 +80,14 @@ typedef struct ScgrGaussians {
     const float* scales;           /* [P,3] or NULL */
     const float* rotations;        /* [P,4] (r,x,y,z), used as given, or NULL */
     const float* cov3D_precomp;    /* [P,6] xx,xy,xz,yy,yz,zz or NULL */
+    /* SURVEY.md section 8(f) row f2, second half -- the SH coefficients read STRAIGHT from the hybrid model's four
+     * arrays (reference scene/gaussian_model.py:131-140 `get_features` cats them on every render): Gaussian i < sh_n0
+     * takes row i of set 0, Gaussian i >= sh_n0 row i - sh_n0 of set 1; coefficient 0 from sh_dc, 1.. from sh_rest.
+     * Selected by shs == NULL && colors_precomp == NULL with sh_dc[0] or sh_dc[1] non-NULL; needs sh_coeffs == 16.
+     * The 192 bytes per Gaussian that the assembled copy costs each way are never written or re-read. */
+    const float* sh_dc[2];         /* [n_k, 1, 3] or NULL for an empty set */
+    const float* sh_rest[2];       /* [n_k, 15, 3] */
+    int32_t sh_n0;                 /* size of set 0 */
 } ScgrGaussians;
 
 /* Gradients returned by _RasterizeGaussians.backward.  Every
@@ -108,6 +116,9 @@ typedef struct ScgrGrads {
      * is set): summed over the ranks it tells which rows of the gradient arrays are non-zero anywhere -- the rest need
      * not cross the NVSwitch (scgr_nvls_allreduce_rows). */
     float* live_count;
+    /* split SH layout (ScgrGaussians.sh_dc / sh_rest): the gradient rows go straight to the model's arrays, dL_dshs NULL */
+    float* dL_dsh_dc[2];       /* [n_k, 1, 3] */
+    float* dL_dsh_rest[2];     /* [n_k, 15, 3] */
 } ScgrGrads;
 
 int scgr_version(void);
@@ -281,14 +292,14 @@ typedef struct ScgrActivated {   /* the operator's inputs, P = set[0].n + set[1]
     float* scales;               /* [P,3] */
     float* rotations;            /* [P,4] */
     float* opacities;            /* [P,1] */
-    float* shs;                  /* [P,sh_rest+1,3] */
+    float* shs;                  /* [P,sh_rest+1,3], or NULL: the operator takes the split SH layout (ScgrGaussians.sh_dc / sh_rest) */
 } ScgrActivated;
 typedef struct ScgrActivatedGrads {   /* what scgr_backward produced (ScgrGrads), all required */
     const float* dL_dmeans3D;
     const float* dL_dscales;
     const float* dL_drotations;
     const float* dL_dopacities;
-    const float* dL_dshs;
+    const float* dL_dshs;        /* NULL with the split SH layout: scgr_backward wrote dL/dfeatures_* itself */
 } ScgrActivatedGrads;
 typedef struct ScgrModelSetGrads {    /* written in full for a set with n > 0 */
     float* dL_dxyz;              /* [n,3] free set only */

@@ -24,7 +24,7 @@ class ScgrGaussians(C.Structure):
     _fields_ = [("P", C.c_int32), ("sh_coeffs", C.c_int32),
                 ("means3D", C.c_void_p), ("opacities", C.c_void_p), ("shs", C.c_void_p),
                 ("colors_precomp", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
-                ("cov3D_precomp", C.c_void_p)]
+                ("cov3D_precomp", C.c_void_p), ("sh_dc", C.c_void_p * 2), ("sh_rest", C.c_void_p * 2), ("sh_n0", C.c_int32)]
 
 
 class ScgrGrads(C.Structure):
@@ -32,7 +32,8 @@ class ScgrGrads(C.Structure):
                 ("dL_dcolors_precomp", C.c_void_p), ("dL_dopacities", C.c_void_p),
                 ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p),
                 ("dL_dcov3D_precomp", C.c_void_p), ("densification_stats", C.c_void_p), ("radii", C.c_void_p),
-                ("accumulate", C.c_int32), ("live_count", C.c_void_p)]
+                ("accumulate", C.c_int32), ("live_count", C.c_void_p), ("dL_dsh_dc", C.c_void_p * 2),
+                ("dL_dsh_rest", C.c_void_p * 2)]
 
 
 class ScgrDebugViews(C.Structure):

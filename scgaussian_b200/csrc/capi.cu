@@ -70,12 +70,19 @@ static void validate(const ScgrView* v, const ScgrGaussians* g) {
     if (g->P == 0) return;
     require(v->bg && v->viewmatrix && v->projmatrix && v->campos, "null camera tensors");
     require(g->means3D && g->opacities, "null means3D / opacities");
-    require((g->shs != nullptr) != (g->colors_precomp != nullptr),
+    const bool split = g->sh_dc[0] != nullptr || g->sh_dc[1] != nullptr;
+    require((int)(g->shs != nullptr) + (int)(g->colors_precomp != nullptr) + (int)split == 1,
             "provide exactly one of shs / colors_precomp");
+    if (split) {
+        require(g->sh_coeffs == 16, "split SH arrays (sh_dc / sh_rest) need 16 coefficients per Gaussian");
+        require(g->sh_n0 >= 0 && g->sh_n0 <= g->P, "split SH arrays: sh_n0 out of range");
+        require(g->sh_n0 == 0 || (g->sh_dc[0] && g->sh_rest[0]), "split SH arrays: set 0 is missing");
+        require(g->sh_n0 == g->P || (g->sh_dc[1] && g->sh_rest[1]), "split SH arrays: set 1 is missing");
+    }
     const bool sr = g->scales != nullptr && g->rotations != nullptr;
     require(sr != (g->cov3D_precomp != nullptr) && (sr || (!g->scales && !g->rotations)),
             "provide exactly one of (scales, rotations) / cov3D_precomp");
-    if (g->shs) {
+    if (g->shs || split) {
         require(v->sh_degree >= 0 && v->sh_degree <= 3, "sh_degree must be 0..3");
         require(g->sh_coeffs >= (v->sh_degree + 1) * (v->sh_degree + 1), "shs has too few coefficients for sh_degree");
     }
@@ -325,6 +332,9 @@ int scgr_backward(const ScgrView* view, const ScgrGaussians* g, const void* geom
         require(dL_dcolor && dL_ddepth && dL_dalpha, "null upstream gradients");
         require(grads->dL_dmeans3D && grads->dL_dmeans2D && grads->dL_dopacities, "null gradient outputs");
         require((g->shs != nullptr) == (grads->dL_dshs != nullptr), "dL_dshs must match shs");
+        for (int k = 0; k < 2; k++)
+            require((g->sh_dc[k] != nullptr) == (grads->dL_dsh_dc[k] != nullptr) &&
+                    (g->sh_rest[k] != nullptr) == (grads->dL_dsh_rest[k] != nullptr), "dL_dsh_dc / dL_dsh_rest must match sh_dc / sh_rest");
         require((g->colors_precomp != nullptr) == (grads->dL_dcolors_precomp != nullptr), "dL_dcolors_precomp must match colors_precomp");
         require((g->scales != nullptr) == (grads->dL_dscales != nullptr) &&
                 (g->rotations != nullptr) == (grads->dL_drotations != nullptr), "dL_dscales / dL_drotations must match inputs");
@@ -508,9 +518,8 @@ int scgr_assemble_forward(const ScgrModel* model, const ScgrActivated* out, scgr
     return guarded([&] {
         validate_model(model);
         if (model->set[0].n + model->set[1].n == 0) return;
-        require(out && out->means3D && out->scales && out->rotations && out->opacities && out->shs,
-                "assemble: null output array");
-        require(aligned16(out->rotations) && aligned16(out->shs), "assemble: outputs must be 16-byte aligned");
+        require(out && out->means3D && out->scales && out->rotations && out->opacities, "assemble: null output array");
+        require(aligned16(out->rotations) && aligned16(out->shs), "assemble: outputs must be 16-byte aligned");      // (shs may be NULL: split SH layout)
         const Launch L{(cudaStream_t)stream, false};
         launch_assemble_forward(*model, *out, L);
     });
@@ -521,8 +530,8 @@ int scgr_assemble_backward(const ScgrModel* model, const ScgrActivatedGrads* gra
     return guarded([&] {
         validate_model(model);
         if (model->set[0].n + model->set[1].n == 0) return;
-        require(grads && grads->dL_dmeans3D && grads->dL_dscales && grads->dL_drotations && grads->dL_dopacities &&
-                    grads->dL_dshs, "assemble: null incoming gradient");
+        require(grads && grads->dL_dmeans3D && grads->dL_dscales && grads->dL_drotations && grads->dL_dopacities,
+                "assemble: null incoming gradient");      // (dL_dshs may be NULL: split SH layout)
         require(aligned16(grads->dL_drotations) && aligned16(grads->dL_dshs),
                 "assemble: incoming gradients must be 16-byte aligned");
         require(out != nullptr, "assemble: null gradient outputs");
@@ -531,9 +540,11 @@ int scgr_assemble_backward(const ScgrModel* model, const ScgrActivatedGrads* gra
             const ScgrModelSetGrads& d = out->set[k];
             if (s.n == 0) continue;
             require(s.rayo ? d.dL_dzval != nullptr : d.dL_dxyz != nullptr, "assemble: null position gradient output");
-            require(d.dL_dscaling && d.dL_drotation && d.dL_dopacity && d.dL_dfeatures_dc,
-                    "assemble: null gradient output");
-            require(model->sh_rest == 0 || d.dL_dfeatures_rest, "assemble: null dL_dfeatures_rest");
+            require(d.dL_dscaling && d.dL_drotation && d.dL_dopacity, "assemble: null gradient output");
+            if (grads->dL_dshs) {
+                require(d.dL_dfeatures_dc != nullptr, "assemble: null gradient output");
+                require(model->sh_rest == 0 || d.dL_dfeatures_rest, "assemble: null dL_dfeatures_rest");
+            }
             require(aligned16(d.dL_drotation), "assemble: dL_drotation must be 16-byte aligned");
         }
         const Launch L{(cudaStream_t)stream, false};

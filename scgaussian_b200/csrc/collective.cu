@@ -48,6 +48,9 @@ nvls_allreduce_kernel(float4* __restrict__ mc, const size_t first, const size_t 
         for (int u = 0; u < NVLS_UNROLL; u++) multimem_st(mc + first + i + u * stride, v[u]);
     }
     for (; i < count; i += stride) multimem_st(mc + first + i, multimem_ld_reduce_add(mc + first + i));
+    // the broadcast must have LANDED in every replica before the cross-rank barrier that follows this kernel lets a
+    // peer read it: the barrier's signal travels as a unicast store and may overtake multicast data still in the switch
+    __threadfence_system();
 }
 
 // ---- row-sparse variant: only the rows some rank actually wrote ----
@@ -112,6 +115,7 @@ nvls_allreduce_rows_kernel(float4* __restrict__ mc, const float* __restrict__ li
                 if (addr[u]) multimem_st(addr[u], v[u]);
         }
     }
+    __threadfence_system();      // (as above)
 }
 
 }  // namespace

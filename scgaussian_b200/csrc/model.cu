@@ -534,8 +534,11 @@ void launch_assemble_forward(const ScgrModel& m, const ScgrActivated& out, const
     const uint32_t n3k = 3u * (uint32_t)(m.sh_rest + 1);
     const uint64_t sh_total = P * n3k;
     const int staged = staged_rows(n3k);
-    const uint32_t sh_blocks = staged ? (uint32_t)((m.set[0].n + STAGE_G - 1) / STAGE_G + (m.set[1].n + STAGE_G - 1) / STAGE_G)
-                                      : sh_block_count(sh_total);
+    // out.shs == NULL: the operator reads the SH rows straight from features_dc / features_rest (ScgrGaussians.sh_dc /
+    // sh_rest, SURVEY 8f row f2 second half) -- no SH CTAs, 192 of the 236 assembled bytes per Gaussian never exist
+    const uint32_t sh_blocks = !out.shs ? 0u
+                               : staged ? (uint32_t)((m.set[0].n + STAGE_G - 1) / STAGE_G + (m.set[1].n + STAGE_G - 1) / STAGE_G)
+                                        : sh_block_count(sh_total);
     const uint32_t blocks = sh_blocks + (uint32_t)((P + MODEL_THREADS - 1) / MODEL_THREADS);
     begin_kernel("assemble_forward", L);
     if (staged == 48)
@@ -554,8 +557,9 @@ void launch_assemble_backward(const ScgrModel& m, const ScgrActivatedGrads& g, c
     const uint32_t n3k = 3u * (uint32_t)(m.sh_rest + 1);
     const uint64_t sh_total = P * n3k;
     const int staged = staged_rows(n3k);
-    const uint32_t sh_blocks = staged ? (uint32_t)((m.set[0].n + STAGE_G - 1) / STAGE_G + (m.set[1].n + STAGE_G - 1) / STAGE_G)
-                                      : sh_block_count(sh_total);
+    const uint32_t sh_blocks = !g.dL_dshs ? 0u      // split SH layout: scgr_backward wrote dL/dfeatures_* itself
+                               : staged ? (uint32_t)((m.set[0].n + STAGE_G - 1) / STAGE_G + (m.set[1].n + STAGE_G - 1) / STAGE_G)
+                                        : sh_block_count(sh_total);
     const uint32_t blocks = sh_blocks + (uint32_t)((P + MODEL_THREADS - 1) / MODEL_THREADS);
     begin_kernel("assemble_backward", L);
     if (staged == 48)

@@ -36,6 +36,21 @@ constexpr int PB_K = PB_G / PB_T;
 static_assert(PB_G % PB_T == 0 && PB_T % 32 == 0 && PB_G <= 256, "backward block shape");
 constexpr int SH_ROW_F4 = 12;       // 48 floats = 12 float4 per Gaussian at M = 16
 constexpr int SH_ROW_F4_PAD = 13;   // padded row stride (float4 units): conflict-free LDS.128/STS.128
+constexpr int SH_ROW_PAD = 4 * SH_ROW_F4_PAD;      // the same in floats
+constexpr int SH_DC = 3, SH_REST = 45;              // floats per Gaussian in features_dc / features_rest at 16 coefficients
+
+// ---- split SH layout (ScgrGaussians.sh_dc / sh_rest: the hybrid model's own four arrays, include/scgr.h) ----
+// Rows [row0, row0 + nrows) of the virtual [P,16,3] array are up to two runs, one per set; inside a set features_dc and
+// features_rest rows are contiguous, so the CTA walks them as flat streams, one float per lane on consecutive addresses
+// (rows of 3 / 45 floats have no 16-byte alignment), and lands them in the padded staging layout the SH_FAST path uses.
+template <typename F>
+__device__ __forceinline__ void for_each_split_run(const ScgrGaussians& g, const int row0, const int nrows, F&& f) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int lo = k == 0 ? row0 : max(row0, g.sh_n0), hi = k == 0 ? min(row0 + nrows, g.sh_n0) : row0 + nrows;
+        if (hi > lo) f(k, lo - (k ? g.sh_n0 : 0), hi - lo, lo - row0);      // set (compile-time after unrolling), first row inside the set, rows, first local row
+    }
+}
 
 __constant__ const float kC0 = 0.28209479177387814f;
 __constant__ const float kC1 = 0.4886025119029199f;
@@ -233,7 +248,8 @@ depth_key_kernel(const float* __restrict__ means3D, const int P, const float* __
 // forward
 // ------------------------------------------------------------------------------------------
 // SH_FAST: M == 16 and shs 16-byte aligned -> CTA-cooperative 128-bit staging through smem.
-template <bool SH_FAST>
+// SPLIT (implies SH_FAST): the SH rows come from the model's features_dc / features_rest arrays of both sets.
+template <bool SH_FAST, bool SPLIT>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __restrict__ rec,
                           uint32_t* __restrict__ tiles_touched,
@@ -242,9 +258,25 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
     __shared__ float4 s_sh[SH_FAST ? PRE_THREADS * SH_ROW_F4_PAD : 1];
     const int P = g.P;
     const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
-    const bool use_sh = g.shs != nullptr;
+    const bool use_sh = SPLIT || g.shs != nullptr;
 
-    if (SH_FAST && use_sh) {
+    if (SPLIT) {
+        float* const sf = reinterpret_cast<float*>(s_sh);
+        const int row0 = blockIdx.x * PRE_THREADS;
+        for_each_split_run(g, row0, min(PRE_THREADS, P - row0), [&](const int k, const int j0, const int cnt, const int r0) {
+            const float* dc = g.sh_dc[k] + (size_t)j0 * SH_DC;
+            const float* rest = g.sh_rest[k] + (size_t)j0 * SH_REST;
+            for (int f = threadIdx.x; f < cnt * SH_DC; f += PRE_THREADS) {
+                const int r = f / SH_DC;
+                sf[(r0 + r) * SH_ROW_PAD + (f - r * SH_DC)] = __ldg(dc + f);
+            }
+            for (int f = threadIdx.x; f < cnt * SH_REST; f += PRE_THREADS) {
+                const int r = f / SH_REST;
+                sf[(r0 + r) * SH_ROW_PAD + SH_DC + (f - r * SH_REST)] = __ldg(rest + f);
+            }
+        });
+        __syncthreads();
+    } else if (SH_FAST && use_sh) {
         // rows [block0, block0 + 128) are one contiguous run of 128*12 float4 in HBM.  (Fetching only the
         // rows of Gaussians in front of the near plane was tried: the test needs means3D first, and the
         // serialised load latencies cost 25 % on an all-visible scene.)
@@ -401,7 +433,7 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
 // ------------------------------------------------------------------------------------------
 // ACC: gradient accumulation over the views of a batch (ScgrGrads.accumulate): every parameter gradient is added to
 // what the array holds, Gaussians without gradient are not touched at all; dL/dmean2D stays per view.
-template <bool SH_FAST, int MINB, bool ACC>
+template <bool SH_FAST, int MINB, bool ACC, bool SPLIT>
 __global__ void __launch_bounds__(PB_T, MINB)
 preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record* __restrict__ rec,
                            const ScreenGrad* __restrict__ sg, const ScgrGrads out) {
@@ -412,7 +444,7 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     __shared__ int s_wcnt[PB_K][PB_T / 32];
     const int P = g.P;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const bool use_sh = g.shs != nullptr;
+    const bool use_sh = SPLIT || g.shs != nullptr;
     const int row0 = blockIdx.x * PB_G;
     const int nrows = min(PB_G, P - row0);
 
@@ -486,7 +518,16 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
             }
         }
     }
-    if (SH_FAST && use_sh && !ACC) {
+    if (SPLIT && !ACC) {
+        for_each_split_run(g, row0, nrows, [&](const int k, const int j0, const int cnt, const int r0) {
+            float* dc = out.dL_dsh_dc[k] + (size_t)j0 * SH_DC;
+            float* rest = out.dL_dsh_rest[k] + (size_t)j0 * SH_REST;
+            for (int f = tid; f < cnt * SH_DC; f += PB_T)
+                if (!s_live[r0 + f / SH_DC]) dc[f] = 0.f;
+            for (int f = tid; f < cnt * SH_REST; f += PB_T)
+                if (!s_live[r0 + f / SH_REST]) rest[f] = 0.f;
+        });
+    } else if (SH_FAST && use_sh && !ACC) {
         float4* dst = reinterpret_cast<float4*>(out.dL_dshs) + (size_t)row0 * SH_ROW_F4;
         const int nf4 = nrows * SH_ROW_F4;
         for (int f = tid; f < nf4; f += PB_T)
@@ -500,7 +541,20 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     const bool live = tid < in_round;
     const int jl = live ? (int)s_list[first + tid] : 0;      // local index of the Gaussian this thread processes
     const int i = row0 + jl;
-    if (SH_FAST && use_sh) {
+    if (SPLIT) {
+        // the 48 floats of every live row of the round, from whichever set the row belongs to
+        float* const sf = reinterpret_cast<float*>(s_sh);
+        for (int f = tid; f < in_round * 48; f += PB_T) {
+            const int r = f / 48, e = f - r * 48;
+            const int gi = row0 + (int)s_list[first + r];
+            const int k = gi >= g.sh_n0;
+            const size_t j = (size_t)(gi - (k ? g.sh_n0 : 0));
+            // (ternaries, not g.sh_dc[k]: a run-time index into the kernel parameters would spill them to local memory)
+            const float* dc = k ? g.sh_dc[1] : g.sh_dc[0];
+            const float* rest = k ? g.sh_rest[1] : g.sh_rest[0];
+            sf[r * SH_ROW_PAD + e] = e < SH_DC ? __ldg(dc + j * SH_DC + e) : __ldg(rest + j * SH_REST + (e - SH_DC));
+        }
+    } else if (SH_FAST && use_sh) {
         const float4* src = reinterpret_cast<const float4*>(g.shs) + (size_t)row0 * SH_ROW_F4;
         for (int f = tid; f < in_round * SH_ROW_F4; f += PB_T) {
             const int r = f / SH_ROW_F4, c = f - r * SH_ROW_F4;
@@ -521,7 +575,7 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
             sc_in = load3(g.scales, i);
         }
     }
-    if (SH_FAST && use_sh) __syncthreads();
+    if (SH_FAST && use_sh) __syncthreads();      // (SPLIT implies SH_FAST)
 
     float dmean[3] = {0.f, 0.f, 0.f};
     float dm2x = 0.f, dm2y = 0.f, dop = 0.f;
@@ -722,7 +776,21 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
             for (int k = 0; k < 6; k++) put(out.dL_dcov3D_precomp + 6 * (size_t)i + k, d6[k]);
         }
     }
-    if (SH_FAST && use_sh) {
+    if (SPLIT) {
+        // the gradient rows of the round sit in smem (written in place above): back to the model's own arrays
+        __syncthreads();
+        const float* const sf = reinterpret_cast<const float*>(s_sh);
+        for (int f = tid; f < in_round * 48; f += PB_T) {
+            const int r = f / 48, e = f - r * 48;
+            const int gi = row0 + (int)s_list[first + r];
+            const int k = gi >= g.sh_n0;
+            const size_t j = (size_t)(gi - (k ? g.sh_n0 : 0));
+            float* d1 = e < SH_DC ? (k ? out.dL_dsh_dc[1] : out.dL_dsh_dc[0]) + j * SH_DC + e
+                                  : (k ? out.dL_dsh_rest[1] : out.dL_dsh_rest[0]) + j * SH_REST + (e - SH_DC);
+            if (ACC) *d1 += sf[r * SH_ROW_PAD + e]; else *d1 = sf[r * SH_ROW_PAD + e];
+        }
+        __syncthreads();      // the staging buffer is reused by the next round
+    } else if (SH_FAST && use_sh) {
         // the 192-byte gradient rows of the round sit in smem (written in place above): stream them out,
         // 12 consecutive 128-bit stores per row
         __syncthreads();
@@ -748,6 +816,8 @@ __global__ void mark_visible_kernel(const float* __restrict__ means3D, int P, co
     present[i] = zv > NEAR_Z ? 1 : 0;
 }
 
+inline bool sh_split(const ScgrGaussians& g) { return g.shs == nullptr && (g.sh_dc[0] != nullptr || g.sh_dc[1] != nullptr); }
+
 inline bool sh_fast_ok(const ScgrGaussians& g, const void* dsh) {
     return g.shs != nullptr && g.sh_coeffs == 16 && (reinterpret_cast<uintptr_t>(g.shs) & 15) == 0 &&
            (reinterpret_cast<uintptr_t>(dsh) & 15) == 0;
@@ -760,10 +830,12 @@ void launch_preprocess_forward(const ScgrView& v, const ScgrGaussians& g, const 
     if (g.P <= 0) return;
     const int blocks = (g.P + PRE_THREADS - 1) / PRE_THREADS;
     begin_kernel("preprocess_forward", L);
-    if (sh_fast_ok(g, nullptr))
-        preprocess_forward_kernel<true><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.tiles_touched, G.rect, G.tile_mask, radii);
+    if (sh_split(g))
+        preprocess_forward_kernel<true, true><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.tiles_touched, G.rect, G.tile_mask, radii);
+    else if (sh_fast_ok(g, nullptr))
+        preprocess_forward_kernel<true, false><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.tiles_touched, G.rect, G.tile_mask, radii);
     else
-        preprocess_forward_kernel<false><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.tiles_touched, G.rect, G.tile_mask, radii);
+        preprocess_forward_kernel<false, false><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.tiles_touched, G.rect, G.tile_mask, radii);
     check_launch("preprocess_forward", L);
 }
 
@@ -783,15 +855,18 @@ void launch_preprocess_backward(const ScgrView& v, const ScgrGaussians& g, const
     begin_kernel("preprocess_backward", L);
     static const int minb = getenv("SCGR_PREB_MINB") ? atoi(getenv("SCGR_PREB_MINB")) : 1;
     const bool acc = out.accumulate != 0;
-    if (sh_fast_ok(g, out.dL_dshs)) {
-        if (acc) preprocess_backward_kernel<true, 1, true><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (minb == 12) preprocess_backward_kernel<true, 12, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (minb == 10) preprocess_backward_kernel<true, 10, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else preprocess_backward_kernel<true, 1, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+    if (sh_split(g)) {
+        if (acc) preprocess_backward_kernel<true, 1, true, true><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else preprocess_backward_kernel<true, 1, false, true><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+    } else if (sh_fast_ok(g, out.dL_dshs)) {
+        if (acc) preprocess_backward_kernel<true, 1, true, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (minb == 12) preprocess_backward_kernel<true, 12, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (minb == 10) preprocess_backward_kernel<true, 10, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else preprocess_backward_kernel<true, 1, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     } else if (acc) {
-        preprocess_backward_kernel<false, 1, true><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        preprocess_backward_kernel<false, 1, true, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     } else {
-        preprocess_backward_kernel<false, 1, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        preprocess_backward_kernel<false, 1, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     }
     check_launch("preprocess_backward", L);
 }

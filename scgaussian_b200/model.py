@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional
 
 import torch
@@ -72,7 +73,7 @@ def _sh_rest(n: int, d: dict) -> Optional[int]:
 
 class _Assemble(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, *args):
+    def forward(ctx, with_sh, *args):
         lib = _lib.load()
         ray_in = dict(zip(_RAY, args[:len(_RAY)]))
         bg_in = dict(zip(_BG, args[len(_RAY):]))
@@ -99,12 +100,14 @@ class _Assemble(torch.autograd.Function):
             scales = torch.empty(P, 3, dtype=torch.float32, device=device)
             rotations = torch.empty(P, 4, dtype=torch.float32, device=device)
             opacities = torch.empty(P, 1, dtype=torch.float32, device=device)
-            shs = torch.empty(P, sh_rest + 1, 3, dtype=torch.float32, device=device)
+            # with_sh False: the operator reads features_dc / features_rest itself (split SH layout), no [P,K,3] copy
+            shs = torch.empty(P, sh_rest + 1, 3, dtype=torch.float32, device=device) if with_sh else None
             out = ScgrActivated(means3D.data_ptr(), scales.data_ptr(), rotations.data_ptr(), opacities.data_ptr(),
-                                shs.data_ptr())
+                                _p(shs))
             stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
             check(lib.scgr_assemble_forward(C.byref(model), C.byref(out), stream))
         ctx.sizes = (n_ray, n_bg, sh_rest)
+        ctx.with_sh = bool(with_sh)
         ctx.layout = [k for k in _RAY if ray.get(k) is not None], [k for k in _BG if bg.get(k) is not None]
         ctx.save_for_backward(*[ray[k] for k in ctx.layout[0]], *[bg[k] for k in ctx.layout[1]])
         return means3D, scales, rotations, opacities, shs
@@ -118,20 +121,23 @@ class _Assemble(torch.autograd.Function):
         bg = dict(zip(ctx.layout[1], saved[len(ctx.layout[0]):]))
         device = saved[0].device
         model = ScgrModel(sh_rest, (ScgrModelSet * 2)(_set(n_ray, ray), _set(n_bg, bg)))
-        gin = [t.to(device=device, dtype=torch.float32).contiguous()
-               for t in (g_means3D, g_scales, g_rotations, g_opacities, g_shs)]
-        grads = ScgrActivatedGrads(*[t.data_ptr() for t in gin])
+        gin = [None if t is None else t.to(device=device, dtype=torch.float32).contiguous()
+               for t in (g_means3D, g_scales, g_rotations, g_opacities, g_shs if ctx.with_sh else None)]
+        if any(t is None for t in gin[:4]) or (ctx.with_sh and gin[4] is None):
+            raise ScgrError("assemble backward: a gradient of the assembled arrays is missing")
+        grads = ScgrActivatedGrads(*[_p(t) for t in gin])
 
         def new(n, *tail):
             return torch.empty(n, *tail, dtype=torch.float32, device=device) if n else None
 
         with torch.cuda.device(device):
+            sh = ctx.with_sh      # split SH layout: the rasterizer's own node returns dL/dfeatures_*
             d_ray = {"zval": new(n_ray, 1), "scaling": new(n_ray, 3), "rotation": new(n_ray, 4),
-                     "opacity": new(n_ray, 1), "features_dc": new(n_ray, 1, 3),
-                     "features_rest": new(n_ray, sh_rest, 3)}
+                     "opacity": new(n_ray, 1), "features_dc": new(n_ray, 1, 3) if sh else None,
+                     "features_rest": new(n_ray, sh_rest, 3) if sh else None}
             d_bg = {"xyz": new(n_bg, 3), "scaling": new(n_bg, 3), "rotation": new(n_bg, 4),
-                    "opacity": new(n_bg, 1), "features_dc": new(n_bg, 1, 3),
-                    "features_rest": new(n_bg, sh_rest, 3)}
+                    "opacity": new(n_bg, 1), "features_dc": new(n_bg, 1, 3) if sh else None,
+                    "features_rest": new(n_bg, sh_rest, 3) if sh else None}
 
             def gset(d):
                 return ScgrModelSetGrads(_p(d.get("xyz")), _p(d.get("zval")), _p(d["scaling"]), _p(d["rotation"]),
@@ -141,17 +147,17 @@ class _Assemble(torch.autograd.Function):
             stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
             check(lib.scgr_assemble_backward(C.byref(model), C.byref(grads), C.byref(out), stream))
         # rayo / rayd are the fixed geometry of the matched rays (reference scene/gaussian_model.py:493 trains zval only)
-        res = [None, None] + [d_ray[k] for k in _RAY[2:]] + [d_bg[k] for k in _BG]
+        res = [None, None, None] + [d_ray[k] for k in _RAY[2:]] + [d_bg[k] for k in _BG]
         return tuple(r if need else None for r, need in zip(res, ctx.needs_input_grad))
 
 
 def assemble(rayo=None, rayd=None, zval=None, scaling=None, rotation=None, opacity=None, features_dc=None,
              features_rest=None, bg_xyz=None, bg_scaling=None, bg_rotation=None, bg_opacity=None,
-             bg_features_dc=None, bg_features_rest=None):
+             bg_features_dc=None, bg_features_rest=None, with_sh=True):
     """(means3D [P,3], scales [P,3], rotations [P,4], opacities [P,1], shs [P,K,3]) of the hybrid model:
     the ray-based set (position rayo + rayd * zval) followed by the free set (position bg_xyz), activated as
     reference scene/gaussian_model.py:105-152 does.  Either set may be absent (all None)."""
-    return _Assemble.apply(rayo, rayd, zval, scaling, rotation, opacity, features_dc, features_rest,
+    return _Assemble.apply(bool(with_sh), rayo, rayd, zval, scaling, rotation, opacity, features_dc, features_rest,
                            bg_xyz, bg_scaling, bg_rotation, bg_opacity, bg_features_dc, bg_features_rest)
 
 
@@ -160,20 +166,39 @@ def _attr(pc, name):
     return t if isinstance(t, torch.Tensor) and t.dim() > 0 and t.shape[0] > 0 else None
 
 
-def assemble_model(pc):
+def assemble_model(pc, with_sh=True):
     """`assemble` on a reference `GaussianModel` (attribute names of reference scene/gaussian_model.py:55-62 and
     the bg_* tensors tested at :109, :118, :126, :135, :146).  A model without ray attributes (plain 3DGS `_xyz`)
-    is taken as one free set."""
+    is taken as one free set.  with_sh=False leaves the SH copy out (fifth output None): see `split_features`."""
     if _attr(pc, "_rayo") is None and _attr(pc, "_xyz") is not None and _attr(pc, "bg_xyz") is None:
         return assemble(bg_xyz=pc._xyz, bg_scaling=pc._scaling, bg_rotation=pc._rotation, bg_opacity=pc._opacity,
-                        bg_features_dc=pc._features_dc, bg_features_rest=pc._features_rest)
+                        bg_features_dc=pc._features_dc, bg_features_rest=pc._features_rest, with_sh=with_sh)
     has_ray = _attr(pc, "_rayo") is not None
     has_bg = _attr(pc, "bg_xyz") is not None
     ray = dict(rayo=pc._rayo, rayd=pc._rayd, zval=pc._zval, scaling=pc._scaling, rotation=pc._rotation,
                opacity=pc._opacity, features_dc=pc._features_dc, features_rest=pc._features_rest) if has_ray else {}
     bg = dict(bg_xyz=pc.bg_xyz, bg_scaling=pc.bg_scaling, bg_rotation=pc.bg_rotation, bg_opacity=pc.bg_opacity,
               bg_features_dc=pc.bg_features_dc, bg_features_rest=pc.bg_features_rest) if has_bg else {}
-    return assemble(**ray, **bg)
+    return assemble(**ray, **bg, with_sh=with_sh)
+
+
+def split_features(pc):
+    """(features_dc, features_rest, bg_features_dc, bg_features_rest) of the model when the operator can read them in
+    place (16 SH coefficients, contiguous fp32: the `sh_split` input of scgaussian_b200.rasterizer), else None."""
+    if _attr(pc, "_rayo") is None and _attr(pc, "_xyz") is not None and _attr(pc, "bg_xyz") is None:
+        sets = (None, None, pc._features_dc, pc._features_rest)
+    else:
+        has_ray, has_bg = _attr(pc, "_rayo") is not None, _attr(pc, "bg_xyz") is not None
+        sets = ((pc._features_dc, pc._features_rest) if has_ray else (None, None)) + \
+               ((pc.bg_features_dc, pc.bg_features_rest) if has_bg else (None, None))
+    for dc, rest in (sets[0:2], sets[2:4]):
+        if dc is None:
+            continue
+        if rest is None or tuple(dc.shape[1:]) != (1, 3) or tuple(rest.shape[1:]) != (15, 3):
+            return None
+        if any(t.dtype != torch.float32 or not t.is_contiguous() or t.device.type != "cuda" for t in (dc, rest)):
+            return None
+    return sets
 
 
 def add_densification_stats(pc, viewspace_point_tensor, update_filter=None, radii=None) -> None:
@@ -224,7 +249,10 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     if getattr(pipe, "compute_cov3D_python", False) or getattr(pipe, "convert_SHs_python", False):
         raise ScgrError("the fused render() has no python covariance / SH path: use the reference's render() for "
                         "pipe.compute_cov3D_python / pipe.convert_SHs_python")
-    means3D, scales, rotations, opacity, shs = assemble_model(pc)
+    # SH degree 3 models (what the reference trains: arguments/__init__.py:49) hand their feature arrays to the operator
+    # as they are; anything else goes through the assembled [P,K,3] copy
+    split = split_features(pc) if override_color is None and os.environ.get("SCGR_SPLIT_SH", "1") != "0" else None
+    means3D, scales, rotations, opacity, shs = assemble_model(pc, with_sh=split is None)
     # reference :28-32: the tensor whose .grad receives dL/dmean2D
     screenspace_points = torch.zeros_like(means3D, requires_grad=True) + 0
     try:
@@ -244,16 +272,21 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
         campos=viewpoint_camera.camera_center,
         prefiltered=False,
         debug=bool(getattr(pipe, "debug", False)))
-    rasterizer = GaussianRasterizer(raster_settings=raster_settings)
-    rendered_image, radii, rendered_depth, rendered_alpha = rasterizer(
-        means3D=means3D,
-        means2D=screenspace_points,
-        shs=shs if override_color is None else None,
-        colors_precomp=override_color,
-        opacities=opacity,
-        scales=scales,
-        rotations=rotations,
-        cov3D_precomp=None)
+    if split is not None:
+        from .rasterizer import rasterize_gaussians_split
+        rendered_image, radii, rendered_depth, rendered_alpha = rasterize_gaussians_split(
+            means3D, screenspace_points, opacity, scales, rotations, split, raster_settings)
+    else:
+        rasterizer = GaussianRasterizer(raster_settings=raster_settings)
+        rendered_image, radii, rendered_depth, rendered_alpha = rasterizer(
+            means3D=means3D,
+            means2D=screenspace_points,
+            shs=shs if override_color is None else None,
+            colors_precomp=override_color,
+            opacities=opacity,
+            scales=scales,
+            rotations=rotations,
+            cov3D_precomp=None)
     return {"render": rendered_image,
             "rendered_depth": rendered_depth,
             "rendered_alpha": rendered_alpha,

@@ -105,6 +105,17 @@ class FlatGradBuffer:
         st[:, 0] = torch.linalg.vector_norm(self.means2D[:, :2], dim=-1) * vis
         st[:, 1] = vis
 
+    def fill_live(self, dL_dopacities: torch.Tensor, dL_dmeans3D: Optional[torch.Tensor] = None) -> None:
+        """The live counts for callers whose backward did not go through out_dict() (autograd through the public
+        operator, which hands back plain gradient tensors): a Gaussian counts as live when its dL/dopacity or any
+        component of its dL/dmean3D is non-zero.  (scgr_backward itself marks a Gaussian live when ANY of its ten
+        screen-space sums is non-zero; the two criteria differ only if those sums cancel to exactly 0.0 in both the
+        opacity and all three position components while another one does not.)"""
+        live = dL_dopacities.reshape(-1) != 0
+        if dL_dmeans3D is not None:
+            live = live | (dL_dmeans3D != 0).any(dim=1)
+        self.views["live"].copy_(live.to(torch.float32))
+
     def _allocate(self, total: int, device: torch.device, world: int, symmetric: Optional[bool]) -> torch.Tensor:
         # measured on 8xB200, dense 244 MB: NVLS kernel 609 us vs NCCL 661 us at 8 ranks, 645 us vs 481 us at 2 ranks;
         # with the row-sparse second shot the switch moves a fraction of that: it is used whenever it is available

@@ -104,11 +104,39 @@ def _make_view(s: GaussianRasterizationSettings, device, keep: list) -> ScgrView
                     int(s.sh_degree), cp.data_ptr(), int(bool(s.prefiltered)), int(bool(s.debug)))
 
 
-def _make_gaussians(means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp) -> ScgrGaussians:
+def _make_gaussians(means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, sh_split=None) -> ScgrGaussians:
     P = int(means3D.shape[0])
     M = int(sh.shape[1]) if sh is not None and sh.numel() > 0 else 0
-    return ScgrGaussians(P, M, _ptr(means3D), _ptr(opacities), _ptr(sh), _ptr(colors_precomp),
-                         _ptr(scales), _ptr(rotations), _ptr(cov3Ds_precomp))
+    g = ScgrGaussians(P, M, _ptr(means3D), _ptr(opacities), _ptr(sh), _ptr(colors_precomp),
+                      _ptr(scales), _ptr(rotations), _ptr(cov3Ds_precomp))
+    if sh_split is not None:
+        dc0, rest0, dc1, rest1 = sh_split
+        g.sh_coeffs = 16
+        g.sh_dc[0], g.sh_rest[0] = _ptr(dc0), _ptr(rest0)
+        g.sh_dc[1], g.sh_rest[1] = _ptr(dc1), _ptr(rest1)
+        g.sh_n0 = 0 if dc0 is None else int(dc0.shape[0])
+    return g
+
+
+def _check_split(sh_split, P, device):
+    """sh_split = (features_dc, features_rest) of the two sets of the hybrid model (reference scene/gaussian_model.py:
+    131-140), either set possibly None: contiguous fp32 [n,1,3] / [n,15,3] on `device`, n0 + n1 == P."""
+    if len(sh_split) != 4:
+        raise ScgrError("sh_split = (features_dc, features_rest, bg_features_dc, bg_features_rest)")
+    n = 0
+    for dc, rest in (sh_split[0:2], sh_split[2:4]):
+        if (dc is None) != (rest is None):
+            raise ScgrError("sh_split: features_dc and features_rest of a set go together")
+        if dc is None:
+            continue
+        if tuple(dc.shape[1:]) != (1, 3) or tuple(rest.shape[1:]) != (15, 3) or rest.shape[0] != dc.shape[0]:
+            raise ScgrError("sh_split needs [n,1,3] / [n,15,3] arrays (16 SH coefficients)")
+        for t in (dc, rest):
+            if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ScgrError("sh_split arrays must be contiguous fp32 tensors on the operator's device")
+        n += int(dc.shape[0])
+    if n != P:
+        raise ScgrError(f"sh_split holds {n} Gaussians, means3D {P}")
 
 
 class ForwardState(NamedTuple):
@@ -123,9 +151,10 @@ class ForwardState(NamedTuple):
 
 
 def rasterize_forward_raw(means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp,
-                          s: GaussianRasterizationSettings):
+                          s: GaussianRasterizationSettings, sh_split=None):
     """Runs the two forward stages of libscgr on the current stream.  Inputs must be contiguous fp32
-    CUDA tensors (or None).  Returns (color, radii, depth, alpha, ForwardState)."""
+    CUDA tensors (or None).  `sh_split` (instead of `sh`): the SH coefficients as the hybrid model stores them, see
+    _check_split.  Returns (color, radii, depth, alpha, ForwardState)."""
     global launch_counter, need_capacity_count
     lib = _lib.load()
     device = means3D.device
@@ -136,7 +165,9 @@ def rasterize_forward_raw(means3D, opacities, sh, colors_precomp, scales, rotati
     keep: list = []
     with torch.cuda.device(device):
         view = _make_view(s, device, keep)
-        g = _make_gaussians(means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp)
+        if sh_split is not None:
+            _check_split(sh_split, P, device)
+        g = _make_gaussians(means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, sh_split)
         stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         geometry = _scratch(lib.scgr_geometry_bytes(P), device)
         image = _scratch(lib.scgr_image_bytes(W, H), device)
@@ -224,7 +255,7 @@ def rasterize_forward_raw(means3D, opacities, sh, colors_precomp, scales, rotati
 
 def rasterize_backward_raw(state: ForwardState, means3D, opacities, sh, colors_precomp, scales, rotations,
                            cov3Ds_precomp, s: GaussianRasterizationSettings, grad_color, grad_depth, grad_alpha,
-                           out: Optional[dict] = None, accumulate: bool = False) -> dict:
+                           out: Optional[dict] = None, accumulate: bool = False, sh_split=None) -> dict:
     """Runs scgr_backward.  `out` may hold pre-allocated gradient tensors (e.g. views into one flat
     all-reduce buffer, scgaussian_b200/parallel.py); missing ones are allocated.  Every returned
     tensor is fully written by the kernels.  out["stats"] ([P,2], optional) receives the two per-view
@@ -264,6 +295,9 @@ def rasterize_backward_raw(state: ForwardState, means3D, opacities, sh, colors_p
         gsc = need("scales", scales, (P, 3))
         grot = need("rotations", rotations, (P, 4))
         gcov = need("cov3D_precomp", cov3Ds_precomp, (P, 6))
+        gsplit = [None] * 4
+        if sh_split is not None:      # gradients in the model's own layout: "sh_split0".."sh_split3"
+            gsplit = [need(f"sh_split{k}", t, tuple(t.shape) if t is not None else ()) for k, t in enumerate(sh_split)]
         stats = out.get("stats")
         if stats is not None:
             assert stats.is_contiguous() and stats.dtype == torch.float32 and tuple(stats.shape) == (P, 2), "stats"
@@ -277,10 +311,12 @@ def rasterize_backward_raw(state: ForwardState, means3D, opacities, sh, colors_p
         if P == 0:
             return out
         view = _make_view(s, device, keep)
-        g = _make_gaussians(means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp)
+        g = _make_gaussians(means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, sh_split)
         grads = ScgrGrads(_ptr(gm3), _ptr(gm2), _ptr(gsh), _ptr(gcol), _ptr(gop), _ptr(gsc), _ptr(grot), _ptr(gcov),
                           _ptr(stats), _ptr(state.radii) if stats is not None else None, int(bool(accumulate)),
                           _ptr(live))
+        grads.dL_dsh_dc[0], grads.dL_dsh_rest[0] = _ptr(gsplit[0]), _ptr(gsplit[1])
+        grads.dL_dsh_dc[1], grads.dL_dsh_rest[1] = _ptr(gsplit[2]), _ptr(gsplit[3])
         gc = _f32c(grad_color, device)
         gd = _f32c(grad_depth, device)
         ga = _f32c(grad_alpha, device)
@@ -343,6 +379,49 @@ class _RasterizeGaussians(torch.autograd.Function):
             raise
         return (g.get("means3D"), g.get("means2D"), g.get("shs"), g.get("colors_precomp"), g.get("opacities"),
                 g.get("scales"), g.get("rotations"), g.get("cov3D_precomp"), None)
+
+
+class _RasterizeGaussiansSplit(torch.autograd.Function):
+    """The operator with the SH coefficients taken straight from the hybrid model's four arrays (SURVEY.md section 8f row
+    f2, second half; include/scgr.h: ScgrGaussians.sh_dc / sh_rest): same outputs, the gradients of the coefficients come
+    back in the arrays' own layout.  Scale / rotation path only (what the training step uses)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, opacities, scales, rotations, dc0, rest0, dc1, rest1, raster_settings):
+        split = (dc0, rest0, dc1, rest1)
+        color, radii, depth, alpha, state = rasterize_forward_raw(means3D, opacities, None, None, scales, rotations, None,
+                                                                  raster_settings, sh_split=split)
+        ctx.raster_settings = raster_settings
+        ctx.state = state
+        ctx.num_rendered = state.num_rendered
+        ctx.has = [t is not None for t in split]
+        ctx.save_for_backward(means3D, opacities, scales, rotations, *[t for t in split if t is not None])
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
+        s = ctx.raster_settings
+        saved = list(ctx.saved_tensors)
+        means3D, opacities, scales, rotations = saved[:4]
+        it = iter(saved[4:])
+        split = tuple(next(it) if h else None for h in ctx.has)
+        H, W = int(s.image_height), int(s.image_width)
+        dev = means3D.device
+        if grad_color is None:
+            grad_color = torch.zeros(3, H, W, device=dev)
+        if grad_depth is None:
+            grad_depth = torch.zeros(1, H, W, device=dev)
+        if grad_alpha is None:
+            grad_alpha = torch.zeros(1, H, W, device=dev)
+        g = rasterize_backward_raw(ctx.state, means3D, opacities, None, None, scales, rotations, None, s, grad_color,
+                                   grad_depth, grad_alpha, sh_split=split)
+        return (g.get("means3D"), g.get("means2D"), g.get("opacities"), g.get("scales"), g.get("rotations"),
+                g.get("sh_split0"), g.get("sh_split1"), g.get("sh_split2"), g.get("sh_split3"), None)
+
+
+def rasterize_gaussians_split(means3D, means2D, opacities, scales, rotations, sh_split, raster_settings):
+    return _RasterizeGaussiansSplit.apply(means3D, means2D, opacities, scales, rotations, *sh_split, raster_settings)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,

@@ -886,3 +886,89 @@ def test_c_abi_on_host_protocols_and_overflow_recovery(emu_abi, monkeypatch):
     rc = emu_abi.scgr_forward(C.byref(view), C.byref(bad), big["gptr"], big["radii"].data_ptr(), big["bptr"], 10, big["iptr"],
                               color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), status.data_ptr(), None)
     assert rc == 1 and b"exactly one of shs / colors_precomp" in emu_abi.scgr_last_error()
+
+
+@pytest.mark.parametrize("n0_of", ["mid", "zero", "all", "one"])
+def test_split_sh_layout_on_host_is_bit_identical_to_the_assembled_one(emu_abi, monkeypatch, n0_of):
+    """SURVEY 8f row f2, second half (include/scgr.h: ScgrGaussians.sh_dc / sh_rest): the operator reading the SH rows
+    straight from the hybrid model's four arrays (reference scene/gaussian_model.py:131-140 cats them on every render)
+    gives the same bits as the assembled [P,16,3] input -- images, radii, and every gradient, the dL/dfeatures_* rows being
+    the slices of dL/dshs; accumulate mode included."""
+    from oracle import torch_oracle as O
+    monkeypatch.setenv("SCGR_FWD_SPLIT", "0,0")
+    monkeypatch.setenv("SCGR_BWD_SPLIT", "0,0")
+    P, W, H = 700, 120, 90
+    case, t, view, g = _host_scene(P, W, H, 3, seed=5, scale_median=0.06, bg=(0.1, 0.2, 0.3), z_shift=-1.7)
+    n0 = {"mid": 333, "zero": 0, "all": P, "one": 1}[n0_of]          # 333: a set boundary inside a 128-Gaussian block
+    shs = t["shs"]
+    # each array in its own allocation, sized exactly: rows of 3 / 45 floats, no padding
+    dc = [shs[:n0, :1].clone().contiguous(), shs[n0:, :1].clone().contiguous()]
+    rest = [shs[:n0, 1:].clone().contiguous(), shs[n0:, 1:].clone().contiguous()]
+    gs = L.ScgrGaussians(P, 16, t["means3D"].data_ptr(), t["opacities"].data_ptr(), None, None, t["scales"].data_ptr(),
+                         t["rotations"].data_ptr(), None)
+    for k in range(2):
+        if dc[k].shape[0]:
+            gs.sh_dc[k], gs.sh_rest[k] = dc[k].data_ptr(), rest[k].data_ptr()
+    gs.sh_n0 = n0
+    gC, gD, gA = [x.contiguous() for x in O.synth_upstream_grads(W, H)]
+
+    def run(gg, split, accumulate):
+        cap = 60000
+        geom, gptr = _aligned(emu_abi.scgr_geometry_bytes(P))
+        image, iptr = _aligned(emu_abi.scgr_image_bytes(W, H))
+        binning, bptr = _aligned(emu_abi.scgr_binning_bytes(P, W, H, cap))
+        radii = torch.zeros(P, dtype=torch.int32)
+        color, depth, alpha = (torch.full((c, H, W), float("nan")) for c in (3, 1, 1))
+        status = torch.zeros(2, dtype=torch.int64)
+        rc = emu_abi.scgr_forward(C.byref(view), C.byref(gg), gptr, radii.data_ptr(), bptr, cap, iptr, color.data_ptr(),
+                                  depth.data_ptr(), alpha.data_ptr(), status.data_ptr(), None)
+        assert rc == 0, emu_abi.scgr_last_error()
+        fill = 0.25 if accumulate else float("nan")
+        outs = {"means3D": torch.full((P, 3), fill), "means2D": torch.full((P, 3), float("nan")),
+                "opacities": torch.full((P, 1), fill), "scales": torch.full((P, 3), fill),
+                "rotations": torch.full((P, 4), fill)}
+        sg = L.ScgrGrads(outs["means3D"].data_ptr(), outs["means2D"].data_ptr(), None, None, outs["opacities"].data_ptr(),
+                         outs["scales"].data_ptr(), outs["rotations"].data_ptr(), None)
+        sg.accumulate = int(accumulate)
+        if split:
+            outs["dc"] = [torch.full_like(x, fill) for x in dc]
+            outs["rest"] = [torch.full_like(x, fill) for x in rest]
+            for k in range(2):
+                if dc[k].shape[0]:
+                    sg.dL_dsh_dc[k], sg.dL_dsh_rest[k] = outs["dc"][k].data_ptr(), outs["rest"][k].data_ptr()
+        else:
+            outs["shs"] = torch.full((P, 16, 3), fill)
+            sg.dL_dshs = outs["shs"].data_ptr()
+        rc = emu_abi.scgr_backward(C.byref(view), C.byref(gg), gptr, bptr, cap, iptr, gC.data_ptr(), gD.data_ptr(),
+                                   gA.data_ptr(), C.byref(sg), None)
+        assert rc == 0, emu_abi.scgr_last_error()
+        return dict(color=color, depth=depth, alpha=alpha, radii=radii, R=int(status[0])), outs
+
+    for accumulate in (False, True):
+        img_a, out_a = run(g, False, accumulate)
+        img_s, out_s = run(gs, True, accumulate)
+        assert img_a["R"] == img_s["R"] > 0
+        for k in ("color", "depth", "alpha", "radii"):
+            assert torch.equal(img_a[k], img_s[k]), k
+        # (render_backward sums the per-Gaussian screen-space gradients with atomics in arrival order: two runs of the SAME
+        # layout differ in the last bits too, so the gradients are compared to rounding, the forward bit for bit)
+        def same(name, a, b):
+            assert a.shape == b.shape and not torch.isnan(a).any() and not torch.isnan(b).any(), name
+            if a.numel():
+                assert float((a - b).abs().max()) <= 2e-5 * float(a.abs().max()) + 1e-12, name
+                assert torch.equal(a == 0, b == 0), name          # rows without gradient are exact zeros in both layouts
+
+        for k in ("means3D", "means2D", "opacities", "scales", "rotations"):
+            same(k, out_a[k], out_s[k])
+        sh_ref = out_a["shs"] - (0.25 if accumulate else 0.0)
+        assert float(sh_ref.abs().max()) > 0
+        same("dc0", out_a["shs"][:n0, :1], out_s["dc"][0]); same("dc1", out_a["shs"][n0:, :1], out_s["dc"][1])
+        same("rest0", out_a["shs"][:n0, 1:], out_s["rest"][0]); same("rest1", out_a["shs"][n0:, 1:], out_s["rest"][1])
+
+    # argument errors of the split layout
+    bad = L.ScgrGaussians(P, 9, t["means3D"].data_ptr(), t["opacities"].data_ptr(), None, None, t["scales"].data_ptr(),
+                          t["rotations"].data_ptr(), None)
+    bad.sh_dc[1], bad.sh_rest[1], bad.sh_n0 = dc[1].data_ptr() or dc[0].data_ptr(), rest[1].data_ptr() or rest[0].data_ptr(), 0
+    status = torch.zeros(2, dtype=torch.int64)
+    rc = emu_abi.scgr_forward(C.byref(view), C.byref(bad), 256, 256, 256, 10, 256, 256, 256, 256, status.data_ptr(), None)
+    assert rc == 1 and b"need 16 coefficients" in emu_abi.scgr_last_error()

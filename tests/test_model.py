@@ -232,12 +232,16 @@ class _Cam:
 
 
 @pytest.mark.gpu
-def test_fused_render_matches_reference_style_render():
+@pytest.mark.parametrize("split_sh", ["1", "0"])
+def test_fused_render_matches_reference_style_render(monkeypatch, split_sh):
     """scgaussian_b200.model.render (fused assembly) against the same operator fed by the reference's chain of torch
     activations (reference gaussian_renderer/__init__.py:55-68 + scene/gaussian_model.py:105-152): same image,
-    same gradients on the raw parameters."""
+    same gradients on the raw parameters.  split_sh "1" (the default): the operator reads features_dc / features_rest of
+    both sets in place and writes dL/dfeatures_* itself (second half); "0": through the assembled
+    [P,16,3] copy."""
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
+    monkeypatch.setenv("SCGR_SPLIT_SH", split_sh)
     import math
     from scgaussian_b200 import GaussianRasterizationSettings, GaussianRasterizer, model
     from tests.util import assert_grad_close, assert_image_close, make_case

@@ -278,6 +278,70 @@ def test_sh_layouts_other_than_16_coefficients(dev, deg, max_deg):
     report("sh_layouts", deg=deg, max_deg=max_deg, **st)
 
 
+@pytest.mark.parametrize("P,n0", [(40_000, 12_345), (3_000, 0), (3_000, 3_000), (300_001, 1)])
+def test_split_sh_layout_matches_the_assembled_one(dev, P, n0):
+    """SURVEY 8f row f2, second half (include/scgr.h: ScgrGaussians.sh_dc / sh_rest): SH rows read in place from the
+    hybrid model's four arrays (reference scene/gaussian_model.py:131-140) -- forward bit-identical to the assembled
+    [P,16,3] input, gradients identical up to the arrival order of the backward's atomic sums, zero rows exact; also
+    through the autograd node, and in accumulate mode."""
+    from scgaussian_b200 import rasterizer as R
+    W, H = 320, 200
+    case = util.make_case(P, W, H, sh_degree=3, scale_median=0.03, seed=P + n0, z_shift=-1.7)
+    s = settings_for(case, dev)
+    t = {k: case[k].to(dev).contiguous() for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+    split = tuple(x.clone().contiguous() if x.shape[0] else None
+                  for x in (t["shs"][:n0, :1], t["shs"][:n0, 1:], t["shs"][n0:, :1], t["shs"][n0:, 1:]))
+    gup = [g.to(dev) for g in O.synth_upstream_grads(W, H)]
+    fa = R.rasterize_forward_raw(t["means3D"], t["opacities"], t["shs"], None, t["scales"], t["rotations"], None, s)
+    fs = R.rasterize_forward_raw(t["means3D"], t["opacities"], None, None, t["scales"], t["rotations"], None, s, sh_split=split)
+    for a, b in zip(fa[:4], fs[:4]):
+        assert torch.equal(a, b)
+    assert fa[4].num_rendered == fs[4].num_rendered > 0
+
+    def close(name, a, b):
+        assert a.shape == b.shape, name
+        if a.numel():
+            assert float((a - b).abs().max()) <= 2e-5 * float(a.abs().max()) + 1e-12, name
+            assert torch.equal(a == 0, b == 0), name
+
+    for acc in (False, True):
+        def pre(shape):
+            return torch.full(shape, 0.5, device=dev) if acc else None
+        oa = {k: pre(tuple(v.shape)) for k, v in t.items()} if acc else {}
+        os_ = {k: pre(tuple(v.shape)) for k, v in t.items() if k != "shs"} if acc else {}
+        if acc:
+            for k, x in enumerate(split):
+                if x is not None:
+                    os_[f"sh_split{k}"] = pre(tuple(x.shape))
+        ga = R.rasterize_backward_raw(fa[4], t["means3D"], t["opacities"], t["shs"], None, t["scales"], t["rotations"], None, s,
+                                      *gup, out=oa, accumulate=acc)
+        gs = R.rasterize_backward_raw(fs[4], t["means3D"], t["opacities"], None, None, t["scales"], t["rotations"], None, s,
+                                      *gup, out=os_, accumulate=acc, sh_split=split)
+        for k in ("means3D", "means2D", "opacities", "scales", "rotations"):
+            close(k, ga[k], gs[k])
+        assert gs.get("shs") is None and float((ga["shs"] - (0.5 if acc else 0.0)).abs().max()) > 0
+        parts = (ga["shs"][:n0, :1], ga["shs"][:n0, 1:], ga["shs"][n0:, :1], ga["shs"][n0:, 1:])
+        for k, want in enumerate(parts):
+            if split[k] is None:
+                assert gs.get(f"sh_split{k}") is None
+            else:
+                close(f"sh_split{k}", want, gs[f"sh_split{k}"])
+        if not acc:
+            plain = [x.clone() for x in parts]
+
+    # the autograd node: gradients land on the four leaves
+    leaves = [None if x is None else x.clone().requires_grad_(True) for x in split]
+    m2d = torch.zeros(P, 3, device=dev, requires_grad=True)
+    color, radii, depth, alpha = R.rasterize_gaussians_split(t["means3D"], m2d, t["opacities"], t["scales"], t["rotations"],
+                                                             tuple(leaves), s)
+    ((color * gup[0]).sum() + (depth * gup[1]).sum() + (alpha * gup[2]).sum()).backward()
+    assert torch.equal(color, fa[0]) and torch.equal(radii, fa[1])
+    for k, x in enumerate(leaves):
+        if x is not None:
+            close(f"leaf{k}", plain[k], x.grad)
+    report("split_sh_layout", P=P, n0=n0, R=int(fa[4].num_rendered))
+
+
 def test_near_plane_and_lateral_clamp(dev):
     """z in [0.1, 8.1]: some Gaussians behind the 0.2 near plane (culled), some so close that their
     splats cover hundreds of tiles and the 1.3*tanfov clamp of A.4 is active (zeroed x/y gradient)."""
