@@ -72,18 +72,23 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The sampler runs from
+    the start of the warm-up (the GPU is loaded without a gap from there to the end of the timed region); every row is
+    stamped on arrival, and the rows that fall inside the timed region are the ones reported.  The timed region of the
+    default run lasts a few tens of milliseconds -- shorter than nvidia-smi's sampling period -- so when no row landed in
+    it the rows taken under the same uninterrupted load just before it are used, and `window` says so."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.rows, self.proc, self.idx = [], None, gpu_index
+        self.t_load = self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -91,15 +96,29 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def under_load(self):          # the warm-up has started: rows from here on see a busy GPU
+        self.t_load = time.perf_counter()
+
+    def n_under_load(self):
+        return sum(1 for t, _ in self.rows if self.t_load is not None and t >= self.t_load + 0.05)
+
+    def timed(self, t0, t1):
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
+        rows = list(self.rows)
+        inside = [r for t, r in rows if self.t0 is not None and self.t0 <= t <= self.t1]
+        window = "timed region"
+        if not inside:
+            inside = [r for t, r in rows if self.t_load is not None and self.t_load + 0.05 <= t <= (self.t1 or t)]
+            window = "warm-up + timed region (one uninterrupted load; the timed region is shorter than the sampling period)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -108,7 +127,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -244,6 +263,7 @@ def main():
     ap.add_argument("--no-train-step", action="store_true")
     ap.add_argument("--no-standin", action="store_true")
     ap.add_argument("--no-batch8", action="store_true")
+    ap.add_argument("--no-config2", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -298,7 +318,8 @@ def main():
         flat.all_reduce()
         got = flat.flat.clone()
         dist.all_reduce(mine, op=dist.ReduceOp.SUM)                       # NCCL on a private copy of the same data
-        err_nccl = float((got - mine).abs().max())       # dyadic values: any summation order gives the same bits
+        # dyadic values: any summation order gives the same bits (over the fields: the tail padding belongs to no field)
+        err_nccl = float((got - mine)[:flat.payload_floats].abs().max())
         sm = flat.views["means3D"]                         # a dense block against its closed form
         off = (sm.data_ptr() - flat.flat.data_ptr()) // 4
         want = base[off:off + sm.numel()] * (world * (world + 1) // 2)
@@ -313,19 +334,39 @@ def main():
         assert allreduce_check["ok"], allreduce_check
 
     # ---------------- device-resident throughput (value) ----------------
-    for i in range(W_):
-        wl.step(i)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.2)               # nvidia-smi is up and printing before the load starts
+        sampler.under_load()
+    for i in range(W_):
+        wl.step(i)
+    # extra untimed steps (same on every rank) until the clock sampler has seen the loaded GPU a few times: the timed
+    # region follows without a gap, so these rows describe its clocks even if none lands inside it
+    settle = 0
+    while True:
+        go = torch.tensor([1 if (rank == 0 and sampler.proc is not None and sampler.n_under_load() < 4 and settle < 2000) else 0], device=dev)
+        if world > 1:
+            dist.broadcast(go, 0)
+        if int(go.item()) == 0:
+            break
+        for i in range(16):
+            wl.step(W_ + settle + i)
+        settle += 16
+    barrier()
     wl.R_seen.clear()
     l0 = lib.scgr_kernel_launch_count()
     nc0 = R.need_capacity_count
-    ms_step = timed(lambda i: wl.step(W_ + i), K, barrier, dev, world)
+    t_0 = time.perf_counter()
+    ms_step = timed(lambda i: wl.step(W_ + settle + i), K, barrier, dev, world)
+    t_1 = time.perf_counter()
     launches = lib.scgr_kernel_launch_count() - l0
     need_capacity_hits = R.need_capacity_count - nc0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        sampler.timed(t_0, t_1)
+        clocks = sampler.stop()
+        clocks["extra_untimed_steps_before_timing"] = settle
     value = world * 1000.0 / ms_step
     R_list = list(wl.R_seen)
     R_mean = sum(R_list) / len(R_list)
@@ -519,9 +560,14 @@ def main():
             pk, _ = peaks()
             ku = train_step.get("fused", {}).get("kernel_us_per_step", {})
             n_ray, n_bg = train_step["n_ray"], train_step["n_bg"]
-            alg = {"assemble_forward": n_ray * 488 + n_bg * 476, "assemble_backward": P_GAUSS * 508,
-                   "adam": (n_ray * 57 + n_bg * 59) * 28}                # csrc/model.cu: algorithmic bytes per launch
+            # csrc/model.cu: algorithmic bytes per launch.  Default (split SH layout): the assembly kernels move the small
+            # arrays only (ray set 60 B raw in, free set 44 B; 44 B out; backward 44 grads + raw in, 36 / 44 out)
+            alg = {"assemble_forward": n_ray * 104 + n_bg * 88, "assemble_backward": n_ray * (44 + 60 + 36) + n_bg * (44 + 44 + 44),
+                   "adam": (n_ray * 57 + n_bg * 59) * 28}
             train_step["hbm_frac"] = {k: alg[k] / (ku[k] * 1e-6) / 1e9 / pk for k in alg if ku.get(k)}
+            ka = train_step.get("fused_assembled_sh", {}).get("kernel_us_per_step", {})
+            alg_a = {"assemble_forward": n_ray * 488 + n_bg * 476, "assemble_backward": P_GAUSS * 508}
+            train_step["hbm_frac_assembled_sh"] = {k: alg_a[k] / (ka[k] * 1e-6) / 1e9 / pk for k in alg_a if ka.get(k)}
         except Exception as e:             # pragma: no cover  (never let the extra entry take the metric down)
             train_step = {"error": repr(e)[:300]}
 
@@ -530,7 +576,7 @@ def main():
     # every step.  ~260 us of GPU work per step: the regime is host-bound, so what matters is whether host and GPU
     # overlap -- "fused" (default) blocks once per forward on R like the reference does, "async" never does.
     config2 = None
-    if world == 1 and args.config == 3:
+    if world == 1 and args.config == 3 and not args.no_config2:
         try:
             from scgaussian_b200 import synthetic as O2
             P2, W2, H2 = 30_000, 504, 378

@@ -190,7 +190,10 @@ __device__ __forceinline__ uint32_t peers_by_ballot(const uint32_t d, const bool
 // RANGES (last tile-partition pass): instead of writing the sorted keys, derive the per-tile
 // [start, end) ranges (A.7) on the fly -- inside a CTA the reordered items are sorted by full key,
 // so every CTA-local run boundary contributes an atomicMin(start) / atomicMax(end).
-template <int THREADS, int ITEMS, bool BALLOT, bool RANGES>
+// MATCH: how a lane finds its peers (lanes of the warp holding the same digit) -- 0: MATCH.ANY, 1: one ballot per digit
+// bit, 2: atomic OR of the lane's bit into a per-warp table of 256 masks in shared memory (one ATOMS + one LDS per item
+// whatever the digit width; the pass is issue-bound, and the ballots were 40 % of its instructions).
+template <int THREADS, int ITEMS, int MATCH, bool RANGES>
 __global__ void __launch_bounds__(THREADS)
 onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
@@ -207,6 +210,8 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     uint32_t* const s_warp = s_gbase + RADIX_BINS;           // [32]
     uint32_t& s_tile = s_warp[32];                           // [1] (+3 pad)
     uint16_t (*s_cnt)[RADIX_BINS] = reinterpret_cast<uint16_t (*)[RADIX_BINS]>(s_warp + 36);   // [WARPS][256] counts -> offsets
+    // MATCH == 2: [WARPS][2][256] peer masks, ping-pong over the items so that a leader's reset never races the next item
+    uint32_t (*s_match)[2][RADIX_BINS] = reinterpret_cast<uint32_t (*)[2][RADIX_BINS]>(&s_cnt[WARPS][0]);
 
     const uint32_t* ghist = sweep;
     uint32_t* ticket = sweep + 256;
@@ -214,6 +219,8 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     for (int i = threadIdx.x; i < WARPS * RADIX_BINS; i += THREADS) (&s_cnt[0][0])[i] = 0;
+    if (MATCH == 2)
+        for (int i = threadIdx.x; i < WARPS * 2 * RADIX_BINS; i += THREADS) (&s_match[0][0][0])[i] = 0u;
     if (threadIdx.x < RADIX_BINS) s_start[threadIdx.x] = 0u;
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -244,23 +251,33 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     if (threadIdx.x < RADIX_BINS)
         st_volatile(lookback + (size_t)tile * RADIX_BINS + threadIdx.x,
                     (tile == 0 ? FLAG_INCLUSIVE : FLAG_PARTIAL) | s_start[threadIdx.x]);
+    if (MATCH != 2) {
 #pragma unroll
-    for (int it = 0; it < ITEMS; it++) {
-        const bool valid = base + w * PER_WARP + it * 32 + lane < n;
-        const uint32_t d = (key[it] >> shift) & mask;
-        // invalid lanes become singletons that match nobody
-        peers[it] = BALLOT ? peers_by_ballot(d, valid, nbits)
-                           : __match_any_sync(0xffffffffu, valid ? d : (0x10000u | (uint32_t)lane));
+        for (int it = 0; it < ITEMS; it++) {
+            const bool valid = base + w * PER_WARP + it * 32 + lane < n;
+            const uint32_t d = (key[it] >> shift) & mask;
+            // invalid lanes become singletons that match nobody
+            peers[it] = MATCH == 1 ? peers_by_ballot(d, valid, nbits)
+                                   : __match_any_sync(0xffffffffu, valid ? d : (0x10000u | (uint32_t)lane));
+        }
     }
 #pragma unroll
     for (int it = 0; it < ITEMS; it++) {
         const bool valid = base + w * PER_WARP + it * 32 + lane < n;
         const uint32_t d = (key[it] >> shift) & mask;
+        if (MATCH == 2) {
+            uint32_t* const mm = s_match[w][it & 1];
+            if (valid) atomicOr(&mm[d], 1u << lane);
+            __syncwarp();
+            peers[it] = valid ? mm[d] : (1u << lane);
+        }
         const int leader = __ffs(peers[it]) - 1;
         uint32_t c = 0u;
+        if (MATCH == 2) __syncwarp();          // every peer has read the mask before its leader clears it
         if (valid && lane == leader) {
             c = s_cnt[w][d];
             s_cnt[w][d] = (uint16_t)(c + __popc(peers[it]));
+            if (MATCH == 2) s_match[w][it & 1][d] = 0u;      // (this table is next used two items on, two barriers away)
         }
         c = __shfl_sync(0xffffffffu, c, leader);
         rank[it] = c + __popc(peers[it] & lt_mask);
@@ -341,8 +358,9 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     }
 }
 
-constexpr size_t onesweep_smem_bytes(int threads) {
-    return (size_t)(2 * RADIX_TILE + 2 * RADIX_BINS + 36) * 4 + (size_t)(threads / 32) * RADIX_BINS * 2;
+constexpr size_t onesweep_smem_bytes(int threads, int match) {
+    return (size_t)(2 * RADIX_TILE + 2 * RADIX_BINS + 36) * 4 + (size_t)(threads / 32) * RADIX_BINS * 2 +
+           (match == 2 ? (size_t)(threads / 32) * 2 * RADIX_BINS * 4 : 0);
 }
 
 __global__ void init_ranges_kernel(uint2* __restrict__ ranges, uint32_t n) {
@@ -355,12 +373,12 @@ int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-template <int THREADS, int ITEMS, bool BALLOT, bool RANGES>
+template <int THREADS, int ITEMS, int MATCH, bool RANGES>
 void launch_onesweep_variant(uint32_t nb, const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout,
                              const int64_t* n_dev, int64_t n_host, int64_t cap, int shift, uint32_t mask,
                              uint32_t* sweep, uint2* ranges, const Launch& L) {
-    auto kern = onesweep_pass_kernel<THREADS, ITEMS, BALLOT, RANGES>;
-    constexpr size_t smem = onesweep_smem_bytes(THREADS);
+    auto kern = onesweep_pass_kernel<THREADS, ITEMS, MATCH, RANGES>;
+    constexpr size_t smem = onesweep_smem_bytes(THREADS, MATCH);
     static bool configured = false;     // per-process, idempotent
     if (!configured) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -369,20 +387,24 @@ void launch_onesweep_variant(uint32_t nb, const uint32_t* kin, const uint32_t* v
     kern<<<nb, THREADS, smem, L.stream>>>(kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges);
 }
 
-// variant 1: 256 threads x 16 items; 2: 512 x 8; 4: 1024 x 4 (all ballot ranking); 0: 256 x 16 with MATCH.ANY
+// variant 1: 256 threads x 16 items; 2: 512 x 8; 4: 1024 x 4 (all ballot ranking); 0: 256 x 16, 3: 512 x 8 with MATCH.ANY;
+// 5: 512 x 8, 6: 1024 x 4, 7: 256 x 16 with the shared-memory atomic-OR match
 template <bool RANGES>
 void launch_onesweep(const char* name, const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout,
                      const int64_t* n_dev, int64_t n_host, int64_t cap, int shift, uint32_t mask, uint32_t* sweep,
                      uint2* ranges, const Launch& L) {
-    static const int variant = env_int("SCGR_SORT_VARIANT", 2);
+    static const int variant = env_int("SCGR_SORT_VARIANT", 5);
     const uint32_t nb = radix_blocks(cap > 0 ? cap : 1);
     begin_kernel(name, L);
     switch (variant) {
-        case 0: launch_onesweep_variant<256, 16, false, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
-        case 1: launch_onesweep_variant<256, 16, true, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
-        case 3: launch_onesweep_variant<512, 8, false, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
-        case 4: launch_onesweep_variant<1024, 4, true, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
-        default: launch_onesweep_variant<512, 8, true, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
+        default: launch_onesweep_variant<512, 8, 2, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
+        case 6: launch_onesweep_variant<1024, 4, 2, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
+        case 7: launch_onesweep_variant<256, 16, 2, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
+        case 0: launch_onesweep_variant<256, 16, 0, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
+        case 1: launch_onesweep_variant<256, 16, 1, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
+        case 3: launch_onesweep_variant<512, 8, 0, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
+        case 4: launch_onesweep_variant<1024, 4, 1, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
+        case 2: launch_onesweep_variant<512, 8, 1, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
     }
     check_launch(name, L);
 }

@@ -260,20 +260,52 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
     const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
     const bool use_sh = SPLIT || g.shs != nullptr;
 
+    // the thread's own small inputs first: their loads are in flight together with the CTA's SH block below (a load cannot
+    // be moved across the barrier that closes the staging, so left after it they would start a second latency period)
+    float3 p = make_float3(0.f, 0.f, 0.f), sc_in = make_float3(0.f, 0.f, 0.f);
+    float4 q_in = make_float4(0.f, 0.f, 0.f, 0.f);
+    float opac = 0.f;
+    const bool has_sr = g.cov3D_precomp == nullptr;
+    if (i < P) {
+        p = load3(g.means3D, i);
+        opac = __ldg(g.opacities + i);
+        if (has_sr) {
+            q_in = __ldg(reinterpret_cast<const float4*>(g.rotations) + i);
+            sc_in = load3(g.scales, i);
+        }
+    }
+
+    const float* my_dc = nullptr;      // SPLIT: this thread's rows inside the staging buffer
+    const float* my_rest = nullptr;
     if (SPLIT) {
+        // The rows of a set are contiguous in features_dc (3 floats each) and features_rest (45 floats each): every run is
+        // copied as ONE flat stream -- 128-bit loads between a scalar head and tail, the shared-memory copy placed at
+        // the same offset modulo 16 bytes as its source -- and kept in that layout: a thread then reads its own row with
+        // a stride of 45 / 3 words, which is odd and therefore free of bank conflicts.
         float* const sf = reinterpret_cast<float*>(s_sh);
+        float* const rest_s = sf;                                    // [128 * 45 + 16]
+        float* const dc_s = sf + PRE_THREADS * SH_REST + 16;         // [128 * 3 + 16]
         const int row0 = blockIdx.x * PRE_THREADS;
+        int cur_rest = 0, cur_dc = 0;
+        auto stage = [&](const float* __restrict__ src, const int n, float* dst, int& cursor) {
+            const int ms = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);
+            const int off = ((cursor + 3) & ~3) + ms;
+            const int head = min(n, (4 - ms) & 3);
+            const int body4 = (n - head) >> 2;
+            if ((int)threadIdx.x < head) dst[off + threadIdx.x] = __ldg(src + threadIdx.x);
+            const float4* s4 = reinterpret_cast<const float4*>(src + head);
+            float4* d4 = reinterpret_cast<float4*>(dst + off + head);
+            for (int q = threadIdx.x; q < body4; q += PRE_THREADS) d4[q] = __ldg(s4 + q);
+            const int done = head + 4 * body4;
+            if ((int)threadIdx.x < n - done) dst[off + done + threadIdx.x] = __ldg(src + done + threadIdx.x);
+            cursor = off + n;
+            return off;
+        };
         for_each_split_run(g, row0, min(PRE_THREADS, P - row0), [&](const int k, const int j0, const int cnt, const int r0) {
-            const float* dc = g.sh_dc[k] + (size_t)j0 * SH_DC;
-            const float* rest = g.sh_rest[k] + (size_t)j0 * SH_REST;
-            for (int f = threadIdx.x; f < cnt * SH_DC; f += PRE_THREADS) {
-                const int r = f / SH_DC;
-                sf[(r0 + r) * SH_ROW_PAD + (f - r * SH_DC)] = __ldg(dc + f);
-            }
-            for (int f = threadIdx.x; f < cnt * SH_REST; f += PRE_THREADS) {
-                const int r = f / SH_REST;
-                sf[(r0 + r) * SH_ROW_PAD + SH_DC + (f - r * SH_REST)] = __ldg(rest + f);
-            }
+            const int o_dc = stage(g.sh_dc[k] + (size_t)j0 * SH_DC, cnt * SH_DC, dc_s, cur_dc);
+            const int o_rest = stage(g.sh_rest[k] + (size_t)j0 * SH_REST, cnt * SH_REST, rest_s, cur_rest);
+            const int r = (int)threadIdx.x - r0;
+            if (r >= 0 && r < cnt) { my_dc = dc_s + o_dc + r * SH_DC; my_rest = rest_s + o_rest + r * SH_REST; }
         });
         __syncthreads();
     } else if (SH_FAST && use_sh) {
@@ -294,7 +326,6 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
 
     Camera cam;
     load_camera(v, cam);
-    const float3 p = load3(g.means3D, i);
     const float zv = view_depth(p, cam.V[2], cam.V[6], cam.V[10], cam.V[14]);
 
     bool alive = zv > NEAR_Z;   // A.1
@@ -313,12 +344,11 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
         const float h3 = p.x * PM[3] + p.y * PM[7] + p.z * PM[11] + PM[15];
         const float pw = 1.f / (h3 + 1e-7f);                          // A.2
         float c6[6];
-        if (g.cov3D_precomp) {
+        if (!has_sr) {
 #pragma unroll
             for (int k = 0; k < 6; k++) c6[k] = __ldg(g.cov3D_precomp + 6 * (size_t)i + k);
         } else {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(g.rotations) + i);
-            cov3d_from_scale_rot(load3(g.scales, i), v.scale_modifier, q, c6);   // A.3
+            cov3d_from_scale_rot(sc_in, v.scale_modifier, q_in, c6);   // A.3
         }
         project_cov(cam, v, p, c6, pr);                               // A.4
         det = pr.a * pr.c - pr.b * pr.b;
@@ -357,7 +387,17 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
         sh_basis(v.sh_degree, d, b);
         const int nk = (v.sh_degree + 1) * (v.sh_degree + 1);
         float acc[3] = {0.f, 0.f, 0.f};
-        if (SH_FAST) {
+        if (SPLIT) {
+            // (same order of accumulation per channel as the assembled layout below: bit-identical colours)
+#pragma unroll
+            for (int c = 0; c < 3; c++) acc[c] += b[0] * my_dc[c];
+#pragma unroll
+            for (int k = 1; k < 16; k++)
+                if (k < nk) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) acc[c] += b[k] * my_rest[3 * (k - 1) + c];
+                }
+        } else if (SH_FAST) {
             const float4* row = s_sh + threadIdx.x * SH_ROW_F4_PAD;
 #pragma unroll
             for (int cc = 0; cc < SH_ROW_F4; cc++) {
@@ -385,7 +425,6 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
     }
 
     const float dinv = 1.f / det;
-    const float opac = __ldg(g.opacities + i);
     // render-ready conic: power2 = cA dx^2 + cB dx dy + cC dy^2 = log2(e) * (-0.5 (A dx^2 + C dy^2) - B dx dy)
     constexpr float LOG2E = 1.4426950408889634f;
     Record r;
@@ -518,15 +557,22 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
             }
         }
     }
+    // SPLIT: a row of the model's arrays is 3 + 45 floats at 4-byte alignment.  16 lanes share a row (lane l moves floats l,
+    // l + 16, l + 32 of features_rest, lanes 0..2 also one float of features_dc), so the row's set and address are
+    // worked out once per lane and row, not once per float.
+    constexpr int RL = 16, RG = PB_T / RL;        // lanes per row, rows in flight per CTA
+    const int rl = tid & (RL - 1), rgrp = tid / RL;
     if (SPLIT && !ACC) {
-        for_each_split_run(g, row0, nrows, [&](const int k, const int j0, const int cnt, const int r0) {
-            float* dc = out.dL_dsh_dc[k] + (size_t)j0 * SH_DC;
-            float* rest = out.dL_dsh_rest[k] + (size_t)j0 * SH_REST;
-            for (int f = tid; f < cnt * SH_DC; f += PB_T)
-                if (!s_live[r0 + f / SH_DC]) dc[f] = 0.f;
-            for (int f = tid; f < cnt * SH_REST; f += PB_T)
-                if (!s_live[r0 + f / SH_REST]) rest[f] = 0.f;
-        });
+        for (int r = rgrp; r < nrows; r += RG) {
+            if (s_live[r]) continue;
+            const int gi = row0 + r;
+            const int k = gi >= g.sh_n0;
+            const size_t j = (size_t)(gi - (k ? g.sh_n0 : 0));
+            float* rest = (k ? out.dL_dsh_rest[1] : out.dL_dsh_rest[0]) + j * SH_REST;
+            rest[rl] = 0.f; rest[rl + RL] = 0.f;
+            if (rl + 2 * RL < SH_REST) rest[rl + 2 * RL] = 0.f;
+            if (rl < SH_DC) ((k ? out.dL_dsh_dc[1] : out.dL_dsh_dc[0]) + j * SH_DC)[rl] = 0.f;
+        }
     } else if (SH_FAST && use_sh && !ACC) {
         float4* dst = reinterpret_cast<float4*>(out.dL_dshs) + (size_t)row0 * SH_ROW_F4;
         const int nf4 = nrows * SH_ROW_F4;
@@ -544,15 +590,17 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     if (SPLIT) {
         // the 48 floats of every live row of the round, from whichever set the row belongs to
         float* const sf = reinterpret_cast<float*>(s_sh);
-        for (int f = tid; f < in_round * 48; f += PB_T) {
-            const int r = f / 48, e = f - r * 48;
+        for (int r = rgrp; r < in_round; r += RG) {
             const int gi = row0 + (int)s_list[first + r];
             const int k = gi >= g.sh_n0;
             const size_t j = (size_t)(gi - (k ? g.sh_n0 : 0));
             // (ternaries, not g.sh_dc[k]: a run-time index into the kernel parameters would spill them to local memory)
-            const float* dc = k ? g.sh_dc[1] : g.sh_dc[0];
-            const float* rest = k ? g.sh_rest[1] : g.sh_rest[0];
-            sf[r * SH_ROW_PAD + e] = e < SH_DC ? __ldg(dc + j * SH_DC + e) : __ldg(rest + j * SH_REST + (e - SH_DC));
+            const float* rest = (k ? g.sh_rest[1] : g.sh_rest[0]) + j * SH_REST;
+            float* const row = sf + r * SH_ROW_PAD;
+            row[SH_DC + rl] = __ldg(rest + rl);
+            row[SH_DC + rl + RL] = __ldg(rest + rl + RL);
+            if (rl + 2 * RL < SH_REST) row[SH_DC + rl + 2 * RL] = __ldg(rest + rl + 2 * RL);
+            if (rl < SH_DC) row[rl] = __ldg((k ? g.sh_dc[1] : g.sh_dc[0]) + j * SH_DC + rl);
         }
     } else if (SH_FAST && use_sh) {
         const float4* src = reinterpret_cast<const float4*>(g.shs) + (size_t)row0 * SH_ROW_F4;
@@ -780,14 +828,17 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
         // the gradient rows of the round sit in smem (written in place above): back to the model's own arrays
         __syncthreads();
         const float* const sf = reinterpret_cast<const float*>(s_sh);
-        for (int f = tid; f < in_round * 48; f += PB_T) {
-            const int r = f / 48, e = f - r * 48;
+        for (int r = rgrp; r < in_round; r += RG) {
             const int gi = row0 + (int)s_list[first + r];
             const int k = gi >= g.sh_n0;
             const size_t j = (size_t)(gi - (k ? g.sh_n0 : 0));
-            float* d1 = e < SH_DC ? (k ? out.dL_dsh_dc[1] : out.dL_dsh_dc[0]) + j * SH_DC + e
-                                  : (k ? out.dL_dsh_rest[1] : out.dL_dsh_rest[0]) + j * SH_REST + (e - SH_DC);
-            if (ACC) *d1 += sf[r * SH_ROW_PAD + e]; else *d1 = sf[r * SH_ROW_PAD + e];
+            float* rest = (k ? out.dL_dsh_rest[1] : out.dL_dsh_rest[0]) + j * SH_REST;
+            const float* const row = sf + r * SH_ROW_PAD;
+            auto put1 = [&](float* d1, const float x) { if (ACC) *d1 += x; else *d1 = x; };
+            put1(rest + rl, row[SH_DC + rl]);
+            put1(rest + rl + RL, row[SH_DC + rl + RL]);
+            if (rl + 2 * RL < SH_REST) put1(rest + rl + 2 * RL, row[SH_DC + rl + 2 * RL]);
+            if (rl < SH_DC) put1((k ? out.dL_dsh_dc[1] : out.dL_dsh_dc[0]) + j * SH_DC + rl, row[rl]);
         }
         __syncthreads();      // the staging buffer is reused by the next round
     } else if (SH_FAST && use_sh) {

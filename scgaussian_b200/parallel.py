@@ -84,6 +84,7 @@ class FlatGradBuffer:
             if name == "shs":
                 self.rows_offset = o
             o += n
+            self.payload_floats = o - n + numel      # end of the last field: what follows is padding up to 4 * world floats
         # means2D is returned by the op but is not a parameter gradient: keep it outside the flat buffer
         self.means2D = torch.empty(P, 3, dtype=torch.float32, device=device)
 
@@ -170,6 +171,12 @@ class FlatGradBuffer:
             hdl.barrier(channel=2)           # every shard has been broadcast
             return None
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+    @property
+    def payload(self) -> torch.Tensor:
+        """The flat buffer without its tail padding (up to 4 * world - 1 floats that no field owns: the dense paths sum
+        them, the row-sparse shot has no reason to)."""
+        return self.flat[:self.payload_floats]
 
     def nbytes(self) -> int:
         return self.flat.numel() * 4

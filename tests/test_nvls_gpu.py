@@ -47,16 +47,19 @@ def _worker(rank, world, port, P, out_dir):
             mine = fill(base * (rank + 1 + rep), density, 1000 * rep + rank)
             buf.all_reduce()
             dist.all_reduce(mine)                                   # NCCL, dense, on a private copy of the same data
-            res[f"equals_nccl_{rep}"] = bool(torch.equal(buf.flat, mine))    # dyadic values: any summation order, same bits
+            # dyadic values: any summation order, same bits.  (Compared over the fields: with 12 P % world != 0 -- P = 1001 at
+            # 8 ranks -- the buffer ends in padding that NCCL sums and the row-sparse shot rightly never touches.)
+            npay = buf.payload_floats
+            res[f"equals_nccl_{rep}"] = bool(torch.equal(buf.payload, mine[:npay]))
             res[f"live_max_{rep}"] = float(buf.views["live"].max())
         g = torch.Generator(device=dev).manual_seed(100 + rank)
         mine = fill(torch.randn(n, device=dev, generator=g), 0.2, 77 + rank)
         buf.all_reduce()
         dist.all_reduce(mine)
-        res["random_max_abs_diff_vs_nccl"] = float((buf.flat - mine).abs().max())
+        res["random_max_abs_diff_vs_nccl"] = float((buf.payload - mine[:buf.payload_floats]).abs().max())
         res["random_scale"] = float(mine.abs().max())
         # replicas must be identical on every rank (one reduction per element, then a broadcast)
-        digest = buf.flat.double().sum().reshape(1)
+        digest = buf.payload.double().sum().reshape(1)
         lo, hi = digest.clone(), digest.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)

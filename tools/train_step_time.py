@@ -3,8 +3,10 @@ train.py:135-208 runs it -- raw parameters -> activations + assembly -> rasteriz
 densification statistics (train.py:192-193) -> Adam on the 12 parameter groups -- in two variants over the SAME
 rasterizer and loss kernels:
 
-  fused      scgaussian_b200.model.render (one assembly kernel each way) + model.add_densification_stats (one launch,
-             no host sync) + optim.step_all (one Adam launch)
+  fused      scgaussian_b200.model.render (one assembly kernel each way for the small arrays; the operator reads the SH
+             coefficients in place and writes dL/dfeatures_* itself) + model.add_densification_stats (one launch, no
+             host sync) + optim.step_all (one Adam launch)
+  fused_assembled_sh   the same with the SH coefficients going through the assembled [P,16,3] copy (SCGR_SPLIT_SH=0)
   torch      the reference's chain of torch activations / cats, its boolean-mask statistics statements and its two
              torch.optim.Adam optimizers
 
@@ -58,7 +60,7 @@ def _groups(pc, prefix):
     return out
 
 
-def measure(sc, cam_d, dev, W, H, steps=20, warm=5, variants=("fused", "torch")):
+def measure(sc, cam_d, dev, W, H, steps=20, warm=5, variants=("fused", "fused_assembled_sh", "torch")):
     """sc / cam_d: scgaussian_b200.synthetic.synth_scene / make_camera outputs (CPU tensors).  Returns the dict the
     command-line tool prints."""
     import ctypes as C
@@ -96,8 +98,12 @@ def measure(sc, cam_d, dev, W, H, steps=20, warm=5, variants=("fused", "torch"))
         return {"render": color, "radii": radii, "viewspace_points": ssp, "visibility_filter": radii > 0}
 
     def run(variant):
+        # "fused": the operator reads features_dc / features_rest in place (split SH layout, the default);
+        # "fused_assembled_sh": the same passes through the assembled [P,16,3] copy (SCGR_SPLIT_SH=0), for comparison
+        os.environ["SCGR_SPLIT_SH"] = "0" if variant == "fused_assembled_sh" else "1"
+        fused = variant.startswith("fused")
         pc = _make_pc(sc, n_ray, dev)
-        if variant == "fused":
+        if fused:
             oa, ob = optim.Adam(_groups(pc, ""), lr=0.0, eps=1e-15), optim.Adam(_groups(pc, "bg"), lr=0.0, eps=1e-15)
         else:
             oa = torch.optim.Adam(_groups(pc, ""), lr=0.0, eps=1e-15)
@@ -105,18 +111,18 @@ def measure(sc, cam_d, dev, W, H, steps=20, warm=5, variants=("fused", "torch"))
         losses = []
 
         def step():
-            out = model.render(cam, pc, pipe, bg) if variant == "fused" else render_torch(pc)
+            out = model.render(cam, pc, pipe, bg) if fused else render_torch(pc)
             loss = photometric_loss(out["render"], gt, 0.2)
             loss.backward()
             # reference train.py:190-193 (every iteration while iteration < densify_until_iter = the whole default run)
-            if variant == "fused":
+            if fused:
                 model.add_densification_stats(pc, out["viewspace_points"], None, out["radii"])
             else:
                 vis, radii = out["visibility_filter"], out["radii"]
                 pc.max_radii2D[vis] = torch.max(pc.max_radii2D[vis], radii[vis])
                 pc.xyz_gradient_accum[vis] += torch.norm(out["viewspace_points"].grad[vis, :2], dim=-1, keepdim=True)
                 pc.denom[vis] += 1
-            if variant == "fused":
+            if fused:
                 optim.step_all(oa, ob)
             else:
                 oa.step()
@@ -136,7 +142,7 @@ def measure(sc, cam_d, dev, W, H, steps=20, warm=5, variants=("fused", "torch"))
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         res = {"ms_per_step": ms, "steps_per_s": 1e3 / ms, "loss_first": float(losses[0]), "loss_last": float(losses[-1])}
-        if variant == "fused":
+        if fused:
             # per-kernel times of 3 more steps (CUDA events bracketing every launch inside the library)
             lib = _lib.load()
             lib.scgr_profile_enable(1)
@@ -153,8 +159,14 @@ def measure(sc, cam_d, dev, W, H, steps=20, warm=5, variants=("fused", "torch"))
         return res
 
     res = {"P": P, "width": W, "height": H, "n_ray": n_ray, "n_bg": P - n_ray, "steps": steps, "warmup": warm}
-    for v in variants:
-        res[v] = run(v)
+    prev = os.environ.get("SCGR_SPLIT_SH")
+    try:
+        for v in variants:
+            res[v] = run(v)
+    finally:
+        os.environ.pop("SCGR_SPLIT_SH", None)
+        if prev is not None:
+            os.environ["SCGR_SPLIT_SH"] = prev
     if "fused" in res and "torch" in res:
         res["speedup"] = res["torch"]["ms_per_step"] / res["fused"]["ms_per_step"]
     return res
