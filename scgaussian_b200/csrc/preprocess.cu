@@ -249,16 +249,33 @@ depth_key_kernel(const float* __restrict__ means3D, const int P, const float* __
 // ------------------------------------------------------------------------------------------
 // SH_FAST: M == 16 and shs 16-byte aligned -> CTA-cooperative 128-bit staging through smem.
 // SPLIT (implies SH_FAST): the SH rows come from the model's features_dc / features_rest arrays of both sets.
-template <bool SH_FAST, bool SPLIT>
-__global__ void __launch_bounds__(PRE_THREADS)
+// TMA (SH_FAST, not SPLIT): every thread pulls the 192-byte row of its Gaussian into the padded staging buffer with one
+// bulk-async copy, completion on one mbarrier per CTA -- nothing waits for the rows until the geometry (projection,
+// covariance, radius, tile rectangle) of the Gaussian is done, where the register-staged variant spends 44 % of its warp
+// time stalled on the loads in front of the barrier that closes the staging (profiles/r02_preprocess.md).
+template <bool SH_FAST, bool SPLIT, bool TMA>
+__global__ void __launch_bounds__(PRE_THREADS, 8)
 preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __restrict__ rec,
                           uint32_t* __restrict__ tiles_touched,
                           uint2* __restrict__ rect, unsigned long long* __restrict__ tile_mask,
                           int32_t* __restrict__ radii) {
-    __shared__ float4 s_sh[SH_FAST ? PRE_THREADS * SH_ROW_F4_PAD : 1];
+    __shared__ __align__(16) float4 s_sh[SH_FAST ? PRE_THREADS * SH_ROW_F4_PAD : 1];
+    __shared__ __align__(8) unsigned long long s_bar;
     const int P = g.P;
     const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
     const bool use_sh = SPLIT || g.shs != nullptr;
+    const bool tma = TMA && use_sh;
+    if (tma) {
+        if (threadIdx.x == 0) {
+            const int nrows = min(PRE_THREADS, P - (int)blockIdx.x * PRE_THREADS);
+            mbar_init(&s_bar, 1);
+            mbar_fence_init();
+            mbar_expect_tx(&s_bar, (uint32_t)nrows * (uint32_t)(SH_ROW_F4 * sizeof(float4)));      // the one arrival of the phase
+        }
+        __syncthreads();
+        if (i < P)
+            bulk_g2s(&s_sh[threadIdx.x * SH_ROW_F4_PAD], g.shs + (size_t)i * (SH_ROW_F4 * 4), SH_ROW_F4 * sizeof(float4), &s_bar);
+    }
 
     // the thread's own small inputs first: their loads are in flight together with the CTA's SH block below (a load cannot
     // be moved across the barrier that closes the staging, so left after it they would start a second latency period)
@@ -308,7 +325,7 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
             if (r >= 0 && r < cnt) { my_dc = dc_s + o_dc + r * SH_DC; my_rest = rest_s + o_rest + r * SH_REST; }
         });
         __syncthreads();
-    } else if (SH_FAST && use_sh) {
+    } else if (SH_FAST && use_sh && !TMA) {
         // rows [block0, block0 + 128) are one contiguous run of 128*12 float4 in HBM.  (Fetching only the
         // rows of Gaussians in front of the near plane was tried: the test needs means3D first, and the
         // serialised load latencies cost 25 % on an all-visible scene.)
@@ -373,8 +390,10 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
         rect[i] = make_uint2(0u, 0u);
         tile_mask[i] = 0ull;
         rec[i].q2 = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));   // radius 0 marks "culled" for the backward
+        if (tma) mbar_wait(&s_bar, 0u);      // the CTA's shared memory must outlive the copies in flight
         return;
     }
+    if (tma) mbar_wait(&s_bar, 0u);
 
     // A.5 colour
     float3 rgb;
@@ -481,6 +500,7 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     __shared__ uint8_t s_live[PB_G];
     __shared__ uint8_t s_list[PB_G];              // local indices of the live Gaussians, compacted
     __shared__ int s_wcnt[PB_K][PB_T / 32];
+    __shared__ uint32_t s_wbal[PB_K][PB_T / 32];   // live mask of local rows [32 (k PB_T / 32 + w), + 32)
     const int P = g.P;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const bool use_sh = SPLIT || g.shs != nullptr;
@@ -509,7 +529,7 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
         }
         s_live[local] = own_live[k] ? 1 : 0;
         bal[k] = __ballot_sync(0xffffffffu, own_live[k]);
-        if (lane == 0) s_wcnt[k][wid] = __popc(bal[k]);
+        if (lane == 0) { s_wcnt[k][wid] = __popc(bal[k]); s_wbal[k][wid] = bal[k]; }
     }
     __syncthreads();
     int n_live = 0;
@@ -562,22 +582,34 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     // worked out once per lane and row, not once per float.
     constexpr int RL = 16, RG = PB_T / RL;        // lanes per row, rows in flight per CTA
     const int rl = tid & (RL - 1), rgrp = tid / RL;
-    if (SPLIT && !ACC) {
-        for (int r = rgrp; r < nrows; r += RG) {
-            if (s_live[r]) continue;
-            const int gi = row0 + r;
-            const int k = gi >= g.sh_n0;
-            const size_t j = (size_t)(gi - (k ? g.sh_n0 : 0));
-            float* rest = (k ? out.dL_dsh_rest[1] : out.dL_dsh_rest[0]) + j * SH_REST;
-            rest[rl] = 0.f; rest[rl + RL] = 0.f;
-            if (rl + 2 * RL < SH_REST) rest[rl + 2 * RL] = 0.f;
-            if (rl < SH_DC) ((k ? out.dL_dsh_dc[1] : out.dL_dsh_dc[0]) + j * SH_DC)[rl] = 0.f;
+    // Zero rows of dL/dSH for the Gaussians without gradient: every group of RL lanes walks the dead rows of its residue class
+    // (row % RG) by bit scanning the live masks -- no memory access decides a branch.
+    if (SH_FAST && use_sh && !ACC) {
+#pragma unroll
+        for (int wd = 0; wd < PB_G / 32; wd++) {
+            const int base = 32 * wd;
+            if (base >= nrows) break;
+            const uint32_t valid = nrows - base >= 32 ? 0xffffffffu : ((1u << (nrows - base)) - 1u);
+            const uint32_t livew = (&s_wbal[0][0])[wd];
+            constexpr uint32_t CLASS = RG == 4 ? 0x11111111u : (RG == 2 ? 0x55555555u : (RG == 8 ? 0x01010101u : 0xffffffffu));
+            static_assert(RG == 1 || RG == 2 || RG == 4 || RG == 8, "rows in flight per CTA");
+            uint32_t bits = ~livew & valid & (CLASS << rgrp);
+            while (bits) {
+                const int r = base + __ffs(bits) - 1;
+                bits &= bits - 1u;
+                const int gi = row0 + r;
+                if (SPLIT) {
+                    const int k = gi >= g.sh_n0;
+                    const size_t j = (size_t)(gi - (k ? g.sh_n0 : 0));
+                    float* rest = (k ? out.dL_dsh_rest[1] : out.dL_dsh_rest[0]) + j * SH_REST;
+                    rest[rl] = 0.f; rest[rl + RL] = 0.f;
+                    if (rl + 2 * RL < SH_REST) rest[rl + 2 * RL] = 0.f;
+                    if (rl < SH_DC) ((k ? out.dL_dsh_dc[1] : out.dL_dsh_dc[0]) + j * SH_DC)[rl] = 0.f;
+                } else if (rl < SH_ROW_F4) {
+                    reinterpret_cast<float4*>(out.dL_dshs)[(size_t)gi * SH_ROW_F4 + rl] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
         }
-    } else if (SH_FAST && use_sh && !ACC) {
-        float4* dst = reinterpret_cast<float4*>(out.dL_dshs) + (size_t)row0 * SH_ROW_F4;
-        const int nf4 = nrows * SH_ROW_F4;
-        for (int f = tid; f < nf4; f += PB_T)
-            if (!s_live[f / SH_ROW_F4]) dst[f] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
 
@@ -590,23 +622,61 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     if (SPLIT) {
         // the 48 floats of every live row of the round, from whichever set the row belongs to
         float* const sf = reinterpret_cast<float*>(s_sh);
-        for (int r = rgrp; r < in_round; r += RG) {
-            const int gi = row0 + (int)s_list[first + r];
-            const int k = gi >= g.sh_n0;
-            const size_t j = (size_t)(gi - (k ? g.sh_n0 : 0));
-            // (ternaries, not g.sh_dc[k]: a run-time index into the kernel parameters would spill them to local memory)
-            const float* rest = (k ? g.sh_rest[1] : g.sh_rest[0]) + j * SH_REST;
-            float* const row = sf + r * SH_ROW_PAD;
-            row[SH_DC + rl] = __ldg(rest + rl);
-            row[SH_DC + rl + RL] = __ldg(rest + rl + RL);
-            if (rl + 2 * RL < SH_REST) row[SH_DC + rl + 2 * RL] = __ldg(rest + rl + 2 * RL);
-            if (rl < SH_DC) row[rl] = __ldg((k ? g.sh_dc[1] : g.sh_dc[0]) + j * SH_DC + rl);
+        // four rows per lane at a time: all their loads are issued before the first one is stored (a row's address comes
+        // from s_list, a byte array the compiler must assume the staging stores alias -- row by row the loads serialise)
+        constexpr int RU = 4;
+        for (int rb = rgrp; rb < in_round; rb += RU * RG) {
+            const float* rest[RU];
+            const float* dc[RU];
+            bool ok[RU];
+#pragma unroll
+            for (int u = 0; u < RU; u++) {
+                const int r = rb + u * RG;
+                ok[u] = r < in_round;
+                const int gi = row0 + (int)s_list[first + (ok[u] ? r : rb)];
+                const int k = gi >= g.sh_n0;
+                const size_t j = (size_t)(gi - (k ? g.sh_n0 : 0));
+                // (ternaries, not g.sh_dc[k]: a run-time index into the kernel parameters would spill them to local memory)
+                rest[u] = (k ? g.sh_rest[1] : g.sh_rest[0]) + j * SH_REST;
+                dc[u] = (k ? g.sh_dc[1] : g.sh_dc[0]) + j * SH_DC;
+            }
+            float x[RU][4];
+#pragma unroll
+            for (int u = 0; u < RU; u++) {
+                x[u][0] = ok[u] ? __ldg(rest[u] + rl) : 0.f;
+                x[u][1] = ok[u] ? __ldg(rest[u] + rl + RL) : 0.f;
+                x[u][2] = ok[u] && rl + 2 * RL < SH_REST ? __ldg(rest[u] + rl + 2 * RL) : 0.f;
+                x[u][3] = ok[u] && rl < SH_DC ? __ldg(dc[u] + rl) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < RU; u++) {
+                if (!ok[u]) continue;
+                float* const row = sf + (rb + u * RG) * SH_ROW_PAD;
+                row[SH_DC + rl] = x[u][0];
+                row[SH_DC + rl + RL] = x[u][1];
+                if (rl + 2 * RL < SH_REST) row[SH_DC + rl + 2 * RL] = x[u][2];
+                if (rl < SH_DC) row[rl] = x[u][3];
+            }
         }
     } else if (SH_FAST && use_sh) {
         const float4* src = reinterpret_cast<const float4*>(g.shs) + (size_t)row0 * SH_ROW_F4;
-        for (int f = tid; f < in_round * SH_ROW_F4; f += PB_T) {
-            const int r = f / SH_ROW_F4, c = f - r * SH_ROW_F4;
-            s_sh[r * SH_ROW_F4_PAD + c] = __ldg(src + (int)s_list[first + r] * SH_ROW_F4 + c);
+        // (four loads in flight per thread before the first store, for the reason given above)
+        constexpr int FU = 4;
+        const int nf = in_round * SH_ROW_F4;
+        for (int fb = tid; fb < nf; fb += FU * PB_T) {
+            float4 x[FU];
+            int dst[FU];
+#pragma unroll
+            for (int u = 0; u < FU; u++) {
+                const int f = fb + u * PB_T;
+                const int fc = f < nf ? f : fb;
+                const int r = fc / SH_ROW_F4, c = fc - r * SH_ROW_F4;
+                dst[u] = f < nf ? r * SH_ROW_F4_PAD + c : -1;
+                x[u] = __ldg(src + (int)s_list[first + r] * SH_ROW_F4 + c);
+            }
+#pragma unroll
+            for (int u = 0; u < FU; u++)
+                if (dst[u] >= 0) s_sh[dst[u]] = x[u];
         }
     }
     // (the per-Gaussian inputs below are fetched while the SH rows are in flight)
@@ -881,12 +951,15 @@ void launch_preprocess_forward(const ScgrView& v, const ScgrGaussians& g, const 
     if (g.P <= 0) return;
     const int blocks = (g.P + PRE_THREADS - 1) / PRE_THREADS;
     begin_kernel("preprocess_forward", L);
+    static const int tma = getenv("SCGR_TMA_PRE") ? atoi(getenv("SCGR_TMA_PRE")) : 1;
     if (sh_split(g))
-        preprocess_forward_kernel<true, true><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.tiles_touched, G.rect, G.tile_mask, radii);
+        preprocess_forward_kernel<true, true, false><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.tiles_touched, G.rect, G.tile_mask, radii);
+    else if (sh_fast_ok(g, nullptr) && tma)
+        preprocess_forward_kernel<true, false, true><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.tiles_touched, G.rect, G.tile_mask, radii);
     else if (sh_fast_ok(g, nullptr))
-        preprocess_forward_kernel<true, false><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.tiles_touched, G.rect, G.tile_mask, radii);
+        preprocess_forward_kernel<true, false, false><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.tiles_touched, G.rect, G.tile_mask, radii);
     else
-        preprocess_forward_kernel<false, false><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.tiles_touched, G.rect, G.tile_mask, radii);
+        preprocess_forward_kernel<false, false, false><<<blocks, PRE_THREADS, 0, L.stream>>>(v, g, G.rec, G.tiles_touched, G.rect, G.tile_mask, radii);
     check_launch("preprocess_forward", L);
 }
 

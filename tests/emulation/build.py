@@ -130,6 +130,10 @@ _RENDER_PTX = {
     "add2": "return make_float2(a.x + b.x, a.y + b.y);",
     "rcp_approx": "return 1.0f / x;",
     "gate_pair": "return (pos < lc && power <= 0.f && og_raw >= 1.0f / 255.0f) ? og_raw : 0.f;",
+}
+# common.cuh's TMA plumbing (render.cu and preprocess.cu both stage through it): a synchronous copy
+_TMA_PTX = {
+    "smem_u32": "(void)p; return 0u;",
     "mbar_init": "(void)bar; (void)count;",
     "mbar_fence_init": "",
     "mbar_expect_tx": "(void)bar; (void)bytes;",
@@ -178,7 +182,10 @@ def _common_host() -> None:
     c = open(os.path.join(CSRC, "common.cuh")).read().replace("#include <cuda_runtime.h>", "")
     c = c.replace('#include "../../include/scgr.h"', '#include "../../../include/scgr.h"')
     c, n = re.subn(r'asm\("sqrt\.approx\.ftz\.f32 %0, %1;"[^;]*;', "y = sqrtf(x);", c)
-    assert n == 1 and "asm" not in c, "common.cuh: expected exactly one inline-PTX statement (sqrt.approx)"
+    assert n == 1, "common.cuh: expected exactly one sqrt.approx statement"
+    for name, new in _TMA_PTX.items():
+        c = _replace_fn_body(c, name, new)
+    assert "asm" not in c, "common.cuh: an inline-PTX statement is not covered"
     with open(os.path.join(OUT_DIR, "common_host.cuh"), "w") as f:
         f.write(c)
 
