@@ -193,8 +193,10 @@ __device__ __forceinline__ uint32_t peers_by_ballot(const uint32_t d, const bool
 // MATCH: how a lane finds its peers (lanes of the warp holding the same digit) -- 0: MATCH.ANY, 1: one ballot per digit
 // bit, 2: atomic OR of the lane's bit into a per-warp table of 256 masks in shared memory (one ATOMS + one LDS per item
 // whatever the digit width; the pass is issue-bound, and the ballots were 40 % of its instructions).
-template <int THREADS, int ITEMS, int MATCH, bool RANGES>
-__global__ void __launch_bounds__(THREADS)
+// MINB 0: registers left to the compiler's default for the block size (64 at 512 threads: two CTAs per SM; an explicit
+// minimum of 1 lets it take 128 and halves the occupancy: +30 % time).
+template <int THREADS, int ITEMS, int MATCH, bool RANGES, int MINB = 0>
+__global__ void __launch_bounds__(THREADS, MINB == 0 ? (2048 / THREADS >= 4 ? 2 : 2048 / THREADS / 2 > 0 ? 2048 / THREADS / 2 : 1) : MINB)
 onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                      const int64_t* __restrict__ n_dev, int64_t n_host, int64_t cap, int shift,
@@ -210,8 +212,8 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     uint32_t* const s_warp = s_gbase + RADIX_BINS;           // [32]
     uint32_t& s_tile = s_warp[32];                           // [1] (+3 pad)
     uint16_t (*s_cnt)[RADIX_BINS] = reinterpret_cast<uint16_t (*)[RADIX_BINS]>(s_warp + 36);   // [WARPS][256] counts -> offsets
-    // MATCH == 2: [WARPS][2][256] peer masks, ping-pong over the items so that a leader's reset never races the next item
-    uint32_t (*s_match)[2][RADIX_BINS] = reinterpret_cast<uint32_t (*)[2][RADIX_BINS]>(&s_cnt[WARPS][0]);
+    // MATCH == 2: [WARPS][256] peer masks
+    uint32_t (*s_match)[RADIX_BINS] = reinterpret_cast<uint32_t (*)[RADIX_BINS]>(&s_cnt[WARPS][0]);
 
     const uint32_t* ghist = sweep;
     uint32_t* ticket = sweep + 256;
@@ -220,7 +222,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     for (int i = threadIdx.x; i < WARPS * RADIX_BINS; i += THREADS) (&s_cnt[0][0])[i] = 0;
     if (MATCH == 2)
-        for (int i = threadIdx.x; i < WARPS * 2 * RADIX_BINS; i += THREADS) (&s_match[0][0][0])[i] = 0u;
+        for (int i = threadIdx.x; i < WARPS * RADIX_BINS; i += THREADS) (&s_match[0][0])[i] = 0u;
     if (threadIdx.x < RADIX_BINS) s_start[threadIdx.x] = 0u;
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -266,7 +268,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
         const bool valid = base + w * PER_WARP + it * 32 + lane < n;
         const uint32_t d = (key[it] >> shift) & mask;
         if (MATCH == 2) {
-            uint32_t* const mm = s_match[w][it & 1];
+            uint32_t* const mm = s_match[w];
             if (valid) atomicOr(&mm[d], 1u << lane);
             __syncwarp();
             peers[it] = valid ? mm[d] : (1u << lane);
@@ -277,7 +279,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
         if (valid && lane == leader) {
             c = s_cnt[w][d];
             s_cnt[w][d] = (uint16_t)(c + __popc(peers[it]));
-            if (MATCH == 2) s_match[w][it & 1][d] = 0u;      // (this table is next used two items on, two barriers away)
+            if (MATCH == 2) s_match[w][d] = 0u;      // (the warp barrier that ends the iteration orders this before the next OR)
         }
         c = __shfl_sync(0xffffffffu, c, leader);
         rank[it] = c + __popc(peers[it] & lt_mask);
@@ -360,7 +362,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 
 constexpr size_t onesweep_smem_bytes(int threads, int match) {
     return (size_t)(2 * RADIX_TILE + 2 * RADIX_BINS + 36) * 4 + (size_t)(threads / 32) * RADIX_BINS * 2 +
-           (match == 2 ? (size_t)(threads / 32) * 2 * RADIX_BINS * 4 : 0);
+           (match == 2 ? (size_t)(threads / 32) * RADIX_BINS * 4 : 0);
 }
 
 __global__ void init_ranges_kernel(uint2* __restrict__ ranges, uint32_t n) {
@@ -373,11 +375,11 @@ int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-template <int THREADS, int ITEMS, int MATCH, bool RANGES>
+template <int THREADS, int ITEMS, int MATCH, bool RANGES, int MINB = 0>
 void launch_onesweep_variant(uint32_t nb, const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout,
                              const int64_t* n_dev, int64_t n_host, int64_t cap, int shift, uint32_t mask,
                              uint32_t* sweep, uint2* ranges, const Launch& L) {
-    auto kern = onesweep_pass_kernel<THREADS, ITEMS, MATCH, RANGES>;
+    auto kern = onesweep_pass_kernel<THREADS, ITEMS, MATCH, RANGES, MINB>;
     constexpr size_t smem = onesweep_smem_bytes(THREADS, MATCH);
     static bool configured = false;     // per-process, idempotent
     if (!configured) {
@@ -398,6 +400,8 @@ void launch_onesweep(const char* name, const uint32_t* kin, const uint32_t* vin,
     begin_kernel(name, L);
     switch (variant) {
         default: launch_onesweep_variant<512, 8, 2, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
+        case 8: launch_onesweep_variant<512, 8, 2, RANGES, 3>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
+        case 9: launch_onesweep_variant<256, 16, 2, RANGES, 4>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
         case 6: launch_onesweep_variant<1024, 4, 2, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
         case 7: launch_onesweep_variant<256, 16, 2, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;
         case 0: launch_onesweep_variant<256, 16, 0, RANGES>(nb, kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges, L); break;

@@ -491,7 +491,9 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
 // ------------------------------------------------------------------------------------------
 // ACC: gradient accumulation over the views of a batch (ScgrGrads.accumulate): every parameter gradient is added to
 // what the array holds, Gaussians without gradient are not touched at all; dL/dmean2D stays per view.
-template <bool SH_FAST, int MINB, bool ACC, bool SPLIT>
+// TMA (SH_FAST, not SPLIT): the SH row of every live Gaussian of a round arrives by one bulk-async copy issued by the thread
+// that will process it; the wait sits in front of step (4), behind the conic / covariance / mean chain of steps (1)-(3).
+template <bool SH_FAST, int MINB, bool ACC, bool SPLIT, bool TMA>
 __global__ void __launch_bounds__(PB_T, MINB)
 preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record* __restrict__ rec,
                            const ScreenGrad* __restrict__ sg, const ScgrGrads out) {
@@ -501,6 +503,11 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     __shared__ uint8_t s_list[PB_G];              // local indices of the live Gaussians, compacted
     __shared__ int s_wcnt[PB_K][PB_T / 32];
     __shared__ uint32_t s_wbal[PB_K][PB_T / 32];   // live mask of local rows [32 (k PB_T / 32 + w), + 32)
+    __shared__ __align__(8) unsigned long long s_bar;
+    if (TMA && threadIdx.x == 0) {
+        mbar_init(&s_bar, PB_T);      // every thread arrives once per round, the live ones with the bytes of their row
+        mbar_fence_init();
+    }
     const int P = g.P;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const bool use_sh = SPLIT || g.shs != nullptr;
@@ -619,7 +626,16 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     const bool live = tid < in_round;
     const int jl = live ? (int)s_list[first + tid] : 0;      // local index of the Gaussian this thread processes
     const int i = row0 + jl;
-    if (SPLIT) {
+    const bool tma = TMA && use_sh;
+    if (tma) {
+        if (live) {
+            fence_proxy_async();      // the previous round read and rewrote this row through the generic proxy
+            mbar_expect_tx(&s_bar, SH_ROW_F4 * sizeof(float4));
+            bulk_g2s(&s_sh[tid * SH_ROW_F4_PAD], g.shs + (size_t)i * (SH_ROW_F4 * 4), SH_ROW_F4 * sizeof(float4), &s_bar);
+        } else {
+            mbar_arrive(&s_bar);
+        }
+    } else if (SPLIT) {
         // the 48 floats of every live row of the round, from whichever set the row belongs to
         float* const sf = reinterpret_cast<float*>(s_sh);
         // four rows per lane at a time: all their loads are issued before the first one is stored (a row's address comes
@@ -693,7 +709,7 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
             sc_in = load3(g.scales, i);
         }
     }
-    if (SH_FAST && use_sh) __syncthreads();      // (SPLIT implies SH_FAST)
+    if (SH_FAST && use_sh && !tma) __syncthreads();      // (SPLIT implies SH_FAST)
 
     float dmean[3] = {0.f, 0.f, 0.f};
     float dm2x = 0.f, dm2y = 0.f, dop = 0.f;
@@ -791,6 +807,7 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
             sh_basis(D, d, bb);
             sh_basis_grad(D, d, bx, by, bz);
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+            if (tma) mbar_wait(&s_bar, (uint32_t)(first / PB_T) & 1u);
             if (SH_FAST) {
                 // in place: the staged input row of the Gaussian becomes its gradient row
                 float4* row = s_sh + tid * SH_ROW_F4_PAD;
@@ -979,18 +996,21 @@ void launch_preprocess_backward(const ScgrView& v, const ScgrGaussians& g, const
     begin_kernel("preprocess_backward", L);
     static const int minb = getenv("SCGR_PREB_MINB") ? atoi(getenv("SCGR_PREB_MINB")) : 1;
     const bool acc = out.accumulate != 0;
+    static const int tma = getenv("SCGR_TMA_PREB") ? atoi(getenv("SCGR_TMA_PREB")) : 1;
     if (sh_split(g)) {
-        if (acc) preprocess_backward_kernel<true, 1, true, true><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else preprocess_backward_kernel<true, 1, false, true><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        if (acc) preprocess_backward_kernel<true, 1, true, true, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else preprocess_backward_kernel<true, 1, false, true, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     } else if (sh_fast_ok(g, out.dL_dshs)) {
-        if (acc) preprocess_backward_kernel<true, 1, true, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (minb == 12) preprocess_backward_kernel<true, 12, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (minb == 10) preprocess_backward_kernel<true, 10, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else preprocess_backward_kernel<true, 1, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        if (acc && tma) preprocess_backward_kernel<true, 1, true, false, true><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (acc) preprocess_backward_kernel<true, 1, true, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (minb == 12) preprocess_backward_kernel<true, 12, false, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (minb == 10) preprocess_backward_kernel<true, 10, false, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (tma) preprocess_backward_kernel<true, 1, false, false, true><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else preprocess_backward_kernel<true, 1, false, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     } else if (acc) {
-        preprocess_backward_kernel<false, 1, true, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        preprocess_backward_kernel<false, 1, true, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     } else {
-        preprocess_backward_kernel<false, 1, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        preprocess_backward_kernel<false, 1, false, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     }
     check_launch("preprocess_backward", L);
 }

@@ -136,6 +136,8 @@ _TMA_PTX = {
     "smem_u32": "(void)p; return 0u;",
     "mbar_init": "(void)bar; (void)count;",
     "mbar_fence_init": "",
+    "fence_proxy_async": "",
+    "mbar_arrive": "(void)bar;",
     "mbar_expect_tx": "(void)bar; (void)bytes;",
     "bulk_g2s": "std::memcpy(dst, src, bytes); (void)bar;",
     "mbar_wait": "(void)bar; (void)parity;",
