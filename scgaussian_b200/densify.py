@@ -1,5 +1,7 @@
-"""Prune compaction (second half): `GaussianModel.prune_points(mask)` of reference
-scene/gaussian_model.py:795-820 with its helper `_prune_optimizer` (:777-793).
+"""Densification bookkeeping: `GaussianModel.prune_points(mask)` of reference
+scene/gaussian_model.py:795-820 with its helper `_prune_optimizer` (:777-793), `densification_postfix` /
+`cat_tensors_to_optimizer` (:822-862) and the clone / split selection around them (`densify_and_clone`,
+`densify_and_split`, `densify_and_prune`, :864-931).
 
 The reference evaluates `t[valid_points_mask]` once per per-Gaussian array -- 12 parameters, their `exp_avg` /
 `exp_avg_sq`, `_rayo`, `_rayd`, `xyz_gradient_accum`, `denom`, `max_radii2D`: ~45 boolean-mask gathers, each a
@@ -200,3 +202,109 @@ def densification_postfix(pc, new_xyz, new_features_dc, new_features_rest, new_o
     for name, t in tensors.items():
         setattr(pc, GROUP_ATTR[name], t)
     pc.xyz_gradient_accum, pc.denom, pc.max_radii2D = accum, denom, max_radii
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Clone / split selection (rest): reference scene/gaussian_model.py:864-931, run every
+# `densification_interval` iterations.  The reference gathers `torch.cat([set0, set1])[mask]` array by array (12 cats +
+# 12 boolean-mask gathers per call, then the 18 cats + 15 zero fills of densification_postfix, then the ~45 gathers of
+# prune_points).  Here the selection mask becomes two index lists once; each set's arrays are gathered by ONE launch
+# (scgr_gather_rows), appended by ONE launch (scgr_copy_segments) and pruned by one launch per index list.  Thresholds,
+# `torch.normal` sampling (same call, same shapes: same random stream as the reference) and the 3x3 rotation of the
+# samples are host PyTorch on the selected rows only.
+# ---------------------------------------------------------------------------------------------------------------
+def _activated_scaling(pc) -> torch.Tensor:
+    return torch.exp(torch.cat([pc._scaling.detach(), pc.bg_scaling.detach()]))      # reference :105-110
+
+
+def _selected_rows(pc, mask: torch.Tensor):
+    """(xyz, features_dc, features_rest, opacity, scaling, rotation) of the Gaussians where `mask` is set, ray-based set
+    first -- `torch.cat([pc._x, pc.bg_x])[mask]` for every array of reference :904-909, two launches in all."""
+    n_ray = int(pc._zval.shape[0])
+    idx_ray = mask[:n_ray].nonzero().squeeze(1)
+    idx_bg = mask[n_ray:].nonzero().squeeze(1)
+    ray = gather_rows([pc._rayo, pc._rayd, pc._zval, pc._features_dc, pc._features_rest, pc._opacity, pc._scaling,
+                       pc._rotation], idx_ray)
+    bg = gather_rows([pc.bg_xyz, pc.bg_features_dc, pc.bg_features_rest, pc.bg_opacity, pc.bg_scaling, pc.bg_rotation], idx_bg)
+    xyz_ray = ray[0] + ray[1] * ray[2]                               # reference :113-116 get_xyz of the ray-based set
+    return [torch.cat([a, b]) for a, b in zip([xyz_ray] + ray[3:], bg)]
+
+
+def build_rotation(r: torch.Tensor) -> torch.Tensor:
+    """reference utils/general_utils.py:84-105 (the quaternion is normalised first), on the tensor's own device."""
+    q = r / torch.sqrt(r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1] + r[:, 2] * r[:, 2] + r[:, 3] * r[:, 3])[:, None]
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                     2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                     2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], dim=1)
+    return R.view(-1, 3, 3)
+
+
+def replace_tensor_to_optimizer(tensor: torch.Tensor, name: str, optimizer) -> Dict[str, nn.Parameter]:
+    """reference scene/gaussian_model.py:758-775: the named group's parameter replaced, its moments cleared."""
+    out = {}
+    for group in optimizer.param_groups:
+        if group["name"] != name:
+            continue
+        old = group["params"][0]
+        st = optimizer.state.get(old, None)
+        new = nn.Parameter(tensor.requires_grad_(True))
+        if st is not None:
+            st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(tensor), torch.zeros_like(tensor)
+            del optimizer.state[old]
+            optimizer.state[new] = st
+        group["params"][0] = new
+        out[name] = new
+    return out
+
+
+def densify_and_clone(pc, grads: torch.Tensor, grad_threshold: float, scene_extent: float) -> None:
+    """reference scene/gaussian_model.py:898-912: small Gaussians with a large view-space gradient are duplicated."""
+    mask = (torch.norm(grads, dim=-1) >= grad_threshold) & \
+           (torch.max(_activated_scaling(pc), dim=1).values <= pc.percent_dense * scene_extent)
+    densification_postfix(pc, *_selected_rows(pc, mask))
+
+
+def densify_and_split(pc, grads: torch.Tensor, grad_threshold: float, scene_extent: float, N: int = 2) -> None:
+    """reference scene/gaussian_model.py:864-896: large Gaussians with a large gradient are replaced by N samples drawn
+    from them (scale / (0.8 N)); a ray-based one stays in place, shrunk, instead of being pruned."""
+    P = int(pc._zval.shape[0]) + int(pc.bg_xyz.shape[0])
+    n_ray = int(pc._zval.shape[0])
+    device = pc._zval.device
+    padded = torch.zeros(P, dtype=grads.dtype, device=device)
+    padded[:grads.shape[0]] = grads.squeeze()
+    mask = (padded >= grad_threshold) & (torch.max(_activated_scaling(pc), dim=1).values > pc.percent_dense * scene_extent)
+    xyz, f_dc, f_rest, opacity, scaling_raw, rotation = _selected_rows(pc, mask)
+    scaling = torch.exp(scaling_raw)
+    stds = scaling.repeat(N, 1)
+    means = torch.zeros((stds.size(0), 3), dtype=stds.dtype, device=device)
+    samples = torch.normal(mean=means, std=stds)                     # (same call as reference :875: same random stream)
+    rots = build_rotation(rotation).repeat(N, 1, 1)
+    new_xyz = torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1) + xyz.repeat(N, 1)
+    new_scaling = torch.log(scaling.repeat(N, 1) / (0.8 * N))
+    densification_postfix(pc, new_xyz, f_dc.repeat(N, 1, 1), f_rest.repeat(N, 1, 1), opacity.repeat(N, 1), new_scaling,
+                          rotation.repeat(N, 1))
+    n_split = int(mask.sum())
+    shrunk = pc._scaling.detach().clone()
+    shrunk[mask[:n_ray]] /= 0.8 * N
+    pc._scaling = replace_tensor_to_optimizer(shrunk, "scaling", pc.optimizer)["scaling"]
+    mask = mask.clone()
+    mask[:n_ray] = False
+    prune_points(pc, torch.cat((mask, torch.zeros(N * n_split, dtype=torch.bool, device=device))))
+
+
+def densify_and_prune(pc, max_grad: float, min_opacity: float, extent: float, max_screen_size) -> None:
+    """reference scene/gaussian_model.py:914-931 (`torch.cuda.empty_cache()` left to the caller)."""
+    grads = pc.xyz_gradient_accum / pc.denom
+    grads[grads.isnan()] = 0.0
+    densify_and_clone(pc, grads, max_grad, extent)
+    densify_and_split(pc, grads, max_grad, extent)
+    n_ray = int(pc._zval.shape[0])
+    opacity = torch.sigmoid(torch.cat([pc._opacity.detach(), pc.bg_opacity.detach()]))
+    prune_mask = (opacity < min_opacity).squeeze(-1)
+    if max_screen_size:
+        big_vs = pc.max_radii2D > 1.5 * max_screen_size
+        big_ws = _activated_scaling(pc).max(dim=1).values > 0.2 * extent
+        prune_mask = prune_mask | big_vs | big_ws
+    prune_mask[:n_ray] = False
+    prune_points(pc, prune_mask)

@@ -286,7 +286,7 @@ def densify_on_host(reference_renderer, monkeypatch):
     return densify, build
 
 
-def _same_model(ours, ref, densify):
+def _same_model(ours, ref, densify, stepped=True):
     attrs = ["_rayo", "_rayd", "xyz_gradient_accum", "denom", "max_radii2D"] + list(densify.GROUP_ATTR.values())
     for a in attrs:
         x, y = getattr(ours, a), getattr(ref, a)
@@ -301,7 +301,7 @@ def _same_model(ours, ref, densify):
             if rp in r_opt.state:
                 for k in ("exp_avg", "exp_avg_sq"):
                     assert torch.equal(o_opt.state[op][k], r_opt.state[rp][k]), (og["name"], k)
-                assert float(o_opt.state[op]["step"]) == 3.0
+                assert float(o_opt.state[op]["step"]) == 3.0 or not stepped
         assert len(o_opt.state) == len(r_opt.state)
 
 
@@ -343,6 +343,51 @@ def test_densification_postfix_mirror_matches_the_reference_method(densify_on_ho
     ref.prune_points(mask.clone())
     densify.prune_points(ours, mask.clone())
     _same_model(ours, ref, densify)
+
+
+@pytest.mark.parametrize("max_screen_size", [None, 20])
+def test_densify_and_prune_mirror_matches_the_reference_method(densify_on_host, max_screen_size):
+    """scgaussian_b200.densify.densify_and_prune (clone / split selection) against the
+    reference's own `GaussianModel.densify_and_prune` (scene/gaussian_model.py:864-931) on the same CPU model and the same
+    random stream: identical parameters, moments, ray geometry and statistics afterwards.  Host logic only."""
+    from scgaussian_b200 import optim
+    densify, build = densify_on_host
+
+    def prepared(adam_cls):
+        pc = build(adam_cls, n_ray=40, n_bg=30)
+        g = torch.Generator().manual_seed(77)
+        P = 70
+        pc.percent_dense = 0.01
+        with torch.no_grad():
+            # scales on both sides of percent_dense * extent, some opacities below the pruning threshold
+            pc._scaling.copy_(torch.log(torch.rand(40, 3, generator=g) * 0.04 + 1e-3))
+            pc.bg_scaling.copy_(torch.log(torch.rand(30, 3, generator=g) * 0.04 + 1e-3))
+            pc._opacity.copy_(torch.randn(40, 1, generator=g) * 3)
+            pc.bg_opacity.copy_(torch.randn(30, 1, generator=g) * 3)
+        pc.xyz_gradient_accum = torch.rand(P, 1, generator=g) * 0.001
+        pc.denom = torch.randint(0, 3, (P, 1), generator=g).float()          # zeros: 0 / 0 -> nan -> 0 (:916)
+        pc.max_radii2D = torch.rand(P, generator=g) * 60
+        return pc
+
+    ref = prepared(None)
+    torch.manual_seed(1234)
+    ref.densify_and_prune(0.0002, 0.05, 2.0, max_screen_size)                   # the reference's own method
+    ours = prepared(optim.Adam)
+    torch.manual_seed(1234)
+    densify.densify_and_prune(ours, 0.0002, 0.05, 2.0, max_screen_size)
+    _same_model(ours, ref, densify, stepped=False)
+    n = ours._zval.shape[0] + ours.bg_xyz.shape[0]
+    assert ours._zval.shape[0] == 40 and n != 70                                # ray-based Gaussians are never pruned; the free set changed
+    assert ours.max_radii2D.shape == (n,)
+
+
+def test_build_rotation_matches_the_reference(reference_renderer, monkeypatch):
+    from utils.general_utils import build_rotation as ref_build
+    from scgaussian_b200.densify import build_rotation
+    real_zeros = torch.zeros
+    monkeypatch.setattr(torch, "zeros", lambda *a, **k: real_zeros(*a, **{kk: vv for kk, vv in k.items() if kk != "device"}))
+    q = torch.randn(257, 4, generator=torch.Generator().manual_seed(3))
+    assert torch.equal(build_rotation(q), ref_build(q))
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -444,3 +489,49 @@ def test_reference_render_runs_on_the_gpu_against_libscgr(reference_renderer, va
         sl = slice(n_ray, None) if n.startswith("bg_") else slice(0, n_ray)
         part = dict(flips, **{k: flips[k][sl] for k in ("gauss_flag", "gauss_margin", "gauss_own")})
         util.assert_grad_close(n, got.cpu().numpy(), want.numpy(), part)
+
+
+@pytest.mark.gpu
+def test_densify_and_prune_on_the_gpu_matches_the_reference_method(reference_renderer):
+    """the reference's own `GaussianModel.densify_and_prune` (scene/gaussian_model.py:864-931,
+    unmodified, its two torch optimizers) against scgaussian_b200.densify.densify_and_prune on the fused optimizer -- the
+    real gather / append kernels -- on the same CUDA model and the same CUDA random stream: identical model afterwards."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import argparse
+    from arguments import OptimizationParams
+    from scgaussian_b200 import densify, optim
+    from tests import util
+    G = reference_renderer
+    dev = torch.device("cuda:0")
+    P, n_ray = 30_000, 18_000
+    case = util.make_case(P, 320, 200, sh_degree=3, scale_median=0.02, seed=4)
+
+    def prepared(fused):
+        pc = _reference_model(G, case, n_ray, dev)
+        pc.spatial_lr_scale = 1.0
+        pc.training_setup(OptimizationParams(argparse.ArgumentParser()))       # reference :486-512
+        if fused:
+            pc.optimizer = optim.Adam(pc.optimizer.param_groups, lr=0.0, eps=1e-15)
+            pc.optimizer_bg = optim.Adam(pc.optimizer_bg.param_groups, lr=0.0, eps=1e-15)
+        g = torch.Generator().manual_seed(8)
+        for opt in (pc.optimizer, pc.optimizer_bg):                             # moments as after some steps
+            for grp in opt.param_groups:
+                p = grp["params"][0]
+                if grp["name"] not in ("f_rest", "bg_scaling"):
+                    opt.state[p] = {"step": torch.tensor(3.0), "exp_avg": torch.randn(p.shape, generator=g).to(dev),
+                                    "exp_avg_sq": torch.randn(p.shape, generator=g).abs().to(dev)}
+        pc.xyz_gradient_accum = (torch.rand(P, 1, generator=g) * 0.001).to(dev)
+        pc.denom = torch.randint(0, 3, (P, 1), generator=g).float().to(dev)
+        pc.max_radii2D = (torch.rand(P, generator=g) * 60).to(dev)
+        return pc
+
+    ref = prepared(False)
+    torch.manual_seed(99)
+    ref.densify_and_prune(0.0002, 0.05, 2.0, 20)                                # the reference's own method
+    ours = prepared(True)
+    torch.manual_seed(99)
+    densify.densify_and_prune(ours, 0.0002, 0.05, 2.0, 20)
+    torch.cuda.synchronize()
+    _same_model(ours, ref, densify, stepped=False)
+    assert ours._zval.shape[0] == n_ray and ours.bg_xyz.shape[0] != P - n_ray
