@@ -249,10 +249,17 @@ depth_key_kernel(const float* __restrict__ means3D, const int P, const float* __
 // ------------------------------------------------------------------------------------------
 // SH_FAST: M == 16 and shs 16-byte aligned -> CTA-cooperative 128-bit staging through smem.
 // SPLIT (implies SH_FAST): the SH rows come from the model's features_dc / features_rest arrays of both sets.
-// TMA (SH_FAST, not SPLIT): every thread pulls the 192-byte row of its Gaussian into the padded staging buffer with one
-// bulk-async copy, completion on one mbarrier per CTA -- nothing waits for the rows until the geometry (projection,
-// covariance, radius, tile rectangle) of the Gaussian is done, where the register-staged variant spends 44 % of its warp
-// time stalled on the loads in front of the barrier that closes the staging (profiles/r02_preprocess.md).
+// TMA (SH_FAST, not SPLIT): the CTA's 128 x 192-byte SH block arrives by 16 bulk-async copies of 8 rows each (one lane per
+// copy: a bulk copy takes its addresses from uniform registers, so per-lane copies are issued one lane at a time -- 32
+// rounds of 8 instructions per warp when every thread fetched its own row), completion on one mbarrier per CTA.  Nothing
+// waits for the rows until the geometry (projection, covariance, radius, tile rectangle) of the Gaussian is done, where
+// the register-staged variant spends 44 % of its warp time stalled in front of the barrier that closes the staging
+// (profiles/r02_preprocess.md).  Chunks are 8 x 192 + 16 bytes apart, and the threads of a warp take the rows in the order
+// 8 (lane & 3) + 2 (lane >> 3) + ((lane >> 2) & 1): the 8 rows a quarter-warp reads with one LDS.128 then start in 8
+// different groups of 4 banks -- conflict-free without padding every row.
+constexpr int TMA_CHUNK_ROWS = 8;
+constexpr int TMA_CHUNK_F4 = TMA_CHUNK_ROWS * SH_ROW_F4 + 1;      // 97 float4 = 1552 bytes
+static_assert(PRE_THREADS / TMA_CHUNK_ROWS * TMA_CHUNK_F4 <= PRE_THREADS * SH_ROW_F4_PAD, "staging buffer");
 template <bool SH_FAST, bool SPLIT, bool TMA>
 __global__ void __launch_bounds__(PRE_THREADS, 8)
 preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __restrict__ rec,
@@ -262,19 +269,28 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
     __shared__ __align__(16) float4 s_sh[SH_FAST ? PRE_THREADS * SH_ROW_F4_PAD : 1];
     __shared__ __align__(8) unsigned long long s_bar;
     const int P = g.P;
-    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
     const bool use_sh = SPLIT || g.shs != nullptr;
     const bool tma = TMA && use_sh;
+    const int lane = threadIdx.x & 31;
+    // local row of the CTA's block this thread processes (TMA: permuted inside the warp, see above)
+    const int lrow = tma ? (int)(threadIdx.x & ~31u) + 8 * (lane & 3) + 2 * (lane >> 3) + ((lane >> 2) & 1) : (int)threadIdx.x;
+    const int i = blockIdx.x * PRE_THREADS + lrow;
     if (tma) {
+        const int nrows = min(PRE_THREADS, P - (int)blockIdx.x * PRE_THREADS);
         if (threadIdx.x == 0) {
-            const int nrows = min(PRE_THREADS, P - (int)blockIdx.x * PRE_THREADS);
             mbar_init(&s_bar, 1);
             mbar_fence_init();
             mbar_expect_tx(&s_bar, (uint32_t)nrows * (uint32_t)(SH_ROW_F4 * sizeof(float4)));      // the one arrival of the phase
         }
         __syncthreads();
-        if (i < P)
-            bulk_g2s(&s_sh[threadIdx.x * SH_ROW_F4_PAD], g.shs + (size_t)i * (SH_ROW_F4 * 4), SH_ROW_F4 * sizeof(float4), &s_bar);
+        if (lane < 32 / TMA_CHUNK_ROWS) {
+            const int chunk = (int)(threadIdx.x >> 5) * (32 / TMA_CHUNK_ROWS) + lane;
+            const int first = chunk * TMA_CHUNK_ROWS;
+            const int rows = min(TMA_CHUNK_ROWS, nrows - first);
+            if (rows > 0)
+                bulk_g2s(&s_sh[chunk * TMA_CHUNK_F4], g.shs + ((size_t)blockIdx.x * PRE_THREADS + first) * (SH_ROW_F4 * 4),
+                         (uint32_t)rows * (uint32_t)(SH_ROW_F4 * sizeof(float4)), &s_bar);
+        }
     }
 
     // the thread's own small inputs first: their loads are in flight together with the CTA's SH block below (a load cannot
@@ -417,7 +433,8 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
                     for (int c = 0; c < 3; c++) acc[c] += b[k] * my_rest[3 * (k - 1) + c];
                 }
         } else if (SH_FAST) {
-            const float4* row = s_sh + threadIdx.x * SH_ROW_F4_PAD;
+            const float4* row = tma ? s_sh + (lrow / TMA_CHUNK_ROWS) * TMA_CHUNK_F4 + (lrow % TMA_CHUNK_ROWS) * SH_ROW_F4
+                                    : s_sh + threadIdx.x * SH_ROW_F4_PAD;
 #pragma unroll
             for (int cc = 0; cc < SH_ROW_F4; cc++) {
                 const float4 q = row[cc];

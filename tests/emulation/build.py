@@ -131,16 +131,17 @@ _RENDER_PTX = {
     "rcp_approx": "return 1.0f / x;",
     "gate_pair": "return (pos < lc && power <= 0.f && og_raw >= 1.0f / 255.0f) ? og_raw : 0.f;",
 }
-# common.cuh's TMA plumbing (render.cu and preprocess.cu both stage through it): a synchronous copy
+# common.cuh's TMA plumbing (render.cu and preprocess.cu both stage through it): a synchronous copy behind a real
+# mbarrier phase protocol (host_cuda_shim.h: emu_mbar_*)
 _TMA_PTX = {
     "smem_u32": "(void)p; return 0u;",
-    "mbar_init": "(void)bar; (void)count;",
+    "mbar_init": "emu_mbar_init(bar, count);",
     "mbar_fence_init": "",
     "fence_proxy_async": "",
-    "mbar_arrive": "(void)bar;",
-    "mbar_expect_tx": "(void)bar; (void)bytes;",
-    "bulk_g2s": "std::memcpy(dst, src, bytes); (void)bar;",
-    "mbar_wait": "(void)bar; (void)parity;",
+    "mbar_arrive": "emu_mbar_update(bar, -1, 0);",
+    "mbar_expect_tx": "emu_mbar_update(bar, -1, (long long)bytes);",
+    "bulk_g2s": "std::memcpy(dst, src, bytes); emu_mbar_update(bar, 0, -(long long)bytes);",
+    "mbar_wait": "emu_mbar_wait(bar, parity);",
 }
 
 

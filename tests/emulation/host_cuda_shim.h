@@ -207,3 +207,25 @@ static void emu_launch(dim3 grid, unsigned threads, F f) {
         });
     for (auto& th : pool) th.join();
 }
+
+// ---- mbarrier + bulk-async copy (common.cuh's TMA plumbing), emulated with a real phase protocol: the 64-bit barrier word
+// holds {phase:1 | init count:15 | pending arrivals:16 | transaction bytes:32 (signed, may go negative transiently)}; a
+// phase completes when no arrival is pending and the byte count is zero, exactly as the hardware object does.  The copy
+// itself is a synchronous memcpy followed by its complete_tx. ----
+static inline void emu_mbar_update(unsigned long long* bar, int d_pending, long long d_tx) {
+    unsigned long long old = __atomic_load_n(bar, __ATOMIC_SEQ_CST), neu;
+    do {
+        unsigned phase = (unsigned)(old >> 63), count = (unsigned)((old >> 48) & 0x7fffu);
+        int pending = (int)((old >> 32) & 0xffffu) + d_pending;
+        long long tx = (long long)(int)(unsigned)(old & 0xffffffffu) + d_tx;
+        if (pending == 0 && tx == 0) { phase ^= 1u; pending = (int)count; }
+        neu = ((unsigned long long)phase << 63) | ((unsigned long long)count << 48) | ((unsigned long long)(pending & 0xffff) << 32) |
+              (unsigned long long)(unsigned)(int)tx;
+    } while (!__atomic_compare_exchange_n(bar, &old, neu, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+}
+static inline void emu_mbar_init(unsigned long long* bar, unsigned count) {
+    __atomic_store_n(bar, ((unsigned long long)count << 48) | ((unsigned long long)count << 32), __ATOMIC_SEQ_CST);
+}
+static inline void emu_mbar_wait(unsigned long long* bar, unsigned parity) {
+    while ((unsigned)(__atomic_load_n(bar, __ATOMIC_SEQ_CST) >> 63) == (parity & 1u)) std::this_thread::yield();
+}
