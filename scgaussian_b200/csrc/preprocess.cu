@@ -254,7 +254,7 @@ depth_key_kernel(const float* __restrict__ means3D, const int P, const float* __
 // rounds of 8 instructions per warp when every thread fetched its own row), completion on one mbarrier per CTA.  Nothing
 // waits for the rows until the geometry (projection, covariance, radius, tile rectangle) of the Gaussian is done, where
 // the register-staged variant spends 44 % of its warp time stalled in front of the barrier that closes the staging
-// (profiles/r02_preprocess.md).  Chunks are 8 x 192 + 16 bytes apart, and the threads of a warp take the rows in the order
+// (profiles/r02_preprocess_sort.md).  Chunks are 8 x 192 + 16 bytes apart, and the threads of a warp take the rows in the order
 // 8 (lane & 3) + 2 (lane >> 3) + ((lane >> 2) & 1): the 8 rows a quarter-warp reads with one LDS.128 then start in 8
 // different groups of 4 banks -- conflict-free without padding every row.
 constexpr int TMA_CHUNK_ROWS = 8;
