@@ -254,6 +254,28 @@ int scgr_nvls_allreduce(void* multicast_ptr, size_t n_floats, int32_t rank, int3
 int scgr_nvls_allreduce_rows(void* multicast_rows, const float* live_count, int64_t n_rows, int32_t row_floats,
                              int32_t rank, int32_t world, scgr_stream_t stream);
 
+/* The whole collective of a step in ONE launch: cross-rank barrier -> dense shot over the first
+ * dense_floats of the buffer -> barrier -> row-sparse shot over the rows block -> barrier, the barriers taken INSIDE the
+ * kernel on flag words in symmetric memory (instead of three host-issued barrier kernels between two launches).
+ * flags[q] is the address, in rank q's replica, of a flag array of `world` uint32 words, zero before the first call (rank
+ * r release-stores into word r of every array and waits on its own); sync_local is 4 zeroed uint32 words of ordinary
+ * device memory owned by the caller; epoch is 1 for the first call and grows by 3 per call (same on every rank).  The
+ * grid is sized to be co-resident.  A wait that exceeds ~2 s raises sync_local[2] instead of hanging the GPU. */
+#define SCGR_NVLS_MAX_WORLD 8
+typedef struct ScgrNvlsFused {
+    void* multicast_ptr;          /* multicast address of the flat buffer */
+    size_t dense_floats;          /* multiple of 4 * world */
+    void* multicast_rows;         /* multicast address of the rows block, or NULL (dense only) */
+    const float* live_count;      /* this rank's own mapping of the live counts (inside the dense part) */
+    int64_t n_rows;
+    int32_t row_floats;           /* multiple of 4 */
+    int32_t rank, world;          /* world <= SCGR_NVLS_MAX_WORLD */
+    uint32_t* flags[SCGR_NVLS_MAX_WORLD];
+    uint32_t* sync_local;
+    uint32_t epoch;
+} ScgrNvlsFused;
+int scgr_nvls_allreduce_fused(const ScgrNvlsFused* args, scgr_stream_t stream);
+
 /* ---- simple_knn._C.distCUDA2 (reference scene/gaussian_model.py:20, :444) ----
  * out[i] = mean over the 3 nearest other points of |p_i - p_j|^2; points [n,3] fp32 device, out [n].
  * One-shot initialisation helper (exact tiled all-pairs scan, n <= 2^20), not on the per-step path. */

@@ -36,6 +36,12 @@ class ScgrGrads(C.Structure):
                 ("dL_dsh_rest", C.c_void_p * 2)]
 
 
+class ScgrNvlsFused(C.Structure):
+    _fields_ = [("multicast_ptr", C.c_void_p), ("dense_floats", C.c_size_t), ("multicast_rows", C.c_void_p),
+                ("live_count", C.c_void_p), ("n_rows", C.c_int64), ("row_floats", C.c_int32), ("rank", C.c_int32),
+                ("world", C.c_int32), ("flags", C.c_void_p * 8), ("sync_local", C.c_void_p), ("epoch", C.c_uint32)]
+
+
 class ScgrDebugViews(C.Structure):
     _fields_ = [("record", C.c_void_p), ("tiles_touched", C.c_void_p), ("depth_order", C.c_void_p),
                 ("point_list", C.c_void_p), ("ranges", C.c_void_p), ("n_contrib", C.c_void_p),
@@ -132,6 +138,7 @@ SYMBOLS = {
     "scgr_masked_mean_backward": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scgr_nvls_allreduce": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p]),
     "scgr_nvls_allreduce_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "scgr_nvls_allreduce_fused": (C.c_int, [C.c_void_p, C.c_void_p]),
     "scgr_knn3_mean_dist2": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "scgr_assemble_forward": (C.c_int, [C.POINTER(ScgrModel), C.POINTER(ScgrActivated), C.c_void_p]),
     "scgr_assemble_backward": (C.c_int, [C.POINTER(ScgrModel), C.POINTER(ScgrActivatedGrads),

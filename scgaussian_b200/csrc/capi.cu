@@ -483,6 +483,26 @@ int scgr_nvls_allreduce_rows(void* multicast_rows, const float* live_count, int6
     });
 }
 
+int scgr_nvls_allreduce_fused(const ScgrNvlsFused* f, scgr_stream_t stream) {
+    return guarded([&] {
+        require(f != nullptr, "nvls all-reduce: null arguments");
+        require(f->world >= 1 && f->world <= SCGR_NVLS_MAX_WORLD && f->rank >= 0 && f->rank < f->world,
+                "nvls all-reduce: bad rank / world size (at most 8 ranks: one NVSwitch box)");
+        require(f->multicast_ptr != nullptr && (reinterpret_cast<uintptr_t>(f->multicast_ptr) & 15) == 0,
+                "nvls all-reduce: buffer must be a 16-byte aligned multicast address");
+        require(f->dense_floats % (4 * (size_t)f->world) == 0, "nvls all-reduce: element count must be a multiple of 4 * world");
+        if (f->multicast_rows) {
+            require(f->n_rows >= 0 && f->live_count != nullptr, "nvls all-reduce: rows need their live counts");
+            require((reinterpret_cast<uintptr_t>(f->multicast_rows) & 15) == 0, "nvls all-reduce: rows must be 16-byte aligned");
+            require(f->row_floats > 0 && f->row_floats % 4 == 0, "nvls all-reduce: row_floats must be a positive multiple of 4");
+        }
+        require(f->sync_local != nullptr, "nvls all-reduce: null sync words");
+        for (int q = 0; q < f->world; q++) require(f->flags[q] != nullptr, "nvls all-reduce: null flag array");
+        const Launch L{(cudaStream_t)stream, false};
+        launch_nvls_allreduce_fused(*f, L);
+    });
+}
+
 int scgr_knn3_mean_dist2(const float* points, int32_t n, float* out, scgr_stream_t stream) {
     return guarded([&] {
         require(n >= 0, "knn3: negative point count");

@@ -35,8 +35,7 @@ __device__ __forceinline__ void multimem_st(float4* mc, const float4 v) {
 }
 
 template <int NVLS_THREADS, int NVLS_UNROLL>
-__global__ void __launch_bounds__(NVLS_THREADS)
-nvls_allreduce_kernel(float4* __restrict__ mc, const size_t first, const size_t count) {
+__device__ __forceinline__ void dense_shot(float4* __restrict__ mc, const size_t first, const size_t count) {
     const size_t stride = (size_t)gridDim.x * NVLS_THREADS;
     size_t i = (size_t)blockIdx.x * NVLS_THREADS + threadIdx.x;
     // NVLS_UNROLL independent reductions in flight per thread
@@ -48,9 +47,15 @@ nvls_allreduce_kernel(float4* __restrict__ mc, const size_t first, const size_t 
         for (int u = 0; u < NVLS_UNROLL; u++) multimem_st(mc + first + i + u * stride, v[u]);
     }
     for (; i < count; i += stride) multimem_st(mc + first + i, multimem_ld_reduce_add(mc + first + i));
-    // the broadcast must have LANDED in every replica before the cross-rank barrier that follows this kernel lets a
-    // peer read it: the barrier's signal travels as a unicast store and may overtake multicast data still in the switch
+    // the broadcast must have LANDED in every replica before the cross-rank barrier that follows lets a peer read it:
+    // the barrier's signal travels as a unicast store and may overtake multicast data still in the switch
     __threadfence_system();
+}
+
+template <int NVLS_THREADS, int NVLS_UNROLL>
+__global__ void __launch_bounds__(NVLS_THREADS)
+nvls_allreduce_kernel(float4* __restrict__ mc, const size_t first, const size_t count) {
+    dense_shot<NVLS_THREADS, NVLS_UNROLL>(mc, first, count);
 }
 
 // ---- row-sparse variant: only the rows some rank actually wrote ----
@@ -76,9 +81,8 @@ __device__ __forceinline__ uint32_t nth_set_bit(uint32_t w, uint32_t k) {      /
 }
 
 template <int THREADS, int UNROLL>
-__global__ void __launch_bounds__(THREADS)
-nvls_allreduce_rows_kernel(float4* __restrict__ mc, const float* __restrict__ live, const long long row_first,
-                           const long long row_end, const int row_f4) {
+__device__ __forceinline__ void rows_shot(float4* __restrict__ mc, const float* __restrict__ live, const long long row_first,
+                                          const long long row_end, const int row_f4) {
     constexpr int CHUNK = 128;
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * THREADS + threadIdx.x) >> 5;
@@ -116,6 +120,109 @@ nvls_allreduce_rows_kernel(float4* __restrict__ mc, const float* __restrict__ li
         }
     }
     __threadfence_system();      // (as above)
+}
+
+template <int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS)
+nvls_allreduce_rows_kernel(float4* __restrict__ mc, const float* __restrict__ live, const long long row_first,
+                           const long long row_end, const int row_f4) {
+    rows_shot<THREADS, UNROLL>(mc, live, row_first, row_end, row_f4);
+}
+
+// ---- the whole collective of a step in ONE launch: the cross-rank barriers that bracket the two shots are taken inside the
+// kernel, on flag words in symmetric memory, instead of three host-issued barrier kernels between two launches ----
+// Barrier s (a monotonically increasing epoch): rank r release-stores s into word r of every peer's flag array, then waits
+// until every word of its own array has reached s.  Inside the grid CTA 0 does that once all CTAs have arrived (atomic
+// counter) and releases the others through a `go` word.  Every wait is bounded: on a timeout the kernel raises
+// sync[2] and carries on (wrong sums, reported by the host, rather than a hung GPU).
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct FusedArgs {
+    float4* mc;
+    size_t dense_first, dense_count;      // this rank's shard of the dense part, float4 units
+    float4* mc_rows;
+    const float* live;
+    long long row_first, row_end;
+    int row_f4;
+    int rank, world;
+    uint32_t* flags[SCGR_NVLS_MAX_WORLD];   // flags[q]: the flag array inside rank q's replica (world words)
+    uint32_t* sync;                          // local: [0] arrivals, [1] go, [2] timeout raised
+    uint32_t epoch;                          // first of the three barrier values of this call
+};
+
+constexpr long long SPIN_LIMIT = 4000000000ll;      // cycles (~2 s): far beyond any legitimate wait
+
+template <typename F>
+__device__ __forceinline__ void bounded_spin(uint32_t* sync, F&& ready) {
+    const long long t0 = clock64();
+    while (!ready()) {
+        if (clock64() - t0 > SPIN_LIMIT) { sync[2] = 1u; break; }
+    }
+}
+
+// every thread of the grid calls this; `arrive`: the CTAs have work of the previous shot to finish first
+__device__ __forceinline__ void fused_barrier(const FusedArgs& a, const uint32_t s, const bool arrive, const uint32_t arrivals) {
+    __syncthreads();
+    if (arrive && threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(a.sync, 1u);
+    }
+    if (blockIdx.x == 0) {
+        if (arrive && threadIdx.x == 0) bounded_spin(a.sync, [&] { return ld_acquire_gpu(a.sync) >= arrivals; });
+        __syncthreads();
+        if ((int)threadIdx.x < a.world) {
+            st_release_sys(a.flags[threadIdx.x] + a.rank, s);
+            const uint32_t* mine = a.flags[a.rank] + threadIdx.x;
+            bounded_spin(a.sync, [&] { return (int)(ld_acquire_sys(mine) - s) >= 0; });
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_gpu(a.sync + 1, s);
+    } else {
+        if (threadIdx.x == 0) bounded_spin(a.sync, [&] { return (int)(ld_acquire_gpu(a.sync + 1) - s) >= 0; });
+        __syncthreads();
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+nvls_allreduce_fused_kernel(const FusedArgs a) {
+    fused_barrier(a, a.epoch, false, 0u);                    // every replica has been written by its rank's backward
+    if (a.dense_count) dense_shot<THREADS, 4>(a.mc, a.dense_first, a.dense_count);
+    fused_barrier(a, a.epoch + 1u, true, gridDim.x);         // the summed live counts are in place on every rank
+    if (a.row_end > a.row_first) rows_shot<THREADS, 4>(a.mc_rows, a.live, a.row_first, a.row_end, a.row_f4);
+    // every shard has been broadcast; the last arrival leaves the counter clean for the next call
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(a.sync, 1u);
+    }
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            bounded_spin(a.sync, [&] { return ld_acquire_gpu(a.sync) >= 2u * gridDim.x; });
+            a.sync[0] = 0u;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < a.world) {
+            st_release_sys(a.flags[threadIdx.x] + a.rank, a.epoch + 2u);
+            const uint32_t* mine = a.flags[a.rank] + threadIdx.x;
+            bounded_spin(a.sync, [&] { return (int)(ld_acquire_sys(mine) - (a.epoch + 2u)) >= 0; });
+        }
+    }
 }
 
 }  // namespace
@@ -162,6 +269,40 @@ void launch_nvls_allreduce(void* multicast_ptr, size_t n_floats, int rank, int w
         default: nvls_allreduce_kernel<512, 4><<<grid_for(512, 4), 512, 0, L.stream>>>(mc, first, per); break;
     }
     check_launch("nvls_allreduce", L);
+}
+
+void launch_nvls_allreduce_fused(const ScgrNvlsFused& f, const Launch& L) {
+    FusedArgs a{};
+    const size_t n4 = f.dense_floats / 4;                  // caller guarantees dense_floats % (4 * world) == 0
+    const size_t per = n4 / (size_t)f.world;
+    a.mc = reinterpret_cast<float4*>(f.multicast_ptr);
+    a.dense_first = per * (size_t)f.rank;
+    a.dense_count = per;
+    a.mc_rows = reinterpret_cast<float4*>(f.multicast_rows);
+    a.live = f.live_count;
+    if (f.multicast_rows && f.n_rows > 0) {
+        const long long rper = (f.n_rows + f.world - 1) / f.world;
+        a.row_first = rper * f.rank;
+        a.row_end = a.row_first + rper < f.n_rows ? a.row_first + rper : f.n_rows;
+        if (a.row_first > a.row_end) a.row_first = a.row_end;
+    }
+    a.row_f4 = f.row_floats / 4;
+    a.rank = f.rank;
+    a.world = f.world;
+    for (int q = 0; q < f.world; q++) a.flags[q] = f.flags[q];
+    a.sync = f.sync_local;
+    a.epoch = f.epoch;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static const int ctas_per_sm = getenv("SCGR_NVLS_CTAS") ? atoi(getenv("SCGR_NVLS_CTAS")) : 2;
+    constexpr int THREADS = 512;
+    // the grid must be co-resident (CTAs wait for one another): never more CTAs than the device holds at once
+    int max_per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_per_sm, nvls_allreduce_fused_kernel<THREADS>, THREADS, 0);
+    const int per_sm = max_per_sm < ctas_per_sm ? (max_per_sm > 0 ? max_per_sm : 1) : ctas_per_sm;
+    begin_kernel("nvls_allreduce_fused", L);
+    nvls_allreduce_fused_kernel<THREADS><<<(unsigned)(per_sm * sms), THREADS, 0, L.stream>>>(a);
+    check_launch("nvls_allreduce_fused", L);
 }
 
 }  // namespace scgr

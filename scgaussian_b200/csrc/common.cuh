@@ -279,6 +279,7 @@ int tile_partition_final_buffer(uint32_t n_tiles);
 void launch_nvls_allreduce(void* multicast_ptr, size_t n_floats, int rank, int world, const Launch& L);
 void launch_nvls_allreduce_rows(void* multicast_rows, const float* live_count, long long n_rows, int row_floats, int rank,
                                 int world, const Launch& L);
+void launch_nvls_allreduce_fused(const ScgrNvlsFused& f, const Launch& L);
 
 // mean squared distance to the 3 nearest neighbours (knn.cu)
 void launch_knn3(const float* points, int32_t n, float* out, const Launch& L);

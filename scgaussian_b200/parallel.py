@@ -37,6 +37,8 @@ import torch.distributed as dist
 
 
 class FlatGradBuffer:
+    FLAG_WORDS = 64          # >= world; keeps the allocation a multiple of 256 bytes
+
     def __init__(self, P: int, sh_coeffs: int = 16, use_sh: bool = True, use_cov: bool = False,
                  device="cuda", with_stats: bool = True, symmetric: Optional[bool] = None):
         self.P = P
@@ -73,7 +75,18 @@ class FlatGradBuffer:
         total = (total + 4 * world - 1) // (4 * world) * (4 * world)      # every rank reduces an equal float4 shard
         self.dense_floats = dense + pad
         self.row_floats = 3 * sh_coeffs if use_sh and (3 * sh_coeffs) % 4 == 0 else 0      # 0: no row-sparse shot
-        self.flat = self._allocate(total, torch.device(device), world, symmetric)
+        # behind the buffer, in the same symmetric allocation: the flag words of the fused collective's in-kernel barriers
+        storage = self._allocate(total + self.FLAG_WORDS, torch.device(device), world, symmetric)
+        self.flat = storage[:total]
+        self._flag_offset = total
+        self._epoch = 1
+        self._sync = None
+        if self._symm is not None:
+            storage[total:].zero_()
+            self._sync = torch.zeros(4, dtype=torch.int32, device=storage.device)
+            torch.cuda.current_stream(storage.device).synchronize()
+            self._symm.barrier(channel=0)        # every rank's flag words are zero before anyone's first collective
+        self._storage = storage
         self.views: Dict[str, torch.Tensor] = {}
         o = 0
         for (name, shp), n in zip(fields, sizes):
@@ -94,6 +107,31 @@ class FlatGradBuffer:
         d = dict(self.views)
         d["means2D"] = self.means2D
         return d
+
+    def fresh_out_dict(self) -> Dict[str, torch.Tensor]:
+        """out_dict() made of NEW view tensors of the same memory: what the autograd node hands back as gradients, so
+        that autograd can adopt them as `.grad` without a copy (it clones a gradient somebody else still references)."""
+        d = {name: v.view(v.shape) for name, v in self.views.items()}
+        d["means2D"] = self.means2D.view(self.means2D.shape)
+        return d
+
+    def capture(self):
+        """Context manager: while active, the PUBLIC operator's backward (GaussianRasterizer / autograd) writes the
+        parameter gradients, the densification statistics and the live counts of the view straight into this buffer --
+        `loss.backward()` leaves it ready for `all_reduce()`, with no packing copies; afterwards the summed gradients are
+        in `self.views[...]` (a leaf's `.grad` aliases its view whenever autograd could adopt the tensor)."""
+        import contextlib
+        from . import rasterizer as R
+
+        @contextlib.contextmanager
+        def cm():
+            prev = getattr(R._grad_sink, "fn", None)
+            R.set_gradient_sink(self.fresh_out_dict)
+            try:
+                yield self
+            finally:
+                R.set_gradient_sink(prev)
+        return cm()
 
     def fill_stats(self, radii: torch.Tensor) -> None:
         """reference scene/gaussian_model.py:932-934 for this rank's view, from torch ops -- for callers whose backward
@@ -140,8 +178,16 @@ class FlatGradBuffer:
     def collective(self) -> str:
         if self._symm is None:
             return "nccl all_reduce"
-        return "nvls two-shot kernels (libscgr): dense small blocks + row-sparse dL/dSH" if self._sparse() else \
-            "nvls two-shot kernel (libscgr), dense"
+        how = ", one launch with in-kernel barriers" if self._fused(int(self._symm.world_size)) else ""
+        return ("nvls two-shot kernels (libscgr): dense small blocks + row-sparse dL/dSH" if self._sparse() else
+                "nvls two-shot kernel (libscgr), dense") + how
+
+    def _fused(self, world: int) -> bool:
+        return world <= 8 and os.environ.get("SCGR_ALLREDUCE_FUSED", "1") != "0"
+
+    def timed_out(self) -> bool:
+        """True if a barrier inside the fused collective ever gave up waiting (the sums are then wrong)."""
+        return self._sync is not None and bool(int(self._sync[2].item()) != 0)
 
     def _sparse(self) -> bool:
         return self.row_floats > 0 and os.environ.get("SCGR_ALLREDUCE_SPARSE", "1") != "0"
@@ -156,9 +202,24 @@ class FlatGradBuffer:
             stream = C.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
             lib = _lib.load()
             rank, world = int(hdl.rank), int(hdl.world_size)
-            hdl.barrier(channel=0)           # every replica has been written by its rank's backward
             # multicast address of flat[0]: same offset from the multicast base as from this rank's own mapping
             mc = int(hdl.multicast_ptr) + (self.flat.data_ptr() - int(hdl.buffer_ptrs[rank]))
+            if self._fused(world):
+                # ONE launch: barrier -> dense shot -> barrier -> row-sparse shot -> barrier, the barriers inside the kernel
+                sparse = self._sparse()
+                f = _lib.ScgrNvlsFused(mc, self.dense_floats if sparse else self.flat.numel(),
+                                       (mc + 4 * self.rows_offset) if sparse else None,
+                                       self.views["live"].data_ptr() if sparse else None, self.P if sparse else 0,
+                                       self.row_floats, rank, world)
+                off = self.flat.data_ptr() - int(hdl.buffer_ptrs[rank]) + 4 * self._flag_offset
+                for q in range(world):
+                    f.flags[q] = int(hdl.buffer_ptrs[q]) + off
+                f.sync_local = self._sync.data_ptr()
+                f.epoch = self._epoch
+                self._epoch = (self._epoch + 3) & 0xffffffff      # (compared modulo 2^32 in the kernel)
+                _lib.check(lib.scgr_nvls_allreduce_fused(C.byref(f), stream))
+                return None
+            hdl.barrier(channel=0)           # every replica has been written by its rank's backward
             if not self._sparse():
                 _lib.check(lib.scgr_nvls_allreduce(C.c_void_p(mc), self.flat.numel(), rank, world, stream))
             else:

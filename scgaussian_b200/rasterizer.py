@@ -337,6 +337,26 @@ def _snapshot(path: str, payload) -> None:
         pass
 
 
+# Where the autograd nodes below put their gradients.  None: fresh tensors.  A callable returning a dict of pre-allocated
+# tensors (scgaussian_b200.parallel.FlatGradBuffer.capture()): scgr_backward writes the parameter gradients, the two
+# densification statistics and the live counts straight into them -- for a data-parallel trainer, straight into the flat
+# all-reduce buffer, with no packing copies between loss.backward() and the collective.
+class _Sink:      # process-wide, not thread-local: autograd runs a CUDA node's backward on its own engine thread
+    fn = None
+
+
+_grad_sink = _Sink()
+
+
+def set_gradient_sink(fn) -> None:
+    _grad_sink.fn = fn
+
+
+def _sink_out() -> Optional[dict]:
+    fn = getattr(_grad_sink, "fn", None)
+    return fn() if fn is not None else None
+
+
 class _RasterizeGaussians(torch.autograd.Function):
     """same argument order as the external package's autograd Function."""
 
@@ -371,7 +391,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             grad_alpha = torch.zeros(1, H, W, device=dev)
         try:
             g = rasterize_backward_raw(ctx.state, means3D, opacities, sh, colors_precomp, scales, rotations,
-                                       cov3Ds_precomp, s, grad_color, grad_depth, grad_alpha)
+                                       cov3Ds_precomp, s, grad_color, grad_depth, grad_alpha, out=_sink_out())
         except Exception:
             if s.debug:
                 _snapshot("snapshot_bw.dump", (means3D, opacities, sh, colors_precomp, scales, rotations,

@@ -252,6 +252,8 @@ def build_full() -> str:
                 f.write("namespace scgr { void launch_nvls_allreduce(void*, size_t, int, int, const Launch&) {\n"
                         '    throw std::runtime_error("scgr: the NVLS collective is not part of the host emulation"); }\n'
                         "void launch_nvls_allreduce_rows(void*, const float*, long long, int, int, int, const Launch&) {\n"
+                        '    throw std::runtime_error("scgr: the NVLS collective is not part of the host emulation"); }\n'
+                        "void launch_nvls_allreduce_fused(const ScgrNvlsFused&, const Launch&) {\n"
                         '    throw std::runtime_error("scgr: the NVLS collective is not part of the host emulation"); } }\n')
         obj = os.path.join(OUT_DIR, f"tu_{n}{'_asan' if ASAN else ''}.o")
         subprocess.check_call([gxx, "-O1", "-std=c++20", "-pthread", "-fPIC", "-ffp-contract=off", "-w", *extra, "-c", "-o", obj, tu],

@@ -14,9 +14,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, P, out_dir):
+def _worker(rank, world, port, P, out_dir, fused):
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SCGR_ALLREDUCE_FUSED=fused)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -65,13 +65,15 @@ def _worker(rank, world, port, P, out_dir):
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         res["replicas_identical"] = bool(lo.item() == hi.item())
         torch.cuda.synchronize()
+        res["timed_out"] = buf.timed_out()
     finally:
         torch.save(res, os.path.join(out_dir, f"r{rank}.pt"))
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("fused", ["1", "0"])      # one launch with in-kernel barriers (default) / two launches between host-issued barriers
 @pytest.mark.parametrize("P", [1_000_000, 1001])
-def test_nvls_allreduce_equals_sum_of_rank_buffers(tmp_path, P):
+def test_nvls_allreduce_equals_sum_of_rank_buffers(tmp_path, P, fused):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs on one box (gpurun --gpus N)")
     import torch.multiprocessing as mp
@@ -79,7 +81,7 @@ def test_nvls_allreduce_equals_sum_of_rank_buffers(tmp_path, P):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(world, port, P, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, P, str(tmp_path), fused), nprocs=world, join=True)
     res = [torch.load(tmp_path / f"r{r}.pt") for r in range(world)]
     if any("skip" in r for r in res):
         pytest.skip(next(r["skip"] for r in res if "skip" in r))
@@ -90,11 +92,13 @@ def test_nvls_allreduce_equals_sum_of_rank_buffers(tmp_path, P):
         assert r["live_max_0"] >= 1.0 and r["live_max_1"] == 0.0 and r["live_max_2"] == float(world), r
         assert r["random_max_abs_diff_vs_nccl"] <= 1e-5 * r["random_scale"], r
         assert r["replicas_identical"], r
+        assert not r["timed_out"], r
+        assert ("one launch" in r["collective"]) == (fused == "1"), r
     try:
         import json
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
         with open(os.path.join(root, "gpurun_out", "parity_report.jsonl"), "a") as f:
-            f.write(json.dumps({"test": "nvls_allreduce", "world": world, "P": P, "ranks": res}) + "\n")
+            f.write(json.dumps({"test": "nvls_allreduce", "world": world, "P": P, "fused": fused, "ranks": res}) + "\n")
     except Exception:
         pass

@@ -342,6 +342,53 @@ def test_split_sh_layout_matches_the_assembled_one(dev, P, n0):
     report("split_sh_layout", P=P, n0=n0, R=int(fa[4].num_rendered))
 
 
+def test_public_operator_writes_into_the_flat_gradient_buffer(dev):
+    """FlatGradBuffer.capture(): the autograd node of the PUBLIC operator puts parameter gradients, densification
+    statistics (reference scene/gaussian_model.py:932-934) and live counts straight into the flat all-reduce buffer --
+    same values as an ordinary backward, `.grad` of the leaves aliasing the buffer (no packing copies)."""
+    from scgaussian_b200 import GaussianRasterizer
+    from scgaussian_b200.parallel import FlatGradBuffer
+    case = util.make_case(20_000, 256, 160, sh_degree=3, scale_median=0.03, seed=12)
+    s = settings_for(case, dev)
+    gup = [g.to(dev) for g in O.synth_upstream_grads(case["W"], case["H"])]
+
+    def run(sink):
+        leaves = {k: case[k].to(dev).clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+        m2d = torch.zeros(case["P"], 3, device=dev, requires_grad=True)
+        color, radii, depth, alpha = GaussianRasterizer(s)(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"],
+                                                           shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+        loss = (color * gup[0]).sum() + (depth * gup[1]).sum() + (alpha * gup[2]).sum()
+        if sink is None:
+            loss.backward()
+        else:
+            with sink.capture():
+                loss.backward()
+        return leaves, m2d, radii
+
+    ref, m2d_ref, radii = run(None)
+    buf = FlatGradBuffer(case["P"], sh_coeffs=16, device=dev)
+    buf.flat.fill_(float("nan"))
+    got, m2d_got, _ = run(buf)
+    torch.cuda.synchronize()
+    aliased = 0
+    for k, v in got.items():
+        a, b, w = v.grad, ref[k].grad, buf.views[k]
+        assert not torch.isnan(w).any(), k
+        assert float((w.reshape(b.shape) - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-12, k
+        assert torch.equal(a.reshape(-1), w.reshape(-1)), k
+        aliased += int(a.data_ptr() == w.data_ptr())
+    assert aliased == len(got), aliased                       # autograd adopted the views: nothing was copied
+    vis = (radii > 0).float()
+    st = buf.views["stats"]
+    want0 = torch.linalg.vector_norm(m2d_ref.grad[:, :2], dim=-1) * vis
+    assert torch.equal(st[:, 1], vis) and float((st[:, 0] - want0).abs().max()) <= 2e-5 * float(want0.max()) + 1e-12
+    live = buf.views["live"]
+    assert torch.equal(live != 0, (ref["opacities"].grad.reshape(-1) != 0) | (ref["means3D"].grad != 0).any(dim=1))
+    # outside the context the operator allocates its gradients again
+    again, _, _ = run(None)
+    assert again["means3D"].grad.data_ptr() != buf.views["means3D"].data_ptr()
+
+
 def test_near_plane_and_lateral_clamp(dev):
     """z in [0.1, 8.1]: some Gaussians behind the 0.2 near plane (culled), some so close that their
     splats cover hundreds of tiles and the 1.3*tanfov clamp of A.4 is active (zeroed x/y gradient)."""
