@@ -315,6 +315,7 @@ def main():
             flat.views["live"].copy_(live)
             flat.views["shs"].mul_(live.view(-1, 1, 1))
         mine = flat.flat.clone()
+        dist.barrier()                       # (the in-kernel barriers of the fused collective wait ~10 s at most)
         flat.all_reduce()
         got = flat.flat.clone()
         dist.all_reduce(mine, op=dist.ReduceOp.SUM)                       # NCCL on a private copy of the same data
@@ -362,6 +363,11 @@ def main():
     t_1 = time.perf_counter()
     launches = lib.scgr_kernel_launch_count() - l0
     need_capacity_hits = R.need_capacity_count - nc0
+    if allreduce_check is not None:
+        to = torch.tensor([1.0 if flat.timed_out() else 0.0], device=dev)
+        dist.all_reduce(to, op=dist.ReduceOp.MAX)
+        allreduce_check["a_barrier_timed_out_during_the_run"] = bool(to.item() != 0)
+        assert not allreduce_check["a_barrier_timed_out_during_the_run"], allreduce_check
     clocks = None
     if rank == 0:
         sampler.timed(t_0, t_1)

@@ -260,7 +260,7 @@ int scgr_nvls_allreduce_rows(void* multicast_rows, const float* live_count, int6
  * flags[q] is the address, in rank q's replica, of a flag array of `world` uint32 words, zero before the first call (rank
  * r release-stores into word r of every array and waits on its own); sync_local is 4 zeroed uint32 words of ordinary
  * device memory owned by the caller; epoch is 1 for the first call and grows by 3 per call (same on every rank).  The
- * grid is sized to be co-resident.  A wait that exceeds ~2 s raises sync_local[2] instead of hanging the GPU. */
+ * grid is sized to be co-resident.  A wait that exceeds ~10 s raises sync_local[2] instead of hanging the GPU. */
 #define SCGR_NVLS_MAX_WORLD 8
 typedef struct ScgrNvlsFused {
     void* multicast_ptr;          /* multicast address of the flat buffer */

@@ -133,7 +133,7 @@ nvls_allreduce_rows_kernel(float4* __restrict__ mc, const float* __restrict__ li
 // kernel, on flag words in symmetric memory, instead of three host-issued barrier kernels between two launches ----
 // Barrier s (a monotonically increasing epoch): rank r release-stores s into word r of every peer's flag array, then waits
 // until every word of its own array has reached s.  Inside the grid CTA 0 does that once all CTAs have arrived (atomic
-// counter) and releases the others through a `go` word.  Every wait is bounded: on a timeout the kernel raises
+// counter) and releases the others through a `go` word.  Every wait is bounded (~10 s): on a timeout the kernel raises
 // sync[2] and carries on (wrong sums, reported by the host, rather than a hung GPU).
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -165,7 +165,7 @@ struct FusedArgs {
     uint32_t epoch;                          // first of the three barrier values of this call
 };
 
-constexpr long long SPIN_LIMIT = 4000000000ll;      // cycles (~2 s): far beyond any legitimate wait
+constexpr long long SPIN_LIMIT = 20000000000ll;     // cycles (~10 s): far beyond any legitimate skew between ranks
 
 template <typename F>
 __device__ __forceinline__ void bounded_spin(uint32_t* sync, F&& ready) {

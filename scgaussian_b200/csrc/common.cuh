@@ -333,6 +333,15 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Per-thread asynchronous copies (LDGSTS): unlike a bulk copy, which takes its addresses from uniform registers and is
+// therefore issued one lane at a time when every lane has its own source (8 instructions x 32 rounds per warp), one
+// cp.async serves the 32 lanes of a warp at once.  Completion is per thread (wait_group), then a warp barrier.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // generic-proxy accesses of a staging buffer (reads, in-place writes) ordered before the async-proxy writes that refill it
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // arrival without bytes: a thread that takes part in the phase but issues no copy

@@ -15,10 +15,12 @@
 //   * The tile's depth-ordered list is consumed 32 Gaussians at a time: lane l fetches the packed
 //     48-byte record of the l-th one and computes, for its Gaussian, an exact
 //     closed-form bound of the maximum of the Gaussian's exponent over each slot rectangle.
-//     Two staging schemes, both double-buffered, chosen per kernel by measurement: the backward uses
-//     TMA -- one `cp.async.bulk` per lane into shared memory, completion on an mbarrier, no register
-//     holds data in flight (which lets 18 warps per SM fit) --, the forward prefetches the next batch
-//     into registers with 3 x 128-bit loads (its register budget has room, and it is 8 % faster so).
+//     Three staging schemes, all double-buffered, chosen per kernel by measurement: three 16-byte `cp.async` per
+//     lane straight into shared memory, completion per thread (wait_group) + a warp barrier -- no register holds
+//     data in flight, which lets 18 warps per SM fit in the backward (the default of both kernels since round 2);
+//     TMA, one `cp.async.bulk` per lane + an mbarrier (round 1's backward: a bulk copy takes its addresses from
+//     uniform registers, so per-lane copies are issued one lane at a time, 256 instructions per batch); and
+//     prefetching the next batch into registers with 3 x 128-bit loads (round 1's forward).
 //     Slots whose bound says alpha < 1/255 everywhere are skipped without touching a pixel
 //     (conservative: the per-pixel test that follows is the reference's, so no output changes).
 //   * Backward: every lane accumulates its 10 per-Gaussian gradient terms over its 8 pixels in
@@ -188,7 +190,8 @@ struct WorkSplit {
 // One warp renders a region of SPW slots (SPW = 8: the whole tile, 4: a 16x8 half, 2: a 16x4 quarter)
 // whose first slot is slot k0 of the tile.  Warps that share a tile never synchronise with each
 // other (disjoint pixels, private staging buffers).
-template <int SPW, bool TMA>
+// TMA: 0 register-prefetched gathers, 1 one bulk copy per lane + mbarrier, 2 three cp.async per lane (see backward_region)
+template <int SPW, int TMA>
 __device__ __forceinline__ void
 forward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[96], unsigned long long* bars,
                const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
@@ -196,7 +199,7 @@ forward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[
                float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha,
                uint32_t* __restrict__ n_contrib, float* __restrict__ final_T, uint4* __restrict__ tile_todo) {
     const int lane = threadIdx.x & 31;
-    if (TMA) {
+    if (TMA == 1) {
         if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
         mbar_fence_init();
         __syncwarp();
@@ -222,10 +225,19 @@ forward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[
     // stage b of the list = entries [32 b, 32 b + 32); buffer b & 1
     auto issue = [&](const int b) {
         const int c = min(32, total - 32 * b);
-        if (lane == 0) mbar_expect_tx(&bars[b & 1], 48u * (uint32_t)c);
-        __syncwarp();
-        if (lane < c)
-            bulk_g2s(&s_rec[b & 1][lane * 3], rec + point_list[range.x + 32 * b + lane], 48u, &bars[b & 1]);
+        if (TMA == 1) {
+            if (lane == 0) mbar_expect_tx(&bars[b & 1], 48u * (uint32_t)c);
+            __syncwarp();
+            if (lane < c)
+                bulk_g2s(&s_rec[b & 1][lane * 3], rec + point_list[range.x + 32 * b + lane], 48u, &bars[b & 1]);
+        } else {
+            if (lane < c) {
+                const float4* src = reinterpret_cast<const float4*>(rec + point_list[range.x + 32 * b + lane]);
+                float4* dst = &s_rec[b & 1][lane * 3];
+                cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
+            }
+            cp_async_commit();
+        }
     };
     Rec nxt;
     nxt.q0 = nxt.q1 = nxt.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -247,7 +259,11 @@ forward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[
         const int cnt = min(32, total - base);
         const float4* const srec = s_rec[TMA ? (b & 1) : 0];
         Rec cur;
-        if (TMA) {
+        if (TMA == 2) {
+            if (b + 1 < nbatch) { issue(b + 1); cp_async_wait_all_but_one(); } else cp_async_wait_all();
+            __syncwarp();
+            cur.q0 = srec[lane * 3]; cur.q1 = srec[lane * 3 + 1]; cur.q2 = srec[lane * 3 + 2];
+        } else if (TMA) {
             mbar_wait(&bars[b & 1], (uint32_t)(b >> 1) & 1u);
             __syncwarp();
             if (b + 1 < nbatch) issue(b + 1);        // the other buffer was released by the __syncwarp below
@@ -306,7 +322,8 @@ forward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[
         }
         __syncwarp();      // every lane is done with this stage before it is refilled
     }
-    if (TMA && b < nbatch) mbar_wait(&bars[b & 1], (uint32_t)(b >> 1) & 1u);   // drain the copy in flight before exiting
+    if (TMA == 1 && b < nbatch) mbar_wait(&bars[b & 1], (uint32_t)(b >> 1) & 1u);   // drain the copy in flight before exiting
+    if (TMA == 2) cp_async_wait_all();
     SCGR_STAT_FLUSH_WARP(0, batches); SCGR_STAT_FLUSH_WARP(1, scanned); SCGR_STAT_FLUSH_WARP(2, hit);
     SCGR_STAT_FLUSH_WARP(3, slots); SCGR_STAT_FLUSH_LANES(4, cand); SCGR_STAT_FLUSH_LANES(5, go);
 #ifdef SCGR_STATS
@@ -465,14 +482,14 @@ forward_region_packed(const int tile, const int tiles_x, const int k0, float4* s
     }
 }
 
-template <int MINB, int MODE>      // MODE 0: register-prefetched gathers, 1: TMA staging, 2: packed-fp32 blend
+template <int MINB, int MODE>      // MODE 0: register-prefetched gathers, 1: TMA staging, 2: packed-fp32 blend, 3: cp.async staging
 __global__ void __launch_bounds__(32, MINB)
 render_forward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __restrict__ ranges,
                       const uint32_t* __restrict__ point_list, const Record* __restrict__ rec, int W, int H,
                       const float* __restrict__ bg, const int64_t* __restrict__ status, int64_t capacity,
                       float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha,
                       uint32_t* __restrict__ n_contrib, float* __restrict__ final_T, uint4* __restrict__ tile_todo) {
-    constexpr bool TMA = MODE == 1;
+    constexpr int TMA = MODE == 1 ? 1 : (MODE == 3 ? 2 : 0);
     __shared__ __align__(16) float4 s_rec[MODE == 2 ? 1 : 2][MODE == 2 ? 32 * DUP_F4 : 96];   // record staging (MODE 2: packed-blend layout)
     __shared__ __align__(8) unsigned long long s_bar[2];
     int b = blockIdx.x;
@@ -570,7 +587,10 @@ __device__ __forceinline__ float transpose_reduce10(const float v[10], const int
     return d;
 }
 
-template <int SPW, bool TMA>
+// TMA: how the records of a batch reach shared memory -- 0: register-prefetched gathers, 1: one bulk copy per lane +
+// mbarrier, 2: three 16-byte cp.async per lane (one instruction serves the warp; a per-lane bulk copy is issued lane by
+// lane, 256 instructions per batch).
+template <int SPW, int TMA>
 __device__ __forceinline__ void
 backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)[96], uint32_t (*s_idb)[32],
                 unsigned long long* bars, float4* s_g4, const uint2* __restrict__ ranges,
@@ -580,7 +600,7 @@ backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)
                 const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha,
                 ScreenGrad* __restrict__ screen_grad) {
     const int lane = threadIdx.x & 31;
-    if (TMA) {
+    if (TMA == 1) {
         if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
         mbar_fence_init();
         __syncwarp();
@@ -624,13 +644,22 @@ backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)
     // stage b = batch entries [32 b, 32 b + 32) of the back-to-front walk; buffer b & 1
     auto issue = [&](const int b) {
         const int c = min(32, toDo - 32 * b);
-        if (lane == 0) mbar_expect_tx(&bars[b & 1], 48u * (uint32_t)c);
-        __syncwarp();
+        if (TMA == 1) {
+            if (lane == 0) mbar_expect_tx(&bars[b & 1], 48u * (uint32_t)c);
+            __syncwarp();
+        }
         if (lane < c) {
             const uint32_t id = point_list[range.x + (toDo - 1 - (32 * b + lane))];
             s_idb[b & 1][lane] = id;
-            bulk_g2s(&s_rec[b & 1][lane * 3], rec + id, 48u, &bars[b & 1]);
+            if (TMA == 1) {
+                bulk_g2s(&s_rec[b & 1][lane * 3], rec + id, 48u, &bars[b & 1]);
+            } else {
+                const float4* src = reinterpret_cast<const float4*>(rec + id);
+                float4* dst = &s_rec[b & 1][lane * 3];
+                cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
+            }
         }
+        if (TMA == 2) cp_async_commit();
     };
     Rec nxt;
     uint32_t nxt_id = 0u;
@@ -650,7 +679,13 @@ backward_region(const int tile, const int tiles_x, const int k0, float4 (*s_rec)
         const float4* const srec = s_rec[TMA ? (b & 1) : 0];
         const uint32_t* const s_id = s_idb[TMA ? (b & 1) : 0];
         Rec cur;
-        if (TMA) {
+        if (TMA == 2) {
+            // the other buffer was released by the __syncwarp that ends the previous iteration: refill it, then wait for
+            // this thread's copies of the current one; the warp barrier makes every lane's copies visible to all
+            if (b + 1 < nbatch) { issue(b + 1); cp_async_wait_all_but_one(); } else cp_async_wait_all();
+            __syncwarp();
+            cur.q0 = srec[lane * 3]; cur.q1 = srec[lane * 3 + 1]; cur.q2 = srec[lane * 3 + 2];
+        } else if (TMA) {
             mbar_wait(&bars[b & 1], (uint32_t)(b >> 1) & 1u);
             __syncwarp();                            // (also orders the generic s_id stores of this stage)
             if (b + 1 < nbatch) issue(b + 1);        // the other buffer was released by the __syncwarp below
@@ -940,7 +975,7 @@ backward_region_packed(const int tile, const int tiles_x, const int k0, float4 (
 #endif
 }
 
-template <int MINB, bool TMA, bool PK>
+template <int MINB, int TMA, bool PK>
 __global__ void __launch_bounds__(32, MINB)
 render_backward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __restrict__ ranges,
                        const uint32_t* __restrict__ point_list, const Record* __restrict__ rec, int W, int H,
@@ -973,9 +1008,9 @@ render_backward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __res
     if constexpr (PK) {
 #define SCGR_ARGS s_rec, s_dup, s_id, s_bar, s_g4, ranges, point_list, rec, W, H, bg, n_contrib, final_T, dL_dcolor, dL_ddepth, \
                   dL_dalpha, screen_grad
-        if (spw == 8) backward_region_packed<8, TMA>(tile, tiles_x, k0, SCGR_ARGS);
-        else if (spw == 4) backward_region_packed<4, TMA>(tile, tiles_x, k0, SCGR_ARGS);
-        else backward_region_packed<2, TMA>(tile, tiles_x, k0, SCGR_ARGS);
+        if (spw == 8) backward_region_packed<8, TMA != 0>(tile, tiles_x, k0, SCGR_ARGS);
+        else if (spw == 4) backward_region_packed<4, TMA != 0>(tile, tiles_x, k0, SCGR_ARGS);
+        else backward_region_packed<2, TMA != 0>(tile, tiles_x, k0, SCGR_ARGS);
 #undef SCGR_ARGS
     } else {
 #define SCGR_ARGS s_rec, s_id, s_bar, s_g4, ranges, point_list, rec, W, H, bg, n_contrib, final_T, dL_dcolor, dL_ddepth, \
@@ -1100,8 +1135,9 @@ void launch_render_forward(const ScgrView& v, const GeometryLayout& G, const Bin
     const int tx = (v.image_width + TILE - 1) / TILE, ty = (v.image_height + TILE - 1) / TILE;
     if (tx == 0 || ty == 0) return;
     static const int minb = env_int("SCGR_FWD_MINB", 20);
-    // staging / blend variant: 0 register-prefetched gathers + scalar blend, 1 TMA staging + scalar blend, 2 packed-fp32 blend
-    static const int tma = env_int("SCGR_FWD_PACKED", 0) ? 2 : env_int("SCGR_TMA_FWD", env_int("SCGR_TMA", 0));
+    // staging / blend variant: 0 register-prefetched gathers + scalar blend, 1 TMA staging + scalar blend, 2 packed-fp32 blend,
+    // 3 cp.async staging + scalar blend
+    static const int tma = env_int("SCGR_FWD_PACKED", 0) ? 2 : env_int("SCGR_TMA_FWD", env_int("SCGR_TMA", 3));
     const WorkSplit ws = make_split(tx * ty, "SCGR_FWD_SPLIT", 10, 5);
     begin_kernel("render_forward", L);
 #define SCGR_FWD(M_, T_) render_forward_kernel<M_, T_><<<ws.items(), 32, 0, L.stream>>>(ws, tx, B.ranges, point_list, G.rec, \
@@ -1109,6 +1145,10 @@ void launch_render_forward(const ScgrView& v, const GeometryLayout& G, const Bin
         I.tile_todo)
     if (tma == 0) { if (minb == 20) SCGR_FWD(20, 0); else if (minb == 24) SCGR_FWD(24, 0); else SCGR_FWD(1, 0); }
     else if (tma == 1) { if (minb == 20) SCGR_FWD(20, 1); else if (minb == 24) SCGR_FWD(24, 1); else SCGR_FWD(1, 1); }
+    else if (tma == 3) {      // cp.async staging
+        if (minb == 20) SCGR_FWD(20, 3); else if (minb == 24) SCGR_FWD(24, 3); else if (minb == 22) SCGR_FWD(22, 3);
+        else if (minb == 26) SCGR_FWD(26, 3); else if (minb == 28) SCGR_FWD(28, 3); else SCGR_FWD(1, 3);
+    }
     else if (minb == 20) SCGR_FWD(20, 2); else if (minb == 24) SCGR_FWD(24, 2); else if (minb == 16) SCGR_FWD(16, 2); else if (minb == 18) SCGR_FWD(18, 2); else SCGR_FWD(1, 2);
 #undef SCGR_FWD
     check_launch("render_forward", L);
@@ -1123,10 +1163,12 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
         cudaMemsetAsync(G.screen_grad, 0, (size_t)(P > 0 ? P : 0) * sizeof(ScreenGrad), L.stream);
         return;
     }
-    // defaults measured on B200 (config 3): TMA-staged records free the 13 prefetch registers, which lets 18
-    // warps per SM fit without rematerialisation: 450 us vs 464 us for register prefetch at 16 warps
+    // defaults measured on B200 (config 3): asynchronously staged records free the 13 prefetch registers, which lets 18
+    // warps per SM fit without rematerialisation (round 1: 450 us with per-lane bulk copies vs 464 us for register prefetch
+    // at 16 warps); round 2: cp.async instead of bulk copies (a per-lane bulk copy is issued lane by lane, 256 instructions
+    // per batch of an issue-bound kernel): 430 -> 416 us
     static const int minb = env_int("SCGR_BWD_MINB", 18);
-    static const int tma = env_int("SCGR_TMA_BWD", env_int("SCGR_TMA", 1));
+    static const int tma = env_int("SCGR_TMA_BWD", env_int("SCGR_TMA", 2));
     WorkSplit ws = make_split(tx * ty, "SCGR_BWD_SPLIT", 0, 0);
     // SCGR_BWD_DEEP="h,q": cut the DEEPEST q % of the tiles in quarters and the next h % in halves instead
     if (const char* e = getenv("SCGR_BWD_DEEP")) {
@@ -1157,6 +1199,10 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
         else if (minb == 16) SCGR_BWD(16, true, true); else if (minb == 14) SCGR_BWD(14, true, true); else if (minb == 18) SCGR_BWD(18, true, true); else SCGR_BWD(1, true, true);
     }
     else if (!tma) { if (minb == 16) SCGR_BWD(16, false, false); else if (minb == 18) SCGR_BWD(18, false, false); else SCGR_BWD(1, false, false); }
+    else if (tma == 2) {      // cp.async staging
+        if (minb == 16) SCGR_BWD(16, 2, false); else if (minb == 20) SCGR_BWD(20, 2, false); else if (minb == 19) SCGR_BWD(19, 2, false);
+        else if (minb == 21) SCGR_BWD(21, 2, false); else SCGR_BWD(18, 2, false);
+    }
     else if (minb == 16) SCGR_BWD(16, true, false); else if (minb == 14) SCGR_BWD(14, true, false); else if (minb == 20) SCGR_BWD(20, true, false); else if (minb == 18) SCGR_BWD(18, true, false); else if (minb == 19) SCGR_BWD(19, true, false); else if (minb == 17) SCGR_BWD(17, true, false); else SCGR_BWD(1, true, false);
 #undef SCGR_BWD
     check_launch("render_backward", L);

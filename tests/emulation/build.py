@@ -138,6 +138,10 @@ _TMA_PTX = {
     "mbar_init": "emu_mbar_init(bar, count);",
     "mbar_fence_init": "",
     "fence_proxy_async": "",
+    "cp_async16": "std::memcpy(dst, src, 16);",
+    "cp_async_commit": "",
+    "cp_async_wait_all_but_one": "",
+    "cp_async_wait_all": "",
     "mbar_arrive": "emu_mbar_update(bar, -1, 0);",
     "mbar_expect_tx": "emu_mbar_update(bar, -1, (long long)bytes);",
     "bulk_g2s": "std::memcpy(dst, src, bytes); emu_mbar_update(bar, 0, -(long long)bytes);",

@@ -536,7 +536,8 @@ def _host_forward(emu_pre, case, t, view, g, P, W, H):
 # work split "halves,quarters" in percent of the tiles: whole tiles (8 slots per warp), halves (4), quarters (2);
 # staging of the records: register-prefetched gathers (0) or the TMA path (1; a synchronous copy in the emulation)
 @pytest.mark.parametrize("P,W,H,smed,split,tma", [(700, 100, 70, 0.06, "0,0", 0), (700, 100, 70, 0.06, "100,0", 1),
-                                                  (400, 64, 48, 0.15, "0,100", 0), (900, 130, 50, 0.05, "30,30", 1)])
+                                                  (400, 64, 48, 0.15, "0,100", 0), (900, 130, 50, 0.05, "30,30", 1),
+                                                  (800, 110, 75, 0.06, "20,20", 2)])      # tma 2: cp.async staging (backward)
 def test_whole_operator_on_host_matches_oracle(emu_pre, monkeypatch, P, W, H, smed, split, tma):
     """Every kernel of the operator, forward and backward, executed on the host and
     compared with the C oracle the way the GPU parity tests compare the GPU: images within 1e-4, gradients within 1e-3,
