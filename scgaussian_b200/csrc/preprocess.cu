@@ -510,7 +510,10 @@ preprocess_forward_kernel(const ScgrView v, const ScgrGaussians g, Record* __res
 // what the array holds, Gaussians without gradient are not touched at all; dL/dmean2D stays per view.
 // TMA (SH_FAST, not SPLIT): the SH row of every live Gaussian of a round arrives by one bulk-async copy issued by the thread
 // that will process it; the wait sits in front of step (4), behind the conic / covariance / mean chain of steps (1)-(3).
-template <bool SH_FAST, int MINB, bool ACC, bool SPLIT, bool TMA>
+// (TMA 2: the same with twelve 16-byte cp.async per thread instead of one bulk copy -- a thread waits for its own copies
+// and reads only its own row, so neither an mbarrier nor a block barrier is involved, and the copies are not issued lane
+// by lane as per-lane bulk copies are.)
+template <bool SH_FAST, int MINB, bool ACC, bool SPLIT, int TMA>
 __global__ void __launch_bounds__(PB_T, MINB)
 preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record* __restrict__ rec,
                            const ScreenGrad* __restrict__ sg, const ScgrGrads out) {
@@ -521,7 +524,7 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     __shared__ int s_wcnt[PB_K][PB_T / 32];
     __shared__ uint32_t s_wbal[PB_K][PB_T / 32];   // live mask of local rows [32 (k PB_T / 32 + w), + 32)
     __shared__ __align__(8) unsigned long long s_bar;
-    if (TMA && threadIdx.x == 0) {
+    if (TMA == 1 && threadIdx.x == 0) {
         mbar_init(&s_bar, PB_T);      // every thread arrives once per round, the live ones with the bytes of their row
         mbar_fence_init();
     }
@@ -643,8 +646,16 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
     const bool live = tid < in_round;
     const int jl = live ? (int)s_list[first + tid] : 0;      // local index of the Gaussian this thread processes
     const int i = row0 + jl;
-    const bool tma = TMA && use_sh;
-    if (tma) {
+    const bool tma = TMA != 0 && use_sh;
+    if (tma && TMA == 2) {
+        if (live) {
+            const float4* src = reinterpret_cast<const float4*>(g.shs) + (size_t)i * SH_ROW_F4;
+            float4* dst = &s_sh[tid * SH_ROW_F4_PAD];
+#pragma unroll
+            for (int c = 0; c < SH_ROW_F4; c++) cp_async16(dst + c, src + c);
+        }
+        cp_async_commit();
+    } else if (tma) {
         if (live) {
             fence_proxy_async();      // the previous round read and rewrote this row through the generic proxy
             mbar_expect_tx(&s_bar, SH_ROW_F4 * sizeof(float4));
@@ -824,7 +835,8 @@ preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record
             sh_basis(D, d, bb);
             sh_basis_grad(D, d, bx, by, bz);
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-            if (tma) mbar_wait(&s_bar, (uint32_t)(first / PB_T) & 1u);
+            if (tma && TMA == 2) cp_async_wait_all();
+            else if (tma) mbar_wait(&s_bar, (uint32_t)(first / PB_T) & 1u);
             if (SH_FAST) {
                 // in place: the staged input row of the Gaussian becomes its gradient row
                 float4* row = s_sh + tid * SH_ROW_F4_PAD;
@@ -1013,21 +1025,23 @@ void launch_preprocess_backward(const ScgrView& v, const ScgrGaussians& g, const
     begin_kernel("preprocess_backward", L);
     static const int minb = getenv("SCGR_PREB_MINB") ? atoi(getenv("SCGR_PREB_MINB")) : 1;
     const bool acc = out.accumulate != 0;
-    static const int tma = getenv("SCGR_TMA_PREB") ? atoi(getenv("SCGR_TMA_PREB")) : 1;
+    static const int tma = getenv("SCGR_TMA_PREB") ? atoi(getenv("SCGR_TMA_PREB")) : 2;
     if (sh_split(g)) {
-        if (acc) preprocess_backward_kernel<true, 1, true, true, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else preprocess_backward_kernel<true, 1, false, true, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        if (acc) preprocess_backward_kernel<true, 1, true, true, 0><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else preprocess_backward_kernel<true, 1, false, true, 0><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     } else if (sh_fast_ok(g, out.dL_dshs)) {
-        if (acc && tma) preprocess_backward_kernel<true, 1, true, false, true><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (acc) preprocess_backward_kernel<true, 1, true, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (minb == 12) preprocess_backward_kernel<true, 12, false, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (minb == 10) preprocess_backward_kernel<true, 10, false, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (tma) preprocess_backward_kernel<true, 1, false, false, true><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else preprocess_backward_kernel<true, 1, false, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        if (acc && tma == 2) preprocess_backward_kernel<true, 1, true, false, 2><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (acc && tma) preprocess_backward_kernel<true, 1, true, false, 1><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (acc) preprocess_backward_kernel<true, 1, true, false, 0><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (minb == 12) preprocess_backward_kernel<true, 12, false, false, 0><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (minb == 10) preprocess_backward_kernel<true, 10, false, false, 0><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (tma == 2) preprocess_backward_kernel<true, 1, false, false, 2><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else if (tma) preprocess_backward_kernel<true, 1, false, false, 1><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        else preprocess_backward_kernel<true, 1, false, false, 0><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     } else if (acc) {
-        preprocess_backward_kernel<false, 1, true, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        preprocess_backward_kernel<false, 1, true, false, 0><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     } else {
-        preprocess_backward_kernel<false, 1, false, false, false><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        preprocess_backward_kernel<false, 1, false, false, 0><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
     }
     check_launch("preprocess_backward", L);
 }
