@@ -273,6 +273,10 @@ typedef struct ScgrNvlsFused {
     uint32_t* flags[SCGR_NVLS_MAX_WORLD];
     uint32_t* sync_local;
     uint32_t epoch;
+    /* optional: peer_ptrs[q] = rank q's peer-to-peer mapping of the flat buffer (all `world` entries, world 2 / 4 / 8).  Non-NULL
+     * selects plain peer loads / stores instead of the multicast instructions for both shots: faster with few ranks, where
+     * the switch's reduction engine runs far below the link rate.  Same sums (one reduction per element, in rank order). */
+    void* peer_ptrs[SCGR_NVLS_MAX_WORLD];
 } ScgrNvlsFused;
 int scgr_nvls_allreduce_fused(const ScgrNvlsFused* args, scgr_stream_t stream);
 

@@ -39,7 +39,8 @@ class ScgrGrads(C.Structure):
 class ScgrNvlsFused(C.Structure):
     _fields_ = [("multicast_ptr", C.c_void_p), ("dense_floats", C.c_size_t), ("multicast_rows", C.c_void_p),
                 ("live_count", C.c_void_p), ("n_rows", C.c_int64), ("row_floats", C.c_int32), ("rank", C.c_int32),
-                ("world", C.c_int32), ("flags", C.c_void_p * 8), ("sync_local", C.c_void_p), ("epoch", C.c_uint32)]
+                ("world", C.c_int32), ("flags", C.c_void_p * 8), ("sync_local", C.c_void_p), ("epoch", C.c_uint32),
+                ("peer_ptrs", C.c_void_p * 8)]
 
 
 class ScgrDebugViews(C.Structure):

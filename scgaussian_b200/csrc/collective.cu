@@ -152,6 +152,73 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
     return v;
 }
 
+// ---- the same two shots over plain peer-to-peer loads and stores (no multicast) ----
+// With few ranks the switch's reduction engine is the slow way: at 2 ranks multimem.ld_reduce + multimem.st move the 60 MB
+// of small blocks at a third of the link rate (0.19 ms; ncclAllReduce's direct path: 0.13 ms).  Here the owner of an
+// element loads it from every replica through the peer mappings, adds the values in rank order (one reduction per
+// element, in a fixed order: replicas stay bit-identical) and stores the sum into every replica.
+template <int WORLD>
+__device__ __forceinline__ float4 p2p_sum(float4* const* __restrict__ peer, const size_t i) {
+    float4 v[WORLD];
+#pragma unroll
+    for (int q = 0; q < WORLD; q++) v[q] = __ldcg(peer[q] + i);      // (L2 of the owning GPU: never a stale L1 line)
+    float4 a = v[0];
+#pragma unroll
+    for (int q = 1; q < WORLD; q++) { a.x += v[q].x; a.y += v[q].y; a.z += v[q].z; a.w += v[q].w; }
+    return a;
+}
+template <int WORLD>
+__device__ __forceinline__ void p2p_store(float4* const* __restrict__ peer, const size_t i, const float4 a) {
+#pragma unroll
+    for (int q = 0; q < WORLD; q++) __stcg(peer[q] + i, a);
+}
+
+template <int THREADS, int WORLD>
+__device__ __forceinline__ void dense_shot_p2p(float4* const* __restrict__ peer, const size_t first, const size_t count) {
+    const size_t stride = (size_t)gridDim.x * THREADS;
+    constexpr int U = WORLD <= 2 ? 4 : 2;
+    size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x;
+    for (; i + (U - 1) * stride < count; i += U * stride) {
+        float4 a[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) a[u] = p2p_sum<WORLD>(peer, first + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < U; u++) p2p_store<WORLD>(peer, first + i + u * stride, a[u]);
+    }
+    for (; i < count; i += stride) p2p_store<WORLD>(peer, first + i, p2p_sum<WORLD>(peer, first + i));
+    __threadfence_system();
+}
+
+template <int THREADS, int WORLD>
+__device__ __forceinline__ void rows_shot_p2p(float4* const* __restrict__ peer, const size_t rows_f4, const float* __restrict__ live,
+                                              const long long row_first, const long long row_end, const int row_f4) {
+    constexpr int CHUNK = 128;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * THREADS + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * THREADS) >> 5;
+    for (long long base = row_first + warp * CHUNK; base < row_end; base += n_warps * CHUNK) {
+        uint32_t bal[4], pre[5];
+        pre[0] = 0u;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const long long i = base + 32 * q + lane;
+            bal[q] = __ballot_sync(0xffffffffu, i < row_end && live[i] != 0.f);
+            pre[q + 1] = pre[q] + __popc(bal[q]);
+        }
+        const uint32_t items = pre[4] * (uint32_t)row_f4;
+        for (uint32_t it = lane; it < items; it += 32u) {
+            const uint32_t k = it / (uint32_t)row_f4, c = it - k * (uint32_t)row_f4;
+            const int q = (k >= pre[1]) + (k >= pre[2]) + (k >= pre[3]);
+            const uint32_t w = q == 0 ? bal[0] : (q == 1 ? bal[1] : (q == 2 ? bal[2] : bal[3]));
+            const uint32_t p0 = q == 0 ? pre[0] : (q == 1 ? pre[1] : (q == 2 ? pre[2] : pre[3]));
+            const long long row = base + 32 * q + (long long)nth_set_bit(w, k - p0);
+            const size_t i = rows_f4 + (size_t)row * row_f4 + c;
+            p2p_store<WORLD>(peer, i, p2p_sum<WORLD>(peer, i));
+        }
+    }
+    __threadfence_system();
+}
+
 struct FusedArgs {
     float4* mc;
     size_t dense_first, dense_count;      // this rank's shard of the dense part, float4 units
@@ -163,6 +230,8 @@ struct FusedArgs {
     uint32_t* flags[SCGR_NVLS_MAX_WORLD];   // flags[q]: the flag array inside rank q's replica (world words)
     uint32_t* sync;                          // local: [0] arrivals, [1] go, [2] timeout raised
     uint32_t epoch;                          // first of the three barrier values of this call
+    float4* peer[SCGR_NVLS_MAX_WORLD];       // peer-to-peer shots: rank q's mapping of the flat buffer (NULL: multicast shots)
+    size_t rows_f4;                          // offset of the rows block inside the flat buffer, float4 units
 };
 
 constexpr long long SPIN_LIMIT = 20000000000ll;     // cycles (~10 s): far beyond any legitimate skew between ranks
@@ -202,9 +271,20 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 nvls_allreduce_fused_kernel(const FusedArgs a) {
     fused_barrier(a, a.epoch, false, 0u);                    // every replica has been written by its rank's backward
-    if (a.dense_count) dense_shot<THREADS, 4>(a.mc, a.dense_first, a.dense_count);
+    const bool p2p = a.peer[0] != nullptr;
+    if (a.dense_count) {
+        if (!p2p) dense_shot<THREADS, 4>(a.mc, a.dense_first, a.dense_count);
+        else if (a.world == 2) dense_shot_p2p<THREADS, 2>(a.peer, a.dense_first, a.dense_count);
+        else if (a.world == 4) dense_shot_p2p<THREADS, 4>(a.peer, a.dense_first, a.dense_count);
+        else dense_shot_p2p<THREADS, 8>(a.peer, a.dense_first, a.dense_count);
+    }
     fused_barrier(a, a.epoch + 1u, true, gridDim.x);         // the summed live counts are in place on every rank
-    if (a.row_end > a.row_first) rows_shot<THREADS, 4>(a.mc_rows, a.live, a.row_first, a.row_end, a.row_f4);
+    if (a.row_end > a.row_first) {
+        if (!p2p) rows_shot<THREADS, 4>(a.mc_rows, a.live, a.row_first, a.row_end, a.row_f4);
+        else if (a.world == 2) rows_shot_p2p<THREADS, 2>(a.peer, a.rows_f4, a.live, a.row_first, a.row_end, a.row_f4);
+        else if (a.world == 4) rows_shot_p2p<THREADS, 4>(a.peer, a.rows_f4, a.live, a.row_first, a.row_end, a.row_f4);
+        else rows_shot_p2p<THREADS, 8>(a.peer, a.rows_f4, a.live, a.row_first, a.row_end, a.row_f4);
+    }
     // every shard has been broadcast; the last arrival leaves the counter clean for the next call
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -290,6 +370,11 @@ void launch_nvls_allreduce_fused(const ScgrNvlsFused& f, const Launch& L) {
     a.rank = f.rank;
     a.world = f.world;
     for (int q = 0; q < f.world; q++) a.flags[q] = f.flags[q];
+    // peer-to-peer shots when the caller passed the peer mappings and the world is one of the compiled sizes
+    if (f.peer_ptrs[0] && (f.world == 2 || f.world == 4 || f.world == 8)) {
+        for (int q = 0; q < f.world; q++) a.peer[q] = reinterpret_cast<float4*>(f.peer_ptrs[q]);
+        a.rows_f4 = f.multicast_rows ? (size_t)((char*)f.multicast_rows - (char*)f.multicast_ptr) / 16 : 0;
+    }
     a.sync = f.sync_local;
     a.epoch = f.epoch;
     int dev = 0, sms = 148;

@@ -38,6 +38,7 @@ import torch.distributed as dist
 
 class FlatGradBuffer:
     FLAG_WORDS = 64          # >= world; keeps the allocation a multiple of 256 bytes
+    P2P_MAX_WORLD = 2        # largest world for which the peer-to-peer shots are the default (measured, profiles/r02_scaling.md)
 
     def __init__(self, P: int, sh_coeffs: int = 16, use_sh: bool = True, use_cov: bool = False,
                  device="cuda", with_stats: bool = True, symmetric: Optional[bool] = None):
@@ -178,12 +179,21 @@ class FlatGradBuffer:
     def collective(self) -> str:
         if self._symm is None:
             return "nccl all_reduce"
-        how = ", one launch with in-kernel barriers" if self._fused(int(self._symm.world_size)) else ""
+        w = int(self._symm.world_size)
+        how = ", one launch with in-kernel barriers" if self._fused(w) else ""
+        if self._fused(w) and self._p2p(w):
+            how += ", peer-to-peer loads / stores"
         return ("nvls two-shot kernels (libscgr): dense small blocks + row-sparse dL/dSH" if self._sparse() else
                 "nvls two-shot kernel (libscgr), dense") + how
 
     def _fused(self, world: int) -> bool:
         return world <= 8 and os.environ.get("SCGR_ALLREDUCE_FUSED", "1") != "0"
+
+    def _p2p(self, world: int) -> bool:
+        """Plain peer loads / stores instead of the multicast instructions: measured faster with few ranks (2: 0.19 ->
+        ~0.1 ms for the small blocks).  SCGR_NVLS_P2P=auto|0|1."""
+        mode = os.environ.get("SCGR_NVLS_P2P", "auto")
+        return world in (2, 4, 8) and (mode == "1" or (mode == "auto" and world <= self.P2P_MAX_WORLD))
 
     def timed_out(self) -> bool:
         """True if a barrier inside the fused collective ever gave up waiting (the sums are then wrong)."""
@@ -216,6 +226,10 @@ class FlatGradBuffer:
                     f.flags[q] = int(hdl.buffer_ptrs[q]) + off
                 f.sync_local = self._sync.data_ptr()
                 f.epoch = self._epoch
+                if self._p2p(world):
+                    base_off = self.flat.data_ptr() - int(hdl.buffer_ptrs[rank])
+                    for q in range(world):
+                        f.peer_ptrs[q] = int(hdl.buffer_ptrs[q]) + base_off
                 self._epoch = (self._epoch + 3) & 0xffffffff      # (compared modulo 2^32 in the kernel)
                 _lib.check(lib.scgr_nvls_allreduce_fused(C.byref(f), stream))
                 return None

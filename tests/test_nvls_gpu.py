@@ -16,7 +16,10 @@ pytestmark = pytest.mark.gpu
 
 def _worker(rank, world, port, P, out_dir, fused):
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SCGR_ALLREDUCE_FUSED=fused)
+    # fused: "1" one launch (shots chosen automatically), "0" two launches between host-issued barriers,
+    #        "mc" one launch with the multicast shots, "p2p" one launch with the peer-to-peer shots
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SCGR_ALLREDUCE_FUSED="0" if fused == "0" else "1",
+                      SCGR_NVLS_P2P={"mc": "0", "p2p": "1"}.get(fused, "auto"))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -71,7 +74,7 @@ def _worker(rank, world, port, P, out_dir, fused):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("fused", ["1", "0"])      # one launch with in-kernel barriers (default) / two launches between host-issued barriers
+@pytest.mark.parametrize("fused", ["1", "0", "mc", "p2p"])      # see _worker
 @pytest.mark.parametrize("P", [1_000_000, 1001])
 def test_nvls_allreduce_equals_sum_of_rank_buffers(tmp_path, P, fused):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
@@ -93,7 +96,9 @@ def test_nvls_allreduce_equals_sum_of_rank_buffers(tmp_path, P, fused):
         assert r["random_max_abs_diff_vs_nccl"] <= 1e-5 * r["random_scale"], r
         assert r["replicas_identical"], r
         assert not r["timed_out"], r
-        assert ("one launch" in r["collective"]) == (fused == "1"), r
+        assert ("one launch" in r["collective"]) == (fused != "0"), r
+        if fused in ("mc", "p2p"):
+            assert ("peer-to-peer" in r["collective"]) == (fused == "p2p"), r
     try:
         import json
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

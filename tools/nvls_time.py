@@ -36,8 +36,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for fused in ("1", "0"):
-        os.environ["SCGR_ALLREDUCE_FUSED"] = fused
+    for fused in ("1", "p2p", "0"):      # one launch (multicast shots), one launch (peer-to-peer shots), two launches
+        os.environ["SCGR_ALLREDUCE_FUSED"] = "0" if fused == "0" else "1"
+        os.environ["SCGR_NVLS_P2P"] = "1" if fused == "p2p" else "0"
         for sparse in ("1", "0"):
             os.environ["SCGR_ALLREDUCE_SPARSE"] = sparse
             buf = FlatGradBuffer(P, sh_coeffs=16, device=dev, symmetric=True)
