@@ -232,6 +232,7 @@ struct FusedArgs {
     uint32_t epoch;                          // first of the three barrier values of this call
     float4* peer[SCGR_NVLS_MAX_WORLD];       // peer-to-peer shots: rank q's mapping of the flat buffer (NULL: multicast shots)
     size_t rows_f4;                          // offset of the rows block inside the flat buffer, float4 units
+    int p2p_dense, p2p_rows;                 // which shot goes peer to peer (measured: both at 2 ranks, the dense one at 4)
 };
 
 constexpr long long SPIN_LIMIT = 20000000000ll;     // cycles (~10 s): far beyond any legitimate skew between ranks
@@ -271,16 +272,15 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 nvls_allreduce_fused_kernel(const FusedArgs a) {
     fused_barrier(a, a.epoch, false, 0u);                    // every replica has been written by its rank's backward
-    const bool p2p = a.peer[0] != nullptr;
     if (a.dense_count) {
-        if (!p2p) dense_shot<THREADS, 4>(a.mc, a.dense_first, a.dense_count);
+        if (!a.p2p_dense) dense_shot<THREADS, 4>(a.mc, a.dense_first, a.dense_count);
         else if (a.world == 2) dense_shot_p2p<THREADS, 2>(a.peer, a.dense_first, a.dense_count);
         else if (a.world == 4) dense_shot_p2p<THREADS, 4>(a.peer, a.dense_first, a.dense_count);
         else dense_shot_p2p<THREADS, 8>(a.peer, a.dense_first, a.dense_count);
     }
     fused_barrier(a, a.epoch + 1u, true, gridDim.x);         // the summed live counts are in place on every rank
     if (a.row_end > a.row_first) {
-        if (!p2p) rows_shot<THREADS, 4>(a.mc_rows, a.live, a.row_first, a.row_end, a.row_f4);
+        if (!a.p2p_rows) rows_shot<THREADS, 4>(a.mc_rows, a.live, a.row_first, a.row_end, a.row_f4);
         else if (a.world == 2) rows_shot_p2p<THREADS, 2>(a.peer, a.rows_f4, a.live, a.row_first, a.row_end, a.row_f4);
         else if (a.world == 4) rows_shot_p2p<THREADS, 4>(a.peer, a.rows_f4, a.live, a.row_first, a.row_end, a.row_f4);
         else rows_shot_p2p<THREADS, 8>(a.peer, a.rows_f4, a.live, a.row_first, a.row_end, a.row_f4);
@@ -374,6 +374,10 @@ void launch_nvls_allreduce_fused(const ScgrNvlsFused& f, const Launch& L) {
     if (f.peer_ptrs[0] && (f.world == 2 || f.world == 4 || f.world == 8)) {
         for (int q = 0; q < f.world; q++) a.peer[q] = reinterpret_cast<float4*>(f.peer_ptrs[q]);
         a.rows_f4 = f.multicast_rows ? (size_t)((char*)f.multicast_rows - (char*)f.multicast_ptr) / 16 : 0;
+        // tools/nvls_time.py on 8 x B200: peer-to-peer wins both shots at 2 ranks, the dense one only at 4, neither at 8
+        static const int force = getenv("SCGR_NVLS_P2P_SHOTS") ? atoi(getenv("SCGR_NVLS_P2P_SHOTS")) : -1;      // bit 0 dense, bit 1 rows
+        a.p2p_dense = force >= 0 ? (force & 1) : (f.world <= 4);
+        a.p2p_rows = force >= 0 ? ((force >> 1) & 1) : (f.world <= 2);
     }
     a.sync = f.sync_local;
     a.epoch = f.epoch;

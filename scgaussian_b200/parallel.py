@@ -38,7 +38,8 @@ import torch.distributed as dist
 
 class FlatGradBuffer:
     FLAG_WORDS = 64          # >= world; keeps the allocation a multiple of 256 bytes
-    P2P_MAX_WORLD = 2        # largest world for which the peer-to-peer shots are the default (measured, profiles/r02_scaling.md)
+    P2P_MAX_WORLD = 4        # largest world that hands the kernel the peer mappings (it goes peer to peer for both shots at 2
+                             # ranks, for the dense one at 4: measured, profiles/r02_scaling.md)
 
     def __init__(self, P: int, sh_coeffs: int = 16, use_sh: bool = True, use_cov: bool = False,
                  device="cuda", with_stats: bool = True, symmetric: Optional[bool] = None):
@@ -182,7 +183,7 @@ class FlatGradBuffer:
         w = int(self._symm.world_size)
         how = ", one launch with in-kernel barriers" if self._fused(w) else ""
         if self._fused(w) and self._p2p(w):
-            how += ", peer-to-peer loads / stores"
+            how += ", peer-to-peer loads / stores" + ("" if w <= 2 or os.environ.get("SCGR_NVLS_P2P") == "1" else " for the dense shot")
         return ("nvls two-shot kernels (libscgr): dense small blocks + row-sparse dL/dSH" if self._sparse() else
                 "nvls two-shot kernel (libscgr), dense") + how
 
@@ -193,6 +194,8 @@ class FlatGradBuffer:
         """Plain peer loads / stores instead of the multicast instructions: measured faster with few ranks (2: 0.19 ->
         ~0.1 ms for the small blocks).  SCGR_NVLS_P2P=auto|0|1."""
         mode = os.environ.get("SCGR_NVLS_P2P", "auto")
+        if mode == "1":
+            os.environ.setdefault("SCGR_NVLS_P2P_SHOTS", "3")      # forced: both shots, whatever the world size (read once by libscgr)
         return world in (2, 4, 8) and (mode == "1" or (mode == "auto" and world <= self.P2P_MAX_WORLD))
 
     def timed_out(self) -> bool:
