@@ -132,8 +132,12 @@ static AuxStream& aux_stream() {
 }
 
 // stage 1 proper (shared by scgr_forward_geometry and scgr_forward): P > 0
+// `early`: the R-independent part of stage 2 (empty ranges, zeroed onesweep words of the tile partition) when the caller
+// already holds a binning buffer: enqueued behind the preprocess, where the main stream otherwise idles until the depth
+// sort on the auxiliary stream is done (0.10 ms against 0.08 ms) -- not between the scan and the emission.
 static void enqueue_geometry_stage(const ScgrView* view, const ScgrGaussians* g, const GeometryLayout& G, int32_t* radii,
-                                   int64_t* status_mapped, const Launch& L) {
+                                   int64_t* status_mapped, const Launch& L, const BinningLayout* early = nullptr,
+                                   int64_t early_capacity = 0) {
     static const bool serial = getenv("SCGR_SERIAL_STAGE1") != nullptr;    // A/B switch: everything on the caller's stream
     if (serial) {
         launch_depth_sort(*view, *g, G, L);
@@ -146,8 +150,10 @@ static void enqueue_geometry_stage(const ScgrView* view, const ScgrGaussians* g,
         launch_depth_sort(*view, *g, G, La);               // aux:  sweep memset, depth keys + histograms, 4 radix passes
         cudaEventRecord(a.join, a.stream);
         launch_preprocess_forward(*view, *g, G, radii, L); // main: project, covariance, SH, tile counts
+        if (early) launch_binning_prologue(*view, *early, g->P, early_capacity, L);
         cudaStreamWaitEvent(L.stream, a.join, 0);
     }
+    if (early && serial) launch_binning_prologue(*view, *early, g->P, early_capacity, L);
     launch_scan_offsets(G, g->P, status_mapped, L);
 }
 
@@ -280,11 +286,12 @@ int scgr_forward(const ScgrView* view, const ScgrGaussians* g, void* geometry_sc
             if (!zero_copy) (void)cudaGetLastError();
             status_host[1] = 0;
             *(volatile int64_t*)status_host = kSentinel;
-            enqueue_geometry_stage(view, g, G, radii, zero_copy ? (int64_t*)mapped : nullptr, L);
-            if (binning_scratch) {   // R-independent part of stage 2: runs while the host waits for R
-                launch_binning_prologue(*view, carve_binning(binning_scratch, view->image_width, view->image_height, capacity),
-                                        g->P, capacity, L);
+            if (binning_scratch) {   // R-independent part of stage 2: enqueued inside stage 1, behind the preprocess
+                const BinningLayout Bearly = carve_binning(binning_scratch, view->image_width, view->image_height, capacity);
+                enqueue_geometry_stage(view, g, G, radii, zero_copy ? (int64_t*)mapped : nullptr, L, &Bearly, capacity);
                 prologue_done = true;
+            } else {
+                enqueue_geometry_stage(view, g, G, radii, zero_copy ? (int64_t*)mapped : nullptr, L);
             }
             if (zero_copy && binning_scratch) {
                 // Stage 2 is enqueued BEFORE R is known: its kernels read R from device memory and do nothing
