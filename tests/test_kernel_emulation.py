@@ -382,11 +382,17 @@ def _host_loss(emu_loss, img, gt, lam, upstream=None):
     return float(out3[0]), float(out3[1]), float(out3[2]), grad.numpy()
 
 
+# SCGR_LOSS_VARIANT: 0 = 32x32 tiles, 1 = streaming column strips (scgaussian_b200/csrc/loss.cu reads it on every launch)
+LOSS_VARIANTS = ["0", "1"]
+
+
+@pytest.mark.parametrize("variant", LOSS_VARIANTS)
 @pytest.mark.parametrize("name", ["a", "b", "c"])
-def test_photometric_kernels_on_host_match_reference_golden(emu_loss, name):
+def test_photometric_kernels_on_host_match_reference_golden(emu_loss, name, variant, monkeypatch):
     """reference train.py:160-161 with utils/loss_utils.py l1_loss / ssim: the vectors in tests/golden/loss_golden.npz were
     produced by the reference's own functions + autograd."""
     from tests import test_loss as TL
+    monkeypatch.setenv("SCGR_LOSS_VARIANT", variant)
     g = np.load(TL.GOLD)
     ll1, s, loss, g_loss = _host_loss(emu_loss, g[f"{name}_img"], g[f"{name}_gt"], 0.2)
     assert abs(ll1 - float(g[f"{name}_l1"])) < TL.TOL_VAL
@@ -399,9 +405,12 @@ def test_photometric_kernels_on_host_match_reference_golden(emu_loss, name):
     assert TL._rel(g_ssim, g[f"{name}_g_ssim"]) < TL.RTOL_GRAD and TL._rel(g_l1, g[f"{name}_g_l1"]) < 1e-6
 
 
-@pytest.mark.parametrize("shape", [(3, 1, 1), (3, 5, 7), (1, 16, 16), (3, 17, 33), (6, 40, 24), (2, 70, 131)])
-def test_photometric_kernels_on_host_match_oracle_f64(emu_loss, shape):
+@pytest.mark.parametrize("variant", LOSS_VARIANTS)
+@pytest.mark.parametrize("shape", [(3, 1, 1), (3, 5, 7), (1, 16, 16), (3, 17, 33), (6, 40, 24), (2, 70, 131), (1, 34, 117),
+                                   (2, 45, 116), (1, 100, 252)])
+def test_photometric_kernels_on_host_match_oracle_f64(emu_loss, shape, variant, monkeypatch):
     from tests import test_loss as TL
+    monkeypatch.setenv("SCGR_LOSS_VARIANT", variant)
     gen = torch.Generator().manual_seed(sum(shape))
     gt = torch.rand(*shape, generator=gen)
     img = (gt + 0.2 * torch.randn(*shape, generator=gen)).clamp(0, 1)

@@ -77,6 +77,14 @@ def dev():
     return torch.device("cuda", 0)
 
 
+@pytest.fixture(params=["tiles", "stream"])
+def variant(request, monkeypatch):
+    """The two kernel designs of scgaussian_b200/csrc/loss.cu (SCGR_LOSS_VARIANT, read on every launch): 32x32 tiles and
+    streaming column strips.  Every GPU test of the fused loss runs under both."""
+    monkeypatch.setenv("SCGR_LOSS_VARIANT", {"tiles": "0", "stream": "1"}[request.param])
+    return request.param
+
+
 def _fused_all(img, gt, dev, lam=0.2):
     from scgaussian_b200 import losses
     x = torch.tensor(img, dtype=torch.float32, device=dev, requires_grad=True)
@@ -92,7 +100,7 @@ def _fused_all(img, gt, dev, lam=0.2):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["a", "b", "c"])
-def test_fused_loss_matches_reference_golden(dev, name):
+def test_fused_loss_matches_reference_golden(dev, name, variant):
     g = np.load(GOLD)
     ll1, s, loss, g_loss, g_ssim, g_l1 = _fused_all(g[f"{name}_img"], g[f"{name}_gt"], dev)
     assert abs(ll1 - float(g[f"{name}_l1"])) < TOL_VAL
@@ -104,8 +112,9 @@ def test_fused_loss_matches_reference_golden(dev, name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(3, 1, 1), (3, 5, 7), (1, 16, 16), (3, 17, 33), (2, 3, 40, 24), (3, 378, 504)])
-def test_fused_loss_matches_oracle_f64(dev, shape):
+@pytest.mark.parametrize("shape", [(3, 1, 1), (3, 5, 7), (1, 16, 16), (3, 17, 33), (2, 3, 40, 24), (3, 378, 504), (1, 70, 131),
+                                   (2, 45, 116), (1, 100, 250)])
+def test_fused_loss_matches_oracle_f64(dev, shape, variant):
     g = torch.Generator().manual_seed(sum(shape))
     gt = torch.rand(*shape, generator=g)
     img = (gt + 0.2 * torch.randn(*shape, generator=g)).clamp(0, 1)
@@ -120,7 +129,7 @@ def test_fused_loss_matches_oracle_f64(dev, shape):
 
 
 @pytest.mark.gpu
-def test_fused_loss_full_size_properties(dev):
+def test_fused_loss_full_size_properties(dev, variant):
     """1080p (BASELINE config 3 image size): identities that need no oracle."""
     from scgaussian_b200 import losses
     g = torch.Generator().manual_seed(3)
@@ -145,3 +154,24 @@ def test_fused_loss_full_size_properties(dev):
     # no_grad forward works and matches
     with torch.no_grad():
         assert float(losses.photometric_loss(x, y, 0.2)) == float(loss)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(3, 1080, 1920), (3, 2160, 3840), (3, 1081, 1918)])
+def test_fused_loss_variants_agree_at_full_size(dev, shape, monkeypatch):
+    """The two kernel designs sum the same 121 products per moment in different orders: values to rounding of the mean,
+    gradients to 1e-5 of their scale, at the image sizes of BASELINE configs 3 and 4 and at one with ragged strips
+    (W % 4 != 0: the element-wise row path)."""
+    from scgaussian_b200 import losses
+    g = torch.Generator().manual_seed(shape[1])
+    y = torch.rand(*shape, generator=g).to(dev)
+    x = (y + 0.1 * torch.randn(*shape, generator=g).to(dev)).clamp(0, 1).requires_grad_(True)
+    out = {}
+    for v in ("0", "1"):
+        monkeypatch.setenv("SCGR_LOSS_VARIANT", v)
+        loss = losses.photometric_loss(x, y, 0.2)
+        gr, = torch.autograd.grad(loss, x)
+        out[v] = (float(loss), gr)
+    assert abs(out["0"][0] - out["1"][0]) < 2e-6
+    assert float((out["0"][1] - out["1"][1]).abs().max()) <= 1e-5 * float(out["0"][1].abs().max())
+    assert bool(torch.isfinite(out["1"][1]).all())
