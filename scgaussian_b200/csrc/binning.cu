@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK)
 scan_offsets_kernel(const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ order, int P,
                     uint32_t* __restrict__ offsets, int64_t* __restrict__ status, unsigned long long* __restrict__ state,
                     volatile int64_t* status_mapped) {
+    pdl_trigger();                  // lets the next kernel of the chain become resident early (common.cuh); it waits for this grid to finish
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_prefix;
@@ -201,6 +202,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                      const int64_t* __restrict__ n_dev, int64_t n_host, int64_t cap, int shift,
                      uint32_t mask, uint32_t* __restrict__ sweep, uint2* __restrict__ ranges) {
+    pdl_wait(); pdl_trigger();      // programmatic dependent launch (common.cuh): nothing is read or written before this
     static_assert(THREADS * ITEMS == RADIX_TILE, "tile size is part of the scratch layout");
     constexpr int WARPS = THREADS / 32;
     constexpr int PER_WARP = RADIX_TILE / WARPS;
@@ -386,7 +388,7 @@ void launch_onesweep_variant(uint32_t nb, const uint32_t* kin, const uint32_t* v
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    kern<<<nb, THREADS, smem, L.stream>>>(kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges);
+    chain(kern, dim3(nb), dim3(THREADS), smem, L)(kin, vin, kout, vout, n_dev, n_host, cap, shift, mask, sweep, ranges);
 }
 
 // variant 1: 256 threads x 16 items; 2: 512 x 8; 4: 1024 x 4 (all ballot ranking); 0: 256 x 16, 3: 512 x 8 with MATCH.ANY;
@@ -454,6 +456,7 @@ emit_instances_kernel(const uint32_t* __restrict__ order, const uint32_t* __rest
                       const Record* __restrict__ rec, int P, int grid_x, int64_t capacity,
                       int64_t* __restrict__ status, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                       uint32_t* __restrict__ sweep, size_t pass_words, const TilePasses tp) {
+    pdl_wait(); pdl_trigger();      // programmatic dependent launch (common.cuh): nothing is read or written before this
     __shared__ uint32_t s_hist[PASSES][RADIX_BINS];
     const int64_t R = status[0];
     if (R > capacity) {
@@ -683,7 +686,7 @@ void launch_emit_and_partition(const ScgrView& v, const GeometryLayout& G, const
     const size_t pw = sweep_pass_words(capacity);
     const uint32_t* order = G.sort_vals[0];   // 32-bit sort = 4 passes = even number of flips
     begin_kernel("emit_instances", L);
-#define SCGR_EMIT(N_) emit_instances_kernel<N_><<<(P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, L.stream>>>( \
+#define SCGR_EMIT(N_) chain(emit_instances_kernel<N_>, dim3((P + EMIT_THREADS - 1) / EMIT_THREADS), dim3(EMIT_THREADS), 0, L)( \
         order, G.offsets, G.rect, G.tile_mask, G.rec, P, gx, capacity, G.status, B.keys[0], B.vals[0], B.sweep, pw, tp)
     switch (tp.passes) {
         case 1: SCGR_EMIT(1); break;

@@ -29,6 +29,18 @@ static std::vector<ProfEntry> g_prof;
 static std::atomic<bool> g_prof_on{false};
 static std::atomic<long long> g_kernel_launches{0};
 
+// SCGR_PDL: programmatic dependent launch between the kernels of a stage (common.cuh).  Never inside a stream capture:
+// graph kernel nodes are already launched back to back by the device.
+#ifndef SCGR_HOST_EMULATION
+bool pdl_allowed(cudaStream_t stream) {
+    static const bool on = getenv("SCGR_PDL") ? atoi(getenv("SCGR_PDL")) != 0 : false;
+    if (!on) return false;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return st == cudaStreamCaptureStatusNone;
+}
+#endif
+
 void begin_kernel(const char* what, const Launch& L) {
     if (!g_prof_on.load(std::memory_order_relaxed)) return;
     ProfEntry e{what, nullptr, nullptr, true};

@@ -252,6 +252,63 @@ struct Launch {
     bool debug;
 };
 
+// ---- programmatic dependent launch (SCGR_PDL=1) ----
+// The kernels of a stage form a chain on one stream (scan -> emission -> partition passes -> render; prologue -> render
+// backward -> preprocess backward; depth keys -> radix passes).  Launched through chain(...) with the programmatic
+// stream-serialization attribute, a kernel's CTAs become resident while the tail of its predecessor is still running and
+// block in griddepcontrol.wait -- the FIRST statement of every chained kernel -- until the predecessor has completed and
+// its writes are visible: the grid launch latency and the kernel's own prologue leave the critical path, nothing else
+// changes (no chained kernel touches memory before the wait).  Every chained kernel also releases its own successor
+// at once (pdl_trigger): the successor can only take SM resources this grid no longer needs, since the trigger fires
+// when ALL of this grid's CTAs have started.  Without the attribute (switch off, a stream being captured into a graph, a
+// predecessor that is not a kernel) both instructions do nothing and the launch is an ordinary one.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifdef SCGR_HOST_EMULATION
+template <class... KA>
+struct ChainLaunch {
+    void (*kernel)(KA...);
+    dim3 grid;
+    unsigned threads;
+    template <class... A>
+    void operator()(A... args) const {
+        void (*k)(KA...) = kernel;
+        emu_launch(grid, threads, [=] { k(args...); });
+    }
+};
+template <class... KA>
+inline ChainLaunch<KA...> chain(void (*kernel)(KA...), dim3 grid, dim3 block, size_t, const Launch&) {
+    return ChainLaunch<KA...>{kernel, grid, block.x};
+}
+#else
+bool pdl_allowed(cudaStream_t stream);      // capi.cu: the switch, and the stream is not being captured
+template <class... KA>
+struct ChainLaunch {
+    void (*kernel)(KA...);
+    dim3 grid, block;
+    size_t smem;
+    cudaStream_t stream;
+    template <class... A>
+    void operator()(A&&... args) const {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr = {};
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = pdl_allowed(stream) ? 1u : 0u;
+        (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<A&&>(args)...);      // errors surface in check_launch
+    }
+};
+template <class... KA>
+inline ChainLaunch<KA...> chain(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, const Launch& L) {
+    return ChainLaunch<KA...>{kernel, grid, block, smem, L.stream};
+}
+#endif
+
 void launch_preprocess_forward(const ScgrView& v, const ScgrGaussians& g, const GeometryLayout& G,
                                int32_t* radii, const Launch& L);
 void launch_preprocess_backward(const ScgrView& v, const ScgrGaussians& g, const GeometryLayout& G,

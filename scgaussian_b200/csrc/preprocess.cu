@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(KEY_THREADS)
 depth_key_kernel(const float* __restrict__ means3D, const int P, const float* __restrict__ V,
                  uint32_t* __restrict__ depth_key, uint32_t* __restrict__ order_init,
                  uint32_t* __restrict__ sweep, const size_t pass_words) {
+    pdl_trigger();                  // lets the next kernel of the chain become resident early (common.cuh); it waits for this grid to finish
     __shared__ uint32_t s_hist[4][RADIX_BINS];
 #pragma unroll
     for (int p = 0; p < 4; p++) s_hist[p][threadIdx.x] = 0u;
@@ -517,6 +518,7 @@ template <bool SH_FAST, int MINB, bool ACC, bool SPLIT, int TMA>
 __global__ void __launch_bounds__(PB_T, MINB)
 preprocess_backward_kernel(const ScgrView v, const ScgrGaussians g, const Record* __restrict__ rec,
                            const ScreenGrad* __restrict__ sg, const ScgrGrads out) {
+    pdl_wait(); pdl_trigger();      // programmatic dependent launch (common.cuh): nothing is read or written before this
     __shared__ float4 s_sh[SH_FAST ? PB_T * SH_ROW_F4_PAD : 1];   // SH rows (then gradient rows) of one round, compact
     __shared__ float4 s_acc[PB_G][3];             // screen-space gradient sums of the live Gaussians
     __shared__ uint8_t s_live[PB_G];
@@ -1027,21 +1029,21 @@ void launch_preprocess_backward(const ScgrView& v, const ScgrGaussians& g, const
     const bool acc = out.accumulate != 0;
     static const int tma = getenv("SCGR_TMA_PREB") ? atoi(getenv("SCGR_TMA_PREB")) : 2;
     if (sh_split(g)) {
-        if (acc) preprocess_backward_kernel<true, 1, true, true, 0><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else preprocess_backward_kernel<true, 1, false, true, 0><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        if (acc) chain(preprocess_backward_kernel<true, 1, true, true, 0>, dim3(blocks), dim3(PB_T), 0, L)(v, g, G.rec, G.screen_grad, out);
+        else chain(preprocess_backward_kernel<true, 1, false, true, 0>, dim3(blocks), dim3(PB_T), 0, L)(v, g, G.rec, G.screen_grad, out);
     } else if (sh_fast_ok(g, out.dL_dshs)) {
-        if (acc && tma == 2) preprocess_backward_kernel<true, 1, true, false, 2><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (acc && tma) preprocess_backward_kernel<true, 1, true, false, 1><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (acc) preprocess_backward_kernel<true, 1, true, false, 0><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (minb == 12) preprocess_backward_kernel<true, 12, false, false, 0><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (minb == 10) preprocess_backward_kernel<true, 10, false, false, 0><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (tma == 2) preprocess_backward_kernel<true, 1, false, false, 2><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else if (tma) preprocess_backward_kernel<true, 1, false, false, 1><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
-        else preprocess_backward_kernel<true, 1, false, false, 0><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        if (acc && tma == 2) chain(preprocess_backward_kernel<true, 1, true, false, 2>, dim3(blocks), dim3(PB_T), 0, L)(v, g, G.rec, G.screen_grad, out);
+        else if (acc && tma) chain(preprocess_backward_kernel<true, 1, true, false, 1>, dim3(blocks), dim3(PB_T), 0, L)(v, g, G.rec, G.screen_grad, out);
+        else if (acc) chain(preprocess_backward_kernel<true, 1, true, false, 0>, dim3(blocks), dim3(PB_T), 0, L)(v, g, G.rec, G.screen_grad, out);
+        else if (minb == 12) chain(preprocess_backward_kernel<true, 12, false, false, 0>, dim3(blocks), dim3(PB_T), 0, L)(v, g, G.rec, G.screen_grad, out);
+        else if (minb == 10) chain(preprocess_backward_kernel<true, 10, false, false, 0>, dim3(blocks), dim3(PB_T), 0, L)(v, g, G.rec, G.screen_grad, out);
+        else if (tma == 2) chain(preprocess_backward_kernel<true, 1, false, false, 2>, dim3(blocks), dim3(PB_T), 0, L)(v, g, G.rec, G.screen_grad, out);
+        else if (tma) chain(preprocess_backward_kernel<true, 1, false, false, 1>, dim3(blocks), dim3(PB_T), 0, L)(v, g, G.rec, G.screen_grad, out);
+        else chain(preprocess_backward_kernel<true, 1, false, false, 0>, dim3(blocks), dim3(PB_T), 0, L)(v, g, G.rec, G.screen_grad, out);
     } else if (acc) {
-        preprocess_backward_kernel<false, 1, true, false, 0><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        chain(preprocess_backward_kernel<false, 1, true, false, 0>, dim3(blocks), dim3(PB_T), 0, L)(v, g, G.rec, G.screen_grad, out);
     } else {
-        preprocess_backward_kernel<false, 1, false, false, 0><<<blocks, PB_T, 0, L.stream>>>(v, g, G.rec, G.screen_grad, out);
+        chain(preprocess_backward_kernel<false, 1, false, false, 0>, dim3(blocks), dim3(PB_T), 0, L)(v, g, G.rec, G.screen_grad, out);
     }
     check_launch("preprocess_backward", L);
 }

@@ -489,6 +489,7 @@ render_forward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __rest
                       const float* __restrict__ bg, const int64_t* __restrict__ status, int64_t capacity,
                       float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha,
                       uint32_t* __restrict__ n_contrib, float* __restrict__ final_T, uint4* __restrict__ tile_todo) {
+    pdl_wait(); pdl_trigger();      // programmatic dependent launch (common.cuh): nothing is read or written before this
     constexpr int TMA = MODE == 1 ? 1 : (MODE == 3 ? 2 : 0);
     __shared__ __align__(16) float4 s_rec[MODE == 2 ? 1 : 2][MODE == 2 ? 32 * DUP_F4 : 96];   // record staging (MODE 2: packed-blend layout)
     __shared__ __align__(8) unsigned long long s_bar[2];
@@ -984,6 +985,7 @@ render_backward_kernel(const WorkSplit ws, const int tiles_x, const uint2* __res
                        const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
                        const float* __restrict__ dL_dalpha, ScreenGrad* __restrict__ screen_grad,
                        const uint32_t* __restrict__ tile_order) {
+    pdl_wait(); pdl_trigger();      // programmatic dependent launch (common.cuh): nothing is read or written before this
     __shared__ __align__(16) float4 s_rec[2][96];        // 2 stages x 32 records x {q0, q1, q2}
     __shared__ __align__(16) float4 s_dup[PK ? 32 * DUP_F4 : 1];  // packed blend: the batch's records in its layout (stage_dup)
     __shared__ uint32_t s_id[2][32];
@@ -1033,6 +1035,7 @@ constexpr int ZERO_F4_PER_CTA = 4096;      // 64 KB of zeros per CTA
 __global__ void __launch_bounds__(ORDER_THREADS)
 backward_prologue_kernel(const uint4* __restrict__ tile_todo, const int n_tiles, uint32_t* __restrict__ tile_order,
                          float4* __restrict__ zero_dst, const size_t zero_f4) {
+    pdl_wait(); pdl_trigger();      // programmatic dependent launch (common.cuh): nothing is read or written before this
     if (blockIdx.x > 0) {
         const size_t base = (size_t)(blockIdx.x - 1) * ZERO_F4_PER_CTA;
 #pragma unroll
@@ -1140,7 +1143,7 @@ void launch_render_forward(const ScgrView& v, const GeometryLayout& G, const Bin
     static const int tma = env_int("SCGR_FWD_PACKED", 0) ? 2 : env_int("SCGR_TMA_FWD", env_int("SCGR_TMA", 3));
     const WorkSplit ws = make_split(tx * ty, "SCGR_FWD_SPLIT", 10, 5);
     begin_kernel("render_forward", L);
-#define SCGR_FWD(M_, T_) render_forward_kernel<M_, T_><<<ws.items(), 32, 0, L.stream>>>(ws, tx, B.ranges, point_list, G.rec, \
+#define SCGR_FWD(M_, T_) chain(render_forward_kernel<M_, T_>, dim3(ws.items()), dim3(32), 0, L)(ws, tx, B.ranges, point_list, G.rec, \
         v.image_width, v.image_height, v.bg, G.status, capacity, out_color, out_depth, out_alpha, I.n_contrib, I.final_T, \
         I.tile_todo)
     if (tma == 0) { if (minb == 20) SCGR_FWD(20, 0); else if (minb == 24) SCGR_FWD(24, 0); else SCGR_FWD(1, 0); }
@@ -1185,12 +1188,12 @@ void launch_render_backward(const ScgrView& v, const GeometryLayout& G, const Bi
         const size_t zero_f4 = (size_t)(P > 0 ? P : 0) * (sizeof(ScreenGrad) / sizeof(float4));
         const unsigned zero_ctas = (unsigned)((zero_f4 + ZERO_F4_PER_CTA - 1) / ZERO_F4_PER_CTA);
         begin_kernel("backward_prologue", L);
-        backward_prologue_kernel<<<1 + zero_ctas, ORDER_THREADS, 0, L.stream>>>(
+        chain(backward_prologue_kernel, dim3(1 + zero_ctas), dim3(ORDER_THREADS), 0, L)(
             I.tile_todo, tx * ty, I.tile_order, reinterpret_cast<float4*>(G.screen_grad), zero_f4);
         check_launch("backward_prologue", L);
     }
     begin_kernel("render_backward", L);
-#define SCGR_BWD(M_, T_, P_) render_backward_kernel<M_, T_, P_><<<ws.items(), 32, 0, L.stream>>>(ws, tx, B.ranges, point_list, \
+#define SCGR_BWD(M_, T_, P_) chain(render_backward_kernel<M_, T_, P_>, dim3(ws.items()), dim3(32), 0, L)(ws, tx, B.ranges, point_list, \
         G.rec, v.image_width, v.image_height, v.bg, G.status, capacity, I.n_contrib, I.final_T, dL_dcolor, dL_ddepth, \
         dL_dalpha, G.screen_grad, I.tile_order)
     static const int packed = env_int("SCGR_BWD_PACKED", 0);      // packed-fp32 blend: measured slower, off by default

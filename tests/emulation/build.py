@@ -146,6 +146,8 @@ _TMA_PTX = {
     "mbar_expect_tx": "emu_mbar_update(bar, -1, (long long)bytes);",
     "bulk_g2s": "std::memcpy(dst, src, bytes); emu_mbar_update(bar, 0, -(long long)bytes);",
     "mbar_wait": "emu_mbar_wait(bar, parity);",
+    "pdl_wait": "",                # programmatic dependent launch: kernels run one after the other here
+    "pdl_trigger": "",
 }
 
 
@@ -160,7 +162,7 @@ def build_preprocess() -> str:
     _common_host()
     body = open(srcs[0]).read().replace('#include "common.cuh"', "")
     with open(os.path.join(OUT_DIR, "preprocess_body.inc"), "w") as f:
-        f.write(_rewrite_launches(body, 8))
+        f.write(_rewrite_launches(body, 5))
     body = open(srcs[1]).read().replace('#include "common.cuh"', "")
     for pat, rep in _VOLATILE:
         body, n = re.subn(pat, rep, body)
@@ -169,7 +171,7 @@ def build_preprocess() -> str:
     body, n = re.subn(r"extern __shared__ __align__\(16\) uint32_t (\w+)\[\];", r"uint32_t* \1 = reinterpret_cast<uint32_t*>(g_dyn_smem);", body)
     assert n == 1, "binning.cu: expected one dynamic shared-memory array"
     with open(os.path.join(OUT_DIR, "binning_body.inc"), "w") as f:
-        f.write(_rewrite_launches(body, 4))
+        f.write(_rewrite_launches(body, 2))
     body = open(srcs[2]).read().replace('#include "common.cuh"', "")
     for name, new in _RENDER_PTX.items():
         body = _replace_fn_body(body, name, new)
@@ -180,7 +182,7 @@ def build_preprocess() -> str:
     body = body.replace("int env_int(const char* name, int dflt) {", "int env_int_render(const char* name, int dflt) {").replace(
         "env_int(", "env_int_render(").replace("int env_int_render_render(", "int env_int_render(")
     with open(os.path.join(OUT_DIR, "render_body.inc"), "w") as f:
-        f.write(_rewrite_launches(body, 3))
+        f.write(_rewrite_launches(body, 0))
     _compile(LIB_PRE, "emu_preprocess.cpp")
     return LIB_PRE
 

@@ -7,6 +7,7 @@
 // the same oracle and golden vectors as the GPU tests.  What it cannot check: warp intrinsics (none are used by
 // these kernels beyond full-mask votes / shuffles / match / reduce), memory-model subtleties, performance.
 #pragma once
+#define SCGR_HOST_EMULATION 1      // common.cuh: chain() launches through emu_launch, griddepcontrol is a no-op
 #include <algorithm>
 #include <barrier>
 #include <cmath>
