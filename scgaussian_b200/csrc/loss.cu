@@ -690,7 +690,8 @@ static StreamGrid stream_grid(int C, int H, int W) {
     }();
     const int strips = (W + SWO - 1) / SWO;
     const int64_t columns = (int64_t)C * strips;
-    const int want = (int)std::max<int64_t>(1, (int64_t)sm_count * SOCC / columns);     // bands that fit in one wave
+    int want = (int)std::max<int64_t>(1, (int64_t)sm_count * SOCC / columns);           // bands that fit in one wave
+    if (const char* e = getenv("SCGR_LOSS_BANDS")) want = std::max(1, atoi(e));           // tuning switch
     const int batches = std::max(3, (H + want * SRB - 1) / (want * SRB));
     StreamGrid g;
     g.band = batches * SRB;
