@@ -370,8 +370,9 @@ __device__ __forceinline__ SsimPoint ssim_point(const float mu1, const float mu2
     const float s12 = e12 - mu12;
     const float A1 = 2.f * mu12 + SSIM_C1, A2 = 2.f * s12 + SSIM_C2;
     const float B1 = mu1_sq + mu2_sq + SSIM_C1, B2 = (ess - mu1_sq - mu2_sq) + SSIM_C2;
-    const float iB1 = __frcp_rn(B1), iB2 = __frcp_rn(B2);
-    const float inv = iB1 * iB2;
+    // one IEEE reciprocal instead of two: B1 B2 >= C1 C2 = 9e-8 up to rounding, far from underflow
+    const float inv = __frcp_rn(B1 * B2);
+    const float iB1 = inv * B2, iB2 = inv * B1;
     SsimPoint o;
     o.ss = A1 * A2 * inv;
     o.d_mu = 2.f * (mu2 * (A2 - A1) * inv + mu1 * o.ss * (iB2 - iB1));
@@ -479,6 +480,12 @@ photometric_forward_stream_kernel(const float* __restrict__ img, const float* __
             const int r = it / SG, g4 = (it - r * SG) * LPT;
             const int py = ya + SRB * (b - 1) + r, px = x0 + g4;
             if (py >= yb || px >= W) continue;
+            // the centre pixels come from L2 (the rows left L1 a batch ago): requested before the filter, used after it
+            const int n_valid = min(LPT, W - px);
+            const size_t off = (size_t)py * W + px;
+            float xs[LPT], ys[LPT];
+            load4(ip + off, n_valid, vec != 0, xs);
+            load4(gp + off, n_valid, vec != 0, ys);
             float o[4][LPT];
 #pragma unroll
             for (int m = 0; m < 4; m++) {
@@ -492,11 +499,6 @@ photometric_forward_stream_kernel(const float* __restrict__ img, const float* __
                     o[m][j] = a;
                 }
             }
-            const int n_valid = min(LPT, W - px);
-            const size_t off = (size_t)py * W + px;
-            float xs[LPT], ys[LPT];
-            load4(ip + off, n_valid, vec != 0, xs);
-            load4(gp + off, n_valid, vec != 0, ys);
             float g_mu[LPT], g_e11[LPT], g_e12[LPT];
 #pragma unroll
             for (int j = 0; j < LPT; j++) {
@@ -617,6 +619,11 @@ photometric_backward_stream_kernel(const float* __restrict__ img, const float* _
             const int r = it / SG, g4 = (it - r * SG) * LPT;
             const int py = ya + SRB * (b - 1) + r, px = x0 + g4;
             if (py >= yb || px >= W) continue;
+            const int n_valid = min(LPT, W - px);
+            const size_t off = plane + (size_t)py * W + px;
+            float xs[LPT], ys[LPT], out[LPT];
+            load4(img + off, n_valid, vec != 0, xs);      // requested before the filter, used after it
+            load4(gt + off, n_valid, vec != 0, ys);
             float o[3][LPT];
 #pragma unroll
             for (int m = 0; m < 3; m++) {
@@ -630,11 +637,6 @@ photometric_backward_stream_kernel(const float* __restrict__ img, const float* _
                     o[m][j] = a;
                 }
             }
-            const int n_valid = min(LPT, W - px);
-            const size_t off = plane + (size_t)py * W + px;
-            float xs[LPT], ys[LPT], out[LPT];
-            load4(img + off, n_valid, vec != 0, xs);
-            load4(gt + off, n_valid, vec != 0, ys);
 #pragma unroll
             for (int j = 0; j < LPT; j++) {
                 const float diff = xs[j] - ys[j];
@@ -692,17 +694,21 @@ static StreamGrid stream_grid(int C, int H, int W) {
     const int64_t columns = (int64_t)C * strips;
     int want = (int)std::max<int64_t>(1, (int64_t)sm_count * SOCC / columns);           // bands that fit in one wave
     if (const char* e = getenv("SCGR_LOSS_BANDS")) want = std::max(1, atoi(e));           // tuning switch
-    const int batches = std::max(3, (H + want * SRB - 1) / (want * SRB));
+    // measured on B200: one full wave (1080p: 11 bands of 99 rows) and several waves of 99-row bands (4K: 22 bands) beat
+    // everything in between (1.1 - 1.4 waves: tail) and taller bands (fewer CTAs than slots: idle SMs)
+    const int batches = std::min(9, std::max(3, (H + want * SRB - 1) / (want * SRB)));
     StreamGrid g;
     g.band = batches * SRB;
     g.grid = dim3(strips, (H + g.band - 1) / g.band, C);
     return g;
 }
 
-// 0: 32x32 tiles; 1: streaming column strips.  Read on every launch (tests switch it between calls).
+// 1 (default): streaming column strips; 0: 32x32 tiles.  Read on every launch (tests switch it between calls).
+// B200, 1080p, end-to-end step of bench.py: 1.351 -> 1.291 ms with the streaming kernels (4K: forward 352 -> 235 us,
+// backward 294 -> 169 us).
 static int loss_variant() {
     const char* e = getenv("SCGR_LOSS_VARIANT");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : 1;
 }
 static bool rows_vectorisable(int W, const void* a, const void* b, const void* c) {
     return W % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;

@@ -382,7 +382,7 @@ def _host_loss(emu_loss, img, gt, lam, upstream=None):
     return float(out3[0]), float(out3[1]), float(out3[2]), grad.numpy()
 
 
-# SCGR_LOSS_VARIANT: 0 = 32x32 tiles, 1 = streaming column strips (scgaussian_b200/csrc/loss.cu reads it on every launch)
+# SCGR_LOSS_VARIANT: 0 = 32x32 tiles, 1 = streaming column strips, the default (scgaussian_b200/csrc/loss.cu reads it on every launch)
 LOSS_VARIANTS = ["0", "1"]
 
 
