@@ -614,16 +614,31 @@ photometric_backward_stream_kernel(const float* __restrict__ img, const float* _
         }
         if (b < nb) fetch(b + 1);
         if (b == 0) continue;
+        // The centre pixels of an item come from DRAM (nothing else in this kernel reads the images): those of the thread's
+        // first item are requested before the barrier, those of every further item before the previous item is filtered.
+        float xs[LPT] = {0.f, 0.f, 0.f, 0.f}, ys[LPT] = {0.f, 0.f, 0.f, 0.f};
+        auto centre = [&](const int it) {
+            const int r = it / SG, g4 = (it - r * SG) * LPT;
+            const int py = ya + SRB * (b - 1) + r, px = x0 + g4;
+            if (it < SRB * SG && py < yb && px < W) {
+                const size_t off = plane + (size_t)py * W + px;
+                load4(img + off, min(LPT, W - px), vec != 0, xs);
+                load4(gt + off, min(LPT, W - px), vec != 0, ys);
+            }
+        };
+        centre(tid);
         __syncthreads();
         for (int it = tid; it < SRB * SG; it += ST) {
             const int r = it / SG, g4 = (it - r * SG) * LPT;
             const int py = ya + SRB * (b - 1) + r, px = x0 + g4;
+            float xc[LPT], yc[LPT];
+#pragma unroll
+            for (int j = 0; j < LPT; j++) { xc[j] = xs[j]; yc[j] = ys[j]; }
+            centre(it + ST);
             if (py >= yb || px >= W) continue;
             const int n_valid = min(LPT, W - px);
             const size_t off = plane + (size_t)py * W + px;
-            float xs[LPT], ys[LPT], out[LPT];
-            load4(img + off, n_valid, vec != 0, xs);      // requested before the filter, used after it
-            load4(gt + off, n_valid, vec != 0, ys);
+            float out[LPT];
             float o[3][LPT];
 #pragma unroll
             for (int m = 0; m < 3; m++) {
@@ -639,9 +654,9 @@ photometric_backward_stream_kernel(const float* __restrict__ img, const float* _
             }
 #pragma unroll
             for (int j = 0; j < LPT; j++) {
-                const float diff = xs[j] - ys[j];
+                const float diff = xc[j] - yc[j];
                 const float sgn = (diff > 0.f ? 1.f : 0.f) - (diff < 0.f ? 1.f : 0.f);   // d|u|/du, 0 at 0 (torch.abs)
-                out[j] = up * (w_ssim * (o[0][j] + 2.f * xs[j] * o[1][j] + ys[j] * o[2][j]) + w_l1 * sgn);
+                out[j] = up * (w_ssim * (o[0][j] + 2.f * xc[j] * o[1][j] + yc[j] * o[2][j]) + w_l1 * sgn);
             }
             store4(dL_dimg + off, n_valid, vec != 0, out);
         }
