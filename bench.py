@@ -863,7 +863,9 @@ def main():
                    "views_per_step": world, "parallelism": f"view-sharded dp{world}",
                    "collective": f"1 all-reduce of the flat gradient buffer per step ({wl.flat.collective if wl.flat is not None else 'nvls/nccl'})" if world > 1 else "none (1 GPU)",
                    "grad_allreduce_bytes": (P_GAUSS * 61 * 4) if world > 1 else 0,
-                   "l2": "no explicit flush: one step streams >1 GB (inputs 236 MB + gradients 244 MB + scratch) through the 126 MB L2, and the camera changes every step"},
+                   "l2": "no explicit flush: one step streams >1 GB (inputs 236 MB + gradients 244 MB + scratch) through the 126 MB L2, and the camera changes every step",
+                   "launch": "kernels of a stage chained by programmatic dependent launch (SCGR_PDL=%s)" % os.environ.get("SCGR_PDL", "1"),
+                   "loss_kernels": "streaming column strips" if os.environ.get("SCGR_LOSS_VARIANT", "1") == "1" else "32x32 tiles"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "roofline_issue": roof_issue,
         "kernels": kernels, "batch8": batch8, "config4": config4, "allreduce_check": allreduce_check,
         "config2": config2, "gpu_standin_baseline": standin, "cpu_baseline": cpu, "train_step": train_step,
