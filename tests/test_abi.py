@@ -185,3 +185,29 @@ def test_product_never_imports_the_oracle():
                 assert "oracle" not in txt.lower().replace("# no oracle", ""), f"{f} mentions the oracle"
     txt = open(os.path.join(ROOT, "diff_gaussian_rasterization", "__init__.py")).read()
     assert "oracle" not in txt
+
+
+def test_library_is_sm_100a_code_with_the_instructions_the_design_names():
+    """DESIGN.md names the hardware paths of the kernels; this reads them back from the SASS of the shipped library: built for
+    sm_100a only, TMA bulk copies + mbarrier waits (UBLKCP / SYNCS), cp.async staging (LDGSTS), multimem loads of the NVLS
+    collective (LDGMC), fp32 reductions to global memory (REDG), programmatic dependent launch (ACQBULK = griddepcontrol.wait,
+    PREEXIT = griddepcontrol.launch_dependents) -- and no kernel of a library (CUB / cuBLAS / Triton) inside it."""
+    import shutil
+    import subprocess
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([tool, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    archs = set(re.findall(r"arch = (sm_\w+)", sass))
+    assert archs == {"sm_100a"}, archs
+    for mnemonic, at_least in (("UBLKCP", 10), ("SYNCS", 10), ("LDGSTS", 10), ("LDGMC", 4), ("REDG.E.ADD.F32", 10),
+                               ("ACQBULK", 20), ("PREEXIT", 20)):
+        assert sass.count(mnemonic) >= at_least, (mnemonic, sass.count(mnemonic))
+    kernels = re.findall(r"Function : (\S+)", sass)
+    assert len(kernels) > 50
+    foreign = [k for k in kernels if "scgr" not in k]
+    assert not foreign, foreign[:5]
+    # every kernel launched through chain() starts by waiting for its predecessor: one ACQBULK per instantiation
+    chained = [k for k in kernels if re.search(r"onesweep_pass_kernel|emit_instances_kernel|render_forward_kernel|render_backward_kernel|"
+                                               r"backward_prologue_kernel|preprocess_backward_kernel", k)]
+    assert sass.count("ACQBULK") >= len(chained) > 20
