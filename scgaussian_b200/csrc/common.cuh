@@ -371,7 +371,7 @@ void launch_masked_mean_forward(const float* values, const uint8_t* mask, size_t
 void launch_masked_mean_backward(const uint8_t* mask, size_t n, const float* out2, const float* upstream, float* dL_dvalues,
                                  const Launch& L);
 
-// Every kernel launch is bracketed:  begin_kernel(name, L); kernel<<<...>>>(...); check_launch(name, L);
+// Every kernel launch is bracketed:  begin_kernel(name, L); kernel<<<...>>>(...) or chain(kernel, ...)(...); check_launch(name, L);
 // begin_kernel records a start event when profiling is on (scgr_profile_enable); check_launch
 // counts the launch, records the stop event, and turns CUDA errors into std::runtime_error
 // (synchronising first when the view's `debug` flag is set, like the reference's CHECK_CUDA).

@@ -7,6 +7,10 @@
 // C2 = 0.03^2, mean over every element.  The 2-D window is the outer product of the 1-D one (:52), so
 // the five windowed moments E[x], E[y], E[x^2], E[y^2], E[xy] are computed separably.
 //
+// Two kernel designs compute the same thing: the streaming column-strip kernels further down (the default,
+// SCGR_LOSS_VARIANT=1: 56 / 49 us at 1080p on B200) and the round-1 tile kernels described here (SCGR_LOSS_VARIANT=0:
+// 88 / 78 us), kept as the measured alternative and as a second implementation for the tests.
+//
 // Forward (one kernel): a CTA owns a 32x32 pixel tile of one channel; both images are staged with a
 // 5-pixel halo in shared memory (42x42), filtered horizontally (5 moments x 42 rows x 32 columns), then
 // vertically; each thread produces 4 adjacent outputs per pass from 14 loaded values (register blocking:
@@ -19,7 +23,7 @@
 // (G symmetric, zero padding = sum over valid pixels), i.e. three more separable filters of the
 // stored derivative maps, plus the L1 term sign(x - y); everything scaled by the weights of the two
 // means and by the upstream scalar read from device memory (no host synchronisation).
-// HBM-bound streaming work on fp32: no tensor cores.
+// Streaming fp32 work bounded by instruction issue (the separable 11-tap filter costs 88 / 66 FMA per pixel): no tensor cores.
 #include <algorithm>
 #include <climits>
 #include <cmath>
